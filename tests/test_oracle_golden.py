@@ -1,0 +1,118 @@
+"""The oracle's `literal` restatements must reproduce, bit for bit, the outputs the UNMODIFIED
+reference produced (tests/golden/*.pt, written by oracle/make_golden.py)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import bf16_ref, int8_ref, jvp_ref
+from oracle.baseline import baseline_pytorch_attention
+
+torch.set_num_threads(1)   # same fp32 summation order as the fixture generator
+
+
+def _fixtures(golden_dir, prefix):
+    fs = sorted(glob.glob(os.path.join(golden_dir, prefix + "*.pt")))
+    assert fs, "golden fixtures missing"
+    return fs
+
+
+def test_int8_fwd_bwd_literal_matches_reference(golden_dir):
+    for f in _fixtures(golden_dir, "int8_"):
+        fx = torch.load(f)
+        out = int8_ref.int8_fwd(fx["q"], fx["k"], fx["v"], fx["Bq"], fx["Bkv"], per_head=False)
+        for i, (a, b) in enumerate(zip(fx["fwd"], out[:8])):
+            assert torch.equal(a, b), (f, i)
+        if "bwd" in fx:
+            bw = int8_ref.int8_bwd_literal(fx["dO"], out[2], out[5], out[3], fx["k_mean_bhk"], out[6],
+                                           out[4], out[7], out[0], out[1], fx["Bq"], fx["Bkv"])
+            for i, (a, b) in enumerate(zip(fx["bwd"], bw)):
+                assert torch.equal(a, b), (f, "bwd", i)
+
+
+def test_bf16_fwd_bwd_literal_matches_reference(golden_dir):
+    for f in _fixtures(golden_dir, "bf16_"):
+        fx = torch.load(f)
+        O, lse = bf16_ref.bf16_fwd(fx["q"], fx["k"], fx["v"], fx["causal"], tile_k=fx["tile_k"], mode="literal")
+        assert torch.equal(O, fx["O"]) and torch.equal(lse, fx["lse"]), f
+        g = bf16_ref.bf16_bwd(fx["q"], fx["k"], fx["v"], O, lse, fx["causal"], fx["dO"], mode="literal")
+        for a, b in zip(g, (fx["dq"], fx["dk"], fx["dv"])):
+            assert torch.equal(a, b), f
+
+
+def test_jvp_literal_matches_reference(golden_dir):
+    for f in _fixtures(golden_dir, "jvp_"):
+        fx = torch.load(f)
+        O, tO, lse = jvp_ref.jvp_fwd(fx["q"], fx["k"], fx["v"], fx["tq"], fx["tk"], fx["tv"], tile_k=16)
+        assert torch.equal(O, fx["O"]) and torch.equal(tO, fx["tO"]) and torch.equal(lse, fx["lse"]), f
+
+
+def test_jvp_matches_torch_func_jvp():
+    g = torch.Generator().manual_seed(5)
+    q, k, v, tq, tk, tv = [torch.randn(1, 2, 96, 64, generator=g) for _ in range(6)]
+    O, tO, _ = jvp_ref.jvp_fwd(q, k, v, tq, tk, tv, tile_k=32)
+    Ob, tOb = torch.func.jvp(lambda a, b, c: baseline_pytorch_attention(a, b, c), (q, k, v), (tq, tk, tv))
+    assert (O - Ob).abs().max() < 1e-5 and (tO - tOb).abs().max() < 1e-4
+
+
+def test_int8_per_head_equals_literal_on_single_head_view():
+    """LEDGER I-2: the literal flattened result is the per-head kernel on x.view(1,1,B*H*S,D), and
+    the quantised tensors/scales are identical in both readings when S % Bq == S % Bkv == 0."""
+    g = torch.Generator().manual_seed(6)
+    q, k, v = [torch.randn(2, 2, 128, 64, generator=g).half() for _ in range(3)]
+    lit = int8_ref.int8_fwd(q, k, v, 32, 32, per_head=False)
+    ph = int8_ref.int8_fwd(q.view(1, 1, 512, 64), k.view(1, 1, 512, 64), v.view(1, 1, 512, 64), 32, 32, per_head=True)
+    assert torch.equal(lit[0].view(-1), ph[0].view(-1)) and torch.equal(lit[1], ph[1])
+    per = int8_ref.int8_fwd(q, k, v, 32, 32, per_head=True)
+    for i in range(2, 8):
+        assert torch.equal(per[i], lit[i])
+    assert not torch.equal(per[0], lit[0])
+
+
+def test_quant_block_edge_cases():
+    x = torch.zeros(64, 64, dtype=torch.float16)
+    x[32:] = torch.randn(32, 64).half()
+    x[40, 3] = 60000.0           # near fp16 max
+    qv, s = int8_ref.quant_block(x, 32)
+    assert s[0] == 0 and (qv[:32] == 0).all()            # LEDGER I-4: zero block -> 0 / scale 0
+    assert qv[40, 3] == 127 or qv[40, 3] == 126          # trunc of x/(x/127)
+    assert qv.abs().max() <= 127
+    # ragged tail block (hl.tile clamps the last tile)
+    y = torch.randn(80, 16, generator=torch.Generator().manual_seed(1)).half()
+    qr, sr = int8_ref.quant_block(y, 32)
+    assert sr.numel() == 3 and torch.equal(qr[:64], int8_ref.quant_block(y[:64], 32)[0])
+    # subnormal fp16 scales must not flush to zero (amax < 7.8e-3)
+    z = (torch.randn(32, 64) * 1e-3).half()
+    qz, sz = int8_ref.quant_block(z, 32)
+    assert 0 < float(sz[0]) < 6.2e-5 and qz.abs().max() >= 126
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_bf16_contract_close_to_fp32_math(causal):
+    g = torch.Generator().manual_seed(7)
+    q, k, v, dO = [torch.randn(1, 2, 256, 128, generator=g) for _ in range(4)]
+    q, k, v = q.half(), k.half(), v.bfloat16()
+    O, lse = bf16_ref.bf16_fwd(q, k, v, causal, tile_k=128, mode="contract")
+    Ob = baseline_pytorch_attention(q.float(), k.float(), v.float(), 128, causal)
+    assert (O - Ob).abs().max() < 3e-2          # bf16 P: same class as the reference's 915/18M @1e-2
+    qf, kf, vf = [t.float().requires_grad_() for t in (q, k, v)]
+    baseline_pytorch_attention(qf, kf, vf, 128, causal).backward(dO)
+    gq, gk, gv = bf16_ref.bf16_bwd(q, k, v, O, lse, causal, dO, mode="contract")
+    for a, b in zip((gq, gk, gv), (qf, kf, vf)):
+        assert (a - b.grad).norm() / b.grad.norm() < 1e-2
+
+
+def test_int8_contract_bwd_close_to_autograd():
+    g = torch.Generator().manual_seed(8)
+    q, k, v, dO = [torch.randn(1, 2, 256, 64, generator=g).half() for _ in range(4)]
+    k = (k.float() + 2.0).half()                         # K offset: exercises smoothing
+    so = int8_ref.sage_forward(q, k, v, 128, 128)
+    Ob = baseline_pytorch_attention(q.float(), k.float(), v.float(), 64, False)
+    assert (so[0].float() - Ob).abs().max() < 8e-2
+    qf, kf, vf = [t.float().requires_grad_() for t in (q, k, v)]
+    baseline_pytorch_attention(qf, kf, vf, 64, False).backward(dO.float())
+    gr = int8_ref.int8_bwd_contract(dO, so[3], so[6], so[4], so[2], so[7], so[5], so[8], so[0], so[1], 128, 128)
+    for a, b in zip(gr, (qf, kf, vf)):
+        cos = torch.nn.functional.cosine_similarity(a.float().flatten(), b.grad.flatten(), dim=0)
+        assert cos > 0.985
