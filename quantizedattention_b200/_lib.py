@@ -1,0 +1,54 @@
+"""ctypes loader for the C-ABI library (include/qattn.h).  There is NO fallback: if libqattn.so is
+missing or a call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqattn.so")
+_lib = None
+
+c_void_p, c_int, c_size_t, c_ll, c_float, c_uint = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
+                                                    ctypes.c_longlong, ctypes.c_float, ctypes.c_uint)
+
+# name -> (restype, argtypes); must list every symbol include/qattn.h declares
+SIGNATURES = {
+    "qa_version": (c_int, []),
+    "qa_last_error": (ctypes.c_char_p, []),
+    "qa_k_mean_workspace_bytes": (c_size_t, [c_int] * 4),
+    "qa_k_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
+    "qa_quant_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "qa_probe_mma": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_uint] + [c_int] * 6 + [c_void_p]),
+    "qa_probe_tma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m quantizedattention_b200.build` "
+                "(there is no CPU / PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError = header/library mismatch: fail loudly
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().qa_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def cur_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,154 @@
+// Self-checking hardware probes (debug entry points of the C-ABI library, used by tests/test_probe_gpu.py).
+// They pin down, on the real B200, the layout/descriptor conventions the attention kernels rely on:
+//   qa_probe_mma : one CTA stages host-built shared-memory images, issues tcgen05.mma with caller-chosen
+//                  descriptors (SS or TS mode) and dumps the TMEM accumulator.
+//   qa_probe_tma : one CTA performs a TMA tiled load with a given swizzle and dumps shared memory.
+#include "qa_ptx.cuh"
+#include "qa_host.h"
+
+namespace qa {
+
+struct ProbeMmaParams {
+  const uint8_t* a_img;   // SS: smem image of A; TS: uint32 [128][a_tmem_cols] TMEM image
+  const uint8_t* b_img;   // smem image of B
+  uint32_t* d_out;        // [128][n_cols] accumulator dump (raw 32-bit)
+  int a_bytes, b_bytes;
+  int a_lbo, a_sbo, a_layout, a_kstep_bytes;
+  int b_lbo, b_sbo, b_layout, b_kstep_bytes;
+  uint32_t idesc;
+  int kind;               // 0 = f16, 1 = i8, 2 = tf32
+  int n_mma, n_cols;
+  int a_in_tmem, a_tmem_cols, a_tmem_kstep_cols;
+};
+
+__global__ void __launch_bounds__(128) probe_mma_kernel(ProbeMmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + ((p.a_in_tmem ? 0 : p.a_bytes) + 1023) / 1024 * 1024;
+
+  if (!p.a_in_tmem)
+    for (int i = tid * 16; i < p.a_bytes; i += 128 * 16)
+      *reinterpret_cast<uint4*>(sa + i) = *reinterpret_cast<const uint4*>(p.a_img + i);
+  for (int i = tid * 16; i < p.b_bytes; i += 128 * 16)
+    *reinterpret_cast<uint4*>(sb + i) = *reinterpret_cast<const uint4*>(p.b_img + i);
+  fence_proxy_async_smem();
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+  const uint32_t a_col0 = 256;   // TS-mode A operand lives at columns [256, 256 + a_tmem_cols)
+
+  if (p.a_in_tmem) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(p.a_img) + (size_t)tid * p.a_tmem_cols;
+    for (int c = 0; c < p.a_tmem_cols; c += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = row[c + i];
+      tmem_st8(lane_addr + a_col0 + c, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  if (tid == 0) {
+    for (int k = 0; k < p.n_mma; ++k) {
+      uint64_t bd = umma_smem_desc(smem_u32(sb) + k * p.b_kstep_bytes, p.b_lbo, p.b_sbo, p.b_layout);
+      uint32_t acc = k > 0;
+      if (p.a_in_tmem) {
+        uint32_t at = tbase + a_col0 + k * p.a_tmem_kstep_cols;
+        if (p.kind == 1) umma_i8_ts(tbase, at, bd, p.idesc, acc);
+        else umma_f16_ts(tbase, at, bd, p.idesc, acc);
+      } else {
+        uint64_t ad = umma_smem_desc(smem_u32(sa) + k * p.a_kstep_bytes, p.a_lbo, p.a_sbo, p.a_layout);
+        if (p.kind == 1) umma_i8_ss(tbase, ad, bd, p.idesc, acc);
+        else if (p.kind == 0) umma_f16_ss(tbase, ad, bd, p.idesc, acc);
+        else umma_tf32_ss(tbase, ad, bd, p.idesc, acc);
+      }
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < p.n_cols; c += 8) {
+    uint32_t r[8];
+    tmem_ld8(lane_addr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p.d_out[(size_t)tid * p.n_cols + c + i] = r[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
+__global__ void __launch_bounds__(128) probe_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* out, int bytes,
+                                                        int rank, int c0, int c1, int c2) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < bytes; i += 128) smem[i] = 0xEE;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, bytes);
+    if (rank == 2) tma_load_2d(smem, &tmap, &bar, c0, c1);
+    else tma_load_3d(smem, &tmap, &bar, c0, c1, c2);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = tid; i < bytes; i += 128) out[i] = smem[i];
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+extern "C" int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, void* d_out, int a_lbo,
+                            int a_sbo, int a_layout, int a_kstep_bytes, int b_lbo, int b_sbo, int b_layout,
+                            int b_kstep_bytes, unsigned idesc, int kind, int n_mma, int n_cols, int a_in_tmem,
+                            int a_tmem_cols, int a_tmem_kstep_cols, void* stream) {
+  ProbeMmaParams p;
+  p.a_img = (const uint8_t*)a_img; p.b_img = (const uint8_t*)b_img; p.d_out = (uint32_t*)d_out;
+  p.a_bytes = a_bytes; p.b_bytes = b_bytes;
+  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.a_layout = a_layout; p.a_kstep_bytes = a_kstep_bytes;
+  p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.b_layout = b_layout; p.b_kstep_bytes = b_kstep_bytes;
+  p.idesc = idesc; p.kind = kind; p.n_mma = n_mma; p.n_cols = n_cols;
+  p.a_in_tmem = a_in_tmem; p.a_tmem_cols = a_tmem_cols; p.a_tmem_kstep_cols = a_tmem_kstep_cols;
+  if (n_cols % 8 || n_cols > 256 || (a_bytes & 15) || (b_bytes & 15)) return qa_fail(QA_ERR_SHAPE, "qa_probe_mma: bad sizes");
+  size_t smem = 1024 + ((size_t)(a_in_tmem ? 0 : a_bytes) + 1023) / 1024 * 1024 + b_bytes;
+  if (smem > 200 * 1024) return qa_fail(QA_ERR_SHAPE, "qa_probe_mma: images too large");
+  cudaFuncSetAttribute(probe_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_mma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  return qa_check_launch("qa_probe_mma");
+}
+
+// elem_bytes in {1,2,4}; dims/box innermost-first; strides in bytes for dims >= 1.
+extern "C" int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box, int swizzle, const int* coords,
+                            void* out, void* stream) {
+  CUtensorMap tm;
+  CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                           : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                             : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  uint64_t d[3], s[3];
+  uint32_t b[3];
+  size_t bytes = elem_bytes;
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; bytes *= box[i]; if (i) s[i - 1] = strides_bytes[i - 1]; }
+  int rc = qa_make_tmap(&tm, gptr, dt, rank, d, s, b, swizzle);
+  if (rc) return rc;
+  size_t smem = bytes + 1024;
+  cudaFuncSetAttribute(probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_tma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tm, (uint8_t*)out, (int)bytes, rank, coords[0], coords[1],
+                                                           rank > 2 ? coords[2] : 0);
+  return qa_check_launch("qa_probe_tma");
+}

@@ -1,0 +1,65 @@
+"""Host-side models of the shared-memory / TMEM layouts the tcgen05 kernels assume.  Used by
+tests/test_probe_gpu.py to check the models against the B200 (one MMA tile at a time)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from quantizedattention_b200 import _lib
+
+SW_BITS = {0: 0, 6: 1, 4: 2, 2: 3}       # UMMA layout type -> swizzle bits (none, 32B, 64B, 128B)
+TMA_SWZ = {0: 0, 6: 1, 4: 2, 2: 3}       # UMMA layout type -> qa_make_tmap swizzle code
+
+
+def swizzle_offsets(off, bits):
+    """Swizzle<bits,4,3>: XOR address bits [4,4+bits) with bits [7,7+bits)."""
+    return off ^ (((off >> 7) & ((1 << bits) - 1)) << 4)
+
+
+def image_rows(mat_bytes: np.ndarray, layout: int) -> np.ndarray:
+    """mat_bytes: [rows, row_bytes] uint8 with row_bytes == swizzle span (or any for no swizzle).
+    Returns the linear shared-memory image: row r at r*row_bytes, 16-byte chunks XOR-swizzled."""
+    rows, rb = mat_bytes.shape
+    lin = np.arange(rows * rb, dtype=np.int64)
+    dst = swizzle_offsets(lin, SW_BITS[layout])
+    img = np.zeros(rows * rb, dtype=np.uint8)
+    img[dst] = mat_bytes.reshape(-1)
+    return img
+
+
+def idesc(c_fmt, a_fmt, b_fmt, a_major, b_major, M, N):
+    return (c_fmt << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def run_mma(a_img, b_img, n_cols, *, a_lbo=16, a_sbo=1024, a_layout=2, a_kstep=32, b_lbo=16, b_sbo=1024, b_layout=2,
+            b_kstep=32, idesc_v=0, kind=1, n_mma=4, a_in_tmem=0, a_tmem_cols=0, a_tmem_kstep_cols=8):
+    L = _lib.lib()
+    a = torch.from_numpy(np.ascontiguousarray(a_img).view(np.uint8).reshape(-1)).cuda()
+    b = torch.from_numpy(np.ascontiguousarray(b_img).view(np.uint8).reshape(-1)).cuda()
+    pad = lambda t: torch.cat([t, torch.zeros((-t.numel()) % 16, dtype=torch.uint8, device="cuda")])
+    a, b = pad(a), pad(b)
+    d = torch.zeros((128, n_cols), dtype=torch.int32, device="cuda")
+    rc = L.qa_probe_mma(_lib.ptr(a), a.numel(), _lib.ptr(b), b.numel(), _lib.ptr(d), a_lbo, a_sbo, a_layout, a_kstep,
+                        b_lbo, b_sbo, b_layout, b_kstep, ctypes.c_uint(idesc_v), kind, n_mma, n_cols, a_in_tmem,
+                        a_tmem_cols, a_tmem_kstep_cols, _lib.cur_stream())
+    _lib.check(rc, "qa_probe_mma")
+    torch.cuda.synchronize()
+    return d.cpu()
+
+
+def run_tma(src: torch.Tensor, elem_bytes, dims, strides_bytes, box, swizzle, coords):
+    L = _lib.lib()
+    rank = len(dims)
+    nbytes = elem_bytes * int(np.prod(box))
+    out = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    U64 = ctypes.c_ulonglong * 3
+    U32 = ctypes.c_uint * 3
+    I32 = ctypes.c_int * 3
+    d = U64(*(list(dims) + [1] * (3 - rank)))
+    s = U64(*(list(strides_bytes) + [0] * (3 - len(strides_bytes))))
+    b = U32(*(list(box) + [1] * (3 - rank)))
+    c = I32(*(list(coords) + [0] * (3 - rank)))
+    rc = L.qa_probe_tma(_lib.ptr(src), elem_bytes, rank, d, s, b, swizzle, c, _lib.ptr(out), _lib.cur_stream())
+    _lib.check(rc, "qa_probe_tma")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
