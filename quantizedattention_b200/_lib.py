@@ -19,6 +19,7 @@ SIGNATURES = {
     "qa_k_mean_workspace_bytes": (c_size_t, [c_int] * 4),
     "qa_k_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_quant_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "qa_int8_fwd": (c_int, [c_void_p] * 12 + [c_int] * 7 + [c_void_p]),
     "qa_probe_mma": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_uint] + [c_int] * 6 + [c_void_p]),
     "qa_probe_tma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }

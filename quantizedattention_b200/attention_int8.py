@@ -1,0 +1,65 @@
+"""Drop-in for the reference's `attention_int8.py` (SageAttention3-style int8 attention), B200-native.
+
+Same callables, argument order, tensor layouts and output tuples as the reference:
+  sage_attention_3_int8(q,k,v)                         attention_int8.py:434-451
+  SageAttention3_Int8_autograd_function                attention_int8.py:20-95
+  helion_atten_int8_hl_dot_fwd(q, k_smoothed, v)       attention_int8.py:101-262
+  helion_atten_int8_hl_dot_bwd(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv)   :268-432
+  baseline_pytorch_attention(q,k,v,head_dim,causal)    attention_int8.py:453-481
+Every kernel is hand-written sm_100a CUDA behind the C-ABI library (include/qattn.h); there is no
+Triton/Helion/CPU path.  Deviations from the reference's literal (partly broken) behaviour follow the
+contract in DESIGN.md / SURVEY.md 8-LEDGER: per-(b,h) attention, per-head K token mean, corrected backward.
+
+`Bq` / `Bkv` are the reference's tunables (PowerOfTwoFragment(32, 256, 32), attention_int8.py:155-158): the
+quantisation block sizes, returned to the caller and forwarded to backward.  The tuned values here are
+Bq = Bkv = 128 (the tcgen05 tile); `set_block_sizes` changes Bq (32/64/128/256).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+_CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2}
+
+
+def set_block_sizes(Bq: int = 128, Bkv: int = 128):
+    if Bq not in (32, 64, 128, 256) or Bkv != 128:
+        raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv = 128")
+    _CFG["Bq"], _CFG["Bkv"] = Bq, Bkv
+
+
+def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False):
+    """Quantise Q/K/V per block and run the fused int8 forward.  Returns the reference 10-tuple
+    (O fp16 [B,H,S,D], lse fp16 [N], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv)."""
+    batch, head, q_tokens, q_head_dim = q_fp16_input.shape
+    _, _, k_tokens, k_head_dim = k_fp16_input.shape
+    _, _, v_tokens, v_head_dim = v_fp16_input.shape
+    assert k_tokens == v_tokens, "k and v tokens are different"
+    assert k_head_dim == v_head_dim, "k head_dim and v head_dim are different"
+    for t in (q_fp16_input, k_fp16_input, v_fp16_input):
+        if t.dtype != torch.float16:
+            raise TypeError("int8 attention takes fp16 q, k, v")
+    Bq, Bkv = _CFG["Bq"], _CFG["Bkv"]
+    D = q_head_dim
+    q_i8, sq = ops.quant_block(q_fp16_input, Bq)
+    k_i8, sk = ops.quant_block(k_fp16_input, Bkv)
+    v_i8, sv = ops.quant_block(v_fp16_input, Bkv)
+    O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
+                                            nsplit=_CFG["nsplit"], want_lse32=_want_lse32)
+    out = (O.view(batch, head, q_tokens, D), lse16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
+    return out + (lse32,) if _want_lse32 else out
+
+
+def baseline_pytorch_attention(q, k, v, head_dim, causal):
+    """The reference's fp32 PyTorch attention math (strict causal mask, finite -128*ln2 fill)."""
+    p = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(head_dim)
+    if causal:
+        b, h, q_token, k_token = p.shape
+        mask = torch.arange(q_token, device=q.device)[:, None] - torch.arange(k_token, device=q.device)[None, :]
+        p = torch.where(mask[None, None] > 0, p, -128 * torch.log(torch.tensor([2], device=q.device)))
+    p = torch.softmax(p.to(torch.float32), dim=-1).to(torch.float32)
+    return torch.matmul(p, v)

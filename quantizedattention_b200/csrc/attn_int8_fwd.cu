@@ -1,0 +1,358 @@
+// int8 SageAttention3-style forward (reference attention_int8.py:170-257) for sm_100a.
+//
+// One CTA = one 128-row query tile of one (batch, head).  Warp roles (NSPLIT = column groups per row):
+//   softmax warps    [0, 4*NSPLIT)            TMEM S tile -> fp16 logits -> online softmax -> int8 P -> smem
+//   correction warps [4*NSPLIT, 8*NSPLIT)     TMEM int32 P.V partial -> fp32 O accumulators in registers
+//   producer warp    8*NSPLIT                 TMA: Q once, K / V tiles into STAGES-deep rings
+//   MMA warp         8*NSPLIT + 1             tcgen05.mma kind::i8 (S = Q K^T, Opart = P V), TMEM owner
+// TMEM (512 cols): S[2] at 0/128, Opart[2] at 256/384.  The int32 P.V accumulator cannot span k-tiles (the
+// P scale is per row per k-tile, the V scale per k-tile), so each k-tile's partial is drained to registers.
+// Numerics follow the reference step by step (fp16 logits, fp16 running max, fp16 subtraction, per-row P scale
+// exp2(rowmax - m)/127, truncation toward zero); see DESIGN.md for the two tolerance-level deviations
+// (single fused scale multiply; reciprocal multiply instead of divide for P/sp).
+#include "qa_ptx.cuh"
+#include "qa_host.h"
+
+namespace qa {
+
+constexpr int kBM = 128;    // query rows per CTA (= tcgen05 M)
+constexpr int kBN = 128;    // keys per k-tile (= Bkv)
+
+template <int D, int NSPLIT, int STAGES>
+struct Int8FwdSmem {
+  static constexpr int kQBytes = kBM * D;
+  static constexpr int kKBytes = kBN * D;
+  static constexpr int kVBytes = kBN * D;
+  static constexpr int kPBytes = kBM * kBN;
+  static constexpr int off_q = 0;
+  static constexpr int off_k = off_q + kQBytes;
+  static constexpr int off_v = off_k + STAGES * kKBytes;
+  static constexpr int off_p = off_v + STAGES * kVBytes;
+  static constexpr int off_end = off_p + 2 * kPBytes;
+  static constexpr int total = off_end + 1024;   // + alignment slack
+};
+
+struct Int8FwdParams {
+  const __half* sq;      // [BH*Sq/Bq]
+  const __half* sk;      // [BH*Sk/128]
+  const __half* sv;      // [BH*Sk/128]
+  __half* O;             // [BH*Sq, D] fp16
+  __half* lse16;         // [BH*Sq]
+  float* lse32;          // [BH*Sq] (may be null)
+  float* m_out;          // optional split outputs for ring attention: unnormalised O + (m, l); null otherwise
+  float* l_out;
+  float* O_acc_out;
+  int Sq, Sk, Bq;
+  float qk_scale;
+};
+
+template <int D, int NSPLIT, int STAGES>
+__global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
+int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
+  using L = Int8FwdSmem<D, NSPLIT, STAGES>;
+  constexpr int NC = kBN / NSPLIT;       // S columns per softmax thread
+  constexpr int DC = D / NSPLIT;         // O columns per correction thread
+  constexpr int kSoftWarps = 4 * NSPLIT;
+  constexpr uint32_t kLayoutQK = (D == 128) ? kSwz128 : kSwz64;   // rows of D bytes
+  constexpr uint32_t kSboQK = (D == 128) ? 1024 : 512;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
+  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2], sc_full[2], sc_empty[2], fin_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float2 row_sc[2][kBM];          // per tile parity: (rescale, sp*sv) per row
+  __shared__ __half xmax[2][2][kBM];         // NSPLIT == 2: row-max exchange between the two column groups
+  __shared__ float l_part[2][kBM];
+  __shared__ __half m_fin[kBM];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, q0 = blockIdx.x * kBM;
+  const int nk = p.Sk / kBN;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], kSoftWarps);
+      mbar_init(&p_full[b], kSoftWarps); mbar_init(&p_empty[b], 1);
+      mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], kSoftWarps);
+      mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], kSoftWarps);
+    }
+    mbar_init(&fin_full, kSoftWarps);
+    fence_mbar_init();
+  }
+  if (warp == 8 * NSPLIT + 1) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp < kSoftWarps) {
+    // =========================== softmax warps ===========================
+    const int split = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const int c0 = split * NC;
+    const float sq_f = __half2float(p.sq[((size_t)bh * p.Sq + q0 + row) / p.Bq]);
+    __half m16 = __float2half_rn(-INFINITY);
+    float l = (split == 0) ? 1.0f : 0.0f;          // reference initialises l to 1.0 (attention_int8.py:173)
+    for (int j = 0; j < nk; ++j) {
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const float sk_f = __half2float(p.sk[((size_t)bh * p.Sk) / kBN + j]);
+      const float sv_f = __half2float(p.sv[((size_t)bh * p.Sk) / kBN + j]);
+      const float c = sq_f * sk_f * p.qk_scale;
+      mbar_wait(&s_full[b], ph);
+      tc_fence_after();
+      // ---- pass 1: int32 -> fp16 logits (packed), row max
+      __half2 sh[NC / 2];
+      __half2 mx2 = __float2half2_rn(-INFINITY);
+#pragma unroll
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + b * kBN + c0 + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a0 = __int2float_rn((int)r[2 * i]) * c;
+          float a1 = __int2float_rn((int)r[2 * i + 1]) * c;
+          __half2 h = __floats2half2_rn(a0, a1);
+          sh[ch * 16 + i] = h;
+          mx2 = __hmax2(mx2, h);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);        // S[b] is in registers: the MMA warp may overwrite it
+      __half rmax = __hmax(__low2half(mx2), __high2half(mx2));
+      if (NSPLIT == 2) {
+        xmax[b][split][row] = rmax;
+        named_bar_sync(1, 128 * NSPLIT);
+        rmax = __hmax(rmax, xmax[b][split ^ 1][row]);
+      }
+      const __half m_new = __hmax(m16, rmax);
+      const float rescale = ex2_approx(__half2float(__hsub(m16, m_new)));       // fp16 subtraction (:217-219)
+      const float sp_e = ex2_approx(__half2float(__hsub(rmax, m_new)));         // (:232-234) sp = sp_e / 127
+      const float inv_sp = __fdividef(127.0f, sp_e);
+      m16 = m_new;
+      // ---- hand (rescale, sp*sv) to the correction warps
+      if (split == 0) {
+        mbar_wait(&sc_empty[b], ph ^ 1);
+        row_sc[b][row] = make_float2(rescale, sp_e * (1.0f / 127.0f) * sv_f);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_full[b]);
+      }
+      // ---- pass 2: P = exp2(S16 - m), l += sum(P), P_i8 = trunc(P / sp) -> swizzled smem (K-major, 128 B rows)
+      mbar_wait(&p_empty[b], ph ^ 1);
+      const __half2 m2 = __half2half2(m_new);
+      float lsum = 0.f;
+      uint8_t* prow = smem + L::off_p + b * L::kPBytes;
+#pragma unroll
+      for (int g = 0; g < NC / 16; ++g) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t bytes[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
+            float p0 = ex2_approx(f.x), p1 = ex2_approx(f.y);
+            lsum += p0 + p1;
+            bytes[h2 * 2] = __float_as_uint(__fmaf_rz(p0, inv_sp, 8388608.0f)) & 0xffu;      // trunc(P/sp)
+            bytes[h2 * 2 + 1] = __float_as_uint(__fmaf_rz(p1, inv_sp, 8388608.0f)) & 0xffu;
+          }
+          w[q4] = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
+        }
+        const uint32_t off = swz128(row, c0 + g * 16);
+        *reinterpret_cast<uint4*>(prow + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l = l * rescale + lsum;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+    l_part[split][row] = l;
+    if (split == 0) m_fin[row] = m16;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&fin_full);
+  } else if (warp < 2 * kSoftWarps) {
+    // =========================== correction warps ===========================
+    const int cw = warp - kSoftWarps;
+    const int split = cw >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const int d0 = split * DC;
+    float acc[DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) acc[i] = 0.f;
+    for (int j = 0; j < nk; ++j) {
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&sc_full[b], ph);
+      const float2 sc = row_sc[b][row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sc_empty[b]);
+      mbar_wait(&o_full[b], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < DC / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + 256 + b * 128 + d0 + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), sc.y, acc[ch * 32 + i] * sc.x);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[b]);
+    }
+    mbar_wait(&fin_full, 0);
+    float l = l_part[0][row];
+    if (NSPLIT == 2) l += l_part[1][row];
+    const size_t grow = (size_t)bh * p.Sq + q0 + row;
+    if (p.O_acc_out != nullptr) {
+      // ring mode: emit the unnormalised accumulator and (m, l); the host-side merge normalises
+      float* dst = p.O_acc_out + grow * D + d0;
+#pragma unroll
+      for (int i = 0; i < DC; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      if (split == 0) { p.m_out[grow] = __half2float(m_fin[row]); p.l_out[grow] = l; }
+    } else {
+      const float inv_l = 1.0f / l;                                            // O / l (:256)
+      __half* dst = p.O + grow * D + d0;
+#pragma unroll
+      for (int i = 0; i < DC; i += 8) {
+        __half2 h0 = __floats2half2_rn(acc[i] * inv_l, acc[i + 1] * inv_l);
+        __half2 h1 = __floats2half2_rn(acc[i + 2] * inv_l, acc[i + 3] * inv_l);
+        __half2 h2 = __floats2half2_rn(acc[i + 4] * inv_l, acc[i + 5] * inv_l);
+        __half2 h3 = __floats2half2_rn(acc[i + 6] * inv_l, acc[i + 7] * inv_l);
+        uint4 v;
+        v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
+        v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + i) = v;
+      }
+      if (split == 0) {
+        const __half m = m_fin[row];
+        const float lg = log2f(l);
+        p.lse16[grow] = __hadd(m, __float2half_rn(lg));                          // (:252)
+        if (p.lse32 != nullptr) p.lse32[grow] = __half2float(m) + lg;
+      }
+    }
+  } else if (warp == 8 * NSPLIT) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+      mbar_expect_tx(&q_full, L::kQBytes);
+      tma_load_2d(smem + L::off_q, &tm_q, &q_full, 0, bh * p.Sq + q0);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (j / STAGES) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], L::kKBytes);
+        tma_load_2d(smem + L::off_k + s * L::kKBytes, &tm_k, &k_full[s], 0, bh * p.Sk + j * kBN);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], L::kVBytes);
+        tma_load_2d(smem + L::off_v + s * L::kVBytes, &tm_v, &v_full[s], 0, bh * p.Sk + j * kBN);
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc(2, 1, 1, 0, 0, kBM, kBN);          // s32 += s8 x s8, both K-major
+      constexpr uint32_t idesc_pv = umma_idesc(2, 1, 1, 0, 1, kBM, D);            // B = V: MN-major
+      const uint32_t q_addr = smem_u32(smem + L::off_q);
+      auto issue_pv = [&](int t) {
+        const int b = t & 1, s = t % STAGES;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(&v_full[s], (t / STAGES) & 1);
+        mbar_wait(&o_empty[b], ph ^ 1);
+        mbar_wait(&p_full[b], ph);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + L::off_p + b * L::kPBytes);
+        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kVBytes);
+#pragma unroll
+        for (int k = 0; k < kBN / 32; ++k) {
+          const uint64_t ad = umma_smem_desc(p_addr + k * 32, 16, 1024, kSwz128);
+          const uint64_t bd = umma_smem_desc(v_addr + k * 32 * D, 16, kSboQK, kLayoutQK);
+          umma_i8_ss(tbase + 256 + b * 128, ad, bd, idesc_pv, k > 0);
+        }
+        umma_commit(&o_full[b]);
+        umma_commit(&v_empty[s]);
+        umma_commit(&p_empty[b]);
+      };
+      mbar_wait(&q_full, 0);
+      for (int j = 0; j < nk; ++j) {
+        const int b = j & 1, s = j % STAGES;
+        mbar_wait(&k_full[s], (j / STAGES) & 1);
+        mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
+#pragma unroll
+        for (int k = 0; k < D / 32; ++k) {
+          const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, kSboQK, kLayoutQK);
+          const uint64_t bd = umma_smem_desc(k_addr + k * 32, 16, kSboQK, kLayoutQK);
+          umma_i8_ss(tbase + b * kBN, ad, bd, idesc_qk, k > 0);
+        }
+        umma_commit(&s_full[b]);
+        umma_commit(&k_empty[s]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(nk - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
+}
+
+template <int D, int NSPLIT, int STAGES>
+static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const Int8FwdParams& p, int BH,
+                           cudaStream_t st) {
+  using L = Int8FwdSmem<D, NSPLIT, STAGES>;
+  CUtensorMap tq, tk, tv;
+  const int sw = (D == 128) ? 3 : 2;
+  uint64_t dq[2] = {(uint64_t)D, (uint64_t)BH * p.Sq}, dk[2] = {(uint64_t)D, (uint64_t)BH * p.Sk};
+  uint64_t str[1] = {(uint64_t)D};
+  uint32_t box[2] = {(uint32_t)D, 128};
+  int rc;
+  if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, str, box, sw))) return rc;
+  if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, box, sw))) return rc;
+  if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, box, sw))) return rc;
+  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  dim3 grid(p.Sq / kBM, BH);
+  kern<<<grid, 256 * NSPLIT + 64, L::total, st>>>(tq, tk, tv, p);
+  return qa_check_launch("qa_int8_fwd");
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+// Forward over pre-quantised operands.  q_i8 [BH*Sq, D], k_i8 / v_i8 [BH*Sk, D] int8 row-major; sq [BH*Sq/Bq],
+// sk / sv [BH*Sk/Bkv] fp16.  Outputs: O fp16 [BH*Sq, D], lse16 fp16 [BH*Sq], lse32 fp32 [BH*Sq] (optional).
+// Ring mode (o_acc != NULL): writes unnormalised fp32 O plus (m, l) per row instead of O / lse.
+extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
+                           const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
+                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, void* stream) {
+  if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: D must be 64 or 128");
+  if (Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 128 (tcgen05 k-tile)");
+  if (Bq != 32 && Bq != 64 && Bq != 128 && Bq != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bq must be 32/64/128/256");
+  if (Sq % 128 || Sk % 128 || Sq % Bq) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Sq, Sk must be multiples of 128 (and of Bq)");
+  if (((uintptr_t)q_i8 | (uintptr_t)k_i8 | (uintptr_t)v_i8 | (uintptr_t)O | (uintptr_t)o_acc) & 15)
+    return qa_fail(QA_ERR_ALIGN, "qa_int8_fwd: 16-byte alignment required");
+  Int8FwdParams p;
+  p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv;
+  p.O = (__half*)O; p.lse16 = (__half*)lse16; p.lse32 = (float*)lse32;
+  p.O_acc_out = (float*)o_acc; p.m_out = (float*)m_out; p.l_out = (float*)l_out;
+  p.Sq = Sq; p.Sk = Sk; p.Bq = Bq;
+  p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128) return nsplit == 2 ? launch_int8_fwd<128, 2, 3>(q_i8, k_i8, v_i8, p, BH, st)
+                                   : launch_int8_fwd<128, 1, 3>(q_i8, k_i8, v_i8, p, BH, st);
+  return nsplit == 2 ? launch_int8_fwd<64, 2, 4>(q_i8, k_i8, v_i8, p, BH, st)
+                     : launch_int8_fwd<64, 1, 4>(q_i8, k_i8, v_i8, p, BH, st);
+}

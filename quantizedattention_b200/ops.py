@@ -48,3 +48,30 @@ def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, row
         _lib.check(L.qa_quant_block(_lib.ptr(x2), _lib.ptr(mean), _lib.ptr(out), _lib.ptr(scales), N, D, blk,
                                     rows_per_head or N, _lib.cur_stream()), "qa_quant_block")
     return out, scales
+
+
+def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=2, want_lse32=True,
+                      ring_state=False):
+    """Fused int8 attention forward over pre-quantised operands (qa_int8_fwd).
+    Returns (O fp16 [BH*Sq, D], lse16 [BH*Sq], lse32 or None); with ring_state=True returns the unnormalised
+    (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead."""
+    _need_cuda(q_i8, k_i8, v_i8, sq, sk, sv)
+    dev = q_i8.device
+    L = _lib.lib()
+    if ring_state:
+        o_acc = torch.empty((BH * Sq, D), dtype=torch.float32, device=dev)
+        m = torch.empty((BH * Sq,), dtype=torch.float32, device=dev)
+        l = torch.empty((BH * Sq,), dtype=torch.float32, device=dev)
+        O = lse16 = lse32 = None
+    else:
+        O = torch.empty((BH * Sq, D), dtype=torch.float16, device=dev)
+        lse16 = torch.empty((BH * Sq,), dtype=torch.float16, device=dev)
+        lse32 = torch.empty((BH * Sq,), dtype=torch.float32, device=dev) if want_lse32 else None
+        o_acc = m = l = None
+    with torch.cuda.device(dev):
+        _lib.check(L.qa_int8_fwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk), _lib.ptr(sv),
+                                 _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc), _lib.ptr(m), _lib.ptr(l),
+                                 BH, Sq, Sk, D, Bq, Bkv, nsplit, _lib.cur_stream()), "qa_int8_fwd")
+    if ring_state:
+        return o_acc, m, l
+    return O, lse16, lse32

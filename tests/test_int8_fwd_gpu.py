@@ -1,0 +1,46 @@
+"""Parity of the fused int8 forward against the oracle and fp32 attention math."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(shape, generator=g).to(torch.float16) for _ in range(3)]
+
+
+def _stats(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return (a - b).abs().max().item(), torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+
+
+@pytest.mark.parametrize("nsplit", [1, 2])
+@pytest.mark.parametrize("shape,Bq", [((1, 2, 256, 128), 128), ((1, 8, 1024, 64), 128), ((2, 2, 512, 128), 32),
+                                      ((1, 1, 128, 64), 64)])
+def test_int8_fwd_matches_oracle(shape, Bq, nsplit):
+    from oracle import int8_ref
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_int8 as A
+    q, k, v = _mk(shape, 1000 + shape[2] + shape[3])
+    A.set_block_sizes(Bq, 128)
+    A._CFG["nsplit"] = nsplit
+    try:
+        out = A.helion_atten_int8_hl_dot_fwd(q.cuda(), k.cuda(), v.cuda(), _want_lse32=True)
+    finally:
+        A.set_block_sizes(128, 128)
+        A._CFG["nsplit"] = 2
+    torch.cuda.synchronize()
+    ref = int8_ref.int8_fwd(q, k, v, Bq, 128, per_head=True, return_lse32=True)
+    # quantised tensors and scales: bit-exact
+    for i in (2, 3, 4, 5, 6, 7):
+        assert torch.equal(out[i].cpu(), ref[i]), f"slot {i}"
+    assert out[8] == Bq and out[9] == 128
+    # O / lse: tolerance vs the eager oracle (same algorithm) and vs fp32 math
+    mx, cos = _stats(out[0].cpu(), ref[0])
+    assert mx < 5e-3 and cos > 0.99999, (mx, cos)
+    assert (out[1].cpu().float() - ref[1].float()).abs().max() < 4e-2          # fp16 lse: 1-2 ulp at |lse| ~ 8..16
+    assert (out[10].cpu() - ref[10]).abs().max() < 2e-3
+    base = baseline_pytorch_attention(q.float(), k.float(), v.float(), shape[3], False)
+    mx, cos = _stats(out[0].cpu(), base)
+    assert mx < 8e-2 and cos > 0.999, (mx, cos)                               # reference yardstick: atol 1e-2 class noise

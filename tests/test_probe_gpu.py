@@ -19,10 +19,6 @@ def _save():
         json.dump(REPORT, f, indent=1)
 
 
-def _i8(rng, r, c):
-    return rng.integers(-127, 128, size=(r, c), dtype=np.int8)
-
-
 def test_tma_swizzle_models():
     import probe_models as pm
     rng = np.random.default_rng(0)
@@ -43,103 +39,34 @@ def test_tma_swizzle_models():
     assert all(res.values()), res
 
 
-def test_umma_int8_layouts():
-    import probe_models as pm
-    rng = np.random.default_rng(1)
+def test_umma_layout_cases():
+    """Each case runs in a child process: a wrong descriptor hypothesis can fault the CUDA context."""
+    import subprocess
+    import sys
+    import probe_cases
+    names = list(probe_cases.CASES)
     res = {}
-    # --- QK^T style: A [128 x 128] K-major SW128, B [N=128 x K=128] K-major SW128 (D = 128)
-    A, B = _i8(rng, 128, 128), _i8(rng, 128, 128)
-    exp = A.astype(np.int32) @ B.astype(np.int32).T
-    idv = pm.idesc(2, 1, 1, 0, 0, 128, 128)
-    got = pm.run_mma(pm.image_rows(A.view(np.uint8), 2), pm.image_rows(B.view(np.uint8), 2), 128, idesc_v=idv, kind=1, n_mma=4)
-    res["i8_kmajor_sw128"] = bool((got.numpy() == exp).all())
-    # --- D = 64: rows of 64 bytes, SW64, SBO = 512
-    A6, B6 = _i8(rng, 128, 64), _i8(rng, 128, 64)
-    exp6 = A6.astype(np.int32) @ B6.astype(np.int32).T
-    got = pm.run_mma(pm.image_rows(A6.view(np.uint8), 4), pm.image_rows(B6.view(np.uint8), 4), 128, idesc_v=idv, kind=1,
-                     n_mma=2, a_sbo=512, a_layout=4, b_sbo=512, b_layout=4)
-    res["i8_kmajor_sw64"] = bool((got.numpy() == exp6).all())
-    # --- PV style: A = P [128 x keys=128] K-major SW128, B = V [keys=128][D=128] MN-major SW128, 4096 B per k-step
-    P, V = rng.integers(0, 128, size=(128, 128), dtype=np.int8), _i8(rng, 128, 128)
-    expv = P.astype(np.int32) @ V.astype(np.int32)
-    idm = pm.idesc(2, 1, 1, 0, 1, 128, 128)
-    for name, lbo, sbo in (("lbo16_sbo1024", 16, 1024), ("lbo1024_sbo16", 1024, 16), ("lbo4096_sbo1024", 4096, 1024),
-                           ("lbo1024_sbo4096", 1024, 4096)):
-        got = pm.run_mma(pm.image_rows(P.view(np.uint8), 2), pm.image_rows(V.view(np.uint8), 2), 128, idesc_v=idm, kind=1,
-                         n_mma=4, b_lbo=lbo, b_sbo=sbo, b_kstep=4096)
-        res["i8_B_mnmajor_sw128_" + name] = bool((got.numpy() == expv).all())
-    # --- PV with D = 64: V rows of 64 bytes (SW64), N = 64; k-step = 32 keys * 64 B = 2048
-    V6 = _i8(rng, 128, 64)
-    expv6 = P.astype(np.int32) @ V6.astype(np.int32)
-    idm6 = pm.idesc(2, 1, 1, 0, 1, 128, 64)
-    for name, lbo, sbo in (("lbo16_sbo512", 16, 512), ("lbo512_sbo16", 512, 16), ("lbo2048_sbo512", 2048, 512)):
-        got = pm.run_mma(pm.image_rows(P.view(np.uint8), 2), pm.image_rows(V6.view(np.uint8), 4), 64, idesc_v=idm6, kind=1,
-                         n_mma=4, b_lbo=lbo, b_sbo=sbo, b_layout=4, b_kstep=2048)
-        res["i8_B_mnmajor_sw64_" + name] = bool((got.numpy() == expv6).all())
-    # --- transposed A (backward: dV = P^T dO): A stored [K = q rows][M = keys] (MN-major SW128), B = dO [q][D] MN-major
-    Pm, dO = _i8(rng, 128, 128), _i8(rng, 128, 128)          # Pm[q][key]
-    expt = Pm.astype(np.int32).T @ dO.astype(np.int32)
-    idt = pm.idesc(2, 1, 1, 1, 1, 128, 128)
-    for name, lbo, sbo in (("lbo16_sbo1024", 16, 1024), ("lbo4096_sbo1024", 4096, 1024)):
-        got = pm.run_mma(pm.image_rows(Pm.view(np.uint8), 2), pm.image_rows(dO.view(np.uint8), 2), 128, idesc_v=idt, kind=1,
-                         n_mma=4, a_lbo=lbo, a_sbo=sbo, a_kstep=4096, b_lbo=lbo, b_sbo=sbo, b_kstep=4096)
-        res["i8_A_mnmajor_sw128_" + name] = bool((got.numpy() == expt).all())
-    # --- TS mode: A = P from TMEM, 4 int8 per 32-bit column (little endian), 8 columns per k-step
-    a_t = P.view(np.uint8).reshape(128, 32, 4).copy().view(np.uint32).reshape(128, 32)
-    got = pm.run_mma(a_t, pm.image_rows(V.view(np.uint8), 2), 128, idesc_v=idm, kind=1, n_mma=4, b_kstep=4096,
-                     a_in_tmem=1, a_tmem_cols=32, a_tmem_kstep_cols=8)
-    res["i8_TS_packed4"] = bool((got.numpy() == expv).all())
-    REPORT["i8"] = res
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "probe_cases.py")
+    todo = list(names)
+    while todo:
+        p = subprocess.run([sys.executable, script] + todo, capture_output=True, text=True, timeout=300)
+        done = []
+        for line in p.stdout.splitlines():
+            if line.startswith("PROBE "):
+                d = json.loads(line[6:])
+                res[d["case"]] = d["result"]
+                done.append(d["case"])
+        todo = [n for n in todo if n not in done]
+        if todo and p.returncode != 0:
+            res[todo[0]] = "crash: " + p.stderr.strip().splitlines()[-1][:200] if p.stderr.strip() else "crash"
+            todo = todo[1:]
+        elif todo:
+            break
+    REPORT["umma"] = res
     _save()
-    need = ["i8_kmajor_sw128", "i8_kmajor_sw64"]
-    assert all(res[k] for k in need), res
-    assert any(v for k, v in res.items() if k.startswith("i8_B_mnmajor_sw128")), res
-
-
-def test_umma_f16_layouts():
-    import probe_models as pm
-    rng = np.random.default_rng(2)
-    res = {}
-    f16 = lambda r, c: (rng.standard_normal((r, c)) * 0.5).astype(np.float16)
-    A, B = f16(128, 64), f16(128, 64)
-    exp = A.astype(np.float32) @ B.astype(np.float32).T
-    idv = pm.idesc(1, 0, 0, 0, 0, 128, 128)           # f32 acc, f16 x f16, K-major
-    got = pm.run_mma(pm.image_rows(A.view(np.uint8), 2), pm.image_rows(B.view(np.uint8), 2), 128, idesc_v=idv, kind=0, n_mma=4)
-    err = np.abs(got.numpy().view(np.float32) - exp).max()
-    res["f16_kmajor_sw128"] = float(err)
-    # bf16 P [128 x 128 keys] (two K atoms of 64 keys) x V [keys][D=64] bf16 MN-major (one 128 B atom along N)
-    to_bf = lambda x: torch.from_numpy(x).to(torch.bfloat16)
-    P = to_bf(np.abs(rng.standard_normal((128, 64))).astype(np.float32))
-    V = to_bf(rng.standard_normal((64, 64)).astype(np.float32))
-    expv = (P.float() @ V.float()).numpy()
-    idm = pm.idesc(1, 1, 1, 0, 1, 128, 64)
-    img = lambda t, lay: pm.image_rows(t.view(torch.int16).numpy().view(np.uint8).reshape(t.shape[0], -1), lay)
-    for name, lbo, sbo in (("lbo16_sbo1024", 16, 1024), ("lbo2048_sbo1024", 2048, 1024)):
-        got = pm.run_mma(img(P, 2), img(V, 2), 64, idesc_v=idm, kind=0, n_mma=4, b_lbo=lbo, b_sbo=sbo, b_kstep=2048)
-        res["bf16_B_mnmajor_sw128_" + name] = float(np.abs(got.numpy().view(np.float32) - expv).max())
-    # D = 128 bf16 V: two 128-byte atoms along N, each [keys][128 B]; LBO = atom stride = keys * 128 B
-    V2 = to_bf(rng.standard_normal((64, 128)).astype(np.float32))
-    expv2 = (P.float() @ V2.float()).numpy()
-    v_img = np.concatenate([img(V2[:, :64].contiguous(), 2), img(V2[:, 64:].contiguous(), 2)])
-    idm2 = pm.idesc(1, 1, 1, 0, 1, 128, 128)
-    for name, lbo, sbo in (("lbo8192_sbo1024", 8192, 1024), ("lbo1024_sbo8192", 1024, 8192)):
-        got = pm.run_mma(img(P, 2), v_img, 128, idesc_v=idm2, kind=0, n_mma=4, b_lbo=lbo, b_sbo=sbo, b_kstep=2048)
-        res["bf16_B_mnmajor_2atoms_" + name] = float(np.abs(got.numpy().view(np.float32) - expv2).max())
-    # TS mode bf16: 2 values per 32-bit column, 8 columns per k-step (K = 16)
-    a_t = P.view(torch.int16).numpy().view(np.uint16).reshape(128, 32, 2).copy().view(np.uint32).reshape(128, 32)
-    got = pm.run_mma(a_t, img(V, 2), 64, idesc_v=idm, kind=0, n_mma=4, b_kstep=2048, a_in_tmem=1, a_tmem_cols=32,
-                     a_tmem_kstep_cols=8)
-    res["bf16_TS_packed2"] = float(np.abs(got.numpy().view(np.float32) - expv).max())
-    # transposed A in 16-bit (backward dV = P^T dO, dK = dS^T Q): A stored [K = q][M = keys] bf16, M = 128 -> two atoms
-    Pq = to_bf(rng.standard_normal((64, 128)).astype(np.float32))      # [q = 64][keys = 128]
-    dO = to_bf(rng.standard_normal((64, 64)).astype(np.float32))       # [q = 64][D = 64]
-    expt = (Pq.float().T @ dO.float()).numpy()
-    a_img = np.concatenate([img(Pq[:, :64].contiguous(), 2), img(Pq[:, 64:].contiguous(), 2)])
-    idt = pm.idesc(1, 1, 1, 1, 1, 128, 64)
-    for name, lbo, sbo in (("lbo8192_sbo1024", 8192, 1024), ("lbo1024_sbo8192", 1024, 8192)):
-        got = pm.run_mma(a_img, img(dO, 2), 64, idesc_v=idt, kind=0, n_mma=4, a_lbo=lbo, a_sbo=sbo, a_kstep=2048,
-                         b_lbo=16, b_sbo=1024, b_kstep=2048)
-        res["bf16_A_mnmajor_2atoms_" + name] = float(np.abs(got.numpy().view(np.float32) - expt).max())
-    REPORT["f16"] = res
-    _save()
-    assert res["f16_kmajor_sw128"] < 1e-2, res
+    print(json.dumps(res, indent=1))
+    ok = lambda v: (v is True) or (isinstance(v, float) and v < 2e-2)
+    for must in ("i8_kmajor_sw128", "i8_kmajor_sw64", "f16_kmajor_sw128"):
+        assert ok(res.get(must)), res
+    assert any(ok(v) for k, v in res.items() if k.startswith("i8_Bmn_sw128")), res
+    assert any(ok(v) for k, v in res.items() if k.startswith("bf16_Bmn_2atoms")), res
