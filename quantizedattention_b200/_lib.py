@@ -20,6 +20,9 @@ SIGNATURES = {
     "qa_k_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_quant_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "qa_int8_fwd": (c_int, [c_void_p] * 12 + [c_int] * 7 + [c_void_p]),
+    "qa_int8_bwd": (c_int, [c_void_p] * 14 + [c_int] * 5 + [c_void_p]),
+    "qa_bwd_delta": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]),
+    "qa_cast_f32": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "qa_probe_mma": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_uint] + [c_int] * 6 + [c_void_p]),
     "qa_probe_tma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }

@@ -63,3 +63,79 @@ def baseline_pytorch_attention(q, k, v, head_dim, causal):
         p = torch.where(mask[None, None] > 0, p, -128 * torch.log(torch.tensor([2], device=q.device)))
     p = torch.softmax(p.to(torch.float32), dim=-1).to(torch.float32)
     return torch.matmul(p, v)
+
+
+def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8_T, k_mean_bh_fp16, sk_bh_fp16,
+                                 v_bh_int8, sv_bh_fp16, O_input_fp16, lse_input_fp16, Bq: int, Bkv: int):
+    """Quantised backward (attention_int8.py:268-432 under the 8-LEDGER contract).  Same argument order as the
+    reference; `k_mean` is the per-head token mean [B,H,1,D]; `lse` may be the fp16 tensor the forward returned
+    or an fp32 copy (LEDGER I-15).  Returns (dq, dk, dv) fp16 [B,H,S,D]."""
+    batch, head, q_tokens, head_dim = O_input_fp16.shape
+    N = batch * head * q_tokens
+    assert q_bh_int8.shape == (N, head_dim) and k_bh_int8_T.shape == (head_dim, N), "q/k int8 shapes"
+    if Bq != 128 or Bkv != 128:
+        raise ValueError("backward needs Bq = Bkv = 128 (int32 accumulation depth, SURVEY.md 7 hard part 3)")
+    k_i8 = k_bh_int8_T.t()
+    if not k_i8.is_contiguous():
+        k_i8 = k_i8.contiguous()
+    dO = dO_input_fp16.contiguous()
+    if dO.dtype != torch.float16:
+        dO = dO.to(torch.float16)
+    delta = ops.bwd_delta(dO, O_input_fp16)
+    do_i8, s_do = ops.quant_block(dO, Bq)
+    lse32 = lse_input_fp16.to(torch.float32).contiguous()
+    km = None
+    if k_mean_bh_fp16 is not None:
+        assert k_mean_bh_fp16.numel() == batch * head * head_dim, "k_mean must be the per-head token mean [B,H,1,D]"
+        km = k_mean_bh_fp16.to(torch.float16).contiguous()
+    dq, dk, dv = ops.int8_bwd_prequant(q_bh_int8.contiguous(), k_i8, v_bh_int8.contiguous(), do_i8, sq_bh_fp16,
+                                       sk_bh_fp16, sv_bh_fp16, s_do, lse32, delta, km, batch * head, q_tokens, head_dim,
+                                       Bq, Bkv)
+    shp = (batch, head, q_tokens, head_dim)
+    return dq.view(shp), dk.view(shp), dv.view(shp)
+
+
+class SageAttention3_Int8_autograd_function(Function):
+    """attention_int8.py:20-95.  forward(q,k,v) -> 11-tuple
+    (O, lse fp16 [N], k_mean [B,H,1,D], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv)."""
+
+    @staticmethod
+    def forward(q_fp16, k_fp16, v_fp16):
+        for t in (q_fp16, k_fp16, v_fp16):
+            if t.dtype != torch.float16:
+                raise TypeError("int8 attention takes fp16 q, k, v")
+        batch, head, q_tokens, D = q_fp16.shape
+        k_tokens = k_fp16.shape[2]
+        Bq, Bkv = _CFG["Bq"], _CFG["Bkv"]
+        k_mean_fp16 = ops.k_mean(k_fp16)                                       # K-smoothing (LEDGER I-1)
+        q_i8, sq = ops.quant_block(q_fp16, Bq)
+        k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean_fp16, rows_per_head=k_tokens)   # fused k - mean
+        v_i8, sv = ops.quant_block(v_fp16, Bkv)
+        O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
+                                                nsplit=_CFG["nsplit"], want_lse32=True)
+        SageAttention3_Int8_autograd_function._lse32_stash = lse32             # picked up by setup_context
+        return (O.view(batch, head, q_tokens, D), lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv = output
+        ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv)
+        lse32 = SageAttention3_Int8_autograd_function._lse32_stash
+        SageAttention3_Int8_autograd_function._lse32_stash = None
+        ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
+        ctx.args = (Bq, Bkv)
+
+    @staticmethod
+    def backward(ctx, dO_fp16, *_ignored):
+        O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32 = ctx.saved_tensors
+        Bq, Bkv = ctx.args
+        dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
+                                                  O_fp16, lse32 if lse32 is not None else l_bh_fp16, Bq, Bkv)
+        return dq, dk, dv
+
+    _lse32_stash = None
+
+
+def sage_attention_3_int8(q_fp16, k_fp16, v_fp16):
+    """attention_int8.py:434-451: returns O fp16 [B,H,S,D], differentiable w.r.t. q, k, v."""
+    return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16)[0]

@@ -75,3 +75,49 @@ def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=1
     if ring_state:
         return o_acc, m, l
     return O, lse16, lse32
+
+
+def bwd_delta(dO: torch.Tensor, O: torch.Tensor, want_bf16_copy: bool = False):
+    """delta = rowsum(dO * O) in fp32 (qa_bwd_delta).  fp16 inputs (int8 path) or fp32 inputs (bf16 path, where a
+    bf16 copy of dO can be emitted in the same pass)."""
+    _need_cuda(dO, O)
+    D = dO.shape[-1]
+    dO2, O2 = dO.contiguous().view(-1, D), O.contiguous().view(-1, D)
+    assert dO2.dtype == O2.dtype and dO2.dtype in (torch.float16, torch.float32)
+    n = dO2.shape[0]
+    delta = torch.empty((n,), dtype=torch.float32, device=dO.device)
+    copy = torch.empty((n, D), dtype=torch.bfloat16, device=dO.device) if want_bf16_copy else None
+    L = _lib.lib()
+    with torch.cuda.device(dO.device):
+        _lib.check(L.qa_bwd_delta(_lib.ptr(dO2), _lib.ptr(O2), _lib.ptr(delta), _lib.ptr(copy), n, D,
+                                  0 if dO2.dtype == torch.float16 else 1, _lib.cur_stream()), "qa_bwd_delta")
+    return (delta, copy) if want_bf16_copy else delta
+
+
+def cast_f32(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 -> fp16 / bf16 (qa_cast_f32)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and dtype in (torch.float16, torch.bfloat16)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        _lib.check(L.qa_cast_f32(_lib.ptr(x), _lib.ptr(out), x.numel(), 0 if dtype == torch.float16 else 1,
+                                 _lib.cur_stream()), "qa_cast_f32")
+    return out
+
+
+def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128):
+    """Fused int8 backward over pre-quantised operands (qa_int8_bwd).  Returns (dq, dk, dv) fp16 [BH*S, D]."""
+    _need_cuda(q_i8, k_i8, v_i8, do_i8)
+    dev = q_i8.device
+    dq_ws = torch.zeros((BH * S, D), dtype=torch.float32, device=dev)
+    dk = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    dv = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
+                                 _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(k_mean),
+                                 _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _lib.cur_stream()),
+                   "qa_int8_bwd")
+    return cast_f32(dq_ws, torch.float16), dk, dv

@@ -1,0 +1,55 @@
+"""Parity of the fused int8 backward against the contract oracle and fp32 autograd."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0).item()
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128)])
+def test_int8_bwd_matches_contract_oracle(shape):
+    from oracle import int8_ref
+    from quantizedattention_b200 import attention_int8 as A
+    B, H, S, D = shape
+    g = torch.Generator().manual_seed(2000 + S + D)
+    q, k, v, dO = [torch.randn(shape, generator=g).to(torch.float16) for _ in range(4)]
+    k = (k.float() + 1.0).to(torch.float16)                 # non-zero token mean: exercises the k_mean term
+    out = A.SageAttention3_Int8_autograd_function.forward(q.cuda(), k.cuda(), v.cuda())
+    A.SageAttention3_Int8_autograd_function._lse32_stash = None
+    O, lse16, kmean, q_i8, k_i8_T, v_i8, sq, sk, sv, Bq, Bkv = out
+    # oracle on the SAME saved tensors (so only the backward is compared)
+    c = lambda t: t.cpu()
+    ref = int8_ref.int8_bwd_contract(dO, c(q_i8), c(sq), c(k_i8_T), c(kmean), c(sk), c(v_i8), c(sv), c(O), c(lse16), Bq, Bkv)
+    got = A.helion_atten_int8_hl_dot_bwd(dO.cuda(), q_i8, sq, k_i8_T, kmean, sk, v_i8, sv, O, lse16, Bq, Bkv)
+    torch.cuda.synchronize()
+    for name, a, b in zip(("dq", "dk", "dv"), got, ref):
+        assert _cos(a.cpu(), b) > 0.9995 and _rel(a.cpu(), b) < 3e-2, (name, _cos(a.cpu(), b), _rel(a.cpu(), b))
+
+
+def test_sage_attention_autograd_end_to_end():
+    """sage_attention_3_int8(...).backward() against fp32 PyTorch attention + autograd (the reference's own
+    comparison, attention_int8.py:517-528, with dO ~ N(0,1) instead of the vacuous mse_loss gradients)."""
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_int8 as A
+    shape = (2, 4, 512, 128)
+    g = torch.Generator().manual_seed(77)
+    q, k, v, dO = [torch.randn(shape, generator=g) for _ in range(4)]
+    qh, kh, vh = [t.to(torch.float16).cuda().requires_grad_() for t in (q, k, v)]
+    O = A.sage_attention_3_int8(qh, kh, vh)
+    assert O.dtype == torch.float16 and O.shape == shape
+    O.backward(dO.to(torch.float16).cuda())
+    qf, kf, vf = [t.to(torch.float16).float().requires_grad_() for t in (q, k, v)]
+    Ob = baseline_pytorch_attention(qf, kf, vf, shape[3], False)
+    Ob.backward(dO.to(torch.float16).float())
+    assert (O.detach().cpu().float() - Ob.detach()).abs().max() < 8e-2
+    for name, a, b in zip("qkv", (qh, kh, vh), (qf, kf, vf)):
+        assert a.grad.dtype == torch.float16
+        cs, rl = _cos(a.grad.cpu(), b.grad), _rel(a.grad.cpu(), b.grad)
+        assert cs > 0.99 and rl < 0.2, (name, cs, rl)      # survey probe (128/128 blocks): cos 0.994-0.997, rel 0.12-0.15
