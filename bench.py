@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200: int8 SageAttention3-style attention forward + backward at
+BASELINE.json configs[2] (B=8, H=32, S=8192, D=128, non-causal), the configuration the headline metric
+("attention fwd/bwd TOPS/GPU and % tensor peak at S=8k, D=128") is quoted on.
+
+  python bench.py --gpus N --steps K --warmup W          our arm   (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                   reference arm: the reference's PyTorch attention math
+                                                         (baseline_pytorch_attention + autograd) on the host CPU
+
+One "step" = one forward + backward pass of `sage_attention_3_int8` over one batch of synthetic fp16 q/k/v/dO:
+K-mean, 4 block quantisations, fused int8 forward, delta pre-pass, fused int8 backward, dQ cast.
+value  : whole-job TOPS (4+10)*B*H*S^2*D ops per step per GPU, inputs resident in HBM.
+e2e    : same metric through the public API with pinned HOST buffers, H2D of q/k/v/dO and D2H of O/dq/dk/dv
+         inside the timed region.
+Multi-GPU: batch x head sharding, no collective on the data path; every rank runs the full per-GPU workload
+(weak scaling), time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=8, H=32, S=8192, D=128)
+OPS_FWD = lambda B, H, S, D: 4.0 * B * H * S * S * D
+OPS_BWD = lambda B, H, S, D: 10.0 * B * H * S * S * D
+
+
+def peaks():
+    p = {}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    int8 = None
+    try:
+        int8 = json.load(open(os.path.join(ROOT, "profiles", "r01_peaks.json"))).get("int8_tops_int_mm")
+    except Exception:  # noqa: BLE001
+        pass
+    return p, int8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_attention_fwd_bwd(q, k, v, dO, threads, group=4):
+    """The reference's PyTorch attention math (oracle/baseline.py restates attention_int8.py:453-481) + autograd,
+    over all heads of q in groups of `group` heads ([S,S] fp32 scores are 256 MiB per head)."""
+    from oracle.baseline import baseline_pytorch_attention
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    for h0 in range(0, q.shape[1], group):
+        qf, kf, vf = [t[:, h0:h0 + group].float().requires_grad_() for t in (q, k, v)]
+        O = baseline_pytorch_attention(qf, kf, vf, q.shape[-1], False)
+        O.backward(dO[:, h0:h0 + group].float())
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: CPU PyTorch attention math on a bounded sample of the workload (heads of S=8192, D=128)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B, H, S, D = CFG["B"], CFG["H"], CFG["S"], CFG["D"]
+    heads = args.ref_heads
+    g = torch.Generator().manual_seed(1003)
+    q, k, v, dO = [torch.randn(1, heads, S, D, generator=g).to(torch.float16) for _ in range(4)]
+    for _ in range(args.warmup):
+        cpu_attention_fwd_bwd(q, k, v, dO, threads)
+    ts = [cpu_attention_fwd_bwd(q, k, v, dO, threads) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    ops = OPS_FWD(1, heads, S, D) + OPS_BWD(1, heads, S, D)
+    val = ops / t / 1e12
+    sample = f"{heads} of {B * H} heads per step (S={S}, D={D}), fp32 PyTorch math fwd+bwd, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "attention fwd+bwd throughput at S=8k, D=128", "value": val, "unit": "TOPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * (B * H / heads),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "int8 attention fwd+bwd B=8 H=32 S=8192 D=128 non-causal (BASELINE configs[2])",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "TOPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-heads", type=int, default=32, help="heads per CPU reference step (bounded sample)")
+    ap.add_argument("--cpu-heads", type=int, default=96, help="heads in the cpu_baseline sample of our arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from quantizedattention_b200 import attention_int8 as A
+    from quantizedattention_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, H, S, D = CFG["B"], CFG["H"], CFG["S"], CFG["D"]
+    W, K = max(args.warmup, 3), args.steps
+    g = torch.Generator().manual_seed(1003 + rank)
+    host = [torch.randn(B, H, S, D, generator=g).to(torch.float16).pin_memory() for _ in range(4)]   # q, k, v, dO
+    q, k, v, dO = [t.to(dev) for t in host]
+    ops_step = OPS_FWD(B, H, S, D) + OPS_BWD(B, H, S, D)
+
+    def step():
+        qr, kr, vr = q.detach().requires_grad_(), k.detach().requires_grad_(), v.detach().requires_grad_()
+        O = A.sage_attention_3_int8(qr, kr, vr)
+        O.backward(dO)
+        return O, qr.grad, kr.grad, vr.grad
+
+    for _ in range(W):
+        step()
+    # ---- timed region 1: inputs resident in HBM (inputs 2 GiB >> 126 MB L2, so every step streams from HBM)
+    ops.TIMING = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    timing, ops.TIMING = ops.TIMING, None
+    kt = {}
+    for name, a, b in timing:
+        kt.setdefault(name, []).append(a.elapsed_time(b))
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = t_ms.item() / K
+    value = ops_step * world / (ms_step * 1e-3) / 1e12
+
+    # ---- timed region 2 (e2e): host buffers -> device -> public API -> results back to pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        outs_host = [torch.empty(B, H, S, D, dtype=torch.float16).pin_memory() for _ in range(4)]
+
+        def step_e2e():
+            dq_, dk_, dv_, ddo = [t.to(dev, non_blocking=True) for t in host]
+            qr, kr, vr = dq_.requires_grad_(), dk_.requires_grad_(), dv_.requires_grad_()
+            O = A.sage_attention_3_int8(qr, kr, vr)
+            O.backward(ddo)
+            for dst, src in zip(outs_host, (O.detach(), qr.grad, kr.grad, vr.grad)):
+                dst.copy_(src, non_blocking=True)
+
+        step_e2e()
+        barrier()
+        Ke = max(2, min(K, 5))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(Ke):
+            step_e2e()
+        f1.record()
+        barrier()
+        te = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        nbytes = 4 * B * H * S * D * 2
+        e2e = {"value": ops_step * world / (te.item() / Ke * 1e-3) / 1e12, "unit": "TOPS",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": Ke}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    mp, int8_peak = peaks()
+    avg = lambda xs: sum(xs) / len(xs)
+    bwd_ms, fwd_ms = avg(kt["int8_bwd"]), avg(kt["int8_fwd"])
+    peak = int8_peak or 2.0 * mp.get("bf16_tflops", 1590.0)
+    roof = {"bound": "tensor", "kernel": "int8_bwd_kernel<128>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
+            "peak": peak, "unit": "TFLOP/s", "traffic": None,
+            "peak_source": "int8 dense: torch._int_mm 8192^3 best-of-10 on this pool (profiles/r01_peaks.json); "
+                           "MEASURED_PEAKS.json has no int8 entry (its bf16 burst x2 = %.0f)" % (2 * mp.get("bf16_tflops", 0)),
+            "share_of_step": bwd_ms / ms_step,
+            "other_kernels": {"int8_fwd_kernel<128,2,3>": {"ms": fwd_ms, "achieved": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12,
+                                                           "frac": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12 / peak}}}
+    roof["frac"] = roof["achieved"] / peak
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        hs = args.cpu_heads
+        gq = torch.Generator().manual_seed(1003)
+        cq, ck, cv, cdo = [torch.randn(1, hs, S, D, generator=gq).to(torch.float16) for _ in range(4)]
+        t = cpu_attention_fwd_bwd(cq, ck, cv, cdo, threads)
+        cpu = {"value": (OPS_FWD(1, hs, S, D) + OPS_BWD(1, hs, S, D)) / t / 1e12, "unit": "TOPS", "cores": threads,
+               "kind": "port", "sample": f"{hs} of {B * H} heads (S={S}, D={D}), fp32 PyTorch attention math fwd+bwd, one pass, {t:.1f} s"}
+
+    print(json.dumps({
+        "metric": "attention fwd+bwd throughput at S=8k, D=128", "value": value, "unit": "TOPS", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8", "data": "synthetic",
+        "config": {"workload": "int8 attention fwd+bwd B=8 H=32 S=8192 D=128 non-causal (BASELINE configs[2]) per GPU",
+                   "Bq": 128, "Bkv": 128, "parallelism": f"batch x head sharded, {world} rank(s), no collective",
+                   "l2": "inputs 2 GiB per step >> 126 MB L2 (no explicit flush)",
+                   "ops_per_step_per_gpu": ops_step, "flop_convention": "fwd 4*B*H*S^2*D + bwd 10*B*H*S^2*D"},
+        "per_gpu_tops": value / world, "frac_of_int8_peak_measured": value / world / peak,
+        "frac_of_int8_peak_spec_4500": value / world / 4500.0,
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": 11 * K,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

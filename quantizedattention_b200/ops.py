@@ -10,6 +10,29 @@ import torch
 from . import _lib
 
 
+# Optional kernel timing hook: set `TIMING = []` and every hot kernel launch appends (name, start_evt, end_evt)
+# recorded on the launching (current) stream; bench.py uses it for the live roofline measurement.
+TIMING = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.b.record()
+            TIMING.append((self.name, self.a, self.b))
+        return False
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -68,7 +91,7 @@ def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=1
         lse16 = torch.empty((BH * Sq,), dtype=torch.float16, device=dev)
         lse32 = torch.empty((BH * Sq,), dtype=torch.float32, device=dev) if want_lse32 else None
         o_acc = m = l = None
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("int8_fwd"):
         _lib.check(L.qa_int8_fwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk), _lib.ptr(sv),
                                  _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc), _lib.ptr(m), _lib.ptr(l),
                                  BH, Sq, Sk, D, Bq, Bkv, nsplit, _lib.cur_stream()), "qa_int8_fwd")
@@ -115,7 +138,7 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
     dk = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
     dv = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("int8_bwd"):
         _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
                                  _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(k_mean),
                                  _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _lib.cur_stream()),
