@@ -23,6 +23,9 @@ SIGNATURES = {
     "qa_int8_bwd": (c_int, [c_void_p] * 14 + [c_int] * 5 + [c_void_p]),
     "qa_bwd_delta": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]),
     "qa_cast_f32": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "qa_bf16_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "qa_jvp_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
+    "qa_bf16_bwd": (c_int, [c_void_p] * 10 + [c_int] * 4 + [c_void_p]),
     "qa_probe_mma": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_uint] + [c_int] * 6 + [c_void_p]),
     "qa_probe_tma": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }

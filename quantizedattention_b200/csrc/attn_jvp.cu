@@ -1,0 +1,329 @@
+// Forward-mode JVP attention (reference attention_jvp.py:129-190) for sm_100a.
+// Emits O, tO and the log2-LSE.  Six contractions per (query tile, key tile), all tcgen05 kind::f16 with bf16
+// operands and fp32 TMEM accumulators (LEDGER J-2; operands are converted fp32 -> bf16 by qa_cast_f32):
+//   S  = Q K^T                      (TMEM cols   0..127)
+//   tS = tQ K^T + Q tK^T            (TMEM cols 128..255, two chained MMAs into one accumulator)
+//   Opart  = P V                    (TMEM cols 256..)
+//   ABpart = P tV + H V, H = P*tS   (TMEM cols 384.., two chained MMAs: A and B of the reference share one tile)
+// Softmax state (m, l, r = rowsum(H)) is fp32 as in the reference.  tO = (AB - r*O) / l,  O = O / l.
+#include "qa_ptx.cuh"
+#include "qa_host.h"
+
+namespace qa {
+
+constexpr int kJAtom = 128 * 128;
+
+template <int D>
+struct JvpSmem {
+  static constexpr int kTile = 128 * D * 2;
+  static constexpr int kPBytes = 128 * 128 * 2;
+  static constexpr int off_q = 0;                       // Q, tQ
+  static constexpr int off_k = off_q + 2 * kTile;       // 2 stages x (K, tK)
+  static constexpr int off_v = off_k + 4 * kTile;       // 1 stage  x (V, tV)
+  static constexpr int off_p = off_v + 2 * kTile;       // P, H
+  static constexpr int total = off_p + 2 * kPBytes + 1024;
+};
+
+struct JvpParams {
+  float *O, *tO, *lse;
+  int Sq, Sk;
+  float sm_scale, qk_scale;
+};
+
+__device__ __forceinline__ uint32_t jpack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int D, int NSPLIT>
+__global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
+jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_tq,
+               const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_tk,
+               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_tv, JvpParams p) {
+  using L = JvpSmem<D>;
+  constexpr int NC = 128 / NSPLIT;
+  constexpr int DC = D / NSPLIT;
+  constexpr int kSoftWarps = 4 * NSPLIT;
+  constexpr int kDAtoms = D / 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty;
+  __shared__ uint64_t s_full, s_empty, p_full, p_empty, o_full, o_empty, sc_full, sc_empty, fin_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float row_sc[128];
+  __shared__ float xmax[2][2][128];
+  __shared__ float l_part[2][128], r_part[2][128], m_fin[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, q0 = blockIdx.x * 128;
+  const int nk = p.Sk / 128;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
+    mbar_init(&s_full, 1); mbar_init(&s_empty, kSoftWarps);
+    mbar_init(&p_full, kSoftWarps); mbar_init(&p_empty, 1);
+    mbar_init(&o_full, 1); mbar_init(&o_empty, kSoftWarps);
+    mbar_init(&sc_full, 4); mbar_init(&sc_empty, kSoftWarps);
+    mbar_init(&fin_full, kSoftWarps);
+    fence_mbar_init();
+  }
+  if (warp == 8 * NSPLIT + 1) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp < kSoftWarps) {
+    // =========================== softmax warps ===========================
+    const int split = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const int c0 = split * NC;
+    float m = -INFINITY, l = 0.f, racc = 0.f;                    // attention_jvp.py:130-134
+    for (int j = 0; j < nk; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(&s_full, ph);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + c0 + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      if (NSPLIT == 2) {
+        xmax[ph][split][row] = mx;
+        named_bar_sync(1, 128 * NSPLIT);
+        mx = fmaxf(mx, xmax[ph][split ^ 1][row]);
+      }
+      const float m_new = fmaxf(m, mx * p.qk_scale);             // :155-158
+      const float resc = ex2_approx(m - m_new);                   // :164
+      m = m_new;
+      if (split == 0) {
+        mbar_wait(&sc_empty, ph ^ 1);
+        row_sc[row] = resc;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_full);
+      }
+      mbar_wait(&p_empty, ph ^ 1);
+      float lsum = 0.f, hsum = 0.f;
+      uint8_t* pbase = smem + L::off_p;
+      uint8_t* hbase = smem + L::off_p + L::kPBytes;
+#pragma unroll
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        uint32_t rs[32], rt[32];
+        tmem_ld32(lane_addr + c0 + ch * 32, rs);
+        tmem_ld32(lane_addr + 128 + c0 + ch * 32, rt);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t wp[4], wh[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = g * 8 + e * 2;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[i]), p.qk_scale, -m_new));        // :160-161
+            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[i + 1]), p.qk_scale, -m_new));
+            const float h0 = p0 * (__uint_as_float(rt[i]) * p.sm_scale);                           // :153, :176
+            const float h1 = p1 * (__uint_as_float(rt[i + 1]) * p.sm_scale);
+            lsum += p0 + p1;
+            hsum += h0 + h1;
+            wp[e] = jpack_bf16(p0, p1);
+            wh[e] = jpack_bf16(h0, h1);
+          }
+          const int col = c0 + ch * 32 + g * 8;
+          const uint32_t off = (uint32_t)(col >> 6) * kJAtom + swz128(row, (col & 63) * 2);
+          *reinterpret_cast<uint4*>(pbase + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<uint4*>(hbase + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        }
+      }
+      tc_fence_before();
+      l = l * resc + lsum;                                        // :165
+      racc = racc * resc + hsum;                                  // :178
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&s_empty); mbar_arrive(&p_full); }
+    }
+    l_part[split][row] = l;
+    r_part[split][row] = racc;
+    if (split == 0) m_fin[row] = m;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&fin_full);
+  } else if (warp < 2 * kSoftWarps) {
+    // =========================== correction warps ===========================
+    const int cw = warp - kSoftWarps;
+    const int split = cw >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const int d0 = split * DC;
+    float accO[DC], accT[DC];
+#pragma unroll
+    for (int i = 0; i < DC; ++i) { accO[i] = 0.f; accT[i] = 0.f; }
+    for (int j = 0; j < nk; ++j) {
+      const uint32_t ph = j & 1;
+      mbar_wait(&sc_full, ph);
+      const float resc = row_sc[row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sc_empty);
+      mbar_wait(&o_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < DC / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + 256 + d0 + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) accO[ch * 32 + i] = fmaf(accO[ch * 32 + i], resc, __uint_as_float(r[i]));
+        tmem_ld32(lane_addr + 384 + d0 + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) accT[ch * 32 + i] = fmaf(accT[ch * 32 + i], resc, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty);
+    }
+    mbar_wait(&fin_full, 0);
+    float l = l_part[0][row], rr = r_part[0][row];
+    if (NSPLIT == 2) { l += l_part[1][row]; rr += r_part[1][row]; }
+    const size_t gr = (size_t)bh * p.Sq + q0 + row;
+    const float inv_l = 1.0f / l;
+    float* dO_ = p.O + gr * D + d0;
+    float* dT_ = p.tO + gr * D + d0;
+#pragma unroll
+    for (int i = 0; i < DC; i += 4) {
+      float o[4], t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e] = accO[i + e] * inv_l;                               // :188
+        t[e] = (accT[i + e] - rr * o[e]) * inv_l;                 // :190  (A + B - r*O) / l
+      }
+      *reinterpret_cast<float4*>(dO_ + i) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dT_ + i) = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    if (split == 0) p.lse[gr] = m_fin[row] + log2f(l);            // :183
+  } else if (warp == 8 * NSPLIT) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      mbar_expect_tx(&q_full, 2 * L::kTile);
+#pragma unroll
+      for (int a = 0; a < kDAtoms; ++a) {
+        tma_load_2d(smem + L::off_q + a * kJAtom, &tm_q, &q_full, a * 64, bh * p.Sq + q0);
+        tma_load_2d(smem + L::off_q + L::kTile + a * kJAtom, &tm_tq, &q_full, a * 64, bh * p.Sq + q0);
+      }
+      for (int j = 0; j < nk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[s], 2 * L::kTile);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a) {
+          tma_load_2d(smem + L::off_k + s * 2 * L::kTile + a * kJAtom, &tm_k, &k_full[s], a * 64, bh * p.Sk + j * 128);
+          tma_load_2d(smem + L::off_k + s * 2 * L::kTile + L::kTile + a * kJAtom, &tm_tk, &k_full[s], a * 64, bh * p.Sk + j * 128);
+        }
+        mbar_wait(&v_empty, (j & 1) ^ 1);
+        mbar_expect_tx(&v_full, 2 * L::kTile);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a) {
+          tma_load_2d(smem + L::off_v + a * kJAtom, &tm_v, &v_full, a * 64, bh * p.Sk + j * 128);
+          tma_load_2d(smem + L::off_v + L::kTile + a * kJAtom, &tm_tv, &v_full, a * 64, bh * p.Sk + j * 128);
+        }
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc(1, 1, 1, 0, 0, 128, 128);        // bf16 x bf16 -> f32, K-major
+      constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // B MN-major
+      const uint32_t q_addr = smem_u32(smem + L::off_q), tq_addr = q_addr + L::kTile;
+      const uint32_t p_addr = smem_u32(smem + L::off_p), h_addr = p_addr + L::kPBytes;
+      const uint32_t v_addr = smem_u32(smem + L::off_v), tv_addr = v_addr + L::kTile;
+      auto issue_pv = [&](int t) {
+        const uint32_t ph = t & 1;
+        mbar_wait(&v_full, ph);
+        mbar_wait(&o_empty, ph ^ 1);
+        mbar_wait(&p_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t ao = (k >> 2) * kJAtom + (k & 3) * 32;
+          const uint64_t pd = umma_smem_desc(p_addr + ao, 16, 1024, kSwz128);
+          const uint64_t hd = umma_smem_desc(h_addr + ao, 16, 1024, kSwz128);
+          const uint64_t vd = umma_smem_desc(v_addr + k * 2048, kJAtom, 1024, kSwz128);
+          const uint64_t tvd = umma_smem_desc(tv_addr + k * 2048, kJAtom, 1024, kSwz128);
+          umma_f16_ss(tbase + 256, pd, vd, idesc_pv, k > 0);        // Opart  = P V
+          umma_f16_ss(tbase + 384, pd, tvd, idesc_pv, k > 0);       // ABpart = P tV
+          umma_f16_ss(tbase + 384, hd, vd, idesc_pv, 1);            //        + H V
+        }
+        umma_commit(&o_full);
+        umma_commit(&v_empty);
+        umma_commit(&p_empty);
+      };
+      mbar_wait(&q_full, 0);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&k_full[s], (j >> 1) & 1);
+        mbar_wait(&s_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + L::off_k + s * 2 * L::kTile), tk_addr = k_addr + L::kTile;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t o = (k >> 2) * kJAtom + (k & 3) * 32;
+          const uint64_t qd = umma_smem_desc(q_addr + o, 16, 1024, kSwz128), tqd = umma_smem_desc(tq_addr + o, 16, 1024, kSwz128);
+          const uint64_t kd = umma_smem_desc(k_addr + o, 16, 1024, kSwz128), tkd = umma_smem_desc(tk_addr + o, 16, 1024, kSwz128);
+          umma_f16_ss(tbase + 0, qd, kd, idesc_qk, k > 0);          // S
+          umma_f16_ss(tbase + 128, tqd, kd, idesc_qk, k > 0);       // tS  = tQ K^T
+          umma_f16_ss(tbase + 128, qd, tkd, idesc_qk, 1);           //     + Q tK^T
+        }
+        umma_commit(&s_full);
+        umma_commit(&k_empty[s]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(nk - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
+}
+
+template <int D, int NSPLIT>
+static int launch_jvp(const void* const* in6, const JvpParams& p, int BH, cudaStream_t st) {
+  using L = JvpSmem<D>;
+  CUtensorMap tm[6];
+  uint64_t str[1] = {(uint64_t)D * 2};
+  uint32_t box[2] = {64, 128};
+  for (int i = 0; i < 6; ++i) {
+    uint64_t dims[2] = {(uint64_t)D, (uint64_t)BH * (i < 2 ? p.Sq : p.Sk)};
+    int rc = qa_make_tmap(&tm[i], in6[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3);
+    if (rc) return rc;
+  }
+  auto kern = jvp_fwd_kernel<D, NSPLIT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  dim3 grid(p.Sq / 128, BH);
+  kern<<<grid, 256 * NSPLIT + 64, L::total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  return qa_check_launch("qa_jvp_fwd");
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+// q, tq: bf16 [BH*Sq, D]; k, tk, v, tv: bf16 [BH*Sk, D]; O, tO: fp32 [BH*Sq, D]; lse: fp32 [BH*Sq].
+extern "C" int qa_jvp_fwd(const void* q, const void* tq, const void* k, const void* tk, const void* v, const void* tv,
+                          void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit, void* stream) {
+  if (D != 64) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: D must be 64 (TMEM budget: S, tS, Opart, ABpart)");
+  if (Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: Sq, Sk must be multiples of 128");
+  const void* in6[6] = {q, tq, k, tk, v, tv};
+  for (int i = 0; i < 6; ++i)
+    if ((uintptr_t)in6[i] & 15) return qa_fail(QA_ERR_ALIGN, "qa_jvp_fwd: 16-byte alignment required");
+  JvpParams p;
+  p.O = (float*)O_f32; p.tO = (float*)tO_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk;
+  p.sm_scale = (float)(1.0 / sqrt((double)D));
+  p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  cudaStream_t st = (cudaStream_t)stream;
+  return nsplit == 2 ? launch_jvp<64, 2>(in6, p, BH, st) : launch_jvp<64, 1>(in6, p, BH, st);
+}

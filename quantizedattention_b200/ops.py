@@ -33,6 +33,27 @@ class _timed:
         return False
 
 
+def _unwrap(t):
+    """Strip functorch wrappers (torch.func.jvp hands GradTrackingTensors to Function.jvp) to reach the storage."""
+    F = torch._C._functorch
+    while t is not None and (F.is_gradtrackingtensor(t) or F.is_batchedtensor(t) or F.is_functionaltensor(t)):
+        t = F.get_unwrapped(t)
+    return t
+
+
+class _raw_mode:
+    """Run raw-pointer kernels below any active functorch transform (inside Function.jvp under torch.func.jvp every
+    torch op would otherwise re-wrap its outputs)."""
+
+    def __enter__(self):
+        from torch._functorch.pyfunctorch import temporarily_clear_interpreter_stack
+        self.cm = temporarily_clear_interpreter_stack()
+        return self.cm.__enter__()
+
+    def __exit__(self, *exc):
+        return self.cm.__exit__(*exc)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -144,3 +165,61 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
                                  _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _lib.cur_stream()),
                    "qa_int8_bwd")
     return cast_f32(dq_ws, torch.float16), dk, dv
+
+
+def bf16_fwd(q, k, v, causal: bool, nsplit: int = 2):
+    """Bias-corrected bf16 flash attention forward (qa_bf16_fwd).  q,k fp16, v bf16 [B,H,S,D] ->
+    (O fp32 [B,H,Sq,D], lse fp32 [B*H,Sq])."""
+    _need_cuda(q, k, v)
+    B, H, Sq, D = q.shape
+    Sk = k.shape[2]
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    O = torch.empty((B, H, Sq, D), dtype=torch.float32, device=q.device)
+    lse = torch.empty((B * H, Sq), dtype=torch.float32, device=q.device)
+    L = _lib.lib()
+    with torch.cuda.device(q.device), _timed("bf16_fwd"):
+        _lib.check(L.qa_bf16_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
+                                 1 if causal else 0, nsplit, _lib.cur_stream()), "qa_bf16_fwd")
+    return O, lse
+
+
+def jvp_fwd(q, k, v, tq, tk, tv, nsplit: int = 2):
+    """Forward-mode JVP attention (qa_jvp_fwd).  Six fp32 [B,H,S,D] tensors -> (O, tO fp32 [B,H,Sq,D], lse [B*H,Sq]).
+    Operands are rounded to bf16 for the tensor cores (fp32 accumulation)."""
+    q, k, v, tq, tk, tv = [_unwrap(t) for t in (q, k, v, tq, tk, tv)]
+    _need_cuda(q, k, v, tq, tk, tv)
+    with _raw_mode():
+        B, H, Sq, D = q.shape
+        Sk = k.shape[2]
+        b16 = [cast_f32(t, torch.bfloat16) if t.dtype == torch.float32 else t.to(torch.bfloat16).contiguous()
+               for t in (q, tq, k, tk, v, tv)]
+        O = torch.empty((B, H, Sq, D), dtype=torch.float32, device=q.device)
+        tO = torch.empty_like(O)
+        lse = torch.empty((B * H, Sq), dtype=torch.float32, device=q.device)
+        L = _lib.lib()
+        with torch.cuda.device(q.device), _timed("jvp_fwd"):
+            _lib.check(L.qa_jvp_fwd(*[_lib.ptr(t) for t in b16], _lib.ptr(O), _lib.ptr(tO), _lib.ptr(lse), B * H, Sq, Sk, D,
+                                    nsplit, _lib.cur_stream()), "qa_jvp_fwd")
+    return O, tO, lse
+
+
+def bf16_bwd(q, k, v, O, lse, causal: bool, dO):
+    """Recompute backward of the bf16 path (qa_bwd_delta + qa_bf16_bwd).  q,k fp16; v bf16; O, dO fp32 [B,H,S,D];
+    lse fp32 [B*H,S].  Returns fp32 (dq, dk, dv) [B,H,S,D]."""
+    _need_cuda(q, k, v, O, lse, dO)
+    B, H, S, D = q.shape
+    assert k.shape[2] == S, "backward is self-attention only (LEDGER I-11)"
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    dO = dO.to(torch.float32).contiguous()
+    O = O.to(torch.float32).contiguous()
+    lse = lse.to(torch.float32).contiguous()
+    delta, dO_bf16 = bwd_delta(dO, O, want_bf16_copy=True)
+    dq = torch.zeros((B, H, S, D), dtype=torch.float32, device=q.device)
+    dk = torch.empty_like(dq)
+    dv = torch.empty_like(dq)
+    L = _lib.lib()
+    with torch.cuda.device(q.device), _timed("bf16_bwd"):
+        _lib.check(L.qa_bf16_bwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dO_bf16), _lib.ptr(dO), _lib.ptr(lse),
+                                 _lib.ptr(delta), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), B * H, S, D, 1 if causal else 0,
+                                 _lib.cur_stream()), "qa_bf16_bwd")
+    return dq, dk, dv
