@@ -1,0 +1,103 @@
+/* qattn.h -- C ABI of libqattn.so: B200 (sm_100a) kernels for the three fused attention paths of
+ * selau642/QuantizedAttention.  This is the drop-in boundary: the reference's Python kernels are replaced by
+ * calls into these entry points (ctypes binding: quantizedattention_b200/_lib.py).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  The CALLER owns every buffer (inputs, outputs, workspaces are device
+ *     pointers, e.g. torch `tensor.data_ptr()`); the library never allocates or frees device memory and never
+ *     synchronises.  All work is enqueued on `stream` (a cudaStream_t passed as void*) of the current device.
+ *   - Tensors are row-major [B*H*S, D] ("[N, D]") views of the reference's contiguous [B, H, S, D] layout.
+ *   - Return value: 0 on success, negative QA_ERR_* otherwise; qa_last_error() gives the message (thread-local).
+ *   - D in {64, 128}; sequence lengths multiples of 128; 16-byte aligned pointers (TMA).
+ *   - Logits live in the log2 domain: qk_scale = log2(e)/sqrt(D); "lse" is log2-sum-exp2 (attention_int8.py:252).
+ */
+#ifndef QATTN_H
+#define QATTN_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QA_ERR_SHAPE (-1)
+#define QA_ERR_ALIGN (-2)
+#define QA_ERR_WORKSPACE (-3)
+#define QA_ERR_CUDA (-4)
+#define QA_ERR_ARCH (-5)
+#define QA_ERR_DRIVER (-6)
+
+int qa_version(void);
+const char* qa_last_error(void);
+
+/* ---- int8 path pre-passes (replace the per-tile-pair recomputation inside attention_int8.py:178-195, 241-247) ---- */
+
+/* K-smoothing mean, attention_int8.py:24-25 under LEDGER I-1: mean over tokens per (b,h), fp32 accumulate, fp16 out
+ * [B*H, D].  workspace >= qa_k_mean_workspace_bytes(). */
+size_t qa_k_mean_workspace_bytes(int B, int H, int S, int D);
+int qa_k_mean(const void* k_fp16, void* mean_fp16, void* workspace, size_t ws_bytes, int B, int H, int S, int D,
+              void* stream);
+
+/* fp32 token sums [B*H, D] of a sequence shard: the ring-KV path all-reduces these across ranks, divides by the global
+ * sequence length and rounds to fp16, so that every rank smooths K with the same mean. */
+int qa_k_token_sum(const void* k_fp16, void* sum_f32, void* workspace, size_t ws_bytes, int B, int H, int S, int D,
+                   void* stream);
+
+/* Per-block int8 quantisation, attention_int8.py:178-186 (Q), :188-195 (K), :241-247 (V), :369-374 (dO):
+ * scale = fp16(amax|block| / 127); value = trunc(fp16(x / scale)); block = blk rows x D.  Bit-exact with the reference
+ * arithmetic.  mean_fp16 != NULL subtracts the per-head mean first (fp16, one rounding): K-smoothing fused in. */
+int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* out_i8, void* scales_fp16, long long n_rows, int D,
+                   int blk, int rows_per_head, void* stream);
+
+/* ---- int8 forward: helion_atten_int8_hl_dot_fwd, attention_int8.py:101-262 (tile loop :170-257) ----
+ * Normal mode: O fp16 [BH*Sq, D], lse16 fp16, lse32 fp32 (optional).  Ring mode (o_acc != NULL): unnormalised fp32
+ * accumulator plus running (m, l) per row for the K/V shard, merged by the caller (sequence-sharded ring KV). */
+int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq_fp16, const void* sk_fp16,
+                const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, void* o_acc_fp32, void* m_out_fp32,
+                void* l_out_fp32, int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, void* stream);
+
+/* Same kernel, continuing from a running online-softmax state (o_acc_in, m_in, l_in) produced by earlier K/V shards of
+ * the ring; all three NULL = fresh state.  In/out state buffers may alias. */
+int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq_fp16, const void* sk_fp16,
+                      const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, void* o_acc_fp32, void* m_out_fp32,
+                      void* l_out_fp32, const void* o_acc_in_fp32, const void* m_in_fp32, const void* l_in_fp32, int BH,
+                      int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, void* stream);
+
+/* ---- backward pre/post passes ---- */
+/* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;
+ * 1: fp32 dO/O and, if dO_bf16 != NULL, a bf16 copy of dO in the same pass. */
+int qa_bwd_delta(const void* dO, const void* O, void* delta_f32, void* dO_bf16, long long n_rows, int D, int in_dtype,
+                 void* stream);
+/* fp32 -> fp16 (out_dtype 0) / bf16 (1) */
+int qa_cast_f32(const void* in_f32, void* out, long long n, int out_dtype, void* stream);
+
+/* ---- int8 backward: helion_atten_int8_hl_dot_bwd, attention_int8.py:268-432 under the 8-LEDGER contract ----
+ * Bq = Bkv = 128.  dq_ws: zero-initialised fp32 [BH*S, D] accumulator (cast with qa_cast_f32); dk, dv fp16. */
+int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq_fp16,
+                const void* sk_fp16, const void* sv_fp16, const void* s_do_fp16, const void* lse_f32,
+                const void* delta_f32, const void* k_mean_f16, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
+                int D, int Bq, int Bkv, void* stream);
+
+/* ---- bf16 path: helion_atten_bf16_fwd_training (attention_bf16.py:111-296), helion_flash_atten_2_algo_4_bwd
+ * (attention_bf16.py:309-448) ---- */
+int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH, int Sq,
+                int Sk, int D, int causal, int nsplit, void* stream);
+int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
+                int causal, void* stream);
+
+/* ---- JVP: helion_attention_jvp_forward_fp32, attention_jvp.py:33-195 (operands pre-cast to bf16) ---- */
+int qa_jvp_fwd(const void* q_bf16, const void* tq_bf16, const void* k_bf16, const void* tk_bf16, const void* v_bf16,
+               const void* tv_bf16, void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit,
+               void* stream);
+
+/* ---- hardware probes used by tests/test_probe_gpu.py (layout / descriptor conventions) ---- */
+int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, void* d_out, int a_lbo, int a_sbo,
+                 int a_layout, int a_kstep_bytes, int b_lbo, int b_sbo, int b_layout, int b_kstep_bytes, unsigned idesc,
+                 int kind, int n_mma, int n_cols, int a_in_tmem, int a_tmem_cols, int a_tmem_kstep_cols, void* stream);
+int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const unsigned long long* dims,
+                 const unsigned long long* strides_bytes, const unsigned* box, int swizzle, const int* coords, void* out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QATTN_H */

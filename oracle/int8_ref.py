@@ -130,6 +130,43 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
     return out
 
 
+def int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bkv, last):
+    """One ring step on pre-quantised operands: the tile loop of `int8_fwd` (attention_int8.py:176-250) over one K/V
+    shard, continuing the online-softmax state (O_acc fp32 [BH*Sq,D], m fp32 (holding an fp16 value), l fp32).
+    last=False -> new state; last=True -> (O fp16 [BH*Sq,D], lse16, lse32) as :252-257."""
+    qk_scale = (1.0 / math.sqrt(D)) * LOG2E
+    qg, kg, vg = q_i8.view(BH, Sq, D), k_i8.view(BH, Sk, D), v_i8.view(BH, Sk, D)
+    sq_rows = sq.view(BH, Sq // Bq).repeat_interleave(Bq, dim=1)[..., None].float()
+    sk_g, sv_g = sk.view(BH, Sk // Bkv), sv.view(BH, Sk // Bkv)
+    if state is None:
+        O = torch.zeros((BH, Sq, D), dtype=torch.float32)
+        l = torch.full((BH, Sq, 1), 1.0, dtype=torch.float32)
+        m = torch.full((BH, Sq, 1), float("-inf"), dtype=torch.float16)
+    else:
+        O = state[0].view(BH, Sq, D).clone()
+        m = state[1].view(BH, Sq, 1).to(torch.float16)
+        l = state[2].view(BH, Sq, 1).clone()
+    for j in range(Sk // Bkv):
+        ks = slice(j * Bkv, (j + 1) * Bkv)
+        S16 = (_imm(qg, kg[:, ks].transpose(1, 2)).to(torch.float32) * sq_rows * sk_g[:, j].view(BH, 1, 1).float()
+               * qk_scale).to(torch.float16)
+        row_max = torch.amax(S16, -1, keepdim=True)
+        m_new = torch.max(m, row_max)
+        P = torch.exp2((S16 - m_new).to(torch.float32))
+        rescale = torch.exp2((m - m_new).to(torch.float32))
+        m = m_new
+        l = l * rescale + torch.sum(P, -1, keepdim=True)
+        O = O * rescale
+        sp = torch.exp2((row_max - m).to(torch.float32)) / 127
+        P_i8 = (P / sp).to(torch.int8)
+        O = O + _imm(P_i8, vg[:, ks]).to(torch.float32) * sp * sv_g[:, j].view(BH, 1, 1).float()
+    if not last:
+        return O.reshape(BH * Sq, D), m.float().reshape(-1), l.reshape(-1)
+    lse32 = m.squeeze(-1).float() + torch.log2(l).squeeze(-1)
+    lse16 = m.squeeze(-1) + torch.log2(l).squeeze(-1).to(torch.float16)
+    return (O / l).to(torch.float16).reshape(BH * Sq, D), lse16.reshape(-1), lse32.reshape(-1)
+
+
 def sage_forward(q, k, v, Bq=32, Bkv=32):
     """Contract version of SageAttention3_Int8_autograd_function.forward
     (attention_int8.py:21-40 with LEDGER I-1): 11-tuple with k_mean [B,H,1,D] in slot 2."""

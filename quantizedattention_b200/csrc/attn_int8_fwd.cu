@@ -39,9 +39,12 @@ struct Int8FwdParams {
   __half* O;             // [BH*Sq, D] fp16
   __half* lse16;         // [BH*Sq]
   float* lse32;          // [BH*Sq] (may be null)
-  float* m_out;          // optional split outputs for ring attention: unnormalised O + (m, l); null otherwise
+  float* m_out;          // optional state outputs for ring attention: unnormalised O + (m, l); null otherwise
   float* l_out;
   float* O_acc_out;
+  const float* m_in;     // optional running state to continue from (previous K/V shards of the ring); null = fresh
+  const float* l_in;
+  const float* O_acc_in;
   int Sq, Sk, Bq;
   float qk_scale;
 };
@@ -98,6 +101,11 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float sq_f = __half2float(p.sq[((size_t)bh * p.Sq + q0 + row) / p.Bq]);
     __half m16 = __float2half_rn(-INFINITY);
     float l = (split == 0) ? 1.0f : 0.0f;          // reference initialises l to 1.0 (attention_int8.py:173)
+    if (p.m_in != nullptr) {                       // ring: continue the online softmax of earlier K/V shards
+      const size_t gr = (size_t)bh * p.Sq + q0 + row;
+      m16 = __float2half_rn(p.m_in[gr]);
+      l = (split == 0) ? p.l_in[gr] : 0.0f;
+    }
     for (int j = 0; j < nk; ++j) {
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
@@ -187,6 +195,14 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float acc[DC];
 #pragma unroll
     for (int i = 0; i < DC; ++i) acc[i] = 0.f;
+    if (p.O_acc_in != nullptr) {
+      const float* src = p.O_acc_in + ((size_t)bh * p.Sq + q0 + row) * D + d0;
+#pragma unroll
+      for (int i = 0; i < DC; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + i);
+        acc[i] = t.x; acc[i + 1] = t.y; acc[i + 2] = t.z; acc[i + 3] = t.w;
+      }
+    }
     for (int j = 0; j < nk; ++j) {
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
@@ -335,9 +351,10 @@ using namespace qa;
 // Forward over pre-quantised operands.  q_i8 [BH*Sq, D], k_i8 / v_i8 [BH*Sk, D] int8 row-major; sq [BH*Sq/Bq],
 // sk / sv [BH*Sk/Bkv] fp16.  Outputs: O fp16 [BH*Sq, D], lse16 fp16 [BH*Sq], lse32 fp32 [BH*Sq] (optional).
 // Ring mode (o_acc != NULL): writes unnormalised fp32 O plus (m, l) per row instead of O / lse.
-extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
-                           const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
-                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, void* stream) {
+extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
+                                 const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
+                                 const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int D,
+                                 int Bq, int Bkv, int nsplit, void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: D must be 64 or 128");
   if (Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 128 (tcgen05 k-tile)");
   if (Bq != 32 && Bq != 64 && Bq != 128 && Bq != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bq must be 32/64/128/256");
@@ -348,6 +365,7 @@ extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
   p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv;
   p.O = (__half*)O; p.lse16 = (__half*)lse16; p.lse32 = (float*)lse32;
   p.O_acc_out = (float*)o_acc; p.m_out = (float*)m_out; p.l_out = (float*)l_out;
+  p.O_acc_in = (const float*)o_acc_in; p.m_in = (const float*)m_in; p.l_in = (const float*)l_in;
   p.Sq = Sq; p.Sk = Sk; p.Bq = Bq;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
@@ -355,4 +373,11 @@ extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
                                    : launch_int8_fwd<128, 1, 3>(q_i8, k_i8, v_i8, p, BH, st);
   return nsplit == 2 ? launch_int8_fwd<64, 2, 4>(q_i8, k_i8, v_i8, p, BH, st)
                      : launch_int8_fwd<64, 1, 4>(q_i8, k_i8, v_i8, p, BH, st);
+}
+
+extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
+                           const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
+                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, void* stream) {
+  return qa_int8_fwd_state(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, nullptr, nullptr, nullptr, BH,
+                           Sq, Sk, D, Bq, Bkv, nsplit, stream);
 }

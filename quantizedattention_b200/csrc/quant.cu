@@ -48,14 +48,15 @@ __global__ void __launch_bounds__(256) kmean_partial_kernel(const __half* __rest
 }
 
 // phase 2: sum partials in fixed order, divide by S, round to fp16.  One thread per (bh, d).
-__global__ void kmean_final_kernel(const float* __restrict__ part, __half* __restrict__ mean, int nchunk, int D, int S,
-                                   int total) {
+__global__ void kmean_final_kernel(const float* __restrict__ part, __half* __restrict__ mean, float* __restrict__ sum_out,
+                                   int nchunk, int D, int S, int total) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int bh = i / D, d = i % D;
   float s = 0.f;
   for (int c = 0; c < nchunk; ++c) s += part[((size_t)bh * nchunk + c) * D + d];
-  mean[i] = __float2half_rn(__fdiv_rn(s, (float)S));
+  if (mean != nullptr) mean[i] = __float2half_rn(__fdiv_rn(s, (float)S));
+  if (sum_out != nullptr) sum_out[i] = s;       // sequence-sharded ring: token sums are all-reduced before the divide
 }
 
 // ------------------------------------------------------------------------------------------
@@ -139,8 +140,8 @@ __global__ void __launch_bounds__(256) quant_block_kernel(const __half* __restri
 
 using namespace qa;
 
-extern "C" int qa_k_mean(const void* k_fp16, void* mean_fp16, void* workspace, size_t ws_bytes, int B, int H, int S,
-                         int D, void* stream) {
+static int k_mean_impl(const void* k_fp16, void* mean_fp16, void* sum_f32, void* workspace, size_t ws_bytes, int B, int H,
+                       int S, int D, void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_k_mean: D must be 64 or 128");
   const int BH = B * H;
   const int chunk = 512;
@@ -154,8 +155,20 @@ extern "C" int qa_k_mean(const void* k_fp16, void* mean_fp16, void* workspace, s
   else
     kmean_partial_kernel<128><<<grid, 256, 0, st>>>((const __half*)k_fp16, (float*)workspace, S, chunk);
   const int total = BH * D;
-  kmean_final_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, (__half*)mean_fp16, nchunk, D, S, total);
+  kmean_final_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, (__half*)mean_fp16, (float*)sum_f32, nchunk,
+                                                         D, S, total);
   return qa_check_launch("qa_k_mean");
+}
+
+extern "C" int qa_k_mean(const void* k_fp16, void* mean_fp16, void* workspace, size_t ws_bytes, int B, int H, int S,
+                         int D, void* stream) {
+  return k_mean_impl(k_fp16, mean_fp16, nullptr, workspace, ws_bytes, B, H, S, D, stream);
+}
+
+// fp32 token sums [B*H, D] of a sequence shard (ring KV: all-reduce the sums, then divide by the global length)
+extern "C" int qa_k_token_sum(const void* k_fp16, void* sum_f32, void* workspace, size_t ws_bytes, int B, int H, int S,
+                              int D, void* stream) {
+  return k_mean_impl(k_fp16, nullptr, sum_f32, workspace, ws_bytes, B, H, S, D, stream);
 }
 
 extern "C" size_t qa_k_mean_workspace_bytes(int B, int H, int S, int D) {

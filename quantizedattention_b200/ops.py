@@ -94,8 +94,23 @@ def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, row
     return out, scales
 
 
+def k_token_sum(k: torch.Tensor) -> torch.Tensor:
+    """fp32 token sums [B,H,1,D] of a (sequence-shard of) K (qa_k_token_sum)."""
+    _need_cuda(k)
+    assert k.dtype == torch.float16 and k.dim() == 4
+    k = k.contiguous()
+    B, H, S, D = k.shape
+    L = _lib.lib()
+    ws = torch.empty(L.qa_k_mean_workspace_bytes(B, H, S, D), dtype=torch.uint8, device=k.device)
+    out = torch.empty((B, H, 1, D), dtype=torch.float32, device=k.device)
+    with torch.cuda.device(k.device):
+        _lib.check(L.qa_k_token_sum(_lib.ptr(k), _lib.ptr(out), _lib.ptr(ws), ws.numel(), B, H, S, D, _lib.cur_stream()),
+                   "qa_k_token_sum")
+    return out
+
+
 def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=2, want_lse32=True,
-                      ring_state=False):
+                      ring_state=False, state_in=None):
     """Fused int8 attention forward over pre-quantised operands (qa_int8_fwd).
     Returns (O fp16 [BH*Sq, D], lse16 [BH*Sq], lse32 or None); with ring_state=True returns the unnormalised
     (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead."""
@@ -112,10 +127,12 @@ def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=1
         lse16 = torch.empty((BH * Sq,), dtype=torch.float16, device=dev)
         lse32 = torch.empty((BH * Sq,), dtype=torch.float32, device=dev) if want_lse32 else None
         o_acc = m = l = None
+    si = state_in if state_in is not None else (None, None, None)       # (o_acc, m, l) of the earlier K/V shards
     with torch.cuda.device(dev), _timed("int8_fwd"):
-        _lib.check(L.qa_int8_fwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk), _lib.ptr(sv),
-                                 _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc), _lib.ptr(m), _lib.ptr(l),
-                                 BH, Sq, Sk, D, Bq, Bkv, nsplit, _lib.cur_stream()), "qa_int8_fwd")
+        _lib.check(L.qa_int8_fwd_state(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk),
+                                       _lib.ptr(sv), _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc),
+                                       _lib.ptr(m), _lib.ptr(l), _lib.ptr(si[0]), _lib.ptr(si[1]), _lib.ptr(si[2]),
+                                       BH, Sq, Sk, D, Bq, Bkv, nsplit, _lib.cur_stream()), "qa_int8_fwd")
     if ring_state:
         return o_acc, m, l
     return O, lse16, lse32

@@ -1,0 +1,69 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/qattn.h declares,
+the ctypes table covers the header, argument validation fails loudly, and the product package has no CPU path and
+never imports the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "qattn.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from quantizedattention_b200 import _lib, build
+    build.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/qattn.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert _lib.lib().qa_version() >= 100
+
+
+def test_argument_validation_needs_no_gpu():
+    from quantizedattention_b200 import _lib
+    L = _lib.lib()
+    z = ctypes.c_void_p(0)
+    assert L.qa_quant_block(z, z, z, z, 128, 96, 32, 128, z) == -1            # D not in {64,128}
+    assert b"D must be" in L.qa_last_error()
+    assert L.qa_quant_block(z, z, z, z, 100, 64, 32, 128, z) == -1            # rows not a multiple of blk
+    assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 64, 1, z) == -1  # Bkv must be 128
+    assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, z) == -1          # Bq = Bkv = 128
+    assert L.qa_bf16_fwd(*([z] * 5), 1, 100, 128, 128, 0, 1, z) == -1         # S % 128
+    assert L.qa_jvp_fwd(*([z] * 9), 1, 128, 128, 128, 1, z) == -1             # D = 64 only
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    from quantizedattention_b200 import attention_bf16, attention_int8, attention_jvp
+    x = torch.randn(1, 1, 128, 64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        attention_int8.helion_atten_int8_hl_dot_fwd(x.half(), x.half(), x.half())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        attention_bf16.helion_atten_bf16_fwd_training(x.half(), x.half(), x.bfloat16(), False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        attention_jvp.helion_attention_jvp_forward_fp32(x, x, x, x, x, x)
+    with pytest.raises(TypeError):
+        attention_bf16.helion_atten_bf16_fwd_training(x.half(), x.half(), x.half(), False)   # LEDGER B-11
+    pkg = os.path.join(ROOT, "quantizedattention_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f"{f} must not use the oracle"
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from quantizedattention_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libqattn.so"))
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        _lib.lib()

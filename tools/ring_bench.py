@@ -1,0 +1,62 @@
+"""Multi-GPU runs (launch with torchrun, one rank per GPU):
+  ring   : BASELINE configs[4] -- int8 long-context forward B=1 H=32 S=131072 D=128, sequence-sharded ring KV
+  check  : small ring problem compared against the single-device kernel (parity of the NCCL ring on real GPUs)
+Prints one JSON line from rank 0."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quantizedattention_b200 import attention_int8 as A  # noqa: E402
+from quantizedattention_b200.parallel import ring_int8_attention_fwd  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "check"
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    if mode == "check":
+        B, H, S, D = 1, 4, 4096, 128
+    else:
+        B, H, S, D = 1, 32, 131072, 128
+    Sl = S // world
+    g = torch.Generator().manual_seed(1005)
+    if mode == "check":
+        q, k, v = [torch.randn(B, H, S, D, generator=g).to(torch.float16) for _ in range(3)]
+        ql, kl, vl = [t[:, :, rank * Sl:(rank + 1) * Sl].contiguous().to(dev) for t in (q, k, v)]
+    else:
+        g = torch.Generator(device=dev).manual_seed(1005 + rank)
+        ql, kl, vl = [torch.randn(B, H, Sl, D, generator=g, device=dev, dtype=torch.float16) for _ in range(3)]
+    for _ in range(2):
+        out = ring_int8_attention_fwd(ql, kl, vl)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 3
+    e0.record()
+    for _ in range(iters):
+        out = ring_int8_attention_fwd(ql, kl, vl)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res = {"mode": mode, "n_gpus": world, "B": B, "H": H, "S": S, "D": D, "ms": t.item(),
+           "TOPS_total": 4.0 * B * H * S * S * D / (t.item() * 1e-3) / 1e12}
+    if mode == "check":
+        ref = A.SageAttention3_Int8_autograd_function.forward(q.to(dev), k.to(dev), v.to(dev))
+        A.SageAttention3_Int8_autograd_function._lse32_stash = None
+        err = (out[0].float() - ref[0][:, :, rank * Sl:(rank + 1) * Sl].float()).abs().max()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        res["max_abs_vs_single_device"] = err.item()
+        res["ok"] = bool(err.item() < 6e-3)
+    if rank == 0:
+        print(json.dumps(res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
