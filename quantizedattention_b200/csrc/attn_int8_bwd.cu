@@ -6,10 +6,12 @@
 //   S    = Q_i  K_j^T     dP    = dO_i V_j^T         (phase A, TMEM cols 0..127 / 128..255)
 //   dV_j += P^T dO_i      dK_j += dS^T Q_i     dQ_i += dS K_j   (phase C, TMEM 256.. / 384.. / 0.. aliasing S)
 // P and dS are re-quantised per [128 x 128] tile (scale = amax/127, truncation), so every int32 product is
-// drained to fp32 after each tile pair: dV/dK accumulate in registers, dQ goes to an fp32 workspace through
-// red.global.add (summation order over k-tiles is therefore not deterministic; LEDGER I-9).
-// Phases are separated by mbarriers; warps 0-7 compute (thread = row, half of the columns), warp 8 issues
-// TMA and MMA.
+// drained to fp32 after each tile pair: dV/dK accumulate in registers, the dQ tile is staged in shared memory and
+// added to an fp32 workspace by a TMA reduce-add (cp.reduce.async.bulk.tensor); the summation order over k-tiles is
+// therefore not deterministic (LEDGER I-9).  P / dS are computed twice (amax pass, quantise pass) from the packed
+// fp16 logits instead of being held in registers, which keeps the kernel spill-free.
+// Phases are separated by named barriers + mbarriers; 8 warps compute (thread = row, half of the columns) and
+// thread 0 issues TMA and MMA at the phase boundaries.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
 
@@ -24,7 +26,8 @@ struct Int8BwdSmem {
   static constexpr int off_do = off_q + 2 * kTile;   // 2 stages
   static constexpr int off_p = off_do + 2 * kTile;   // int8 [128 q][128 keys]
   static constexpr int off_ds = off_p + 128 * 128;
-  static constexpr int total = off_ds + 128 * 128 + 1024;
+  static constexpr int off_dq = off_ds + 128 * 128;  // fp32 [128 q][D] staging for the TMA reduce-add (D/32 swizzled atoms)
+  static constexpr int total = off_dq + 128 * D * 4 + 1024;
 };
 
 struct Int8BwdParams {
@@ -32,244 +35,267 @@ struct Int8BwdParams {
   const float* lse;                    // [BH*S] fp32 log2-sum-exp2
   const float* delta;                  // [BH*S]
   const __half* k_mean;                // [BH, D] fp16 (may be null)
-  float* dq_ws;                        // [BH*S, D] fp32, zero-initialised by the caller
   __half *dk, *dv;                     // [BH*S, D] fp16
   int S;
   float sm_scale, qk_scale;
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
+// 256 threads: thread = (row, column half).  Thread 0 additionally issues TMA / tcgen05.mma at the phase boundaries.
 template <int D>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(256, 1)
 int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, Int8BwdParams p) {
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_dq, Int8BwdParams p) {
   using L = Int8BwdSmem<D>;
   constexpr int DH = D / 2;                                     // output columns per thread
   constexpr uint32_t kLay = (D == 128) ? kSwz128 : kSwz64;      // operand rows of D bytes
   constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t kv_full, qdo_full[2], sd_full, pds_full, parts_full, tmem_free;
+  __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red_p[2][8], red_ds[2][8];
   __shared__ float rowsum_ds[2][2][128];
   __shared__ float kmean_s[D];                                  // sm_scale * k_mean[d]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool leader = (tid == 0);
   const int bh = blockIdx.y, j = blockIdx.x;
   const int nq = p.S / 128;
   const size_t head_row0 = (size_t)bh * p.S;
 
-  if (tid == 0) {
+  if (leader) {
     mbar_init(&kv_full, 1); mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
-    mbar_init(&sd_full, 1); mbar_init(&pds_full, 8); mbar_init(&parts_full, 1); mbar_init(&tmem_free, 8);
+    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(&tmem_base_s);
-  if (tid < D) kmean_s[tid] = p.k_mean ? __half2float(p.k_mean[(size_t)blockIdx.y * D + tid]) * p.sm_scale : 0.f;
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  if (tid < D) kmean_s[tid] = p.k_mean ? __half2float(p.k_mean[(size_t)bh * D + tid]) * p.sm_scale : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
 
-  if (warp == 8) {
-    // =========================== control warp: TMA + MMA issue ===========================
-    if (elect_one()) {
-      constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128);     // S, dP: A, B K-major, N = 128
-      constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);       // dV, dK: A^T (MN-major), B MN-major, N = D
-      constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);       // dQ: A K-major, B MN-major
-      const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
-      const uint32_t a_p = smem_u32(smem + L::off_p), a_ds = smem_u32(smem + L::off_ds);
-      mbar_expect_tx(&kv_full, 2 * L::kTile);
-      tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
-      tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
-      mbar_expect_tx(&qdo_full[0], 2 * L::kTile);
-      tma_load_2d(smem + L::off_q, &tm_q, &qdo_full[0], 0, (int)head_row0);
-      tma_load_2d(smem + L::off_do, &tm_do, &qdo_full[0], 0, (int)head_row0);
-      mbar_wait(&kv_full, 0);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i & 1;
-        const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
-        mbar_wait(&qdo_full[st], (i >> 1) & 1);
-        if (i > 0) mbar_wait(&tmem_free, (i - 1) & 1);          // previous tile's partials drained
-        tc_fence_after();
-        if (i + 1 < nq) {                                        // prefetch next Q / dO tile (its stage is idle now)
-          mbar_expect_tx(&qdo_full[st ^ 1], 2 * L::kTile);
-          tma_load_2d(smem + L::off_q + (st ^ 1) * L::kTile, &tm_q, &qdo_full[st ^ 1], 0, (int)head_row0 + (i + 1) * 128);
-          tma_load_2d(smem + L::off_do + (st ^ 1) * L::kTile, &tm_do, &qdo_full[st ^ 1], 0, (int)head_row0 + (i + 1) * 128);
-        }
+  constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128);     // S, dP: A, B K-major, N = 128
+  constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);       // dV, dK: A^T (MN-major), B MN-major, N = D
+  constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);       // dQ: A K-major, B MN-major
+  const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
+  const uint32_t a_p = smem_u32(smem + L::off_p), a_ds = smem_u32(smem + L::off_ds);
+
+  auto issue_s_dp = [&](int st) {                                  // phase A: S = Q K^T, dP = dO V^T
+    const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
 #pragma unroll
-        for (int k = 0; k < D / 32; ++k) {
-          umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, k > 0);
-          umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, k > 0);
-        }
-        umma_commit(&sd_full);
-        mbar_wait(&pds_full, i & 1);
-        tc_fence_after();
+    for (int k = 0; k < D / 32; ++k) {
+      umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, k > 0);
+      umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, k > 0);
+    }
+    umma_commit(&sd_full);
+  };
+
+  if (leader) {
+    mbar_expect_tx(&kv_full, 2 * L::kTile);
+    tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
+    tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
+    mbar_expect_tx(&qdo_full[0], 2 * L::kTile);
+    tma_load_2d(smem + L::off_q, &tm_q, &qdo_full[0], 0, (int)head_row0);
+    tma_load_2d(smem + L::off_do, &tm_do, &qdo_full[0], 0, (int)head_row0);
+    mbar_wait(&kv_full, 0);
+    mbar_wait(&qdo_full[0], 0);
+    issue_s_dp(0);
+  }
+
+  const int half = warp >> 2;                                   // column half handled by this thread
+  const int row = (warp & 3) * 32 + lane;                       // TMEM lane: query row (S, dP, dQ) or key (dV, dK)
+  const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+  const float sk_f = __half2float(p.sk[head_row0 / 128 + j]);
+  const float sv_f = __half2float(p.sv[head_row0 / 128 + j]);
+  const float* kmean = kmean_s + half * DH;
+  float dv_acc[DH], dk_acc[DH];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {                           // contraction over the 128 query rows / keys
-          const uint64_t pT = umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128);
-          const uint64_t dsT = umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128);
-          const uint64_t dsK = umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128);
-          umma_i8_ss(tbase + 256, pT, umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
-          umma_i8_ss(tbase + 384, dsT, umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
-          umma_i8_ss(tbase + 0, dsK, umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
-        }
-        umma_commit(&parts_full);
+  for (int d = 0; d < DH; ++d) { dv_acc[d] = 0.f; dk_acc[d] = 0.f; }
+
+  for (int i = 0; i < nq; ++i) {
+    const uint32_t ph = i & 1;
+    const int st = i & 1;
+    if (leader && i + 1 < nq) {                                  // prefetch the next Q / dO tile (its stage is idle)
+      mbar_expect_tx(&qdo_full[st ^ 1], 2 * L::kTile);
+      tma_load_2d(smem + L::off_q + (st ^ 1) * L::kTile, &tm_q, &qdo_full[st ^ 1], 0, (int)head_row0 + (i + 1) * 128);
+      tma_load_2d(smem + L::off_do + (st ^ 1) * L::kTile, &tm_do, &qdo_full[st ^ 1], 0, (int)head_row0 + (i + 1) * 128);
+    }
+    const size_t qrow = head_row0 + (size_t)i * 128 + row;
+    const float sq_f = __half2float(p.sq[head_row0 / 128 + i]);
+    const float sdo_f = __half2float(p.s_do[head_row0 / 128 + i]);
+    const float lse = p.lse[qrow];
+    const float dlt = p.delta[qrow];
+    const float c_s = sq_f * sk_f * p.qk_scale;
+    const float c_dp = sdo_f * sv_f;
+    mbar_wait(&sd_full, ph);
+    tc_fence_after();
+    // ---- pass 1: fp16 logits (kept packed), tile amax of P and |dS|, row sum of dS
+    __half2 sh[32];
+    float amax_p = 0.f, amax_ds = 0.f, rs = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r[32], r2[32];
+      tmem_ld32(lane_addr + half * 64 + ch * 32, r);
+      tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const __half2 h = __floats2half2_rn(__int2float_rn((int)r[c]) * c_s, __int2float_rn((int)r[c + 1]) * c_s);
+        sh[ch * 16 + c / 2] = h;
+        const float2 f = __half22float2(h);
+        const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
+        amax_p = fmaxf(amax_p, fmaxf(p0, p1));
+        const float d0 = p0 * fmaf(__int2float_rn((int)r2[c]), c_dp, -dlt);
+        const float d1 = p1 * fmaf(__int2float_rn((int)r2[c + 1]), c_dp, -dlt);
+        amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d0), fabsf(d1)));
+        rs += d0 + d1;
       }
     }
-  } else {
-    // =========================== compute warps ===========================
-    const int half = warp >> 2;                                 // column half handled by this thread
-    const int row = (warp & 3) * 32 + lane;                     // TMEM lane: query row (S, dP, dQ) or key (dV, dK)
-    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    const float sk_f = __half2float(p.sk[head_row0 / 128 + j]);
-    const float sv_f = __half2float(p.sv[head_row0 / 128 + j]);
-    const float* kmean = kmean_s + half * DH;
-    float dv_acc[DH], dk_acc[DH];
+    // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
 #pragma unroll
-    for (int d = 0; d < DH; ++d) { dv_acc[d] = 0.f; dk_acc[d] = 0.f; }
-
-    for (int i = 0; i < nq; ++i) {
-      const uint32_t ph = i & 1;
-      const size_t qrow = head_row0 + (size_t)i * 128 + row;
-      const float sq_f = __half2float(p.sq[head_row0 / 128 + i]);
-      const float sdo_f = __half2float(p.s_do[head_row0 / 128 + i]);
-      const float lse = p.lse[qrow];
-      const float dlt = p.delta[qrow];
-      const float c_s = sq_f * sk_f * p.qk_scale;
-      const float c_dp = sdo_f * sv_f;
-      mbar_wait(&sd_full, ph);
-      tc_fence_after();
-      // ---- P = exp2(fp16(S) - lse),  dS = P * (dP - delta)   for this thread's 64 columns
-      float P[64], dS[64];
-      float amax_p = 0.f, amax_ds = 0.f, rs = 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      amax_p = fmaxf(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, o));
+      amax_ds = fmaxf(amax_ds, __shfl_xor_sync(0xffffffffu, amax_ds, o));
+    }
+    if (lane == 0) { red_p[ph][warp] = amax_p; red_ds[ph][warp] = amax_ds; }
+    rowsum_ds[ph][half][row] = rs;
+    named_bar_sync(1, 256);
+    amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + half * 64 + ch * 32, r);
-        tmem_ld_wait();
+    for (int w = 1; w < 8; ++w) { amax_p = fmaxf(amax_p, red_p[ph][w]); amax_ds = fmaxf(amax_ds, red_ds[ph][w]); }
+    const float sP = amax_p * (1.0f / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
+    const float inv_p = amax_p > 0.f ? __fdividef(127.0f, amax_p) : 0.f;
+    const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
+    // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
+    //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ)
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float s16 = __half2float(__float2half_rn(__int2float_rn((int)r[c]) * c_s));
-          const float pv = ex2_approx(s16 - lse);
-          P[ch * 32 + c] = pv;
-          amax_p = fmaxf(amax_p, pv);
-        }
-        tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, r);
-        tmem_ld_wait();
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r2[32];
+      tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, r2);
+      tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float ds = P[ch * 32 + c] * (__int2float_rn((int)r[c]) * c_dp - dlt);
-          dS[ch * 32 + c] = ds;
-          amax_ds = fmaxf(amax_ds, fabsf(ds));
-          rs += ds;
-        }
-      }
-      // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        amax_p = fmaxf(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, o));
-        amax_ds = fmaxf(amax_ds, __shfl_xor_sync(0xffffffffu, amax_ds, o));
-      }
-      if (lane == 0) { red_p[ph][warp] = amax_p; red_ds[ph][warp] = amax_ds; }
-      rowsum_ds[ph][half][row] = rs;
-      named_bar_sync(1, 256);
-      amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) { amax_p = fmaxf(amax_p, red_p[ph][w]); amax_ds = fmaxf(amax_ds, red_ds[ph][w]); }
-      const float sP = amax_p * (1.0f / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
-      const float inv_p = amax_p > 0.f ? __fdividef(127.0f, amax_p) : 0.f;
-      const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
-      // ---- quantise (truncate toward zero) and store both tiles as [q row][128 key bytes], 128B-swizzled
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < 2; ++g) {
         uint32_t wp[4], wd[4];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t bp = 0, bd = 0;
+          uint32_t bp[4], bd[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 4; e += 2) {
             const int c = g * 16 + q4 * 4 + e;
-            bp |= ((uint32_t)__float2int_rz(P[c] * inv_p) & 0xffu) << (8 * e);
-            bd |= ((uint32_t)__float2int_rz(dS[c] * inv_ds) & 0xffu) << (8 * e);
+            const float2 f = __half22float2(sh[ch * 16 + c / 2]);
+            const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
+            const float d0 = p0 * fmaf(__int2float_rn((int)r2[c]), c_dp, -dlt);
+            const float d1 = p1 * fmaf(__int2float_rn((int)r2[c + 1]), c_dp, -dlt);
+            bp[e] = __float_as_uint(__fmaf_rz(p0, inv_p, 8388608.0f));          // P >= 0: low byte = trunc(P / sP)
+            bp[e + 1] = __float_as_uint(__fmaf_rz(p1, inv_p, 8388608.0f));
+            bd[e] = (uint32_t)__float2int_rz(d0 * inv_ds);
+            bd[e + 1] = (uint32_t)__float2int_rz(d1 * inv_ds);
           }
-          wp[q4] = bp; wd[q4] = bd;
+          wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
+          wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
         }
-        const uint32_t off = swz128(row, half * 64 + g * 16);
+        const uint32_t off = swz128(row, half * 64 + ch * 32 + g * 16);
         *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
         *reinterpret_cast<uint4*>(smem + L::off_ds + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_full);
-      // ---- drain the three int32 partials
-      const float rs_row = rowsum_ds[ph][0][row] + rowsum_ds[ph][1][row];     // full-row sum of dS (query row = lane)
-      mbar_wait(&parts_full, ph);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    if (leader) tma_store_wait_read();                           // previous dQ reduce has finished reading its staging tile
+    named_bar_sync(2, 256);
+    if (leader) {                                                // phase C: contraction over the 128 query rows / keys
       tc_fence_after();
-      const float c_dv = sdo_f * sP;
-      const float c_dk = sdS * sq_f * p.sm_scale;
-      const float c_dq = sdS * sk_f * p.sm_scale;
-      float* dq_dst = p.dq_ws + qrow * D + half * DH;
+      const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
 #pragma unroll
-      for (int ch = 0; ch < DH / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) dv_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 32 + c]);
-        tmem_ld32(lane_addr + 384 + half * DH + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) dk_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dk, dk_acc[ch * 32 + c]);
-        tmem_ld32(lane_addr + 0 + half * DH + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          red_add_v4(dq_dst + ch * 32 + c,
-                     fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 32 + c]),
-                     fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 32 + c + 1]),
-                     fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 32 + c + 2]),
-                     fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 32 + c + 3]));
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t pT = umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128);
+        const uint64_t dsT = umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128);
+        const uint64_t dsK = umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128);
+        umma_i8_ss(tbase + 256, pT, umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+        umma_i8_ss(tbase + 384, dsT, umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+        umma_i8_ss(tbase + 0, dsK, umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_free);
+      umma_commit(&parts_full);
     }
-    // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
-    const size_t krow = head_row0 + (size_t)j * 128 + row;
-    __half* dk_dst = p.dk + krow * D + half * DH;
-    __half* dv_dst = p.dv + krow * D + half * DH;
+    // ---- drain the three int32 partials
+    const float rs_row = rowsum_ds[ph][0][row] + rowsum_ds[ph][1][row];     // full-row sum of dS (query row = lane)
+    const float c_dv = sdo_f * sP;
+    const float c_dk = sdS * sq_f * p.sm_scale;
+    const float c_dq = sdS * sk_f * p.sm_scale;
+    mbar_wait(&parts_full, ph);
+    tc_fence_after();
 #pragma unroll
-    for (int d = 0; d < DH; d += 8) {
-      uint4 a, b;
-      __half2 t;
-      t = __floats2half2_rn(dk_acc[d], dk_acc[d + 1]); a.x = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dk_acc[d + 2], dk_acc[d + 3]); a.y = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dk_acc[d + 4], dk_acc[d + 5]); a.z = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dk_acc[d + 6], dk_acc[d + 7]); a.w = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dv_acc[d], dv_acc[d + 1]); b.x = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dv_acc[d + 2], dv_acc[d + 3]); b.y = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dv_acc[d + 4], dv_acc[d + 5]); b.z = *reinterpret_cast<uint32_t*>(&t);
-      t = __floats2half2_rn(dv_acc[d + 6], dv_acc[d + 7]); b.w = *reinterpret_cast<uint32_t*>(&t);
-      *reinterpret_cast<uint4*>(dk_dst + d) = a;
-      *reinterpret_cast<uint4*>(dv_dst + d) = b;
+    for (int ch = 0; ch < DH / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dv_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 32 + c]);
+      tmem_ld32(lane_addr + 384 + half * DH + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dk_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dk, dk_acc[ch * 32 + c]);
+      tmem_ld32(lane_addr + 0 + half * DH + ch * 32, r);
+      tmem_ld_wait();
+      // dQ tile -> fp32 staging, one 128-byte (32-float) swizzled atom column per (half, ch)
+      uint8_t* atom = smem + L::off_dq + (half * (DH / 32) + ch) * (128 * 128);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 o;
+        o.x = fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 32 + c]);
+        o.y = fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 32 + c + 1]);
+        o.z = fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 32 + c + 2]);
+        o.w = fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 32 + c + 3]);
+        *reinterpret_cast<float4*>(atom + swz128(row, c * 4)) = o;
+      }
     }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(3, 256);
+    if (leader) {
+      tc_fence_after();
+#pragma unroll
+      for (int a = 0; a < D / 32; ++a)                           // dQ[i] += tile  (L2 reduction, order over k-tiles not fixed)
+        tma_reduce_add_2d(&tm_dq, smem + L::off_dq + a * (128 * 128), a * 32, (int)head_row0 + i * 128);
+      tma_store_commit();
+      if (i + 1 < nq) {
+        mbar_wait(&qdo_full[st ^ 1], ((i + 1) >> 1) & 1);
+        issue_s_dp(st ^ 1);
+      }
+    }
+  }
+  if (leader) tma_store_wait_all();
+  // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
+  const size_t krow = head_row0 + (size_t)j * 128 + row;
+  __half* dk_dst = p.dk + krow * D + half * DH;
+  __half* dv_dst = p.dv + krow * D + half * DH;
+#pragma unroll
+  for (int d = 0; d < DH; d += 8) {
+    uint4 a, b;
+    __half2 t;
+    t = __floats2half2_rn(dk_acc[d], dk_acc[d + 1]); a.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dk_acc[d + 2], dk_acc[d + 3]); a.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dk_acc[d + 4], dk_acc[d + 5]); a.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dk_acc[d + 6], dk_acc[d + 7]); a.w = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dv_acc[d], dv_acc[d + 1]); b.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dv_acc[d + 2], dv_acc[d + 3]); b.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dv_acc[d + 4], dv_acc[d + 5]); b.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2half2_rn(dv_acc[d + 6], dv_acc[d + 7]); b.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(dk_dst + d) = a;
+    *reinterpret_cast<uint4*>(dv_dst + d) = b;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tbase);
+  if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
 template <int D>
-static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const Int8BwdParams& p,
-                           int BH, cudaStream_t st) {
+static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
+                           const Int8BwdParams& p, int BH, cudaStream_t st) {
   using L = Int8BwdSmem<D>;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq;
   const int sw = (D == 128) ? 3 : 2;
   uint64_t dims[2] = {(uint64_t)D, (uint64_t)BH * p.S};
   uint64_t str[1] = {(uint64_t)D};
@@ -279,11 +305,14 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tdo, do_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+  uint64_t strq[1] = {(uint64_t)D * 4};
+  uint32_t boxq[2] = {32, 128};
+  if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
   auto kern = int8_bwd_kernel<D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.S / 128, BH);
-  kern<<<grid, 288, L::total, st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, 256, L::total, st>>>(tq, tk, tv, tdo, tdq, p);
   return qa_check_launch("qa_int8_bwd");
 }
 
@@ -303,11 +332,11 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   Int8BwdParams p;
   p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv; p.s_do = (const __half*)s_do;
   p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32; p.k_mean = (const __half*)k_mean_f16;
-  p.dq_ws = (float*)dq_ws_f32; p.dk = (__half*)dk_f16; p.dv = (__half*)dv_f16;
+  p.dk = (__half*)dk_f16; p.dv = (__half*)dv_f16;
   p.S = S;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
-  return D == 128 ? launch_int8_bwd<128>(q_i8, k_i8, v_i8, do_i8, p, BH, st)
-                  : launch_int8_bwd<64>(q_i8, k_i8, v_i8, do_i8, p, BH, st);
+  return D == 128 ? launch_int8_bwd<128>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+                  : launch_int8_bwd<64>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
 }

@@ -168,10 +168,10 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
             float p0 = ex2_approx(f.x), p1 = ex2_approx(f.y);
             lsum += p0 + p1;
-            bytes[h2 * 2] = __float_as_uint(__fmaf_rz(p0, inv_sp, 8388608.0f)) & 0xffu;      // trunc(P/sp)
-            bytes[h2 * 2 + 1] = __float_as_uint(__fmaf_rz(p1, inv_sp, 8388608.0f)) & 0xffu;
+            bytes[h2 * 2] = __float_as_uint(__fmaf_rz(p0, inv_sp, 8388608.0f));          // low byte = trunc(P/sp)
+            bytes[h2 * 2 + 1] = __float_as_uint(__fmaf_rz(p1, inv_sp, 8388608.0f));
           }
-          w[q4] = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
+          w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
         }
         const uint32_t off = swz128(row, c0 + g * 16);
         *reinterpret_cast<uint4*>(prow + off) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -210,6 +210,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float2 sc = row_sc[b][row];
       __syncwarp();
       if (lane == 0) mbar_arrive(&sc_empty[b]);
+      const bool no_rescale = __all_sync(0xffffffffu, sc.x == 1.0f);
       mbar_wait(&o_full[b], ph);
       tc_fence_after();
 #pragma unroll
@@ -217,9 +218,14 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(lane_addr + 256 + b * 128 + d0 + ch * 32, r);
         tmem_ld_wait();
+        if (no_rescale) {                              // warp-uniform: the running max did not move for these 32 rows
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), sc.y, acc[ch * 32 + i] * sc.x);
+          for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), sc.y, acc[ch * 32 + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), sc.y, acc[ch * 32 + i] * sc.x);
+        }
       }
       tc_fence_before();
       __syncwarp();

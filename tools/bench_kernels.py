@@ -39,6 +39,40 @@ def int8_fwd(BH=256, S=8192, D=128):
     print(json.dumps(res, indent=1))
 
 
+def bf16(B=4, H=16, S=4096, D=128, causal=1):
+    torch.manual_seed(0)
+    q, k = [torch.randn(B, H, S, D, device="cuda", dtype=torch.float16) for _ in range(2)]
+    v = torch.randn(B, H, S, D, device="cuda", dtype=torch.bfloat16)
+    dO = torch.randn(B, H, S, D, device="cuda")
+    res = {}
+    f = 0.5 if causal else 1.0
+    for ns in (1, 2):
+        med, best = timeit(lambda: ops.bf16_fwd(q, k, v, bool(causal), nsplit=ns))
+        res[f"bf16_fwd_nsplit{ns}"] = {"ms": med, "TFLOPS": f * 4 * B * H * S * S * D / med / 1e9}
+    O, lse = ops.bf16_fwd(q, k, v, bool(causal))
+    ops.TIMING = []
+    med, best = timeit(lambda: ops.bf16_bwd(q, k, v, O, lse, bool(causal), dO))
+    kt = [a.elapsed_time(b) for n, a, b in ops.TIMING if n == "bf16_bwd"]
+    ops.TIMING = None
+    kms = sorted(kt)[len(kt) // 2]
+    res["bf16_bwd"] = {"ms_total": med, "ms_kernel": kms, "TFLOPS_kernel": f * 10 * B * H * S * S * D / kms / 1e9}
+    print(json.dumps(res, indent=1))
+
+
+def jvp(B=16, H=16, S=4096, D=64):
+    torch.manual_seed(0)
+    t = [torch.randn(B, H, S, D, device="cuda") for _ in range(6)]
+    res = {}
+    for ns in (1, 2):
+        ops.TIMING = []
+        med, best = timeit(lambda: ops.jvp_fwd(*t, nsplit=ns))
+        kt = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "jvp_fwd")
+        ops.TIMING = None
+        kms = kt[len(kt) // 2]
+        res[f"jvp_nsplit{ns}"] = {"ms_total": med, "ms_kernel": kms, "TFLOPS_kernel": 12 * B * H * S * S * D / kms / 1e9}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
     args = [int(a) for a in sys.argv[2:]]
     globals()[sys.argv[1]](*args)
