@@ -25,8 +25,8 @@ struct Int8BwdSmem {
   static constexpr int off_q = off_v + kTile;        // 2 stages
   static constexpr int off_do = off_q + 2 * kTile;   // 2 stages
   static constexpr int off_p = off_do + 2 * kTile;   // int8 [128 q][128 keys]
-  static constexpr int off_ds = off_p + 128 * 128;
-  static constexpr int off_dq = off_ds + 128 * 128;  // fp32 [128 q][D] staging for the TMA reduce-add (D/32 swizzled atoms)
+  static constexpr int off_ds = off_p + 128 * 128;   // 2 buffers (dQ of tile t-1 reads dS while tile t is quantised)
+  static constexpr int off_dq = off_ds + 2 * 128 * 128;  // fp32 [128 q][D] staging for the TMA reduce-add (D/32 swizzled atoms)
   static constexpr int total = off_dq + 128 * D * 4 + 1024;
 };
 
@@ -40,7 +40,11 @@ struct Int8BwdParams {
   float sm_scale, qk_scale;
 };
 
-// 256 threads: thread = (row, column half).  Thread 0 additionally issues TMA / tcgen05.mma at the phase boundaries.
+// 256 threads: thread = (row, column half).  Thread 0 additionally issues TMA / tcgen05.mma at the two barriers per
+// tile.  Software pipeline (tile t): the S/dP MMAs of tile t+1 and the dV/dK MMAs of tile t are issued together, so
+// pass 1 of tile t+1 runs while the tensor core computes dV_t/dK_t; dQ_t is issued one barrier later into the TMEM
+// columns freed by draining dV_t and overlaps the quantise pass of tile t+1.
+//   TMEM: [0,128) S   [128,256) dP   [256,384) dV partial, then dQ partial   [384,512) dK partial
 template <int D>
 __global__ void __launch_bounds__(256, 1)
 int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -52,7 +56,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full;
+  __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full, dq_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red_p[2][8], red_ds[2][8];
   __shared__ float rowsum_ds[2][2][128];
@@ -66,7 +70,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (leader) {
     mbar_init(&kv_full, 1); mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
-    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1);
+    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1); mbar_init(&dq_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_s);
@@ -80,9 +84,14 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);       // dV, dK: A^T (MN-major), B MN-major, N = D
   constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);       // dQ: A K-major, B MN-major
   const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
-  const uint32_t a_p = smem_u32(smem + L::off_p), a_ds = smem_u32(smem + L::off_ds);
+  const uint32_t a_p = smem_u32(smem + L::off_p), a_ds0 = smem_u32(smem + L::off_ds);
 
-  auto issue_s_dp = [&](int st) {                                  // phase A: S = Q K^T, dP = dO V^T
+  auto load_qdo = [&](int tile, int st) {
+    mbar_expect_tx(&qdo_full[st], 2 * L::kTile);
+    tma_load_2d(smem + L::off_q + st * L::kTile, &tm_q, &qdo_full[st], 0, (int)head_row0 + tile * 128);
+    tma_load_2d(smem + L::off_do + st * L::kTile, &tm_do, &qdo_full[st], 0, (int)head_row0 + tile * 128);
+  };
+  auto issue_s_dp = [&](int st) {                                  // S = Q K^T, dP = dO V^T
     const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
 #pragma unroll
     for (int k = 0; k < D / 32; ++k) {
@@ -91,14 +100,29 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     umma_commit(&sd_full);
   };
+  auto issue_dv_dk = [&](int st, int dsb) {                        // dV = P^T dO, dK = dS^T Q (contraction over query rows)
+    const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
+    const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+      umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+    }
+    umma_commit(&parts_full);
+  };
+  auto issue_dq = [&](int dsb) {                                   // dQ = dS K (contraction over keys) -> cols 256..
+    const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
+    umma_commit(&dq_full);
+  };
 
   if (leader) {
     mbar_expect_tx(&kv_full, 2 * L::kTile);
     tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
     tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
-    mbar_expect_tx(&qdo_full[0], 2 * L::kTile);
-    tma_load_2d(smem + L::off_q, &tm_q, &qdo_full[0], 0, (int)head_row0);
-    tma_load_2d(smem + L::off_do, &tm_do, &qdo_full[0], 0, (int)head_row0);
+    load_qdo(0, 0);
     mbar_wait(&kv_full, 0);
     mbar_wait(&qdo_full[0], 0);
     issue_s_dp(0);
@@ -113,18 +137,52 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   float dv_acc[DH], dk_acc[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) { dv_acc[d] = 0.f; dk_acc[d] = 0.f; }
+  float c_dv_prev = 0.f, c_dk_prev = 0.f, c_dq_prev = 0.f, rs_prev = 0.f;
 
-  for (int i = 0; i < nq; ++i) {
-    const uint32_t ph = i & 1;
-    const int st = i & 1;
-    if (leader && i + 1 < nq) {                                  // prefetch the next Q / dO tile (its stage is idle)
-      mbar_expect_tx(&qdo_full[st ^ 1], 2 * L::kTile);
-      tma_load_2d(smem + L::off_q + (st ^ 1) * L::kTile, &tm_q, &qdo_full[st ^ 1], 0, (int)head_row0 + (i + 1) * 128);
-      tma_load_2d(smem + L::off_do + (st ^ 1) * L::kTile, &tm_do, &qdo_full[st ^ 1], 0, (int)head_row0 + (i + 1) * 128);
+  auto drain_dv_dk = [&](float c_dv, float c_dk) {
+#pragma unroll
+    for (int ch = 0; ch < DH / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dv_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 32 + c]);
+      tmem_ld32(lane_addr + 384 + half * DH + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) dk_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dk, dk_acc[ch * 32 + c]);
     }
-    const size_t qrow = head_row0 + (size_t)i * 128 + row;
-    const float sq_f = __half2float(p.sq[head_row0 / 128 + i]);
-    const float sdo_f = __half2float(p.s_do[head_row0 / 128 + i]);
+  };
+  auto drain_dq = [&](float c_dq, float rs_row) {                 // dQ partial -> fp32 staging (swizzled 32-float atoms)
+#pragma unroll
+    for (int ch = 0; ch < DH / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
+      tmem_ld_wait();
+      uint8_t* atom = smem + L::off_dq + (half * (DH / 32) + ch) * (128 * 128);
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 o;
+        o.x = fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 32 + c]);
+        o.y = fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 32 + c + 1]);
+        o.z = fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 32 + c + 2]);
+        o.w = fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 32 + c + 3]);
+        *reinterpret_cast<float4*>(atom + swz128(row, c * 4)) = o;
+      }
+    }
+  };
+  auto reduce_dq = [&](int tile) {                                // dQ[tile] += staging (L2 reduction; k-tile order not fixed)
+#pragma unroll
+    for (int a = 0; a < D / 32; ++a)
+      tma_reduce_add_2d(&tm_dq, smem + L::off_dq + a * (128 * 128), a * 32, (int)head_row0 + tile * 128);
+    tma_store_commit();
+  };
+
+  for (int t = 0; t < nq; ++t) {
+    const uint32_t ph = t & 1;
+    const size_t qrow = head_row0 + (size_t)t * 128 + row;
+    const float sq_f = __half2float(p.sq[head_row0 / 128 + t]);
+    const float sdo_f = __half2float(p.s_do[head_row0 / 128 + t]);
     const float lse = p.lse[qrow];
     const float dlt = p.delta[qrow];
     const float c_s = sq_f * sk_f * p.qk_scale;
@@ -153,7 +211,6 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         rs += d0 + d1;
       }
     }
-    // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       amax_p = fmaxf(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, o));
@@ -161,15 +218,30 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     if (lane == 0) { red_p[ph][warp] = amax_p; red_ds[ph][warp] = amax_ds; }
     rowsum_ds[ph][half][row] = rs;
-    named_bar_sync(1, 256);
+    // ---- drain dV / dK of the previous tile (its MMAs ran while pass 1 executed)
+    if (t > 0) {
+      mbar_wait(&parts_full, (t - 1) & 1);
+      tc_fence_after();
+      if (leader && t + 1 < nq) load_qdo(t + 1, (t + 1) & 1);      // that stage's last readers (dV/dK of t-1) are done
+      drain_dv_dk(c_dv_prev, c_dk_prev);
+    } else if (leader && nq > 1) {
+      load_qdo(1, 1);
+    }
+    tc_fence_before();
+    if (leader) tma_store_wait_read();                             // the dQ staging tile may be rewritten after this barrier
+    named_bar_sync(1, 256);                                        // amax partials visible; dV/dK partial columns drained
+    if (leader && t > 0) { tc_fence_after(); issue_dq((t - 1) & 1); }
+    // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
     amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) { amax_p = fmaxf(amax_p, red_p[ph][w]); amax_ds = fmaxf(amax_ds, red_ds[ph][w]); }
+    const float rs_row = rowsum_ds[ph][0][row] + rowsum_ds[ph][1][row];      // full-row sum of dS (query row = lane)
     const float sP = amax_p * (1.0f / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
     const float inv_p = amax_p > 0.f ? __fdividef(127.0f, amax_p) : 0.f;
     const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
     // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
-    //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ)
+    //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
+    uint8_t* ds_tile = smem + L::off_ds + ph * (128 * 128);
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       uint32_t r2[32];
@@ -198,75 +270,47 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         const uint32_t off = swz128(row, half * 64 + ch * 32 + g * 16);
         *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-        *reinterpret_cast<uint4*>(smem + L::off_ds + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
       }
     }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    if (leader) tma_store_wait_read();                           // previous dQ reduce has finished reading its staging tile
-    named_bar_sync(2, 256);
-    if (leader) {                                                // phase C: contraction over the 128 query rows / keys
+    // ---- drain dQ of the previous tile (its MMA ran while pass 2 executed)
+    if (t > 0) {
+      mbar_wait(&dq_full, (t - 1) & 1);
       tc_fence_after();
-      const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t pT = umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128);
-        const uint64_t dsT = umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128);
-        const uint64_t dsK = umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128);
-        umma_i8_ss(tbase + 256, pT, umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
-        umma_i8_ss(tbase + 384, dsT, umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
-        umma_i8_ss(tbase + 0, dsK, umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
-      }
-      umma_commit(&parts_full);
-    }
-    // ---- drain the three int32 partials
-    const float rs_row = rowsum_ds[ph][0][row] + rowsum_ds[ph][1][row];     // full-row sum of dS (query row = lane)
-    const float c_dv = sdo_f * sP;
-    const float c_dk = sdS * sq_f * p.sm_scale;
-    const float c_dq = sdS * sk_f * p.sm_scale;
-    mbar_wait(&parts_full, ph);
-    tc_fence_after();
-#pragma unroll
-    for (int ch = 0; ch < DH / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; ++c) dv_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 32 + c]);
-      tmem_ld32(lane_addr + 384 + half * DH + ch * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; ++c) dk_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dk, dk_acc[ch * 32 + c]);
-      tmem_ld32(lane_addr + 0 + half * DH + ch * 32, r);
-      tmem_ld_wait();
-      // dQ tile -> fp32 staging, one 128-byte (32-float) swizzled atom column per (half, ch)
-      uint8_t* atom = smem + L::off_dq + (half * (DH / 32) + ch) * (128 * 128);
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 o;
-        o.x = fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 32 + c]);
-        o.y = fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 32 + c + 1]);
-        o.z = fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 32 + c + 2]);
-        o.w = fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 32 + c + 3]);
-        *reinterpret_cast<float4*>(atom + swz128(row, c * 4)) = o;
-      }
+      drain_dq(c_dq_prev, rs_prev);
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    named_bar_sync(3, 256);
+    named_bar_sync(2, 256);                                        // P / dS tiles and the dQ staging tile are complete
     if (leader) {
       tc_fence_after();
-#pragma unroll
-      for (int a = 0; a < D / 32; ++a)                           // dQ[i] += tile  (L2 reduction, order over k-tiles not fixed)
-        tma_reduce_add_2d(&tm_dq, smem + L::off_dq + a * (128 * 128), a * 32, (int)head_row0 + i * 128);
-      tma_store_commit();
-      if (i + 1 < nq) {
-        mbar_wait(&qdo_full[st ^ 1], ((i + 1) >> 1) & 1);
-        issue_s_dp(st ^ 1);
+      if (t > 0) reduce_dq(t - 1);
+      if (t + 1 < nq) {
+        mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+        issue_s_dp((t + 1) & 1);
       }
+      issue_dv_dk(t & 1, ph);
     }
+    c_dv_prev = sdo_f * sP;
+    c_dk_prev = sdS * sq_f * p.sm_scale;
+    c_dq_prev = sdS * sk_f * p.sm_scale;
+    rs_prev = rs_row;
   }
-  if (leader) tma_store_wait_all();
+  // ---- pipeline tail: last tile's dV / dK / dQ
+  mbar_wait(&parts_full, (nq - 1) & 1);
+  tc_fence_after();
+  drain_dv_dk(c_dv_prev, c_dk_prev);
+  tc_fence_before();
+  if (leader) tma_store_wait_read();
+  named_bar_sync(1, 256);
+  if (leader) { tc_fence_after(); issue_dq((nq - 1) & 1); }
+  mbar_wait(&dq_full, (nq - 1) & 1);
+  tc_fence_after();
+  drain_dq(c_dq_prev, rs_prev);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  named_bar_sync(2, 256);
+  if (leader) { reduce_dq(nq - 1); tma_store_wait_all(); }
   // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
   const size_t krow = head_row0 + (size_t)j * 128 + row;
   __half* dk_dst = p.dk + krow * D + half * DH;
@@ -274,15 +318,15 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
   for (int d = 0; d < DH; d += 8) {
     uint4 a, b;
-    __half2 t;
-    t = __floats2half2_rn(dk_acc[d], dk_acc[d + 1]); a.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dk_acc[d + 2], dk_acc[d + 3]); a.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dk_acc[d + 4], dk_acc[d + 5]); a.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dk_acc[d + 6], dk_acc[d + 7]); a.w = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dv_acc[d], dv_acc[d + 1]); b.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dv_acc[d + 2], dv_acc[d + 3]); b.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dv_acc[d + 4], dv_acc[d + 5]); b.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2half2_rn(dv_acc[d + 6], dv_acc[d + 7]); b.w = *reinterpret_cast<uint32_t*>(&t);
+    __half2 t2;
+    t2 = __floats2half2_rn(dk_acc[d], dk_acc[d + 1]); a.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dk_acc[d + 2], dk_acc[d + 3]); a.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dk_acc[d + 4], dk_acc[d + 5]); a.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dk_acc[d + 6], dk_acc[d + 7]); a.w = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dv_acc[d], dv_acc[d + 1]); b.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dv_acc[d + 2], dv_acc[d + 3]); b.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dv_acc[d + 4], dv_acc[d + 5]); b.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2half2_rn(dv_acc[d + 6], dv_acc[d + 7]); b.w = *reinterpret_cast<uint32_t*>(&t2);
     *reinterpret_cast<uint4*>(dk_dst + d) = a;
     *reinterpret_cast<uint4*>(dv_dst + d) = b;
   }
