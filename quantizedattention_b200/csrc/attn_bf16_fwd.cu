@@ -1,7 +1,9 @@
 // bf16 flash attention forward with the Qiu & Yao bias-corrected running max (reference
-// attention_bf16.py:195-294) for sm_100a.  Same warp-specialised skeleton as the int8 forward:
-//   softmax warps -> correction warps (fp32 O accumulators) -> TMA producer warp -> MMA warp.
-// S = Q K^T : tcgen05 kind::f16, fp16 x fp16 -> fp32 TMEM.   O += P V : bf16 x bf16 -> fp32 TMEM partial.
+// attention_bf16.py:195-294) for sm_100a.  Warp roles: softmax warps, one correction warpgroup, TMA producer warp,
+// MMA warp.  S = Q K^T : tcgen05 kind::f16, fp16 x fp16 -> fp32 TMEM (double-buffered).  O += P V : bf16 x bf16,
+// the fp32 accumulator stays RESIDENT in TMEM across k-tiles; the correction warps multiply it by the bf16 rescale
+// factor only when a row's running max moved (rescale == 1 exactly otherwise), so the steady-state TMEM->register
+// traffic is the S tile alone (TMEM read bandwidth, ~100 B/clk/SM measured, is what bounds these kernels).
 // Per k-tile numerics (contract mode): Sb = bf16(S); u = bf16(Sb * qk_scale); strict causal mask with
 // masked weight 0; m' = max(m, rowmax(u)) in bf16; if >= 2 entries lie within 1e-3 of m' (one scaled domain):
 // m' = beta*m' (m' > 0) or 0 (m' < 0); P = bf16(exp2(bf16(u - m'))); l = l*rescale + sum(P);
@@ -41,19 +43,21 @@ __device__ __forceinline__ __nv_bfloat162 as_bf2(uint32_t v) { return *reinterpr
 __device__ __forceinline__ uint32_t as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 template <int D, int NSPLIT, int STAGES, int PBUF>
-__global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
+__global__ void __launch_bounds__(128 * NSPLIT + 192, 1)
 bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Bf16FwdParams p) {
   using L = Bf16FwdSmem<D, STAGES, PBUF>;
   constexpr int NC = 128 / NSPLIT;
-  constexpr int DC = D / NSPLIT;
   constexpr int kSoftWarps = 4 * NSPLIT;
+  constexpr int kCorrWarp0 = kSoftWarps;       // 4 correction warps
+  constexpr int kProdWarp = kSoftWarps + 4;
+  constexpr int kMmaWarp = kSoftWarps + 5;
   constexpr int kDAtoms = D / 64;              // 128-byte atoms along D for 16-bit operands
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2], sc_full[2], sc_empty[2], fin_full;
+  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full, o_ready, sc_full[2], sc_empty[2], fin_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float row_sc[2][128];            // rescale per row
   __shared__ uint32_t xtop[2][2][128];        // NSPLIT == 2: packed (top1, top2) bf16 exchange
@@ -72,13 +76,13 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], kSoftWarps);
       mbar_init(&p_full[b], kSoftWarps); mbar_init(&p_empty[b], 1);
-      mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], kSoftWarps);
-      mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], kSoftWarps);
+      mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], 4);
     }
+    mbar_init(&o_full, 1); mbar_init(&o_ready, 4);
     mbar_init(&fin_full, kSoftWarps);
     fence_mbar_init();
   }
-  if (warp == 8 * NSPLIT + 1) tmem_alloc<512>(&tmem_base_s);
+  if (warp == kMmaWarp) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,11 +153,12 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       else if (many && mf < 0.f) m_new = __float2bfloat16(0.f);
       const float resc = __bfloat162float(__float2bfloat16(ex2_approx(__bfloat162float(__hsub(m_bf, m_new)))));
       m_bf = m_new;
-      if (split == 0) {
-        mbar_wait(&sc_empty[b], ph ^ 1);
-        row_sc[b][row] = resc;
+      if (split == 0 && j > 0) {                                 // tile 0 overwrites O: no rescale to hand over
+        const int sb = (j - 1) & 1;
+        mbar_wait(&sc_empty[sb], (((j - 1) >> 1) & 1) ^ 1);
+        row_sc[sb][row] = resc;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sc_full[b]);
+        if (lane == 0) mbar_arrive(&sc_full[sb]);
       }
       // ---- pass 2: P = bf16(exp2(bf16(u - m'))), l += sum(P), P -> smem (K-major, two 64-key atoms)
       mbar_wait(&p_empty[pb], pph ^ 1);
@@ -183,48 +188,55 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (split == 0) m_fin[row] = __bfloat162float(m_bf);
     __syncwarp();
     if (lane == 0) mbar_arrive(&fin_full);
-  } else if (warp < 2 * kSoftWarps) {
-    // =========================== correction warps ===========================
-    const int cw = warp - kSoftWarps;
-    const int split = cw >> 2;
+  } else if (warp < kProdWarp) {
+    // =========================== correction warpgroup (4 warps, thread = row) ===========================
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    const int d0 = split * DC;
-    float acc[DC];
-#pragma unroll
-    for (int i = 0; i < DC; ++i) acc[i] = 0.f;
-    for (int j = 0; j < nk; ++j) {
-      const int b = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&sc_full[b], ph);
-      const float resc = row_sc[b][row];
+    for (int j = 1; j < nk; ++j) {                               // tile 0 overwrites O (accumulate = 0): nothing to rescale
+      const int sb = (j - 1) & 1;
+      mbar_wait(&sc_full[sb], ((j - 1) >> 1) & 1);
+      const float resc = row_sc[sb][row];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sc_empty[b]);
-      mbar_wait(&o_full[b], ph);
-      tc_fence_after();
+      if (lane == 0) mbar_arrive(&sc_empty[sb]);
+      if (__any_sync(0xffffffffu, resc != 1.0f)) {               // some row's running max moved: O *= rescale (:280)
+        mbar_wait(&o_full, (j - 1) & 1);                         // P V of tile j-1 has landed in TMEM
+        tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < DC / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + 256 + b * 128 + d0 + ch * 32, r);
-        tmem_ld_wait();
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + 256 + ch * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(acc[ch * 32 + i], resc, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
+          tmem_st32(lane_addr + 256 + ch * 32, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[b]);
+      if (lane == 0) mbar_arrive(&o_ready);                      // the MMA warp may accumulate tile j
     }
     mbar_wait(&fin_full, 0);
+    mbar_wait(&o_full, (nk - 1) & 1);
+    tc_fence_after();
     float l = l_part[0][row];
     if (NSPLIT == 2) l += l_part[1][row];
     const size_t gr = (size_t)bh * p.Sq + q0 + row;
     const float inv_l = 1.0f / l;
-    float* dst = p.O + gr * D + d0;
+    float* dst = p.O + gr * D;
 #pragma unroll
-    for (int i = 0; i < DC; i += 4)
-      *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i] * inv_l, acc[i + 1] * inv_l, acc[i + 2] * inv_l, acc[i + 3] * inv_l);
-    if (split == 0) p.lse[gr] = m_fin[row] + log2f(l);                       // attention_bf16.py:288
-  } else if (warp == 8 * NSPLIT) {
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + 256 + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + ch * 32 + i) =
+            make_float4(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l, __uint_as_float(r[i + 2]) * inv_l,
+                        __uint_as_float(r[i + 3]) * inv_l);
+    }
+    p.lse[gr] = m_fin[row] + log2f(l);                                       // attention_bf16.py:288
+  } else if (warp == kProdWarp) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
@@ -258,7 +270,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t ph = (t >> 1) & 1;
         const uint32_t pph = (PBUF == 2) ? ph : (t & 1);
         mbar_wait(&v_full[s], (t / STAGES) & 1);
-        mbar_wait(&o_empty[b], ph ^ 1);
+        if (t > 0) mbar_wait(&o_ready, (t - 1) & 1);                              // O rescaled (if needed) for tile t
         mbar_wait(&p_full[pb], pph);
         tc_fence_after();
         const uint32_t p_addr = smem_u32(smem + L::off_p + pb * L::kPBytes);
@@ -267,9 +279,9 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int k = 0; k < 8; ++k) {                                            // 128 keys / 16
           const uint64_t ad = umma_smem_desc(p_addr + (k >> 2) * kAtom + (k & 3) * 32, 16, 1024, kSwz128);
           const uint64_t bd = umma_smem_desc(v_addr + k * 2048, kAtom, 1024, kSwz128);
-          umma_f16_ss(tbase + 256 + b * 128, ad, bd, idesc_pv, k > 0);
+          umma_f16_ss(tbase + 256, ad, bd, idesc_pv, (t > 0) || (k > 0));       // O stays resident in TMEM
         }
-        umma_commit(&o_full[b]);
+        umma_commit(&o_full);
         umma_commit(&v_empty[s]);
         umma_commit(&p_empty[pb]);
       };
@@ -295,7 +307,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tbase);
 }
 
 // causal row 0 has no visible key: reference kernel and baseline both produce the uniform average over ALL keys
@@ -324,7 +336,7 @@ static int launch_bf16_fwd(const void* q, const void* k, const void* v, const Bf
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / 128, BH);
-  kern<<<grid, 256 * NSPLIT + 64, L::total, st>>>(tq, tk, tv, p);
+  kern<<<grid, 128 * NSPLIT + 192, L::total, st>>>(tq, tk, tv, p);
   int r = qa_check_launch("qa_bf16_fwd");
   if (r) return r;
   if (p.causal) {

@@ -14,6 +14,7 @@
 // thread 0 issues TMA and MMA at the phase boundaries.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <stdlib.h>
 
 namespace qa {
 
@@ -45,21 +46,24 @@ struct Int8BwdParams {
 // pass 1 of tile t+1 runs while the tensor core computes dV_t/dK_t; dQ_t is issued one barrier later into the TMEM
 // columns freed by draining dV_t and overlaps the quantise pass of tile t+1.
 //   TMEM: [0,128) S   [128,256) dP   [256,384) dV partial, then dQ partial   [384,512) dK partial
-template <int D>
-__global__ void __launch_bounds__(256, 1)
+template <int D, int NG>
+__global__ void __launch_bounds__(128 * NG, 1)
 int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, Int8BwdParams p) {
   using L = Int8BwdSmem<D>;
-  constexpr int DH = D / 2;                                     // output columns per thread
+  constexpr int DH = D / NG;                                    // output columns per thread
+  constexpr int CW = 128 / NG;                                  // S / dP columns per thread
+  constexpr int NT = 128 * NG;                                  // threads
+  constexpr int NW = 4 * NG;                                    // warps
   constexpr uint32_t kLay = (D == 128) ? kSwz128 : kSwz64;      // operand rows of D bytes
   constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full, dq_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red_p[2][8], red_ds[2][8];
-  __shared__ float rowsum_ds[2][2][128];
+  __shared__ float red_p[2][NW], red_ds[2][NW];
+  __shared__ float rowsum_ds[2][NG][128];
   __shared__ float kmean_s[D];                                  // sm_scale * k_mean[d]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -128,7 +132,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     issue_s_dp(0);
   }
 
-  const int half = warp >> 2;                                   // column half handled by this thread
+  const int half = warp >> 2;                                   // column group handled by this thread
   const int row = (warp & 3) * 32 + lane;                       // TMEM lane: query row (S, dP, dQ) or key (dV, dK)
   const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
   const float sk_f = __half2float(p.sk[head_row0 / 128 + j]);
@@ -141,33 +145,34 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   auto drain_dv_dk = [&](float c_dv, float c_dk) {
 #pragma unroll
-    for (int ch = 0; ch < DH / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
+    for (int ch = 0; ch < DH / 16; ++ch) {
+      uint32_t r[16], r2[16];
+      tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
+      tmem_ld16(lane_addr + 384 + half * DH + ch * 16, r2);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) dv_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 32 + c]);
-      tmem_ld32(lane_addr + 384 + half * DH + ch * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 32; ++c) dk_acc[ch * 32 + c] = fmaf(__int2float_rn((int)r[c]), c_dk, dk_acc[ch * 32 + c]);
+      for (int c = 0; c < 16; ++c) {
+        dv_acc[ch * 16 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 16 + c]);
+        dk_acc[ch * 16 + c] = fmaf(__int2float_rn((int)r2[c]), c_dk, dk_acc[ch * 16 + c]);
+      }
     }
   };
   auto drain_dq = [&](float c_dq, float rs_row) {                 // dQ partial -> fp32 staging (swizzled 32-float atoms)
 #pragma unroll
-    for (int ch = 0; ch < DH / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + 256 + half * DH + ch * 32, r);
+    for (int ch = 0; ch < DH / 16; ++ch) {
+      uint32_t r[16];
+      tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
       tmem_ld_wait();
-      uint8_t* atom = smem + L::off_dq + (half * (DH / 32) + ch) * (128 * 128);
+      const int col = half * DH + ch * 16;                         // first output column of this chunk
+      uint8_t* atom = smem + L::off_dq + (col >> 5) * (128 * 128);
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) {
+      for (int c = 0; c < 16; c += 4) {
         float4 o;
-        o.x = fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 32 + c]);
-        o.y = fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 32 + c + 1]);
-        o.z = fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 32 + c + 2]);
-        o.w = fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 32 + c + 3]);
-        *reinterpret_cast<float4*>(atom + swz128(row, c * 4)) = o;
+        o.x = fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 16 + c]);
+        o.y = fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 16 + c + 1]);
+        o.z = fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 16 + c + 2]);
+        o.w = fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 16 + c + 3]);
+        *reinterpret_cast<float4*>(atom + swz128(row, ((col & 31) + c) * 4)) = o;
       }
     }
   };
@@ -190,18 +195,18 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_wait(&sd_full, ph);
     tc_fence_after();
     // ---- pass 1: fp16 logits (kept packed), tile amax of P and |dS|, row sum of dS
-    __half2 sh[32];
+    __half2 sh[CW / 2];
     float amax_p = 0.f, amax_ds = 0.f, rs = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t r[32], r2[32];
-      tmem_ld32(lane_addr + half * 64 + ch * 32, r);
-      tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, r2);
+    for (int ch = 0; ch < CW / 16; ++ch) {
+      uint32_t r[16], r2[16];
+      tmem_ld16(lane_addr + half * CW + ch * 16, r);
+      tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
+      for (int c = 0; c < 16; c += 2) {
         const __half2 h = __floats2half2_rn(__int2float_rn((int)r[c]) * c_s, __int2float_rn((int)r[c + 1]) * c_s);
-        sh[ch * 16 + c / 2] = h;
+        sh[ch * 8 + c / 2] = h;
         const float2 f = __half22float2(h);
         const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
         amax_p = fmaxf(amax_p, fmaxf(p0, p1));
@@ -229,13 +234,15 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     tc_fence_before();
     if (leader) tma_store_wait_read();                             // the dQ staging tile may be rewritten after this barrier
-    named_bar_sync(1, 256);                                        // amax partials visible; dV/dK partial columns drained
+    named_bar_sync(1, NT);                                        // amax partials visible; dV/dK partial columns drained
     if (leader && t > 0) { tc_fence_after(); issue_dq((t - 1) & 1); }
     // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
     amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) { amax_p = fmaxf(amax_p, red_p[ph][w]); amax_ds = fmaxf(amax_ds, red_ds[ph][w]); }
-    const float rs_row = rowsum_ds[ph][0][row] + rowsum_ds[ph][1][row];      // full-row sum of dS (query row = lane)
+    for (int w = 1; w < NW; ++w) { amax_p = fmaxf(amax_p, red_p[ph][w]); amax_ds = fmaxf(amax_ds, red_ds[ph][w]); }
+    float rs_row = 0.f;                                                      // full-row sum of dS (query row = lane)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) rs_row += rowsum_ds[ph][g][row];
     const float sP = amax_p * (1.0f / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
     const float inv_p = amax_p > 0.f ? __fdividef(127.0f, amax_p) : 0.f;
     const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
@@ -243,35 +250,32 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
     uint8_t* ds_tile = smem + L::off_ds + ph * (128 * 128);
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t r2[32];
-      tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, r2);
+    for (int ch = 0; ch < CW / 16; ++ch) {
+      uint32_t r2[16];
+      tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
       tmem_ld_wait();
+      uint32_t wp[4], wd[4];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t wp[4], wd[4];
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t bp[4], bd[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t bp[4], bd[4];
-#pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int c = g * 16 + q4 * 4 + e;
-            const float2 f = __half22float2(sh[ch * 16 + c / 2]);
-            const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
-            const float d0 = p0 * fmaf(__int2float_rn((int)r2[c]), c_dp, -dlt);
-            const float d1 = p1 * fmaf(__int2float_rn((int)r2[c + 1]), c_dp, -dlt);
-            bp[e] = __float_as_uint(__fmaf_rz(p0, inv_p, 8388608.0f));          // P >= 0: low byte = trunc(P / sP)
-            bp[e + 1] = __float_as_uint(__fmaf_rz(p1, inv_p, 8388608.0f));
-            bd[e] = (uint32_t)__float2int_rz(d0 * inv_ds);
-            bd[e + 1] = (uint32_t)__float2int_rz(d1 * inv_ds);
-          }
-          wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
-          wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
+        for (int e = 0; e < 4; e += 2) {
+          const int c = q4 * 4 + e;
+          const float2 f = __half22float2(sh[ch * 8 + c / 2]);
+          const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
+          const float d0 = p0 * fmaf(__int2float_rn((int)r2[c]), c_dp, -dlt);
+          const float d1 = p1 * fmaf(__int2float_rn((int)r2[c + 1]), c_dp, -dlt);
+          bp[e] = __float_as_uint(__fmaf_rz(p0, inv_p, 8388608.0f));          // P >= 0: low byte = trunc(P / sP)
+          bp[e + 1] = __float_as_uint(__fmaf_rz(p1, inv_p, 8388608.0f));
+          bd[e] = (uint32_t)__float2int_rz(d0 * inv_ds);
+          bd[e + 1] = (uint32_t)__float2int_rz(d1 * inv_ds);
         }
-        const uint32_t off = swz128(row, half * 64 + ch * 32 + g * 16);
-        *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-        *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
+        wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
       }
+      const uint32_t off = swz128(row, half * CW + ch * 16);
+      *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+      *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
     }
     // ---- drain dQ of the previous tile (its MMA ran while pass 2 executed)
     if (t > 0) {
@@ -281,7 +285,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    named_bar_sync(2, 256);                                        // P / dS tiles and the dQ staging tile are complete
+    named_bar_sync(2, NT);                                        // P / dS tiles and the dQ staging tile are complete
     if (leader) {
       tc_fence_after();
       if (t > 0) reduce_dq(t - 1);
@@ -302,14 +306,14 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   drain_dv_dk(c_dv_prev, c_dk_prev);
   tc_fence_before();
   if (leader) tma_store_wait_read();
-  named_bar_sync(1, 256);
+  named_bar_sync(1, NT);
   if (leader) { tc_fence_after(); issue_dq((nq - 1) & 1); }
   mbar_wait(&dq_full, (nq - 1) & 1);
   tc_fence_after();
   drain_dq(c_dq_prev, rs_prev);
   fence_proxy_async_smem();
   tc_fence_before();
-  named_bar_sync(2, 256);
+  named_bar_sync(2, NT);
   if (leader) { reduce_dq(nq - 1); tma_store_wait_all(); }
   // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
   const size_t krow = head_row0 + (size_t)j * 128 + row;
@@ -335,7 +339,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
-template <int D>
+template <int D, int NG>
 static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
                            const Int8BwdParams& p, int BH, cudaStream_t st) {
   using L = Int8BwdSmem<D>;
@@ -352,11 +356,11 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   uint64_t strq[1] = {(uint64_t)D * 4};
   uint32_t boxq[2] = {32, 128};
   if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
-  auto kern = int8_bwd_kernel<D>;
+  auto kern = int8_bwd_kernel<D, NG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.S / 128, BH);
-  kern<<<grid, 256, L::total, st>>>(tq, tk, tv, tdo, tdq, p);
+  kern<<<grid, 128 * NG, L::total, st>>>(tq, tk, tv, tdo, tdq, p);
   return qa_check_launch("qa_int8_bwd");
 }
 
@@ -381,6 +385,10 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
-  return D == 128 ? launch_int8_bwd<128>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
-                  : launch_int8_bwd<64>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
+  const char* env = getenv("QA_INT8_BWD_NG");
+  const int ng = env ? atoi(env) : 4;
+  if (D == 128) return ng == 2 ? launch_int8_bwd<128, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+                               : launch_int8_bwd<128, 4>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
+  return ng == 2 ? launch_int8_bwd<64, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+                 : launch_int8_bwd<64, 4>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
 }

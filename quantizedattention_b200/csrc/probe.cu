@@ -152,3 +152,41 @@ extern "C" int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const un
                                                            rank > 2 ? coords[2] : 0);
   return qa_check_launch("qa_probe_tma");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// TMEM -> register read bandwidth probe: every warp streams tcgen05.ld.32x32b.x32 over its lane quadrant.
+// Gives the measured ceiling for kernels whose accumulators must be drained from TMEM every tile.
+// ---------------------------------------------------------------------------------------------------------
+namespace qa {
+__global__ void __launch_bounds__(1024, 1) probe_tmem_bw_kernel(uint32_t* sink, int iters) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t lane_addr = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + ((warp >> 2) * 128 + c * 32) % 512, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc ^= r[i];
+    }
+  }
+  if (acc == 0x12345678u) sink[threadIdx.x] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
+}
+}  // namespace qa
+
+// Launches `blocks` CTAs of `threads` threads; each warp issues iters * 4 loads of 4 KiB.
+extern "C" int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream) {
+  if (threads % 128 || threads > 1024) return qa_fail(QA_ERR_SHAPE, "qa_probe_tmem_bw: threads must be a multiple of 128");
+  qa::probe_tmem_bw_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((uint32_t*)sink, iters);
+  return qa_check_launch("qa_probe_tmem_bw");
+}

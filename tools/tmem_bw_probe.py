@@ -1,0 +1,30 @@
+"""Measure TMEM->register read bandwidth per SM (bytes/clk) for 4..32 warps per CTA, one CTA per SM."""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from quantizedattention_b200 import _lib  # noqa: E402
+
+L = _lib.lib()
+sink = torch.zeros(2048, dtype=torch.int32, device="cuda")
+props = torch.cuda.get_device_properties(0)
+sms = props.multi_processor_count
+out = {}
+for threads in (128, 256, 512, 1024):
+    iters = 20000
+    L.qa_probe_tmem_bw(_lib.ptr(sink), sms, threads, 100, _lib.cur_stream())
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _lib.check(L.qa_probe_tmem_bw(_lib.ptr(sink), sms, threads, iters, _lib.cur_stream()), "probe")
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    bytes_per_sm = (threads // 32) * iters * 4 * 4096
+    clk_hz = 1.965e9
+    out[f"{threads}_threads"] = {"ms": ms, "GBps_per_sm": bytes_per_sm / ms / 1e6,
+                                 "bytes_per_clk_per_sm_at_1965MHz": bytes_per_sm / (ms * 1e-3) / clk_hz}
+print(json.dumps(out, indent=1))
+json.dump(out, open("gpurun_out/tmem_bw.json", "w"), indent=1)
