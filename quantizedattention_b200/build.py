@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqattn.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["host.cu", "quant.cu", "probe.cu", "attn_int8_fwd.cu", "attn_bf16_fwd.cu", "attn_jvp.cu", "attn_int8_bwd.cu", "attn_bf16_bwd.cu", "prepass.cu"]
+SOURCES = ["host.cu", "quant.cu", "probe.cu", "attn_int8_fwd.cu", "attn_bf16_fwd.cu", "attn_bf16_fwd2.cu", "attn_jvp.cu", "attn_int8_bwd.cu", "attn_bf16_bwd.cu", "prepass.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",
          "-lcudart", "-Xptxas", "-v"]

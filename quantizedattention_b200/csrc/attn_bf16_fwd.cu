@@ -346,6 +346,11 @@ static int launch_bf16_fwd(const void* q, const void* k, const void* v, const Bf
   return r;
 }
 
+// two-query-tile variant (attn_bf16_fwd2.cu)
+template <int D, int STAGES>
+int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
+                     float qk_scale, cudaStream_t st);
+
 }  // namespace qa
 
 using namespace qa;
@@ -362,6 +367,17 @@ extern "C" int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_b
   p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((nsplit == 0 || nsplit == 3) && Sq % 256 == 0) {           // default schedule: two query tiles per CTA, P and O in TMEM
+    int rc = D == 128 ? launch_bf16_fwd2<128, 2>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, st)
+                      : launch_bf16_fwd2<64, 3>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, st);
+    if (rc) return rc;
+    if (causal) {
+      bf16_row0_fixup_kernel<<<BH, D, 0, st>>>((const __nv_bfloat16*)v_bf16, p.O, p.lse, Sq, Sk, D);
+      rc = qa_check_launch("qa_bf16_fwd(row0)");
+    }
+    return rc;
+  }
+  if (nsplit == 0 || nsplit == 3) nsplit = 2;
   if (D == 128) return nsplit == 2 ? launch_bf16_fwd<128, 2, 2, 1>(q_f16, k_f16, v_bf16, p, BH, st)
                                    : launch_bf16_fwd<128, 1, 2, 1>(q_f16, k_f16, v_bf16, p, BH, st);
   return nsplit == 2 ? launch_bf16_fwd<64, 2, 3, 2>(q_f16, k_f16, v_bf16, p, BH, st)

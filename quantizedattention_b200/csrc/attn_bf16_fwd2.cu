@@ -1,0 +1,321 @@
+// bf16 bias-corrected flash attention forward, two-query-tile variant (used when Sq % 256 == 0).
+// Same numerics as attn_bf16_fwd.cu (reference attention_bf16.py:195-294, contract mode); different schedule:
+//   * one CTA owns TWO 128-row query tiles (A, B) of one head and shares every K/V tile between them;
+//   * each softmax warpgroup owns one query tile, one thread per row (128 columns): no cross-warp exchange;
+//   * S_A / S_B live in TMEM (one buffer each): while warpgroup A runs its softmax the tensor core computes S_B;
+//   * P is written back to TMEM over the S columns (bf16, 2 per column) and consumed as the A operand of the
+//     P V MMA straight from TMEM (no shared-memory round trip, no proxy fence);
+//   * O_A / O_B stay resident in TMEM; the correction warpgroup rescales them only when a row maximum moved.
+// TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,256+D)  O_B [384,384+D).
+#include "qa_ptx.cuh"
+#include "qa_host.h"
+
+namespace qa {
+
+constexpr int kAtom2 = 128 * 128;
+
+template <int D, int STAGES>
+struct Bf16Fwd2Smem {
+  static constexpr int kTile = 128 * D * 2;
+  static constexpr int off_q = 0;                          // Q_A, Q_B
+  static constexpr int off_k = off_q + 2 * kTile;
+  static constexpr int off_v = off_k + STAGES * kTile;
+  static constexpr int total = off_v + STAGES * kTile + 1024;
+};
+
+struct Bf16Fwd2Params {
+  float* O;
+  float* lse;
+  int Sq, Sk, causal;
+  float qk_scale;
+};
+
+__device__ __forceinline__ float bf2_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf2_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ __nv_bfloat162 u2bf(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+__device__ __forceinline__ uint32_t bf2u(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+template <int D, int STAGES>
+__global__ void __launch_bounds__(448, 1)
+bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, Bf16Fwd2Params p) {
+  using L = Bf16Fwd2Smem<D, STAGES>;
+  constexpr int kDAtoms = D / 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
+  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_ready[2], sc_full[2][2], sc_empty[2][2], fin_full[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float row_sc[2][2][128];          // [query tile][parity][row]
+  __shared__ float l_fin[2][128], m_fin[2][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y;
+  const int pt = (int)gridDim.x - 1 - (int)blockIdx.x;           // pair of query tiles; heaviest causal pairs first
+  const int q0 = pt * 256;
+  const int nk_full = p.Sk / 128;
+  // per query tile: number of k-tiles that contain at least one visible key (strict causal: key < query)
+  const int nkx[2] = {p.causal ? min(nk_full, 2 * pt + 1) : nk_full, p.causal ? min(nk_full, 2 * pt + 2) : nk_full};
+  const int nk = nkx[1];
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&o_full[x], 1); mbar_init(&o_ready[x], 4);
+      mbar_init(&fin_full[x], 4);
+      for (int b = 0; b < 2; ++b) { mbar_init(&sc_full[x][b], 4); mbar_init(&sc_empty[x][b], 4); }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp < 8) {
+    // =========================== softmax warpgroups: warps 0-3 -> tile A, 4-7 -> tile B ===========================
+    const int x = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t s_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + x * 128;
+    const int grow = q0 + x * 128 + row;                          // query index inside the head
+    const int qt = 2 * pt + x;                                    // this tile's diagonal k-tile
+    const int nkq = nkx[x];
+    __nv_bfloat16 m_bf = __float2bfloat16(-INFINITY);
+    float l = 1.0f;                                               // attention_bf16.py:198
+    const uint32_t ninf2 = 0xff80ff80u;
+    for (int j = 0; j < nkq; ++j) {
+      const bool diag = p.causal && (j == qt);
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      // ---- pass 1: u = bf16(bf16(S) * qk_scale), masked; top-2 of the row tile
+      uint32_t u2[64];
+      __nv_bfloat162 t1 = u2bf(ninf2), t2 = u2bf(ninf2);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(s_addr + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t sb = pack2_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          uint32_t u = pack2_bf16(bf2_lo(sb) * p.qk_scale, bf2_hi(sb) * p.qk_scale);
+          if (diag) {
+            const int key = j * 128 + ch * 32 + 2 * i;
+            if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
+            if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+          }
+          u2[ch * 16 + i] = u;
+          const __nv_bfloat162 xv = u2bf(u);
+          t2 = __hmax2(t2, __hmin2(t1, xv));
+          t1 = __hmax2(t1, xv);
+        }
+      }
+      const __nv_bfloat16 a1 = __low2bfloat16(t1), b1 = __high2bfloat16(t1), a2 = __low2bfloat16(t2), b2 = __high2bfloat16(t2);
+      const __nv_bfloat16 top1 = __hmax(a1, b1);
+      const __nv_bfloat16 top2 = __hmax(__hmin(a1, b1), __hmax(a2, b2));
+      // ---- bias-corrected running max (attention_bf16.py:236-264, predicate in the scaled domain)
+      __nv_bfloat16 m_new = __hmax(m_bf, top1);
+      const __nv_bfloat16 thr = __float2bfloat16(__bfloat162float(m_new) - 1e-3f);
+      const bool many = (top2 >= thr) && (top1 >= thr);
+      const float mf = __bfloat162float(m_new);
+      if (many && mf > 0.f) m_new = __float2bfloat16(2.0f * mf);
+      else if (many && mf < 0.f) m_new = __float2bfloat16(0.f);
+      const float resc = __bfloat162float(__float2bfloat16(ex2_approx(__bfloat162float(__hsub(m_bf, m_new)))));
+      m_bf = m_new;
+      if (j > 0) {                                                // tile 0 overwrites O: nothing to rescale
+        const int sb = (j - 1) & 1;
+        mbar_wait(&sc_empty[x][sb], (((j - 1) >> 1) & 1) ^ 1);
+        row_sc[x][sb][row] = resc;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_full[x][sb]);
+      }
+      // ---- pass 2: P = bf16(exp2(bf16(u - m'))) written back over the S columns (2 per column), l += sum(P)
+      const __nv_bfloat162 m2 = __bfloat162bfloat162(m_new);
+      float lsum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t t = bf2u(__hsub2(u2bf(u2[ch * 32 + i]), m2));
+          const uint32_t pp = pack2_bf16(ex2_approx(bf2_lo(t)), ex2_approx(bf2_hi(t)));
+          lsum += bf2_lo(pp) + bf2_hi(pp);
+          w[i] = pp;
+        }
+        tmem_st32(s_addr + ch * 32, w);
+      }
+      tmem_st_wait();
+      l = l * resc + lsum;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+    }
+    l_fin[x][row] = l;
+    m_fin[x][row] = __bfloat162float(m_bf);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&fin_full[x]);
+  } else if (warp < 12) {
+    // =========================== correction warpgroup (both query tiles) ===========================
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int j = 1; j < nk; ++j) {
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        if (j >= nkx[x]) continue;
+        const int sb = (j - 1) & 1;
+        mbar_wait(&sc_full[x][sb], ((j - 1) >> 1) & 1);
+        const float resc = row_sc[x][sb][row];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_empty[x][sb]);
+        if (__any_sync(0xffffffffu, resc != 1.0f)) {             // O *= rescale (:280) only when a row maximum moved
+          mbar_wait(&o_full[x], (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ch = 0; ch < D / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(lane_addr + 256 + x * 128 + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
+            tmem_st32(lane_addr + 256 + x * 128 + ch * 32, r);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_ready[x]);
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      mbar_wait(&fin_full[x], 0);
+      mbar_wait(&o_full[x], (nkx[x] - 1) & 1);
+      tc_fence_after();
+      const float l = l_fin[x][row];
+      const size_t gr = (size_t)bh * p.Sq + q0 + x * 128 + row;
+      const float inv_l = 1.0f / l;
+      float* dst = p.O + gr * D;
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(lane_addr + 256 + x * 128 + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + ch * 32 + i) =
+              make_float4(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l, __uint_as_float(r[i + 2]) * inv_l,
+                          __uint_as_float(r[i + 3]) * inv_l);
+      }
+      p.lse[gr] = m_fin[x][row] + log2f(l);                                  // attention_bf16.py:288
+    }
+  } else if (warp == 12) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+      mbar_expect_tx(&q_full, 2 * L::kTile);
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a)
+          tma_load_2d(smem + L::off_q + x * L::kTile + a * kAtom2, &tm_q, &q_full, a * 64, bh * p.Sq + q0 + x * 128);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (j / STAGES) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], L::kTile);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a)
+          tma_load_2d(smem + L::off_k + s * L::kTile + a * kAtom2, &tm_k, &k_full[s], a * 64, bh * p.Sk + j * 128);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], L::kTile);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a)
+          tma_load_2d(smem + L::off_v + s * L::kTile + a * kAtom2, &tm_v, &v_full[s], a * 64, bh * p.Sk + j * 128);
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc(1, 0, 0, 0, 0, 128, 128);        // f32 += f16 x f16, K-major
+      constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // f32 += bf16 (TMEM) x bf16 (V MN-major)
+      auto issue_qk = [&](int x, int j) {                                        // S_x = Q_x K_j^T
+        const int s = j % STAGES;
+        const uint32_t q_addr = smem_u32(smem + L::off_q + x * L::kTile), k_addr = smem_u32(smem + L::off_k + s * L::kTile);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t o = (k >> 2) * kAtom2 + (k & 3) * 32;
+          umma_f16_ss(tbase + x * 128, umma_smem_desc(q_addr + o, 16, 1024, kSwz128), umma_smem_desc(k_addr + o, 16, 1024, kSwz128),
+                      idesc_qk, k > 0);
+        }
+        umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int j) {                                        // O_x += P_x V_j, P from TMEM
+        const int s = j % STAGES;
+        mbar_wait(&p_full[x], j & 1);
+        if (j > 0) mbar_wait(&o_ready[x], (j - 1) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16_ts(tbase + 256 + x * 128, tbase + x * 128 + k * 8, umma_smem_desc(v_addr + k * 2048, kAtom2, 1024, kSwz128),
+                      idesc_pv, (j > 0) || (k > 0));
+        umma_commit(&o_full[x]);
+      };
+      mbar_wait(&q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j % STAGES;
+        const bool more = (j + 1 < nk);
+        mbar_wait(&v_full[s], (j / STAGES) & 1);
+        if (more) { mbar_wait(&k_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1); }
+        if (j < nkx[0]) {
+          issue_pv(0, j);
+          if (j + 1 < nkx[0]) issue_qk(0, j + 1);                // executes after P_A has been consumed (in-order pipe)
+        }
+        issue_pv(1, j);
+        umma_commit(&v_empty[s]);
+        if (more) { issue_qk(1, j + 1); umma_commit(&k_empty[(j + 1) % STAGES]); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) tmem_dealloc<512>(tbase);
+}
+
+template <int D, int STAGES>
+int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
+                     float qk_scale, cudaStream_t st) {
+  using L = Bf16Fwd2Smem<D, STAGES>;
+  CUtensorMap tq, tk, tv;
+  uint64_t dq[2] = {(uint64_t)D, (uint64_t)BH * Sq}, dk[2] = {(uint64_t)D, (uint64_t)BH * Sk};
+  uint64_t str[1] = {(uint64_t)D * 2};
+  uint32_t box[2] = {64, 128};
+  int rc;
+  if ((rc = qa_make_tmap(&tq, q, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dq, str, box, 3))) return rc;
+  if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
+  if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
+  Bf16Fwd2Params p;
+  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.qk_scale = qk_scale;
+  auto kern = bf16_fwd2_kernel<D, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  dim3 grid(Sq / 256, BH);
+  kern<<<grid, 448, L::total, st>>>(tq, tk, tv, p);
+  return qa_check_launch("qa_bf16_fwd(2 query tiles)");
+}
+
+template int launch_bf16_fwd2<128, 2>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
+template int launch_bf16_fwd2<64, 3>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
+
+}  // namespace qa

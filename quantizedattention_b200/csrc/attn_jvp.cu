@@ -3,9 +3,12 @@
 // operands and fp32 TMEM accumulators (LEDGER J-2; operands are converted fp32 -> bf16 by qa_cast_f32):
 //   S  = Q K^T                      (TMEM cols   0..127)
 //   tS = tQ K^T + Q tK^T            (TMEM cols 128..255, two chained MMAs into one accumulator)
-//   Opart  = P V                    (TMEM cols 256..)
-//   ABpart = P tV + H V, H = P*tS   (TMEM cols 384.., two chained MMAs: A and B of the reference share one tile)
+//   O  += P V                       (TMEM cols 256..256+D, resident accumulator)
+//   AB += P tV + H V, H = P*tS      (TMEM cols 256+D.., two chained MMAs: A and B of the reference share one tile)
 // Softmax state (m, l, r = rowsum(H)) is fp32 as in the reference.  tO = (AB - r*O) / l,  O = O / l.
+// The O and AB accumulators stay RESIDENT in TMEM across k-tiles; the correction warpgroup multiplies them by the
+// rescale factor only when a row maximum moved (exp2(0) == 1 exactly otherwise), and the softmax warps keep the S
+// tile in registers between the max pass and the exp pass, so steady-state TMEM->register traffic is S + tS only.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
 
@@ -36,21 +39,22 @@ __device__ __forceinline__ uint32_t jpack_bf16(float a, float b) {
 }
 
 template <int D, int NSPLIT>
-__global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
+__global__ void __launch_bounds__(128 * NSPLIT + 192, 1)
 jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_tq,
                const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_tk,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_tv, JvpParams p) {
   using L = JvpSmem<D>;
   constexpr int NC = 128 / NSPLIT;
-  constexpr int DC = D / NSPLIT;
   constexpr int kSoftWarps = 4 * NSPLIT;
+  constexpr int kProdWarp = kSoftWarps + 4;
+  constexpr int kMmaWarp = kSoftWarps + 5;
   constexpr int kDAtoms = D / 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty;
-  __shared__ uint64_t s_full, s_empty, p_full, p_empty, o_full, o_empty, sc_full, sc_empty, fin_full;
+  __shared__ uint64_t s_full, s_empty, p_full, p_empty, o_full, o_ready, sc_full[2], sc_empty[2], fin_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float row_sc[128];
+  __shared__ float row_sc[2][128];
   __shared__ float xmax[2][2][128];
   __shared__ float l_part[2][128], r_part[2][128], m_fin[128];
 
@@ -64,12 +68,12 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
     mbar_init(&s_full, 1); mbar_init(&s_empty, kSoftWarps);
     mbar_init(&p_full, kSoftWarps); mbar_init(&p_empty, 1);
-    mbar_init(&o_full, 1); mbar_init(&o_empty, kSoftWarps);
-    mbar_init(&sc_full, 4); mbar_init(&sc_empty, kSoftWarps);
+    mbar_init(&o_full, 1); mbar_init(&o_ready, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], 4); }
     mbar_init(&fin_full, kSoftWarps);
     fence_mbar_init();
   }
-  if (warp == 8 * NSPLIT + 1) tmem_alloc<512>(&tmem_base_s);
+  if (warp == kMmaWarp) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -87,13 +91,14 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       mbar_wait(&s_full, ph);
       tc_fence_after();
       float mx = -INFINITY;
+      uint32_t sreg[NC];                                          // S row segment stays in registers between the passes
 #pragma unroll
       for (int ch = 0; ch < NC / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(lane_addr + c0 + ch * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) { sreg[ch * 32 + i] = r[i]; mx = fmaxf(mx, __uint_as_float(r[i])); }
       }
       if (NSPLIT == 2) {
         xmax[ph][split][row] = mx;
@@ -103,11 +108,12 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       const float m_new = fmaxf(m, mx * p.qk_scale);             // :155-158
       const float resc = ex2_approx(m - m_new);                   // :164
       m = m_new;
-      if (split == 0) {
-        mbar_wait(&sc_empty, ph ^ 1);
-        row_sc[row] = resc;
+      if (split == 0 && j > 0) {                                  // tile 0 overwrites O / AB: nothing to rescale
+        const int sb = (j - 1) & 1;
+        mbar_wait(&sc_empty[sb], (((j - 1) >> 1) & 1) ^ 1);
+        row_sc[sb][row] = resc;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sc_full);
+        if (lane == 0) mbar_arrive(&sc_full[sb]);
       }
       mbar_wait(&p_empty, ph ^ 1);
       float lsum = 0.f, hsum = 0.f;
@@ -115,8 +121,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       uint8_t* hbase = smem + L::off_p + L::kPBytes;
 #pragma unroll
       for (int ch = 0; ch < NC / 32; ++ch) {
-        uint32_t rs[32], rt[32];
-        tmem_ld32(lane_addr + c0 + ch * 32, rs);
+        uint32_t rt[32];
         tmem_ld32(lane_addr + 128 + c0 + ch * 32, rt);
         tmem_ld_wait();
 #pragma unroll
@@ -125,8 +130,8 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = g * 8 + e * 2;
-            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[i]), p.qk_scale, -m_new));        // :160-161
-            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[i + 1]), p.qk_scale, -m_new));
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[ch * 32 + i]), p.qk_scale, -m_new));        // :160-161
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[ch * 32 + i + 1]), p.qk_scale, -m_new));
             const float h0 = p0 * (__uint_as_float(rt[i]) * p.sm_scale);                           // :153, :176
             const float h1 = p1 * (__uint_as_float(rt[i + 1]) * p.sm_scale);
             lsum += p0 + p1;
@@ -152,60 +157,63 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (split == 0) m_fin[row] = m;
     __syncwarp();
     if (lane == 0) mbar_arrive(&fin_full);
-  } else if (warp < 2 * kSoftWarps) {
-    // =========================== correction warps ===========================
-    const int cw = warp - kSoftWarps;
-    const int split = cw >> 2;
+  } else if (warp < kProdWarp) {
+    // =========================== correction warpgroup (4 warps, thread = row) ===========================
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    const int d0 = split * DC;
-    float accO[DC], accT[DC];
-#pragma unroll
-    for (int i = 0; i < DC; ++i) { accO[i] = 0.f; accT[i] = 0.f; }
-    for (int j = 0; j < nk; ++j) {
-      const uint32_t ph = j & 1;
-      mbar_wait(&sc_full, ph);
-      const float resc = row_sc[row];
+    for (int j = 1; j < nk; ++j) {
+      const int sb = (j - 1) & 1;
+      mbar_wait(&sc_full[sb], ((j - 1) >> 1) & 1);
+      const float resc = row_sc[sb][row];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sc_empty);
-      mbar_wait(&o_full, ph);
-      tc_fence_after();
+      if (lane == 0) mbar_arrive(&sc_empty[sb]);
+      if (__any_sync(0xffffffffu, resc != 1.0f)) {               // O, A, B *= rescale (:167, :173, :180)
+        mbar_wait(&o_full, (j - 1) & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < DC / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + 256 + d0 + ch * 32, r);
-        tmem_ld_wait();
+        for (int ch = 0; ch < 2 * D / 32; ++ch) {                // O at 256.., AB at 256 + D..
+          uint32_t r[32];
+          tmem_ld32(lane_addr + 256 + ch * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) accO[ch * 32 + i] = fmaf(accO[ch * 32 + i], resc, __uint_as_float(r[i]));
-        tmem_ld32(lane_addr + 384 + d0 + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) accT[ch * 32 + i] = fmaf(accT[ch * 32 + i], resc, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
+          tmem_st32(lane_addr + 256 + ch * 32, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
       }
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty);
+      if (lane == 0) mbar_arrive(&o_ready);
     }
     mbar_wait(&fin_full, 0);
+    mbar_wait(&o_full, (nk - 1) & 1);
+    tc_fence_after();
     float l = l_part[0][row], rr = r_part[0][row];
     if (NSPLIT == 2) { l += l_part[1][row]; rr += r_part[1][row]; }
     const size_t gr = (size_t)bh * p.Sq + q0 + row;
     const float inv_l = 1.0f / l;
-    float* dO_ = p.O + gr * D + d0;
-    float* dT_ = p.tO + gr * D + d0;
+    float* dO_ = p.O + gr * D;
+    float* dT_ = p.tO + gr * D;
 #pragma unroll
-    for (int i = 0; i < DC; i += 4) {
-      float o[4], t[4];
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t ro[32], rt[32];
+      tmem_ld32(lane_addr + 256 + ch * 32, ro);
+      tmem_ld32(lane_addr + 256 + D + ch * 32, rt);
+      tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        o[e] = accO[i + e] * inv_l;                               // :188
-        t[e] = (accT[i + e] - rr * o[e]) * inv_l;                 // :190  (A + B - r*O) / l
+      for (int i = 0; i < 32; i += 4) {
+        float o[4], t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[e] = __uint_as_float(ro[i + e]) * inv_l;                          // :188
+          t[e] = (__uint_as_float(rt[i + e]) - rr * o[e]) * inv_l;            // :190  (A + B - r*O) / l
+        }
+        *reinterpret_cast<float4*>(dO_ + ch * 32 + i) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dT_ + ch * 32 + i) = make_float4(t[0], t[1], t[2], t[3]);
       }
-      *reinterpret_cast<float4*>(dO_ + i) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(dT_ + i) = make_float4(t[0], t[1], t[2], t[3]);
     }
-    if (split == 0) p.lse[gr] = m_fin[row] + log2f(l);            // :183
-  } else if (warp == 8 * NSPLIT) {
+    p.lse[gr] = m_fin[row] + log2f(l);                            // :183
+  } else if (warp == kProdWarp) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       mbar_expect_tx(&q_full, 2 * L::kTile);
@@ -243,7 +251,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       auto issue_pv = [&](int t) {
         const uint32_t ph = t & 1;
         mbar_wait(&v_full, ph);
-        mbar_wait(&o_empty, ph ^ 1);
+        if (t > 0) mbar_wait(&o_ready, (t - 1) & 1);              // accumulators rescaled (if needed) for tile t
         mbar_wait(&p_full, ph);
         tc_fence_after();
 #pragma unroll
@@ -253,9 +261,9 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           const uint64_t hd = umma_smem_desc(h_addr + ao, 16, 1024, kSwz128);
           const uint64_t vd = umma_smem_desc(v_addr + k * 2048, kJAtom, 1024, kSwz128);
           const uint64_t tvd = umma_smem_desc(tv_addr + k * 2048, kJAtom, 1024, kSwz128);
-          umma_f16_ss(tbase + 256, pd, vd, idesc_pv, k > 0);        // Opart  = P V
-          umma_f16_ss(tbase + 384, pd, tvd, idesc_pv, k > 0);       // ABpart = P tV
-          umma_f16_ss(tbase + 384, hd, vd, idesc_pv, 1);            //        + H V
+          umma_f16_ss(tbase + 256, pd, vd, idesc_pv, (t > 0) || (k > 0));       // O  += P V
+          umma_f16_ss(tbase + 256 + D, pd, tvd, idesc_pv, (t > 0) || (k > 0));  // AB += P tV
+          umma_f16_ss(tbase + 256 + D, hd, vd, idesc_pv, 1);                    //     + H V
         }
         umma_commit(&o_full);
         umma_commit(&v_empty);
@@ -286,7 +294,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tbase);
 }
 
 template <int D, int NSPLIT>
@@ -304,7 +312,7 @@ static int launch_jvp(const void* const* in6, const JvpParams& p, int BH, cudaSt
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / 128, BH);
-  kern<<<grid, 256 * NSPLIT + 64, L::total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  kern<<<grid, 128 * NSPLIT + 192, L::total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   return qa_check_launch("qa_jvp_fwd");
 }
 

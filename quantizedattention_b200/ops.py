@@ -184,7 +184,7 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
     return cast_f32(dq_ws, torch.float16), dk, dv
 
 
-def bf16_fwd(q, k, v, causal: bool, nsplit: int = 2):
+def bf16_fwd(q, k, v, causal: bool, nsplit: int = 0):
     """Bias-corrected bf16 flash attention forward (qa_bf16_fwd).  q,k fp16, v bf16 [B,H,S,D] ->
     (O fp32 [B,H,Sq,D], lse fp32 [B*H,Sq])."""
     _need_cuda(q, k, v)

@@ -10,9 +10,9 @@ def _stats(a, b):
     return (a - b).abs().max().item(), ((a - b) ** 2).mean().item()
 
 
-@pytest.mark.parametrize("nsplit", [1, 2])
+@pytest.mark.parametrize("nsplit", [1, 2, 3])
 @pytest.mark.parametrize("causal", [False, True])
-@pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128)])
+@pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128), (1, 2, 1024, 128)])
 def test_bf16_fwd_matches_oracle(shape, causal, nsplit):
     from oracle import bf16_ref
     from oracle.baseline import baseline_lse_log2, baseline_pytorch_attention

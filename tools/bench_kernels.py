@@ -46,7 +46,7 @@ def bf16(B=4, H=16, S=4096, D=128, causal=1):
     dO = torch.randn(B, H, S, D, device="cuda")
     res = {}
     f = 0.5 if causal else 1.0
-    for ns in (1, 2):
+    for ns in (1, 2, 3):
         med, best = timeit(lambda: ops.bf16_fwd(q, k, v, bool(causal), nsplit=ns))
         res[f"bf16_fwd_nsplit{ns}"] = {"ms": med, "TFLOPS": f * 4 * B * H * S * S * D / med / 1e9}
     O, lse = ops.bf16_fwd(q, k, v, bool(causal))

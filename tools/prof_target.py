@@ -1,0 +1,28 @@
+"""Small single-kernel targets for ncu.  Usage: python tools/prof_target.py bf16_fwd|jvp|int8_fwd"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from quantizedattention_b200 import ops  # noqa: E402
+
+which = sys.argv[1]
+torch.manual_seed(0)
+if which == "bf16_fwd":
+    B, H, S, D = 4, 16, 4096, 128
+    q, k = [torch.randn(B, H, S, D, device="cuda", dtype=torch.float16) for _ in range(2)]
+    v = torch.randn(B, H, S, D, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.bf16_fwd(q, k, v, False)
+elif which == "jvp":
+    t = [torch.randn(4, 16, 4096, 64, device="cuda") for _ in range(6)]
+    for _ in range(3):
+        ops.jvp_fwd(*t)
+elif which == "int8_fwd":
+    BH, S, D = 64, 8192, 128
+    q, k, v = [torch.randn(BH, S, D, device="cuda", dtype=torch.float16) for _ in range(3)]
+    qi, sq = ops.quant_block(q, 128); ki, sk = ops.quant_block(k, 128); vi, sv = ops.quant_block(v, 128)
+    for _ in range(3):
+        ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D)
+torch.cuda.synchronize()
+print("ok")
