@@ -9,6 +9,7 @@
 // fp32 (TF32 tl.dot) -- tolerance-level parity, stated in tests/test_bf16_bwd_gpu.py.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <type_traits>
 
 namespace qa {
 
@@ -139,37 +140,42 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool diag = p.causal && (i == j);
       mbar_wait(&sd_full, ph);
       tc_fence_after();
+      auto compute = [&](auto masked) {                            // masked = diagonal tile or causal query row 0
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t rs[32], rp[32];
-        tmem_ld32(lane_addr + half * 64 + ch * 32, rs);
-        tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, rp);
-        tmem_ld_wait();
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(lane_addr + half * 64 + ch * 32, rs);
+          tmem_ld32(lane_addr + 128 + half * 64 + ch * 32, rp);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t wp[4], wd[4];
+          for (int g = 0; g < 4; ++g) {
+            uint32_t wp[4], wd[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float pv[2], ds[2];
+            for (int e = 0; e < 4; ++e) {
+              float pv[2], ds[2];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int c = g * 8 + e * 2 + t;
-              float P = ex2_approx(fmaf(__uint_as_float(rs[c]), p.qk_scale, -lse));            // :391-392
-              if (diag && (j * 128 + half * 64 + ch * 32 + c >= qi)) P = 0.f;                   // strict causal, weight 0
-              if (p.causal && qi == 0) P = 0.f;                                                 // row 0: handled by the fixup
-              pv[t] = P;
-              ds[t] = P * (__uint_as_float(rp[c]) - dlt);                                        // dS = P*(dP - delta)
+              for (int t = 0; t < 2; ++t) {
+                const int c = g * 8 + e * 2 + t;
+                float P = ex2_approx(fmaf(__uint_as_float(rs[c]), p.qk_scale, -lse));            // :391-392
+                if (decltype(masked)::value) {
+                  if (diag && (j * 128 + half * 64 + ch * 32 + c >= qi)) P = 0.f;               // strict causal, weight 0
+                  if (qi == 0) P = 0.f;                                                         // row 0: handled by the fixup
+                }
+                pv[t] = P;
+                ds[t] = P * (__uint_as_float(rp[c]) - dlt);                                      // dS = P*(dP - delta)
+              }
+              __nv_bfloat162 pb = __floats2bfloat162_rn(pv[0], pv[1]);
+              __half2 dh = __floats2half2_rn(ds[0], ds[1]);
+              wp[e] = *reinterpret_cast<uint32_t*>(&pb);
+              wd[e] = *reinterpret_cast<uint32_t*>(&dh);
             }
-            __nv_bfloat162 pb = __floats2bfloat162_rn(pv[0], pv[1]);
-            __half2 dh = __floats2half2_rn(ds[0], ds[1]);
-            wp[e] = *reinterpret_cast<uint32_t*>(&pb);
-            wd[e] = *reinterpret_cast<uint32_t*>(&dh);
+            const uint32_t off = (uint32_t)half * kBAtom + swz128(row, (ch * 32 + g * 8) * 2);
+            *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+            *reinterpret_cast<uint4*>(smem + L::off_ds + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
           }
-          const uint32_t off = (uint32_t)half * kBAtom + swz128(row, (ch * 32 + g * 8) * 2);
-          *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-          *reinterpret_cast<uint4*>(smem + L::off_ds + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         }
-      }
+      };
+      if (p.causal && (diag || i == 0)) compute(std::true_type{}); else compute(std::false_type{});
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

@@ -10,6 +10,7 @@
 // rescale = bf16(exp2(bf16(m - m'))); O = O*rescale + P V.  Output O fp32, lse = m + log2(l) fp32.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <type_traits>
 
 namespace qa {
 
@@ -109,26 +110,29 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---- pass 1: u = bf16(bf16(S) * qk_scale), masked; per-thread top-2
       uint32_t u2[NC / 2];
       __nv_bfloat162 t1 = as_bf2(ninf2), t2 = as_bf2(ninf2);
+      auto pass1 = [&](auto masked) {                              // two instantiations: the mask costs nothing off-diagonal
 #pragma unroll
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
-        tmem_ld_wait();
+        for (int ch = 0; ch < NC / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t sb = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));    // bf16(S)
-          uint32_t u = pack_bf16(bf_lo(sb) * p.qk_scale, bf_hi(sb) * p.qk_scale);
-          if (diag) {                                              // strict causal: keep key < query
-            const int key = j * 128 + c0 + ch * 32 + 2 * i;
-            if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
-            if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t sb = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));    // bf16(S)
+            uint32_t u = pack_bf16(bf_lo(sb) * p.qk_scale, bf_hi(sb) * p.qk_scale);
+            if (decltype(masked)::value) {                         // strict causal: keep key < query
+              const int key = j * 128 + c0 + ch * 32 + 2 * i;
+              if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
+              if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+            }
+            u2[ch * 16 + i] = u;
+            const __nv_bfloat162 x = as_bf2(u);
+            t2 = __hmax2(t2, __hmin2(t1, x));
+            t1 = __hmax2(t1, x);
           }
-          u2[ch * 16 + i] = u;
-          const __nv_bfloat162 x = as_bf2(u);
-          t2 = __hmax2(t2, __hmin2(t1, x));
-          t1 = __hmax2(t1, x);
         }
-      }
+      };
+      if (diag) pass1(std::true_type{}); else pass1(std::false_type{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);

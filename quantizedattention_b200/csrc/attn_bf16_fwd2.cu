@@ -5,10 +5,14 @@
 //   * S_A / S_B live in TMEM (one buffer each): while warpgroup A runs its softmax the tensor core computes S_B;
 //   * P is written back to TMEM over the S columns (bf16, 2 per column) and consumed as the A operand of the
 //     P V MMA straight from TMEM (no shared-memory round trip, no proxy fence);
-//   * O_A / O_B stay resident in TMEM; the correction warpgroup rescales them only when a row maximum moved.
+//   * O_A / O_B stay resident in TMEM; a softmax warp rescales its own 32 rows only when one of their maxima moved
+//     (no separate correction warpgroup: 10 warps per CTA leave 168 registers per thread for instruction-level
+//     parallelism in the softmax loop, which is what bounds this kernel).
 // TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,256+D)  O_B [384,384+D).
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <type_traits>
+#include <stdlib.h>
 
 namespace qa {
 
@@ -40,7 +44,7 @@ __device__ __forceinline__ __nv_bfloat162 u2bf(uint32_t v) { return *reinterpret
 __device__ __forceinline__ uint32_t bf2u(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 template <int D, int STAGES>
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(320, 1)
 bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, Bf16Fwd2Params p) {
   using L = Bf16Fwd2Smem<D, STAGES>;
@@ -48,10 +52,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_ready[2], sc_full[2][2], sc_empty[2][2], fin_full[2];
+  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_ready[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float row_sc[2][2][128];          // [query tile][parity][row]
-  __shared__ float l_fin[2][128], m_fin[2][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y;
@@ -67,12 +69,10 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
       mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&o_full[x], 1); mbar_init(&o_ready[x], 4);
-      mbar_init(&fin_full[x], 4);
-      for (int b = 0; b < 2; ++b) { mbar_init(&sc_full[x][b], 4); mbar_init(&sc_empty[x][b], 4); }
     }
     fence_mbar_init();
   }
-  if (warp == 13) tmem_alloc<512>(&tmem_base_s);
+  if (warp == 9) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,6 +83,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int x = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t s_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + x * 128;
+    const uint32_t o_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 256 + x * 128;
     const int grow = q0 + x * 128 + row;                          // query index inside the head
     const int qt = 2 * pt + x;                                    // this tile's diagonal k-tile
     const int nkq = nkx[x];
@@ -96,26 +97,29 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ---- pass 1: u = bf16(bf16(S) * qk_scale), masked; top-2 of the row tile
       uint32_t u2[64];
       __nv_bfloat162 t1 = u2bf(ninf2), t2 = u2bf(ninf2);
+      auto pass1 = [&](auto masked) {                              // two instantiations: the mask costs nothing off-diagonal
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + ch * 32, r);
-        tmem_ld_wait();
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(s_addr + ch * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t sb = pack2_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-          uint32_t u = pack2_bf16(bf2_lo(sb) * p.qk_scale, bf2_hi(sb) * p.qk_scale);
-          if (diag) {
-            const int key = j * 128 + ch * 32 + 2 * i;
-            if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
-            if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t sb = pack2_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            uint32_t u = pack2_bf16(bf2_lo(sb) * p.qk_scale, bf2_hi(sb) * p.qk_scale);
+            if (decltype(masked)::value) {                         // strict causal: keep key < query
+              const int key = j * 128 + ch * 32 + 2 * i;
+              if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
+              if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+            }
+            u2[ch * 16 + i] = u;
+            const __nv_bfloat162 xv = u2bf(u);
+            t2 = __hmax2(t2, __hmin2(t1, xv));
+            t1 = __hmax2(t1, xv);
           }
-          u2[ch * 16 + i] = u;
-          const __nv_bfloat162 xv = u2bf(u);
-          t2 = __hmax2(t2, __hmin2(t1, xv));
-          t1 = __hmax2(t1, xv);
         }
-      }
+      };
+      if (diag) pass1(std::true_type{}); else pass1(std::false_type{});
       const __nv_bfloat16 a1 = __low2bfloat16(t1), b1 = __high2bfloat16(t1), a2 = __low2bfloat16(t2), b2 = __high2bfloat16(t2);
       const __nv_bfloat16 top1 = __hmax(a1, b1);
       const __nv_bfloat16 top2 = __hmax(__hmin(a1, b1), __hmax(a2, b2));
@@ -129,11 +133,23 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const float resc = __bfloat162float(__float2bfloat16(ex2_approx(__bfloat162float(__hsub(m_bf, m_new)))));
       m_bf = m_new;
       if (j > 0) {                                                // tile 0 overwrites O: nothing to rescale
-        const int sb = (j - 1) & 1;
-        mbar_wait(&sc_empty[x][sb], (((j - 1) >> 1) & 1) ^ 1);
-        row_sc[x][sb][row] = resc;
+        if (__any_sync(0xffffffffu, resc != 1.0f)) {             // O *= rescale (:280) only when a row maximum moved
+          mbar_wait(&o_full[x], (j - 1) & 1);                    // P V of tile j-1 has landed in TMEM
+          tc_fence_after();
+#pragma unroll
+          for (int ch = 0; ch < D / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(o_addr + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
+            tmem_st32(o_addr + ch * 32, r);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sc_full[x][sb]);
+        if (lane == 0) mbar_arrive(&o_ready[x]);                  // the MMA warp may accumulate tile j into O
       }
       // ---- pass 2: P = bf16(exp2(bf16(u - m'))) written back over the S columns (2 per column), l += sum(P)
       const __nv_bfloat162 m2 = __bfloat162bfloat162(m_new);
@@ -156,65 +172,25 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x]);
     }
-    l_fin[x][row] = l;
-    m_fin[x][row] = __bfloat162float(m_bf);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&fin_full[x]);
-  } else if (warp < 12) {
-    // =========================== correction warpgroup (both query tiles) ===========================
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int j = 1; j < nk; ++j) {
+    // ---- epilogue: O / l and the log2-LSE, straight from the resident accumulator
+    mbar_wait(&o_full[x], (nkq - 1) & 1);
+    tc_fence_after();
+    const size_t gr = (size_t)bh * p.Sq + grow;
+    const float inv_l = 1.0f / l;
+    float* dst = p.O + gr * D;
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        if (j >= nkx[x]) continue;
-        const int sb = (j - 1) & 1;
-        mbar_wait(&sc_full[x][sb], ((j - 1) >> 1) & 1);
-        const float resc = row_sc[x][sb][row];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sc_empty[x][sb]);
-        if (__any_sync(0xffffffffu, resc != 1.0f)) {             // O *= rescale (:280) only when a row maximum moved
-          mbar_wait(&o_full[x], (j - 1) & 1);
-          tc_fence_after();
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(o_addr + ch * 32, r);
+      tmem_ld_wait();
 #pragma unroll
-          for (int ch = 0; ch < D / 32; ++ch) {
-            uint32_t r[32];
-            tmem_ld32(lane_addr + 256 + x * 128 + ch * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
-            tmem_st32(lane_addr + 256 + x * 128 + ch * 32, r);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_ready[x]);
-      }
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + ch * 32 + i) =
+            make_float4(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l, __uint_as_float(r[i + 2]) * inv_l,
+                        __uint_as_float(r[i + 3]) * inv_l);
     }
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-      mbar_wait(&fin_full[x], 0);
-      mbar_wait(&o_full[x], (nkx[x] - 1) & 1);
-      tc_fence_after();
-      const float l = l_fin[x][row];
-      const size_t gr = (size_t)bh * p.Sq + q0 + x * 128 + row;
-      const float inv_l = 1.0f / l;
-      float* dst = p.O + gr * D;
-#pragma unroll
-      for (int ch = 0; ch < D / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + 256 + x * 128 + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(dst + ch * 32 + i) =
-              make_float4(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l, __uint_as_float(r[i + 2]) * inv_l,
-                          __uint_as_float(r[i + 3]) * inv_l);
-      }
-      p.lse[gr] = m_fin[x][row] + log2f(l);                                  // attention_bf16.py:288
-    }
-  } else if (warp == 12) {
+    p.lse[gr] = __bfloat162float(m_bf) + log2f(l);                             // attention_bf16.py:288
+  } else if (warp == 8) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
@@ -290,12 +266,13 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) tmem_dealloc<512>(tbase);
+  if (warp == 9) tmem_dealloc<512>(tbase);
 }
 
 template <int D, int STAGES>
 int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
                      float qk_scale, cudaStream_t st) {
+
   using L = Bf16Fwd2Smem<D, STAGES>;
   CUtensorMap tq, tk, tv;
   uint64_t dq[2] = {(uint64_t)D, (uint64_t)BH * Sq}, dk[2] = {(uint64_t)D, (uint64_t)BH * Sk};
@@ -311,7 +288,7 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(Sq / 256, BH);
-  kern<<<grid, 448, L::total, st>>>(tq, tk, tv, p);
+  kern<<<grid, 320, L::total, st>>>(tq, tk, tv, p);
   return qa_check_launch("qa_bf16_fwd(2 query tiles)");
 }
 
