@@ -7,7 +7,8 @@ Modes:
   literal  -- the source: logits fp32->fp16->bf16, strict causal with a finite -126 fill applied
               BEFORE scaling (leaky), near-max predicate comparing unscaled S with scaled m,
               backward with dS = S*(dP - D) and qk_scale on dQ/dK.
-  contract -- what the CUDA kernels implement: single RN fp32->bf16 of the logits, masked weight
+  contract -- what the CUDA kernels implement: scaled logits u = bf16(S*qk_scale) rounded ONCE from the fp32
+              accumulator (the literal rounds fp32->fp16->bf16, scales, rounds again; LEDGER B-9), masked weight
               exactly 0 for rows >= 1 (fully-masked tiles skipped), row 0 = uniform over ALL keys
               (what both the reference kernel and its baseline produce), the near-max predicate
               evaluated in ONE (scaled) domain, backward with dS = P*(dP - delta) and sm_scale.
@@ -60,7 +61,8 @@ def bf16_fwd(q, k, v, causal: bool, tile_k: int = 32, mode: str = "literal"):
             S16 = torch.bmm(qg, kgT[:, :, kb:ke])                        # :215 fp16 result
             Sb = S16.to(torch.bfloat16)                                  # :216
         else:
-            Sb = torch.bmm(qg.float(), kgT[:, :, kb:ke].float()).to(torch.bfloat16)
+            Sf = torch.bmm(qg.float(), kgT[:, :, kb:ke].float())          # fp32 logits (tensor-core accumulator)
+            Sb = (Sf * qk_scale).to(torch.bfloat16)                        # contract: ONE rounding, u = bf16(S * qk_scale)
         if causal:
             keep = (qi - torch.arange(kb, ke)[None, :]) > 0              # :226 strict
             if mode == "literal":
@@ -71,7 +73,7 @@ def bf16_fwd(q, k, v, causal: bool, tile_k: int = 32, mode: str = "literal"):
             m_new = _bias_corrected_max(m, torch.amax(Sb, -1, keepdim=True) * qk_scale, Sb)  # :236-264
             Ssh = Sb * qk_scale - m_new                                  # :267
         else:
-            u = Sb * qk_scale                                            # bf16 scaled logits
+            u = Sb                                                       # bf16 scaled logits (already scaled above)
             m_new = _bias_corrected_max(m, torch.amax(u, -1, keepdim=True), u)
             # rows whose every key so far is masked keep m = -inf; avoid (-inf) - (-inf)
             m_fin = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)

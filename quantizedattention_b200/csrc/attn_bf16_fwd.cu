@@ -4,7 +4,7 @@
 // the fp32 accumulator stays RESIDENT in TMEM across k-tiles; the correction warps multiply it by the bf16 rescale
 // factor only when a row's running max moved (rescale == 1 exactly otherwise), so the steady-state TMEM->register
 // traffic is the S tile alone (TMEM read bandwidth, ~100 B/clk/SM measured, is what bounds these kernels).
-// Per k-tile numerics (contract mode): Sb = bf16(S); u = bf16(Sb * qk_scale); strict causal mask with
+// Per k-tile numerics (contract mode): u = bf16(S * qk_scale) (one rounding of the fp32 logit); strict causal mask with
 // masked weight 0; m' = max(m, rowmax(u)) in bf16; if >= 2 entries lie within 1e-3 of m' (one scaled domain):
 // m' = beta*m' (m' > 0) or 0 (m' < 0); P = bf16(exp2(bf16(u - m'))); l = l*rescale + sum(P);
 // rescale = bf16(exp2(bf16(m - m'))); O = O*rescale + P V.  Output O fp32, lse = m + log2(l) fp32.
@@ -118,8 +118,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const uint32_t sb = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));    // bf16(S)
-            uint32_t u = pack_bf16(bf_lo(sb) * p.qk_scale, bf_hi(sb) * p.qk_scale);
+            uint32_t u = pack_bf16(__uint_as_float(r[2 * i]) * p.qk_scale, __uint_as_float(r[2 * i + 1]) * p.qk_scale);   // u = bf16(S * qk_scale)
             if (decltype(masked)::value) {                         // strict causal: keep key < query
               const int key = j * 128 + c0 + ch * 32 + 2 * i;
               if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;

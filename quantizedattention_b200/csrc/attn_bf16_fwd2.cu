@@ -105,8 +105,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const uint32_t sb = pack2_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            uint32_t u = pack2_bf16(bf2_lo(sb) * p.qk_scale, bf2_hi(sb) * p.qk_scale);
+            uint32_t u = pack2_bf16(__uint_as_float(r[2 * i]) * p.qk_scale, __uint_as_float(r[2 * i + 1]) * p.qk_scale);   // u = bf16(S * qk_scale)
             if (decltype(masked)::value) {                         // strict causal: keep key < query
               const int key = j * 128 + ch * 32 + 2 * i;
               if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
