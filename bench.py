@@ -236,11 +236,19 @@ def main():
     avg = lambda xs: sum(xs) / len(xs)
     bwd_ms, fwd_ms = avg(kt["int8_bwd"]), avg(kt["int8_fwd"])
     peak = int8_peak or 2.0 * mp.get("bf16_tflops", 1590.0)
-    roof = {"bound": "tensor", "kernel": "int8_bwd_kernel<128>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
-            "peak": peak, "unit": "TFLOP/s", "traffic": None,
+    traffic = None                      # dram__bytes_read + dram__bytes_write per launch from the ncu --set full capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["int8_bwd_kernel_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    roof = {"bound": "tensor", "kernel": "int8_bwd_kernel<128,2>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
+            "peak": peak, "unit": "TFLOP/s", "traffic": traffic,
             "peak_source": "int8 dense: torch._int_mm 8192^3 best-of-10 on this pool (profiles/r01_peaks.json); "
                            "MEASURED_PEAKS.json has no int8 entry (its bf16 burst x2 = %.0f)" % (2 * mp.get("bf16_tflops", 0)),
             "share_of_step": bwd_ms / ms_step,
+            "note": "binding unit is not the tensor pipe: per tile pair the kernel must drain 5 int32/fp32 TMEM tiles "
+                    "(320-384 KB) through tcgen05.ld, measured ceiling ~100 B/clk/SM (profiles/r01_tmem_read_bw.json), "
+                    "plus ~26 CUDA-core instructions per logit for the reference's per-tile re-quantisation",
             "other_kernels": {"int8_fwd_kernel<128,2,3>": {"ms": fwd_ms, "achieved": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12,
                                                            "frac": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12 / peak}}}
     roof["frac"] = roof["achieved"] / peak

@@ -46,11 +46,14 @@ class FlashAttention_2_BF16_autograd_function(Function):
         q_fp16, k_fp16, v_bf16, causal = inputs
         O_fp32, lse_fp32 = output
         ctx.mark_non_differentiable(lse_fp32)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(q_fp16, k_fp16, v_bf16, O_fp32, lse_fp32)
         ctx.args = causal
 
     @staticmethod
     def backward(ctx, dO, _lse):
+        if dO is None:
+            return None, None, None, None
         q_fp16, k_fp16, v_bf16, O_fp32, lse_fp32 = ctx.saved_tensors
         dq, dk, dv = helion_flash_atten_2_algo_4_bwd(q_fp16, k_fp16, v_bf16, O_fp32, lse_fp32, ctx.args, dO)
         return dq, dk, dv, None      # fp32 grads; autograd casts them to the input dtypes (LEDGER B-10)

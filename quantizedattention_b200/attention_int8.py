@@ -120,6 +120,7 @@ class SageAttention3_Int8_autograd_function(Function):
     def setup_context(ctx, inputs, output):
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv = output
         ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv)
+        ctx.set_materialize_grads(False)       # do not allocate zero grads for the 10 auxiliary outputs
         lse32 = SageAttention3_Int8_autograd_function._lse32_stash
         SageAttention3_Int8_autograd_function._lse32_stash = None
         ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
@@ -127,6 +128,8 @@ class SageAttention3_Int8_autograd_function(Function):
 
     @staticmethod
     def backward(ctx, dO_fp16, *_ignored):
+        if dO_fp16 is None:
+            return None, None, None
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32 = ctx.saved_tensors
         Bq, Bkv = ctx.args
         dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
