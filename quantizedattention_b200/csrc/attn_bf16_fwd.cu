@@ -314,14 +314,36 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // causal row 0 has no visible key: reference kernel and baseline both produce the uniform average over ALL keys
-// (LEDGER B-1).  grid = BH, block = D threads.
-__global__ void bf16_row0_fixup_kernel(const __nv_bfloat16* __restrict__ v, float* __restrict__ O, float* __restrict__ lse,
-                                       int Sq, int Sk, int D) {
-  const int bh = blockIdx.x, d = threadIdx.x;
-  float s = 0.f;
-  for (int k = 0; k < Sk; ++k) s += __bfloat162float(v[((size_t)bh * Sk + k) * D + d]);
-  O[(size_t)bh * Sq * D + d] = s / (float)Sk;
-  if (d == 0) lse[(size_t)bh * Sq] = -128.0f + log2f((float)Sk);
+// (LEDGER B-1).  grid = BH, block = 1024 threads: D/8 threads across the head dim (16-byte loads), the rest across keys.
+template <int D>
+__global__ void __launch_bounds__(1024) bf16_row0_fixup_kernel(const __nv_bfloat16* __restrict__ v, float* __restrict__ O,
+                                                              float* __restrict__ lse, int Sq, int Sk) {
+  constexpr int TX = D / 8, TY = 1024 / TX;
+  __shared__ float red[TY][D + 1];
+  const int bh = blockIdx.x, tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const uint4* base = reinterpret_cast<const uint4*>(v + (size_t)bh * Sk * D);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = ty; k < Sk; k += TY) {
+    const uint4 t = __ldg(base + (size_t)k * TX + tx);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] += bf_lo(w[i]); acc[2 * i + 1] += bf_hi(w[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float s = 0.f;
+    for (int r = 0; r < TY; ++r) s += red[r][threadIdx.x];
+    O[(size_t)bh * Sq * D + threadIdx.x] = s / (float)Sk;
+    if (threadIdx.x == 0) lse[(size_t)bh * Sq] = -128.0f + log2f((float)Sk);
+  }
+}
+
+static int launch_row0_fixup(const void* v, float* O, float* lse, int BH, int Sq, int Sk, int D, cudaStream_t st) {
+  if (D == 128) bf16_row0_fixup_kernel<128><<<BH, 1024, 0, st>>>((const __nv_bfloat16*)v, O, lse, Sq, Sk);
+  else bf16_row0_fixup_kernel<64><<<BH, 1024, 0, st>>>((const __nv_bfloat16*)v, O, lse, Sq, Sk);
+  return qa_check_launch("qa_bf16_fwd(row0)");
 }
 
 template <int D, int NSPLIT, int STAGES, int PBUF>
@@ -342,10 +364,7 @@ static int launch_bf16_fwd(const void* q, const void* k, const void* v, const Bf
   kern<<<grid, 128 * NSPLIT + 192, L::total, st>>>(tq, tk, tv, p);
   int r = qa_check_launch("qa_bf16_fwd");
   if (r) return r;
-  if (p.causal) {
-    bf16_row0_fixup_kernel<<<BH, D, 0, st>>>((const __nv_bfloat16*)v, p.O, p.lse, p.Sq, p.Sk, D);
-    r = qa_check_launch("qa_bf16_fwd(row0)");
-  }
+  if (p.causal) r = launch_row0_fixup(v, p.O, p.lse, BH, p.Sq, p.Sk, D, st);
   return r;
 }
 
@@ -374,10 +393,7 @@ extern "C" int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_b
     int rc = D == 128 ? launch_bf16_fwd2<128, 2>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, st)
                       : launch_bf16_fwd2<64, 3>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, st);
     if (rc) return rc;
-    if (causal) {
-      bf16_row0_fixup_kernel<<<BH, D, 0, st>>>((const __nv_bfloat16*)v_bf16, p.O, p.lse, Sq, Sk, D);
-      rc = qa_check_launch("qa_bf16_fwd(row0)");
-    }
+    if (causal) rc = launch_row0_fixup(v_bf16, p.O, p.lse, BH, Sq, Sk, D, st);
     return rc;
   }
   if (nsplit == 0 || nsplit == 3) nsplit = 2;
