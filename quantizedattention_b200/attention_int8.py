@@ -12,7 +12,8 @@ contract in DESIGN.md / SURVEY.md 8-LEDGER: per-(b,h) attention, per-head K toke
 
 `Bq` / `Bkv` are the reference's tunables (PowerOfTwoFragment(32, 256, 32), attention_int8.py:155-158): the
 quantisation block sizes, returned to the caller and forwarded to backward.  The tuned values here are
-Bq = Bkv = 128 (the tcgen05 tile); `set_block_sizes` changes Bq (32/64/128/256).
+Bq = Bkv = 128 (the tcgen05 tile); `set_block_sizes` selects others: the forward runs Bq in {32,64,128,256} and
+Bkv in {32,64,128} (32/32 is the reference's untuned default), the backward needs 128/128.
 """
 from __future__ import annotations
 
@@ -27,8 +28,8 @@ _CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2}
 
 
 def set_block_sizes(Bq: int = 128, Bkv: int = 128):
-    if Bq not in (32, 64, 128, 256) or Bkv != 128:
-        raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv = 128")
+    if Bq not in (32, 64, 128, 256) or Bkv not in (32, 64, 128):
+        raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv in {32,64,128} (backward: 128/128)")
     _CFG["Bq"], _CFG["Bkv"] = Bq, Bkv
 
 

@@ -16,14 +16,16 @@
 namespace qa {
 
 constexpr int kBM = 128;    // query rows per CTA (= tcgen05 M)
-constexpr int kBN = 128;    // keys per k-tile (= Bkv)
+// BN = keys per k-tile = Bkv (the reference's tunable, attention_int8.py:158): 128 is the tuned value; 32 (the reference
+// default) and 64 run the same kernel with narrower S tiles -- one online-softmax step, one P scale per row and one
+// drained P.V partial per Bkv keys, exactly as the reference's k-tile loop -- at proportionally more TMEM drains.
 
-template <int D, int NSPLIT, int STAGES>
+template <int D, int NSPLIT, int STAGES, int BN>
 struct Int8FwdSmem {
   static constexpr int kQBytes = kBM * D;
-  static constexpr int kKBytes = kBN * D;
-  static constexpr int kVBytes = kBN * D;
-  static constexpr int kPBytes = kBM * kBN;
+  static constexpr int kKBytes = BN * D;
+  static constexpr int kVBytes = BN * D;
+  static constexpr int kPBytes = kBM * 128;      // P rows keep a 128-byte pitch (128B swizzle); BN bytes of each row are used
   static constexpr int off_q = 0;
   static constexpr int off_k = off_q + kQBytes;
   static constexpr int off_v = off_k + STAGES * kKBytes;
@@ -49,12 +51,14 @@ struct Int8FwdParams {
   float qk_scale;
 };
 
-template <int D, int NSPLIT, int STAGES>
+template <int D, int NSPLIT, int STAGES, int BN>
 __global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
 int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
-  using L = Int8FwdSmem<D, NSPLIT, STAGES>;
+  using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
+  constexpr int kBN = BN;
   constexpr int NC = kBN / NSPLIT;       // S columns per softmax thread
+  static_assert(NC % 32 == 0, "a softmax thread handles a multiple of 32 columns");
   constexpr int DC = D / NSPLIT;         // O columns per correction thread
   constexpr int kSoftWarps = 4 * NSPLIT;
   constexpr uint32_t kLayoutQK = (D == 128) ? kSwz128 : kSwz64;   // rows of D bytes
@@ -120,7 +124,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int ch = 0; ch < NC / 32; ++ch) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + b * kBN + c0 + ch * 32, r);
+        tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -315,7 +319,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int k = 0; k < D / 32; ++k) {
           const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, kSboQK, kLayoutQK);
           const uint64_t bd = umma_smem_desc(k_addr + k * 32, 16, kSboQK, kLayoutQK);
-          umma_i8_ss(tbase + b * kBN, ad, bd, idesc_qk, k > 0);
+          umma_i8_ss(tbase + b * 128, ad, bd, idesc_qk, k > 0);
         }
         umma_commit(&s_full[b]);
         umma_commit(&k_empty[s]);
@@ -329,20 +333,21 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
 }
 
-template <int D, int NSPLIT, int STAGES>
+template <int D, int NSPLIT, int STAGES, int BN>
 static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const Int8FwdParams& p, int BH,
                            cudaStream_t st) {
-  using L = Int8FwdSmem<D, NSPLIT, STAGES>;
+  using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
   CUtensorMap tq, tk, tv;
   const int sw = (D == 128) ? 3 : 2;
   uint64_t dq[2] = {(uint64_t)D, (uint64_t)BH * p.Sq}, dk[2] = {(uint64_t)D, (uint64_t)BH * p.Sk};
   uint64_t str[1] = {(uint64_t)D};
   uint32_t box[2] = {(uint32_t)D, 128};
+  uint32_t boxk[2] = {(uint32_t)D, (uint32_t)BN};
   int rc;
   if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, str, box, sw))) return rc;
-  if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, box, sw))) return rc;
-  if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, box, sw))) return rc;
-  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES>;
+  if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
+  if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
+  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / kBM, BH);
@@ -362,9 +367,9 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
                                  const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int D,
                                  int Bq, int Bkv, int nsplit, void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: D must be 64 or 128");
-  if (Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 128 (tcgen05 k-tile)");
+  if (Bkv != 32 && Bkv != 64 && Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 32, 64 or 128");
   if (Bq != 32 && Bq != 64 && Bq != 128 && Bq != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bq must be 32/64/128/256");
-  if (Sq % 128 || Sk % 128 || Sq % Bq) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Sq, Sk must be multiples of 128 (and of Bq)");
+  if (Sq % 128 || Sk % Bkv || Sq % Bq) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Sq must be a multiple of 128 (and of Bq), Sk of Bkv");
   if (((uintptr_t)q_i8 | (uintptr_t)k_i8 | (uintptr_t)v_i8 | (uintptr_t)O | (uintptr_t)o_acc) & 15)
     return qa_fail(QA_ERR_ALIGN, "qa_int8_fwd: 16-byte alignment required");
   Int8FwdParams p;
@@ -375,10 +380,16 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   p.Sq = Sq; p.Sk = Sk; p.Bq = Bq;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 128) return nsplit == 2 ? launch_int8_fwd<128, 2, 3>(q_i8, k_i8, v_i8, p, BH, st)
-                                   : launch_int8_fwd<128, 1, 3>(q_i8, k_i8, v_i8, p, BH, st);
-  return nsplit == 2 ? launch_int8_fwd<64, 2, 4>(q_i8, k_i8, v_i8, p, BH, st)
-                     : launch_int8_fwd<64, 1, 4>(q_i8, k_i8, v_i8, p, BH, st);
+  if (Bkv == 128) {
+    if (D == 128) return nsplit == 2 ? launch_int8_fwd<128, 2, 3, 128>(q_i8, k_i8, v_i8, p, BH, st)
+                                     : launch_int8_fwd<128, 1, 3, 128>(q_i8, k_i8, v_i8, p, BH, st);
+    return nsplit == 2 ? launch_int8_fwd<64, 2, 4, 128>(q_i8, k_i8, v_i8, p, BH, st)
+                       : launch_int8_fwd<64, 1, 4, 128>(q_i8, k_i8, v_i8, p, BH, st);
+  }
+  if (Bkv == 64) return D == 128 ? launch_int8_fwd<128, 1, 4, 64>(q_i8, k_i8, v_i8, p, BH, st)
+                                 : launch_int8_fwd<64, 1, 4, 64>(q_i8, k_i8, v_i8, p, BH, st);
+  return D == 128 ? launch_int8_fwd<128, 1, 4, 32>(q_i8, k_i8, v_i8, p, BH, st)
+                  : launch_int8_fwd<64, 1, 4, 32>(q_i8, k_i8, v_i8, p, BH, st);
 }
 
 extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,

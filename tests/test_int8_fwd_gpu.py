@@ -44,3 +44,43 @@ def test_int8_fwd_matches_oracle(shape, Bq, nsplit):
     base = baseline_pytorch_attention(q.float(), k.float(), v.float(), shape[3], False)
     mx, cos = _stats(out[0].cpu(), base)
     assert mx < 8e-2 and cos > 0.999, (mx, cos)                               # reference yardstick: atol 1e-2 class noise
+
+
+@pytest.mark.parametrize("shape,Bq,Bkv", [((1, 2, 256, 128), 32, 32), ((2, 2, 256, 64), 32, 32), ((1, 2, 512, 128), 64, 64),
+                                          ((1, 1, 256, 64), 128, 64), ((1, 2, 256, 128), 256, 32)])
+def test_int8_fwd_reference_default_block_sizes(shape, Bq, Bkv):
+    """Bkv = 32 / 64: the reference's untuned default tunables (PowerOfTwoFragment(32, 256, 32), attention_int8.py:155-158)."""
+    from oracle import int8_ref
+    from quantizedattention_b200 import attention_int8 as A
+    q, k, v = _mk(shape, 77 + Bq + Bkv + shape[3])
+    A.set_block_sizes(Bq, Bkv)
+    try:
+        out = A.helion_atten_int8_hl_dot_fwd(q.cuda(), k.cuda(), v.cuda(), _want_lse32=True)
+    finally:
+        A.set_block_sizes(128, 128)
+    ref = int8_ref.int8_fwd(q, k, v, Bq, Bkv, per_head=True, return_lse32=True)
+    for i in (2, 3, 4, 5, 6, 7):
+        assert torch.equal(out[i].cpu(), ref[i]), f"slot {i}"
+    assert out[8:10] == (Bq, Bkv)
+    mx, cos = _stats(out[0].cpu(), ref[0])
+    assert mx < 5e-3 and cos > 0.99999, (mx, cos)
+    assert (out[10].cpu() - ref[10]).abs().max() < 2e-3
+
+
+def test_int8_fwd_against_real_reference_fixture(golden_dir):
+    """The fixture holds the outputs of the UNMODIFIED reference (Bq = Bkv = 32, attention over the flattened B*H*S
+    axis, LEDGER I-2).  The literal result is the per-head kernel on x.view(1, 1, B*H*S, D)."""
+    import os
+    from quantizedattention_b200 import attention_int8 as A
+    fx = torch.load(os.path.join(golden_dir, "int8_B1H2S128D64_bq32_bkv32.pt"))
+    q, k, v = [fx[n].reshape(1, 1, -1, 64).cuda() for n in ("q", "k", "v")]
+    A.set_block_sizes(32, 32)
+    try:
+        out = A.helion_atten_int8_hl_dot_fwd(q, k, v)
+    finally:
+        A.set_block_sizes(128, 128)
+    O_ref, lse_ref, q_i8, k_i8_T, v_i8, sq, sk, sv = fx["fwd"]
+    assert torch.equal(out[2].cpu(), q_i8) and torch.equal(out[3].cpu(), k_i8_T) and torch.equal(out[4].cpu(), v_i8)
+    assert torch.equal(out[5].cpu(), sq) and torch.equal(out[6].cpu(), sk) and torch.equal(out[7].cpu(), sv)
+    assert (out[0].cpu().float().reshape(-1) - O_ref.float().reshape(-1)).abs().max() < 5e-3
+    assert (out[1].cpu().float() - lse_ref.float()).abs().max() < 4e-2

@@ -24,5 +24,13 @@ elif which == "int8_fwd":
     qi, sq = ops.quant_block(q, 128); ki, sk = ops.quant_block(k, 128); vi, sv = ops.quant_block(v, 128)
     for _ in range(3):
         ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D)
+elif which == "bf16_bwd":
+    B, H, S, D = 4, 16, 4096, 128
+    q, k = [torch.randn(B, H, S, D, device="cuda", dtype=torch.float16) for _ in range(2)]
+    v = torch.randn(B, H, S, D, device="cuda", dtype=torch.bfloat16)
+    dO = torch.randn(B, H, S, D, device="cuda")
+    O, lse = ops.bf16_fwd(q, k, v, True)
+    for _ in range(3):
+        ops.bf16_bwd(q, k, v, O, lse, True, dO)
 torch.cuda.synchronize()
 print("ok")
