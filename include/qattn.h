@@ -84,7 +84,7 @@ int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const 
                 const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
                 int causal, void* stream);
 
-/* ---- JVP: helion_attention_jvp_forward_fp32, attention_jvp.py:33-195 (operands pre-cast to bf16) ---- */
+/* ---- JVP: helion_attention_jvp_forward_fp32, attention_jvp.py:33-195 (operands pre-cast to bf16); D in {64,128} ---- */
 int qa_jvp_fwd(const void* q_bf16, const void* tq_bf16, const void* k_bf16, const void* tk_bf16, const void* v_bf16,
                const void* tv_bf16, void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit,
                void* stream);

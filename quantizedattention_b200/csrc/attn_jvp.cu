@@ -16,12 +16,15 @@ namespace qa {
 
 constexpr int kJAtom = 128 * 128;
 
-template <int D>
+// BN = keys per k-tile: 128 at D = 64; 64 at D = 128 (shared memory: six operand tiles + P + H per stage)
+template <int D, int BN>
 struct JvpSmem {
-  static constexpr int kTile = 128 * D * 2;
-  static constexpr int kPBytes = 128 * 128 * 2;
+  static constexpr int kTileQ = 128 * D * 2;            // Q / tQ tile (128 rows)
+  static constexpr int kTile = BN * D * 2;              // K / tK / V / tV tile (BN rows)
+  static constexpr int kKAtom = BN * 128;               // one 128-byte column of a BN-row tile
+  static constexpr int kPBytes = 128 * BN * 2;
   static constexpr int off_q = 0;                       // Q, tQ
-  static constexpr int off_k = off_q + 2 * kTile;       // 2 stages x (K, tK)
+  static constexpr int off_k = off_q + 2 * kTileQ;      // 2 stages x (K, tK)
   static constexpr int off_v = off_k + 4 * kTile;       // 1 stage  x (V, tV)
   static constexpr int off_p = off_v + 2 * kTile;       // P, H
   static constexpr int total = off_p + 2 * kPBytes + 1024;
@@ -38,13 +41,14 @@ __device__ __forceinline__ uint32_t jpack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int D, int NSPLIT>
+template <int D, int NSPLIT, int BN>
 __global__ void __launch_bounds__(128 * NSPLIT + 192, 1)
 jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_tq,
                const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_tk,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_tv, JvpParams p) {
-  using L = JvpSmem<D>;
-  constexpr int NC = 128 / NSPLIT;
+  using L = JvpSmem<D, BN>;
+  constexpr int NC = BN / NSPLIT;
+  static_assert(NC % 32 == 0, "a softmax thread handles a multiple of 32 columns");
   constexpr int kSoftWarps = 4 * NSPLIT;
   constexpr int kProdWarp = kSoftWarps + 4;
   constexpr int kMmaWarp = kSoftWarps + 5;
@@ -60,7 +64,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * 128;
-  const int nk = p.Sk / 128;
+  const int nk = p.Sk / BN;
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -216,11 +220,11 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   } else if (warp == kProdWarp) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
-      mbar_expect_tx(&q_full, 2 * L::kTile);
+      mbar_expect_tx(&q_full, 2 * L::kTileQ);
 #pragma unroll
       for (int a = 0; a < kDAtoms; ++a) {
         tma_load_2d(smem + L::off_q + a * kJAtom, &tm_q, &q_full, a * 64, bh * p.Sq + q0);
-        tma_load_2d(smem + L::off_q + L::kTile + a * kJAtom, &tm_tq, &q_full, a * 64, bh * p.Sq + q0);
+        tma_load_2d(smem + L::off_q + L::kTileQ + a * kJAtom, &tm_tq, &q_full, a * 64, bh * p.Sq + q0);
       }
       for (int j = 0; j < nk; ++j) {
         const int s = j & 1;
@@ -228,24 +232,24 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_expect_tx(&k_full[s], 2 * L::kTile);
 #pragma unroll
         for (int a = 0; a < kDAtoms; ++a) {
-          tma_load_2d(smem + L::off_k + s * 2 * L::kTile + a * kJAtom, &tm_k, &k_full[s], a * 64, bh * p.Sk + j * 128);
-          tma_load_2d(smem + L::off_k + s * 2 * L::kTile + L::kTile + a * kJAtom, &tm_tk, &k_full[s], a * 64, bh * p.Sk + j * 128);
+          tma_load_2d(smem + L::off_k + s * 2 * L::kTile + a * L::kKAtom, &tm_k, &k_full[s], a * 64, bh * p.Sk + j * BN);
+          tma_load_2d(smem + L::off_k + s * 2 * L::kTile + L::kTile + a * L::kKAtom, &tm_tk, &k_full[s], a * 64, bh * p.Sk + j * BN);
         }
         mbar_wait(&v_empty, (j & 1) ^ 1);
         mbar_expect_tx(&v_full, 2 * L::kTile);
 #pragma unroll
         for (int a = 0; a < kDAtoms; ++a) {
-          tma_load_2d(smem + L::off_v + a * kJAtom, &tm_v, &v_full, a * 64, bh * p.Sk + j * 128);
-          tma_load_2d(smem + L::off_v + L::kTile + a * kJAtom, &tm_tv, &v_full, a * 64, bh * p.Sk + j * 128);
+          tma_load_2d(smem + L::off_v + a * L::kKAtom, &tm_v, &v_full, a * 64, bh * p.Sk + j * BN);
+          tma_load_2d(smem + L::off_v + L::kTile + a * L::kKAtom, &tm_tv, &v_full, a * 64, bh * p.Sk + j * BN);
         }
       }
     }
   } else {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc(1, 1, 1, 0, 0, 128, 128);        // bf16 x bf16 -> f32, K-major
+      constexpr uint32_t idesc_qk = umma_idesc(1, 1, 1, 0, 0, 128, BN);         // bf16 x bf16 -> f32, K-major
       constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // B MN-major
-      const uint32_t q_addr = smem_u32(smem + L::off_q), tq_addr = q_addr + L::kTile;
+      const uint32_t q_addr = smem_u32(smem + L::off_q), tq_addr = q_addr + L::kTileQ;
       const uint32_t p_addr = smem_u32(smem + L::off_p), h_addr = p_addr + L::kPBytes;
       const uint32_t v_addr = smem_u32(smem + L::off_v), tv_addr = v_addr + L::kTile;
       auto issue_pv = [&](int t) {
@@ -255,12 +259,12 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_wait(&p_full, ph);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < BN / 16; ++k) {
           const uint32_t ao = (k >> 2) * kJAtom + (k & 3) * 32;
           const uint64_t pd = umma_smem_desc(p_addr + ao, 16, 1024, kSwz128);
           const uint64_t hd = umma_smem_desc(h_addr + ao, 16, 1024, kSwz128);
-          const uint64_t vd = umma_smem_desc(v_addr + k * 2048, kJAtom, 1024, kSwz128);
-          const uint64_t tvd = umma_smem_desc(tv_addr + k * 2048, kJAtom, 1024, kSwz128);
+          const uint64_t vd = umma_smem_desc(v_addr + k * 2048, L::kKAtom, 1024, kSwz128);
+          const uint64_t tvd = umma_smem_desc(tv_addr + k * 2048, L::kKAtom, 1024, kSwz128);
           umma_f16_ss(tbase + 256, pd, vd, idesc_pv, (t > 0) || (k > 0));       // O  += P V
           umma_f16_ss(tbase + 256 + D, pd, tvd, idesc_pv, (t > 0) || (k > 0));  // AB += P tV
           umma_f16_ss(tbase + 256 + D, hd, vd, idesc_pv, 1);                    //     + H V
@@ -279,8 +283,9 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t o = (k >> 2) * kJAtom + (k & 3) * 32;
+          const uint32_t ok = (k >> 2) * L::kKAtom + (k & 3) * 32;
           const uint64_t qd = umma_smem_desc(q_addr + o, 16, 1024, kSwz128), tqd = umma_smem_desc(tq_addr + o, 16, 1024, kSwz128);
-          const uint64_t kd = umma_smem_desc(k_addr + o, 16, 1024, kSwz128), tkd = umma_smem_desc(tk_addr + o, 16, 1024, kSwz128);
+          const uint64_t kd = umma_smem_desc(k_addr + ok, 16, 1024, kSwz128), tkd = umma_smem_desc(tk_addr + ok, 16, 1024, kSwz128);
           umma_f16_ss(tbase + 0, qd, kd, idesc_qk, k > 0);          // S
           umma_f16_ss(tbase + 128, tqd, kd, idesc_qk, k > 0);       // tS  = tQ K^T
           umma_f16_ss(tbase + 128, qd, tkd, idesc_qk, 1);           //     + Q tK^T
@@ -297,18 +302,18 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (warp == kMmaWarp) tmem_dealloc<512>(tbase);
 }
 
-template <int D, int NSPLIT>
+template <int D, int NSPLIT, int BN>
 static int launch_jvp(const void* const* in6, const JvpParams& p, int BH, cudaStream_t st) {
-  using L = JvpSmem<D>;
+  using L = JvpSmem<D, BN>;
   CUtensorMap tm[6];
   uint64_t str[1] = {(uint64_t)D * 2};
-  uint32_t box[2] = {64, 128};
   for (int i = 0; i < 6; ++i) {
     uint64_t dims[2] = {(uint64_t)D, (uint64_t)BH * (i < 2 ? p.Sq : p.Sk)};
+    uint32_t box[2] = {64, (uint32_t)(i < 2 ? 128 : BN)};
     int rc = qa_make_tmap(&tm[i], in6[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3);
     if (rc) return rc;
   }
-  auto kern = jvp_fwd_kernel<D, NSPLIT>;
+  auto kern = jvp_fwd_kernel<D, NSPLIT, BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / 128, BH);
@@ -323,7 +328,7 @@ using namespace qa;
 // q, tq: bf16 [BH*Sq, D]; k, tk, v, tv: bf16 [BH*Sk, D]; O, tO: fp32 [BH*Sq, D]; lse: fp32 [BH*Sq].
 extern "C" int qa_jvp_fwd(const void* q, const void* tq, const void* k, const void* tk, const void* v, const void* tv,
                           void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit, void* stream) {
-  if (D != 64) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: D must be 64 (TMEM budget: S, tS, Opart, ABpart)");
+  if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: D must be 64 or 128");
   if (Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: Sq, Sk must be multiples of 128");
   const void* in6[6] = {q, tq, k, tk, v, tv};
   for (int i = 0; i < 6; ++i)
@@ -333,5 +338,6 @@ extern "C" int qa_jvp_fwd(const void* q, const void* tq, const void* k, const vo
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
-  return nsplit == 2 ? launch_jvp<64, 2>(in6, p, BH, st) : launch_jvp<64, 1>(in6, p, BH, st);
+  if (D == 128) return nsplit == 1 ? launch_jvp<128, 1, 64>(in6, p, BH, st) : launch_jvp<128, 2, 64>(in6, p, BH, st);
+  return nsplit == 2 ? launch_jvp<64, 2, 128>(in6, p, BH, st) : launch_jvp<64, 1, 128>(in6, p, BH, st);
 }

@@ -39,7 +39,7 @@ def test_argument_validation_needs_no_gpu():
     assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, z) == -1  # Bkv in {32,64,128}
     assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, z) == -1          # Bq = Bkv = 128
     assert L.qa_bf16_fwd(*([z] * 5), 1, 100, 128, 128, 0, 1, z) == -1         # S % 128
-    assert L.qa_jvp_fwd(*([z] * 9), 1, 128, 128, 128, 1, z) == -1             # D = 64 only
+    assert L.qa_jvp_fwd(*([z] * 9), 1, 128, 128, 96, 1, z) == -1              # D in {64,128}
 
 
 def test_no_cpu_fallback_and_no_oracle_in_product():

@@ -56,20 +56,21 @@ def test_bf16_fwd_stress_duplicate_keys():
     assert (O.cpu() - base).abs().max() < 1e-1               # bf16 logits at |s| ~ 4..8: the oracle itself is 6e-2 off
 
 
+@pytest.mark.parametrize("D", [64, 128])
 @pytest.mark.parametrize("nsplit", [1, 2])
 @pytest.mark.parametrize("ones", [True, False])
-def test_jvp_matches_oracle_and_torch_func(ones, nsplit):
+def test_jvp_matches_oracle_and_torch_func(ones, nsplit, D):
     from oracle import jvp_ref
     from oracle.baseline import baseline_pytorch_attention
     from quantizedattention_b200 import ops
-    shape = (2, 2, 256, 64)
+    shape = (2, 2, 256, D)
     g = torch.Generator().manual_seed(41 + ones)
     q, k, v = [torch.randn(shape, generator=g) for _ in range(3)]
     tq, tk, tv = [torch.ones(shape) if ones else torch.randn(shape, generator=g) for _ in range(3)]
     O, tO, lse = ops.jvp_fwd(*[t.cuda() for t in (q, k, v, tq, tk, tv)], nsplit=nsplit)
     torch.cuda.synchronize()
     # same-operand-rounding oracle (bf16 MMA operands, fp32 accumulate): tight
-    Oe, tOe, lsee = jvp_ref.jvp_fwd(q, k, v, tq, tk, tv, tile_k=128, operand_dtype=torch.bfloat16)
+    Oe, tOe, lsee = jvp_ref.jvp_fwd(q, k, v, tq, tk, tv, tile_k=128 if D == 64 else 64, operand_dtype=torch.bfloat16)
     assert (O.cpu() - Oe).abs().max() < 2e-3 and (tO.cpu() - tOe).abs().max() < 8e-3
     assert (lse.cpu() - lsee).abs().max() < 1e-3
     # fp32 truth: torch.func.jvp of the reference baseline (attention_jvp.py:254-258); yardstick atol 1e-2
