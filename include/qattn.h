@@ -93,6 +93,8 @@ int qa_jvp_fwd(const void* q_bf16, const void* tq_bf16, const void* k_bf16, cons
 int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, void* d_out, int a_lbo, int a_sbo,
                  int a_layout, int a_kstep_bytes, int b_lbo, int b_sbo, int b_layout, int b_kstep_bytes, unsigned idesc,
                  int kind, int n_mma, int n_cols, int a_in_tmem, int a_tmem_cols, int a_tmem_kstep_cols, void* stream);
+/* Development aid: per-k-tile SM-clock stamps of CTA (0,0) of the next qa_int8_fwd launches ([64][16] int64); NULL = off */
+int qa_debug_set_int8_fwd_timeline(void* buf);
 /* TMEM -> register read bandwidth (tcgen05.ld.32x32b.x32 streamed by every warp): measured ceiling of the drains */
 int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream);
 int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const unsigned long long* dims,

@@ -141,7 +141,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __nv_bfloat16 top2 = __hmax(__hmin(a1, b1), __hmax(a2, b2));
       if (NSPLIT == 2) {
         xtop[b][split][row] = (uint32_t)__bfloat16_as_ushort(top1) | ((uint32_t)__bfloat16_as_ushort(top2) << 16);
-        named_bar_sync(1, 128 * NSPLIT);
+        named_bar_sync(1 + (warp & 3), 32 * NSPLIT);   // only the warps that share these 32 rows meet
         const uint32_t o = xtop[b][split ^ 1][row];
         const __nv_bfloat16 o1 = __ushort_as_bfloat16((unsigned short)(o & 0xffff)), o2 = __ushort_as_bfloat16((unsigned short)(o >> 16));
         top2 = __hmax(__hmin(top1, o1), __hmax(top2, o2));

@@ -49,7 +49,14 @@ struct Int8FwdParams {
   const float* O_acc_in;
   int Sq, Sk, Bq;
   float qk_scale;
+  long long* dbg;        // optional timeline buffer [tile][16] of SM clock stamps written by CTA (0,0) (tools/timeline.py)
 };
+
+#define QA_TL(slot)                                                                                   \
+  do {                                                                                                \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < 64)                \
+      p.dbg[j * 16 + (slot)] = clock64();                                                             \
+  } while (0)
 
 template <int D, int NSPLIT, int STAGES, int BN>
 __global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
@@ -116,8 +123,10 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float sk_f = __half2float(p.sk[((size_t)bh * p.Sk) / kBN + j]);
       const float sv_f = __half2float(p.sv[((size_t)bh * p.Sk) / kBN + j]);
       const float c = sq_f * sk_f * p.qk_scale;
+      if (warp == 0) QA_TL(0);
       mbar_wait(&s_full[b], ph);
       tc_fence_after();
+      if (warp == 0) QA_TL(1);
       // ---- pass 1: int32 -> fp16 logits (packed), row max
       __half2 sh[NC / 2];
       __half2 mx2 = __float2half2_rn(-INFINITY);
@@ -139,9 +148,10 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);        // S[b] is in registers: the MMA warp may overwrite it
       __half rmax = __hmax(__low2half(mx2), __high2half(mx2));
+      if (warp == 0) QA_TL(2);
       if (NSPLIT == 2) {
         xmax[b][split][row] = rmax;
-        named_bar_sync(1, 128 * NSPLIT);
+        named_bar_sync(1 + (warp & 3), 32 * NSPLIT);   // only the warps that share these 32 rows meet
         rmax = __hmax(rmax, xmax[b][split ^ 1][row]);
       }
       const __half m_new = __hmax(m16, rmax);
@@ -157,7 +167,9 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (lane == 0) mbar_arrive(&sc_full[b]);
       }
       // ---- pass 2: P = exp2(S16 - m), l += sum(P), P_i8 = trunc(P / sp) -> swizzled smem (K-major, 128 B rows)
+      if (warp == 0) QA_TL(3);
       mbar_wait(&p_empty[b], ph ^ 1);
+      if (warp == 0) QA_TL(4);
       const __half2 m2 = __half2half2(m_new);
       float lsum = 0.f;
       uint8_t* prow = smem + L::off_p + b * L::kPBytes;
@@ -184,6 +196,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (warp == 0) QA_TL(5);
     }
     l_part[split][row] = l;
     if (split == 0) m_fin[row] = m16;
@@ -207,6 +220,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         acc[i] = t.x; acc[i + 1] = t.y; acc[i + 2] = t.z; acc[i + 3] = t.w;
       }
     }
+    float s_pend = 1.0f;
     for (int j = 0; j < nk; ++j) {
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
@@ -214,26 +228,31 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float2 sc = row_sc[b][row];
       __syncwarp();
       if (lane == 0) mbar_arrive(&sc_empty[b]);
-      const bool no_rescale = __all_sync(0xffffffffu, sc.x == 1.0f);
+      // Lazy rescale: the accumulator holds O / s_pend, so O*rescale + x*c (attention_int8.py:225, 249-250) costs one
+      // FMA per element: s_pend *= rescale; acc += x * (c / s_pend).  rescale == 0 only on a fresh first tile (acc == 0).
+      if (sc.x != 0.f) s_pend *= sc.x;
+      if (__any_sync(0xffffffffu, s_pend < 1e-12f)) {       // rare: fold the pending factor back in before it underflows
+#pragma unroll
+        for (int i = 0; i < DC; ++i) acc[i] *= s_pend;
+        s_pend = 1.0f;
+      }
+      const float c_eff = __fdividef(sc.y, s_pend);
+      if (cw == 0) QA_TL(6);
       mbar_wait(&o_full[b], ph);
       tc_fence_after();
+      if (cw == 0) QA_TL(7);
 #pragma unroll
       for (int ch = 0; ch < DC / 32; ++ch) {
         uint32_t r[32];
         tmem_ld32(lane_addr + 256 + b * 128 + d0 + ch * 32, r);
         tmem_ld_wait();
-        if (no_rescale) {                              // warp-uniform: the running max did not move for these 32 rows
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), sc.y, acc[ch * 32 + i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), sc.y, acc[ch * 32 + i] * sc.x);
-        }
+        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), c_eff, acc[ch * 32 + i]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[b]);
+      if (cw == 0) QA_TL(8);
     }
     mbar_wait(&fin_full, 0);
     float l = l_part[0][row];
@@ -243,10 +262,11 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ring mode: emit the unnormalised accumulator and (m, l); the host-side merge normalises
       float* dst = p.O_acc_out + grow * D + d0;
 #pragma unroll
-      for (int i = 0; i < DC; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      for (int i = 0; i < DC; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i] * s_pend, acc[i + 1] * s_pend, acc[i + 2] * s_pend, acc[i + 3] * s_pend);
       if (split == 0) { p.m_out[grow] = __half2float(m_fin[row]); p.l_out[grow] = l; }
     } else {
-      const float inv_l = 1.0f / l;                                            // O / l (:256)
+      const float inv_l = s_pend / l;                                          // O / l (:256), pending rescale folded in
       __half* dst = p.O + grow * D + d0;
 #pragma unroll
       for (int i = 0; i < DC; i += 8) {
@@ -296,6 +316,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&o_empty[b], ph ^ 1);
         mbar_wait(&p_full[b], ph);
         tc_fence_after();
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < 64) p.dbg[t * 16 + 11] = clock64();   // PV issue
         const uint32_t p_addr = smem_u32(smem + L::off_p + b * L::kPBytes);
         const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kVBytes);
 #pragma unroll
@@ -312,8 +333,10 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int j = 0; j < nk; ++j) {
         const int b = j & 1, s = j % STAGES;
         mbar_wait(&k_full[s], (j / STAGES) & 1);
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) p.dbg[j * 16 + 9] = clock64();    // K landed
         mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) p.dbg[j * 16 + 10] = clock64();   // QK issue
         const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
 #pragma unroll
         for (int k = 0; k < D / 32; ++k) {
@@ -359,6 +382,14 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
 
 using namespace qa;
 
+static void* g_int8_fwd_dbg = nullptr;
+// Development aid: CTA (0,0) of subsequent qa_int8_fwd launches records SM-clock stamps per k-tile into buf
+// ([64 tiles][16 slots] int64); pass NULL to switch it off.  Not thread-safe; used by tools/timeline.py only.
+extern "C" int qa_debug_set_int8_fwd_timeline(void* buf) {
+  g_int8_fwd_dbg = buf;
+  return 0;
+}
+
 // Forward over pre-quantised operands.  q_i8 [BH*Sq, D], k_i8 / v_i8 [BH*Sk, D] int8 row-major; sq [BH*Sq/Bq],
 // sk / sv [BH*Sk/Bkv] fp16.  Outputs: O fp16 [BH*Sq, D], lse16 fp16 [BH*Sq], lse32 fp32 [BH*Sq] (optional).
 // Ring mode (o_acc != NULL): writes unnormalised fp32 O plus (m, l) per row instead of O / lse.
@@ -379,6 +410,7 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   p.O_acc_in = (const float*)o_acc_in; p.m_in = (const float*)m_in; p.l_in = (const float*)l_in;
   p.Sq = Sq; p.Sk = Sk; p.Bq = Bq;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  p.dbg = (long long*)g_int8_fwd_dbg;
   cudaStream_t st = (cudaStream_t)stream;
   if (Bkv == 128) {
     if (D == 128) return nsplit == 2 ? launch_int8_fwd<128, 2, 3, 128>(q_i8, k_i8, v_i8, p, BH, st)

@@ -106,7 +106,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
       if (NSPLIT == 2) {
         xmax[ph][split][row] = mx;
-        named_bar_sync(1, 128 * NSPLIT);
+        named_bar_sync(1 + (warp & 3), 32 * NSPLIT);   // only the warps that share these 32 rows meet
         mx = fmaxf(mx, xmax[ph][split ^ 1][row]);
       }
       const float m_new = fmaxf(m, mx * p.qk_scale);             // :155-158
