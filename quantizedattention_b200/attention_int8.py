@@ -18,11 +18,17 @@ Bkv in {32,64,128} (32/32 is the reference's untuned default), the backward need
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 from torch.autograd import Function
 
 from . import ops
+
+# fp32 copy of the log2-LSE for the backward (LEDGER I-15), keyed weakly by the fp16 lse tensor the forward returns:
+# forward() has no ctx in the new-style Function API, so setup_context() picks the copy up from here.  Entries vanish
+# with their key, so a forward under no_grad leaves nothing behind.
+_LSE32 = weakref.WeakKeyDictionary()
 
 _CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2}
 
@@ -114,7 +120,7 @@ class SageAttention3_Int8_autograd_function(Function):
         v_i8, sv = ops.quant_block(v_fp16, Bkv)
         O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
                                                 nsplit=_CFG["nsplit"], want_lse32=True)
-        SageAttention3_Int8_autograd_function._lse32_stash = lse32             # picked up by setup_context
+        _LSE32[lse16] = lse32                                                  # picked up by setup_context
         return (O.view(batch, head, q_tokens, D), lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
 
     @staticmethod
@@ -122,8 +128,7 @@ class SageAttention3_Int8_autograd_function(Function):
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv = output
         ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv)
         ctx.set_materialize_grads(False)       # do not allocate zero grads for the 10 auxiliary outputs
-        lse32 = SageAttention3_Int8_autograd_function._lse32_stash
-        SageAttention3_Int8_autograd_function._lse32_stash = None
+        lse32 = _LSE32.pop(l_bh_fp16, None)
         ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
         ctx.args = (Bq, Bkv)
 
@@ -136,8 +141,6 @@ class SageAttention3_Int8_autograd_function(Function):
         dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
                                                   O_fp16, lse32 if lse32 is not None else l_bh_fp16, Bq, Bkv)
         return dq, dk, dv
-
-    _lse32_stash = None
 
 
 def sage_attention_3_int8(q_fp16, k_fp16, v_fp16):

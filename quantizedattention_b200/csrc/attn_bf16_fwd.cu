@@ -50,7 +50,6 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   using L = Bf16FwdSmem<D, STAGES, PBUF>;
   constexpr int NC = 128 / NSPLIT;
   constexpr int kSoftWarps = 4 * NSPLIT;
-  constexpr int kCorrWarp0 = kSoftWarps;       // 4 correction warps
   constexpr int kProdWarp = kSoftWarps + 4;
   constexpr int kMmaWarp = kSoftWarps + 5;
   constexpr int kDAtoms = D / 64;              // 128-byte atoms along D for 16-bit operands

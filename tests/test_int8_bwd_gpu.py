@@ -22,7 +22,6 @@ def test_int8_bwd_matches_contract_oracle(shape):
     q, k, v, dO = [torch.randn(shape, generator=g).to(torch.float16) for _ in range(4)]
     k = (k.float() + 1.0).to(torch.float16)                 # non-zero token mean: exercises the k_mean term
     out = A.SageAttention3_Int8_autograd_function.forward(q.cuda(), k.cuda(), v.cuda())
-    A.SageAttention3_Int8_autograd_function._lse32_stash = None
     O, lse16, kmean, q_i8, k_i8_T, v_i8, sq, sk, sv, Bq, Bkv = out
     # oracle on the SAME saved tensors (so only the backward is compared)
     c = lambda t: t.cpu()
