@@ -25,10 +25,16 @@ from torch.autograd import Function
 
 from . import ops
 
-# fp32 copy of the log2-LSE for the backward (LEDGER I-15), keyed weakly by the fp16 lse tensor the forward returns:
-# forward() has no ctx in the new-style Function API, so setup_context() picks the copy up from here.  Entries vanish
-# with their key, so a forward under no_grad leaves nothing behind.
-_LSE32 = weakref.WeakKeyDictionary()
+# fp32 copy of the log2-LSE for the backward (LEDGER I-15), keyed by the identity of the fp16 lse tensor the forward
+# returns: forward() has no ctx in the new-style Function API, so setup_context() picks the copy up from here.  A
+# finalizer drops the entry with its key, so a forward under no_grad leaves nothing behind.
+_LSE32 = {}
+
+
+def _stash_lse32(lse16, lse32):
+    k = id(lse16)
+    _LSE32[k] = lse32
+    weakref.finalize(lse16, _LSE32.pop, k, None)
 
 _CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2}
 
@@ -120,7 +126,7 @@ class SageAttention3_Int8_autograd_function(Function):
         v_i8, sv = ops.quant_block(v_fp16, Bkv)
         O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
                                                 nsplit=_CFG["nsplit"], want_lse32=True)
-        _LSE32[lse16] = lse32                                                  # picked up by setup_context
+        _stash_lse32(lse16, lse32)                                             # picked up by setup_context
         return (O.view(batch, head, q_tokens, D), lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
 
     @staticmethod
@@ -128,7 +134,7 @@ class SageAttention3_Int8_autograd_function(Function):
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv = output
         ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv)
         ctx.set_materialize_grads(False)       # do not allocate zero grads for the 10 auxiliary outputs
-        lse32 = _LSE32.pop(l_bh_fp16, None)
+        lse32 = _LSE32.pop(id(l_bh_fp16), None)
         ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
         ctx.args = (Bq, Bkv)
 

@@ -43,6 +43,8 @@ def test_sage_attention_autograd_end_to_end():
     qh, kh, vh = [t.to(torch.float16).cuda().requires_grad_() for t in (q, k, v)]
     O = A.sage_attention_3_int8(qh, kh, vh)
     assert O.dtype == torch.float16 and O.shape == shape
+    saved = O.grad_fn.saved_tensors
+    assert saved[-1] is not None and saved[-1].dtype == torch.float32      # fp32 lse reached the backward (LEDGER I-15)
     O.backward(dO.to(torch.float16).cuda())
     qf, kf, vf = [t.to(torch.float16).float().requires_grad_() for t in (q, k, v)]
     Ob = baseline_pytorch_attention(qf, kf, vf, shape[3], False)
