@@ -64,7 +64,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   __shared__ float red_p[2][NW], red_ds[2][NW];
   __shared__ float rowsum_ds[2][NG][128];
-  __shared__ float kmean_s[D];                                  // sm_scale * k_mean[d]
+  __shared__ __align__(16) float kmean_s[D];                    // sm_scale * k_mean[d]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool leader = (tid == 0);
@@ -138,9 +138,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const float sk_f = __half2float(p.sk[head_row0 / 128 + j]);
   const float sv_f = __half2float(p.sv[head_row0 / 128 + j]);
   const float* kmean = kmean_s + half * DH;
-  float dv_acc[DH], dk_acc[DH];
+  float2 dv_acc[DH / 2], dk_acc[DH / 2];                        // fp32x2: FFMA2 / FMUL2 / FADD2 halve the issue slots
 #pragma unroll
-  for (int d = 0; d < DH; ++d) { dv_acc[d] = 0.f; dk_acc[d] = 0.f; }
+  for (int d = 0; d < DH / 2; ++d) { dv_acc[d] = make_float2(0.f, 0.f); dk_acc[d] = make_float2(0.f, 0.f); }
   float c_dv_prev = 0.f, c_dk_prev = 0.f, c_dq_prev = 0.f, rs_prev = 0.f;
 
   auto drain_dv_dk = [&](float c_dv, float c_dk) {
@@ -151,9 +151,11 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld16(lane_addr + 384 + half * DH + ch * 16, r2);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        dv_acc[ch * 16 + c] = fmaf(__int2float_rn((int)r[c]), c_dv, dv_acc[ch * 16 + c]);
-        dk_acc[ch * 16 + c] = fmaf(__int2float_rn((int)r2[c]), c_dk, dk_acc[ch * 16 + c]);
+      for (int c = 0; c < 8; ++c) {
+        dv_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r[2 * c]), __int2float_rn((int)r[2 * c + 1])),
+                                        make_float2(c_dv, c_dv), dv_acc[ch * 8 + c]);
+        dk_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r2[2 * c]), __int2float_rn((int)r2[2 * c + 1])),
+                                        make_float2(c_dk, c_dk), dk_acc[ch * 8 + c]);
       }
     }
   };
@@ -167,12 +169,11 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint8_t* atom = smem + L::off_dq + (col >> 5) * (128 * 128);
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
-        float4 o;
-        o.x = fmaf(__int2float_rn((int)r[c]), c_dq, rs_row * kmean[ch * 16 + c]);
-        o.y = fmaf(__int2float_rn((int)r[c + 1]), c_dq, rs_row * kmean[ch * 16 + c + 1]);
-        o.z = fmaf(__int2float_rn((int)r[c + 2]), c_dq, rs_row * kmean[ch * 16 + c + 2]);
-        o.w = fmaf(__int2float_rn((int)r[c + 3]), c_dq, rs_row * kmean[ch * 16 + c + 3]);
-        *reinterpret_cast<float4*>(atom + swz128(row, ((col & 31) + c) * 4)) = o;
+        const float2 k01 = *reinterpret_cast<const float2*>(kmean + ch * 16 + c), k23 = *reinterpret_cast<const float2*>(kmean + ch * 16 + c + 2);
+        const float2 rs2 = make_float2(rs_row, rs_row), cq2 = make_float2(c_dq, c_dq);
+        const float2 o01 = __ffma2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2, __fmul2_rn(rs2, k01));
+        const float2 o23 = __ffma2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2, __fmul2_rn(rs2, k23));
+        *reinterpret_cast<float4*>(atom + swz128(row, ((col & 31) + c) * 4)) = make_float4(o01.x, o01.y, o23.x, o23.y);
       }
     }
   };
@@ -196,7 +197,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_after();
     // ---- pass 1: fp16 logits (kept packed), tile amax of P and |dS|, row sum of dS
     __half2 sh[CW / 2];
-    float amax_p = 0.f, amax_ds = 0.f, rs = 0.f;
+    float amax_p = 0.f, amax_ds = 0.f;
+    float2 rs2acc = make_float2(0.f, 0.f);
+    const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(-lse, -lse), cdp2 = make_float2(c_dp, c_dp), ndlt2 = make_float2(-dlt, -dlt);
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
       uint32_t r[16], r2[16];
@@ -205,15 +208,14 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
-        const __half2 h = __floats2half2_rn(__int2float_rn((int)r[c]) * c_s, __int2float_rn((int)r[c + 1]) * c_s);
+        const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cs2));
         sh[ch * 8 + c / 2] = h;
-        const float2 f = __half22float2(h);
-        const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
-        amax_p = fmaxf(amax_p, fmaxf(p0, p1));
-        const float d0 = p0 * fmaf(__int2float_rn((int)r2[c]), c_dp, -dlt);
-        const float d1 = p1 * fmaf(__int2float_rn((int)r2[c + 1]), c_dp, -dlt);
-        amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d0), fabsf(d1)));
-        rs += d0 + d1;
+        const float2 e = __fadd2_rn(__half22float2(h), nlse2);
+        const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+        amax_p = fmaxf(amax_p, fmaxf(pp.x, pp.y));
+        const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdp2, ndlt2));
+        amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d.x), fabsf(d.y)));
+        rs2acc = __fadd2_rn(rs2acc, d);
       }
     }
 #pragma unroll
@@ -222,7 +224,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       amax_ds = fmaxf(amax_ds, __shfl_xor_sync(0xffffffffu, amax_ds, o));
     }
     if (lane == 0) { red_p[ph][warp] = amax_p; red_ds[ph][warp] = amax_ds; }
-    rowsum_ds[ph][half][row] = rs;
+    rowsum_ds[ph][half][row] = rs2acc.x + rs2acc.y;
     // ---- drain dV / dK of the previous tile (its MMAs ran while pass 1 executed)
     if (t > 0) {
       mbar_wait(&parts_full, (t - 1) & 1);
@@ -249,6 +251,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
     //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
     uint8_t* ds_tile = smem + L::off_ds + ph * (128 * 128);
+    const float2 cdpi2 = make_float2(c_dp * inv_ds, c_dp * inv_ds), ndlti2 = make_float2(-dlt * inv_ds, -dlt * inv_ds);
+    const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
       uint32_t r2[16];
@@ -261,14 +265,15 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 4; e += 2) {
           const int c = q4 * 4 + e;
-          const float2 f = __half22float2(sh[ch * 8 + c / 2]);
-          const float p0 = ex2_approx(f.x - lse), p1 = ex2_approx(f.y - lse);
-          const float d0 = p0 * fmaf(__int2float_rn((int)r2[c]), c_dp, -dlt);
-          const float d1 = p1 * fmaf(__int2float_rn((int)r2[c + 1]), c_dp, -dlt);
-          bp[e] = __float_as_uint(__fmaf_rz(p0, inv_p, 8388608.0f));          // P >= 0: low byte = trunc(P / sP)
-          bp[e + 1] = __float_as_uint(__fmaf_rz(p1, inv_p, 8388608.0f));
-          bd[e] = (uint32_t)__float2int_rz(d0 * inv_ds);
-          bd[e + 1] = (uint32_t)__float2int_rz(d1 * inv_ds);
+          const float2 e2 = __fadd2_rn(__half22float2(sh[ch * 8 + c / 2]), nlse2);
+          const float2 pp = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
+          // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS folded into the FFMA2 constants
+          const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
+          const float2 pq = __ffma2_rz(pp, invp2, magic2);                      // P >= 0: low byte = trunc(P / sP)
+          bp[e] = __float_as_uint(pq.x);
+          bp[e + 1] = __float_as_uint(pq.y);
+          bd[e] = (uint32_t)__float2int_rz(dq.x);
+          bd[e + 1] = (uint32_t)__float2int_rz(dq.y);
         }
         wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
         wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
@@ -323,14 +328,14 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   for (int d = 0; d < DH; d += 8) {
     uint4 a, b;
     __half2 t2;
-    t2 = __floats2half2_rn(dk_acc[d], dk_acc[d + 1]); a.x = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dk_acc[d + 2], dk_acc[d + 3]); a.y = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dk_acc[d + 4], dk_acc[d + 5]); a.z = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dk_acc[d + 6], dk_acc[d + 7]); a.w = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dv_acc[d], dv_acc[d + 1]); b.x = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dv_acc[d + 2], dv_acc[d + 3]); b.y = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dv_acc[d + 4], dv_acc[d + 5]); b.z = *reinterpret_cast<uint32_t*>(&t2);
-    t2 = __floats2half2_rn(dv_acc[d + 6], dv_acc[d + 7]); b.w = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2]); a.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2 + 1]); a.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2 + 2]); a.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2 + 3]); a.w = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2]); b.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2 + 1]); b.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2 + 2]); b.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2 + 3]); b.w = *reinterpret_cast<uint32_t*>(&t2);
     *reinterpret_cast<uint4*>(dk_dst + d) = a;
     *reinterpret_cast<uint4*>(dv_dst + d) = b;
   }

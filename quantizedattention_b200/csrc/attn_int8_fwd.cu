@@ -123,6 +123,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float sk_f = __half2float(p.sk[((size_t)bh * p.Sk) / kBN + j]);
       const float sv_f = __half2float(p.sv[((size_t)bh * p.Sk) / kBN + j]);
       const float c = sq_f * sk_f * p.qk_scale;
+      const float2 c2 = make_float2(c, c);
       if (warp == 0) QA_TL(0);
       mbar_wait(&s_full[b], ph);
       tc_fence_after();
@@ -136,10 +137,9 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a0 = __int2float_rn((int)r[2 * i]) * c;
-          float a1 = __int2float_rn((int)r[2 * i + 1]) * c;
-          __half2 h = __floats2half2_rn(a0, a1);
+        for (int i = 0; i < 16; ++i) {                            // packed fp32x2 multiply (FMUL2): half the issue slots
+          const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
+          __half2 h = __float22half2_rn(a);
           sh[ch * 16 + i] = h;
           mx2 = __hmax2(mx2, h);
         }
@@ -171,7 +171,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(&p_empty[b], ph ^ 1);
       if (warp == 0) QA_TL(4);
       const __half2 m2 = __half2half2(m_new);
-      float lsum = 0.f;
+      float2 ls2 = make_float2(0.f, 0.f);
+      const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
       uint8_t* prow = smem + L::off_p + b * L::kPBytes;
 #pragma unroll
       for (int g = 0; g < NC / 16; ++g) {
@@ -181,18 +182,19 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           uint32_t bytes[4];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
-            float p0 = ex2_approx(f.x), p1 = ex2_approx(f.y);
-            lsum += p0 + p1;
-            bytes[h2 * 2] = __float_as_uint(__fmaf_rz(p0, inv_sp, 8388608.0f));          // low byte = trunc(P/sp)
-            bytes[h2 * 2 + 1] = __float_as_uint(__fmaf_rz(p1, inv_sp, 8388608.0f));
+            const float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
+            const float2 pp = make_float2(ex2_approx(f.x), ex2_approx(f.y));
+            ls2 = __fadd2_rn(ls2, pp);
+            const float2 qf = __ffma2_rz(pp, inv2, magic2);                           // low byte = trunc(P/sp)
+            bytes[h2 * 2] = __float_as_uint(qf.x);
+            bytes[h2 * 2 + 1] = __float_as_uint(qf.y);
           }
           w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
         }
         const uint32_t off = swz128(row, c0 + g * 16);
         *reinterpret_cast<uint4*>(prow + off) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      l = l * rescale + lsum;
+      l = l * rescale + (ls2.x + ls2.y);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
@@ -209,15 +211,15 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const int d0 = split * DC;
-    float acc[DC];
+    float2 acc2[DC / 2];                                   // fp32x2 accumulators: one FFMA2 per two elements
 #pragma unroll
-    for (int i = 0; i < DC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < DC / 2; ++i) acc2[i] = make_float2(0.f, 0.f);
     if (p.O_acc_in != nullptr) {
       const float* src = p.O_acc_in + ((size_t)bh * p.Sq + q0 + row) * D + d0;
 #pragma unroll
       for (int i = 0; i < DC; i += 4) {
         const float4 t = *reinterpret_cast<const float4*>(src + i);
-        acc[i] = t.x; acc[i + 1] = t.y; acc[i + 2] = t.z; acc[i + 3] = t.w;
+        acc2[i / 2] = make_float2(t.x, t.y); acc2[i / 2 + 1] = make_float2(t.z, t.w);
       }
     }
     float s_pend = 1.0f;
@@ -233,10 +235,11 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (sc.x != 0.f) s_pend *= sc.x;
       if (__any_sync(0xffffffffu, s_pend < 1e-12f)) {       // rare: fold the pending factor back in before it underflows
 #pragma unroll
-        for (int i = 0; i < DC; ++i) acc[i] *= s_pend;
+        for (int i = 0; i < DC / 2; ++i) acc2[i] = __fmul2_rn(acc2[i], make_float2(s_pend, s_pend));
         s_pend = 1.0f;
       }
       const float c_eff = __fdividef(sc.y, s_pend);
+      const float2 ce2 = make_float2(c_eff, c_eff);
       if (cw == 0) QA_TL(6);
       mbar_wait(&o_full[b], ph);
       tc_fence_after();
@@ -247,7 +250,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld32(lane_addr + 256 + b * 128 + d0 + ch * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[ch * 32 + i] = fmaf(__int2float_rn((int)r[i]), c_eff, acc[ch * 32 + i]);
+        for (int i = 0; i < 16; ++i)
+          acc2[ch * 16 + i] = __ffma2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), ce2, acc2[ch * 16 + i]);
       }
       tc_fence_before();
       __syncwarp();
@@ -263,17 +267,17 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float* dst = p.O_acc_out + grow * D + d0;
 #pragma unroll
       for (int i = 0; i < DC; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i] * s_pend, acc[i + 1] * s_pend, acc[i + 2] * s_pend, acc[i + 3] * s_pend);
+        *reinterpret_cast<float4*>(dst + i) = make_float4(acc2[i / 2].x * s_pend, acc2[i / 2].y * s_pend, acc2[i / 2 + 1].x * s_pend, acc2[i / 2 + 1].y * s_pend);
       if (split == 0) { p.m_out[grow] = __half2float(m_fin[row]); p.l_out[grow] = l; }
     } else {
       const float inv_l = s_pend / l;                                          // O / l (:256), pending rescale folded in
       __half* dst = p.O + grow * D + d0;
 #pragma unroll
       for (int i = 0; i < DC; i += 8) {
-        __half2 h0 = __floats2half2_rn(acc[i] * inv_l, acc[i + 1] * inv_l);
-        __half2 h1 = __floats2half2_rn(acc[i + 2] * inv_l, acc[i + 3] * inv_l);
-        __half2 h2 = __floats2half2_rn(acc[i + 4] * inv_l, acc[i + 5] * inv_l);
-        __half2 h3 = __floats2half2_rn(acc[i + 6] * inv_l, acc[i + 7] * inv_l);
+        __half2 h0 = __floats2half2_rn(acc2[i / 2].x * inv_l, acc2[i / 2].y * inv_l);
+        __half2 h1 = __floats2half2_rn(acc2[i / 2 + 1].x * inv_l, acc2[i / 2 + 1].y * inv_l);
+        __half2 h2 = __floats2half2_rn(acc2[i / 2 + 2].x * inv_l, acc2[i / 2 + 2].y * inv_l);
+        __half2 h3 = __floats2half2_rn(acc2[i / 2 + 3].x * inv_l, acc2[i / 2 + 3].y * inv_l);
         uint4 v;
         v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1);
         v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
