@@ -140,6 +140,7 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool diag = p.causal && (i == j);
       mbar_wait(&sd_full, ph);
       tc_fence_after();
+      const float2 qk2 = make_float2(p.qk_scale, p.qk_scale), nlse2 = make_float2(-lse, -lse), ndlt2 = make_float2(-dlt, -dlt);
       auto compute = [&](auto masked) {                            // masked = diagonal tile or causal query row 0
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -152,20 +153,17 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             uint32_t wp[4], wd[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float pv[2], ds[2];
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                const int c = g * 8 + e * 2 + t;
-                float P = ex2_approx(fmaf(__uint_as_float(rs[c]), p.qk_scale, -lse));            // :391-392
-                if (decltype(masked)::value) {
-                  if (diag && (j * 128 + half * 64 + ch * 32 + c >= qi)) P = 0.f;               // strict causal, weight 0
-                  if (qi == 0) P = 0.f;                                                         // row 0: handled by the fixup
-                }
-                pv[t] = P;
-                ds[t] = P * (__uint_as_float(rp[c]) - dlt);                                      // dS = P*(dP - delta)
+              const int c = g * 8 + e * 2;
+              const float2 ex = __ffma2_rn(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), qk2, nlse2);
+              float2 pv = make_float2(ex2_approx(ex.x), ex2_approx(ex.y));                       // :391-392
+              if (decltype(masked)::value) {
+                const int key = j * 128 + half * 64 + ch * 32 + c;
+                if ((diag && key >= qi) || qi == 0) pv.x = 0.f;                                  // strict causal, weight 0; row 0: fixup
+                if ((diag && key + 1 >= qi) || qi == 0) pv.y = 0.f;
               }
-              __nv_bfloat162 pb = __floats2bfloat162_rn(pv[0], pv[1]);
-              __half2 dh = __floats2half2_rn(ds[0], ds[1]);
+              const float2 ds = __fmul2_rn(pv, __fadd2_rn(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), ndlt2));   // dS = P*(dP - delta)
+              __nv_bfloat162 pb = __float22bfloat162_rn(pv);
+              __half2 dh = __float22half2_rn(ds);
               wp[e] = *reinterpret_cast<uint32_t*>(&pb);
               wd[e] = *reinterpret_cast<uint32_t*>(&dh);
             }
@@ -190,9 +188,12 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld32(lane_addr + half * DH + ch * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          red_add_v4f(dq_dst + ch * 32 + c, __uint_as_float(r[c]) * p.sm_scale, __uint_as_float(r[c + 1]) * p.sm_scale,
-                      __uint_as_float(r[c + 2]) * p.sm_scale, __uint_as_float(r[c + 3]) * p.sm_scale);
+        for (int c = 0; c < 32; c += 4) {
+          const float2 sm2 = make_float2(p.sm_scale, p.sm_scale);
+          const float2 a = __fmul2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), sm2);
+          const float2 b = __fmul2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), sm2);
+          red_add_v4f(dq_dst + ch * 32 + c, a.x, a.y, b.x, b.y);
+        }
       }
       tc_fence_before();
       __syncwarp();

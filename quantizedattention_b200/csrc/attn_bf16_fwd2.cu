@@ -96,6 +96,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       tc_fence_after();
       // ---- pass 1: u = bf16(bf16(S) * qk_scale), masked; top-2 of the row tile
       uint32_t u2[64];
+      const float2 qk2 = make_float2(p.qk_scale, p.qk_scale);
       __nv_bfloat162 t1 = u2bf(ninf2), t2 = u2bf(ninf2);
       auto pass1 = [&](auto masked) {                              // two instantiations: the mask costs nothing off-diagonal
 #pragma unroll
@@ -105,7 +106,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            uint32_t u = pack2_bf16(__uint_as_float(r[2 * i]) * p.qk_scale, __uint_as_float(r[2 * i + 1]) * p.qk_scale);   // u = bf16(S * qk_scale)
+            const __nv_bfloat162 ub = __float22bfloat162_rn(__fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), qk2));
+            uint32_t u = bf2u(ub);                                 // u = bf16(S * qk_scale), one FMUL2 + one pack per pair
             if (decltype(masked)::value) {                         // strict causal: keep key < query
               const int key = j * 128 + ch * 32 + 2 * i;
               if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
@@ -141,7 +143,10 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tmem_ld32(o_addr + ch * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
+            for (int i = 0; i < 32; i += 2) {
+              const float2 o2 = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(resc, resc));
+              r[i] = __float_as_uint(o2.x); r[i + 1] = __float_as_uint(o2.y);
+            }
             tmem_st32(o_addr + ch * 32, r);
           }
           tmem_st_wait();
@@ -152,7 +157,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       // ---- pass 2: P = bf16(exp2(bf16(u - m'))) written back over the S columns (2 per column), l += sum(P)
       const __nv_bfloat162 m2 = __bfloat162bfloat162(m_new);
-      float lsum = 0.f;
+      float2 ls2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t w[32];
@@ -160,13 +165,13 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int i = 0; i < 32; ++i) {
           const uint32_t t = bf2u(__hsub2(u2bf(u2[ch * 32 + i]), m2));
           const uint32_t pp = pack2_bf16(ex2_approx(bf2_lo(t)), ex2_approx(bf2_hi(t)));
-          lsum += bf2_lo(pp) + bf2_hi(pp);
+          ls2 = __fadd2_rn(ls2, make_float2(bf2_lo(pp), bf2_hi(pp)));
           w[i] = pp;
         }
         tmem_st32(s_addr + ch * 32, w);
       }
       tmem_st_wait();
-      l = l * resc + lsum;
+      l = l * resc + (ls2.x + ls2.y);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x]);
