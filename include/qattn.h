@@ -80,6 +80,12 @@ int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void
  * (attention_bf16.py:309-448) ---- */
 int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH, int Sq,
                 int Sk, int D, int causal, int nsplit, void* stream);
+/* Same, with the lazy-rescale threshold explicit: a new running maximum m' (attention_bf16.py:236-264) is adopted only
+ * when it exceeds the current one by more than rescale_tau (log2 units, 0..16); until then P = exp2(u - m) may reach
+ * 2^rescale_tau and O is not rescaled (:280).  Mathematically neutral; 0 reproduces the reference's step-by-step
+ * maximum, qa_bf16_fwd uses 8. */
+int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH, int Sq,
+                   int Sk, int D, int causal, int nsplit, float rescale_tau, void* stream);
 int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
                 const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
                 int causal, void* stream);

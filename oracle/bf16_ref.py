@@ -35,11 +35,13 @@ def _bias_corrected_max(m_prev, u_or_s, cmp_vals):
     return m_new
 
 
-def bf16_fwd(q, k, v, causal: bool, tile_k: int = 32, mode: str = "literal"):
+def bf16_fwd(q, k, v, causal: bool, tile_k: int = 32, mode: str = "literal", lazy_tau: float = 0.0):
     """helion_atten_bf16_fwd_training (attention_bf16.py:195-294), vectorised over q rows
     (rows are independent; the `begin_q < end_k` guard only skips a no-op mask).
     q,k fp16, v bf16 [B,H,S,D] -> (O fp32 [B,H,S,D], lse fp32 [B*H,S]).  tile_k = k-tile width
-    (the literal result depends on it through the running bf16 max)."""
+    (the literal result depends on it through the running bf16 max).  lazy_tau (contract mode only): a new running
+    maximum is adopted only when it exceeds the current one by more than lazy_tau log2 units (the CUDA kernel's
+    lazy rescale, include/qattn.h qa_bf16_fwd_ex); 0 = the reference's step-by-step maximum."""
     assert mode in ("literal", "contract")
     B, H, S, D = q.shape
     Sk = k.shape[2]
@@ -75,6 +77,9 @@ def bf16_fwd(q, k, v, causal: bool, tile_k: int = 32, mode: str = "literal"):
         else:
             u = Sb                                                       # bf16 scaled logits (already scaled above)
             m_new = _bias_corrected_max(m, torch.amax(u, -1, keepdim=True), u)
+            if lazy_tau > 0:
+                adopt = (m_new - m).float() > lazy_tau                   # bf16 difference, as the kernel computes it
+                m_new = torch.where(adopt, m_new, m)
             # rows whose every key so far is masked keep m = -inf; avoid (-inf) - (-inf)
             m_fin = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)
             Ssh = u - m_fin

@@ -32,6 +32,7 @@ struct Bf16FwdParams {
   float* lse;      // [BH*Sq] fp32
   int Sq, Sk, causal;
   float qk_scale;
+  float rescale_tau;   // see qa_bf16_fwd_ex
 };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -153,6 +154,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float mf = __bfloat162float(m_new);
       if (many && mf > 0.f) m_new = __float2bfloat16(2.0f * mf);
       else if (many && mf < 0.f) m_new = __float2bfloat16(0.f);
+      if (!(__bfloat162float(__hsub(m_new, m_bf)) > p.rescale_tau)) m_new = m_bf;     // lazy rescale (qa_bf16_fwd_ex)
       const float resc = __bfloat162float(__float2bfloat16(ex2_approx(__bfloat162float(__hsub(m_bf, m_new)))));
       m_bf = m_new;
       if (split == 0 && j > 0) {                                 // tile 0 overwrites O: no rescale to hand over
@@ -370,27 +372,28 @@ static int launch_bf16_fwd(const void* q, const void* k, const void* v, const Bf
 // two-query-tile variant (attn_bf16_fwd2.cu)
 template <int D, int STAGES>
 int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
-                     float qk_scale, cudaStream_t st);
+                     float qk_scale, float rescale_tau, cudaStream_t st);
 
 }  // namespace qa
 
 using namespace qa;
 
 // q, k: fp16 [BH*S, D]; v: bf16 [BH*Sk, D]; O: fp32 [BH*Sq, D]; lse: fp32 [BH*Sq] (log2-sum-exp2).
-extern "C" int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH,
-                           int Sq, int Sk, int D, int causal, int nsplit, void* stream) {
+extern "C" int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH,
+                              int Sq, int Sk, int D, int causal, int nsplit, float rescale_tau, void* stream) {
+  if (!(rescale_tau >= 0.f && rescale_tau <= 16.f)) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: rescale_tau must be in [0, 16]");
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: D must be 64 or 128");
   if (Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: Sq, Sk must be multiples of 128");
   if (causal && Sq != Sk) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: causal needs Sq == Sk");
   if (((uintptr_t)q_f16 | (uintptr_t)k_f16 | (uintptr_t)v_bf16 | (uintptr_t)O_f32) & 15)
     return qa_fail(QA_ERR_ALIGN, "qa_bf16_fwd: 16-byte alignment required");
   Bf16FwdParams p;
-  p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
+  p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.rescale_tau = rescale_tau;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
   if ((nsplit == 0 || nsplit == 3) && Sq % 256 == 0) {           // default schedule: two query tiles per CTA, P and O in TMEM
-    int rc = D == 128 ? launch_bf16_fwd2<128, 2>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, st)
-                      : launch_bf16_fwd2<64, 3>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, st);
+    int rc = D == 128 ? launch_bf16_fwd2<128, 2>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, rescale_tau, st)
+                      : launch_bf16_fwd2<64, 3>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, rescale_tau, st);
     if (rc) return rc;
     if (causal) rc = launch_row0_fixup(v_bf16, p.O, p.lse, BH, Sq, Sk, D, st);
     return rc;
@@ -400,4 +403,10 @@ extern "C" int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_b
                                    : launch_bf16_fwd<128, 1, 2, 1>(q_f16, k_f16, v_bf16, p, BH, st);
   return nsplit == 2 ? launch_bf16_fwd<64, 2, 3, 2>(q_f16, k_f16, v_bf16, p, BH, st)
                      : launch_bf16_fwd<64, 1, 3, 2>(q_f16, k_f16, v_bf16, p, BH, st);
+}
+
+// Default schedule and the default lazy-rescale threshold (8 log2 units, i.e. P <= 256).
+extern "C" int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH,
+                           int Sq, int Sk, int D, int causal, int nsplit, void* stream) {
+  return qa_bf16_fwd_ex(q_f16, k_f16, v_bf16, O_f32, lse_f32, BH, Sq, Sk, D, causal, nsplit, 8.0f, stream);
 }

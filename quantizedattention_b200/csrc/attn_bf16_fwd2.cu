@@ -2,13 +2,15 @@
 // Same numerics as attn_bf16_fwd.cu (reference attention_bf16.py:195-294, contract mode); different schedule:
 //   * one CTA owns TWO 128-row query tiles (A, B) of one head and shares every K/V tile between them;
 //   * each softmax warpgroup owns one query tile, one thread per row (128 columns): no cross-warp exchange;
-//   * S_A / S_B live in TMEM (one buffer each): while warpgroup A runs its softmax the tensor core computes S_B;
+//   * the softmax advances in steps of 64 keys (half a K/V tile).  S_A / S_B are double-buffered in TMEM
+//     (2 x 64 columns each): Q K^T of step t+2 is issued right behind P V of step t, so the logits of step t+1 are
+//     already waiting when a softmax warp finishes step t - the softmax warps never idle on the tensor pipe;
 //   * P is written back to TMEM over the S columns (bf16, 2 per column) and consumed as the A operand of the
 //     P V MMA straight from TMEM (no shared-memory round trip, no proxy fence);
-//   * O_A / O_B stay resident in TMEM; a softmax warp rescales its own 32 rows only when one of their maxima moved
-//     (no separate correction warpgroup: 10 warps per CTA leave 168 registers per thread for instruction-level
-//     parallelism in the softmax loop, which is what bounds this kernel).
-// TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,256+D)  O_B [384,384+D).
+//   * O_A / O_B stay resident in TMEM; a softmax warp rescales its own 32 rows only when one of their maxima moved.
+//     With the lazy running maximum (rescale_tau, qa_bf16_fwd_ex) that is rare, so there is no correction warpgroup:
+//     10 warps per CTA leave 168 registers per thread for instruction-level parallelism in the softmax loop.
+// TMEM (512 columns): S_A[2] [0,64) [64,128)  S_B[2] [128,192) [192,256)  O_A [256,256+D)  O_B [384,384+D).
 #include "qa_ptx.cuh"
 #include "qa_host.h"
 #include <type_traits>
@@ -32,6 +34,7 @@ struct Bf16Fwd2Params {
   float* lse;
   int Sq, Sk, causal;
   float qk_scale;
+  float rescale_tau;   // adopt a new running maximum only when it exceeds the current one by more than this (log2 units)
 };
 
 __device__ __forceinline__ float bf2_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -52,7 +55,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_ready[2];
+  __shared__ uint64_t s_full[2][2], p_full[2][2], o_full[2][2], o_ready[2][2];   // [query tile][S buffer]: a softmax warp may run up to two steps ahead
+                                                                                   // of the issuer, so every barrier is per buffer (a single one aliases parities)
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -68,7 +72,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&o_full[x], 1); mbar_init(&o_ready[x], 4);
+      mbar_init(&s_full[x][0], 1); mbar_init(&s_full[x][1], 1); mbar_init(&p_full[x][0], 4); mbar_init(&p_full[x][1], 4);
+      mbar_init(&o_full[x][0], 1); mbar_init(&o_full[x][1], 1); mbar_init(&o_ready[x][0], 4); mbar_init(&o_ready[x][1], 4);
     }
     fence_mbar_init();
   }
@@ -86,30 +91,32 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const uint32_t o_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 256 + x * 128;
     const int grow = q0 + x * 128 + row;                          // query index inside the head
     const int qt = 2 * pt + x;                                    // this tile's diagonal k-tile
-    const int nkq = nkx[x];
+    const int nst = 2 * nkx[x];                                   // 64-key steps of this query tile
     __nv_bfloat16 m_bf = __float2bfloat16(-INFINITY);
     float l = 1.0f;                                               // attention_bf16.py:198
     const uint32_t ninf2 = 0xff80ff80u;
-    for (int j = 0; j < nkq; ++j) {
+    const float2 qk2 = make_float2(p.qk_scale, p.qk_scale);
+    for (int t = 0; t < nst; ++t) {
+      const int j = t >> 1, b = t & 1;
       const bool diag = p.causal && (j == qt);
-      mbar_wait(&s_full[x], j & 1);
+      const uint32_t sb_addr = s_addr + b * 64;
+      mbar_wait(&s_full[x][b], j & 1);
       tc_fence_after();
-      // ---- pass 1: u = bf16(bf16(S) * qk_scale), masked; top-2 of the row tile
-      uint32_t u2[64];
-      const float2 qk2 = make_float2(p.qk_scale, p.qk_scale);
+      // ---- pass 1: u = bf16(S * qk_scale), masked; top-2 of the row segment
+      uint32_t u2[32];
       __nv_bfloat162 t1 = u2bf(ninf2), t2 = u2bf(ninf2);
       auto pass1 = [&](auto masked) {                              // two instantiations: the mask costs nothing off-diagonal
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t r[32];
-          tmem_ld32(s_addr + ch * 32, r);
+          tmem_ld32(sb_addr + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const __nv_bfloat162 ub = __float22bfloat162_rn(__fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), qk2));
             uint32_t u = bf2u(ub);                                 // u = bf16(S * qk_scale), one FMUL2 + one pack per pair
             if (decltype(masked)::value) {                         // strict causal: keep key < query
-              const int key = j * 128 + ch * 32 + 2 * i;
+              const int key = t * 64 + ch * 32 + 2 * i;
               if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
               if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
             }
@@ -131,53 +138,52 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const float mf = __bfloat162float(m_new);
       if (many && mf > 0.f) m_new = __float2bfloat16(2.0f * mf);
       else if (many && mf < 0.f) m_new = __float2bfloat16(0.f);
+      // lazy rescale: while the candidate is within rescale_tau of the current maximum keep the current one
+      // (P <= 2^tau, mathematically neutral; rescale_tau = 0 is the step-by-step maximum of the reference)
+      if (!(__bfloat162float(__hsub(m_new, m_bf)) > p.rescale_tau)) m_new = m_bf;
       const float resc = __bfloat162float(__float2bfloat16(ex2_approx(__bfloat162float(__hsub(m_bf, m_new)))));
       m_bf = m_new;
-      if (j > 0) {                                                // tile 0 overwrites O: nothing to rescale
-        if (__any_sync(0xffffffffu, resc != 1.0f)) {             // O *= rescale (:280) only when a row maximum moved
-          mbar_wait(&o_full[x], (j - 1) & 1);                    // P V of tile j-1 has landed in TMEM
-          tc_fence_after();
+      if (t > 0 && __any_sync(0xffffffffu, resc != 1.0f)) {       // O *= rescale (:280): rare with the lazy maximum
+        mbar_wait(&o_full[x][b ^ 1], ((t - 1) >> 1) & 1);        // P V of step t-1 has landed in TMEM
+        tc_fence_after();
+        const float2 rs2 = make_float2(resc, resc);
 #pragma unroll
-          for (int ch = 0; ch < D / 32; ++ch) {
-            uint32_t r[32];
-            tmem_ld32(o_addr + ch * 32, r);
-            tmem_ld_wait();
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(o_addr + ch * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float2 o2 = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(resc, resc));
-              r[i] = __float_as_uint(o2.x); r[i + 1] = __float_as_uint(o2.y);
-            }
-            tmem_st32(o_addr + ch * 32, r);
+          for (int i = 0; i < 32; i += 2) {
+            const float2 o2 = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), rs2);
+            r[i] = __float_as_uint(o2.x); r[i + 1] = __float_as_uint(o2.y);
           }
-          tmem_st_wait();
-          tc_fence_before();
+          tmem_st32(o_addr + ch * 32, r);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_ready[x]);                  // the MMA warp may accumulate tile j into O
+        tmem_st_wait();
+        tc_fence_before();
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_ready[x][b]);                 // the MMA warp may accumulate step t into O
       // ---- pass 2: P = bf16(exp2(bf16(u - m'))) written back over the S columns (2 per column), l += sum(P)
       const __nv_bfloat162 m2 = __bfloat162bfloat162(m_new);
       float2 ls2 = make_float2(0.f, 0.f);
+      uint32_t w[32];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t w[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t t = bf2u(__hsub2(u2bf(u2[ch * 32 + i]), m2));
-          const uint32_t pp = pack2_bf16(ex2_approx(bf2_lo(t)), ex2_approx(bf2_hi(t)));
-          ls2 = __fadd2_rn(ls2, make_float2(bf2_lo(pp), bf2_hi(pp)));
-          w[i] = pp;
-        }
-        tmem_st32(s_addr + ch * 32, w);
+      for (int i = 0; i < 32; ++i) {
+        const uint32_t d = bf2u(__hsub2(u2bf(u2[i]), m2));
+        const uint32_t pp = pack2_bf16(ex2_approx(bf2_lo(d)), ex2_approx(bf2_hi(d)));
+        ls2 = __fadd2_rn(ls2, make_float2(bf2_lo(pp), bf2_hi(pp)));
+        w[i] = pp;
       }
+      tmem_st32(sb_addr, w);
       tmem_st_wait();
       l = l * resc + (ls2.x + ls2.y);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[x]);
+      if (lane == 0) mbar_arrive(&p_full[x][b]);
     }
     // ---- epilogue: O / l and the log2-LSE, straight from the resident accumulator
-    mbar_wait(&o_full[x], (nkq - 1) & 1);
+    mbar_wait(&o_full[x][(nst - 1) & 1], ((nst - 1) >> 1) & 1);
     tc_fence_after();
     const size_t gr = (size_t)bh * p.Sq + grow;
     const float inv_l = 1.0f / l;
@@ -222,49 +228,60 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   } else {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc(1, 0, 0, 0, 0, 128, 128);        // f32 += f16 x f16, K-major
+      constexpr uint32_t idesc_qk = umma_idesc(1, 0, 0, 0, 0, 128, 64);         // f32 += f16 x f16, K-major, 64 keys
       constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // f32 += bf16 (TMEM) x bf16 (V MN-major)
-      auto issue_qk = [&](int x, int j) {                                        // S_x = Q_x K_j^T
-        const int s = j % STAGES;
-        const uint32_t q_addr = smem_u32(smem + L::off_q + x * L::kTile), k_addr = smem_u32(smem + L::off_k + s * L::kTile);
+      auto issue_qk = [&](int x, int t) {                                        // S_x[t&1] = Q_x K_step(t)^T
+        const int s = (t >> 1) % STAGES, h = t & 1;
+        const uint32_t q_addr = smem_u32(smem + L::off_q + x * L::kTile);
+        const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile) + h * (64 * 128);   // rows 64.. of every 64-column atom
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t o = (k >> 2) * kAtom2 + (k & 3) * 32;
-          umma_f16_ss(tbase + x * 128, umma_smem_desc(q_addr + o, 16, 1024, kSwz128), umma_smem_desc(k_addr + o, 16, 1024, kSwz128),
+          umma_f16_ss(tbase + x * 128 + h * 64, umma_smem_desc(q_addr + o, 16, 1024, kSwz128), umma_smem_desc(k_addr + o, 16, 1024, kSwz128),
                       idesc_qk, k > 0);
         }
-        umma_commit(&s_full[x]);
+        umma_commit(&s_full[x][h]);
       };
-      auto issue_pv = [&](int x, int j) {                                        // O_x += P_x V_j, P from TMEM
-        const int s = j % STAGES;
-        mbar_wait(&p_full[x], j & 1);
-        if (j > 0) mbar_wait(&o_ready[x], (j - 1) & 1);
+      auto issue_pv = [&](int x, int t) {                                        // O_x += P_x V_step(t), P from TMEM
+        const int s = (t >> 1) % STAGES, h = t & 1;
+        mbar_wait(&p_full[x][h], (t >> 1) & 1);
+        mbar_wait(&o_ready[x][h], (t >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile);
+        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile) + h * (4 * 2048);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16_ts(tbase + 256 + x * 128, tbase + x * 128 + k * 8, umma_smem_desc(v_addr + k * 2048, kAtom2, 1024, kSwz128),
-                      idesc_pv, (j > 0) || (k > 0));
-        umma_commit(&o_full[x]);
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(tbase + 256 + x * 128, tbase + x * 128 + h * 64 + k * 8, umma_smem_desc(v_addr + k * 2048, kAtom2, 1024, kSwz128),
+                      idesc_pv, (t > 0) || (k > 0));
+        umma_commit(&o_full[x][h]);
       };
+      const int nst[2] = {2 * nkx[0], 2 * nkx[1]};
       mbar_wait(&q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_qk(0, 0);
       issue_qk(1, 0);
+      issue_qk(0, 1);
+      issue_qk(1, 1);
       umma_commit(&k_empty[0]);
-      for (int j = 0; j < nk; ++j) {
-        const int s = j % STAGES;
+      for (int t = 0; t < 2 * nk; ++t) {
+        const int j = t >> 1, h = t & 1;
         const bool more = (j + 1 < nk);
-        mbar_wait(&v_full[s], (j / STAGES) & 1);
-        if (more) { mbar_wait(&k_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1); }
-        if (j < nkx[0]) {
-          issue_pv(0, j);
-          if (j + 1 < nkx[0]) issue_qk(0, j + 1);                // executes after P_A has been consumed (in-order pipe)
+        if (h == 0) {
+          mbar_wait(&v_full[j % STAGES], (j / STAGES) & 1);
+          if (more) mbar_wait(&k_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
+          tc_fence_after();
         }
-        issue_pv(1, j);
-        umma_commit(&v_empty[s]);
-        if (more) { issue_qk(1, j + 1); umma_commit(&k_empty[(j + 1) % STAGES]); }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (t < nst[x]) {
+            issue_pv(x, t);
+            if (t + 2 < nst[x]) issue_qk(x, t + 2);               // behind P V in the in-order pipe: P_x(t) is consumed first
+          }
+        }
+        if (h == 1) {
+          umma_commit(&v_empty[j % STAGES]);
+          if (more) umma_commit(&k_empty[(j + 1) % STAGES]);
+        }
       }
     }
   }
@@ -275,7 +292,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 template <int D, int STAGES>
 int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
-                     float qk_scale, cudaStream_t st) {
+                     float qk_scale, float rescale_tau, cudaStream_t st) {
 
   using L = Bf16Fwd2Smem<D, STAGES>;
   CUtensorMap tq, tk, tv;
@@ -287,7 +304,7 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   Bf16Fwd2Params p;
-  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.qk_scale = qk_scale;
+  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.qk_scale = qk_scale; p.rescale_tau = rescale_tau;
   auto kern = bf16_fwd2_kernel<D, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
@@ -296,7 +313,7 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   return qa_check_launch("qa_bf16_fwd(2 query tiles)");
 }
 
-template int launch_bf16_fwd2<128, 2>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
-template int launch_bf16_fwd2<64, 3>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, cudaStream_t);
+template int launch_bf16_fwd2<128, 2>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, float, cudaStream_t);
+template int launch_bf16_fwd2<64, 3>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, float, cudaStream_t);
 
 }  // namespace qa

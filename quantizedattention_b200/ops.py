@@ -184,8 +184,18 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
     return cast_f32(dq_ws, torch.float16), dk, dv
 
 
-def bf16_fwd(q, k, v, causal: bool, nsplit: int = 0):
-    """Bias-corrected bf16 flash attention forward (qa_bf16_fwd).  q,k fp16, v bf16 [B,H,S,D] ->
+def bf16_fwd_key_step(Sq: int, nsplit: int = 0) -> int:
+    """Keys per online-softmax step of the kernel qa_bf16_fwd dispatches to: the running maximum (and its bias
+    correction) advances once per step, so an oracle comparison at rounding level must use the same `tile_k`.
+    The reference's own default is 32 (attention_bf16.py:139); the choice is mathematically neutral."""
+    return 64 if (nsplit in (0, 3) and Sq % 256 == 0) else 128
+
+
+BF16_RESCALE_TAU = 8.0      # default lazy-rescale threshold of qa_bf16_fwd (log2 units); 0 = the reference's step-by-step maximum
+
+
+def bf16_fwd(q, k, v, causal: bool, nsplit: int = 0, rescale_tau: float | None = None):
+    """Bias-corrected bf16 flash attention forward (qa_bf16_fwd / qa_bf16_fwd_ex).  q,k fp16, v bf16 [B,H,S,D] ->
     (O fp32 [B,H,Sq,D], lse fp32 [B*H,Sq])."""
     _need_cuda(q, k, v)
     B, H, Sq, D = q.shape
@@ -195,8 +205,13 @@ def bf16_fwd(q, k, v, causal: bool, nsplit: int = 0):
     lse = torch.empty((B * H, Sq), dtype=torch.float32, device=q.device)
     L = _lib.lib()
     with torch.cuda.device(q.device), _timed("bf16_fwd"):
-        _lib.check(L.qa_bf16_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
-                                 1 if causal else 0, nsplit, _lib.cur_stream()), "qa_bf16_fwd")
+        if rescale_tau is None:
+            rc = L.qa_bf16_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
+                               1 if causal else 0, nsplit, _lib.cur_stream())
+        else:
+            rc = L.qa_bf16_fwd_ex(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
+                                  1 if causal else 0, nsplit, float(rescale_tau), _lib.cur_stream())
+        _lib.check(rc, "qa_bf16_fwd")
     return O, lse
 
 

@@ -39,6 +39,8 @@ def test_argument_validation_needs_no_gpu():
     assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, z) == -1  # Bkv in {32,64,128}
     assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, z) == -1          # Bq = Bkv = 128
     assert L.qa_bf16_fwd(*([z] * 5), 1, 100, 128, 128, 0, 1, z) == -1         # S % 128
+    assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, -1.0, z) == -1  # rescale_tau outside [0, 16]
+    assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, 32.0, z) == -1
     assert L.qa_jvp_fwd(*([z] * 9), 1, 128, 128, 96, 1, z) == -1              # D in {64,128}
 
 

@@ -10,20 +10,21 @@ def _stats(a, b):
     return (a - b).abs().max().item(), ((a - b) ** 2).mean().item()
 
 
+@pytest.mark.parametrize("tau", [0.0, 8.0])
 @pytest.mark.parametrize("nsplit", [1, 2, 3])
 @pytest.mark.parametrize("causal", [False, True])
-@pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128), (1, 2, 1024, 128)])
-def test_bf16_fwd_matches_oracle(shape, causal, nsplit):
+@pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128), (1, 2, 1024, 128), (1, 1, 2048, 64)])
+def test_bf16_fwd_matches_oracle(shape, causal, nsplit, tau):
     from oracle import bf16_ref
     from oracle.baseline import baseline_lse_log2, baseline_pytorch_attention
     from quantizedattention_b200 import ops
     g = torch.Generator().manual_seed(3000 + shape[2] + shape[3] + causal)
     q, k, v = [torch.randn(shape, generator=g) for _ in range(3)]
     q, k, v = q.half(), k.half(), v.bfloat16()
-    O, lse = ops.bf16_fwd(q.cuda(), k.cuda(), v.cuda(), causal, nsplit=nsplit)
+    O, lse = ops.bf16_fwd(q.cuda(), k.cuda(), v.cuda(), causal, nsplit=nsplit, rescale_tau=tau)
     torch.cuda.synchronize()
     assert O.dtype == torch.float32 and lse.shape == (shape[0] * shape[1], shape[2])
-    Or, lser = bf16_ref.bf16_fwd(q, k, v, causal, tile_k=128, mode="contract")
+    Or, lser = bf16_ref.bf16_fwd(q, k, v, causal, tile_k=ops.bf16_fwd_key_step(shape[2], nsplit), mode="contract", lazy_tau=tau)
     mx, mse = _stats(O.cpu(), Or)
     assert mx < 2.5e-2 and mse < 5e-6, (mx, mse)             # bf16 P rounding class: reference yardstick max-abs 2e-2, MSE 3e-6
     assert (lse.cpu() - lser).abs().max() < 2e-2
@@ -51,7 +52,7 @@ def test_bf16_fwd_stress_duplicate_keys():
     O, _ = ops.bf16_fwd(q.cuda(), k.cuda(), v.cuda(), False)
     base = baseline_pytorch_attention(q.float(), k.float(), v.float(), 64, False)
     assert torch.isfinite(O).all()
-    Or, _ = bf16_ref.bf16_fwd(q, k, v, False, tile_k=128, mode="contract")
+    Or, _ = bf16_ref.bf16_fwd(q, k, v, False, tile_k=ops.bf16_fwd_key_step(256), mode="contract", lazy_tau=ops.BF16_RESCALE_TAU)
     assert (O.cpu() - Or).abs().max() < 2.5e-2               # same algorithm: only MMA summation order differs
     assert (O.cpu() - base).abs().max() < 1e-1               # bf16 logits at |s| ~ 4..8: the oracle itself is 6e-2 off
 

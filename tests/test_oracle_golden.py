@@ -116,3 +116,22 @@ def test_int8_contract_bwd_close_to_autograd():
     for a, b in zip(gr, (qf, kf, vf)):
         cos = torch.nn.functional.cosine_similarity(a.float().flatten(), b.grad.flatten(), dim=0)
         assert cos > 0.985
+
+
+def test_bf16_contract_lazy_rescale_is_neutral():
+    """The kernel's lazy rescale (qa_bf16_fwd_ex rescale_tau) changes only which running maximum the bf16 roundings are
+    taken against: O and lse stay inside the reference's own yardstick against fp32 math for tau = 0 and tau = 8."""
+    from oracle import bf16_ref
+    from oracle.baseline import baseline_lse_log2, baseline_pytorch_attention
+    g = torch.Generator().manual_seed(77)
+    q, k, v = [torch.randn(1, 2, 512, 64, generator=g) for _ in range(3)]
+    q, k, v = q.half(), k.half(), v.bfloat16()
+    base = baseline_pytorch_attention(q.float(), k.float(), v.float(), 64, False)
+    lb = baseline_lse_log2(q, k, False)
+    outs = {}
+    for tau in (0.0, 8.0):
+        O, lse = bf16_ref.bf16_fwd(q, k, v, False, tile_k=64, mode="contract", lazy_tau=tau)
+        outs[tau] = O
+        assert (O - base).abs().max() < 3e-2 and ((O - base) ** 2).mean() < 5e-6
+        assert (lse - lb.reshape(lse.shape)).abs().max() < 2e-2
+    assert (outs[0.0] - outs[8.0]).abs().max() < 3e-2

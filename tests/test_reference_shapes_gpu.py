@@ -102,7 +102,7 @@ def test_cross_attention_lengths_forward():
     q = torch.randn(1, 2, 256, 128, generator=g)
     k, v = [torch.randn(1, 2, 512, 128, generator=g) for _ in range(2)]
     O, lse = ops.bf16_fwd(q.half().cuda(), k.half().cuda(), v.bfloat16().cuda(), False)
-    Or, _ = bf16_ref.bf16_fwd(q.half(), k.half(), v.bfloat16(), False, tile_k=128, mode="contract")
+    Or, _ = bf16_ref.bf16_fwd(q.half(), k.half(), v.bfloat16(), False, tile_k=ops.bf16_fwd_key_step(q.shape[2]), mode="contract", lazy_tau=ops.BF16_RESCALE_TAU)
     assert (O.cpu() - Or).abs().max() < 2.5e-2
     qi, sq = ops.quant_block(q.half().cuda(), 128)
     ki, sk = ops.quant_block(k.half().cuda(), 128)
