@@ -10,8 +10,9 @@ BASELINE.json configs[2] (B=8, H=32, S=8192, D=128, non-causal), the configurati
 One "step" = one forward + backward pass of `sage_attention_3_int8` over one batch of synthetic fp16 q/k/v/dO:
 K-mean, 4 block quantisations, fused int8 forward, delta pre-pass, fused int8 backward, dQ cast.
 value  : whole-job TOPS (4+10)*B*H*S^2*D ops per step per GPU, inputs resident in HBM.
-e2e    : same metric through the public API with pinned HOST buffers, H2D of q/k/v/dO and D2H of O/dq/dk/dv
-         inside the timed region.
+e2e    : same metric through the public host-staged API (quantizedattention_b200.host_pipeline) with pinned HOST
+         buffers: H2D of q/k/v/dO and D2H of O/dq/dk/dv inside the timed region, pipelined over head chunks on three
+         CUDA streams.
 Multi-GPU: batch x head sharding, no collective on the data path; every rank runs the full per-GPU workload
 (weak scaling), time = max over ranks.
 """
@@ -203,13 +204,11 @@ def main():
     if not args.no_e2e:
         outs_host = [torch.empty(B, H, S, D, dtype=torch.float16).pin_memory() for _ in range(4)]
 
-        def step_e2e():
-            dq_, dk_, dv_, ddo = [t.to(dev, non_blocking=True) for t in host]
-            qr, kr, vr = dq_.requires_grad_(), dk_.requires_grad_(), dv_.requires_grad_()
-            O = A.sage_attention_3_int8(qr, kr, vr)
-            O.backward(ddo)
-            for dst, src in zip(outs_host, (O.detach(), qr.grad, kr.grad, vr.grad)):
-                dst.copy_(src, non_blocking=True)
+        from quantizedattention_b200.host_pipeline import HostStagedSageAttention
+        pipe = HostStagedSageAttention(dev, heads_per_chunk=16, slots=4)
+
+        def step_e2e():                                             # H2D / forward+backward / D2H pipelined over head chunks
+            pipe(host[0], host[1], host[2], host[3], out=outs_host)
 
         step_e2e()
         barrier()

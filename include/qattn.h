@@ -103,6 +103,8 @@ int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
 int qa_debug_set_int8_fwd_timeline(void* buf);
 /* TMEM -> register read bandwidth (tcgen05.ld.32x32b.x32 streamed by every warp): measured ceiling of the drains */
 int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream);
+/* shape: 0 = 32x32b.x32, 1 = 16x256b.x8, 2 = 16x128b.x16, 3 = 16x64b.x32; depth = loads in flight per warp (1, 2) */
+int qa_probe_tmem_bw_ex(void* sink, int blocks, int threads, int iters, int shape, int depth, void* stream);
 int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const unsigned long long* dims,
                  const unsigned long long* strides_bytes, const unsigned* box, int swizzle, const int* coords, void* out,
                  void* stream);

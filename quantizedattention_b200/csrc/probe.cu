@@ -154,11 +154,31 @@ extern "C" int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const un
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// TMEM -> register read bandwidth probe: every warp streams tcgen05.ld.32x32b.x32 over its lane quadrant.
+// TMEM -> register read bandwidth probe: every warp streams tcgen05.ld over its lane quadrant (4 KiB per load, 32
+// registers per thread) in one of the instruction shapes, with `DEPTH` loads in flight before the wait.
 // Gives the measured ceiling for kernels whose accumulators must be drained from TMEM every tile.
 // ---------------------------------------------------------------------------------------------------------
 namespace qa {
-__global__ void __launch_bounds__(1024, 1) probe_tmem_bw_kernel(uint32_t* sink, int iters) {
+#define QA_LD32(NAME, MNEMONIC)                                                                                        \
+  __device__ __forceinline__ void NAME(uint32_t taddr, uint32_t (&r)[32]) {                                            \
+    asm volatile("tcgen05.ld.sync.aligned." MNEMONIC ".b32 "                                                           \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
+                 "%27,%28,%29,%30,%31}, [%32];"                                                                        \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),            \
+                   "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),          \
+                   "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),          \
+                   "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                               \
+                 : "r"(taddr));                                                                                        \
+  }
+QA_LD32(ld_32x32b, "32x32b.x32")
+QA_LD32(ld_16x256b, "16x256b.x8")
+QA_LD32(ld_16x128b, "16x128b.x16")
+QA_LD32(ld_16x64b, "16x64b.x32")
+#undef QA_LD32
+
+template <int SHAPE, int DEPTH>
+__global__ void __launch_bounds__(DEPTH == 1 ? 1024 : 512, 1) probe_tmem_bw_kernel(uint32_t* sink, int iters) {
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
@@ -169,12 +189,21 @@ __global__ void __launch_bounds__(1024, 1) probe_tmem_bw_kernel(uint32_t* sink, 
   uint32_t acc = 0;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + ((warp >> 2) * 128 + c * 32) % 512, r);
+    for (int c = 0; c < 4; c += DEPTH) {
+      uint32_t r[DEPTH][32];
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const uint32_t a = lane_addr + ((warp >> 2) * 128 + (c + d) * 64) % 448;   // 16-lane shapes span 64 columns
+        if (SHAPE == 0) ld_32x32b(a, r[d]);
+        else if (SHAPE == 1) ld_16x256b(a, r[d]);      // 16 lanes x 64 columns
+        else if (SHAPE == 2) ld_16x128b(a, r[d]);
+        else ld_16x64b(a, r[d]);
+      }
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc ^= r[i];
+      for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc ^= r[d][i];
     }
   }
   if (acc == 0x12345678u) sink[threadIdx.x] = acc;
@@ -185,8 +214,21 @@ __global__ void __launch_bounds__(1024, 1) probe_tmem_bw_kernel(uint32_t* sink, 
 }  // namespace qa
 
 // Launches `blocks` CTAs of `threads` threads; each warp issues iters * 4 loads of 4 KiB.
-extern "C" int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream) {
+// shape: 0 = 32x32b.x32, 1 = 16x256b.x8, 2 = 16x128b.x16, 3 = 16x64b.x32; depth: 1 or 2 loads in flight per warp.
+extern "C" int qa_probe_tmem_bw_ex(void* sink, int blocks, int threads, int iters, int shape, int depth, void* stream) {
   if (threads % 128 || threads > 1024) return qa_fail(QA_ERR_SHAPE, "qa_probe_tmem_bw: threads must be a multiple of 128");
-  qa::probe_tmem_bw_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((uint32_t*)sink, iters);
+  if (shape < 0 || shape > 3 || (depth != 1 && depth != 2) || (depth == 2 && threads > 512))
+    return qa_fail(QA_ERR_SHAPE, "qa_probe_tmem_bw: bad shape/depth");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* s = (uint32_t*)sink;
+#define QA_GO(S, DP) qa::probe_tmem_bw_kernel<S, DP><<<blocks, threads, 0, st>>>(s, iters)
+#define QA_SH(S) (depth == 1 ? QA_GO(S, 1) : QA_GO(S, 2))
+  if (shape == 0) QA_SH(0); else if (shape == 1) QA_SH(1); else if (shape == 2) QA_SH(2); else QA_SH(3);
+#undef QA_SH
+#undef QA_GO
   return qa_check_launch("qa_probe_tmem_bw");
+}
+
+extern "C" int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream) {
+  return qa_probe_tmem_bw_ex(sink, blocks, threads, iters, 0, 1, stream);
 }

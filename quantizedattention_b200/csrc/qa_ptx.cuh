@@ -199,6 +199,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// 64 consecutive columns as two x32 loads in flight (no wait).  tcgen05.wait::ld is the expensive part of a TMEM read
+// (tools/tmem_bw_probe.py: one load per wait ~100 B/clk/SM, two loads per wait 350-450 B/clk/SM), so kernels batch
+// as many loads as their registers allow in front of a single wait.
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  tmem_ld32(taddr, *reinterpret_cast<uint32_t (*)[32]>(&r[0]));
+  tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t (*)[32]>(&r[32]));
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])

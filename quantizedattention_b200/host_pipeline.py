@@ -1,0 +1,150 @@
+"""Host-staged int8 attention: q, k, v (and dO) live in pinned HOST memory; results come back to pinned host memory.
+
+The batch x head axis is the path's natural shard (every (b, h) is an independent attention problem, the
+K token mean and the quantisation blocks never straddle heads), so a head chunk is a complete unit of work.  Three CUDA
+streams run the chunks as a pipeline,
+
+    copy-in stream  :  H2D(q,k,v,dO of chunk i+1)
+    compute stream  :  sage_attention_3_int8 forward + backward of chunk i   (attention_int8.py:434-451, :20-95)
+    copy-out stream :  D2H(O,dq,dk,dv of chunk i-1)
+
+with a few device staging slots for the inputs and CUDA events between the stages.  PCIe is full duplex, so the whole
+job costs about max(H2D, compute, D2H) instead of their sum.  This is the call `bench.py` times as `e2e`.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import attention_int8 as A
+
+
+class HostStagedSageAttention:
+    """Reusable pipeline object (device staging buffers and streams are allocated once per shape)."""
+
+    def __init__(self, device=None, heads_per_chunk: int = 16, slots: int = 4):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.heads_per_chunk = heads_per_chunk
+        self.slots = max(2, slots)                                 # device staging slots for the inputs
+        self.trace = None                                          # set to [] to collect (stage, chunk, start, end) timing events
+        self._key = None
+
+    def _span(self, stage, chunk, stream):
+        """When tracing, record the start of a (stage, chunk) span on `stream` and return its end event."""
+        if self.trace is None:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        self.trace.append((stage, chunk, a, b))
+        return b
+
+    def _setup(self, BH, S, D, with_grad):
+        hc = min(self.heads_per_chunk, BH)
+        while BH % hc:
+            hc -= 1
+        key = (BH, S, D, hc, with_grad, self.slots)
+        if key == self._key:
+            return
+        dev = self.device
+        n_in = 4 if with_grad else 3
+        self.hc = hc
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.inbuf = [[torch.empty((1, hc, S, D), dtype=torch.float16, device=dev) for _ in range(n_in)] for _ in range(self.slots)]
+        self._key = key
+
+    @staticmethod
+    def _check_host(*ts):
+        for t in ts:
+            if t is None:
+                continue
+            if t.is_cuda or t.dtype != torch.float16 or not t.is_contiguous():
+                raise TypeError("host-staged attention takes contiguous fp16 HOST tensors [B,H,S,D]")
+            if not t.is_pinned():
+                raise RuntimeError("host tensors must be pinned (tensor.pin_memory()): pageable memory cannot overlap copies")
+
+    def __call__(self, q, k, v, dO=None, out=None):
+        """q, k, v (and optionally dO): pinned fp16 host tensors [B,H,S,D].
+        Returns O (and dq, dk, dv when dO is given) as pinned fp16 host tensors; `out` supplies them if given."""
+        self._check_host(q, k, v, dO)
+        B, H, S, D = q.shape
+        if k.shape != q.shape or v.shape != q.shape or (dO is not None and dO.shape != q.shape):
+            raise ValueError("q, k, v, dO must share one [B,H,S,D] shape (self-attention)")
+        BH = B * H
+        with_grad = dO is not None
+        self._setup(BH, S, D, with_grad)
+        hc, dev = self.hc, self.device
+        n_out = 4 if with_grad else 1
+        if out is None:
+            out = [torch.empty((B, H, S, D), dtype=torch.float16).pin_memory() for _ in range(n_out)]
+        self._check_host(*out)
+        srcs = [t.view(BH, S, D) for t in ((q, k, v, dO) if with_grad else (q, k, v))]
+        dsts = [t.view(BH, S, D) for t in out]
+        n = BH // hc
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_event(start)                                    # the pipeline starts after the caller's prior work
+        ev_in, ev_cmp, ev_out = [None] * n, [None] * n, [None] * n
+        results = [None] * n
+        for i in range(n + 2):
+            if i < n:                                              # ---- stage 1: H2D of chunk i
+                slot = i % self.slots
+                with torch.cuda.stream(self.s_in):
+                    if i >= self.slots:
+                        self.s_in.wait_event(ev_cmp[i - self.slots])   # the slot's previous reader has finished
+                    sp = self._span("h2d", i, self.s_in)
+                    for dst, src in zip(self.inbuf[slot], srcs):
+                        dst.view(hc, S, D).copy_(src[i * hc:(i + 1) * hc], non_blocking=True)
+                    if sp is not None:
+                        sp.record(self.s_in)
+                    ev_in[i] = torch.cuda.Event()
+                    ev_in[i].record(self.s_in)
+            j = i - 1
+            if 0 <= j < n:                                         # ---- stage 2: forward (+ backward) of chunk j
+                slot = j % self.slots
+                with torch.cuda.stream(self.s_cmp):
+                    self.s_cmp.wait_event(ev_in[j])
+                    sp = self._span("compute", j, self.s_cmp)
+                    bufs = self.inbuf[slot]
+                    if with_grad:
+                        qr, kr, vr = (t.detach().requires_grad_() for t in bufs[:3])
+                        O = A.sage_attention_3_int8(qr, kr, vr)
+                        O.backward(bufs[3])
+                        results[j] = (O.detach(), qr.grad, kr.grad, vr.grad)
+                    else:
+                        with torch.no_grad():
+                            results[j] = (A.sage_attention_3_int8(*bufs[:3]),)
+                    if sp is not None:
+                        sp.record(self.s_cmp)
+                    ev_cmp[j] = torch.cuda.Event()
+                    ev_cmp[j].record(self.s_cmp)
+            m = i - 2
+            if 0 <= m < n:                                         # ---- stage 3: D2H of chunk m
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_cmp[m])
+                    sp = self._span("d2h", m, self.s_out)
+                    for dst, src in zip(dsts, results[m]):
+                        src.record_stream(self.s_out)              # allocated on the compute stream, read here
+                        dst[m * hc:(m + 1) * hc].copy_(src.view(hc, S, D), non_blocking=True)
+                    if sp is not None:
+                        sp.record(self.s_out)
+                    ev_out[m] = torch.cuda.Event()
+                    ev_out[m].record(self.s_out)
+                results[m] = None
+        cur.wait_event(ev_out[n - 1])                              # results are complete for work queued after the call
+        cur.wait_event(ev_cmp[n - 1])
+        return out[0] if not with_grad else tuple(out)
+
+
+_DEFAULT = {}
+
+
+def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 16, device=None):
+    """Functional form of HostStagedSageAttention (one cached pipeline per device and chunk size).
+    Returns O, or (O, dq, dk, dv) when dO is given; the copies are asynchronous on the current stream's timeline:
+    synchronise (or record an event) before reading the host results."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (dev, heads_per_chunk)
+    if key not in _DEFAULT:
+        _DEFAULT[key] = HostStagedSageAttention(dev, heads_per_chunk)
+    return _DEFAULT[key](q, k, v, dO, out)
