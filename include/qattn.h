@@ -70,11 +70,15 @@ int qa_bwd_delta(const void* dO, const void* O, void* delta_f32, void* dO_bf16, 
 int qa_cast_f32(const void* in_f32, void* out, long long n, int out_dtype, void* stream);
 
 /* ---- int8 backward: helion_atten_int8_hl_dot_bwd, attention_int8.py:268-432 under the 8-LEDGER contract ----
- * Bq = Bkv = 128.  dq_ws: zero-initialised fp32 [BH*S, D] accumulator (cast with qa_cast_f32); dk, dv fp16. */
+ * Bq = Bkv = 128.  dq_ws: zero-initialised fp32 [BH*S, D] accumulator; rowsum_ws: zero-initialised fp32 [BH*S]
+ * accumulator of rowsum(dS) for the K-smoothing term (NULL when K was not smoothed); dk, dv fp16.
+ * qa_int8_bwd_finalize turns the two workspaces into dq = fp16(dq_ws + sm_scale * rowsum * k_mean[b,h]). */
 int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq_fp16,
                 const void* sk_fp16, const void* sv_fp16, const void* s_do_fp16, const void* lse_f32,
-                const void* delta_f32, const void* k_mean_f16, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
+                const void* delta_f32, void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
                 int D, int Bq, int Bkv, void* stream);
+int qa_int8_bwd_finalize(const void* dq_ws_f32, const void* rowsum_ws_f32, const void* k_mean_f16, void* dq_f16, int BH,
+                         int S, int D, void* stream);
 
 /* ---- bf16 path: helion_atten_bf16_fwd_training (attention_bf16.py:111-296), helion_flash_atten_2_algo_4_bwd
  * (attention_bf16.py:309-448) ---- */
@@ -101,6 +105,7 @@ int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
                  int kind, int n_mma, int n_cols, int a_in_tmem, int a_tmem_cols, int a_tmem_kstep_cols, void* stream);
 /* Development aid: per-k-tile SM-clock stamps of CTA (0,0) of the next qa_int8_fwd launches ([64][16] int64); NULL = off */
 int qa_debug_set_int8_fwd_timeline(void* buf);
+int qa_debug_set_int8_bwd_timeline(void* buf_i64_64x2x16);   /* same for qa_int8_bwd: leader warp and warp 5, per q-tile */
 /* TMEM -> register read bandwidth (tcgen05.ld.32x32b.x32 streamed by every warp): measured ceiling of the drains */
 int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream);
 /* shape: 0 = 32x32b.x32, 1 = 16x256b.x8, 2 = 16x128b.x16, 3 = 16x64b.x32; depth = loads in flight per warp (1, 2) */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "qa_int8_fwd_state": (c_int, [c_void_p] * 15 + [c_int] * 7 + [c_void_p]),
     "qa_int8_fwd": (c_int, [c_void_p] * 12 + [c_int] * 7 + [c_void_p]),
     "qa_int8_bwd": (c_int, [c_void_p] * 14 + [c_int] * 5 + [c_void_p]),
+    "qa_int8_bwd_finalize": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "qa_bwd_delta": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]),
     "qa_cast_f32": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "qa_bf16_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
@@ -30,6 +31,7 @@ SIGNATURES = {
     "qa_jvp_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "qa_bf16_bwd": (c_int, [c_void_p] * 10 + [c_int] * 4 + [c_void_p]),
     "qa_debug_set_int8_fwd_timeline": (c_int, [c_void_p]),
+    "qa_debug_set_int8_bwd_timeline": (c_int, [c_void_p]),
     "qa_probe_tmem_bw": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "qa_probe_tmem_bw_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_probe_mma": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_uint] + [c_int] * 6 + [c_void_p]),

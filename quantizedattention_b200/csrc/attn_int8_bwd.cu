@@ -35,10 +35,11 @@ struct Int8BwdParams {
   const __half *sq, *sk, *sv, *s_do;   // per-128-block fp16 scales
   const float* lse;                    // [BH*S] fp32 log2-sum-exp2
   const float* delta;                  // [BH*S]
-  const __half* k_mean;                // [BH, D] fp16 (may be null)
+  float* rowsum;                       // [BH*S] fp32, zero-initialised: sum over k-tiles of rowsum(dS) (null without K smoothing)
   __half *dk, *dv;                     // [BH*S, D] fp16
   int S;
   float sm_scale, qk_scale;
+  long long* dbg;                      // optional timeline buffer [tile][2 warps][16] of SM clock stamps (tools/timeline_bwd.py)
 };
 
 // 256 threads: thread = (row, column half).  Thread 0 additionally issues TMA / tcgen05.mma at the two barriers per
@@ -46,6 +47,12 @@ struct Int8BwdParams {
 // pass 1 of tile t+1 runs while the tensor core computes dV_t/dK_t; dQ_t is issued one barrier later into the TMEM
 // columns freed by draining dV_t and overlaps the quantise pass of tile t+1.
 //   TMEM: [0,128) S   [128,256) dP   [256,384) dV partial, then dQ partial   [384,512) dK partial
+#define QA_TLB(slot)                                                                                          \
+  do {                                                                                                        \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 5) && t < 64) \
+      p.dbg[(t * 2 + (warp != 0)) * 16 + (slot)] = clock64();                                                 \
+  } while (0)
+
 template <int D, int NG>
 __global__ void __launch_bounds__(128 * NG, 1)
 int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -64,7 +71,6 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   __shared__ float red_p[2][NW], red_ds[2][NW];
   __shared__ float rowsum_ds[2][NG][128];
-  __shared__ __align__(16) float kmean_s[D];                    // sm_scale * k_mean[d]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool leader = (tid == 0);
@@ -78,7 +84,6 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_s);
-  if (tid < D) kmean_s[tid] = p.k_mean ? __half2float(p.k_mean[(size_t)bh * D + tid]) * p.sm_scale : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -95,13 +100,17 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_load_2d(smem + L::off_q + st * L::kTile, &tm_q, &qdo_full[st], 0, (int)head_row0 + tile * 128);
     tma_load_2d(smem + L::off_do + st * L::kTile, &tm_do, &qdo_full[st], 0, (int)head_row0 + tile * 128);
   };
-  auto issue_s_dp = [&](int st) {                                  // S = Q K^T, dP = dO V^T
-    const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
+  auto issue_s = [&](int st) {                                     // S = Q K^T (issued one barrier ahead of dP: the S columns
+    const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);          // are free as soon as pass 1 is over)
 #pragma unroll
-    for (int k = 0; k < D / 32; ++k) {
+    for (int k = 0; k < D / 32; ++k)
       umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, k > 0);
+  };
+  auto issue_dp = [&](int st) {                                    // dP = dO V^T; the commit also covers the earlier S MMAs
+    const uint32_t a_do = smem_u32(smem + L::off_do + st * L::kTile);
+#pragma unroll
+    for (int k = 0; k < D / 32; ++k)
       umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, k > 0);
-    }
     umma_commit(&sd_full);
   };
   auto issue_dv_dk = [&](int st, int dsb) {                        // dV = P^T dO, dK = dS^T Q (contraction over query rows)
@@ -129,7 +138,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     load_qdo(0, 0);
     mbar_wait(&kv_full, 0);
     mbar_wait(&qdo_full[0], 0);
-    issue_s_dp(0);
+    issue_s(0);
+    issue_dp(0);
   }
 
   const int half = warp >> 2;                                   // column group handled by this thread
@@ -137,11 +147,10 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
   const float sk_f = __half2float(p.sk[head_row0 / 128 + j]);
   const float sv_f = __half2float(p.sv[head_row0 / 128 + j]);
-  const float* kmean = kmean_s + half * DH;
   float2 dv_acc[DH / 2], dk_acc[DH / 2];                        // fp32x2: FFMA2 / FMUL2 / FADD2 halve the issue slots
 #pragma unroll
   for (int d = 0; d < DH / 2; ++d) { dv_acc[d] = make_float2(0.f, 0.f); dk_acc[d] = make_float2(0.f, 0.f); }
-  float c_dv_prev = 0.f, c_dk_prev = 0.f, c_dq_prev = 0.f, rs_prev = 0.f;
+  float c_dv_prev = 0.f, c_dk_prev = 0.f, c_dq_prev = 0.f;
 
   auto drain_dv_dk = [&](float c_dv, float c_dk) {
 #pragma unroll
@@ -159,7 +168,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
   };
-  auto drain_dq = [&](float c_dq, float rs_row) {                 // dQ partial -> fp32 staging (swizzled 32-float atoms)
+  auto drain_dq = [&](float c_dq) {                 // dQ partial -> fp32 staging (swizzled 32-float atoms)
 #pragma unroll
     for (int ch = 0; ch < DH / 16; ++ch) {
       uint32_t r[16];
@@ -169,10 +178,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint8_t* atom = smem + L::off_dq + (col >> 5) * (128 * 128);
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
-        const float2 k01 = *reinterpret_cast<const float2*>(kmean + ch * 16 + c), k23 = *reinterpret_cast<const float2*>(kmean + ch * 16 + c + 2);
-        const float2 rs2 = make_float2(rs_row, rs_row), cq2 = make_float2(c_dq, c_dq);
-        const float2 o01 = __ffma2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2, __fmul2_rn(rs2, k01));
-        const float2 o23 = __ffma2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2, __fmul2_rn(rs2, k23));
+        const float2 cq2 = make_float2(c_dq, c_dq);
+        const float2 o01 = __fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2);
+        const float2 o23 = __fmul2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2);
         *reinterpret_cast<float4*>(atom + swz128(row, ((col & 31) + c) * 4)) = make_float4(o01.x, o01.y, o23.x, o23.y);
       }
     }
@@ -184,6 +192,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_store_commit();
   };
 
+  constexpr float kPs = 1.0f / 1024.0f;                          // P is carried between the passes as fp16(1024 * P)
   for (int t = 0; t < nq; ++t) {
     const uint32_t ph = t & 1;
     const size_t qrow = head_row0 + (size_t)t * 128 + row;
@@ -193,13 +202,22 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float dlt = p.delta[qrow];
     const float c_s = sq_f * sk_f * p.qk_scale;
     const float c_dp = sdo_f * sv_f;
+    QA_TLB(0);
+    if (leader && t + 1 < nq) {                                    // next Q / dO tile: its stage was last read by dV/dK of t-1
+      if (t > 0) mbar_wait(&parts_full, (t - 1) & 1);
+      load_qdo(t + 1, (t + 1) & 1);
+    }
     mbar_wait(&sd_full, ph);
     tc_fence_after();
-    // ---- pass 1: fp16 logits (kept packed), tile amax of P and |dS|, row sum of dS
-    __half2 sh[CW / 2];
+    QA_TLB(1);
+    // ---- pass 1: P = exp2(fp16 logit - lse), kept as packed fp16 of 1024 * P (11-bit mantissa, no subnormals down to
+    //      P = 6e-8) so that pass 2 needs no second exp2; tile amax of P and |dS|, row sum of dS
+    __half2 pk[CW / 2];
     float amax_p = 0.f, amax_ds = 0.f;
+    __half2 amax_ph = __float2half2_rn(0.f);
     float2 rs2acc = make_float2(0.f, 0.f);
-    const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(-lse, -lse), cdp2 = make_float2(c_dp, c_dp), ndlt2 = make_float2(-dlt, -dlt);
+    const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(10.0f - lse, 10.0f - lse);
+    const float2 cdp2 = make_float2(c_dp * kPs, c_dp * kPs), ndlt2 = make_float2(-dlt * kPs, -dlt * kPs);
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
       uint32_t r[16], r2[16];
@@ -209,15 +227,17 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
         const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cs2));
-        sh[ch * 8 + c / 2] = h;
         const float2 e = __fadd2_rn(__half22float2(h), nlse2);
-        const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-        amax_p = fmaxf(amax_p, fmaxf(pp.x, pp.y));
+        const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));               // 1024 * P
+        const __half2 pr = __float22half2_rn(pp);
+        pk[ch * 8 + c / 2] = pr;
+        amax_ph = __hmax2(amax_ph, pr);
         const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdp2, ndlt2));
         amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d.x), fabsf(d.y)));
         rs2acc = __fadd2_rn(rs2acc, d);
       }
     }
+    amax_p = fmaxf(__low2float(amax_ph), __high2float(amax_ph));                       // of the rounded 1024 * P
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       amax_p = fmaxf(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, o));
@@ -225,19 +245,28 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     if (lane == 0) { red_p[ph][warp] = amax_p; red_ds[ph][warp] = amax_ds; }
     rowsum_ds[ph][half][row] = rs2acc.x + rs2acc.y;
+    QA_TLB(2);
     // ---- drain dV / dK of the previous tile (its MMAs ran while pass 1 executed)
     if (t > 0) {
       mbar_wait(&parts_full, (t - 1) & 1);
       tc_fence_after();
-      if (leader && t + 1 < nq) load_qdo(t + 1, (t + 1) & 1);      // that stage's last readers (dV/dK of t-1) are done
+      QA_TLB(3);
       drain_dv_dk(c_dv_prev, c_dk_prev);
-    } else if (leader && nq > 1) {
-      load_qdo(1, 1);
+      QA_TLB(4);
     }
     tc_fence_before();
     if (leader) tma_store_wait_read();                             // the dQ staging tile may be rewritten after this barrier
     named_bar_sync(1, NT);                                        // amax partials visible; dV/dK partial columns drained
-    if (leader && t > 0) { tc_fence_after(); issue_dq((t - 1) & 1); }
+    QA_TLB(5);
+    if (leader) {
+      tc_fence_after();
+      if (t > 0) issue_dq((t - 1) & 1);
+      if (t + 1 < nq) {                                            // S of the next tile: everybody is past pass 1
+        mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+        issue_s((t + 1) & 1);
+      }
+    }
+    QA_TLB(6);
     // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
     amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
 #pragma unroll
@@ -245,13 +274,16 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float rs_row = 0.f;                                                      // full-row sum of dS (query row = lane)
 #pragma unroll
     for (int g = 0; g < NG; ++g) rs_row += rowsum_ds[ph][g][row];
-    const float sP = amax_p * (1.0f / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
+    // K-smoothing term of dQ (LEDGER I-1): sm_scale * rowsum(dS) * k_mean is rank one per query row, so only the
+    // row sums are accumulated here (one fp32 reduction per row and tile); qa_int8_bwd_finalize applies k_mean once.
+    if (half == 0 && p.rowsum != nullptr) atomicAdd(p.rowsum + qrow, rs_row);
+    const float sP = amax_p * (kPs / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
     const float inv_p = amax_p > 0.f ? __fdividef(127.0f, amax_p) : 0.f;
     const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
     // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
     //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
     uint8_t* ds_tile = smem + L::off_ds + ph * (128 * 128);
-    const float2 cdpi2 = make_float2(c_dp * inv_ds, c_dp * inv_ds), ndlti2 = make_float2(-dlt * inv_ds, -dlt * inv_ds);
+    const float2 cdpi2 = make_float2(c_dp * kPs * inv_ds, c_dp * kPs * inv_ds), ndlti2 = make_float2(-dlt * kPs * inv_ds, -dlt * kPs * inv_ds);
     const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
@@ -265,9 +297,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 4; e += 2) {
           const int c = q4 * 4 + e;
-          const float2 e2 = __fadd2_rn(__half22float2(sh[ch * 8 + c / 2]), nlse2);
-          const float2 pp = make_float2(ex2_approx(e2.x), ex2_approx(e2.y));
-          // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS folded into the FFMA2 constants
+          const float2 pp = __half22float2(pk[ch * 8 + c / 2]);                  // 1024 * P from pass 1
+          // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS (and the 1/1024) folded into the FFMA2 constants
           const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
           const float2 pq = __ffma2_rz(pp, invp2, magic2);                      // P >= 0: low byte = trunc(P / sP)
           bp[e] = __float_as_uint(pq.x);
@@ -282,28 +313,30 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
       *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
     }
+    QA_TLB(7);
     // ---- drain dQ of the previous tile (its MMA ran while pass 2 executed)
     if (t > 0) {
       mbar_wait(&dq_full, (t - 1) & 1);
       tc_fence_after();
-      drain_dq(c_dq_prev, rs_prev);
+      QA_TLB(8);
+      drain_dq(c_dq_prev);
     }
+    QA_TLB(9);
     fence_proxy_async_smem();
     tc_fence_before();
     named_bar_sync(2, NT);                                        // P / dS tiles and the dQ staging tile are complete
+    QA_TLB(10);
     if (leader) {
       tc_fence_after();
       if (t > 0) reduce_dq(t - 1);
-      if (t + 1 < nq) {
-        mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
-        issue_s_dp((t + 1) & 1);
-      }
+      if (t + 1 < nq) issue_dp((t + 1) & 1);
+      QA_TLB(11);
       issue_dv_dk(t & 1, ph);
     }
+    QA_TLB(12);
     c_dv_prev = sdo_f * sP;
     c_dk_prev = sdS * sq_f * p.sm_scale;
     c_dq_prev = sdS * sk_f * p.sm_scale;
-    rs_prev = rs_row;
   }
   // ---- pipeline tail: last tile's dV / dK / dQ
   mbar_wait(&parts_full, (nq - 1) & 1);
@@ -315,7 +348,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (leader) { tc_fence_after(); issue_dq((nq - 1) & 1); }
   mbar_wait(&dq_full, (nq - 1) & 1);
   tc_fence_after();
-  drain_dq(c_dq_prev, rs_prev);
+  drain_dq(c_dq_prev);
   fence_proxy_async_smem();
   tc_fence_before();
   named_bar_sync(2, NT);
@@ -375,18 +408,26 @@ using namespace qa;
 
 // Backward over pre-quantised operands (Bq = Bkv = 128).  dq_ws: fp32 [BH*S, D] zero-initialised accumulation
 // workspace (cast to fp16 with qa_cast_f32 afterwards); dk, dv: fp16 [BH*S, D].
+static void* g_int8_bwd_dbg = nullptr;
+// Development aid (tools/timeline_bwd.py): CTA (0,0) of subsequent qa_int8_bwd launches records SM-clock stamps of the
+// leader warp and of warp 5 per q-tile into buf ([64 tiles][2][16] int64); NULL switches it off.  Not thread-safe.
+extern "C" int qa_debug_set_int8_bwd_timeline(void* buf) {
+  g_int8_bwd_dbg = buf;
+  return 0;
+}
+
 extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
                            const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
-                           const void* k_mean_f16, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
+                           void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
                            int Bq, int Bkv, void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: D must be 64 or 128");
   if (Bq != 128 || Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: Bq = Bkv = 128 required");
   if (S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S must be a multiple of 128");
   Int8BwdParams p;
   p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv; p.s_do = (const __half*)s_do;
-  p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32; p.k_mean = (const __half*)k_mean_f16;
+  p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32; p.rowsum = (float*)rowsum_ws_f32;
   p.dk = (__half*)dk_f16; p.dv = (__half*)dv_f16;
-  p.S = S;
+  p.S = S; p.dbg = (long long*)g_int8_bwd_dbg;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;

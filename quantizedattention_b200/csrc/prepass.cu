@@ -80,3 +80,51 @@ extern "C" int qa_cast_f32(const void* in_f32, void* out, long long n, int out_d
   else cast_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float4*)in_f32, (__nv_bfloat16*)out, n4);
   return qa_check_launch("qa_cast_f32");
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// dQ epilogue of the int8 backward: dq = fp16(dq_ws + sm_scale * rowsum[row] * k_mean[head][col]).
+// The second term is the K-smoothing correction (LEDGER I-1); rowsum / k_mean may be null (no smoothing).
+// ---------------------------------------------------------------------------------------------------------
+namespace qa {
+template <int D>
+__global__ void __launch_bounds__(256) dq_finalize_kernel(const float4* __restrict__ ws, const float* __restrict__ rowsum,
+                                                          const __half* __restrict__ k_mean, __half* __restrict__ out,
+                                                          long long n_rows, int S, float sm_scale) {
+  constexpr int V = D / 4;                                          // float4 per row
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * V) return;
+  const long long row = i / V;
+  const int c = (int)(i % V) * 4;
+  float4 v = ws[i];
+  if (rowsum != nullptr) {
+    const float rs = rowsum[row] * sm_scale;
+    const __half2* km = reinterpret_cast<const __half2*>(k_mean + (row / S) * D + c);
+    const float2 k0 = __half22float2(km[0]), k1 = __half22float2(km[1]);
+    v.x = fmaf(rs, k0.x, v.x); v.y = fmaf(rs, k0.y, v.y); v.z = fmaf(rs, k1.x, v.z); v.w = fmaf(rs, k1.y, v.w);
+  }
+  __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(out + i * 4) = o;
+}
+}  // namespace qa
+
+extern "C" int qa_int8_bwd_finalize(const void* dq_ws_f32, const void* rowsum_ws_f32, const void* k_mean_f16, void* dq_f16,
+                                    int BH, int S, int D, void* stream) {
+  if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_finalize: D must be 64 or 128");
+  if ((rowsum_ws_f32 == nullptr) != (k_mean_f16 == nullptr))
+    return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_finalize: rowsum workspace and k_mean go together");
+  if (((uintptr_t)dq_ws_f32 & 15) || ((uintptr_t)dq_f16 & 7)) return qa_fail(QA_ERR_ALIGN, "qa_int8_bwd_finalize: alignment");
+  const long long n_rows = (long long)BH * S;
+  const long long n = n_rows * (D / 4);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  const float sm_scale = (float)(1.0 / sqrt((double)D));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128)
+    qa::dq_finalize_kernel<128><<<grid, 256, 0, st>>>((const float4*)dq_ws_f32, (const float*)rowsum_ws_f32,
+                                                      (const __half*)k_mean_f16, (__half*)dq_f16, n_rows, S, sm_scale);
+  else
+    qa::dq_finalize_kernel<64><<<grid, 256, 0, st>>>((const float4*)dq_ws_f32, (const float*)rowsum_ws_f32,
+                                                     (const __half*)k_mean_f16, (__half*)dq_f16, n_rows, S, sm_scale);
+  return qa_check_launch("qa_int8_bwd_finalize");
+}

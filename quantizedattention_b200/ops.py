@@ -173,15 +173,22 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
     _need_cuda(q_i8, k_i8, v_i8, do_i8)
     dev = q_i8.device
     dq_ws = torch.zeros((BH * S, D), dtype=torch.float32, device=dev)
+    rowsum_ws = torch.zeros((BH * S,), dtype=torch.float32, device=dev) if k_mean is not None else None
     dk = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
     dv = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    dq = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    if k_mean is not None:
+        k_mean = k_mean.contiguous()
     L = _lib.lib()
-    with torch.cuda.device(dev), _timed("int8_bwd"):
-        _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
-                                 _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(k_mean),
-                                 _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _lib.cur_stream()),
-                   "qa_int8_bwd")
-    return cast_f32(dq_ws, torch.float16), dk, dv
+    with torch.cuda.device(dev):
+        with _timed("int8_bwd"):
+            _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
+                                     _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(rowsum_ws),
+                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _lib.cur_stream()),
+                       "qa_int8_bwd")
+        _lib.check(L.qa_int8_bwd_finalize(_lib.ptr(dq_ws), _lib.ptr(rowsum_ws), _lib.ptr(k_mean), _lib.ptr(dq), BH, S, D,
+                                          _lib.cur_stream()), "qa_int8_bwd_finalize")
+    return dq, dk, dv
 
 
 def bf16_fwd_key_step(Sq: int, nsplit: int = 0) -> int:

@@ -32,5 +32,14 @@ elif which == "bf16_bwd":
     O, lse = ops.bf16_fwd(q, k, v, True)
     for _ in range(3):
         ops.bf16_bwd(q, k, v, O, lse, True, dO)
+elif which == "int8_bwd":
+    BH, S, D = 37, 8192, 128                                   # 37 heads x 64 k-tiles = 16 waves of 148 CTAs
+    q, k, v, dO = [torch.randn(BH, S, D, device="cuda", dtype=torch.float16) for _ in range(4)]
+    qi, sq = ops.quant_block(q, 128); ki, sk = ops.quant_block(k, 128); vi, sv = ops.quant_block(v, 128)
+    doi, sdo = ops.quant_block(dO, 128)
+    O, lse16, lse32 = ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D)
+    delta = ops.bwd_delta(dO.view(-1, D), O)
+    for _ in range(3):
+        ops.int8_bwd_prequant(qi, ki, vi, doi, sq, sk, sv, sdo, lse32, delta, None, BH, S, D)
 torch.cuda.synchronize()
 print("ok")
