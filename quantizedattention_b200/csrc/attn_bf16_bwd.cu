@@ -168,8 +168,8 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               wd[e] = *reinterpret_cast<uint32_t*>(&dh);
             }
             const uint32_t off = (uint32_t)half * kBAtom + swz128(row, (ch * 32 + g * 8) * 2);
-            *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-            *reinterpret_cast<uint4*>(smem + L::off_ds + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            sts128(smem_u32(smem) + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
+            sts128(smem_u32(smem) + L::off_ds + off, wd[0], wd[1], wd[2], wd[3]);
           }
         }
       };

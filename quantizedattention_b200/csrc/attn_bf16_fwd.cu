@@ -181,7 +181,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         const int col = c0 + g * 8;
         const uint32_t off = (uint32_t)(col >> 6) * kAtom + swz128(row, (col & 63) * 2);
-        *reinterpret_cast<uint4*>(pbase + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        sts128(smem_u32(pbase) + off, w[0], w[1], w[2], w[3]);
       }
       l = l * resc + lsum;
       fence_proxy_async_smem();

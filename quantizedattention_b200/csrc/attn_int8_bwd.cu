@@ -142,6 +142,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     issue_dp(0);
   }
 
+  const uint32_t smem_base = smem_u32(smem);
   const int half = warp >> 2;                                   // column group handled by this thread
   const int row = (warp & 3) * 32 + lane;                       // TMEM lane: query row (S, dP, dQ) or key (dV, dK)
   const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
@@ -175,13 +176,13 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
       tmem_ld_wait();
       const int col = half * DH + ch * 16;                         // first output column of this chunk
-      uint8_t* atom = smem + L::off_dq + (col >> 5) * (128 * 128);
+      const uint32_t atom = smem_base + L::off_dq + (col >> 5) * (128 * 128);
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
         const float2 cq2 = make_float2(c_dq, c_dq);
         const float2 o01 = __fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2);
         const float2 o23 = __fmul2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2);
-        *reinterpret_cast<float4*>(atom + swz128(row, ((col & 31) + c) * 4)) = make_float4(o01.x, o01.y, o23.x, o23.y);
+        sts128f(atom + swz128(row, ((col & 31) + c) * 4), o01.x, o01.y, o23.x, o23.y);
       }
     }
   };
@@ -282,7 +283,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
     // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
     //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
-    uint8_t* ds_tile = smem + L::off_ds + ph * (128 * 128);
+    const uint32_t ds_tile = smem_base + L::off_ds + ph * (128 * 128);
     const float2 cdpi2 = make_float2(c_dp * kPs * inv_ds, c_dp * kPs * inv_ds), ndlti2 = make_float2(-dlt * kPs * inv_ds, -dlt * kPs * inv_ds);
     const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
 #pragma unroll
@@ -310,8 +311,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
       }
       const uint32_t off = swz128(row, half * CW + ch * 16);
-      *reinterpret_cast<uint4*>(smem + L::off_p + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-      *reinterpret_cast<uint4*>(ds_tile + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
+      sts128(ds_tile + off, wd[0], wd[1], wd[2], wd[3]);
     }
     QA_TLB(7);
     // ---- drain dQ of the previous tile (its MMA ran while pass 2 executed)

@@ -173,7 +173,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const __half2 m2 = __half2half2(m_new);
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
-      uint8_t* prow = smem + L::off_p + b * L::kPBytes;
+      const uint32_t prow = smem_u32(smem) + L::off_p + b * L::kPBytes;
 #pragma unroll
       for (int g = 0; g < NC / 16; ++g) {
         uint32_t w[4];
@@ -192,7 +192,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
         }
         const uint32_t off = swz128(row, c0 + g * 16);
-        *reinterpret_cast<uint4*>(prow + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        sts128(prow + off, w[0], w[1], w[2], w[3]);
       }
       l = l * rescale + (ls2.x + ls2.y);
       fence_proxy_async_smem();

@@ -145,8 +145,8 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           }
           const int col = c0 + ch * 32 + g * 8;
           const uint32_t off = (uint32_t)(col >> 6) * kJAtom + swz128(row, (col & 63) * 2);
-          *reinterpret_cast<uint4*>(pbase + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-          *reinterpret_cast<uint4*>(hbase + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+          sts128(smem_u32(pbase) + off, wp[0], wp[1], wp[2], wp[3]);
+          sts128(smem_u32(hbase) + off, wh[0], wh[1], wh[2], wh[3]);
         }
       }
       tc_fence_before();

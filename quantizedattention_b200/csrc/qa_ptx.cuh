@@ -59,6 +59,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- shared-memory stores
+// The kernels' tile pointers are derived from a manually aligned base, which hides the address space from the
+// compiler (it then emits generic ST.E with 64-bit addresses); these wrappers keep the stores as STS.128.
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> visible to TMA / tcgen05
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
