@@ -205,7 +205,7 @@ def main():
         outs_host = [torch.empty(B, H, S, D, dtype=torch.float16).pin_memory() for _ in range(4)]
 
         from quantizedattention_b200.host_pipeline import HostStagedSageAttention
-        pipe = HostStagedSageAttention(dev, heads_per_chunk=16, slots=4)
+        pipe = HostStagedSageAttention(dev, heads_per_chunk=32, slots=3)
 
         def step_e2e():                                             # H2D / forward+backward / D2H pipelined over head chunks
             pipe(host[0], host[1], host[2], host[3], out=outs_host)
@@ -245,9 +245,10 @@ def main():
             "peak_source": "int8 dense: torch._int_mm 8192^3 best-of-10 on this pool (profiles/r01_peaks.json); "
                            "MEASURED_PEAKS.json has no int8 entry (its bf16 burst x2 = %.0f)" % (2 * mp.get("bf16_tflops", 0)),
             "share_of_step": bwd_ms / ms_step,
-            "note": "binding unit is not the tensor pipe: per tile pair the kernel must drain 5 int32/fp32 TMEM tiles "
-                    "(320-384 KB) through tcgen05.ld, measured ceiling ~100 B/clk/SM (profiles/r01_tmem_read_bw.json), "
-                    "plus ~26 CUDA-core instructions per logit for the reference's per-tile re-quantisation",
+            "note": "binding unit is not the tensor pipe: per (128 x 128) tile the int8 MMAs take ~2.5k of ~7.7k clk "
+                    "(tools/timeline_bwd.py); the rest is the reference's per-tile re-quantisation on the CUDA cores "
+                    "(two passes, ~24 instructions per logit, 384 KB of int32 TMEM drains per tile) executed by 8 warps "
+                    "whose 255 registers hold the fp32 dV/dK accumulators, so latencies are exposed (issue slots 43 % busy)",
             "other_kernels": {"int8_fwd_kernel<128,2,3>": {"ms": fwd_ms, "achieved": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12,
                                                            "frac": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12 / peak}}}
     roof["frac"] = roof["achieved"] / peak
@@ -273,7 +274,7 @@ def main():
         "per_gpu_tops": value / world, "frac_of_int8_peak_measured": value / world / peak,
         "frac_of_int8_peak_spec_4500": value / world / 4500.0,
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": 10 * K,   # k_mean x2, quant x4 (q, k, v, dO), int8 fwd, delta, int8 bwd, dQ cast
+        "gpu_launches": 10 * K,   # k_mean x2, quant x4 (q, k, v, dO), int8 fwd, delta, int8 bwd, dQ finalize
     }))
     if world > 1:
         dist.destroy_process_group()

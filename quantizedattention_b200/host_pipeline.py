@@ -21,7 +21,7 @@ from . import attention_int8 as A
 class HostStagedSageAttention:
     """Reusable pipeline object (device staging buffers and streams are allocated once per shape)."""
 
-    def __init__(self, device=None, heads_per_chunk: int = 16, slots: int = 4):
+    def __init__(self, device=None, heads_per_chunk: int = 32, slots: int = 3):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.heads_per_chunk = heads_per_chunk
         self.slots = max(2, slots)                                 # device staging slots for the inputs
@@ -49,6 +49,11 @@ class HostStagedSageAttention:
         self.hc = hc
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.inbuf = [[torch.empty((1, hc, S, D), dtype=torch.float16, device=dev) for _ in range(n_in)] for _ in range(self.slots)]
+        # results are copied into persistent staging slots on the compute stream, so every temporary of the attention
+        # call is allocated and freed on ONE stream (the caching allocator then never has to cudaMalloc, which would
+        # synchronise the device and stall the pipeline) and the copy-out stream only ever reads these buffers
+        self.outbuf = [[torch.empty((hc, S, D), dtype=torch.float16, device=dev) for _ in range(4 if with_grad else 1)]
+                       for _ in range(self.slots)]
         self._key = key
 
     @staticmethod
@@ -85,7 +90,6 @@ class HostStagedSageAttention:
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_event(start)                                    # the pipeline starts after the caller's prior work
         ev_in, ev_cmp, ev_out = [None] * n, [None] * n, [None] * n
-        results = [None] * n
         for i in range(n + 2):
             if i < n:                                              # ---- stage 1: H2D of chunk i
                 slot = i % self.slots
@@ -106,14 +110,19 @@ class HostStagedSageAttention:
                     self.s_cmp.wait_event(ev_in[j])
                     sp = self._span("compute", j, self.s_cmp)
                     bufs = self.inbuf[slot]
+                    if j >= self.slots:
+                        self.s_cmp.wait_event(ev_out[j - self.slots])   # the output slot has been copied out
                     if with_grad:
                         qr, kr, vr = (t.detach().requires_grad_() for t in bufs[:3])
                         O = A.sage_attention_3_int8(qr, kr, vr)
                         O.backward(bufs[3])
-                        results[j] = (O.detach(), qr.grad, kr.grad, vr.grad)
+                        res = (O.detach(), qr.grad, kr.grad, vr.grad)
                     else:
                         with torch.no_grad():
-                            results[j] = (A.sage_attention_3_int8(*bufs[:3]),)
+                            res = (A.sage_attention_3_int8(*bufs[:3]),)
+                    for dst, src in zip(self.outbuf[slot], res):
+                        dst.copy_(src.view(hc, S, D))
+                    del res
                     if sp is not None:
                         sp.record(self.s_cmp)
                     ev_cmp[j] = torch.cuda.Event()
@@ -123,14 +132,12 @@ class HostStagedSageAttention:
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(ev_cmp[m])
                     sp = self._span("d2h", m, self.s_out)
-                    for dst, src in zip(dsts, results[m]):
-                        src.record_stream(self.s_out)              # allocated on the compute stream, read here
-                        dst[m * hc:(m + 1) * hc].copy_(src.view(hc, S, D), non_blocking=True)
+                    for dst, src in zip(dsts, self.outbuf[m % self.slots]):
+                        dst[m * hc:(m + 1) * hc].copy_(src, non_blocking=True)
                     if sp is not None:
                         sp.record(self.s_out)
                     ev_out[m] = torch.cuda.Event()
                     ev_out[m].record(self.s_out)
-                results[m] = None
         cur.wait_event(ev_out[n - 1])                              # results are complete for work queued after the call
         cur.wait_event(ev_cmp[n - 1])
         return out[0] if not with_grad else tuple(out)
@@ -139,7 +146,7 @@ class HostStagedSageAttention:
 _DEFAULT = {}
 
 
-def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 16, device=None):
+def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 32, device=None):
     """Functional form of HostStagedSageAttention (one cached pipeline per device and chunk size).
     Returns O, or (O, dq, dk, dv) when dO is given; the copies are asynchronous on the current stream's timeline:
     synchronise (or record an event) before reading the host results."""

@@ -16,6 +16,16 @@ pipe = HostStagedSageAttention(heads_per_chunk=hc, slots=slots)
 for _ in range(2):
     pipe(*host, out=out)
 torch.cuda.synchronize()
+import time
+for rep in range(3):                                    # untraced: host time to enqueue one step vs device time
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    pipe(*host, out=out)
+    b.record()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print("hc", hc, "slots", slots, "device ms", round(a.elapsed_time(b), 2), "host enqueue ms", round((t1 - t0) * 1e3, 2))
 pipe.trace = []
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
