@@ -22,7 +22,14 @@ LOG2E = 1.44269504  # the reference's literal constant (attention_int8.py:153)
 # --------------------------------------------------------------------------------------
 # block quantisation -- attention_int8.py:178-186 (Q), :188-195 (K), :241-247 (V)
 # --------------------------------------------------------------------------------------
-def quant_block(x2d: torch.Tensor, blk: int):
+def _to_i8(x: torch.Tensor, rounding: str = "trunc") -> torch.Tensor:
+    """"trunc": the reference's `.to(torch.int8)` (toward zero, LEDGER I-3); "nearest": round half to even - the opt-in
+    accuracy mode of the CUDA path, which removes the truncation bias."""
+    assert rounding in ("trunc", "nearest")
+    return (torch.round(x.float()) if rounding == "nearest" else x).to(torch.int8)
+
+
+def quant_block(x2d: torch.Tensor, blk: int, rounding: str = "trunc"):
     """x2d: [N, D] fp16 -> (int8 [N, D], fp16 scales [ceil(N/blk)]).
 
     scale = amax(|block|)/127 in fp16; value = trunc_toward_zero(fp16(x / scale)).
@@ -39,14 +46,14 @@ def quant_block(x2d: torch.Tensor, blk: int):
         s = torch.amax(xb.abs(), dim=1) / 127                     # fp16 (:180)
         qv = xb / s[:, None]                                      # fp16 divide (:182)
         qv = torch.where(s[:, None] == 0, torch.zeros_like(qv), qv)
-        out.copy_(qv.to(torch.int8).reshape(n, d))                # trunc (:183)
+        out.copy_(_to_i8(qv, rounding).reshape(n, d))             # trunc (:183)
         scales.copy_(s)
         return out, scales
     for b in range(nblk):                                         # ragged tail (hl.tile clamps)
         blkx = x2d[b * blk:(b + 1) * blk]
         s = torch.amax(blkx.abs().flatten(), dim=0) / 127
         qv = blkx / s if float(s) != 0.0 else torch.zeros_like(blkx)
-        out[b * blk:(b + 1) * blk] = qv.to(torch.int8)
+        out[b * blk:(b + 1) * blk] = _to_i8(qv, rounding)
         scales[b] = s
     return out, scales
 
@@ -73,7 +80,7 @@ def _imm(a_i8: torch.Tensor, b_i8: torch.Tensor) -> torch.Tensor:
 # forward -- attention_int8.py:170-257
 # --------------------------------------------------------------------------------------
 def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
-             return_lse32: bool = False):
+             return_lse32: bool = False, rounding: str = "trunc"):
     """Returns the reference 10-tuple
         (O fp16 [B,H,S,D], lse fp16 [N], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D],
          sq [N/Bq], sk [N/Bkv], sv [N/Bkv], Bq, Bkv)
@@ -82,9 +89,9 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
     """
     B, H, S, D = q.shape
     N = B * H * S
-    q_i8, sq = quant_block(q.reshape(N, D), Bq)
-    k_i8, sk = quant_block(k_smooth.reshape(N, D), Bkv)
-    v_i8, sv = quant_block(v.reshape(N, D), Bkv)
+    q_i8, sq = quant_block(q.reshape(N, D), Bq, rounding)
+    k_i8, sk = quant_block(k_smooth.reshape(N, D), Bkv, rounding)
+    v_i8, sv = quant_block(v.reshape(N, D), Bkv, rounding)
 
     sm_scale = 1.0 / math.sqrt(D)
     qk_scale = sm_scale * LOG2E
@@ -117,7 +124,7 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
         l = l * rescale + l_new                                          # :223
         O = O * rescale                                                  # :225
         sp = torch.exp2((row_max - m).to(torch.float32)) / 127           # :232-234
-        P_i8 = (P / sp).to(torch.int8)                                   # :236-237
+        P_i8 = _to_i8(P / sp, rounding)                                  # :236-237
         svj = sv_g[:, j].view(G, 1, 1).float()
         O = O + _imm(P_i8, vg[:, ks]).to(torch.float32) * sp * svj       # :249-250
 
@@ -167,11 +174,11 @@ def int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bk
     return (O / l).to(torch.float16).reshape(BH * Sq, D), lse16.reshape(-1), lse32.reshape(-1)
 
 
-def sage_forward(q, k, v, Bq=32, Bkv=32):
+def sage_forward(q, k, v, Bq=32, Bkv=32, rounding: str = "trunc"):
     """Contract version of SageAttention3_Int8_autograd_function.forward
     (attention_int8.py:21-40 with LEDGER I-1): 11-tuple with k_mean [B,H,1,D] in slot 2."""
     km = k_token_mean(k)
-    out = int8_fwd(q, smooth_k(k, km), v, Bq, Bkv, per_head=True)
+    out = int8_fwd(q, smooth_k(k, km), v, Bq, Bkv, per_head=True, rounding=rounding)
     return out[:2] + (km,) + out[2:]
 
 
@@ -222,15 +229,15 @@ def int8_bwd_literal(dO, q_i8, sq, k_i8_T, k_mean_bhk, sk, v_i8, sv, O, lse16, B
     return dq.view(B, H, S, D), dk.view(B, H, S, D), dv.view(B, H, S, D)
 
 
-def quant_tile_fp32(x: torch.Tensor):
+def quant_tile_fp32(x: torch.Tensor, rounding: str = "trunc"):
     """Per-[Bq,Bkv]-tile quantisation of an fp32 tile batch x: [..., r, c] (attention_int8.py
     :363-365, :403-405): scale = amax|x|/127 (fp32), value = trunc(x/scale); zero tile -> 0."""
     s = torch.amax(x.abs(), dim=(-2, -1), keepdim=True) / 127
     qv = torch.where(s == 0, torch.zeros_like(x), x / s)
-    return qv.to(torch.int8), s
+    return _to_i8(qv, rounding), s
 
 
-def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv):
+def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv, rounding: str = "trunc"):
     """CONTRACT backward (what the CUDA kernel implements; LEDGER I-1,5,6,7,8,9,10,12,15).
 
     Per (b,h); k-tile j, q-tile i:
@@ -261,7 +268,7 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
     lse32 = lse.float().view(G, nq, Bq, 1)
     dOg = dO.reshape(G, nq, Bq, D)
     delta = (dOg.float() * O.reshape(G, nq, Bq, D).float()).sum(-1, keepdim=True)   # fp32 pre-pass
-    dO_i8, s_dO = quant_block(dO.reshape(N, D).to(torch.float16), Bq)
+    dO_i8, s_dO = quant_block(dO.reshape(N, D).to(torch.float16), Bq, rounding)
     dO_i8 = dO_i8.view(G, nq, Bq, D)
     s_dO = s_dO.view(G, nq).float()
     km = k_mean.reshape(G, 1, D).float()
@@ -277,11 +284,11 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
             acc = _imm(qi, kj.transpose(1, 2))
             S16 = (acc.to(torch.float32) * sqg[:, i, None, None] * skg[:, j, None, None] * qk_scale).to(torch.float16)
             P = torch.exp2(S16.to(torch.float32) - lse32[:, i])
-            P_i8, sP = quant_tile_fp32(P)
+            P_i8, sP = quant_tile_fp32(P, rounding)
             dv[:, j] += _imm(P_i8.transpose(1, 2), dO_i8[:, i]).to(torch.float32) * s_dO[:, i, None, None] * sP
             dP = _imm(dO_i8[:, i], vj.transpose(1, 2)).to(torch.float32) * s_dO[:, i, None, None] * svg[:, j, None, None]
             dS = P * (dP - delta[:, i])
-            dS_i8, s_dS = quant_tile_fp32(dS)
+            dS_i8, s_dS = quant_tile_fp32(dS, rounding)
             dq[:, i] += _imm(dS_i8, kj).to(torch.float32) * s_dS * skg[:, j, None, None] * sm_scale \
                 + sm_scale * dS.sum(-1, keepdim=True) * km
             dk[:, j] += _imm(dS_i8.transpose(1, 2), qi).to(torch.float32) * s_dS * sqg[:, i, None, None] * sm_scale

@@ -36,13 +36,23 @@ def _stash_lse32(lse16, lse32):
     _LSE32[k] = lse32
     weakref.finalize(lse16, _LSE32.pop, k, None)
 
-_CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2}
+_CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2, "rounding": "trunc"}
 
 
 def set_block_sizes(Bq: int = 128, Bkv: int = 128):
     if Bq not in (32, 64, 128, 256) or Bkv not in (32, 64, 128):
         raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv in {32,64,128} (backward: 128/128)")
     _CFG["Bq"], _CFG["Bkv"] = Bq, Bkv
+
+
+def set_quant_rounding(mode: str = "trunc"):
+    """int8 rounding of every quantiser of the path (Q, K, V, P, dO, dS).  "trunc" is the reference's `.to(torch.int8)`
+    (attention_int8.py:183 etc., LEDGER I-3) and the default; "nearest" (round half to even) is the opt-in accuracy mode
+    of SURVEY.md 8f.1: it removes the truncation bias, at identical speed, but its int8 tensors are by construction
+    not the reference's.  The fused kernels are instantiated for the tuned Bkv = 128 tile in this mode."""
+    if mode not in ops.ROUNDING:
+        raise ValueError('rounding mode must be "trunc" or "nearest"')
+    _CFG["rounding"] = mode
 
 
 def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False):
@@ -58,11 +68,12 @@ def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want
             raise TypeError("int8 attention takes fp16 q, k, v")
     Bq, Bkv = _CFG["Bq"], _CFG["Bkv"]
     D = q_head_dim
-    q_i8, sq = ops.quant_block(q_fp16_input, Bq)
-    k_i8, sk = ops.quant_block(k_fp16_input, Bkv)
-    v_i8, sv = ops.quant_block(v_fp16_input, Bkv)
+    rnd = _CFG["rounding"]
+    q_i8, sq = ops.quant_block(q_fp16_input, Bq, rounding=rnd)
+    k_i8, sk = ops.quant_block(k_fp16_input, Bkv, rounding=rnd)
+    v_i8, sv = ops.quant_block(v_fp16_input, Bkv, rounding=rnd)
     O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                            nsplit=_CFG["nsplit"], want_lse32=_want_lse32)
+                                            nsplit=_CFG["nsplit"], want_lse32=_want_lse32, rounding=rnd)
     out = (O.view(batch, head, q_tokens, D), lse16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
     return out + (lse32,) if _want_lse32 else out
 
@@ -95,7 +106,7 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
     if dO.dtype != torch.float16:
         dO = dO.to(torch.float16)
     delta = ops.bwd_delta(dO, O_input_fp16)
-    do_i8, s_do = ops.quant_block(dO, Bq)
+    do_i8, s_do = ops.quant_block(dO, Bq, rounding=_CFG["rounding"])
     lse32 = lse_input_fp16.to(torch.float32).contiguous()
     km = None
     if k_mean_bh_fp16 is not None:
@@ -103,7 +114,7 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
         km = k_mean_bh_fp16.to(torch.float16).contiguous()
     dq, dk, dv = ops.int8_bwd_prequant(q_bh_int8.contiguous(), k_i8, v_bh_int8.contiguous(), do_i8, sq_bh_fp16,
                                        sk_bh_fp16, sv_bh_fp16, s_do, lse32, delta, km, batch * head, q_tokens, head_dim,
-                                       Bq, Bkv)
+                                       Bq, Bkv, rounding=_CFG["rounding"])
     shp = (batch, head, q_tokens, head_dim)
     return dq.view(shp), dk.view(shp), dv.view(shp)
 
@@ -121,11 +132,12 @@ class SageAttention3_Int8_autograd_function(Function):
         k_tokens = k_fp16.shape[2]
         Bq, Bkv = _CFG["Bq"], _CFG["Bkv"]
         k_mean_fp16 = ops.k_mean(k_fp16)                                       # K-smoothing (LEDGER I-1)
-        q_i8, sq = ops.quant_block(q_fp16, Bq)
-        k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean_fp16, rows_per_head=k_tokens)   # fused k - mean
-        v_i8, sv = ops.quant_block(v_fp16, Bkv)
+        rnd = _CFG["rounding"]
+        q_i8, sq = ops.quant_block(q_fp16, Bq, rounding=rnd)
+        k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean_fp16, rows_per_head=k_tokens, rounding=rnd)   # fused k - mean
+        v_i8, sv = ops.quant_block(v_fp16, Bkv, rounding=rnd)
         O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                                nsplit=_CFG["nsplit"], want_lse32=True)
+                                                nsplit=_CFG["nsplit"], want_lse32=True, rounding=rnd)
         _stash_lse32(lse16, lse32)                                             # picked up by setup_context
         return (O.view(batch, head, q_tokens, D), lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
 

@@ -14,6 +14,7 @@
 // thread 0 issues TMA and MMA at the phase boundaries.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <type_traits>
 #include <stdlib.h>
 
 namespace qa {
@@ -53,7 +54,7 @@ struct Int8BwdParams {
       p.dbg[(t * 2 + (warp != 0)) * 16 + (slot)] = clock64();                                                 \
   } while (0)
 
-template <int D, int NG>
+template <int D, int NG, bool RN>
 __global__ void __launch_bounds__(128 * NG, 1)
 int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -286,33 +287,36 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t ds_tile = smem_base + L::off_ds + ph * (128 * 128);
     const float2 cdpi2 = make_float2(c_dp * kPs * inv_ds, c_dp * kPs * inv_ds), ndlti2 = make_float2(-dlt * kPs * inv_ds, -dlt * kPs * inv_ds);
     const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
+    {                                                              // RN: the rounding mode is an instruction modifier
 #pragma unroll
-    for (int ch = 0; ch < CW / 16; ++ch) {
-      uint32_t r2[16];
-      tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
-      tmem_ld_wait();
-      uint32_t wp[4], wd[4];
+      for (int ch = 0; ch < CW / 16; ++ch) {
+        uint32_t r2[16];
+        tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
+        tmem_ld_wait();
+        uint32_t wp[4], wd[4];
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint32_t bp[4], bd[4];
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t bp[4], bd[4];
 #pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          const int c = q4 * 4 + e;
-          const float2 pp = __half22float2(pk[ch * 8 + c / 2]);                  // 1024 * P from pass 1
-          // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS (and the 1/1024) folded into the FFMA2 constants
-          const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
-          const float2 pq = __ffma2_rz(pp, invp2, magic2);                      // P >= 0: low byte = trunc(P / sP)
-          bp[e] = __float_as_uint(pq.x);
-          bp[e + 1] = __float_as_uint(pq.y);
-          bd[e] = (uint32_t)__float2int_rz(dq.x);
-          bd[e + 1] = (uint32_t)__float2int_rz(dq.y);
+          for (int e = 0; e < 4; e += 2) {
+            const int c = q4 * 4 + e;
+            const float2 pp = __half22float2(pk[ch * 8 + c / 2]);                  // 1024 * P from pass 1
+            // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS (and the 1/1024) folded into the FFMA2 constants
+            const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
+            // P >= 0: low byte of the biased sum = trunc(P / sP), or its nearest-even rounding in accuracy mode
+            const float2 pq = RN ? __ffma2_rn(pp, invp2, magic2) : __ffma2_rz(pp, invp2, magic2);
+            bp[e] = __float_as_uint(pq.x);
+            bp[e + 1] = __float_as_uint(pq.y);
+            bd[e] = (uint32_t)(RN ? __float2int_rn(dq.x) : __float2int_rz(dq.x));
+            bd[e + 1] = (uint32_t)(RN ? __float2int_rn(dq.y) : __float2int_rz(dq.y));
+          }
+          wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
+          wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
         }
-        wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
-        wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
+        const uint32_t off = swz128(row, half * CW + ch * 16);
+        sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
+        sts128(ds_tile + off, wd[0], wd[1], wd[2], wd[3]);
       }
-      const uint32_t off = swz128(row, half * CW + ch * 16);
-      sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
-      sts128(ds_tile + off, wd[0], wd[1], wd[2], wd[3]);
     }
     QA_TLB(7);
     // ---- drain dQ of the previous tile (its MMA ran while pass 2 executed)
@@ -378,7 +382,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
-template <int D, int NG>
+template <int D, int NG, bool RN = false>
 static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
                            const Int8BwdParams& p, int BH, cudaStream_t st) {
   using L = Int8BwdSmem<D>;
@@ -395,7 +399,7 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   uint64_t strq[1] = {(uint64_t)D * 4};
   uint32_t boxq[2] = {32, 128};
   if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
-  auto kern = int8_bwd_kernel<D, NG>;
+  auto kern = int8_bwd_kernel<D, NG, RN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.S / 128, BH);
@@ -420,7 +424,8 @@ extern "C" int qa_debug_set_int8_bwd_timeline(void* buf) {
 extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
                            const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
                            void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
-                           int Bq, int Bkv, void* stream) {
+                           int Bq, int Bkv, int rounding, void* stream) {
+  if (rounding != 0 && rounding != 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: rounding must be 0 (toward zero) or 1 (nearest)");
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: D must be 64 or 128");
   if (Bq != 128 || Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: Bq = Bkv = 128 required");
   if (S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S must be a multiple of 128");
@@ -434,6 +439,9 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   cudaStream_t st = (cudaStream_t)stream;
   const char* env = getenv("QA_INT8_BWD_NG");
   const int ng = env ? atoi(env) : 2;   // 2 column groups (8 warps, 255 regs) measured faster than 4 (16 warps)
+  if (rounding == 1)                                              // accuracy mode: instantiated for the default shape only
+    return D == 128 ? launch_int8_bwd<128, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+                    : launch_int8_bwd<64, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
   if (D == 128) return ng == 2 ? launch_int8_bwd<128, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
                                : launch_int8_bwd<128, 4>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
   return ng == 2 ? launch_int8_bwd<64, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)

@@ -12,6 +12,7 @@
 // (single fused scale multiply; reciprocal multiply instead of divide for P/sp).
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <type_traits>
 
 namespace qa {
 
@@ -58,7 +59,7 @@ struct Int8FwdParams {
       p.dbg[j * 16 + (slot)] = clock64();                                                             \
   } while (0)
 
-template <int D, int NSPLIT, int STAGES, int BN>
+template <int D, int NSPLIT, int STAGES, int BN, bool RN>
 __global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
 int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
@@ -174,25 +175,28 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
       const uint32_t prow = smem_u32(smem) + L::off_p + b * L::kPBytes;
+      {                                                            // RN: the rounding mode is an FFMA2 modifier
 #pragma unroll
-      for (int g = 0; g < NC / 16; ++g) {
-        uint32_t w[4];
+        for (int g = 0; g < NC / 16; ++g) {
+          uint32_t w[4];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t bytes[4];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t bytes[4];
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
-            const float2 pp = make_float2(ex2_approx(f.x), ex2_approx(f.y));
-            ls2 = __fadd2_rn(ls2, pp);
-            const float2 qf = __ffma2_rz(pp, inv2, magic2);                           // low byte = trunc(P/sp)
-            bytes[h2 * 2] = __float_as_uint(qf.x);
-            bytes[h2 * 2 + 1] = __float_as_uint(qf.y);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
+              const float2 pp = make_float2(ex2_approx(f.x), ex2_approx(f.y));
+              ls2 = __fadd2_rn(ls2, pp);
+              // low byte of the biased sum = trunc(P/sp) (reference) or its nearest-even rounding (accuracy mode)
+              const float2 qf = RN ? __ffma2_rn(pp, inv2, magic2) : __ffma2_rz(pp, inv2, magic2);
+              bytes[h2 * 2] = __float_as_uint(qf.x);
+              bytes[h2 * 2 + 1] = __float_as_uint(qf.y);
+            }
+            w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
           }
-          w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
+          const uint32_t off = swz128(row, c0 + g * 16);
+          sts128(prow + off, w[0], w[1], w[2], w[3]);
         }
-        const uint32_t off = swz128(row, c0 + g * 16);
-        sts128(prow + off, w[0], w[1], w[2], w[3]);
       }
       l = l * rescale + (ls2.x + ls2.y);
       fence_proxy_async_smem();
@@ -360,7 +364,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
 }
 
-template <int D, int NSPLIT, int STAGES, int BN>
+template <int D, int NSPLIT, int STAGES, int BN, bool RN = false>
 static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const Int8FwdParams& p, int BH,
                            cudaStream_t st) {
   using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
@@ -374,7 +378,7 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
   if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
   if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
-  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN>;
+  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / kBM, BH);
@@ -400,7 +404,8 @@ extern "C" int qa_debug_set_int8_fwd_timeline(void* buf) {
 extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
                                  const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
                                  const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int D,
-                                 int Bq, int Bkv, int nsplit, void* stream) {
+                                 int Bq, int Bkv, int nsplit, int rounding, void* stream) {
+  if (rounding != 0 && rounding != 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: rounding must be 0 (toward zero) or 1 (nearest)");
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: D must be 64 or 128");
   if (Bkv != 32 && Bkv != 64 && Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 32, 64 or 128");
   if (Bq != 32 && Bq != 64 && Bq != 128 && Bq != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bq must be 32/64/128/256");
@@ -417,11 +422,17 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   p.dbg = (long long*)g_int8_fwd_dbg;
   cudaStream_t st = (cudaStream_t)stream;
   if (Bkv == 128) {
+    if (rounding == 1) {                                         // accuracy mode: instantiated for the tuned tile only
+      if (nsplit != 2) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nearest rounding needs nsplit = 2");
+      return D == 128 ? launch_int8_fwd<128, 2, 3, 128, true>(q_i8, k_i8, v_i8, p, BH, st)
+                      : launch_int8_fwd<64, 2, 4, 128, true>(q_i8, k_i8, v_i8, p, BH, st);
+    }
     if (D == 128) return nsplit == 2 ? launch_int8_fwd<128, 2, 3, 128>(q_i8, k_i8, v_i8, p, BH, st)
                                      : launch_int8_fwd<128, 1, 3, 128>(q_i8, k_i8, v_i8, p, BH, st);
     return nsplit == 2 ? launch_int8_fwd<64, 2, 4, 128>(q_i8, k_i8, v_i8, p, BH, st)
                        : launch_int8_fwd<64, 1, 4, 128>(q_i8, k_i8, v_i8, p, BH, st);
   }
+  if (rounding == 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nearest rounding needs Bkv = 128");
   if (Bkv == 64) return D == 128 ? launch_int8_fwd<128, 1, 4, 64>(q_i8, k_i8, v_i8, p, BH, st)
                                  : launch_int8_fwd<64, 1, 4, 64>(q_i8, k_i8, v_i8, p, BH, st);
   return D == 128 ? launch_int8_fwd<128, 1, 4, 32>(q_i8, k_i8, v_i8, p, BH, st)
@@ -430,7 +441,7 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
 
 extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
                            const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
-                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, void* stream) {
+                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int rounding, void* stream) {
   return qa_int8_fwd_state(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, nullptr, nullptr, nullptr, BH,
-                           Sq, Sk, D, Bq, Bkv, nsplit, stream);
+                           Sq, Sk, D, Bq, Bkv, nsplit, rounding, stream);
 }

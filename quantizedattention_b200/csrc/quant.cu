@@ -65,18 +65,20 @@ __global__ void kmean_final_kernel(const float* __restrict__ part, __half* __res
 // registers between the amax pass and the quantise pass, so HBM is read exactly once.
 // mean != nullptr: subtract the per-head fp16 mean first (one fp16 rounding), i.e. K-smoothing.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int quant_one(float x, float s, float y) {
-  // correctly rounded x / s (y = RN(1/s)), rounded to fp16, truncated toward zero
+__device__ __forceinline__ int quant_one(float x, float s, float y, bool nearest) {
+  // correctly rounded x / s (y = RN(1/s)), rounded to fp16, then truncated toward zero (the reference, LEDGER I-3)
+  // or rounded half-to-even (opt-in accuracy mode)
   float q0 = x * y;
   float r = __fmaf_rn(-s, q0, x);
   float q1 = __fmaf_rn(r, y, q0);
-  return (int)__half2float(__float2half_rn(q1));
+  const float qh = __half2float(__float2half_rn(q1));
+  return nearest ? __float2int_rn(qh) : (int)qh;
 }
 
 template <int ITERS>
 __global__ void __launch_bounds__(256) quant_block_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
                                                           int8_t* __restrict__ out, __half* __restrict__ scales,
-                                                          int vec_per_block, int D, int rows_per_head, int blk) {
+                                                          int vec_per_block, int D, int rows_per_head, int blk, int rounding) {
   const size_t b = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(x) + b * vec_per_block;
   uint2* dst = reinterpret_cast<uint2*>(out) + b * vec_per_block;
@@ -126,8 +128,8 @@ __global__ void __launch_bounds__(256) quant_block_kernel(const __half* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 f = __half22float2(h[j]);
-      q[2 * j] = zero ? 0 : quant_one(f.x, s, y);
-      q[2 * j + 1] = zero ? 0 : quant_one(f.y, s, y);
+      q[2 * j] = zero ? 0 : quant_one(f.x, s, y, rounding != 0);
+      q[2 * j + 1] = zero ? 0 : quant_one(f.y, s, y, rounding != 0);
     }
     uint2 o;
     o.x = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
@@ -176,8 +178,10 @@ extern "C" size_t qa_k_mean_workspace_bytes(int B, int H, int S, int D) {
 }
 
 // x: [n_rows, D] fp16 (n_rows = B*H*S); blk rows per quantisation block; mean: [n_rows/rows_per_head, D] fp16 or NULL.
+// rounding: 0 = toward zero (the reference), 1 = nearest even (accuracy mode).
 extern "C" int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* out_i8, void* scales_fp16, long long n_rows,
-                              int D, int blk, int rows_per_head, void* stream) {
+                              int D, int blk, int rows_per_head, int rounding, void* stream) {
+  if (rounding != 0 && rounding != 1) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: rounding must be 0 (toward zero) or 1 (nearest)");
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: D must be 64 or 128");
   if (blk != 32 && blk != 64 && blk != 128 && blk != 256) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: blk must be 32/64/128/256");
   if (n_rows % blk != 0 || (mean_fp16 && rows_per_head % blk != 0))
@@ -189,7 +193,7 @@ extern "C" int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* o
   cudaStream_t st = (cudaStream_t)stream;
 #define QA_LAUNCH_Q(IT)                                                                                              \
   quant_block_kernel<IT><<<(unsigned)nblk, 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (int8_t*)out_i8, \
-                                                         (__half*)scales_fp16, vec, D, rows_per_head, blk)
+                                                         (__half*)scales_fp16, vec, D, rows_per_head, blk, rounding)
   switch (iters) {
     case 1: QA_LAUNCH_Q(1); break;
     case 2: QA_LAUNCH_Q(2); break;

@@ -74,7 +74,11 @@ def k_mean(k: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, rows_per_head: int | None = None):
+ROUNDING = {"trunc": 0, "nearest": 1}       # int8 rounding of the quantisers: the reference truncates (LEDGER I-3)
+
+
+def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, rows_per_head: int | None = None,
+                rounding: str = "trunc"):
     """x: [..., D] fp16 (flattened to [N, D]) -> (int8 [N, D], fp16 scales [N/blk]).
     mean: optional [B,H,1,D] fp16 subtracted per head before quantisation (needs rows_per_head = S)."""
     _need_cuda(x, mean)
@@ -90,7 +94,7 @@ def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, row
     L = _lib.lib()
     with torch.cuda.device(x.device):
         _lib.check(L.qa_quant_block(_lib.ptr(x2), _lib.ptr(mean), _lib.ptr(out), _lib.ptr(scales), N, D, blk,
-                                    rows_per_head or N, _lib.cur_stream()), "qa_quant_block")
+                                    rows_per_head or N, ROUNDING[rounding], _lib.cur_stream()), "qa_quant_block")
     return out, scales
 
 
@@ -110,7 +114,7 @@ def k_token_sum(k: torch.Tensor) -> torch.Tensor:
 
 
 def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=2, want_lse32=True,
-                      ring_state=False, state_in=None):
+                      ring_state=False, state_in=None, rounding: str = "trunc"):
     """Fused int8 attention forward over pre-quantised operands (qa_int8_fwd).
     Returns (O fp16 [BH*Sq, D], lse16 [BH*Sq], lse32 or None); with ring_state=True returns the unnormalised
     (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead."""
@@ -132,7 +136,7 @@ def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=1
         _lib.check(L.qa_int8_fwd_state(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk),
                                        _lib.ptr(sv), _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc),
                                        _lib.ptr(m), _lib.ptr(l), _lib.ptr(si[0]), _lib.ptr(si[1]), _lib.ptr(si[2]),
-                                       BH, Sq, Sk, D, Bq, Bkv, nsplit, _lib.cur_stream()), "qa_int8_fwd")
+                                       BH, Sq, Sk, D, Bq, Bkv, nsplit, ROUNDING[rounding], _lib.cur_stream()), "qa_int8_fwd")
     if ring_state:
         return o_acc, m, l
     return O, lse16, lse32
@@ -168,7 +172,8 @@ def cast_f32(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128):
+def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128,
+                      rounding: str = "trunc"):
     """Fused int8 backward over pre-quantised operands (qa_int8_bwd).  Returns (dq, dk, dv) fp16 [BH*S, D]."""
     _need_cuda(q_i8, k_i8, v_i8, do_i8)
     dev = q_i8.device
@@ -184,7 +189,7 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
         with _timed("int8_bwd"):
             _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
                                      _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(rowsum_ws),
-                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _lib.cur_stream()),
+                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, ROUNDING[rounding], _lib.cur_stream()),
                        "qa_int8_bwd")
         _lib.check(L.qa_int8_bwd_finalize(_lib.ptr(dq_ws), _lib.ptr(rowsum_ws), _lib.ptr(k_mean), _lib.ptr(dq), BH, S, D,
                                           _lib.cur_stream()), "qa_int8_bwd_finalize")

@@ -33,11 +33,12 @@ def test_argument_validation_needs_no_gpu():
     from quantizedattention_b200 import _lib
     L = _lib.lib()
     z = ctypes.c_void_p(0)
-    assert L.qa_quant_block(z, z, z, z, 128, 96, 32, 128, z) == -1            # D not in {64,128}
+    assert L.qa_quant_block(z, z, z, z, 128, 96, 32, 128, 0, z) == -1         # D not in {64,128}
     assert b"D must be" in L.qa_last_error()
-    assert L.qa_quant_block(z, z, z, z, 100, 64, 32, 128, z) == -1            # rows not a multiple of blk
-    assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, z) == -1  # Bkv in {32,64,128}
-    assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, z) == -1          # Bq = Bkv = 128
+    assert L.qa_quant_block(z, z, z, z, 100, 64, 32, 128, 0, z) == -1         # rows not a multiple of blk
+    assert L.qa_quant_block(z, z, z, z, 128, 64, 32, 128, 2, z) == -1         # rounding in {0, 1}
+    assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, 0, z) == -1  # Bkv in {32,64,128}
+    assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, 0, z) == -1       # Bq = Bkv = 128
     assert L.qa_bf16_fwd(*([z] * 5), 1, 100, 128, 128, 0, 1, z) == -1         # S % 128
     assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, -1.0, z) == -1  # rescale_tau outside [0, 16]
     assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, 32.0, z) == -1
