@@ -47,6 +47,17 @@ class HostStagedSageAttention:
         dev = self.device
         n_in = 4 if with_grad else 3
         self.hc = hc
+        # chunk schedule: the first H2D and the last D2H cannot overlap anything, so the edge chunks are small
+        # (hc/4, 3hc/4, hc, ..., hc, 3hc/4, hc/4) when there are enough heads for that
+        if hc % 4 == 0 and BH >= 4 * hc:
+            sizes = [hc // 4, 3 * hc // 4] + [hc] * (BH // hc - 2) + [3 * hc // 4, hc // 4]
+        else:
+            sizes = [hc] * (BH // hc)
+        self.sched, h0 = [], 0
+        for nh in sizes:
+            self.sched.append((h0, nh))
+            h0 += nh
+        assert h0 == BH
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.inbuf = [[torch.empty((1, hc, S, D), dtype=torch.float16, device=dev) for _ in range(n_in)] for _ in range(self.slots)]
         # results are copied into persistent staging slots on the compute stream, so every temporary of the attention
@@ -83,7 +94,8 @@ class HostStagedSageAttention:
         self._check_host(*out)
         srcs = [t.view(BH, S, D) for t in ((q, k, v, dO) if with_grad else (q, k, v))]
         dsts = [t.view(BH, S, D) for t in out]
-        n = BH // hc
+        sched = self.sched
+        n = len(sched)
         cur = torch.cuda.current_stream(dev)
         start = torch.cuda.Event()
         start.record(cur)
@@ -97,8 +109,9 @@ class HostStagedSageAttention:
                     if i >= self.slots:
                         self.s_in.wait_event(ev_cmp[i - self.slots])   # the slot's previous reader has finished
                     sp = self._span("h2d", i, self.s_in)
+                    h0, nh = sched[i]
                     for dst, src in zip(self.inbuf[slot], srcs):
-                        dst.view(hc, S, D).copy_(src[i * hc:(i + 1) * hc], non_blocking=True)
+                        dst.view(hc, S, D)[:nh].copy_(src[h0:h0 + nh], non_blocking=True)
                     if sp is not None:
                         sp.record(self.s_in)
                     ev_in[i] = torch.cuda.Event()
@@ -109,7 +122,8 @@ class HostStagedSageAttention:
                 with torch.cuda.stream(self.s_cmp):
                     self.s_cmp.wait_event(ev_in[j])
                     sp = self._span("compute", j, self.s_cmp)
-                    bufs = self.inbuf[slot]
+                    nh = sched[j][1]
+                    bufs = [t[:, :nh] for t in self.inbuf[slot]]
                     if j >= self.slots:
                         self.s_cmp.wait_event(ev_out[j - self.slots])   # the output slot has been copied out
                     if with_grad:
@@ -121,7 +135,7 @@ class HostStagedSageAttention:
                         with torch.no_grad():
                             res = (A.sage_attention_3_int8(*bufs[:3]),)
                     for dst, src in zip(self.outbuf[slot], res):
-                        dst.copy_(src.view(hc, S, D))
+                        dst[:nh].copy_(src.view(nh, S, D))
                     del res
                     if sp is not None:
                         sp.record(self.s_cmp)
@@ -132,8 +146,9 @@ class HostStagedSageAttention:
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(ev_cmp[m])
                     sp = self._span("d2h", m, self.s_out)
+                    h0, nh = sched[m]
                     for dst, src in zip(dsts, self.outbuf[m % self.slots]):
-                        dst[m * hc:(m + 1) * hc].copy_(src, non_blocking=True)
+                        dst[h0:h0 + nh].copy_(src[:nh], non_blocking=True)
                     if sp is not None:
                         sp.record(self.s_out)
                     ev_out[m] = torch.cuda.Event()

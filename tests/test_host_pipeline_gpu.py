@@ -6,7 +6,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("shape,hc", [((2, 4, 256, 64), 2), ((1, 6, 384, 128), 4), ((1, 2, 128, 128), 32)])
+@pytest.mark.parametrize("shape,hc", [((2, 4, 256, 64), 2), ((1, 6, 384, 128), 4), ((1, 2, 128, 128), 32), ((2, 8, 256, 64), 4)])
 def test_host_pipeline_matches_device_api(shape, hc):
     from quantizedattention_b200 import attention_int8 as A
     from quantizedattention_b200.host_pipeline import HostStagedSageAttention
