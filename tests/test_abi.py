@@ -87,3 +87,16 @@ def test_bench_reference_arm_prints_contract_json():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_torch_library_ops_register_without_gpu():
+    """the operator schemas and fake kernels exist on import (shape inference needs no device)."""
+    import torch
+    from quantizedattention_b200 import torch_ops  # noqa: F401
+    assert "Tensor q, Tensor k, Tensor v" in str(torch.ops.qattn.sage_int8_fwd.default._schema)
+    with torch._subclasses.FakeTensorMode():
+        q = torch.empty((2, 4, 256, 128), dtype=torch.float16, device="cuda")
+        out = torch.ops.qattn.sage_int8_fwd(q, q, q, 128, 128, False)
+        assert out[0].shape == (2, 4, 256, 128) and out[3].dtype == torch.int8 and out[6].shape == (2 * 4 * 256 // 128,)
+        O, lse = torch.ops.qattn.flash_bf16_fwd(q, q, q.to(torch.bfloat16), True)
+        assert O.dtype == torch.float32 and lse.shape == (8, 256)
