@@ -44,9 +44,13 @@ int qa_k_token_sum(const void* k_fp16, void* sum_f32, void* workspace, size_t ws
 /* Per-block int8 quantisation, attention_int8.py:178-186 (Q), :188-195 (K), :241-247 (V), :369-374 (dO):
  * scale = fp16(amax|block| / 127); value = trunc(fp16(x / scale)); block = blk rows x D.  Bit-exact with the reference
  * arithmetic.  mean_fp16 != NULL subtracts the per-head mean first (fp16, one rounding): K-smoothing fused in.
- * rounding (here and in qa_int8_fwd / qa_int8_bwd): 0 = truncate toward zero, the reference's `.to(torch.int8)`
- * (attention_int8.py:183); 1 = round half to even, the opt-in accuracy mode (removes the truncation bias; not
- * bit-comparable with the reference by construction). */
+ * rounding: 0 = truncate toward zero, the reference's `.to(torch.int8)` (attention_int8.py:183); 1 = round half to even,
+ * the opt-in accuracy mode (removes the truncation bias; not bit-comparable with the reference by construction).
+ * qa_int8_fwd / qa_int8_bwd take it as bit 0 of their `flags` (QA_FLAG_NEAREST); bit 1 (QA_FLAG_CAUSAL) selects the
+ * strict causal mask of the reference's baseline (key < query, attention_int8.py:465-473; row 0 of a head = uniform
+ * average over all keys), a mode the reference's int8 kernel does not have (Sq == Sk, Bq = Bkv = 128). */
+#define QA_FLAG_NEAREST 1
+#define QA_FLAG_CAUSAL 2
 int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* out_i8, void* scales_fp16, long long n_rows, int D,
                    int blk, int rows_per_head, int rounding, void* stream);
 
@@ -55,14 +59,14 @@ int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* out_i8, void
  * accumulator plus running (m, l) per row for the K/V shard, merged by the caller (sequence-sharded ring KV). */
 int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq_fp16, const void* sk_fp16,
                 const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, void* o_acc_fp32, void* m_out_fp32,
-                void* l_out_fp32, int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int rounding, void* stream);
+                void* l_out_fp32, int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int flags, void* stream);
 
 /* Same kernel, continuing from a running online-softmax state (o_acc_in, m_in, l_in) produced by earlier K/V shards of
  * the ring; all three NULL = fresh state.  In/out state buffers may alias. */
 int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq_fp16, const void* sk_fp16,
                       const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, void* o_acc_fp32, void* m_out_fp32,
                       void* l_out_fp32, const void* o_acc_in_fp32, const void* m_in_fp32, const void* l_in_fp32, int BH,
-                      int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int rounding, void* stream);
+                      int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int flags, void* stream);
 
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;
@@ -79,7 +83,7 @@ int qa_cast_f32(const void* in_f32, void* out, long long n, int out_dtype, void*
 int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq_fp16,
                 const void* sk_fp16, const void* sv_fp16, const void* s_do_fp16, const void* lse_f32,
                 const void* delta_f32, void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
-                int D, int Bq, int Bkv, int rounding, void* stream);
+                int D, int Bq, int Bkv, int flags, void* stream);
 int qa_int8_bwd_finalize(const void* dq_ws_f32, const void* rowsum_ws_f32, const void* k_mean_f16, void* dq_f16, int BH,
                          int S, int D, void* stream);
 

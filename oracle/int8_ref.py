@@ -80,12 +80,17 @@ def _imm(a_i8: torch.Tensor, b_i8: torch.Tensor) -> torch.Tensor:
 # forward -- attention_int8.py:170-257
 # --------------------------------------------------------------------------------------
 def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
-             return_lse32: bool = False, rounding: str = "trunc"):
+             return_lse32: bool = False, rounding: str = "trunc", causal: bool = False):
     """Returns the reference 10-tuple
         (O fp16 [B,H,S,D], lse fp16 [N], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D],
          sq [N/Bq], sk [N/Bkv], sv [N/Bkv], Bq, Bkv)
     per_head=False reproduces the literal flattened attention (LEDGER I-2).
     Every dtype/rounding step follows the table in SURVEY.md 3.1.
+    causal=True (absent in the reference; contract of the CUDA path): the strict mask of the
+    reference's own baseline (key < query, attention_int8.py:465-473) with weight exactly 0; row maxima, P scales and
+    row sums run over the visible keys only; a (row, tile) pair without a visible key contributes nothing; row 0 of a
+    head, which sees no key at all, is the uniform average over ALL keys of the de-quantised V with
+    lse = -128 + log2(S) (LEDGER B-1, what the baseline's finite fill value produces).
     """
     B, H, S, D = q.shape
     N = B * H * S
@@ -115,22 +120,37 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
         skj = sk_g[:, j].view(G, 1, 1).float()
         S32 = acc.to(torch.float32) * sq_rows * skj * qk_scale           # :200
         S16 = S32.to(torch.float16)                                      # :203
+        if causal:
+            assert per_head
+            keep = torch.arange(L)[:, None] > torch.arange(j * Bkv, (j + 1) * Bkv)[None, :]     # strict: key < query
+            S16 = torch.where(keep, S16, torch.tensor(float("-inf"), dtype=torch.float16))
         row_max = torch.amax(S16, -1, keepdim=True)                      # :205
         m_new = torch.max(m, row_max)                                    # :206-209
         P = torch.exp2((S16 - m_new).to(torch.float32))                  # :211-213 (fp16 subtract)
-        l_new = torch.sum(P, -1, keepdim=True)                           # :215
         rescale = torch.exp2((m - m_new).to(torch.float32))              # :217-219
+        sp = torch.exp2((row_max - m_new).to(torch.float32)) / 127       # :232-234
+        if causal:                                                       # (-inf) - (-inf): nothing visible yet / in this tile
+            P = torch.where(keep, P, torch.zeros_like(P))
+            rescale = torch.where(torch.isinf(m_new), torch.ones_like(rescale), rescale)
+        l_new = torch.sum(P, -1, keepdim=True)                           # :215
         m = m_new
         l = l * rescale + l_new                                          # :223
         O = O * rescale                                                  # :225
-        sp = torch.exp2((row_max - m).to(torch.float32)) / 127           # :232-234
-        P_i8 = _to_i8(P / sp, rounding)                                  # :236-237
+        Pq = P / sp
+        if causal:
+            Pq = torch.where(torch.isinf(row_max), torch.zeros_like(Pq), Pq)
+        P_i8 = _to_i8(Pq, rounding)                                      # :236-237
         svj = sv_g[:, j].view(G, 1, 1).float()
         O = O + _imm(P_i8, vg[:, ks]).to(torch.float32) * sp * svj       # :249-250
 
     lse32 = m.squeeze(-1).float() + torch.log2(l).squeeze(-1)
     lse16 = m.squeeze(-1) + torch.log2(l).squeeze(-1).to(torch.float16)  # :252
     O16 = (O / l).to(torch.float16)                                      # :256-257
+    if causal:                                                           # row 0 of every head (LEDGER B-1)
+        v_deq = vg.float() * sv_g.repeat_interleave(Bkv, dim=1)[..., None].float()
+        O16[:, 0] = v_deq.mean(dim=1).to(torch.float16)
+        lse32[:, 0] = -128.0 + math.log2(L)
+        lse16[:, 0] = torch.tensor(-128.0 + math.log2(L), dtype=torch.float16)
     out = (O16.view(B, H, S, D), lse16.reshape(N), q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
     if return_lse32:
         return out + (lse32.reshape(N),)
@@ -174,11 +194,11 @@ def int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bk
     return (O / l).to(torch.float16).reshape(BH * Sq, D), lse16.reshape(-1), lse32.reshape(-1)
 
 
-def sage_forward(q, k, v, Bq=32, Bkv=32, rounding: str = "trunc"):
+def sage_forward(q, k, v, Bq=32, Bkv=32, rounding: str = "trunc", causal: bool = False):
     """Contract version of SageAttention3_Int8_autograd_function.forward
     (attention_int8.py:21-40 with LEDGER I-1): 11-tuple with k_mean [B,H,1,D] in slot 2."""
     km = k_token_mean(k)
-    out = int8_fwd(q, smooth_k(k, km), v, Bq, Bkv, per_head=True, rounding=rounding)
+    out = int8_fwd(q, smooth_k(k, km), v, Bq, Bkv, per_head=True, rounding=rounding, causal=causal)
     return out[:2] + (km,) + out[2:]
 
 
@@ -237,7 +257,8 @@ def quant_tile_fp32(x: torch.Tensor, rounding: str = "trunc"):
     return _to_i8(qv, rounding), s
 
 
-def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv, rounding: str = "trunc"):
+def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv, rounding: str = "trunc",
+                      causal: bool = False):
     """CONTRACT backward (what the CUDA kernel implements; LEDGER I-1,5,6,7,8,9,10,12,15).
 
     Per (b,h); k-tile j, q-tile i:
@@ -251,6 +272,9 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
       dQ[i] += float(dS_i8 k_i8) * s_dS * sk * sm_scale + sm_scale * rowsum(dS) x k_mean
       dK[j] += float(dS_i8^T q_i8) * s_dS * sq * sm_scale
     fp32 accumulation, fp16 outputs.  k_mean: [B,H,1,D] fp16.
+    causal=True: tiles with q-tile < k-tile are skipped, masked P is exactly 0 (so dS is 0 there and the
+    tile-wide amax runs over the visible entries); row 0 of a head attends uniformly to all S keys (LEDGER B-1), which
+    adds dO[0]/S to every dV row and nothing to dQ / dK.
     """
     N, D = q_i8.shape
     B, H, S, _ = O.shape
@@ -280,10 +304,15 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
         kj = kg[:, j]                                              # [G,Bkv,D]
         vj = vg[:, j]
         for i in range(nq):
+            if causal and i * Bq + Bq - 1 <= j * Bkv:                # no (query, key) pair with key < query
+                continue
             qi = qg[:, i]
             acc = _imm(qi, kj.transpose(1, 2))
             S16 = (acc.to(torch.float32) * sqg[:, i, None, None] * skg[:, j, None, None] * qk_scale).to(torch.float16)
             P = torch.exp2(S16.to(torch.float32) - lse32[:, i])
+            if causal:
+                keep = torch.arange(i * Bq, (i + 1) * Bq)[:, None] > torch.arange(j * Bkv, (j + 1) * Bkv)[None, :]
+                P = torch.where(keep, P, torch.zeros_like(P))
             P_i8, sP = quant_tile_fp32(P, rounding)
             dv[:, j] += _imm(P_i8.transpose(1, 2), dO_i8[:, i]).to(torch.float32) * s_dO[:, i, None, None] * sP
             dP = _imm(dO_i8[:, i], vj.transpose(1, 2)).to(torch.float32) * s_dO[:, i, None, None] * svg[:, j, None, None]
@@ -292,5 +321,7 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
             dq[:, i] += _imm(dS_i8, kj).to(torch.float32) * s_dS * skg[:, j, None, None] * sm_scale \
                 + sm_scale * dS.sum(-1, keepdim=True) * km
             dk[:, j] += _imm(dS_i8.transpose(1, 2), qi).to(torch.float32) * s_dS * sqg[:, i, None, None] * sm_scale
+    if causal:                                                     # row 0: uniform over all keys
+        dv = dv + (dO.reshape(G, S, D)[:, :1].float() / S).view(G, 1, 1, D)
     f = lambda t: t.to(torch.float16).view(B, H, S, D)
     return f(dq), f(dk), f(dv)

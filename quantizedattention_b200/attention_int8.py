@@ -55,7 +55,7 @@ def set_quant_rounding(mode: str = "trunc"):
     _CFG["rounding"] = mode
 
 
-def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False):
+def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False, causal: bool = False):
     """Quantise Q/K/V per block and run the fused int8 forward.  Returns the reference 10-tuple
     (O fp16 [B,H,S,D], lse fp16 [N], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv)."""
     batch, head, q_tokens, q_head_dim = q_fp16_input.shape
@@ -73,7 +73,7 @@ def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want
     k_i8, sk = ops.quant_block(k_fp16_input, Bkv, rounding=rnd)
     v_i8, sv = ops.quant_block(v_fp16_input, Bkv, rounding=rnd)
     O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                            nsplit=_CFG["nsplit"], want_lse32=_want_lse32, rounding=rnd)
+                                            nsplit=_CFG["nsplit"], want_lse32=_want_lse32, rounding=rnd, causal=causal)
     out = (O.view(batch, head, q_tokens, D), lse16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
     return out + (lse32,) if _want_lse32 else out
 
@@ -90,7 +90,7 @@ def baseline_pytorch_attention(q, k, v, head_dim, causal):
 
 
 def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8_T, k_mean_bh_fp16, sk_bh_fp16,
-                                 v_bh_int8, sv_bh_fp16, O_input_fp16, lse_input_fp16, Bq: int, Bkv: int):
+                                 v_bh_int8, sv_bh_fp16, O_input_fp16, lse_input_fp16, Bq: int, Bkv: int, causal: bool = False):
     """Quantised backward (attention_int8.py:268-432 under the 8-LEDGER contract).  Same argument order as the
     reference; `k_mean` is the per-head token mean [B,H,1,D]; `lse` may be the fp16 tensor the forward returned
     or an fp32 copy (LEDGER I-15).  Returns (dq, dk, dv) fp16 [B,H,S,D]."""
@@ -114,7 +114,7 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
         km = k_mean_bh_fp16.to(torch.float16).contiguous()
     dq, dk, dv = ops.int8_bwd_prequant(q_bh_int8.contiguous(), k_i8, v_bh_int8.contiguous(), do_i8, sq_bh_fp16,
                                        sk_bh_fp16, sv_bh_fp16, s_do, lse32, delta, km, batch * head, q_tokens, head_dim,
-                                       Bq, Bkv, rounding=_CFG["rounding"])
+                                       Bq, Bkv, rounding=_CFG["rounding"], causal=causal)
     shp = (batch, head, q_tokens, head_dim)
     return dq.view(shp), dk.view(shp), dv.view(shp)
 
@@ -124,7 +124,7 @@ class SageAttention3_Int8_autograd_function(Function):
     (O, lse fp16 [N], k_mean [B,H,1,D], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv)."""
 
     @staticmethod
-    def forward(q_fp16, k_fp16, v_fp16):
+    def forward(q_fp16, k_fp16, v_fp16, causal=False):
         for t in (q_fp16, k_fp16, v_fp16):
             if t.dtype != torch.float16:
                 raise TypeError("int8 attention takes fp16 q, k, v")
@@ -137,7 +137,7 @@ class SageAttention3_Int8_autograd_function(Function):
         k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean_fp16, rows_per_head=k_tokens, rounding=rnd)   # fused k - mean
         v_i8, sv = ops.quant_block(v_fp16, Bkv, rounding=rnd)
         O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                                nsplit=_CFG["nsplit"], want_lse32=True, rounding=rnd)
+                                                nsplit=_CFG["nsplit"], want_lse32=True, rounding=rnd, causal=bool(causal))
         _stash_lse32(lse16, lse32)                                             # picked up by setup_context
         return (O.view(batch, head, q_tokens, D), lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
 
@@ -148,19 +148,24 @@ class SageAttention3_Int8_autograd_function(Function):
         ctx.set_materialize_grads(False)       # do not allocate zero grads for the 10 auxiliary outputs
         lse32 = _LSE32.pop(id(l_bh_fp16), None)
         ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
-        ctx.args = (Bq, Bkv)
+        ctx.args = (Bq, Bkv, bool(inputs[3]) if len(inputs) > 3 else False)
 
     @staticmethod
     def backward(ctx, dO_fp16, *_ignored):
+        Bq, Bkv, causal = ctx.args
+        pad = (None,) * (len(ctx.needs_input_grad) - 3)
         if dO_fp16 is None:
-            return None, None, None
+            return (None, None, None) + pad
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32 = ctx.saved_tensors
-        Bq, Bkv = ctx.args
         dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
-                                                  O_fp16, lse32 if lse32 is not None else l_bh_fp16, Bq, Bkv)
-        return dq, dk, dv
+                                                  O_fp16, lse32 if lse32 is not None else l_bh_fp16, Bq, Bkv, causal=causal)
+        return (dq, dk, dv) + pad
 
 
-def sage_attention_3_int8(q_fp16, k_fp16, v_fp16):
-    """attention_int8.py:434-451: returns O fp16 [B,H,S,D], differentiable w.r.t. q, k, v."""
+def sage_attention_3_int8(q_fp16, k_fp16, v_fp16, causal: bool = False):
+    """attention_int8.py:434-451: returns O fp16 [B,H,S,D], differentiable w.r.t. q, k, v.
+    `causal=True` (absent in the reference's int8 kernel) applies the strict mask of the reference's own
+    `baseline_pytorch_attention(..., causal=True)`: key < query, row 0 of a head = uniform average over all keys."""
+    if causal:
+        return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16, True)[0]
     return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16)[0]

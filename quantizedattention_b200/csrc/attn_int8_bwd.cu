@@ -54,7 +54,7 @@ struct Int8BwdParams {
       p.dbg[(t * 2 + (warp != 0)) * 16 + (slot)] = clock64();                                                 \
   } while (0)
 
-template <int D, int NG, bool RN>
+template <int D, int NG, bool RN, bool CAUSAL>
 __global__ void __launch_bounds__(128 * NG, 1)
 int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -77,6 +77,10 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const bool leader = (tid == 0);
   const int bh = blockIdx.y, j = blockIdx.x;
   const int nq = p.S / 128;
+  // CAUSAL (strict mask, key < query): k-tile j meets the query tiles j .. nq-1; `t` below is the position in
+  // that sequence (pipeline stages and barrier parities), t0 + t the query tile
+  const int t0 = CAUSAL ? j : 0;
+  const int nt = nq - t0;
   const size_t head_row0 = (size_t)bh * p.S;
 
   if (leader) {
@@ -136,7 +140,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_expect_tx(&kv_full, 2 * L::kTile);
     tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
     tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
-    load_qdo(0, 0);
+    load_qdo(t0, 0);
     mbar_wait(&kv_full, 0);
     mbar_wait(&qdo_full[0], 0);
     issue_s(0);
@@ -195,19 +199,20 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   };
 
   constexpr float kPs = 1.0f / 1024.0f;                          // P is carried between the passes as fp16(1024 * P)
-  for (int t = 0; t < nq; ++t) {
+  for (int t = 0; t < nt; ++t) {
     const uint32_t ph = t & 1;
-    const size_t qrow = head_row0 + (size_t)t * 128 + row;
-    const float sq_f = __half2float(p.sq[head_row0 / 128 + t]);
-    const float sdo_f = __half2float(p.s_do[head_row0 / 128 + t]);
+    const int tq = t0 + t;
+    const size_t qrow = head_row0 + (size_t)tq * 128 + row;
+    const float sq_f = __half2float(p.sq[head_row0 / 128 + tq]);
+    const float sdo_f = __half2float(p.s_do[head_row0 / 128 + tq]);
     const float lse = p.lse[qrow];
     const float dlt = p.delta[qrow];
     const float c_s = sq_f * sk_f * p.qk_scale;
     const float c_dp = sdo_f * sv_f;
     QA_TLB(0);
-    if (leader && t + 1 < nq) {                                    // next Q / dO tile: its stage was last read by dV/dK of t-1
+    if (leader && t + 1 < nt) {                                    // next Q / dO tile: its stage was last read by dV/dK of t-1
       if (t > 0) mbar_wait(&parts_full, (t - 1) & 1);
-      load_qdo(t + 1, (t + 1) & 1);
+      load_qdo(tq + 1, (t + 1) & 1);
     }
     mbar_wait(&sd_full, ph);
     tc_fence_after();
@@ -220,6 +225,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float2 rs2acc = make_float2(0.f, 0.f);
     const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(10.0f - lse, 10.0f - lse);
     const float2 cdp2 = make_float2(c_dp * kPs, c_dp * kPs), ndlt2 = make_float2(-dlt * kPs, -dlt * kPs);
+    auto pass1 = [&](auto masked) {                                // masked: the diagonal tile of a causal head
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
       uint32_t r[16], r2[16];
@@ -230,7 +236,12 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int c = 0; c < 16; c += 2) {
         const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cs2));
         const float2 e = __fadd2_rn(__half22float2(h), nlse2);
-        const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));               // 1024 * P
+        float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));                     // 1024 * P
+        if (decltype(masked)::value) {                                 // strict causal: keep key < query (same tile: col < row)
+          const int col = half * CW + ch * 16 + c;
+          if (col >= row) pp.x = 0.f;
+          if (col + 1 >= row) pp.y = 0.f;
+        }
         const __half2 pr = __float22half2_rn(pp);
         pk[ch * 8 + c / 2] = pr;
         amax_ph = __hmax2(amax_ph, pr);
@@ -239,6 +250,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         rs2acc = __fadd2_rn(rs2acc, d);
       }
     }
+    };
+    if (CAUSAL && t == 0) pass1(std::true_type{}); else pass1(std::false_type{});
     amax_p = fmaxf(__low2float(amax_ph), __high2float(amax_ph));                       // of the rounded 1024 * P
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -263,7 +276,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (leader) {
       tc_fence_after();
       if (t > 0) issue_dq((t - 1) & 1);
-      if (t + 1 < nq) {                                            // S of the next tile: everybody is past pass 1
+      if (t + 1 < nt) {                                            // S of the next tile: everybody is past pass 1
         mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
         issue_s((t + 1) & 1);
       }
@@ -333,8 +346,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     QA_TLB(10);
     if (leader) {
       tc_fence_after();
-      if (t > 0) reduce_dq(t - 1);
-      if (t + 1 < nq) issue_dp((t + 1) & 1);
+      if (t > 0) reduce_dq(tq - 1);
+      if (t + 1 < nt) issue_dp((t + 1) & 1);
       QA_TLB(11);
       issue_dv_dk(t & 1, ph);
     }
@@ -344,20 +357,20 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     c_dq_prev = sdS * sk_f * p.sm_scale;
   }
   // ---- pipeline tail: last tile's dV / dK / dQ
-  mbar_wait(&parts_full, (nq - 1) & 1);
+  mbar_wait(&parts_full, (nt - 1) & 1);
   tc_fence_after();
   drain_dv_dk(c_dv_prev, c_dk_prev);
   tc_fence_before();
   if (leader) tma_store_wait_read();
   named_bar_sync(1, NT);
-  if (leader) { tc_fence_after(); issue_dq((nq - 1) & 1); }
-  mbar_wait(&dq_full, (nq - 1) & 1);
+  if (leader) { tc_fence_after(); issue_dq((nt - 1) & 1); }
+  mbar_wait(&dq_full, (nt - 1) & 1);
   tc_fence_after();
   drain_dq(c_dq_prev);
   fence_proxy_async_smem();
   tc_fence_before();
   named_bar_sync(2, NT);
-  if (leader) { reduce_dq(nq - 1); tma_store_wait_all(); }
+  if (leader) { reduce_dq(nq - 1); tma_store_wait_all(); }   // the last query tile, causal or not
   // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
   const size_t krow = head_row0 + (size_t)j * 128 + row;
   __half* dk_dst = p.dk + krow * D + half * DH;
@@ -382,7 +395,29 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
-template <int D, int NG, bool RN = false>
+// Causal row 0 of every head attends uniformly to all S keys (LEDGER B-1): dV[k] += dO[0] / S for every key k; dQ and
+// dK get nothing from it (its P is exactly 0 inside the fused kernel).  dO[0] is taken de-quantised (do_i8 * s_dO).
+template <int D>
+__global__ void __launch_bounds__(256) int8_bwd_row0_fixup_kernel(const int8_t* __restrict__ do_i8, const __half* __restrict__ s_do,
+                                                                  __half* dv, int S) {
+  const int bh = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;                 // one 8-element vector of dV[bh]
+  if (i >= S * (D / 8)) return;
+  const int d0 = (i % (D / 8)) * 8;
+  const float c = __half2float(s_do[(size_t)bh * (S / 128)]) / (float)S;
+  const int8_t* src = do_i8 + (size_t)bh * S * D + d0;
+  uint4* dst = reinterpret_cast<uint4*>(dv + (size_t)bh * S * D) + i;
+  uint4 v = *dst;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    h[e] = __floats2half2_rn(fmaf((float)src[2 * e], c, f.x), fmaf((float)src[2 * e + 1], c, f.y));
+  }
+  *dst = v;
+}
+
+template <int D, int NG, bool RN = false, bool CAUSAL = false>
 static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
                            const Int8BwdParams& p, int BH, cudaStream_t st) {
   using L = Int8BwdSmem<D>;
@@ -399,7 +434,7 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   uint64_t strq[1] = {(uint64_t)D * 4};
   uint32_t boxq[2] = {32, 128};
   if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
-  auto kern = int8_bwd_kernel<D, NG, RN>;
+  auto kern = int8_bwd_kernel<D, NG, RN, CAUSAL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.S / 128, BH);
@@ -424,8 +459,10 @@ extern "C" int qa_debug_set_int8_bwd_timeline(void* buf) {
 extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
                            const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
                            void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
-                           int Bq, int Bkv, int rounding, void* stream) {
-  if (rounding != 0 && rounding != 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: rounding must be 0 (toward zero) or 1 (nearest)");
+                           int Bq, int Bkv, int flags, void* stream) {
+  if (flags & ~(QA_FLAG_NEAREST | QA_FLAG_CAUSAL)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: unknown flag bits");
+  const int rounding = (flags & QA_FLAG_NEAREST) ? 1 : 0;
+  const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: D must be 64 or 128");
   if (Bq != 128 || Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: Bq = Bkv = 128 required");
   if (S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S must be a multiple of 128");
@@ -439,6 +476,16 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   cudaStream_t st = (cudaStream_t)stream;
   const char* env = getenv("QA_INT8_BWD_NG");
   const int ng = env ? atoi(env) : 2;   // 2 column groups (8 warps, 255 regs) measured faster than 4 (16 warps)
+  if (causal) {                                                   // instantiated for the default shape only
+    if (rounding) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: causal is built for truncation mode");
+    int rc = D == 128 ? launch_int8_bwd<128, 2, false, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+                      : launch_int8_bwd<64, 2, false, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
+    if (rc) return rc;
+    dim3 grid((unsigned)((S * (D / 8) + 255) / 256), (unsigned)BH);
+    if (D == 128) int8_bwd_row0_fixup_kernel<128><<<grid, 256, 0, st>>>((const int8_t*)do_i8, p.s_do, p.dv, S);
+    else int8_bwd_row0_fixup_kernel<64><<<grid, 256, 0, st>>>((const int8_t*)do_i8, p.s_do, p.dv, S);
+    return qa_check_launch("qa_int8_bwd(causal row 0)");
+  }
   if (rounding == 1)                                              // accuracy mode: instantiated for the default shape only
     return D == 128 ? launch_int8_bwd<128, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
                     : launch_int8_bwd<64, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);

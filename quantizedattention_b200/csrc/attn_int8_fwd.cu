@@ -59,7 +59,7 @@ struct Int8FwdParams {
       p.dbg[j * 16 + (slot)] = clock64();                                                             \
   } while (0)
 
-template <int D, int NSPLIT, int STAGES, int BN, bool RN>
+template <int D, int NSPLIT, int STAGES, int BN, bool RN, bool CAUSAL>
 __global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
 int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
@@ -83,8 +83,9 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ __half m_fin[kBM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y, q0 = blockIdx.x * kBM;
-  const int nk = p.Sk / kBN;
+  // CAUSAL (strict mask, key < query): a query tile visits the k-tiles up to its own; heaviest tiles first
+  const int bh = blockIdx.y, q0 = (CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * kBM;
+  const int nk = CAUSAL ? min(p.Sk / kBN, q0 / kBN + 1) : p.Sk / kBN;
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -132,19 +133,28 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---- pass 1: int32 -> fp16 logits (packed), row max
       __half2 sh[NC / 2];
       __half2 mx2 = __float2half2_rn(-INFINITY);
+      auto pass1 = [&](auto masked) {                              // masked: the diagonal tile of a causal head
 #pragma unroll
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
-        tmem_ld_wait();
+        for (int ch = 0; ch < NC / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {                            // packed fp32x2 multiply (FMUL2): half the issue slots
-          const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
-          __half2 h = __float22half2_rn(a);
-          sh[ch * 16 + i] = h;
-          mx2 = __hmax2(mx2, h);
+          for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
+            const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
+            __half2 h = __float22half2_rn(a);
+            if (decltype(masked)::value) {                         // strict causal: keep key < query (same tile: col < row)
+              const int col = c0 + ch * 32 + 2 * i;
+              const __half ninf = __float2half_rn(-INFINITY);
+              if (col >= row) h = __halves2half2(ninf, __high2half(h));
+              if (col + 1 >= row) h = __halves2half2(__low2half(h), ninf);
+            }
+            sh[ch * 16 + i] = h;
+            mx2 = __hmax2(mx2, h);
+          }
         }
-      }
+      };
+      if (CAUSAL && j * kBN == q0) pass1(std::true_type{}); else pass1(std::false_type{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);        // S[b] is in registers: the MMA warp may overwrite it
@@ -156,9 +166,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         rmax = __hmax(rmax, xmax[b][split ^ 1][row]);
       }
       const __half m_new = __hmax(m16, rmax);
-      const float rescale = ex2_approx(__half2float(__hsub(m16, m_new)));       // fp16 subtraction (:217-219)
-      const float sp_e = ex2_approx(__half2float(__hsub(rmax, m_new)));         // (:232-234) sp = sp_e / 127
-      const float inv_sp = __fdividef(127.0f, sp_e);
+      float rescale = ex2_approx(__half2float(__hsub(m16, m_new)));             // fp16 subtraction (:217-219)
+      float sp_e = ex2_approx(__half2float(__hsub(rmax, m_new)));               // (:232-234) sp = sp_e / 127
+      float inv_sp = __fdividef(127.0f, sp_e);
+      if (CAUSAL) {                                   // a row may have no visible key in this tile / so far: (-inf) - (-inf)
+        if (__hisinf(m_new)) rescale = 1.0f;
+        if (__hisinf(rmax)) { sp_e = 0.f; inv_sp = 0.f; }
+      }
       m16 = m_new;
       // ---- hand (rescale, sp*sv) to the correction warps
       if (split == 0) {
@@ -171,7 +185,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (warp == 0) QA_TL(3);
       mbar_wait(&p_empty[b], ph ^ 1);
       if (warp == 0) QA_TL(4);
-      const __half2 m2 = __half2half2(m_new);
+      const __half2 m2 = __half2half2((CAUSAL && __hisinf(m_new)) ? __float2half_rn(0.f) : m_new);
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
       const uint32_t prow = smem_u32(smem) + L::off_p + b * L::kPBytes;
@@ -364,7 +378,39 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 8 * NSPLIT + 1) tmem_dealloc<512>(tbase);
 }
 
-template <int D, int NSPLIT, int STAGES, int BN, bool RN = false>
+// Causal row 0 of every head sees no key: it is the uniform average over ALL keys of the de-quantised V (LEDGER B-1:
+// what the reference's baseline computes with its finite fill value), lse = -128 + log2(S).
+template <int D>
+__global__ void __launch_bounds__(512) int8_row0_fixup_kernel(const int8_t* __restrict__ v_i8, const __half* __restrict__ sv,
+                                                              __half* O, __half* lse16, float* lse32, int S) {
+  constexpr int NSTR = 512 / D;                                 // key stripes
+  __shared__ float part[NSTR][D];
+  const int bh = blockIdx.x, d = threadIdx.x % D, st = threadIdx.x / D;
+  const int ntile = S / 128;
+  float acc = 0.f;
+  for (int t = st; t < ntile; t += NSTR) {
+    const int8_t* vt = v_i8 + ((size_t)bh * S + (size_t)t * 128) * D + d;
+    int sum = 0;
+#pragma unroll 8
+    for (int r = 0; r < 128; ++r) sum += vt[(size_t)r * D];
+    acc = fmaf((float)sum, __half2float(sv[(size_t)bh * ntile + t]), acc);
+  }
+  part[st][d] = acc;
+  __syncthreads();
+  if (st == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NSTR; ++i) tot += part[i][d];
+    O[(size_t)bh * S * D + d] = __float2half_rn(tot / (float)S);
+    if (d == 0) {
+      const float l = -128.0f + log2f((float)S);
+      lse16[(size_t)bh * S] = __float2half_rn(l);
+      if (lse32 != nullptr) lse32[(size_t)bh * S] = l;
+    }
+  }
+}
+
+template <int D, int NSPLIT, int STAGES, int BN, bool RN = false, bool CAUSAL = false>
 static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const Int8FwdParams& p, int BH,
                            cudaStream_t st) {
   using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
@@ -378,7 +424,7 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
   if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
   if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
-  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN>;
+  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN, CAUSAL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / kBM, BH);
@@ -404,8 +450,10 @@ extern "C" int qa_debug_set_int8_fwd_timeline(void* buf) {
 extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
                                  const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
                                  const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int D,
-                                 int Bq, int Bkv, int nsplit, int rounding, void* stream) {
-  if (rounding != 0 && rounding != 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: rounding must be 0 (toward zero) or 1 (nearest)");
+                                 int Bq, int Bkv, int nsplit, int flags, void* stream) {
+  if (flags & ~(QA_FLAG_NEAREST | QA_FLAG_CAUSAL)) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: unknown flag bits");
+  const int rounding = (flags & QA_FLAG_NEAREST) ? 1 : 0;
+  const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: D must be 64 or 128");
   if (Bkv != 32 && Bkv != 64 && Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 32, 64 or 128");
   if (Bq != 32 && Bq != 64 && Bq != 128 && Bq != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bq must be 32/64/128/256");
@@ -421,6 +469,16 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   p.dbg = (long long*)g_int8_fwd_dbg;
   cudaStream_t st = (cudaStream_t)stream;
+  if (causal) {                                                  // instantiated for the tuned tile only
+    if (Bkv != 128 || Bq != 128 || nsplit != 2 || rounding || Sq != Sk || o_acc != nullptr || o_acc_in != nullptr)
+      return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: causal needs Sq == Sk, Bq = Bkv = 128, nsplit = 2, truncation, no ring state");
+    int rc = D == 128 ? launch_int8_fwd<128, 2, 3, 128, false, true>(q_i8, k_i8, v_i8, p, BH, st)
+                      : launch_int8_fwd<64, 2, 4, 128, false, true>(q_i8, k_i8, v_i8, p, BH, st);
+    if (rc) return rc;
+    if (D == 128) int8_row0_fixup_kernel<128><<<BH, 512, 0, st>>>((const int8_t*)v_i8, p.sv, p.O, p.lse16, p.lse32, Sq);
+    else int8_row0_fixup_kernel<64><<<BH, 512, 0, st>>>((const int8_t*)v_i8, p.sv, p.O, p.lse16, p.lse32, Sq);
+    return qa_check_launch("qa_int8_fwd(causal row 0)");
+  }
   if (Bkv == 128) {
     if (rounding == 1) {                                         // accuracy mode: instantiated for the tuned tile only
       if (nsplit != 2) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nearest rounding needs nsplit = 2");
@@ -441,7 +499,7 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
 
 extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
                            const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
-                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int rounding, void* stream) {
+                           int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int flags, void* stream) {
   return qa_int8_fwd_state(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, nullptr, nullptr, nullptr, BH,
-                           Sq, Sk, D, Bq, Bkv, nsplit, rounding, stream);
+                           Sq, Sk, D, Bq, Bkv, nsplit, flags, stream);
 }

@@ -75,6 +75,11 @@ def k_mean(k: torch.Tensor) -> torch.Tensor:
 
 
 ROUNDING = {"trunc": 0, "nearest": 1}       # int8 rounding of the quantisers: the reference truncates (LEDGER I-3)
+FLAG_NEAREST, FLAG_CAUSAL = 1, 2            # `flags` of qa_int8_fwd / qa_int8_bwd (include/qattn.h)
+
+
+def _flags(rounding: str, causal: bool) -> int:
+    return (FLAG_NEAREST if ROUNDING[rounding] else 0) | (FLAG_CAUSAL if causal else 0)
 
 
 def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, rows_per_head: int | None = None,
@@ -114,7 +119,7 @@ def k_token_sum(k: torch.Tensor) -> torch.Tensor:
 
 
 def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=2, want_lse32=True,
-                      ring_state=False, state_in=None, rounding: str = "trunc"):
+                      ring_state=False, state_in=None, rounding: str = "trunc", causal: bool = False):
     """Fused int8 attention forward over pre-quantised operands (qa_int8_fwd).
     Returns (O fp16 [BH*Sq, D], lse16 [BH*Sq], lse32 or None); with ring_state=True returns the unnormalised
     (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead."""
@@ -136,7 +141,7 @@ def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=1
         _lib.check(L.qa_int8_fwd_state(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk),
                                        _lib.ptr(sv), _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc),
                                        _lib.ptr(m), _lib.ptr(l), _lib.ptr(si[0]), _lib.ptr(si[1]), _lib.ptr(si[2]),
-                                       BH, Sq, Sk, D, Bq, Bkv, nsplit, ROUNDING[rounding], _lib.cur_stream()), "qa_int8_fwd")
+                                       BH, Sq, Sk, D, Bq, Bkv, nsplit, _flags(rounding, causal), _lib.cur_stream()), "qa_int8_fwd")
     if ring_state:
         return o_acc, m, l
     return O, lse16, lse32
@@ -173,7 +178,7 @@ def cast_f32(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128,
-                      rounding: str = "trunc"):
+                      rounding: str = "trunc", causal: bool = False):
     """Fused int8 backward over pre-quantised operands (qa_int8_bwd).  Returns (dq, dk, dv) fp16 [BH*S, D]."""
     _need_cuda(q_i8, k_i8, v_i8, do_i8)
     dev = q_i8.device
@@ -189,7 +194,7 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
         with _timed("int8_bwd"):
             _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
                                      _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(rowsum_ws),
-                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, ROUNDING[rounding], _lib.cur_stream()),
+                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _flags(rounding, causal), _lib.cur_stream()),
                        "qa_int8_bwd")
         _lib.check(L.qa_int8_bwd_finalize(_lib.ptr(dq_ws), _lib.ptr(rowsum_ws), _lib.ptr(k_mean), _lib.ptr(dq), BH, S, D,
                                           _lib.cur_stream()), "qa_int8_bwd_finalize")

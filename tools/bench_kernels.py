@@ -73,6 +73,29 @@ def jvp(B=16, H=16, S=4096, D=64):
     print(json.dumps(res, indent=1))
 
 
+def int8_causal(BH=256, S=8192, D=128):
+    """Causal int8 forward + backward kernels; ops counted as half of the dense convention."""
+    torch.manual_seed(0)
+    q, k, v, dO = [torch.randn(BH, S, D, device="cuda", dtype=torch.float16) for _ in range(4)]
+    qi, sq = ops.quant_block(q, 128); ki, sk = ops.quant_block(k, 128); vi, sv = ops.quant_block(v, 128)
+    doi, sdo = ops.quant_block(dO, 128)
+    res = {}
+    for causal in (False, True):
+        f = 0.5 if causal else 1.0
+        fwd = lambda: ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D, causal=causal)
+        med, _ = timeit(fwd)
+        O, lse16, lse32 = fwd()
+        delta = ops.bwd_delta(dO.view(-1, D), O)
+        ops.TIMING = []
+        timeit(lambda: ops.int8_bwd_prequant(qi, ki, vi, doi, sq, sk, sv, sdo, lse32, delta, None, BH, S, D, causal=causal))
+        kt = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "int8_bwd")
+        ops.TIMING = None
+        kms = kt[len(kt) // 2]
+        res["causal" if causal else "dense"] = {"fwd_ms": med, "fwd_TOPS": f * 4 * BH * S * S * D / med / 1e9,
+                                                "bwd_ms": kms, "bwd_TOPS": f * 10 * BH * S * S * D / kms / 1e9}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
     args = [int(a) for a in sys.argv[2:]]
     globals()[sys.argv[1]](*args)
