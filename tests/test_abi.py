@@ -100,3 +100,12 @@ def test_torch_library_ops_register_without_gpu():
         assert out[0].shape == (2, 4, 256, 128) and out[3].dtype == torch.int8 and out[6].shape == (2 * 4 * 256 // 128,)
         O, lse = torch.ops.qattn.flash_bf16_fwd(q, q, q.to(torch.bfloat16), True)
         assert O.dtype == torch.float32 and lse.shape == (8, 256)
+
+
+def test_tools_and_entry_points_compile():
+    """Every script that is only ever run on the GPU box at least parses here."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]:
+        py_compile.compile(f, doraise=True)

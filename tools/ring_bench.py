@@ -48,7 +48,7 @@ def main():
            "TOPS_total": 4.0 * B * H * S * S * D / (t.item() * 1e-3) / 1e12}
     if mode == "check":
         ref = A.SageAttention3_Int8_autograd_function.forward(q.to(dev), k.to(dev), v.to(dev))
-            err = (out[0].float() - ref[0][:, :, rank * Sl:(rank + 1) * Sl].float()).abs().max()
+        err = (out[0].float() - ref[0][:, :, rank * Sl:(rank + 1) * Sl].float()).abs().max()
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         res["max_abs_vs_single_device"] = err.item()
         res["ok"] = bool(err.item() < 6e-3)
