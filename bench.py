@@ -154,6 +154,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        try:                                    # pin this rank to the CPUs next to its GPU: the pinned host buffers of the
+            import pynvml                       # e2e path are then first-touched on the GPU's NUMA node
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:  # noqa: BLE001
+            pass
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
