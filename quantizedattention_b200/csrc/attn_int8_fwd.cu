@@ -26,12 +26,10 @@ struct Int8FwdSmem {
   static constexpr int kQBytes = kBM * D;
   static constexpr int kKBytes = BN * D;
   static constexpr int kVBytes = BN * D;
-  static constexpr int kPBytes = kBM * 128;      // P rows keep a 128-byte pitch (128B swizzle); BN bytes of each row are used
   static constexpr int off_q = 0;
   static constexpr int off_k = off_q + kQBytes;
   static constexpr int off_v = off_k + STAGES * kKBytes;
-  static constexpr int off_p = off_v + STAGES * kVBytes;
-  static constexpr int off_end = off_p + 2 * kPBytes;
+  static constexpr int off_end = off_v + STAGES * kVBytes;
   static constexpr int total = off_end + 1024;   // + alignment slack
 };
 
@@ -75,7 +73,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  __shared__ uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2], o_full[2], o_empty[2], sc_full[2], sc_empty[2], fin_full;
+  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_empty[2], sc_full[2], sc_empty[2], fin_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float2 row_sc[2][kBM];          // per tile parity: (rescale, sp*sv) per row
   __shared__ __half xmax[2][2][kBM];         // NSPLIT == 2: row-max exchange between the two column groups
@@ -91,8 +89,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], kSoftWarps);
-      mbar_init(&p_full[b], kSoftWarps); mbar_init(&p_empty[b], 1);
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], kSoftWarps);
       mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], kSoftWarps);
       mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], kSoftWarps);
     }
@@ -155,9 +153,6 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       };
       if (CAUSAL && j * kBN == q0) pass1(std::true_type{}); else pass1(std::false_type{});
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);        // S[b] is in registers: the MMA warp may overwrite it
       __half rmax = __hmax(__low2half(mx2), __high2half(mx2));
       if (warp == 0) QA_TL(2);
       if (NSPLIT == 2) {
@@ -181,24 +176,24 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&sc_full[b]);
       }
-      // ---- pass 2: P = exp2(S16 - m), l += sum(P), P_i8 = trunc(P / sp) -> swizzled smem (K-major, 128 B rows)
+      // ---- pass 2: P = exp2(S16 - m), l += sum(P), P_i8 = trunc(P / sp) -> written back to TMEM over the S columns
+      //      (4 int8 per column): the P V MMA takes its A operand straight from TMEM (no shared-memory round trip,
+      //      no proxy fence, no second buffer to wait for - the S buffer is ours until that MMA has been issued)
       if (warp == 0) QA_TL(3);
-      mbar_wait(&p_empty[b], ph ^ 1);
       if (warp == 0) QA_TL(4);
       const __half2 m2 = __half2half2((CAUSAL && __hisinf(m_new)) ? __float2half_rn(0.f) : m_new);
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
-      const uint32_t prow = smem_u32(smem) + L::off_p + b * L::kPBytes;
       {                                                            // RN: the rounding mode is an FFMA2 modifier
 #pragma unroll
-        for (int g = 0; g < NC / 16; ++g) {
-          uint32_t w[4];
+        for (int g = 0; g < NC / 32; ++g) {
+          uint32_t w[8];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
+          for (int q4 = 0; q4 < 8; ++q4) {
             uint32_t bytes[4];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
-              const float2 f = __half22float2(__hsub2(sh[g * 8 + q4 * 2 + h2], m2));    // fp16 subtraction (:211-213)
+              const float2 f = __half22float2(__hsub2(sh[g * 16 + q4 * 2 + h2], m2));   // fp16 subtraction (:211-213)
               const float2 pp = make_float2(ex2_approx(f.x), ex2_approx(f.y));
               ls2 = __fadd2_rn(ls2, pp);
               // low byte of the biased sum = trunc(P/sp) (reference) or its nearest-even rounding (accuracy mode)
@@ -208,12 +203,12 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
           }
-          const uint32_t off = swz128(row, c0 + g * 16);
-          sts128(prow + off, w[0], w[1], w[2], w[3]);
+          tmem_st8(lane_addr + b * 128 + c0 / 4 + g * 8, w);
         }
       }
+      tmem_st_wait();
       l = l * rescale + (ls2.x + ls2.y);
-      fence_proxy_async_smem();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
       if (warp == 0) QA_TL(5);
@@ -331,7 +326,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc_qk = umma_idesc(2, 1, 1, 0, 0, kBM, kBN);          // s32 += s8 x s8, both K-major
       constexpr uint32_t idesc_pv = umma_idesc(2, 1, 1, 0, 1, kBM, D);            // B = V: MN-major
       const uint32_t q_addr = smem_u32(smem + L::off_q);
-      auto issue_pv = [&](int t) {
+      auto issue_pv = [&](int t) {                                 // Opart[b] = P_t V_t, P from TMEM (S[b] columns)
         const int b = t & 1, s = t % STAGES;
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(&v_full[s], (t / STAGES) & 1);
@@ -339,26 +334,19 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&p_full[b], ph);
         tc_fence_after();
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < 64) p.dbg[t * 16 + 11] = clock64();   // PV issue
-        const uint32_t p_addr = smem_u32(smem + L::off_p + b * L::kPBytes);
         const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kVBytes);
 #pragma unroll
         for (int k = 0; k < kBN / 32; ++k) {
-          const uint64_t ad = umma_smem_desc(p_addr + k * 32, 16, 1024, kSwz128);
           const uint64_t bd = umma_smem_desc(v_addr + k * 32 * D, 16, kSboQK, kLayoutQK);
-          umma_i8_ss(tbase + 256 + b * 128, ad, bd, idesc_pv, k > 0);
+          umma_i8_ts(tbase + 256 + b * 128, tbase + b * 128 + k * 8, bd, idesc_pv, k > 0);
         }
         umma_commit(&o_full[b]);
         umma_commit(&v_empty[s]);
-        umma_commit(&p_empty[b]);
       };
-      mbar_wait(&q_full, 0);
-      for (int j = 0; j < nk; ++j) {
+      auto issue_qk = [&](int j) {                                 // S[b] = Q K_j^T
         const int b = j & 1, s = j % STAGES;
         mbar_wait(&k_full[s], (j / STAGES) & 1);
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) p.dbg[j * 16 + 9] = clock64();    // K landed
-        mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) p.dbg[j * 16 + 10] = clock64();   // QK issue
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) { p.dbg[j * 16 + 9] = clock64(); p.dbg[j * 16 + 10] = clock64(); }
         const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
 #pragma unroll
         for (int k = 0; k < D / 32; ++k) {
@@ -368,9 +356,15 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         umma_commit(&s_full[b]);
         umma_commit(&k_empty[s]);
-        if (j > 0) issue_pv(j - 1);
+      };
+      mbar_wait(&q_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (nk > 1) issue_qk(1);
+      for (int j = 0; j < nk; ++j) {
+        issue_pv(j);
+        if (j + 2 < nk) issue_qk(j + 2);     // behind P V in the in-order pipe: S[b] is rewritten only after P_j was consumed
       }
-      issue_pv(nk - 1);
     }
   }
   tc_fence_before();
