@@ -22,12 +22,10 @@ struct JvpSmem {
   static constexpr int kTileQ = 128 * D * 2;            // Q / tQ tile (128 rows)
   static constexpr int kTile = BN * D * 2;              // K / tK / V / tV tile (BN rows)
   static constexpr int kKAtom = BN * 128;               // one 128-byte column of a BN-row tile
-  static constexpr int kPBytes = 128 * BN * 2;
   static constexpr int off_q = 0;                       // Q, tQ
   static constexpr int off_k = off_q + 2 * kTileQ;      // 2 stages x (K, tK)
   static constexpr int off_v = off_k + 4 * kTile;       // 1 stage  x (V, tV)
-  static constexpr int off_p = off_v + 2 * kTile;       // P, H
-  static constexpr int total = off_p + 2 * kPBytes + 1024;
+  static constexpr int total = off_v + 2 * kTile + 1024;
 };
 
 struct JvpParams {
@@ -53,6 +51,10 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   constexpr int kProdWarp = kSoftWarps + 4;
   constexpr int kMmaWarp = kSoftWarps + 5;
   constexpr int kDAtoms = D / 64;
+  // TMEM: S [0,BN)  tS [128,128+BN)  O [256,256+D)  AB [256+D,256+2D); P / H (BN/2 columns each) use what is left:
+  // D = 64 (BN = 128): [384,448) / [448,512);  D = 128 (BN = 64): [64,96) / [192,224)
+  constexpr uint32_t kPCol = (D == 64) ? 384 : 64, kHCol = (D == 64) ? 448 : 192;
+  static_assert((D == 64 && BN == 128) || (D == 128 && BN == 64), "TMEM column plan");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty;
@@ -121,19 +123,19 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
       mbar_wait(&p_empty, ph ^ 1);
       float lsum = 0.f, hsum = 0.f;
-      uint8_t* pbase = smem + L::off_p;
-      uint8_t* hbase = smem + L::off_p + L::kPBytes;
+      // P and H = P * tS (bf16, two per column) go to spare TMEM columns and are consumed from there as the A operands
+      // of the three accumulating MMAs (TS mode): no swizzled shared-memory stores, no proxy fence
 #pragma unroll
       for (int ch = 0; ch < NC / 32; ++ch) {
         uint32_t rt[32];
         tmem_ld32(lane_addr + 128 + c0 + ch * 32, rt);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t wp[4], wh[4];
+        for (int g = 0; g < 2; ++g) {
+          uint32_t wp[8], wh[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = g * 8 + e * 2;
+          for (int e = 0; e < 8; ++e) {
+            const int i = g * 16 + e * 2;
             const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[ch * 32 + i]), p.qk_scale, -m_new));        // :160-161
             const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[ch * 32 + i + 1]), p.qk_scale, -m_new));
             const float h0 = p0 * (__uint_as_float(rt[i]) * p.sm_scale);                           // :153, :176
@@ -143,16 +145,15 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             wp[e] = jpack_bf16(p0, p1);
             wh[e] = jpack_bf16(h0, h1);
           }
-          const int col = c0 + ch * 32 + g * 8;
-          const uint32_t off = (uint32_t)(col >> 6) * kJAtom + swz128(row, (col & 63) * 2);
-          sts128(smem_u32(pbase) + off, wp[0], wp[1], wp[2], wp[3]);
-          sts128(smem_u32(hbase) + off, wh[0], wh[1], wh[2], wh[3]);
+          const int col = (c0 + ch * 32 + g * 16) / 2;            // two keys per TMEM column
+          tmem_st8(lane_addr + kPCol + col, wp);
+          tmem_st8(lane_addr + kHCol + col, wh);
         }
       }
+      tmem_st_wait();
       tc_fence_before();
       l = l * resc + lsum;                                        // :165
       racc = racc * resc + hsum;                                  // :178
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&s_empty); mbar_arrive(&p_full); }
     }
@@ -250,7 +251,6 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc(1, 1, 1, 0, 0, 128, BN);         // bf16 x bf16 -> f32, K-major
       constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // B MN-major
       const uint32_t q_addr = smem_u32(smem + L::off_q), tq_addr = q_addr + L::kTileQ;
-      const uint32_t p_addr = smem_u32(smem + L::off_p), h_addr = p_addr + L::kPBytes;
       const uint32_t v_addr = smem_u32(smem + L::off_v), tv_addr = v_addr + L::kTile;
       auto issue_pv = [&](int t) {
         const uint32_t ph = t & 1;
@@ -260,14 +260,11 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
-          const uint32_t ao = (k >> 2) * kJAtom + (k & 3) * 32;
-          const uint64_t pd = umma_smem_desc(p_addr + ao, 16, 1024, kSwz128);
-          const uint64_t hd = umma_smem_desc(h_addr + ao, 16, 1024, kSwz128);
           const uint64_t vd = umma_smem_desc(v_addr + k * 2048, L::kKAtom, 1024, kSwz128);
           const uint64_t tvd = umma_smem_desc(tv_addr + k * 2048, L::kKAtom, 1024, kSwz128);
-          umma_f16_ss(tbase + 256, pd, vd, idesc_pv, (t > 0) || (k > 0));       // O  += P V
-          umma_f16_ss(tbase + 256 + D, pd, tvd, idesc_pv, (t > 0) || (k > 0));  // AB += P tV
-          umma_f16_ss(tbase + 256 + D, hd, vd, idesc_pv, 1);                    //     + H V
+          umma_f16_ts(tbase + 256, tbase + kPCol + k * 8, vd, idesc_pv, (t > 0) || (k > 0));       // O  += P V
+          umma_f16_ts(tbase + 256 + D, tbase + kPCol + k * 8, tvd, idesc_pv, (t > 0) || (k > 0));  // AB += P tV
+          umma_f16_ts(tbase + 256 + D, tbase + kHCol + k * 8, vd, idesc_pv, 1);                    //     + H V
         }
         umma_commit(&o_full);
         umma_commit(&v_empty);
