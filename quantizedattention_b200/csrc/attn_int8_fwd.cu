@@ -1,10 +1,10 @@
 // int8 SageAttention3-style forward (reference attention_int8.py:170-257) for sm_100a.
 //
 // One CTA = one 128-row query tile of one (batch, head).  Warp roles (NSPLIT = column groups per row):
-//   softmax warps    [0, 4*NSPLIT)            TMEM S tile -> fp16 logits -> online softmax -> int8 P -> smem
+//   softmax warps    [0, 4*NSPLIT)            TMEM S tile -> fp16 logits -> online softmax -> int8 P -> TMEM (over S)
 //   correction warps [4*NSPLIT, 8*NSPLIT)     TMEM int32 P.V partial -> fp32 O accumulators in registers
 //   producer warp    8*NSPLIT                 TMA: Q once, K / V tiles into STAGES-deep rings
-//   MMA warp         8*NSPLIT + 1             tcgen05.mma kind::i8 (S = Q K^T, Opart = P V), TMEM owner
+//   MMA warp         8*NSPLIT + 1             tcgen05.mma kind::i8 (S = Q K^T SS mode; Opart = P V with P from TMEM), TMEM owner
 // TMEM (512 cols): S[2] at 0/128, Opart[2] at 256/384.  The int32 P.V accumulator cannot span k-tiles (the
 // P scale is per row per k-tile, the V scale per k-tile), so each k-tile's partial is drained to registers.
 // Numerics follow the reference step by step (fp16 logits, fp16 running max, fp16 subtraction, per-row P scale
@@ -179,8 +179,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ---- pass 2: P = exp2(S16 - m), l += sum(P), P_i8 = trunc(P / sp) -> written back to TMEM over the S columns
       //      (4 int8 per column): the P V MMA takes its A operand straight from TMEM (no shared-memory round trip,
       //      no proxy fence, no second buffer to wait for - the S buffer is ours until that MMA has been issued)
-      if (warp == 0) QA_TL(3);
-      if (warp == 0) QA_TL(4);
+      if (warp == 0) { QA_TL(3); QA_TL(4); }
       const __half2 m2 = __half2half2((CAUSAL && __hisinf(m_new)) ? __float2half_rn(0.f) : m_new);
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);

@@ -1,5 +1,5 @@
 """Per-tile timeline of one CTA of the int8 forward (SM clock stamps recorded by the kernel's roles).
-slots: 0 softmax: before s_full wait | 1 S ready | 2 pass-1 done | 3 before p_empty wait | 4 p_empty ok | 5 P handed over
+slots: 0 softmax: before s_full wait | 1 S ready | 2 pass-1 done | 3, 4 scales handed over, pass 2 starts | 5 P handed over
        6 correction: before o_full wait | 7 Opart ready | 8 drained     9 MMA: K landed | 10 QK issued | 11 PV issued"""
 import json
 import sys
