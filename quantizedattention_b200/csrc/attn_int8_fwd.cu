@@ -1,12 +1,19 @@
 // int8 SageAttention3-style forward (reference attention_int8.py:170-257) for sm_100a.
 //
-// One CTA = one 128-row query tile of one (batch, head).  Warp roles (NSPLIT = column groups per row):
-//   softmax warps    [0, 4*NSPLIT)            TMEM S tile -> fp16 logits -> online softmax -> int8 P -> TMEM (over S)
-//   correction warps [4*NSPLIT, 8*NSPLIT)     TMEM int32 P.V partial -> fp32 O accumulators in registers
-//   producer warp    8*NSPLIT                 TMA: Q once, K / V tiles into STAGES-deep rings
-//   MMA warp         8*NSPLIT + 1             tcgen05.mma kind::i8 (S = Q K^T SS mode; Opart = P V with P from TMEM), TMEM owner
-// TMEM (512 cols): S[2] at 0/128, Opart[2] at 256/384.  The int32 P.V accumulator cannot span k-tiles (the
-// P scale is per row per k-tile, the V scale per k-tile), so each k-tile's partial is drained to registers.
+// One CTA = one 128-row query tile of one (batch, head).
+// NSPLIT == 2 (the tuned 128-key tile; 20 warps): the online softmax is a two-stage pipeline across warpgroups
+//   exp warps        0..7    second stage: fp16 logits (TMEM) -> exp2, row sums, int8 P -> TMEM; two warps per 32 rows,
+//                            64 columns each
+//   logit warps      8..11   first stage, whole rows: TMEM int32 S -> packed fp16 logits written back over S, running
+//                            maximum, rescale factor and P scale of the tile, published per 32-row group
+//   drain warps      12..15  TMEM int32 P.V partial -> fp32 O accumulators (all D columns) in registers
+//   TMA producer 16, MMA issuer 17 (tcgen05.mma kind::i8; S = Q K^T from shared memory, Opart = P V with P from TMEM),
+//   18..19 idle; setmaxnreg moves the registers of everybody else to the drain warps (80/80/80/192/40 per sub-partition).
+//   TMEM (512 cols): S[3] at 0/128/256 (Q K^T runs two tiles ahead), one Opart at 384.
+// NSPLIT == 1 (Bkv = 32 / 64 and the one-thread-per-row variant): softmax warps [0,4) do both stages, correction warps
+//   [4,8), producer 8, MMA 9; TMEM S[2] at 0/128, Opart[2] at 256/384.
+// The int32 P.V accumulator cannot span k-tiles (the P scale is per row per k-tile, the V scale per k-tile), so each
+// k-tile's partial is drained to registers.
 // Numerics follow the reference step by step (fp16 logits, fp16 running max, fp16 subtraction, per-row P scale
 // exp2(rowmax - m)/127, truncation toward zero); see DESIGN.md for the two tolerance-level deviations
 // (single fused scale multiply; reciprocal multiply instead of divide for P/sp).
@@ -58,7 +65,7 @@ struct Int8FwdParams {
   } while (0)
 
 template <int D, int NSPLIT, int STAGES, int BN, bool RN, bool CAUSAL>
-__global__ void __launch_bounds__(256 * NSPLIT + 64, 1)
+__global__ void __launch_bounds__(256 * NSPLIT + 128, 1)
 int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
   using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
@@ -67,16 +74,27 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   static_assert(NC % 32 == 0, "a softmax thread handles a multiple of 32 columns");
   constexpr int DC = D / NSPLIT;         // O columns per correction thread
   constexpr int kSoftWarps = 4 * NSPLIT;
+  // NSPLIT == 2: S[b] columns hold, per 64-column half h, the packed fp16 logits at [64h, 64h+32); P (int8) at [32, 64)
+  constexpr uint32_t kPOff = (NSPLIT == 2) ? 32 : 0;
+  // TMEM buffers: NSPLIT == 1: S[2] at 0/128, Opart[2] at 256/384.  NSPLIT == 2: S[3] at 0/128/256 (Q K^T runs two tiles
+  // ahead, so the logit warps never wait for the tensor pipe behind a P V) and a single Opart at 384 (the drain of tile
+  // j is shorter than a tile period, P V of tile j+1 waits for it).
+  constexpr int kSBuf = (NSPLIT == 2) ? 3 : 2, kOBuf = (NSPLIT == 2) ? 1 : 2;
+  constexpr uint32_t kOCol = kSBuf * 128;
+  static_assert(NSPLIT == 1 || BN == 128, "the two-stage softmax is laid out for 128-key tiles");
   constexpr uint32_t kLayoutQK = (D == 128) ? kSwz128 : kSwz64;   // rows of D bytes
   constexpr uint32_t kSboQK = (D == 128) ? 1024 : 512;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  __shared__ uint64_t s_full[2], p_full[2], o_full[2], o_empty[2], sc_full[2], sc_empty[2], fin_full;
+  __shared__ uint64_t s_full[3], p_full[3], o_full[2], o_empty[2], sc_full[2], sc_empty[2], fin_full;
+  // NSPLIT == 2: logits + per-row parameters (rescale, 127/sp, m, sp*sv) of tile j published in ring slot j & 3: slot
+  // j is rewritten for tile j+4, i.e. after P V of tile j+2, which itself waits for the drain of tile j
+  __shared__ uint64_t lg_full[4][4];
+  __shared__ float4 prm_s[4][kBM];
   __shared__ uint32_t tmem_base_s;
   __shared__ float2 row_sc[2][kBM];          // per tile parity: (rescale, sp*sv) per row
-  __shared__ __half xmax[2][2][kBM];         // NSPLIT == 2: row-max exchange between the two column groups
   __shared__ float l_part[2][kBM];
   __shared__ __half m_fin[kBM];
 
@@ -91,10 +109,12 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&p_full[b], kSoftWarps);
-      mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], kSoftWarps);
+      if (b == 0) { mbar_init(&s_full[2], 1); mbar_init(&p_full[2], kSoftWarps); }
+      for (int qd = 0; qd < 4; ++qd) { mbar_init(&lg_full[b][qd], 1); mbar_init(&lg_full[b + 2][qd], 1); }
+      mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4);                     // one drain warp per 32-row group
       mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], kSoftWarps);
     }
-    mbar_init(&fin_full, kSoftWarps);
+    mbar_init(&fin_full, kSoftWarps + (NSPLIT == 2 ? 4 : 0));
     fence_mbar_init();
   }
   if (warp == 8 * NSPLIT + 1) tmem_alloc<512>(&tmem_base_s);
@@ -103,8 +123,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
 
+  // NSPLIT == 2 (20 warps, 5 per SM sub-partition, 96 registers each at launch = the CTA's whole budget): the exp warps,
+  // the logit warps and the last warpgroup (TMA, MMA, two idle warps) hand registers to the drain warps, which hold the
+  // fp32 O accumulators of all D columns: 80 + 80 + 80 + 192 + 40 <= 5 x 96 per lane of a sub-partition (setmaxnreg.inc
+  // can only take what the CTA's other warps released)
   if (warp < kSoftWarps) {
     // =========================== softmax warps ===========================
+    if (NSPLIT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     const int split = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
@@ -120,57 +145,61 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int j = 0; j < nk; ++j) {
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
+      const int sb = j % kSBuf;                                    // S buffer of this tile
       const float sk_f = __half2float(p.sk[((size_t)bh * p.Sk) / kBN + j]);
       const float sv_f = __half2float(p.sv[((size_t)bh * p.Sk) / kBN + j]);
       const float c = sq_f * sk_f * p.qk_scale;
       const float2 c2 = make_float2(c, c);
       if (warp == 0) QA_TL(0);
-      mbar_wait(&s_full[b], ph);
-      tc_fence_after();
-      if (warp == 0) QA_TL(1);
-      // ---- pass 1: int32 -> fp16 logits (packed), row max
       __half2 sh[NC / 2];
-      __half2 mx2 = __float2half2_rn(-INFINITY);
-      auto pass1 = [&](auto masked) {                              // masked: the diagonal tile of a causal head
+      __half rmax = __float2half_rn(0.f);
+      float4 prm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (NSPLIT == 2) {
+        // ---- two-stage softmax: the logit warps (below) have turned S into packed fp16 logits in TMEM and published
+        //      the row maxima; this warp only does the exponential / quantisation half of the work
+        mbar_wait(&lg_full[j & 3][warp & 3], (j >> 2) & 1);
+        tc_fence_after();
+        if (warp == 0) QA_TL(1);
+        uint32_t lg[32];
+        tmem_ld32(lane_addr + sb * 128 + split * 64, lg);
+        prm = prm_s[j & 3][row];
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sh[i] = *reinterpret_cast<__half2*>(&lg[i]);
+        if (warp == 0) QA_TL(2);
+      } else {
+        mbar_wait(&s_full[sb], (j / kSBuf) & 1);
+        tc_fence_after();
+        if (warp == 0) QA_TL(1);
+        // ---- pass 1: int32 -> fp16 logits (packed), row max
+        __half2 mx2 = __float2half2_rn(-INFINITY);
 #pragma unroll
         for (int ch = 0; ch < NC / 32; ++ch) {
           uint32_t r[32];
-          tmem_ld32(lane_addr + b * 128 + c0 + ch * 32, r);
+          tmem_ld32(lane_addr + sb * 128 + c0 + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
             const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
-            __half2 h = __float22half2_rn(a);
-            if (decltype(masked)::value) {                         // strict causal: keep key < query (same tile: col < row)
-              const int col = c0 + ch * 32 + 2 * i;
-              const __half ninf = __float2half_rn(-INFINITY);
-              if (col >= row) h = __halves2half2(ninf, __high2half(h));
-              if (col + 1 >= row) h = __halves2half2(__low2half(h), ninf);
-            }
+            const __half2 h = __float22half2_rn(a);
             sh[ch * 16 + i] = h;
             mx2 = __hmax2(mx2, h);
           }
         }
-      };
-      if (CAUSAL && j * kBN == q0) pass1(std::true_type{}); else pass1(std::false_type{});
-      __half rmax = __hmax(__low2half(mx2), __high2half(mx2));
-      if (warp == 0) QA_TL(2);
-      if (NSPLIT == 2) {
-        xmax[b][split][row] = rmax;
-        named_bar_sync(1 + (warp & 3), 32 * NSPLIT);   // only the warps that share these 32 rows meet
-        rmax = __hmax(rmax, xmax[b][split ^ 1][row]);
+        rmax = __hmax(__low2half(mx2), __high2half(mx2));
+        if (warp == 0) QA_TL(2);
       }
-      const __half m_new = __hmax(m16, rmax);
-      float rescale = ex2_approx(__half2float(__hsub(m16, m_new)));             // fp16 subtraction (:217-219)
-      float sp_e = ex2_approx(__half2float(__hsub(rmax, m_new)));               // (:232-234) sp = sp_e / 127
-      float inv_sp = __fdividef(127.0f, sp_e);
-      if (CAUSAL) {                                   // a row may have no visible key in this tile / so far: (-inf) - (-inf)
-        if (__hisinf(m_new)) rescale = 1.0f;
-        if (__hisinf(rmax)) { sp_e = 0.f; inv_sp = 0.f; }
-      }
-      m16 = m_new;
-      // ---- hand (rescale, sp*sv) to the correction warps
-      if (split == 0) {
+      __half m_new;
+      float rescale, inv_sp;
+      if (NSPLIT == 2) {                             // the logit warps own the running maximum and the per-row scales
+        rescale = prm.x; inv_sp = prm.y; m_new = __float2half_rn(prm.z);
+      } else {
+        m_new = __hmax(m16, rmax);
+        rescale = ex2_approx(__half2float(__hsub(m16, m_new)));                 // fp16 subtraction (:217-219)
+        const float sp_e = ex2_approx(__half2float(__hsub(rmax, m_new)));       // (:232-234) sp = sp_e / 127
+        inv_sp = __fdividef(127.0f, sp_e);
+        m16 = m_new;
+        // ---- hand (rescale, sp*sv) to the correction warps
         mbar_wait(&sc_empty[b], ph ^ 1);
         row_sc[b][row] = make_float2(rescale, sp_e * (1.0f / 127.0f) * sv_f);
         __syncwarp();
@@ -180,7 +209,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       //      (4 int8 per column): the P V MMA takes its A operand straight from TMEM (no shared-memory round trip,
       //      no proxy fence, no second buffer to wait for - the S buffer is ours until that MMA has been issued)
       if (warp == 0) { QA_TL(3); QA_TL(4); }
-      const __half2 m2 = __half2half2((CAUSAL && __hisinf(m_new)) ? __float2half_rn(0.f) : m_new);
+      const __half2 m2 = __half2half2(m_new);       // (causal: the logit warps publish 0 while a row has seen no key)
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
       {                                                            // RN: the rounding mode is an FFMA2 modifier
@@ -202,34 +231,108 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
           }
-          tmem_st8(lane_addr + b * 128 + c0 / 4 + g * 8, w);
+          tmem_st8(lane_addr + sb * 128 + kPOff + c0 / 4 + g * 8, w);
         }
       }
       tmem_st_wait();
       l = l * rescale + (ls2.x + ls2.y);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
       if (warp == 0) QA_TL(5);
     }
     l_part[split][row] = l;
-    if (split == 0) m_fin[row] = m16;
+    if (NSPLIT == 1) m_fin[row] = m16;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&fin_full);
+  } else if (NSPLIT == 2 && warp < kSoftWarps + 4) {
+    // =========================== logit warps (two-stage softmax, NSPLIT == 2) ===========================
+    // First stage of the online softmax for one 32-row group, whole rows (no cross-warp exchange): int32 S -> packed
+    // fp16 logits written back over the first half of each 64-column half of S[b], running maximum, rescale factor
+    // and P scale of the tile published for the exp warps (second stage) and the drain warp.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
+    const float sq_f = __half2float(p.sq[((size_t)bh * p.Sq + q0 + row) / p.Bq]);
+    const __half* sk_p = p.sk + ((size_t)bh * p.Sk) / kBN;
+    const __half* sv_p = p.sv + ((size_t)bh * p.Sk) / kBN;
+    __half m16 = __float2half_rn(-INFINITY);
+    if (p.m_in != nullptr) m16 = __float2half_rn(p.m_in[(size_t)bh * p.Sq + q0 + row]);
+    for (int j = 0; j < nk; ++j) {
+      const int sb = j % kSBuf;
+      const float c = sq_f * __half2float(sk_p[j]) * p.qk_scale;
+      const float2 c2 = make_float2(c, c);
+      mbar_wait(&s_full[sb], (j / kSBuf) & 1);
+      tc_fence_after();
+      __half2 mx2 = __float2half2_rn(-INFINITY);
+      auto pass1 = [&](auto masked) {                              // masked: the diagonal tile of a causal head
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {                          // 32 columns in, 16 columns (32 packed pairs) out
+          const uint32_t src = lane_addr + sb * 128 + ch * 32;
+          const uint32_t dst = lane_addr + sb * 128 + (ch >> 1) * 64 + (ch & 1) * 16;   // read before it is overwritten
+          uint32_t r[32];
+          tmem_ld32(src, r);
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
+            const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
+            __half2 h = __float22half2_rn(a);
+            if (decltype(masked)::value) {                         // strict causal: keep key < query (same tile: col < row)
+              const int col = ch * 32 + 2 * i;
+              const __half ninf = __float2half_rn(-INFINITY);
+              if (col >= row) h = __halves2half2(ninf, __high2half(h));
+              if (col + 1 >= row) h = __halves2half2(__low2half(h), ninf);
+            }
+            mx2 = __hmax2(mx2, h);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          tmem_st8(dst, *reinterpret_cast<uint32_t (*)[8]>(&w[0]));
+          tmem_st8(dst + 8, *reinterpret_cast<uint32_t (*)[8]>(&w[8]));
+        }
+      };
+      if (CAUSAL && j * kBN == q0) pass1(std::true_type{}); else pass1(std::false_type{});
+      const __half rmax = __hmax(__low2half(mx2), __high2half(mx2));
+      const __half m_new = __hmax(m16, rmax);
+      float rescale = ex2_approx(__half2float(__hsub(m16, m_new)));             // fp16 subtraction (:217-219)
+      float sp_e = ex2_approx(__half2float(__hsub(rmax, m_new)));               // (:232-234) sp = sp_e / 127
+      float inv_sp = __fdividef(127.0f, sp_e);
+      if (CAUSAL) {                                   // a row may have no visible key in this tile / so far: (-inf) - (-inf)
+        if (__hisinf(m_new)) rescale = 1.0f;
+        if (__hisinf(rmax)) { sp_e = 0.f; inv_sp = 0.f; }
+      }
+      m16 = m_new;
+      prm_s[j & 3][row] = make_float4(rescale, inv_sp, (CAUSAL && __hisinf(m_new)) ? 0.f : __half2float(m_new),
+                                      sp_e * (1.0f / 127.0f) * __half2float(sv_p[j]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lg_full[j & 3][qd]);
+    }
+    m_fin[row] = m16;
     __syncwarp();
     if (lane == 0) mbar_arrive(&fin_full);
   } else if (warp < 2 * kSoftWarps) {
-    // =========================== correction warps ===========================
+    // =========================== drain (correction) warps ===========================
+    // NSPLIT == 1: 4 warps, scales handed over by the softmax warps.  NSPLIT == 2: warps 12..15, one per 32-row group,
+    // all D output columns (the registers come from the other warpgroups), scales published by the logit warps.
+    constexpr bool kTwoStage = (NSPLIT == 2);
+    constexpr int DCx = kTwoStage ? D : DC;
+    if (kTwoStage) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     const int cw = warp - kSoftWarps;
-    const int split = cw >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    const int d0 = split * DC;
-    float2 acc2[DC / 2];                                   // fp32x2 accumulators: one FFMA2 per two elements
+    const int split = kTwoStage ? 0 : (cw >> 2);
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
+    const int d0 = split * DCx;
+    float2 acc2[DCx / 2];                                  // fp32x2 accumulators: one FFMA2 per two elements
 #pragma unroll
-    for (int i = 0; i < DC / 2; ++i) acc2[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < DCx / 2; ++i) acc2[i] = make_float2(0.f, 0.f);
     if (p.O_acc_in != nullptr) {
       const float* src = p.O_acc_in + ((size_t)bh * p.Sq + q0 + row) * D + d0;
 #pragma unroll
-      for (int i = 0; i < DC; i += 4) {
+      for (int i = 0; i < DCx; i += 4) {
         const float4 t = *reinterpret_cast<const float4*>(src + i);
         acc2[i / 2] = make_float2(t.x, t.y); acc2[i / 2 + 1] = make_float2(t.z, t.w);
       }
@@ -238,28 +341,36 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int j = 0; j < nk; ++j) {
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&sc_full[b], ph);
-      const float2 sc = row_sc[b][row];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sc_empty[b]);
+      const int ob = j % kOBuf;                                    // P.V partial buffer of this tile
+      float2 sc;
+      if (kTwoStage) {
+        mbar_wait(&lg_full[j & 3][qd], (j >> 2) & 1);
+        const float4 prm = prm_s[j & 3][row];
+        sc = make_float2(prm.x, prm.w);
+      } else {
+        mbar_wait(&sc_full[b], ph);
+        sc = row_sc[b][row];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_empty[b]);
+      }
       // Lazy rescale: the accumulator holds O / s_pend, so O*rescale + x*c (attention_int8.py:225, 249-250) costs one
       // FMA per element: s_pend *= rescale; acc += x * (c / s_pend).  rescale == 0 only on a fresh first tile (acc == 0).
       if (sc.x != 0.f) s_pend *= sc.x;
       if (__any_sync(0xffffffffu, s_pend < 1e-12f)) {       // rare: fold the pending factor back in before it underflows
 #pragma unroll
-        for (int i = 0; i < DC / 2; ++i) acc2[i] = __fmul2_rn(acc2[i], make_float2(s_pend, s_pend));
+        for (int i = 0; i < DCx / 2; ++i) acc2[i] = __fmul2_rn(acc2[i], make_float2(s_pend, s_pend));
         s_pend = 1.0f;
       }
       const float c_eff = __fdividef(sc.y, s_pend);
       const float2 ce2 = make_float2(c_eff, c_eff);
-      if (cw == 0) QA_TL(6);
-      mbar_wait(&o_full[b], ph);
+      if (cw == 0 || (kTwoStage && cw == 4)) QA_TL(6);
+      mbar_wait(&o_full[ob], (j / kOBuf) & 1);
       tc_fence_after();
-      if (cw == 0) QA_TL(7);
+      if (cw == 0 || (kTwoStage && cw == 4)) QA_TL(7);
 #pragma unroll
-      for (int ch = 0; ch < DC / 32; ++ch) {
+      for (int ch = 0; ch < DCx / 32; ++ch) {
         uint32_t r[32];
-        tmem_ld32(lane_addr + 256 + b * 128 + d0 + ch * 32, r);
+        tmem_ld32(lane_addr + kOCol + ob * 128 + d0 + ch * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -267,8 +378,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[b]);
-      if (cw == 0) QA_TL(8);
+      if (lane == 0) mbar_arrive(&o_empty[ob]);
+      if (cw == 0 || (kTwoStage && cw == 4)) QA_TL(8);
     }
     mbar_wait(&fin_full, 0);
     float l = l_part[0][row];
@@ -278,14 +389,14 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ring mode: emit the unnormalised accumulator and (m, l); the host-side merge normalises
       float* dst = p.O_acc_out + grow * D + d0;
 #pragma unroll
-      for (int i = 0; i < DC; i += 4)
+      for (int i = 0; i < DCx; i += 4)
         *reinterpret_cast<float4*>(dst + i) = make_float4(acc2[i / 2].x * s_pend, acc2[i / 2].y * s_pend, acc2[i / 2 + 1].x * s_pend, acc2[i / 2 + 1].y * s_pend);
       if (split == 0) { p.m_out[grow] = __half2float(m_fin[row]); p.l_out[grow] = l; }
     } else {
       const float inv_l = s_pend / l;                                          // O / l (:256), pending rescale folded in
       __half* dst = p.O + grow * D + d0;
 #pragma unroll
-      for (int i = 0; i < DC; i += 8) {
+      for (int i = 0; i < DCx; i += 8) {
         __half2 h0 = __floats2half2_rn(acc2[i / 2].x * inv_l, acc2[i / 2].y * inv_l);
         __half2 h1 = __floats2half2_rn(acc2[i / 2 + 1].x * inv_l, acc2[i / 2 + 1].y * inv_l);
         __half2 h2 = __floats2half2_rn(acc2[i / 2 + 2].x * inv_l, acc2[i / 2 + 2].y * inv_l);
@@ -302,8 +413,11 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (p.lse32 != nullptr) p.lse32[grow] = __half2float(m) + lg;
       }
     }
+  } else if (warp >= 8 * NSPLIT + 2) {
+    if (NSPLIT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");     // idle warps of the last warpgroup
   } else if (warp == 8 * NSPLIT) {
     // =========================== TMA producer ===========================
+    if (NSPLIT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
       mbar_expect_tx(&q_full, L::kQBytes);
@@ -321,29 +435,29 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     // =========================== MMA issuer ===========================
+    if (NSPLIT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc(2, 1, 1, 0, 0, kBM, kBN);          // s32 += s8 x s8, both K-major
       constexpr uint32_t idesc_pv = umma_idesc(2, 1, 1, 0, 1, kBM, D);            // B = V: MN-major
       const uint32_t q_addr = smem_u32(smem + L::off_q);
       auto issue_pv = [&](int t) {                                 // Opart[b] = P_t V_t, P from TMEM (S[b] columns)
-        const int b = t & 1, s = t % STAGES;
-        const uint32_t ph = (t >> 1) & 1;
+        const int sb = t % kSBuf, ob = t % kOBuf, s = t % STAGES;
         mbar_wait(&v_full[s], (t / STAGES) & 1);
-        mbar_wait(&o_empty[b], ph ^ 1);
-        mbar_wait(&p_full[b], ph);
+        mbar_wait(&o_empty[ob], ((t / kOBuf) & 1) ^ 1);
+        mbar_wait(&p_full[sb], (t / kSBuf) & 1);
         tc_fence_after();
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < 64) p.dbg[t * 16 + 11] = clock64();   // PV issue
         const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kVBytes);
 #pragma unroll
         for (int k = 0; k < kBN / 32; ++k) {
           const uint64_t bd = umma_smem_desc(v_addr + k * 32 * D, 16, kSboQK, kLayoutQK);
-          umma_i8_ts(tbase + 256 + b * 128, tbase + b * 128 + k * 8, bd, idesc_pv, k > 0);
+          umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * 128 + kPOff + k * 8, bd, idesc_pv, k > 0);
         }
-        umma_commit(&o_full[b]);
+        umma_commit(&o_full[ob]);
         umma_commit(&v_empty[s]);
       };
       auto issue_qk = [&](int j) {                                 // S[b] = Q K_j^T
-        const int b = j & 1, s = j % STAGES;
+        const int sb = j % kSBuf, s = j % STAGES;
         mbar_wait(&k_full[s], (j / STAGES) & 1);
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) { p.dbg[j * 16 + 9] = clock64(); p.dbg[j * 16 + 10] = clock64(); }
         const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
@@ -351,19 +465,18 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int k = 0; k < D / 32; ++k) {
           const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, kSboQK, kLayoutQK);
           const uint64_t bd = umma_smem_desc(k_addr + k * 32, 16, kSboQK, kLayoutQK);
-          umma_i8_ss(tbase + b * 128, ad, bd, idesc_qk, k > 0);
+          umma_i8_ss(tbase + sb * 128, ad, bd, idesc_qk, k > 0);
         }
-        umma_commit(&s_full[b]);
+        umma_commit(&s_full[sb]);
         umma_commit(&k_empty[s]);
       };
       mbar_wait(&q_full, 0);
       tc_fence_after();
-      issue_qk(0);
-      if (nk > 1) issue_qk(1);
+      for (int j = 0; j < kSBuf && j < nk; ++j) issue_qk(j);
       for (int j = 0; j < nk; ++j) {
         issue_pv(j);
-        if (j + 2 < nk) issue_qk(j + 2);     // behind P V in the in-order pipe: S[b] is rewritten only after P_j was consumed
-      }
+        if (j + kSBuf < nk) issue_qk(j + kSBuf);   // behind P V in the in-order pipe: the S buffer is rewritten only after
+      }                                            // its P was consumed
     }
   }
   tc_fence_before();
@@ -421,7 +534,7 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / kBM, BH);
-  kern<<<grid, 256 * NSPLIT + 64, L::total, st>>>(tq, tk, tv, p);
+  kern<<<grid, 256 * NSPLIT + 128, L::total, st>>>(tq, tk, tv, p);
   return qa_check_launch("qa_int8_fwd");
 }
 
