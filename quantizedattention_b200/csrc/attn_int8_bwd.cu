@@ -395,6 +395,369 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-specialised variant (default): 16 warps.  Warps 0..7 ("quantise" role) run pass 1, the tile-wide amax exchange
+// and pass 2 of tile t; warps 8..15 ("drain" role) hold the fp32 dV / dK accumulators, drain the int32 partial
+// products of tile t-1 and stage dQ; thread 256 issues TMA and tcgen05.mma.  setmaxnreg splits the register file
+// 96 / 160 per thread.  Same TMEM / shared-memory plan, numerics and software pipeline as int8_bwd_kernel.
+// Cross-role hand-over: sd_full (MMA -> quantise), pds_full (quantise -> leader: P / dS tiles stored, S / dP columns
+// free), parts_full / dq_full (MMA -> drain), the tile scales through sc_ring (written before pds_full, read after
+// parts_full of the same tile).  The quantise role never waits on dq_full (its parity could alias): completion of
+// dQ(t-2), the last reader of the dS buffer it overwrites, is implied by sd_full(t), which was committed after it.
+// ---------------------------------------------------------------------------------------------------------
+template <int D, bool RN, bool CAUSAL>
+__global__ void __launch_bounds__(512, 1)
+int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dq, Int8BwdParams p) {
+  using L = Int8BwdSmem<D>;
+  constexpr int NG = 2;
+  constexpr int DH = D / NG;                                    // output columns per drain thread
+  constexpr int CW = 128 / NG;                                  // S / dP columns per quantise thread
+  constexpr int NT = 256;                                       // threads per role
+  constexpr uint32_t kLay = (D == 128) ? kSwz128 : kSwz64;      // operand rows of D bytes
+  constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full, dq_full, pds_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red_p[2][8], red_ds[2][8];
+  __shared__ float rowsum_ds[2][NG][128];
+  __shared__ float sc_ring[2][4];                               // per tile parity: c_dv, c_dk, c_dq
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool quant_role = warp < 8;
+  const int rw = warp & 7;                                      // warp index inside the role
+  const bool leader = (tid == 256);
+  const int bh = blockIdx.y, j = blockIdx.x;
+  const int nq = p.S / 128;
+  const int t0 = CAUSAL ? j : 0;                                // causal: k-tile j meets the query tiles j .. nq-1
+  const int nt = nq - t0;
+  const size_t head_row0 = (size_t)bh * p.S;
+
+  if (tid == 0) {
+    mbar_init(&kv_full, 1); mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
+    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1); mbar_init(&dq_full, 1); mbar_init(&pds_full, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  const int half = rw >> 2;                                     // column group handled by this thread
+  const int row = (rw & 3) * 32 + lane;                         // TMEM lane: query row (S, dP, dQ) or key (dV, dK)
+  const uint32_t lane_addr = tbase + ((uint32_t)((rw & 3) * 32) << 16);
+  const float sk_f = __half2float(p.sk[head_row0 / 128 + j]);
+  const float sv_f = __half2float(p.sv[head_row0 / 128 + j]);
+  constexpr float kPs = 1.0f / 1024.0f;                          // P is carried between the passes as fp16(1024 * P)
+
+  if (quant_role) {
+    // =========================== quantise role: pass 1, amax, pass 2 ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    for (int t = 0; t < nt; ++t) {
+      const uint32_t ph = t & 1;
+      const int tq = t0 + t;
+      const size_t qrow = head_row0 + (size_t)tq * 128 + row;
+      const float sq_f = __half2float(p.sq[head_row0 / 128 + tq]);
+      const float sdo_f = __half2float(p.s_do[head_row0 / 128 + tq]);
+      const float lse = p.lse[qrow];
+      const float dlt = p.delta[qrow];
+      const float c_s = sq_f * sk_f * p.qk_scale;
+      const float c_dp = sdo_f * sv_f;
+      mbar_wait(&sd_full, ph);
+      tc_fence_after();
+      // ---- pass 1: P = exp2(fp16 logit - lse), kept as packed fp16 of 1024 * P (11-bit mantissa, no subnormals down to
+      //      P = 6e-8) so that pass 2 needs no second exp2; tile amax of P and |dS|, row sum of dS
+      __half2 pk[CW / 2];
+      float amax_p = 0.f, amax_ds = 0.f;
+      __half2 amax_ph = __float2half2_rn(0.f);
+      float2 rs2acc = make_float2(0.f, 0.f);
+      const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(10.0f - lse, 10.0f - lse);
+      const float2 cdp2 = make_float2(c_dp * kPs, c_dp * kPs), ndlt2 = make_float2(-dlt * kPs, -dlt * kPs);
+      auto pass1 = [&](auto masked) {                                // masked: the diagonal tile of a causal head
+  #pragma unroll
+      for (int ch = 0; ch < CW / 16; ++ch) {
+        uint32_t r[16], r2[16];
+        tmem_ld16(lane_addr + half * CW + ch * 16, r);
+        tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
+        tmem_ld_wait();
+  #pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cs2));
+          const float2 e = __fadd2_rn(__half22float2(h), nlse2);
+          float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));                     // 1024 * P
+          if (decltype(masked)::value) {                                 // strict causal: keep key < query (same tile: col < row)
+            const int col = half * CW + ch * 16 + c;
+            if (col >= row) pp.x = 0.f;
+            if (col + 1 >= row) pp.y = 0.f;
+          }
+          const __half2 pr = __float22half2_rn(pp);
+          pk[ch * 8 + c / 2] = pr;
+          amax_ph = __hmax2(amax_ph, pr);
+          const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdp2, ndlt2));
+          amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d.x), fabsf(d.y)));
+          rs2acc = __fadd2_rn(rs2acc, d);
+        }
+      }
+      };
+      if (CAUSAL && t == 0) pass1(std::true_type{}); else pass1(std::false_type{});
+      amax_p = fmaxf(__low2float(amax_ph), __high2float(amax_ph));                       // of the rounded 1024 * P
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        amax_p = fmaxf(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, o));
+        amax_ds = fmaxf(amax_ds, __shfl_xor_sync(0xffffffffu, amax_ds, o));
+      }
+      if (lane == 0) { red_p[ph][rw] = amax_p; red_ds[ph][rw] = amax_ds; }
+      rowsum_ds[ph][half][row] = rs2acc.x + rs2acc.y;
+
+      named_bar_sync(3, NT);                                       // amax partials of the 8 quantise warps visible
+      // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
+      amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
+  #pragma unroll
+      for (int w = 1; w < 8; ++w) { amax_p = fmaxf(amax_p, red_p[ph][w]); amax_ds = fmaxf(amax_ds, red_ds[ph][w]); }
+      float rs_row = 0.f;                                                      // full-row sum of dS (query row = lane)
+  #pragma unroll
+      for (int g = 0; g < 2; ++g) rs_row += rowsum_ds[ph][g][row];
+      // K-smoothing term of dQ (LEDGER I-1): sm_scale * rowsum(dS) * k_mean is rank one per query row, so only the
+      // row sums are accumulated here (one fp32 reduction per row and tile); qa_int8_bwd_finalize applies k_mean once.
+      if (half == 0 && p.rowsum != nullptr) atomicAdd(p.rowsum + qrow, rs_row);
+      const float sP = amax_p * (kPs / 127.0f), sdS = amax_ds * (1.0f / 127.0f);
+      const float inv_p = amax_p > 0.f ? __fdividef(127.0f, amax_p) : 0.f;
+      const float inv_ds = amax_ds > 0.f ? __fdividef(127.0f, amax_ds) : 0.f;
+      if (tid == 0) {                                              // tile scales for the drain role (read after parts_full(t))
+        sc_ring[ph][0] = sdo_f * sP;
+        sc_ring[ph][1] = sdS * sq_f * p.sm_scale;
+        sc_ring[ph][2] = sdS * sk_f * p.sm_scale;
+      }
+      // the P tile and this dS buffer were last read by dV/dK of tile t-1 (dS[ph] also by dQ of t-2, which completed
+      // before sd_full(t) was signalled)
+      if (t > 0) mbar_wait(&parts_full, (t - 1) & 1);
+      // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
+      //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
+      const uint32_t ds_tile = smem_base + L::off_ds + ph * (128 * 128);
+      const float2 cdpi2 = make_float2(c_dp * kPs * inv_ds, c_dp * kPs * inv_ds), ndlti2 = make_float2(-dlt * kPs * inv_ds, -dlt * kPs * inv_ds);
+      const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
+      {                                                              // RN: the rounding mode is an instruction modifier
+  #pragma unroll
+        for (int ch = 0; ch < CW / 16; ++ch) {
+          uint32_t r2[16];
+          tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
+          tmem_ld_wait();
+          uint32_t wp[4], wd[4];
+  #pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t bp[4], bd[4];
+  #pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const int c = q4 * 4 + e;
+              const float2 pp = __half22float2(pk[ch * 8 + c / 2]);                  // 1024 * P from pass 1
+              // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS (and the 1/1024) folded into the FFMA2 constants
+              const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
+              // P >= 0: low byte of the biased sum = trunc(P / sP), or its nearest-even rounding in accuracy mode
+              const float2 pq = RN ? __ffma2_rn(pp, invp2, magic2) : __ffma2_rz(pp, invp2, magic2);
+              bp[e] = __float_as_uint(pq.x);
+              bp[e + 1] = __float_as_uint(pq.y);
+              bd[e] = (uint32_t)(RN ? __float2int_rn(dq.x) : __float2int_rz(dq.x));
+              bd[e + 1] = (uint32_t)(RN ? __float2int_rn(dq.y) : __float2int_rz(dq.y));
+            }
+            wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
+            wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
+          }
+          const uint32_t off = swz128(row, half * CW + ch * 16);
+          sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
+          sts128(ds_tile + off, wd[0], wd[1], wd[2], wd[3]);
+        }
+      }
+
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full);
+    }
+  } else {
+    // =========================== drain role: accumulators, dQ staging, TMA / MMA issue ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128);     // S, dP: A, B K-major, N = 128
+    constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);       // dV, dK: A^T (MN-major), B MN-major, N = D
+    constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);       // dQ: A K-major, B MN-major
+    const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
+    const uint32_t a_p = smem_u32(smem + L::off_p), a_ds0 = smem_u32(smem + L::off_ds);
+    auto load_qdo = [&](int tile, int st) {
+      mbar_expect_tx(&qdo_full[st], 2 * L::kTile);
+      tma_load_2d(smem + L::off_q + st * L::kTile, &tm_q, &qdo_full[st], 0, (int)head_row0 + tile * 128);
+      tma_load_2d(smem + L::off_do + st * L::kTile, &tm_do, &qdo_full[st], 0, (int)head_row0 + tile * 128);
+    };
+    auto issue_s = [&](int st) {                                     // S = Q K^T (issued one barrier ahead of dP: the S columns
+      const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);          // are free as soon as pass 1 is over)
+  #pragma unroll
+      for (int k = 0; k < D / 32; ++k)
+        umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, k > 0);
+    };
+    auto issue_dp = [&](int st) {                                    // dP = dO V^T; the commit also covers the earlier S MMAs
+      const uint32_t a_do = smem_u32(smem + L::off_do + st * L::kTile);
+  #pragma unroll
+      for (int k = 0; k < D / 32; ++k)
+        umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, k > 0);
+      umma_commit(&sd_full);
+    };
+    auto issue_dv_dk = [&](int st, int dsb) {                        // dV = P^T dO, dK = dS^T Q (contraction over query rows)
+      const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
+      const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+  #pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+        umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+      }
+      umma_commit(&parts_full);
+    };
+    auto issue_dq = [&](int dsb) {                                   // dQ = dS K (contraction over keys) -> cols 256..
+      const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+  #pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
+      umma_commit(&dq_full);
+    };
+
+    if (leader) {
+      mbar_expect_tx(&kv_full, 2 * L::kTile);
+      tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
+      tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
+      load_qdo(t0, 0);
+      mbar_wait(&kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      issue_s(0);
+      issue_dp(0);
+    }
+    float2 dv_acc[DH / 2], dk_acc[DH / 2];                        // fp32x2: FFMA2 / FMUL2 / FADD2 halve the issue slots
+#pragma unroll
+    for (int d = 0; d < DH / 2; ++d) { dv_acc[d] = make_float2(0.f, 0.f); dk_acc[d] = make_float2(0.f, 0.f); }
+    auto drain_dv_dk = [&](float c_dv, float c_dk) {
+  #pragma unroll
+      for (int ch = 0; ch < DH / 16; ++ch) {
+        uint32_t r[16], r2[16];
+        tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
+        tmem_ld16(lane_addr + 384 + half * DH + ch * 16, r2);
+        tmem_ld_wait();
+  #pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dv_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r[2 * c]), __int2float_rn((int)r[2 * c + 1])),
+                                          make_float2(c_dv, c_dv), dv_acc[ch * 8 + c]);
+          dk_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r2[2 * c]), __int2float_rn((int)r2[2 * c + 1])),
+                                          make_float2(c_dk, c_dk), dk_acc[ch * 8 + c]);
+        }
+      }
+    };
+    auto drain_dq = [&](float c_dq) {                 // dQ partial -> fp32 staging (swizzled 32-float atoms)
+  #pragma unroll
+      for (int ch = 0; ch < DH / 16; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
+        tmem_ld_wait();
+        const int col = half * DH + ch * 16;                         // first output column of this chunk
+        const uint32_t atom = smem_base + L::off_dq + (col >> 5) * (128 * 128);
+  #pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          const float2 cq2 = make_float2(c_dq, c_dq);
+          const float2 o01 = __fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2);
+          const float2 o23 = __fmul2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2);
+          sts128f(atom + swz128(row, ((col & 31) + c) * 4), o01.x, o01.y, o23.x, o23.y);
+        }
+      }
+    };
+    auto reduce_dq = [&](int tile) {                                // dQ[tile] += staging (L2 reduction; k-tile order not fixed)
+  #pragma unroll
+      for (int a = 0; a < D / 32; ++a)
+        tma_reduce_add_2d(&tm_dq, smem + L::off_dq + a * (128 * 128), a * 32, (int)head_row0 + tile * 128);
+      tma_store_commit();
+    };
+
+    for (int t = 0; t < nt; ++t) {
+      const uint32_t ph = t & 1;
+      const int tq = t0 + t;
+      if (leader && t + 1 < nt) {                                  // next Q / dO tile: its stage was last read by dV/dK of t-1
+        if (t > 0) mbar_wait(&parts_full, (t - 1) & 1);
+        load_qdo(tq + 1, (t + 1) & 1);
+      }
+      float c_dq_prev = 0.f;
+      if (t > 0) {                                                 // dV / dK partials of tile t-1
+        mbar_wait(&parts_full, (t - 1) & 1);
+        tc_fence_after();
+        const float c_dv_prev = sc_ring[(t - 1) & 1][0], c_dk_prev = sc_ring[(t - 1) & 1][1];
+        c_dq_prev = sc_ring[(t - 1) & 1][2];
+        drain_dv_dk(c_dv_prev, c_dk_prev);
+      }
+      tc_fence_before();
+      if (leader) tma_store_wait_read();                           // the dQ staging tile may be rewritten after this barrier
+      named_bar_sync(1, NT);                                      // dV/dK partial columns drained by the whole role
+      if (leader && t > 0) { tc_fence_after(); issue_dq((t - 1) & 1); }
+      if (t > 0) {                                                 // dQ partial of tile t-1 -> staging tile
+        mbar_wait(&dq_full, (t - 1) & 1);
+        tc_fence_after();
+        drain_dq(c_dq_prev);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(2, NT);                                      // staging tile complete, dQ partial columns drained
+      if (leader) {
+        tc_fence_after();
+        if (t > 0) reduce_dq(tq - 1);
+        mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored; S and dP columns free
+        tc_fence_after();
+        if (t + 1 < nt) {
+          mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+          issue_s((t + 1) & 1);
+          issue_dp((t + 1) & 1);
+        }
+        issue_dv_dk(t & 1, ph);
+      }
+    }
+    // ---- pipeline tail: last tile's dV / dK / dQ
+    mbar_wait(&parts_full, (nt - 1) & 1);
+    tc_fence_after();
+    {
+      const float c_dv_prev = sc_ring[(nt - 1) & 1][0], c_dk_prev = sc_ring[(nt - 1) & 1][1], c_dq_prev = sc_ring[(nt - 1) & 1][2];
+      drain_dv_dk(c_dv_prev, c_dk_prev);
+      tc_fence_before();
+      if (leader) tma_store_wait_read();
+      named_bar_sync(1, NT);
+      if (leader) { tc_fence_after(); issue_dq((nt - 1) & 1); }
+      mbar_wait(&dq_full, (nt - 1) & 1);
+      tc_fence_after();
+      drain_dq(c_dq_prev);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(2, NT);
+    if (leader) { reduce_dq(nq - 1); tma_store_wait_all(); }
+    // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
+    const size_t krow = head_row0 + (size_t)j * 128 + row;
+    __half* dk_dst = p.dk + krow * D + half * DH;
+    __half* dv_dst = p.dv + krow * D + half * DH;
+  #pragma unroll
+    for (int d = 0; d < DH; d += 8) {
+      uint4 a, b;
+      __half2 t2;
+      t2 = __float22half2_rn(dk_acc[d / 2]); a.x = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dk_acc[d / 2 + 1]); a.y = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dk_acc[d / 2 + 2]); a.z = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dk_acc[d / 2 + 3]); a.w = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dv_acc[d / 2]); b.x = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dv_acc[d / 2 + 1]); b.y = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dv_acc[d / 2 + 2]); b.z = *reinterpret_cast<uint32_t*>(&t2);
+      t2 = __float22half2_rn(dv_acc[d / 2 + 3]); b.w = *reinterpret_cast<uint32_t*>(&t2);
+      *reinterpret_cast<uint4*>(dk_dst + d) = a;
+      *reinterpret_cast<uint4*>(dv_dst + d) = b;
+    }
+
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tbase);
+}
+
 // Causal row 0 of every head attends uniformly to all S keys (LEDGER B-1): dV[k] += dO[0] / S for every key k; dQ and
 // dK get nothing from it (its P is exactly 0 inside the fused kernel).  dO[0] is taken de-quantised (do_i8 * s_dO).
 template <int D>
@@ -417,7 +780,7 @@ __global__ void __launch_bounds__(256) int8_bwd_row0_fixup_kernel(const int8_t* 
   *dst = v;
 }
 
-template <int D, int NG, bool RN = false, bool CAUSAL = false>
+template <int D, int NG, bool RN = false, bool CAUSAL = false, bool WS = false>
 static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
                            const Int8BwdParams& p, int BH, cudaStream_t st) {
   using L = Int8BwdSmem<D>;
@@ -434,10 +797,17 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   uint64_t strq[1] = {(uint64_t)D * 4};
   uint32_t boxq[2] = {32, 128};
   if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
+  dim3 grid(p.S / 128, BH);
+  if (WS) {                                                        // warp-specialised: 8 quantise + 8 drain warps
+    auto kern = int8_bwd_ws_kernel<D, RN, CAUSAL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+    if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+    kern<<<grid, 512, L::total, st>>>(tq, tk, tv, tdo, tdq, p);
+    return qa_check_launch("qa_int8_bwd");
+  }
   auto kern = int8_bwd_kernel<D, NG, RN, CAUSAL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  dim3 grid(p.S / 128, BH);
   kern<<<grid, 128 * NG, L::total, st>>>(tq, tk, tv, tdo, tdq, p);
   return qa_check_launch("qa_int8_bwd");
 }
@@ -475,7 +845,23 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
   const char* env = getenv("QA_INT8_BWD_NG");
-  const int ng = env ? atoi(env) : 2;   // 2 column groups (8 warps, 255 regs) measured faster than 4 (16 warps)
+  const int ng = env ? atoi(env) : 2;
+  const char* env_ws = getenv("QA_INT8_BWD_WS");
+  const bool ws = env_ws ? atoi(env_ws) != 0 : true;    // warp-specialised kernel (default); 0 = the 8-warp kernel
+  if (ws && !env) {
+    int rc;
+#define QA_WS(DD, RNN, CC) launch_int8_bwd<DD, 2, RNN, CC, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+    if (causal && rounding) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: causal is built for truncation mode");
+    if (causal) rc = D == 128 ? QA_WS(128, false, true) : QA_WS(64, false, true);
+    else if (rounding) rc = D == 128 ? QA_WS(128, true, false) : QA_WS(64, true, false);
+    else rc = D == 128 ? QA_WS(128, false, false) : QA_WS(64, false, false);
+#undef QA_WS
+    if (rc || !causal) return rc;
+    dim3 grid((unsigned)((S * (D / 8) + 255) / 256), (unsigned)BH);
+    if (D == 128) int8_bwd_row0_fixup_kernel<128><<<grid, 256, 0, st>>>((const int8_t*)do_i8, p.s_do, p.dv, S);
+    else int8_bwd_row0_fixup_kernel<64><<<grid, 256, 0, st>>>((const int8_t*)do_i8, p.s_do, p.dv, S);
+    return qa_check_launch("qa_int8_bwd(causal row 0)");
+  }
   if (causal) {                                                   // instantiated for the default shape only
     if (rounding) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: causal is built for truncation mode");
     int rc = D == 128 ? launch_int8_bwd<128, 2, false, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
