@@ -246,15 +246,15 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["int8_bwd_kernel_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
-    roof = {"bound": "tensor", "kernel": "int8_bwd_kernel<128,2>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
+    roof = {"bound": "tensor", "kernel": "int8_bwd_ws_kernel<128>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
             "peak": peak, "unit": "TFLOP/s", "traffic": traffic,
             "peak_source": "int8 dense: torch._int_mm 8192^3 best-of-10 on this pool (profiles/r01_peaks.json); "
                            "MEASURED_PEAKS.json has no int8 entry (its bf16 burst x2 = %.0f)" % (2 * mp.get("bf16_tflops", 0)),
             "share_of_step": bwd_ms / ms_step,
-            "note": "binding unit is not the tensor pipe: per (128 x 128) tile the int8 MMAs take ~2.5k of ~7.7k clk "
-                    "(tools/timeline_bwd.py); the rest is the reference's per-tile re-quantisation on the CUDA cores "
-                    "(two passes, ~24 instructions per logit, 384 KB of int32 TMEM drains per tile) executed by 8 warps "
-                    "whose 255 registers hold the fp32 dV/dK accumulators, so latencies are exposed (issue slots 43 % busy)",
+            "note": "binding unit is not the tensor pipe: per (128 x 128) tile the int8 MMAs take ~2.5k of ~6.7k clk; the "
+                    "rest is the reference's per-tile re-quantisation on the CUDA cores (two passes, ~24 instructions per "
+                    "logit, 384 KB of int32 TMEM drains per tile).  The kernel is warp-specialised: 8 quantise warps "
+                    "(96 registers) and 8 drain warps (160 registers, fp32 dV/dK accumulators) share the register file",
             "other_kernels": {"int8_fwd_kernel<128,2,3>": {"ms": fwd_ms, "achieved": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12,
                                                            "frac": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12 / peak}}}
     roof["frac"] = roof["achieved"] / peak

@@ -514,6 +514,18 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       rowsum_ds[ph][half][row] = rs2acc.x + rs2acc.y;
 
       named_bar_sync(3, NT);                                       // amax partials of the 8 quantise warps visible
+      // S = Q K^T and dP = dO V^T of the next tile are issued from this role (thread 0): it knows first when their TMEM
+      // columns are free and it has slack, while every tcgen05.mma issue blocks its thread at the tensor pipe's rate -
+      // the drain role's leader keeps dQ, dV / dK and the TMA traffic
+      if (tid == 0 && t + 1 < nt) {                                // every quantise warp is past pass 1: the S columns are free
+        tc_fence_after();
+        mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+        const uint32_t aq = smem_u32(smem + L::off_q + ((t + 1) & 1) * L::kTile), ak = smem_u32(smem + L::off_k);
+#pragma unroll
+        for (int k = 0; k < D / 32; ++k)
+          umma_i8_ss(tbase + 0, umma_smem_desc(aq + k * 32, 16, kSbo, kLay), umma_smem_desc(ak + k * 32, 16, kSbo, kLay),
+                     umma_idesc(2, 1, 1, 0, 0, 128, 128), k > 0);
+      }
       // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
       amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
   #pragma unroll
@@ -576,6 +588,16 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full);
+      if (tid == 0 && t + 1 < nt) {                                // all quantise warps past pass 2: the dP columns are free
+        mbar_wait(&pds_full, ph);
+        tc_fence_after();
+        const uint32_t ado = smem_u32(smem + L::off_do + ((t + 1) & 1) * L::kTile), av = smem_u32(smem + L::off_v);
+#pragma unroll
+        for (int k = 0; k < D / 32; ++k)
+          umma_i8_ss(tbase + 128, umma_smem_desc(ado + k * 32, 16, kSbo, kLay), umma_smem_desc(av + k * 32, 16, kSbo, kLay),
+                     umma_idesc(2, 1, 1, 0, 0, 128, 128), k > 0);
+        umma_commit(&sd_full);                                     // also covers the S MMAs issued above
+      }
     }
   } else {
     // =========================== drain role: accumulators, dQ staging, TMA / MMA issue ===========================
@@ -706,11 +728,6 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         if (t > 0) reduce_dq(tq - 1);
         mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored; S and dP columns free
         tc_fence_after();
-        if (t + 1 < nt) {
-          mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
-          issue_s((t + 1) & 1);
-          issue_dp((t + 1) & 1);
-        }
         issue_dv_dk(t & 1, ph);
       }
     }

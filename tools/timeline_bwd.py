@@ -25,6 +25,22 @@ ops.int8_bwd_prequant(*args)
 torch.cuda.synchronize()
 L.qa_debug_set_int8_bwd_timeline(None)
 t = buf.view(64, 2, 16).cpu()
+import os
+if os.environ.get("QA_INT8_BWD_WS", "1") != "0":        # warp-specialised kernel: quantise warp 1 (slots 0-5), leader warp 8 (6-15)
+    qn = ["top", "S_rdy", "pass1", "amax_bar", "P_free", "pass2"]
+    dn = ["top", "dVK_rdy", "dVK_drn", "bar1", "dQ+S_iss", "dQ_rdy", "dQ_drn", "bar2", "pds_ok", "iss_end"]
+    print("quantise warp 1 - stamps relative to the tile's loop top (cycles); last column = iteration length")
+    print("tile " + " ".join(f"{n:>8s}" for n in qn) + "     iter")
+    for j in range(20, 28):
+        t0 = int(t[j, 0, 0])
+        print(f"{j:4d} " + " ".join(f"{int(t[j, 0, s]) - t0:8d}" for s in range(6)) + f" {int(t[j + 1, 0, 0]) - t0:8d}")
+    print("leader warp 8 (drain role) - relative to the quantise warp's loop top of the same tile")
+    print("tile " + " ".join(f"{n:>8s}" for n in dn) + "     iter")
+    for j in range(20, 28):
+        t0 = int(t[j, 0, 0])
+        print(f"{j:4d} " + " ".join(f"{int(t[j, 1, s]) - t0:8d}" for s in range(6, 16)) + f" {int(t[j + 1, 1, 6]) - int(t[j, 1, 6]):8d}")
+    print("cycles per tile:", (int(t[52, 0, 0]) - int(t[20, 0, 0])) / 32)
+    sys.exit(0)
 names = ["top", "S_rdy", "pass1", "dVK_rdy", "dVK_drn", "bar1", "dQ_iss", "pass2", "dQ_rdy", "dQ_drn", "bar2", "SdP_iss", "dVK_iss"]
 for w, label in ((0, "leader warp 0"), (1, "warp 5")):
     print(label, "- stamps relative to the tile's loop top (cycles); last column = iteration length")
