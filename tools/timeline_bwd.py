@@ -1,4 +1,8 @@
-"""Per-q-tile timeline of one CTA of the int8 backward (SM clock stamps of the leader warp 0 and of warp 5).
+"""NOTE: the default (warp-specialised) kernel carries its stamps only when csrc/attn_int8_bwd.cu is compiled with
+-DQA_BWD_TIMELINE (they cost 3-4 % through register pressure); QA_INT8_BWD_WS=0 selects the 8-warp kernel, whose stamps
+are always compiled in.
+
+Per-q-tile timeline of one CTA of the int8 backward (SM clock stamps of the leader warp 0 and of warp 5).
 slots: 0 loop top | 1 S/dP ready | 2 pass 1 done | 3 dV/dK partial ready | 4 dV/dK drained | 5 barrier 1 passed |
        6 dQ issued (leader) | 7 pass 2 done | 8 dQ partial ready | 9 dQ drained | 10 barrier 2 passed |
        11 S/dP(t+1) issued (leader) | 12 dV/dK issued (leader) = end of iteration"""
