@@ -13,9 +13,12 @@ def _rel(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm()).item()
 
 
+@pytest.mark.parametrize("kernel", ["warp_specialised", "eight_warp"])
 @pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128)])
-def test_int8_bwd_matches_contract_oracle(shape):
+def test_int8_bwd_matches_contract_oracle(shape, kernel, monkeypatch):
     from oracle import int8_ref
+    # the default kernel is the warp-specialised one; the 8-warp kernel stays selectable (read per call by qa_int8_bwd)
+    monkeypatch.setenv("QA_INT8_BWD_WS", "1" if kernel == "warp_specialised" else "0")
     from quantizedattention_b200 import attention_int8 as A
     B, H, S, D = shape
     g = torch.Generator().manual_seed(2000 + S + D)
