@@ -420,7 +420,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full, dq_full, pds_full;
+  __shared__ uint64_t kv_full, qdo_full[2], sd_full, parts_full, dq_full, pds_full, s_free;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red_p[2][8], red_ds[2][8];
   __shared__ float rowsum_ds[2][NG][128];
@@ -429,7 +429,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool quant_role = warp < 8;
   const int rw = warp & 7;                                      // warp index inside the role
-  const bool leader = (tid == 256);
+  // Three issuing threads in the drain role, on different SM sub-partitions (a tcgen05.mma / TMA issue blocks its thread):
+  // 256: Q/dO loads, dQ, dV/dK;  288: S and dP of the next tile;  320: the TMA reduce-add of the dQ staging tile
+  const bool leader = (tid == 256), leader_sdp = (tid == 288), leader_red = (tid == 320);
   const int bh = blockIdx.y, j = blockIdx.x;
   const int nq = p.S / 128;
   const int t0 = CAUSAL ? j : 0;                                // causal: k-tile j meets the query tiles j .. nq-1
@@ -438,7 +440,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (tid == 0) {
     mbar_init(&kv_full, 1); mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
-    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1); mbar_init(&dq_full, 1); mbar_init(&pds_full, 8);
+    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1); mbar_init(&dq_full, 1); mbar_init(&pds_full, 8); mbar_init(&s_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_s);
@@ -514,18 +516,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       rowsum_ds[ph][half][row] = rs2acc.x + rs2acc.y;
 
       named_bar_sync(3, NT);                                       // amax partials of the 8 quantise warps visible
-      // S = Q K^T and dP = dO V^T of the next tile are issued from this role (thread 0): it knows first when their TMEM
-      // columns are free and it has slack, while every tcgen05.mma issue blocks its thread at the tensor pipe's rate -
-      // the drain role's leader keeps dQ, dV / dK and the TMA traffic
-      if (tid == 0 && t + 1 < nt) {                                // every quantise warp is past pass 1: the S columns are free
-        tc_fence_after();
-        mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
-        const uint32_t aq = smem_u32(smem + L::off_q + ((t + 1) & 1) * L::kTile), ak = smem_u32(smem + L::off_k);
-#pragma unroll
-        for (int k = 0; k < D / 32; ++k)
-          umma_i8_ss(tbase + 0, umma_smem_desc(aq + k * 32, 16, kSbo, kLay), umma_smem_desc(ak + k * 32, 16, kSbo, kLay),
-                     umma_idesc(2, 1, 1, 0, 0, 128, 128), k > 0);
-      }
+      if (tid == 0) { tc_fence_before(); mbar_arrive(&s_free); }   // every quantise warp is past pass 1: the S columns are free
       // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
       amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
   #pragma unroll
@@ -588,16 +579,6 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full);
-      if (tid == 0 && t + 1 < nt) {                                // all quantise warps past pass 2: the dP columns are free
-        mbar_wait(&pds_full, ph);
-        tc_fence_after();
-        const uint32_t ado = smem_u32(smem + L::off_do + ((t + 1) & 1) * L::kTile), av = smem_u32(smem + L::off_v);
-#pragma unroll
-        for (int k = 0; k < D / 32; ++k)
-          umma_i8_ss(tbase + 128, umma_smem_desc(ado + k * 32, 16, kSbo, kLay), umma_smem_desc(av + k * 32, 16, kSbo, kLay),
-                     umma_idesc(2, 1, 1, 0, 0, 128, 128), k > 0);
-        umma_commit(&sd_full);                                     // also covers the S MMAs issued above
-      }
     }
   } else {
     // =========================== drain role: accumulators, dQ staging, TMA / MMA issue ===========================
@@ -712,9 +693,15 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         drain_dv_dk(c_dv_prev, c_dk_prev);
       }
       tc_fence_before();
-      if (leader) tma_store_wait_read();                           // the dQ staging tile may be rewritten after this barrier
+      if (leader_red) tma_store_wait_read();                       // the dQ staging tile may be rewritten after this barrier
       named_bar_sync(1, NT);                                      // dV/dK partial columns drained by the whole role
       if (leader && t > 0) { tc_fence_after(); issue_dq((t - 1) & 1); }
+      if (leader_sdp && t + 1 < nt) {                              // S of the next tile as soon as pass 1 of this one is over
+        mbar_wait(&s_free, ph);
+        tc_fence_after();
+        mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+        issue_s((t + 1) & 1);
+      }
       if (t > 0) {                                                 // dQ partial of tile t-1 -> staging tile
         mbar_wait(&dq_full, (t - 1) & 1);
         tc_fence_after();
@@ -723,10 +710,14 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(2, NT);                                      // staging tile complete, dQ partial columns drained
-      if (leader) {
+      if (leader_red && t > 0) reduce_dq(tq - 1);
+      if (leader_sdp && t + 1 < nt) {                              // dP of the next tile once pass 2 has released its columns
+        mbar_wait(&pds_full, ph);
         tc_fence_after();
-        if (t > 0) reduce_dq(tq - 1);
-        mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored; S and dP columns free
+        issue_dp((t + 1) & 1);                                     // its commit (sd_full) also covers the S MMAs above
+      }
+      if (leader) {
+        mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored
         tc_fence_after();
         issue_dv_dk(t & 1, ph);
       }
@@ -738,7 +729,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const float c_dv_prev = sc_ring[(nt - 1) & 1][0], c_dk_prev = sc_ring[(nt - 1) & 1][1], c_dq_prev = sc_ring[(nt - 1) & 1][2];
       drain_dv_dk(c_dv_prev, c_dk_prev);
       tc_fence_before();
-      if (leader) tma_store_wait_read();
+      if (leader_red) tma_store_wait_read();
       named_bar_sync(1, NT);
       if (leader) { tc_fence_after(); issue_dq((nt - 1) & 1); }
       mbar_wait(&dq_full, (nt - 1) & 1);
@@ -748,7 +739,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     fence_proxy_async_smem();
     tc_fence_before();
     named_bar_sync(2, NT);
-    if (leader) { reduce_dq(nq - 1); tma_store_wait_all(); }
+    if (leader_red) { reduce_dq(nq - 1); tma_store_wait_all(); }
     // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
     const size_t krow = head_row0 + (size_t)j * 128 + row;
     __half* dk_dst = p.dk + krow * D + half * DH;
