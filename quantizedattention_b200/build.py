@@ -38,6 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-c",
                "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", CSRC, src, "-o", obj]
+        cmd += os.environ.get("QA_NVCC_EXTRA", "").split()     # development switches, e.g. -DQA_BWD_TIMELINE
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

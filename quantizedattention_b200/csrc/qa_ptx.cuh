@@ -9,7 +9,7 @@
 namespace qa {
 
 #ifndef QA_SPIN_LIMIT
-#define QA_SPIN_LIMIT (1u << 9)   // bounded mbarrier waits (each up to ~10 ms): a protocol bug traps instead of hanging
+#define QA_SPIN_LIMIT (1u << 14)   // bounded mbarrier waits (each up to ~10 ms): a protocol bug traps instead of hanging
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

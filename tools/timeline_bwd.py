@@ -1,6 +1,5 @@
-"""NOTE: the default (warp-specialised) kernel carries its stamps only when csrc/attn_int8_bwd.cu is compiled with
--DQA_BWD_TIMELINE (they cost 3-4 % through register pressure); QA_INT8_BWD_WS=0 selects the 8-warp kernel, whose stamps
-are always compiled in.
+"""NOTE: run with QA_INT8_BWD_WS=0: the stamps live in the 8-warp kernel; the default warp-specialised kernel carries
+none (they cost 3-4 % through register pressure).
 
 Per-q-tile timeline of one CTA of the int8 backward (SM clock stamps of the leader warp 0 and of warp 5).
 slots: 0 loop top | 1 S/dP ready | 2 pass 1 done | 3 dV/dK partial ready | 4 dV/dK drained | 5 barrier 1 passed |
