@@ -51,6 +51,7 @@ int qa_k_token_sum(const void* k_fp16, void* sum_f32, void* workspace, size_t ws
  * average over all keys), a mode the reference's int8 kernel does not have (Sq == Sk, Bq = Bkv = 128). */
 #define QA_FLAG_NEAREST 1
 #define QA_FLAG_CAUSAL 2
+#define QA_FLAG_BWD_8WARP 4   /* qa_int8_bwd only: the 8-warp (not warp-specialised) kernel; default = warp-specialised */
 int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* out_i8, void* scales_fp16, long long n_rows, int D,
                    int blk, int rows_per_head, int rounding, void* stream);
 
@@ -105,21 +106,6 @@ int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const 
 int qa_jvp_fwd(const void* q_bf16, const void* tq_bf16, const void* k_bf16, const void* tk_bf16, const void* v_bf16,
                const void* tv_bf16, void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit,
                void* stream);
-
-/* ---- hardware probes used by tests/test_probe_gpu.py (layout / descriptor conventions) ---- */
-int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, void* d_out, int a_lbo, int a_sbo,
-                 int a_layout, int a_kstep_bytes, int b_lbo, int b_sbo, int b_layout, int b_kstep_bytes, unsigned idesc,
-                 int kind, int n_mma, int n_cols, int a_in_tmem, int a_tmem_cols, int a_tmem_kstep_cols, void* stream);
-/* Development aid: per-k-tile SM-clock stamps of CTA (0,0) of the next qa_int8_fwd launches ([64][16] int64); NULL = off */
-int qa_debug_set_int8_fwd_timeline(void* buf);
-int qa_debug_set_int8_bwd_timeline(void* buf_i64_64x2x16);   /* same for qa_int8_bwd: leader warp and warp 5, per q-tile */
-/* TMEM -> register read bandwidth (tcgen05.ld.32x32b.x32 streamed by every warp): measured ceiling of the drains */
-int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream);
-/* shape: 0 = 32x32b.x32, 1 = 16x256b.x8, 2 = 16x128b.x16, 3 = 16x64b.x32; depth = loads in flight per warp (1, 2) */
-int qa_probe_tmem_bw_ex(void* sink, int blocks, int threads, int iters, int shape, int depth, void* stream);
-int qa_probe_tma(const void* gptr, int elem_bytes, int rank, const unsigned long long* dims,
-                 const unsigned long long* strides_bytes, const unsigned* box, int swizzle, const int* coords, void* out,
-                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqattn.so")
+DEV_LIB_PATH = os.path.join(_HERE, "libqattn_dev.so")
 _lib = None
+_dev = None
 
 c_void_p, c_int, c_size_t, c_ll, c_float, c_uint = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
                                                     ctypes.c_longlong, ctypes.c_float, ctypes.c_uint)
@@ -30,6 +32,11 @@ SIGNATURES = {
     "qa_bf16_fwd_ex": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float, c_void_p]),
     "qa_jvp_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "qa_bf16_bwd": (c_int, [c_void_p] * 10 + [c_int] * 4 + [c_void_p]),
+}
+
+
+# development library only (include/qattn_dev.h): hardware probes and kernel timeline hooks
+DEV_SIGNATURES = {
     "qa_debug_set_int8_fwd_timeline": (c_int, [c_void_p]),
     "qa_debug_set_int8_bwd_timeline": (c_int, [c_void_p]),
     "qa_probe_tmem_bw": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -39,24 +46,41 @@ SIGNATURES = {
 }
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} not found: build it with `python -m quantizedattention_b200.build` "
-                "(there is no CPU / PyTorch fallback)")
-        L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+def _load(path, tables):
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -m quantizedattention_b200.build{' --dev' if path.endswith('_dev.so') else ''}` "
+            "(there is no CPU / PyTorch fallback)")
+    L = ctypes.CDLL(path)
+    for table in tables:
+        for name, (res, args) in table.items():
             fn = getattr(L, name)          # AttributeError = header/library mismatch: fail loudly
             fn.restype, fn.argtypes = res, args
-        _lib = L
+    return L
+
+
+def lib():
+    """The product library.  QA_DEV_LIB=1 in the environment makes every call go through the development library
+    instead (same kernels compiled with the timeline hooks; tools/timeline*.py)."""
+    global _lib
+    if _lib is None:
+        if os.environ.get("QA_DEV_LIB") == "1":
+            _lib = dev_lib()
+        else:
+            _lib = _load(LIB_PATH, [SIGNATURES])
     return _lib
 
 
-def check(rc: int, what: str):
+def dev_lib():
+    global _dev
+    if _dev is None:
+        _dev = _load(DEV_LIB_PATH, [SIGNATURES, DEV_SIGNATURES])
+    return _dev
+
+
+def check(rc: int, what: str, L=None):
     if rc != 0:
-        msg = lib().qa_last_error().decode(errors="replace")
+        msg = (L or lib()).qa_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 

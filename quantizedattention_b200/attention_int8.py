@@ -12,50 +12,92 @@ contract in DESIGN.md / SURVEY.md 8-LEDGER: per-(b,h) attention, per-head K toke
 
 `Bq` / `Bkv` are the reference's tunables (PowerOfTwoFragment(32, 256, 32), attention_int8.py:155-158): the
 quantisation block sizes, returned to the caller and forwarded to backward.  The tuned values here are
-Bq = Bkv = 128 (the tcgen05 tile); `set_block_sizes` selects others: the forward runs Bq in {32,64,128,256} and
-Bkv in {32,64,128} (32/32 is the reference's untuned default), the backward needs 128/128.
+Bq = Bkv = 128 (the tcgen05 tile); pass Bq= / Bkv= per call (or `set_block_sizes` for the process default): 32/32 is
+the reference's untuned default.
 """
 from __future__ import annotations
 
 import math
-import weakref
+import threading
+import warnings
 
 import torch
 from torch.autograd import Function
 
 from . import ops
 
-# fp32 copy of the log2-LSE for the backward (LEDGER I-15), keyed by the identity of the fp16 lse tensor the forward
-# returns: forward() has no ctx in the new-style Function API, so setup_context() picks the copy up from here.  A
-# finalizer drops the entry with its key, so a forward under no_grad leaves nothing behind.
-_LSE32 = {}
-
-
-def _stash_lse32(lse16, lse32):
-    k = id(lse16)
-    _LSE32[k] = lse32
-    weakref.finalize(lse16, _LSE32.pop, k, None)
-
-_CFG = {"Bq": 128, "Bkv": 128, "nsplit": 2, "rounding": "trunc"}
+# Process-wide DEFAULTS of the tunables.  Every entry point below also takes them as per-call keyword arguments
+# (Bq=, Bkv=, rounding=), which is the re-entrant / thread-safe way to choose them; the setters only change what a call
+# without those keywords uses.
+_CFG = {"Bq": 128, "Bkv": 128, "nsplit": 0, "rounding": "trunc"}
+_CFG_LOCK = threading.Lock()
+_BQ_OK, _BKV_OK = (32, 64, 128, 256), (32, 64, 128, 256)
 
 
 def set_block_sizes(Bq: int = 128, Bkv: int = 128):
-    if Bq not in (32, 64, 128, 256) or Bkv not in (32, 64, 128):
-        raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv in {32,64,128} (backward: 128/128)")
-    _CFG["Bq"], _CFG["Bkv"] = Bq, Bkv
+    """Default quantisation block sizes (the reference's tunables, attention_int8.py:155-158) for calls that do not pass
+    Bq= / Bkv= themselves."""
+    if Bq not in _BQ_OK or Bkv not in _BKV_OK:
+        raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv in {32,64,128,256}")
+    with _CFG_LOCK:
+        _CFG["Bq"], _CFG["Bkv"] = Bq, Bkv
 
 
 def set_quant_rounding(mode: str = "trunc"):
-    """int8 rounding of every quantiser of the path (Q, K, V, P, dO, dS).  "trunc" is the reference's `.to(torch.int8)`
-    (attention_int8.py:183 etc., LEDGER I-3) and the default; "nearest" (round half to even) is the opt-in accuracy mode
-    of SURVEY.md 8f.1: it removes the truncation bias, at identical speed, but its int8 tensors are by construction
+    """Default int8 rounding of every quantiser of the path (Q, K, V, P, dO, dS).  "trunc" is the reference's
+    `.to(torch.int8)` (attention_int8.py:183 etc., LEDGER I-3); "nearest" (round half to even) is the opt-in accuracy
+    mode of SURVEY.md 8f.1: it removes the truncation bias, at identical speed, but its int8 tensors are by construction
     not the reference's.  The fused kernels are instantiated for the tuned Bkv = 128 tile in this mode."""
     if mode not in ops.ROUNDING:
         raise ValueError('rounding mode must be "trunc" or "nearest"')
-    _CFG["rounding"] = mode
+    with _CFG_LOCK:
+        _CFG["rounding"] = mode
 
 
-def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False, causal: bool = False):
+def _resolve(Bq, Bkv, rounding):
+    Bq = _CFG["Bq"] if Bq is None else int(Bq)
+    Bkv = _CFG["Bkv"] if Bkv is None else int(Bkv)
+    rounding = _CFG["rounding"] if rounding is None else rounding
+    if Bq not in _BQ_OK or Bkv not in _BKV_OK:
+        raise ValueError("supported tunables: Bq in {32,64,128,256}, Bkv in {32,64,128,256}")
+    if rounding not in ops.ROUNDING:
+        raise ValueError('rounding mode must be "trunc" or "nearest"')
+    return Bq, Bkv, rounding
+
+
+_CAUSAL_WARNED = False
+
+
+def _warn_causal():
+    global _CAUSAL_WARNED
+    if not _CAUSAL_WARNED:
+        _CAUSAL_WARNED = True
+        warnings.warn("quantizedattention_b200 int8 causal=True follows the reference's own baseline mask "
+                      "(attention_int8.py:465-473): STRICT key < query, and row 0 of every head is the uniform average over "
+                      "ALL keys (so token 0 depends on future tokens).  This is not the usual key <= query causal mask.",
+                      stacklevel=3)
+
+
+def _check_fp16(*ts):
+    for t in ts:
+        if t.dtype != torch.float16:
+            raise TypeError("int8 attention takes fp16 q, k, v")
+
+
+def _fwd_tensors(q_fp16, k_fp16, v_fp16, k_mean, Bq, Bkv, rounding, causal):
+    """Quantise (K optionally smoothed) and run the fused forward.  Returns everything either wrapper needs."""
+    batch, head, q_tokens, D = q_fp16.shape
+    k_tokens = k_fp16.shape[2]
+    q_i8, sq = ops.quant_block(q_fp16, Bq, rounding=rounding)
+    k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean, rows_per_head=k_tokens if k_mean is not None else None, rounding=rounding)
+    v_i8, sv = ops.quant_block(v_fp16, Bkv, rounding=rounding)
+    O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
+                                            nsplit=_CFG["nsplit"], want_lse32=True, rounding=rounding, causal=causal)
+    return O.view(batch, head, q_tokens, D), lse16, lse32, q_i8, k_i8, v_i8, sq, sk, sv
+
+
+def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False, causal: bool = False,
+                                 *, Bq: int | None = None, Bkv: int | None = None, rounding: str | None = None):
     """Quantise Q/K/V per block and run the fused int8 forward.  Returns the reference 10-tuple
     (O fp16 [B,H,S,D], lse fp16 [N], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv)."""
     batch, head, q_tokens, q_head_dim = q_fp16_input.shape
@@ -63,18 +105,13 @@ def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want
     _, _, v_tokens, v_head_dim = v_fp16_input.shape
     assert k_tokens == v_tokens, "k and v tokens are different"
     assert k_head_dim == v_head_dim, "k head_dim and v head_dim are different"
-    for t in (q_fp16_input, k_fp16_input, v_fp16_input):
-        if t.dtype != torch.float16:
-            raise TypeError("int8 attention takes fp16 q, k, v")
-    Bq, Bkv = _CFG["Bq"], _CFG["Bkv"]
-    D = q_head_dim
-    rnd = _CFG["rounding"]
-    q_i8, sq = ops.quant_block(q_fp16_input, Bq, rounding=rnd)
-    k_i8, sk = ops.quant_block(k_fp16_input, Bkv, rounding=rnd)
-    v_i8, sv = ops.quant_block(v_fp16_input, Bkv, rounding=rnd)
-    O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                            nsplit=_CFG["nsplit"], want_lse32=_want_lse32, rounding=rnd, causal=causal)
-    out = (O.view(batch, head, q_tokens, D), lse16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
+    _check_fp16(q_fp16_input, k_fp16_input, v_fp16_input)
+    Bq, Bkv, rounding = _resolve(Bq, Bkv, rounding)
+    if causal:
+        _warn_causal()
+    O, lse16, lse32, q_i8, k_i8, v_i8, sq, sk, sv = _fwd_tensors(q_fp16_input, k_fp16_input, v_fp16_input, None, Bq, Bkv,
+                                                                 rounding, bool(causal))
+    out = (O, lse16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
     return out + (lse32,) if _want_lse32 else out
 
 
@@ -90,15 +127,16 @@ def baseline_pytorch_attention(q, k, v, head_dim, causal):
 
 
 def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8_T, k_mean_bh_fp16, sk_bh_fp16,
-                                 v_bh_int8, sv_bh_fp16, O_input_fp16, lse_input_fp16, Bq: int, Bkv: int, causal: bool = False):
+                                 v_bh_int8, sv_bh_fp16, O_input_fp16, lse_input_fp16, Bq: int, Bkv: int, causal: bool = False,
+                                 *, rounding: str | None = None, kernel: str = "ws"):
     """Quantised backward (attention_int8.py:268-432 under the 8-LEDGER contract).  Same argument order as the
     reference; `k_mean` is the per-head token mean [B,H,1,D]; `lse` may be the fp16 tensor the forward returned
-    or an fp32 copy (LEDGER I-15).  Returns (dq, dk, dv) fp16 [B,H,S,D]."""
+    or an fp32 copy (LEDGER I-15).  `kernel`: "ws" (warp-specialised, default) or "8warp".
+    Returns (dq, dk, dv) fp16 [B,H,S,D]."""
     batch, head, q_tokens, head_dim = O_input_fp16.shape
     N = batch * head * q_tokens
     assert q_bh_int8.shape == (N, head_dim) and k_bh_int8_T.shape == (head_dim, N), "q/k int8 shapes"
-    if Bq != 128 or Bkv != 128:
-        raise ValueError("backward needs Bq = Bkv = 128 (int32 accumulation depth, SURVEY.md 7 hard part 3)")
+    _, _, rounding = _resolve(Bq, Bkv, rounding)
     k_i8 = k_bh_int8_T.t()
     if not k_i8.is_contiguous():
         k_i8 = k_i8.contiguous()
@@ -106,7 +144,7 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
     if dO.dtype != torch.float16:
         dO = dO.to(torch.float16)
     delta = ops.bwd_delta(dO, O_input_fp16)
-    do_i8, s_do = ops.quant_block(dO, Bq, rounding=_CFG["rounding"])
+    do_i8, s_do = ops.quant_block(dO, Bq, rounding=rounding)
     lse32 = lse_input_fp16.to(torch.float32).contiguous()
     km = None
     if k_mean_bh_fp16 is not None:
@@ -114,40 +152,69 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
         km = k_mean_bh_fp16.to(torch.float16).contiguous()
     dq, dk, dv = ops.int8_bwd_prequant(q_bh_int8.contiguous(), k_i8, v_bh_int8.contiguous(), do_i8, sq_bh_fp16,
                                        sk_bh_fp16, sv_bh_fp16, s_do, lse32, delta, km, batch * head, q_tokens, head_dim,
-                                       Bq, Bkv, rounding=_CFG["rounding"], causal=causal)
+                                       Bq, Bkv, rounding=rounding, causal=causal, kernel=kernel)
     shp = (batch, head, q_tokens, head_dim)
     return dq.view(shp), dk.view(shp), dv.view(shp)
 
 
+class _SageInt8Fn(Function):
+    """The Function that actually runs: the reference's 11 outputs plus the fp32 log2-LSE as a 12th, non-differentiable
+    output, so that the backward recomputes P from an fp32 lse (LEDGER I-15) without any state outside ctx.  Block sizes,
+    rounding mode and the mask are explicit arguments."""
+
+    @staticmethod
+    def forward(q_fp16, k_fp16, v_fp16, causal, Bq, Bkv, rounding):
+        k_mean_fp16 = ops.k_mean(k_fp16)                                       # K-smoothing (LEDGER I-1)
+        O, lse16, lse32, q_i8, k_i8, v_i8, sq, sk, sv = _fwd_tensors(q_fp16, k_fp16, v_fp16, k_mean_fp16, Bq, Bkv, rounding, causal)
+        return (O, lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv, lse32)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv, lse32 = output
+        ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv, lse32)
+        ctx.set_materialize_grads(False)       # do not allocate zero grads for the auxiliary outputs
+        ctx.save_for_backward(O_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
+        ctx.args = (Bq, Bkv, bool(inputs[3]), inputs[6])
+
+    @staticmethod
+    def backward(ctx, dO_fp16, *_ignored):
+        Bq, Bkv, causal, rounding = ctx.args
+        if dO_fp16 is None:
+            return (None,) * 7
+        O_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32 = ctx.saved_tensors
+        dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
+                                                  O_fp16, lse32, Bq, Bkv, causal=causal, rounding=rounding)
+        return dq, dk, dv, None, None, None, None
+
+
 class SageAttention3_Int8_autograd_function(Function):
-    """attention_int8.py:20-95.  forward(q,k,v) -> 11-tuple
-    (O, lse fp16 [N], k_mean [B,H,1,D], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv)."""
+    """attention_int8.py:20-95.  `.apply(q, k, v)` -> the reference's 11-tuple
+    (O, lse fp16 [N], k_mean [B,H,1,D], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D], sq, sk, sv, Bq, Bkv), differentiable through
+    O.  `.apply` is a thin shim over `_SageInt8Fn` (which carries the fp32 lse to its backward as a hidden 12th output);
+    `forward` / `setup_context` / `backward` keep the reference's literal signatures for callers that use them directly
+    (that route has only the fp16 lse the reference returns)."""
+
+    @classmethod
+    def apply(cls, q_fp16, k_fp16, v_fp16, causal: bool = False, *, Bq: int | None = None, Bkv: int | None = None,
+              rounding: str | None = None):
+        _check_fp16(q_fp16, k_fp16, v_fp16)
+        Bq, Bkv, rounding = _resolve(Bq, Bkv, rounding)
+        if causal:
+            _warn_causal()
+        return _SageInt8Fn.apply(q_fp16, k_fp16, v_fp16, bool(causal), Bq, Bkv, rounding)[:11]
 
     @staticmethod
     def forward(q_fp16, k_fp16, v_fp16, causal=False):
-        for t in (q_fp16, k_fp16, v_fp16):
-            if t.dtype != torch.float16:
-                raise TypeError("int8 attention takes fp16 q, k, v")
-        batch, head, q_tokens, D = q_fp16.shape
-        k_tokens = k_fp16.shape[2]
-        Bq, Bkv = _CFG["Bq"], _CFG["Bkv"]
-        k_mean_fp16 = ops.k_mean(k_fp16)                                       # K-smoothing (LEDGER I-1)
-        rnd = _CFG["rounding"]
-        q_i8, sq = ops.quant_block(q_fp16, Bq, rounding=rnd)
-        k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean_fp16, rows_per_head=k_tokens, rounding=rnd)   # fused k - mean
-        v_i8, sv = ops.quant_block(v_fp16, Bkv, rounding=rnd)
-        O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                                nsplit=_CFG["nsplit"], want_lse32=True, rounding=rnd, causal=bool(causal))
-        _stash_lse32(lse16, lse32)                                             # picked up by setup_context
-        return (O.view(batch, head, q_tokens, D), lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv)
+        _check_fp16(q_fp16, k_fp16, v_fp16)
+        Bq, Bkv, rounding = _resolve(None, None, None)
+        return _SageInt8Fn.forward(q_fp16, k_fp16, v_fp16, bool(causal), Bq, Bkv, rounding)[:11]
 
     @staticmethod
     def setup_context(ctx, inputs, output):
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv = output
         ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv)
-        ctx.set_materialize_grads(False)       # do not allocate zero grads for the 10 auxiliary outputs
-        lse32 = _LSE32.pop(id(l_bh_fp16), None)
-        ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv)
         ctx.args = (Bq, Bkv, bool(inputs[3]) if len(inputs) > 3 else False)
 
     @staticmethod
@@ -156,16 +223,16 @@ class SageAttention3_Int8_autograd_function(Function):
         pad = (None,) * (len(ctx.needs_input_grad) - 3)
         if dO_fp16 is None:
             return (None, None, None) + pad
-        O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32 = ctx.saved_tensors
+        O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv = ctx.saved_tensors
         dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
-                                                  O_fp16, lse32 if lse32 is not None else l_bh_fp16, Bq, Bkv, causal=causal)
+                                                  O_fp16, l_bh_fp16, Bq, Bkv, causal=causal)
         return (dq, dk, dv) + pad
 
 
-def sage_attention_3_int8(q_fp16, k_fp16, v_fp16, causal: bool = False):
+def sage_attention_3_int8(q_fp16, k_fp16, v_fp16, causal: bool = False, *, Bq: int | None = None, Bkv: int | None = None,
+                          rounding: str | None = None):
     """attention_int8.py:434-451: returns O fp16 [B,H,S,D], differentiable w.r.t. q, k, v.
     `causal=True` (absent in the reference's int8 kernel) applies the strict mask of the reference's own
-    `baseline_pytorch_attention(..., causal=True)`: key < query, row 0 of a head = uniform average over all keys."""
-    if causal:
-        return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16, True)[0]
-    return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16)[0]
+    `baseline_pytorch_attention(..., causal=True)`: key < query, row 0 of a head = uniform average over all keys (a
+    one-time warning says so).  Bq / Bkv / rounding: per-call tunables (default: the module defaults)."""
+    return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16, causal, Bq=Bq, Bkv=Bkv, rounding=rounding)[0]

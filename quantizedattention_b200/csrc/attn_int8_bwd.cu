@@ -15,7 +15,6 @@
 #include "qa_ptx.cuh"
 #include "qa_host.h"
 #include <type_traits>
-#include <stdlib.h>
 
 namespace qa {
 
@@ -48,11 +47,15 @@ struct Int8BwdParams {
 // pass 1 of tile t+1 runs while the tensor core computes dV_t/dK_t; dQ_t is issued one barrier later into the TMEM
 // columns freed by draining dV_t and overlaps the quantise pass of tile t+1.
 //   TMEM: [0,128) S   [128,256) dP   [256,384) dV partial, then dQ partial   [384,512) dK partial
+#ifdef QA_DEV_TIMELINE
 #define QA_TLB(slot)                                                                                          \
   do {                                                                                                        \
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 5) && t < 64) \
       p.dbg[(t * 2 + (warp != 0)) * 16 + (slot)] = clock64();                                                 \
   } while (0)
+#else
+#define QA_TLB(slot) do { } while (0)
+#endif
 
 template <int D, int NG, bool RN, bool CAUSAL>
 __global__ void __launch_bounds__(128 * NG, 1)
@@ -826,37 +829,46 @@ using namespace qa;
 
 // Backward over pre-quantised operands (Bq = Bkv = 128).  dq_ws: fp32 [BH*S, D] zero-initialised accumulation
 // workspace (cast to fp16 with qa_cast_f32 afterwards); dk, dv: fp16 [BH*S, D].
+#ifdef QA_DEV_TIMELINE
 static void* g_int8_bwd_dbg = nullptr;
-// Development aid (tools/timeline_bwd.py): CTA (0,0) of subsequent qa_int8_bwd launches records SM-clock stamps of the
-// leader warp and of warp 5 per q-tile into buf ([64 tiles][2][16] int64); NULL switches it off.  Not thread-safe.
+// Development library only (include/qattn_dev.h, tools/timeline_bwd.py): CTA (0,0) of subsequent qa_int8_bwd launches
+// records SM-clock stamps per q-tile into buf ([64 tiles][2][16] int64); NULL switches it off.  Not thread-safe.
 extern "C" int qa_debug_set_int8_bwd_timeline(void* buf) {
   g_int8_bwd_dbg = buf;
   return 0;
 }
+#endif
 
 extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
                            const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
                            void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
                            int Bq, int Bkv, int flags, void* stream) {
-  if (flags & ~(QA_FLAG_NEAREST | QA_FLAG_CAUSAL)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: unknown flag bits");
+  if (flags & ~(QA_FLAG_NEAREST | QA_FLAG_CAUSAL | QA_FLAG_BWD_8WARP)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: unknown flag bits");
   const int rounding = (flags & QA_FLAG_NEAREST) ? 1 : 0;
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
+  const bool ws = (flags & QA_FLAG_BWD_8WARP) == 0;     // warp-specialised kernel unless the caller asks for the 8-warp one
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: D must be 64 or 128");
   if (Bq != 128 || Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: Bq = Bkv = 128 required");
-  if (S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S must be a multiple of 128");
+  if (BH <= 0 || S <= 0 || S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S must be a positive multiple of 128");
+  if ((long long)BH * S >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: BH * S must be below 2^31 (TMA coordinates)");
+  if (!q_i8 || !k_i8 || !v_i8 || !do_i8 || !sq || !sk || !sv || !s_do || !lse_f32 || !delta_f32 || !dq_ws_f32 || !dk_f16 || !dv_f16)
+    return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: null pointer (only rowsum_ws may be NULL)");
+  if (((uintptr_t)q_i8 | (uintptr_t)k_i8 | (uintptr_t)v_i8 | (uintptr_t)do_i8 | (uintptr_t)dq_ws_f32 | (uintptr_t)dk_f16 | (uintptr_t)dv_f16) & 15)
+    return qa_fail(QA_ERR_ALIGN, "qa_int8_bwd: 16-byte alignment required");
   Int8BwdParams p;
   p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv; p.s_do = (const __half*)s_do;
   p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32; p.rowsum = (float*)rowsum_ws_f32;
   p.dk = (__half*)dk_f16; p.dv = (__half*)dv_f16;
-  p.S = S; p.dbg = (long long*)g_int8_bwd_dbg;
+  p.S = S;
+#ifdef QA_DEV_TIMELINE
+  p.dbg = (long long*)g_int8_bwd_dbg;
+#else
+  p.dbg = nullptr;
+#endif
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
-  const char* env = getenv("QA_INT8_BWD_NG");
-  const int ng = env ? atoi(env) : 2;
-  const char* env_ws = getenv("QA_INT8_BWD_WS");
-  const bool ws = env_ws ? atoi(env_ws) != 0 : true;    // warp-specialised kernel (default); 0 = the 8-warp kernel
-  if (ws && !env) {
+  if (ws) {
     int rc;
 #define QA_WS(DD, RNN, CC) launch_int8_bwd<DD, 2, RNN, CC, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
     if (causal && rounding) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: causal is built for truncation mode");
@@ -883,8 +895,6 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   if (rounding == 1)                                              // accuracy mode: instantiated for the default shape only
     return D == 128 ? launch_int8_bwd<128, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
                     : launch_int8_bwd<64, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
-  if (D == 128) return ng == 2 ? launch_int8_bwd<128, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
-                               : launch_int8_bwd<128, 4>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
-  return ng == 2 ? launch_int8_bwd<64, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
-                 : launch_int8_bwd<64, 4>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
+  return D == 128 ? launch_int8_bwd<128, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
+                  : launch_int8_bwd<64, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
 }

@@ -24,6 +24,9 @@
 namespace qa {
 
 constexpr int kBM = 128;    // query rows per CTA (= tcgen05 M)
+#ifndef QA_DRAIN_W
+#define QA_DRAIN_W 16
+#endif
 // BN = keys per k-tile = Bkv (the reference's tunable, attention_int8.py:158): 128 is the tuned value; 32 (the reference
 // default) and 64 run the same kernel with narrower S tiles -- one online-softmax step, one P scale per row and one
 // drained P.V partial per Bkv keys, exactly as the reference's k-tile loop -- at proportionally more TMEM drains.
@@ -36,7 +39,8 @@ struct Int8FwdSmem {
   static constexpr int off_q = 0;
   static constexpr int off_k = off_q + kQBytes;
   static constexpr int off_v = off_k + STAGES * kKBytes;
-  static constexpr int off_end = off_v + STAGES * kVBytes;
+  static constexpr int off_c = off_v + STAGES * kVBytes;      // constant fp16 tiles (A, B) of the accumulator-initialising MMA (MG)
+  static constexpr int off_end = off_c + 2 * kQBytes;
   static constexpr int total = off_end + 1024;   // + alignment slack
 };
 
@@ -58,13 +62,28 @@ struct Int8FwdParams {
   long long* dbg;        // optional timeline buffer [tile][16] of SM clock stamps written by CTA (0,0) (tools/timeline.py)
 };
 
+// Timeline stamps exist only in development builds (-DQA_DEV_TIMELINE, libqattn_dev.so; tools/timeline.py): the shipped
+// kernel carries no debug hooks.
+#ifdef QA_DEV_TIMELINE
 #define QA_TL(slot)                                                                                   \
   do {                                                                                                \
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < 64)                \
       p.dbg[j * 16 + (slot)] = clock64();                                                             \
   } while (0)
+#define QA_TLX(cond, idx, slot)                                                                       \
+  do {                                                                                                \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (cond)) p.dbg[(idx) * 16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define QA_TL(slot) do { } while (0)
+#define QA_TLX(cond, idx, slot) do { } while (0)
+#endif
 
-template <int D, int NSPLIT, int STAGES, int BN, bool RN, bool CAUSAL>
+// MG ("magic" accumulators, two-stage kernel only): every S and P.V accumulator is initialised by a kind::f16 MMA over a
+// constant tile to kMagic (qa_ptx.cuh), so the int32 results are read back as floats kMagic + x and the int -> float
+// conversions fold into the scale FMAs; the exp warps fold the P scale into the exponent (one FHADD per element takes the
+// fp16 logit to fp32, subtracts the running maximum and adds log2(127 / sp)), so exp2 yields P / sp directly.
+template <int D, int NSPLIT, int STAGES, int BN, bool RN, bool CAUSAL, bool MG>
 __global__ void __launch_bounds__(256 * NSPLIT + 128, 1)
 int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
@@ -82,6 +101,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr int kSBuf = (NSPLIT == 2) ? 3 : 2, kOBuf = (NSPLIT == 2) ? 1 : 2;
   constexpr uint32_t kOCol = kSBuf * 128;
   static_assert(NSPLIT == 1 || BN == 128, "the two-stage softmax is laid out for 128-key tiles");
+  static_assert(!MG || NSPLIT == 2, "magic accumulators are built into the two-stage kernel");
   constexpr uint32_t kLayoutQK = (D == 128) ? kSwz128 : kSwz64;   // rows of D bytes
   constexpr uint32_t kSboQK = (D == 128) ? 1024 : 512;
 
@@ -118,6 +138,14 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 8 * NSPLIT + 1) tmem_alloc<512>(&tmem_base_s);
+  if (MG) {                                                      // constant operand tiles: every fp16 element = 1024 (A) / 768 (B)
+    const uint32_t c_addr = smem_u32(smem + L::off_c);
+    for (int i = tid * 16; i < L::kQBytes; i += (256 * NSPLIT + 128) * 16) {
+      sts128(c_addr + i, kMagicElemA2, kMagicElemA2, kMagicElemA2, kMagicElemA2);
+      sts128(c_addr + L::kQBytes + i, kMagicElemB2, kMagicElemB2, kMagicElemB2, kMagicElemB2);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -209,6 +237,37 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       //      (4 int8 per column): the P V MMA takes its A operand straight from TMEM (no shared-memory round trip,
       //      no proxy fence, no second buffer to wait for - the S buffer is ours until that MMA has been issued)
       if (warp == 0) { QA_TL(3); QA_TL(4); }
+      if (MG) {
+        // y = P / sp = exp2(S16 - m + log2(127 / sp_e)): prm.y = log2(127) - (rmax - m) - m from the logit warps.  The
+        // subtraction S16 - m is taken in fp32 here (the reference rounds it to fp16 first, attention_int8.py:211-213;
+        // the two differ by < 2^-9 in the exponent, and only for entries at least 2^-4 below the row maximum).
+        // trunc(y) is the bit pattern of the subnormal y * 2^-149 rounded toward zero; I2IP saturates y in (127, 128.5).
+        const float kk = prm.y;
+        float2 ys2 = make_float2(0.f, 0.f);
+        const float2 tiny2 = make_float2(1.401298464324817e-45f, 1.401298464324817e-45f);
+#pragma unroll
+        for (int g = 0; g < NC / 32; ++g) {
+          uint32_t w[8];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint32_t h0 = *reinterpret_cast<uint32_t*>(&sh[g * 16 + q4 * 2]), h1 = *reinterpret_cast<uint32_t*>(&sh[g * 16 + q4 * 2 + 1]);
+            const float2 y0 = make_float2(ex2_approx(fhadd_lo(h0, kk)), ex2_approx(fhadd_hi(h0, kk)));
+            const float2 y1 = make_float2(ex2_approx(fhadd_lo(h1, kk)), ex2_approx(fhadd_hi(h1, kk)));
+            ys2 = __fadd2_rn(ys2, y0);
+            ys2 = __fadd2_rn(ys2, y1);
+            const float2 q0 = RN ? __fmul2_rn(y0, tiny2) : __fmul2_rz(y0, tiny2);
+            const float2 q1 = RN ? __fmul2_rn(y1, tiny2) : __fmul2_rz(y1, tiny2);
+            w[q4] = pack_sat_s8x4(__float_as_int(q0.x), __float_as_int(q0.y), __float_as_int(q1.x), __float_as_int(q1.y));
+          }
+          tmem_st8(lane_addr + sb * 128 + kPOff + c0 / 4 + g * 8, w);
+        }
+        tmem_st_wait();
+        l = l * prm.x + (ys2.x + ys2.y) * prm.z;                   // sum(P) = sum(y) * sp   (attention_int8.py:215-223)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sb]);
+        continue;
+      }
       const __half2 m2 = __half2half2(m_new);       // (causal: the logit warps publish 0 while a row has seen no key)
       float2 ls2 = make_float2(0.f, 0.f);
       const float2 inv2 = make_float2(inv_sp, inv_sp), magic2 = make_float2(8388608.0f, 8388608.0f);
@@ -261,8 +320,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (p.m_in != nullptr) m16 = __float2half_rn(p.m_in[(size_t)bh * p.Sq + q0 + row]);
     for (int j = 0; j < nk; ++j) {
       const int sb = j % kSBuf;
-      const float c = sq_f * __half2float(sk_p[j]) * p.qk_scale;
-      const float2 c2 = make_float2(c, c);
+      const float c = MG ? magic_scale(sq_f * __half2float(sk_p[j]) * p.qk_scale) : sq_f * __half2float(sk_p[j]) * p.qk_scale;
+      const float2 c2 = make_float2(c, c), nb2 = make_float2(-kMagic * c, -kMagic * c);       // kMagic * c is exact
       mbar_wait(&s_full[sb], (j / kSBuf) & 1);
       tc_fence_after();
       __half2 mx2 = __float2half2_rn(-INFINITY);
@@ -277,7 +336,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
-            const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
+            const float2 a = MG ? __ffma2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nb2)   // (kMagic + x) * c - kMagic * c
+                                : __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
             __half2 h = __float22half2_rn(a);
             if (decltype(masked)::value) {                         // strict causal: keep key < query (same tile: col < row)
               const int col = ch * 32 + 2 * i;
@@ -288,8 +348,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mx2 = __hmax2(mx2, h);
             w[i] = *reinterpret_cast<uint32_t*>(&h);
           }
-          tmem_st8(dst, *reinterpret_cast<uint32_t (*)[8]>(&w[0]));
-          tmem_st8(dst + 8, *reinterpret_cast<uint32_t (*)[8]>(&w[8]));
+          tmem_st16(dst, w);
         }
       };
       if (CAUSAL && j * kBN == q0) pass1(std::true_type{}); else pass1(std::false_type{});
@@ -303,6 +362,11 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (__hisinf(rmax)) { sp_e = 0.f; inv_sp = 0.f; }
       }
       m16 = m_new;
+      if (MG) {                                       // (rescale, exponent offset of y = P / sp, sp, sp * sv)
+        const float dsp = __half2float(__hsub(rmax, m_new));
+        const float kk = (CAUSAL && __hisinf(rmax)) ? 0.f : (6.988684686772166f + 2.0e-6f) - dsp - __half2float(m_new);   // log2(127) + eps: the row maximum quantises to 127
+        prm_s[j & 3][row] = make_float4(rescale, kk, sp_e * (1.0f / 127.0f), sp_e * (1.0f / 127.0f) * __half2float(sv_p[j]));
+      } else
       prm_s[j & 3][row] = make_float4(rescale, inv_sp, (CAUSAL && __hisinf(m_new)) ? 0.f : __half2float(m_new),
                                       sp_e * (1.0f / 127.0f) * __half2float(sv_p[j]));
       tmem_st_wait();
@@ -354,12 +418,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (lane == 0) mbar_arrive(&sc_empty[b]);
       }
       // Lazy rescale: the accumulator holds O / s_pend, so O*rescale + x*c (attention_int8.py:225, 249-250) costs one
-      // FMA per element: s_pend *= rescale; acc += x * (c / s_pend).  rescale == 0 only on a fresh first tile (acc == 0).
-      if (sc.x != 0.f) s_pend *= sc.x;
-      if (__any_sync(0xffffffffu, s_pend < 1e-12f)) {       // rare: fold the pending factor back in before it underflows
+      // FMA per element: s_pend *= rescale; acc += x * (c / s_pend).
+      float fold = 1.0f;                            // usually nothing to do
+      if (sc.x != 0.f) s_pend *= sc.x; else { fold = 0.f; s_pend = 1.0f; }
+      if (s_pend < 1e-18f) { fold = s_pend; s_pend = 1.0f; }
+      if (__any_sync(0xffffffffu, fold != 1.0f)) {
 #pragma unroll
-        for (int i = 0; i < DCx / 2; ++i) acc2[i] = __fmul2_rn(acc2[i], make_float2(s_pend, s_pend));
-        s_pend = 1.0f;
+        for (int i = 0; i < DCx / 2; ++i) acc2[i] = __fmul2_rn(acc2[i], make_float2(fold, fold));
       }
       const float c_eff = __fdividef(sc.y, s_pend);
       const float2 ce2 = make_float2(c_eff, c_eff);
@@ -368,13 +433,17 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       if (cw == 0 || (kTwoStage && cw == 4)) QA_TL(7);
 #pragma unroll
-      for (int ch = 0; ch < DCx / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + kOCol + ob * 128 + d0 + ch * 32, r);
+      for (int ch = 0; ch < DCx / QA_DRAIN_W; ++ch) {
+        uint32_t r[QA_DRAIN_W];
+        if (QA_DRAIN_W == 32) tmem_ld32(lane_addr + kOCol + ob * 128 + d0 + ch * 32, *reinterpret_cast<uint32_t (*)[32]>(&r[0]));
+        else tmem_ld16(lane_addr + kOCol + ob * 128 + d0 + ch * 16, *reinterpret_cast<uint32_t (*)[16]>(&r[0]));
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          acc2[ch * 16 + i] = __ffma2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), ce2, acc2[ch * 16 + i]);
+        for (int i = 0; i < QA_DRAIN_W / 2; ++i) {
+          const float2 x = MG ? __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), make_float2(-kMagic, -kMagic))   // exact
+                              : make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1]));
+          acc2[ch * (QA_DRAIN_W / 2) + i] = __ffma2_rn(x, ce2, acc2[ch * (QA_DRAIN_W / 2) + i]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -440,18 +509,23 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc_qk = umma_idesc(2, 1, 1, 0, 0, kBM, kBN);          // s32 += s8 x s8, both K-major
       constexpr uint32_t idesc_pv = umma_idesc(2, 1, 1, 0, 1, kBM, D);            // B = V: MN-major
       const uint32_t q_addr = smem_u32(smem + L::off_q);
+      // accumulator initialisation (MG): D = A B^T over K = 16 fp16 elements of the constant tiles = kMagic everywhere
+      constexpr uint32_t idesc_cqk = umma_idesc(1, 0, 0, 0, 0, kBM, kBN), idesc_cpv = umma_idesc(1, 0, 0, 0, 0, kBM, D);
+      const uint64_t cdesc_a = umma_smem_desc(smem_u32(smem + L::off_c), 16, kSboQK, kLayoutQK);
+      const uint64_t cdesc_b = umma_smem_desc(smem_u32(smem + L::off_c + L::kQBytes), 16, kSboQK, kLayoutQK);
       auto issue_pv = [&](int t) {                                 // Opart[b] = P_t V_t, P from TMEM (S[b] columns)
         const int sb = t % kSBuf, ob = t % kOBuf, s = t % STAGES;
         mbar_wait(&v_full[s], (t / STAGES) & 1);
         mbar_wait(&o_empty[ob], ((t / kOBuf) & 1) ^ 1);
         mbar_wait(&p_full[sb], (t / kSBuf) & 1);
         tc_fence_after();
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t < 64) p.dbg[t * 16 + 11] = clock64();   // PV issue
+        QA_TLX(t < 64, t, 11);   // PV issue
         const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kVBytes);
+        if (MG) umma_f16_ss(tbase + kOCol + ob * 128, cdesc_a, cdesc_b, idesc_cpv, 0);     // Opart = kMagic
 #pragma unroll
         for (int k = 0; k < kBN / 32; ++k) {
           const uint64_t bd = umma_smem_desc(v_addr + k * 32 * D, 16, kSboQK, kLayoutQK);
-          umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * 128 + kPOff + k * 8, bd, idesc_pv, k > 0);
+          umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * 128 + kPOff + k * 8, bd, idesc_pv, MG || k > 0);
         }
         umma_commit(&o_full[ob]);
         umma_commit(&v_empty[s]);
@@ -459,13 +533,14 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto issue_qk = [&](int j) {                                 // S[b] = Q K_j^T
         const int sb = j % kSBuf, s = j % STAGES;
         mbar_wait(&k_full[s], (j / STAGES) & 1);
-        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && j < 64) { p.dbg[j * 16 + 9] = clock64(); p.dbg[j * 16 + 10] = clock64(); }
+        QA_TLX(j < 64, j, 9);
         const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
+        if (MG) umma_f16_ss(tbase + sb * 128, cdesc_a, cdesc_b, idesc_cqk, 0);             // S = kMagic
 #pragma unroll
         for (int k = 0; k < D / 32; ++k) {
           const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, kSboQK, kLayoutQK);
           const uint64_t bd = umma_smem_desc(k_addr + k * 32, 16, kSboQK, kLayoutQK);
-          umma_i8_ss(tbase + sb * 128, ad, bd, idesc_qk, k > 0);
+          umma_i8_ss(tbase + sb * 128, ad, bd, idesc_qk, MG || k > 0);
         }
         umma_commit(&s_full[sb]);
         umma_commit(&k_empty[s]);
@@ -516,7 +591,7 @@ __global__ void __launch_bounds__(512) int8_row0_fixup_kernel(const int8_t* __re
   }
 }
 
-template <int D, int NSPLIT, int STAGES, int BN, bool RN = false, bool CAUSAL = false>
+template <int D, int NSPLIT, int STAGES, int BN, bool RN = false, bool CAUSAL = false, bool MG = false>
 static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const Int8FwdParams& p, int BH,
                            cudaStream_t st) {
   using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
@@ -530,7 +605,7 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
   if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
   if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
-  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN, CAUSAL>;
+  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN, CAUSAL, MG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / kBM, BH);
@@ -542,13 +617,15 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
 
 using namespace qa;
 
+#ifdef QA_DEV_TIMELINE
 static void* g_int8_fwd_dbg = nullptr;
-// Development aid: CTA (0,0) of subsequent qa_int8_fwd launches records SM-clock stamps per k-tile into buf
-// ([64 tiles][16 slots] int64); pass NULL to switch it off.  Not thread-safe; used by tools/timeline.py only.
+// Development library only (include/qattn_dev.h): CTA (0,0) of subsequent qa_int8_fwd launches records SM-clock stamps
+// per k-tile into buf ([64 tiles][16 slots] int64); NULL switches it off.  Not thread-safe; used by tools/timeline.py.
 extern "C" int qa_debug_set_int8_fwd_timeline(void* buf) {
   g_int8_fwd_dbg = buf;
   return 0;
 }
+#endif
 
 // Forward over pre-quantised operands.  q_i8 [BH*Sq, D], k_i8 / v_i8 [BH*Sk, D] int8 row-major; sq [BH*Sq/Bq],
 // sk / sv [BH*Sk/Bkv] fp16.  Outputs: O fp16 [BH*Sq, D], lse16 fp16 [BH*Sq], lse32 fp32 [BH*Sq] (optional).
@@ -573,13 +650,20 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   p.O_acc_in = (const float*)o_acc_in; p.m_in = (const float*)m_in; p.l_in = (const float*)l_in;
   p.Sq = Sq; p.Sk = Sk; p.Bq = Bq;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+#ifdef QA_DEV_TIMELINE
   p.dbg = (long long*)g_int8_fwd_dbg;
+#else
+  p.dbg = nullptr;
+#endif
   cudaStream_t st = (cudaStream_t)stream;
+  // nsplit: 0 = default kernel for the tile; 1 = single-stage softmax (one thread per row); 2 = two-stage softmax without
+  // magic accumulators (A/B comparison).  Bkv = 128 defaults to the two-stage kernel with magic accumulators.
+  if (nsplit != 0 && nsplit != 1 && nsplit != 2) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nsplit must be 0, 1 or 2");
   if (causal) {                                                  // instantiated for the tuned tile only
-    if (Bkv != 128 || Bq != 128 || nsplit != 2 || rounding || Sq != Sk || o_acc != nullptr || o_acc_in != nullptr)
-      return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: causal needs Sq == Sk, Bq = Bkv = 128, nsplit = 2, truncation, no ring state");
-    int rc = D == 128 ? launch_int8_fwd<128, 2, 3, 128, false, true>(q_i8, k_i8, v_i8, p, BH, st)
-                      : launch_int8_fwd<64, 2, 4, 128, false, true>(q_i8, k_i8, v_i8, p, BH, st);
+    if (Bkv != 128 || Bq != 128 || nsplit == 1 || rounding || Sq != Sk || o_acc != nullptr || o_acc_in != nullptr)
+      return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: causal needs Sq == Sk, Bq = Bkv = 128, the two-stage kernel, truncation, no ring state");
+    int rc = D == 128 ? launch_int8_fwd<128, 2, 3, 128, false, true, true>(q_i8, k_i8, v_i8, p, BH, st)
+                      : launch_int8_fwd<64, 2, 4, 128, false, true, true>(q_i8, k_i8, v_i8, p, BH, st);
     if (rc) return rc;
     if (D == 128) int8_row0_fixup_kernel<128><<<BH, 512, 0, st>>>((const int8_t*)v_i8, p.sv, p.O, p.lse16, p.lse32, Sq);
     else int8_row0_fixup_kernel<64><<<BH, 512, 0, st>>>((const int8_t*)v_i8, p.sv, p.O, p.lse16, p.lse32, Sq);
@@ -587,10 +671,13 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   }
   if (Bkv == 128) {
     if (rounding == 1) {                                         // accuracy mode: instantiated for the tuned tile only
-      if (nsplit != 2) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nearest rounding needs nsplit = 2");
-      return D == 128 ? launch_int8_fwd<128, 2, 3, 128, true>(q_i8, k_i8, v_i8, p, BH, st)
-                      : launch_int8_fwd<64, 2, 4, 128, true>(q_i8, k_i8, v_i8, p, BH, st);
+      if (nsplit == 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nearest rounding needs the two-stage kernel");
+      return D == 128 ? launch_int8_fwd<128, 2, 3, 128, true, false, true>(q_i8, k_i8, v_i8, p, BH, st)
+                      : launch_int8_fwd<64, 2, 4, 128, true, false, true>(q_i8, k_i8, v_i8, p, BH, st);
     }
+    if (nsplit == 0)                                             // two-stage kernel with magic accumulators
+      return D == 128 ? launch_int8_fwd<128, 2, 3, 128, false, false, true>(q_i8, k_i8, v_i8, p, BH, st)
+                      : launch_int8_fwd<64, 2, 4, 128, false, false, true>(q_i8, k_i8, v_i8, p, BH, st);
     if (D == 128) return nsplit == 2 ? launch_int8_fwd<128, 2, 3, 128>(q_i8, k_i8, v_i8, p, BH, st)
                                      : launch_int8_fwd<128, 1, 3, 128>(q_i8, k_i8, v_i8, p, BH, st);
     return nsplit == 2 ? launch_int8_fwd<64, 2, 4, 128>(q_i8, k_i8, v_i8, p, BH, st)

@@ -15,7 +15,7 @@ enum {
   QA_ERR_DRIVER = -6,
 };
 
-enum { QA_FLAG_NEAREST = 1, QA_FLAG_CAUSAL = 2 };   // `flags` of qa_int8_fwd / qa_int8_bwd (include/qattn.h)
+enum { QA_FLAG_NEAREST = 1, QA_FLAG_CAUSAL = 2, QA_FLAG_BWD_8WARP = 4 };   // `flags` of qa_int8_fwd / qa_int8_bwd (include/qattn.h)
 
 int qa_fail(int code, const char* msg);            // records msg in the thread-local error slot, returns code
 int qa_check_launch(const char* where);            // cudaGetLastError -> QA_OK / QA_ERR_CUDA (never synchronises)

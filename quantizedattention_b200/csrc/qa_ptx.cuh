@@ -221,6 +221,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -247,6 +254,39 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // low bytes of four 32-bit words -> one word (w0 lowest): 3 PRMTs
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
   return prmt(prmt(w0, w1, 0x0040u), prmt(w2, w3, 0x0040u), 0x5410u);
+}
+// ---------------------------------------------------------------- "magic" accumulators (int8 kernels)
+// A kind::f16 MMA over two constant shared-memory tiles (every fp16 element of A = 1024, of B = 768, K = 16) initialises
+// an fp32 accumulator to kMagic = 16 * 1024 * 768 = 1.5 * 2^23 = 12582912.0f (bits 0x4B400000), a value of the binade
+// [2^23, 2^24) where one unit in the last place is 1.  The kind::i8 MMAs that follow accumulate int32 onto that bit
+// pattern, so the accumulator read back as a FLOAT is exactly kMagic + x for every |x| <= 127*127*128 < 2^22: the
+// int32 -> fp32 conversion (one I2FP per element) disappears into the FFMA that applies the de-quantisation scale,
+//   x*c = fma(bits_as_float, c, -kMagic*c),
+// which is exactly rounded when kMagic*c is representable, i.e. when c carries at most 22 significant bits
+// (magic_scale() rounds the scale to 22 bits: relative change <= 2^-22, below the fp32 rounding of the scale itself).
+constexpr float kMagic = 12582912.0f;
+constexpr uint32_t kMagicElemA2 = 0x64006400u;       // two fp16 1024.0
+constexpr uint32_t kMagicElemB2 = 0x62006200u;       // two fp16 768.0
+__device__ __forceinline__ float magic_scale(float c) {   // c rounded to 22 significant bits: kMagic * c is then exact
+  return __uint_as_float((__float_as_uint(c) + 2u) & 0xFFFFFFFCu);
+}
+// Mixed-precision add (PTX ISA 8.6, sm_100: SASS FHADD): float(h.lo / h.hi) + c in one instruction
+__device__ __forceinline__ float fhadd_lo(uint32_t h2, float c) {
+  float d;
+  asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, lo, %2;}" : "=f"(d) : "r"(h2), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhadd_hi(uint32_t h2, float c) {
+  float d;
+  asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, hi, %2;}" : "=f"(d) : "r"(h2), "f"(c));
+  return d;
+}
+// four int32 (each already in [-128, 127] or saturated to it) -> four int8 in one word, w0 lowest: 2 x I2IP
+__device__ __forceinline__ uint32_t pack_sat_s8x4(int w0, int w1, int w2, int w3) {
+  uint32_t t, o;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(w3), "r"(w2), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(o) : "r"(w1), "r"(w0), "r"(t));
+  return o;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

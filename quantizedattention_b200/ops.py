@@ -75,7 +75,7 @@ def k_mean(k: torch.Tensor) -> torch.Tensor:
 
 
 ROUNDING = {"trunc": 0, "nearest": 1}       # int8 rounding of the quantisers: the reference truncates (LEDGER I-3)
-FLAG_NEAREST, FLAG_CAUSAL = 1, 2            # `flags` of qa_int8_fwd / qa_int8_bwd (include/qattn.h)
+FLAG_NEAREST, FLAG_CAUSAL, FLAG_BWD_8WARP = 1, 2, 4      # `flags` of qa_int8_fwd / qa_int8_bwd (include/qattn.h)
 
 
 def _flags(rounding: str, causal: bool) -> int:
@@ -118,9 +118,11 @@ def k_token_sum(k: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=2, want_lse32=True,
+def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=0, want_lse32=True,
                       ring_state=False, state_in=None, rounding: str = "trunc", causal: bool = False):
     """Fused int8 attention forward over pre-quantised operands (qa_int8_fwd).
+    nsplit: 0 = the default kernel for the tile (Bkv = 128: two-stage softmax with magic accumulators); 1 = single-stage
+    softmax (one thread per row); 2 = two-stage softmax without magic accumulators (kept for A/B comparison).
     Returns (O fp16 [BH*Sq, D], lse16 [BH*Sq], lse32 or None); with ring_state=True returns the unnormalised
     (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead."""
     _need_cuda(q_i8, k_i8, v_i8, sq, sk, sv)
@@ -178,8 +180,12 @@ def cast_f32(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128,
-                      rounding: str = "trunc", causal: bool = False):
-    """Fused int8 backward over pre-quantised operands (qa_int8_bwd).  Returns (dq, dk, dv) fp16 [BH*S, D]."""
+                      rounding: str = "trunc", causal: bool = False, kernel: str = "ws"):
+    """Fused int8 backward over pre-quantised operands (qa_int8_bwd).  Returns (dq, dk, dv) fp16 [BH*S, D].
+    kernel: "ws" = the warp-specialised kernel (default), "8warp" = the 8-warp kernel (QA_FLAG_BWD_8WARP)."""
+    if kernel not in ("ws", "8warp"):
+        raise ValueError('kernel must be "ws" or "8warp"')
+    flags = _flags(rounding, causal) | (FLAG_BWD_8WARP if kernel == "8warp" else 0)
     _need_cuda(q_i8, k_i8, v_i8, do_i8)
     dev = q_i8.device
     dq_ws = torch.zeros((BH * S, D), dtype=torch.float32, device=dev)
@@ -194,7 +200,7 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
         with _timed("int8_bwd"):
             _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
                                      _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(rowsum_ws),
-                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, _flags(rounding, causal), _lib.cur_stream()),
+                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, flags, _lib.cur_stream()),
                        "qa_int8_bwd")
         _lib.check(L.qa_int8_bwd_finalize(_lib.ptr(dq_ws), _lib.ptr(rowsum_ws), _lib.ptr(k_mean), _lib.ptr(dq), BH, S, D,
                                           _lib.cur_stream()), "qa_int8_bwd_finalize")

@@ -42,7 +42,7 @@ class RingInt8Kernels:
     def quant(self, x, blk, mean=None, rows_per_head=None):  # -> (int8 [N,D], fp16 scales)
         raise NotImplementedError
 
-    def attend(self, q_i8, sq, kv, state, BH, Sq, Sk, D, Bq, last):
+    def attend(self, q_i8, sq, kv, state, BH, Sq, Sk, D, Bq, Bkv, last):
         """Attend the local queries to one K/V shard `kv = (k_i8, v_i8, sk, sv)`, continuing `state`
         (None or (O_acc, m, l)).  last=False -> new state; last=True -> (O fp16, lse16, lse32)."""
         raise NotImplementedError
@@ -57,10 +57,10 @@ class CudaRingKernels(RingInt8Kernels):
         from . import ops
         return ops.quant_block(x, blk, mean=mean, rows_per_head=rows_per_head)
 
-    def attend(self, q_i8, sq, kv, state, BH, Sq, Sk, D, Bq, last):
+    def attend(self, q_i8, sq, kv, state, BH, Sq, Sk, D, Bq, Bkv, last):
         from . import ops
         k_i8, v_i8, sk, sv = kv
-        return ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq, 128, ring_state=not last,
+        return ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq, Bkv, ring_state=not last,
                                      state_in=state, want_lse32=True)
 
 
@@ -95,7 +95,7 @@ def ring_int8_attention_fwd(q, k, v, Bq: int = 128, Bkv: int = 128, group=None, 
             else:
                 reqs = dist.batch_isend_irecv(ops_)
         last = step == world - 1
-        res = kernels.attend(q_i8, sq, cur, state, BH, Sl, Sl, D, Bq, last)
+        res = kernels.attend(q_i8, sq, cur, state, BH, Sl, Sl, D, Bq, Bkv, last)
         if last:
             out = res
         else:

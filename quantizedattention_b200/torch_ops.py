@@ -81,10 +81,12 @@ def _sage_backward(ctx, dO, *_unused):
 sage_int8_fwd.register_autograd(_sage_backward, setup_context=_sage_setup)
 
 
-def sage_attention_3_int8_op(q_fp16: _T, k_fp16: _T, v_fp16: _T) -> _T:
-    """`sage_attention_3_int8` (attention_int8.py:434-451) as a traceable operator: O fp16 [B,H,S,D]."""
-    cfg = _int8._CFG
-    return sage_int8_fwd(q_fp16, k_fp16, v_fp16, cfg["Bq"], cfg["Bkv"], cfg["rounding"] == "nearest")[0]
+def sage_attention_3_int8_op(q_fp16: _T, k_fp16: _T, v_fp16: _T, *, Bq: int | None = None, Bkv: int | None = None,
+                             rounding: str | None = None) -> _T:
+    """`sage_attention_3_int8` (attention_int8.py:434-451) as a traceable operator: O fp16 [B,H,S,D].  Bq / Bkv / rounding
+    are per-call arguments (default: the module defaults of attention_int8 at call / trace time)."""
+    Bq, Bkv, rounding = _int8._resolve(Bq, Bkv, rounding)
+    return sage_int8_fwd(q_fp16, k_fp16, v_fp16, Bq, Bkv, rounding == "nearest")[0]
 
 
 # ------------------------------------------------------------------------------------------------ bf16 flash attention

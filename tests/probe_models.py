@@ -33,7 +33,7 @@ def idesc(c_fmt, a_fmt, b_fmt, a_major, b_major, M, N):
 
 def run_mma(a_img, b_img, n_cols, *, a_lbo=16, a_sbo=1024, a_layout=2, a_kstep=32, b_lbo=16, b_sbo=1024, b_layout=2,
             b_kstep=32, idesc_v=0, kind=1, n_mma=4, a_in_tmem=0, a_tmem_cols=0, a_tmem_kstep_cols=8):
-    L = _lib.lib()
+    L = _lib.dev_lib()
     a = torch.from_numpy(np.ascontiguousarray(a_img).view(np.uint8).reshape(-1)).cuda()
     b = torch.from_numpy(np.ascontiguousarray(b_img).view(np.uint8).reshape(-1)).cuda()
     pad = lambda t: torch.cat([t, torch.zeros((-t.numel()) % 16, dtype=torch.uint8, device="cuda")])
@@ -42,13 +42,13 @@ def run_mma(a_img, b_img, n_cols, *, a_lbo=16, a_sbo=1024, a_layout=2, a_kstep=3
     rc = L.qa_probe_mma(_lib.ptr(a), a.numel(), _lib.ptr(b), b.numel(), _lib.ptr(d), a_lbo, a_sbo, a_layout, a_kstep,
                         b_lbo, b_sbo, b_layout, b_kstep, ctypes.c_uint(idesc_v), kind, n_mma, n_cols, a_in_tmem,
                         a_tmem_cols, a_tmem_kstep_cols, _lib.cur_stream())
-    _lib.check(rc, "qa_probe_mma")
+    _lib.check(rc, "qa_probe_mma", L)
     torch.cuda.synchronize()
     return d.cpu()
 
 
 def run_tma(src: torch.Tensor, elem_bytes, dims, strides_bytes, box, swizzle, coords):
-    L = _lib.lib()
+    L = _lib.dev_lib()
     rank = len(dims)
     nbytes = elem_bytes * int(np.prod(box))
     out = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
@@ -60,6 +60,6 @@ def run_tma(src: torch.Tensor, elem_bytes, dims, strides_bytes, box, swizzle, co
     b = U32(*(list(box) + [1] * (3 - rank)))
     c = I32(*(list(coords) + [0] * (3 - rank)))
     rc = L.qa_probe_tma(_lib.ptr(src), elem_bytes, rank, d, s, b, swizzle, c, _lib.ptr(out), _lib.cur_stream())
-    _lib.check(rc, "qa_probe_tma")
+    _lib.check(rc, "qa_probe_tma", L)
     torch.cuda.synchronize()
     return out.cpu().numpy()

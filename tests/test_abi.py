@@ -11,8 +11,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols():
-    src = open(os.path.join(ROOT, "include", "qattn.h")).read()
+def _header_symbols(name="qattn.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(qa_[a-z0-9_]+)\s*\(", src)))
 
@@ -27,6 +27,23 @@ def test_library_exports_every_header_symbol():
         assert hasattr(L, s), f"{s} declared in include/qattn.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), "ctypes table and header disagree"
     assert _lib.lib().qa_version() >= 100
+    # the product library carries no probe / debug entry points, its sources no environment switches
+    assert not [s for s in syms if s.startswith(("qa_probe", "qa_debug"))]
+    for s in _header_symbols("qattn_dev.h"):
+        assert not hasattr(L, s), f"{s} is a development symbol but libqattn.so exports it"
+    csrc = os.path.join(ROOT, "quantizedattention_b200", "csrc")
+    for f in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f"{f}: kernel selection must be an argument, not an env var"
+
+
+def test_dev_library_exports_dev_header():
+    from quantizedattention_b200 import _lib, build
+    build.build(dev=True)
+    L = ctypes.CDLL(_lib.DEV_LIB_PATH)
+    dev = _header_symbols("qattn_dev.h")
+    assert set(dev) == set(_lib.DEV_SIGNATURES), "ctypes dev table and qattn_dev.h disagree"
+    for s in dev + _header_symbols():
+        assert hasattr(L, s), s
 
 
 def test_argument_validation_needs_no_gpu():
@@ -37,7 +54,7 @@ def test_argument_validation_needs_no_gpu():
     assert b"D must be" in L.qa_last_error()
     assert L.qa_quant_block(z, z, z, z, 100, 64, 32, 128, 0, z) == -1         # rows not a multiple of blk
     assert L.qa_quant_block(z, z, z, z, 128, 64, 32, 128, 2, z) == -1         # rounding in {0, 1}
-    assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, 0, z) == -1  # Bkv in {32,64,128}
+    assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, 0, z) == -1  # Bkv in {32,64,128,256}
     assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, 0, z) == -1       # Bq = Bkv = 128
     assert L.qa_bf16_fwd(*([z] * 5), 1, 100, 128, 128, 0, 1, z) == -1         # S % 128
     assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, -1.0, z) == -1  # rescale_tau outside [0, 16]

@@ -15,10 +15,9 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("kernel", ["warp_specialised", "eight_warp"])
 @pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 512, 64), (1, 1, 128, 128)])
-def test_int8_bwd_matches_contract_oracle(shape, kernel, monkeypatch):
+def test_int8_bwd_matches_contract_oracle(shape, kernel):
     from oracle import int8_ref
-    # the default kernel is the warp-specialised one; the 8-warp kernel stays selectable (read per call by qa_int8_bwd)
-    monkeypatch.setenv("QA_INT8_BWD_WS", "1" if kernel == "warp_specialised" else "0")
+    # the default kernel is the warp-specialised one; the 8-warp kernel stays selectable per call (QA_FLAG_BWD_8WARP)
     from quantizedattention_b200 import attention_int8 as A
     B, H, S, D = shape
     g = torch.Generator().manual_seed(2000 + S + D)
@@ -29,7 +28,8 @@ def test_int8_bwd_matches_contract_oracle(shape, kernel, monkeypatch):
     # oracle on the SAME saved tensors (so only the backward is compared)
     c = lambda t: t.cpu()
     ref = int8_ref.int8_bwd_contract(dO, c(q_i8), c(sq), c(k_i8_T), c(kmean), c(sk), c(v_i8), c(sv), c(O), c(lse16), Bq, Bkv)
-    got = A.helion_atten_int8_hl_dot_bwd(dO.cuda(), q_i8, sq, k_i8_T, kmean, sk, v_i8, sv, O, lse16, Bq, Bkv)
+    got = A.helion_atten_int8_hl_dot_bwd(dO.cuda(), q_i8, sq, k_i8_T, kmean, sk, v_i8, sv, O, lse16, Bq, Bkv,
+                                         kernel="ws" if kernel == "warp_specialised" else "8warp")
     torch.cuda.synchronize()
     for name, a, b in zip(("dq", "dk", "dv"), got, ref):
         assert _cos(a.cpu(), b) > 0.9995 and _rel(a.cpu(), b) < 3e-2, (name, _cos(a.cpu(), b), _rel(a.cpu(), b))

@@ -15,7 +15,7 @@ def _stats(a, b):
     return (a - b).abs().max().item(), torch.nn.functional.cosine_similarity(a, b, dim=0).item()
 
 
-@pytest.mark.parametrize("nsplit", [1, 2])
+@pytest.mark.parametrize("nsplit", [0, 1, 2])
 @pytest.mark.parametrize("shape,Bq", [((1, 2, 256, 128), 128), ((1, 8, 1024, 64), 128), ((2, 2, 512, 128), 32),
                                       ((1, 1, 128, 64), 64)])
 def test_int8_fwd_matches_oracle(shape, Bq, nsplit):
@@ -29,7 +29,7 @@ def test_int8_fwd_matches_oracle(shape, Bq, nsplit):
         out = A.helion_atten_int8_hl_dot_fwd(q.cuda(), k.cuda(), v.cuda(), _want_lse32=True)
     finally:
         A.set_block_sizes(128, 128)
-        A._CFG["nsplit"] = 2
+        A._CFG["nsplit"] = 0
     torch.cuda.synchronize()
     ref = int8_ref.int8_fwd(q, k, v, Bq, 128, per_head=True, return_lse32=True)
     # quantised tensors and scales: bit-exact
@@ -72,7 +72,7 @@ def test_int8_fwd_against_real_reference_fixture(golden_dir):
     axis, LEDGER I-2).  The literal result is the per-head kernel on x.view(1, 1, B*H*S, D)."""
     import os
     from quantizedattention_b200 import attention_int8 as A
-    fx = torch.load(os.path.join(golden_dir, "int8_B1H2S128D64_bq32_bkv32.pt"))
+    fx = torch.load(os.path.join(golden_dir, "int8_B1H2S128D64_bq32_bkv32.pt"), weights_only=True)
     q, k, v = [fx[n].reshape(1, 1, -1, 64).cuda() for n in ("q", "k", "v")]
     A.set_block_sizes(32, 32)
     try:

@@ -20,7 +20,7 @@ def _fixtures(golden_dir, prefix):
 
 def test_int8_fwd_bwd_literal_matches_reference(golden_dir):
     for f in _fixtures(golden_dir, "int8_"):
-        fx = torch.load(f)
+        fx = torch.load(f, weights_only=True)
         out = int8_ref.int8_fwd(fx["q"], fx["k"], fx["v"], fx["Bq"], fx["Bkv"], per_head=False)
         for i, (a, b) in enumerate(zip(fx["fwd"], out[:8])):
             assert torch.equal(a, b), (f, i)
@@ -33,7 +33,7 @@ def test_int8_fwd_bwd_literal_matches_reference(golden_dir):
 
 def test_bf16_fwd_bwd_literal_matches_reference(golden_dir):
     for f in _fixtures(golden_dir, "bf16_"):
-        fx = torch.load(f)
+        fx = torch.load(f, weights_only=True)
         O, lse = bf16_ref.bf16_fwd(fx["q"], fx["k"], fx["v"], fx["causal"], tile_k=fx["tile_k"], mode="literal")
         assert torch.equal(O, fx["O"]) and torch.equal(lse, fx["lse"]), f
         g = bf16_ref.bf16_bwd(fx["q"], fx["k"], fx["v"], O, lse, fx["causal"], fx["dO"], mode="literal")
@@ -43,7 +43,7 @@ def test_bf16_fwd_bwd_literal_matches_reference(golden_dir):
 
 def test_jvp_literal_matches_reference(golden_dir):
     for f in _fixtures(golden_dir, "jvp_"):
-        fx = torch.load(f)
+        fx = torch.load(f, weights_only=True)
         O, tO, lse = jvp_ref.jvp_fwd(fx["q"], fx["k"], fx["v"], fx["tq"], fx["tk"], fx["tv"], tile_k=16)
         assert torch.equal(O, fx["O"]) and torch.equal(tO, fx["tO"]) and torch.equal(lse, fx["lse"]), f
 

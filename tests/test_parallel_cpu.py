@@ -18,10 +18,10 @@ class OracleRingKernels:
             x = int8_ref.smooth_k(x, mean)
         return int8_ref.quant_block(x.reshape(-1, x.shape[-1]), blk)
 
-    def attend(self, q_i8, sq, kv, state, BH, Sq, Sk, D, Bq, last):
+    def attend(self, q_i8, sq, kv, state, BH, Sq, Sk, D, Bq, Bkv, last):
         from oracle import int8_ref
         k_i8, v_i8, sk, sv = kv
-        return int8_ref.int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, 128, last)
+        return int8_ref.int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bkv, last)
 
 
 def _full_inputs():
@@ -31,7 +31,7 @@ def _full_inputs():
     return q, k, v
 
 
-def _ring_worker(rank, world, port, ret):
+def _ring_worker(rank, world, port, ret, Bq=128, Bkv=128):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
@@ -40,19 +40,20 @@ def _ring_worker(rank, world, port, ret):
     Sl = q.shape[2] // world
     sl = slice(rank * Sl, (rank + 1) * Sl)
     O, lse16, lse32, km = ring_int8_attention_fwd(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(), v[:, :, sl].contiguous(),
-                                                  128, 128, kernels=OracleRingKernels())
+                                                  Bq, Bkv, kernels=OracleRingKernels())
     ret[rank] = (O, lse32, km)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_ring_kv_world2_matches_single_device():
+@pytest.mark.parametrize("Bq,Bkv", [(128, 128), (32, 64)])
+def test_ring_kv_world2_matches_single_device(Bq, Bkv):
     from oracle import int8_ref
-    world, port = 2, 29500 + (os.getpid() % 500)
+    world, port = 2, 29500 + (os.getpid() % 500) + Bkv
     ret = mp.Manager().dict()
-    mp.spawn(_ring_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_ring_worker, args=(world, port, ret, Bq, Bkv), nprocs=world, join=True)
     q, k, v = _full_inputs()
-    full = int8_ref.sage_forward(q, k, v, 128, 128)
+    full = int8_ref.sage_forward(q, k, v, Bq, Bkv)
     O = torch.cat([ret[r][0] for r in range(world)], dim=2)
     # every rank smoothed K with the same GLOBAL mean (all-reduce of token sums)
     assert torch.equal(ret[0][2], ret[1][2])
@@ -60,7 +61,7 @@ def test_ring_kv_world2_matches_single_device():
     # k-tile visiting order differs per rank -> tolerance, not bitwise
     assert (O.float() - full[0].float()).abs().max() < 6e-3
     lse = torch.cat([ret[r][1].view(1, 2, -1) for r in range(world)], dim=2).reshape(-1)
-    ref_lse = int8_ref.int8_fwd(q, int8_ref.smooth_k(k, full[2]), v, 128, 128, return_lse32=True)[10]
+    ref_lse = int8_ref.int8_fwd(q, int8_ref.smooth_k(k, full[2]), v, Bq, Bkv, return_lse32=True)[10]
     assert (lse - ref_lse).abs().max() < 3e-2
 
 

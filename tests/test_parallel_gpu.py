@@ -6,8 +6,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("D", [64, 128])
-def test_ring_state_continuation_matches_single_shot(D):
+@pytest.mark.parametrize("D,Bkv", [(64, 128), (128, 128), (128, 64), (64, 32)])
+def test_ring_state_continuation_matches_single_shot(D, Bkv):
     from oracle import int8_ref
     from quantizedattention_b200 import ops
     from quantizedattention_b200.parallel import CudaRingKernels
@@ -22,22 +22,22 @@ def test_ring_state_continuation_matches_single_shot(D):
     for r in range(world):
         sl = slice(r * Sl, (r + 1) * Sl)
         q_i8, sq = kern.quant(q[:, :, sl].contiguous().cuda(), 128)
-        k_i8, sk = kern.quant(k[:, :, sl].contiguous().cuda(), 128, mean=km, rows_per_head=Sl)
-        v_i8, sv = kern.quant(v[:, :, sl].contiguous().cuda(), 128)
+        k_i8, sk = kern.quant(k[:, :, sl].contiguous().cuda(), Bkv, mean=km, rows_per_head=Sl)
+        v_i8, sv = kern.quant(v[:, :, sl].contiguous().cuda(), Bkv)
         shards.append((q_i8, sq, (k_i8, v_i8, sk, sv)))
     outs = []
     for r in range(world):                      # rank r visits its own shard first, then the one received from r-1
         q_i8, sq, _ = shards[r]
-        st = kern.attend(q_i8, sq, shards[r][2], None, BH, Sl, Sl, D, 128, last=False)
-        O, lse16, lse32 = kern.attend(q_i8, sq, shards[(r - 1) % world][2], st, BH, Sl, Sl, D, 128, last=True)
+        st = kern.attend(q_i8, sq, shards[r][2], None, BH, Sl, Sl, D, 128, Bkv, last=False)
+        O, lse16, lse32 = kern.attend(q_i8, sq, shards[(r - 1) % world][2], st, BH, Sl, Sl, D, 128, Bkv, last=True)
         outs.append(O.view(B, H, Sl, D).cpu())
     O_ring = torch.cat(outs, dim=2)
-    full = int8_ref.int8_fwd(q, int8_ref.smooth_k(k, km.cpu()), v, 128, 128, per_head=True)
+    full = int8_ref.int8_fwd(q, int8_ref.smooth_k(k, km.cpu()), v, 128, Bkv, per_head=True)
     assert (O_ring.float() - full[0].float()).abs().max() < 6e-3       # different k-tile order: tolerance, not bitwise
     # oracle ring step (same order) is tighter
     c = lambda t: t.cpu()
     r = 1
     q_i8, sq, _ = shards[r]
-    st = int8_ref.int8_attend_state(c(q_i8), c(sq), *[c(t) for t in shards[1][2]], None, BH, Sl, Sl, D, 128, 128, False)
-    Oo, _, _ = int8_ref.int8_attend_state(c(q_i8), c(sq), *[c(t) for t in shards[0][2]], st, BH, Sl, Sl, D, 128, 128, True)
+    st = int8_ref.int8_attend_state(c(q_i8), c(sq), *[c(t) for t in shards[1][2]], None, BH, Sl, Sl, D, 128, Bkv, False)
+    Oo, _, _ = int8_ref.int8_attend_state(c(q_i8), c(sq), *[c(t) for t in shards[0][2]], st, BH, Sl, Sl, D, 128, Bkv, True)
     assert (outs[1].reshape(-1, D).float() - Oo.float()).abs().max() < 5e-3

@@ -33,7 +33,7 @@ def int8_fwd(BH=256, S=8192, D=128):
     res["k_mean_GBs"] = 2 * k.numel() / med / 1e6
     med, _ = timeit(lambda: ops.quant_block(k, 128, mean=km, rows_per_head=S))
     res["quant_k_smooth_GBs"] = 3 * k.numel() / med / 1e6
-    for ns in (1, 2):
+    for ns in (0, 1, 2):
         med, best = timeit(lambda: ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, S, S, D, 128, 128, nsplit=ns))
         res[f"int8_fwd_nsplit{ns}"] = {"ms_med": med, "ms_best": best, "TOPS_med": 4 * BH * S * S * D / med / 1e9}
     print(json.dumps(res, indent=1))

@@ -19,11 +19,12 @@ elif which == "jvp":
     for _ in range(3):
         ops.jvp_fwd(*t)
 elif which == "int8_fwd":
-    BH, S, D = 64, 8192, 128
+    import os
+    BH, S, D = 37, 8192, 128                                   # 37 heads x 64 q-tiles = 16 waves of 148 CTAs
     q, k, v = [torch.randn(BH, S, D, device="cuda", dtype=torch.float16) for _ in range(3)]
     qi, sq = ops.quant_block(q, 128); ki, sk = ops.quant_block(k, 128); vi, sv = ops.quant_block(v, 128)
     for _ in range(3):
-        ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D)
+        ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D, nsplit=int(os.environ.get("QA_NSPLIT", "0")))
 elif which == "bf16_bwd":
     B, H, S, D = 4, 16, 4096, 128
     q, k = [torch.randn(B, H, S, D, device="cuda", dtype=torch.float16) for _ in range(2)]

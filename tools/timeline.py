@@ -2,6 +2,8 @@
 slots: 0 softmax: before s_full wait | 1 S ready | 2 pass-1 done | 3, 4 scales handed over, pass 2 starts | 5 P handed over
        6 correction: before o_full wait | 7 Opart ready | 8 drained     9 MMA: K landed | 10 QK issued | 11 PV issued"""
 import json
+import os
+os.environ["QA_DEV_LIB"] = "1"      # every call goes through libqattn_dev.so (kernels with timeline hooks)
 import sys
 
 import torch

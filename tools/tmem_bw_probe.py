@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, ".")
 from quantizedattention_b200 import _lib  # noqa: E402
 
-L = _lib.lib()
+L = _lib.dev_lib()
 sink = torch.zeros(2048, dtype=torch.int32, device="cuda")
 props = torch.cuda.get_device_properties(0)
 sms = props.multi_processor_count
@@ -19,7 +19,7 @@ for shape, depth, threads in [(s, d, t) for s in SHAPES for d in (1, 2) for t in
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    _lib.check(L.qa_probe_tmem_bw_ex(_lib.ptr(sink), sms, threads, iters, shape, depth, _lib.cur_stream()), "probe")
+    _lib.check(L.qa_probe_tmem_bw_ex(_lib.ptr(sink), sms, threads, iters, shape, depth, _lib.cur_stream()), "probe", L)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
