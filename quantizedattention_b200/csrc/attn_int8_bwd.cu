@@ -28,7 +28,8 @@ struct Int8BwdSmem {
   static constexpr int off_p = off_do + 2 * kTile;   // int8 [128 q][128 keys]
   static constexpr int off_ds = off_p + 128 * 128;   // 2 buffers (dQ of tile t-1 reads dS while tile t is quantised)
   static constexpr int off_dq = off_ds + 2 * 128 * 128;  // fp32 [128 q][D] staging for the TMA reduce-add (D/32 swizzled atoms)
-  static constexpr int total = off_dq + 128 * D * 4 + 1024;
+  static constexpr int off_c = off_dq + 128 * D * 4;     // two 1 KB constant fp16 atoms (A: 1024.0, B: 768.0) of the accumulator-initialising MMA
+  static constexpr int total = off_c + 2 * 1024 + 1024;
 };
 
 struct Int8BwdParams {
@@ -92,6 +93,11 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  if (tid >= 64 && tid < 192) {                                 // constant atoms of the accumulator-initialising MMA
+    const uint32_t v2 = tid < 128 ? kMagicElemA2 : kMagicElemB2;
+    sts128(smem_u32(smem + L::off_c) + (tid - 64) * 16, v2, v2, v2, v2);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,6 +106,10 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128);     // S, dP: A, B K-major, N = 128
   constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);       // dV, dK: A^T (MN-major), B MN-major, N = D
   constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);       // dQ: A K-major, B MN-major
+  // "magic" accumulators (qa_ptx.cuh): a kind::f16 MMA over two constant atoms sets an accumulator to kMagic before the
+  // kind::i8 MMAs add to it; all sixteen 8-row groups read the same 1 KB atom (SBO = 0)
+  constexpr uint32_t id_c128 = umma_idesc(1, 0, 0, 0, 0, 128, 128), id_cD = umma_idesc(1, 0, 0, 0, 0, 128, D);
+  const uint64_t cdesc_a = umma_smem_desc(smem_u32(smem + L::off_c), 16, 0, kLay), cdesc_b = umma_smem_desc(smem_u32(smem + L::off_c + 1024), 16, 0, kLay);
   const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
   const uint32_t a_p = smem_u32(smem + L::off_p), a_ds0 = smem_u32(smem + L::off_ds);
 
@@ -110,32 +120,37 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   };
   auto issue_s = [&](int st) {                                     // S = Q K^T (issued one barrier ahead of dP: the S columns
     const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);          // are free as soon as pass 1 is over)
+      umma_f16_ss(tbase + 0, cdesc_a, cdesc_b, id_c128, 0);                     // S = kMagic (qa_ptx.cuh)
 #pragma unroll
     for (int k = 0; k < D / 32; ++k)
-      umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, k > 0);
+      umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, 1);
   };
   auto issue_dp = [&](int st) {                                    // dP = dO V^T; the commit also covers the earlier S MMAs
     const uint32_t a_do = smem_u32(smem + L::off_do + st * L::kTile);
+      umma_f16_ss(tbase + 128, cdesc_a, cdesc_b, id_c128, 0);                   // dP = kMagic
 #pragma unroll
     for (int k = 0; k < D / 32; ++k)
-      umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, k > 0);
+      umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, 1);
     umma_commit(&sd_full);
   };
   auto issue_dv_dk = [&](int st, int dsb) {                        // dV = P^T dO, dK = dS^T Q (contraction over query rows)
     const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
     const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+    umma_f16_ss(tbase + 256, cdesc_a, cdesc_b, id_cD, 0);                     // dV, dK partials = kMagic
+    umma_f16_ss(tbase + 384, cdesc_a, cdesc_b, id_cD, 0);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
-      umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+      umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, 1);
+      umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, 1);
     }
     umma_commit(&parts_full);
   };
   auto issue_dq = [&](int dsb) {                                   // dQ = dS K (contraction over keys) -> cols 256..
     const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+    umma_f16_ss(tbase + 256, cdesc_a, cdesc_b, id_cD, 0);                     // dQ partial = kMagic
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
+      umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, 1);
     umma_commit(&dq_full);
   };
 
@@ -161,6 +176,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   for (int d = 0; d < DH / 2; ++d) { dv_acc[d] = make_float2(0.f, 0.f); dk_acc[d] = make_float2(0.f, 0.f); }
   float c_dv_prev = 0.f, c_dk_prev = 0.f, c_dq_prev = 0.f;
 
+  const float2 nM2 = make_float2(-kMagic, -kMagic);
   auto drain_dv_dk = [&](float c_dv, float c_dk) {
 #pragma unroll
     for (int ch = 0; ch < DH / 16; ++ch) {
@@ -170,9 +186,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        dv_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r[2 * c]), __int2float_rn((int)r[2 * c + 1])),
+        dv_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), nM2),
                                         make_float2(c_dv, c_dv), dv_acc[ch * 8 + c]);
-        dk_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r2[2 * c]), __int2float_rn((int)r2[2 * c + 1])),
+        dk_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1])), nM2),
                                         make_float2(c_dk, c_dk), dk_acc[ch * 8 + c]);
       }
     }
@@ -187,9 +203,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t atom = smem_base + L::off_dq + (col >> 5) * (128 * 128);
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
-        const float2 cq2 = make_float2(c_dq, c_dq);
-        const float2 o01 = __fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2);
-        const float2 o23 = __fmul2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2);
+        const float2 cq2 = make_float2(c_dq, c_dq), nbq2 = make_float2(-kMagic * c_dq, -kMagic * c_dq);   // c_dq: 22 significant bits
+        const float2 o01 = __ffma2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), cq2, nbq2);
+        const float2 o23 = __ffma2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), cq2, nbq2);
         sts128f(atom + swz128(row, ((col & 31) + c) * 4), o01.x, o01.y, o23.x, o23.y);
       }
     }
@@ -210,7 +226,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float sdo_f = __half2float(p.s_do[head_row0 / 128 + tq]);
     const float lse = p.lse[qrow];
     const float dlt = p.delta[qrow];
-    const float c_s = sq_f * sk_f * p.qk_scale;
+    const float c_s = magic_scale(sq_f * sk_f * p.qk_scale);
     const float c_dp = sdo_f * sv_f;
     QA_TLB(0);
     if (leader && t + 1 < nt) {                                    // next Q / dO tile: its stage was last read by dV/dK of t-1
@@ -226,8 +242,11 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float amax_p = 0.f, amax_ds = 0.f;
     __half2 amax_ph = __float2half2_rn(0.f);
     float2 rs2acc = make_float2(0.f, 0.f);
-    const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(10.0f - lse, 10.0f - lse);
-    const float2 cdp2 = make_float2(c_dp * kPs, c_dp * kPs), ndlt2 = make_float2(-dlt * kPs, -dlt * kPs);
+    // magic accumulators: TMEM holds kMagic + x as a float; the scales carry 22 significant bits, so kMagic * scale is
+    // exact and (kMagic + x) * scale - kMagic * scale is one rounding of x * scale
+    const float nlse = 10.0f - lse, cdpk = magic_scale(c_dp * kPs);
+    const float2 cs2 = make_float2(c_s, c_s), nbs2 = make_float2(-kMagic * c_s, -kMagic * c_s);
+    const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(-dlt * kPs - kMagic * cdpk, -dlt * kPs - kMagic * cdpk);
     auto pass1 = [&](auto masked) {                                // masked: the diagonal tile of a causal head
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
@@ -237,8 +256,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
-        const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cs2));
-        const float2 e = __fadd2_rn(__half22float2(h), nlse2);
+        const __half2 h = __float22half2_rn(__ffma2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), cs2, nbs2));
+        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 e = make_float2(fhadd_lo(hu, nlse), fhadd_hi(hu, nlse));           // float(logit) - lse + 10: one FHADD each
         float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));                     // 1024 * P
         if (decltype(masked)::value) {                                 // strict causal: keep key < query (same tile: col < row)
           const int col = half * CW + ch * 16 + c;
@@ -248,7 +268,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const __half2 pr = __float22half2_rn(pp);
         pk[ch * 8 + c / 2] = pr;
         amax_ph = __hmax2(amax_ph, pr);
-        const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdp2, ndlt2));
+        const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), cdp2, ndlt2));
         amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d.x), fabsf(d.y)));
         rs2acc = __fadd2_rn(rs2acc, d);
       }
@@ -301,7 +321,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
     //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
     const uint32_t ds_tile = smem_base + L::off_ds + ph * (128 * 128);
-    const float2 cdpi2 = make_float2(c_dp * kPs * inv_ds, c_dp * kPs * inv_ds), ndlti2 = make_float2(-dlt * kPs * inv_ds, -dlt * kPs * inv_ds);
+    const float cdpi = magic_scale(c_dp * kPs * inv_ds);
+    const float2 cdpi2 = make_float2(cdpi, cdpi), ndlti2 = make_float2(-dlt * kPs * inv_ds - kMagic * cdpi, -dlt * kPs * inv_ds - kMagic * cdpi);
     const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
     {                                                              // RN: the rounding mode is an instruction modifier
 #pragma unroll
@@ -318,7 +339,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const int c = q4 * 4 + e;
             const float2 pp = __half22float2(pk[ch * 8 + c / 2]);                  // 1024 * P from pass 1
             // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS (and the 1/1024) folded into the FFMA2 constants
-            const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
+            const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), cdpi2, ndlti2));
             // P >= 0: low byte of the biased sum = trunc(P / sP), or its nearest-even rounding in accuracy mode
             const float2 pq = RN ? __ffma2_rn(pp, invp2, magic2) : __ffma2_rz(pp, invp2, magic2);
             bp[e] = __float_as_uint(pq.x);
@@ -327,7 +348,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             bd[e + 1] = (uint32_t)(RN ? __float2int_rn(dq.y) : __float2int_rz(dq.y));
           }
           wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
-          wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
+          wd[q4] = pack_sat_s8x4((int)bd[0], (int)bd[1], (int)bd[2], (int)bd[3]);
         }
         const uint32_t off = swz128(row, half * CW + ch * 16);
         sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
@@ -357,7 +378,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     QA_TLB(12);
     c_dv_prev = sdo_f * sP;
     c_dk_prev = sdS * sq_f * p.sm_scale;
-    c_dq_prev = sdS * sk_f * p.sm_scale;
+    c_dq_prev = magic_scale(sdS * sk_f * p.sm_scale);
   }
   // ---- pipeline tail: last tile's dV / dK / dQ
   mbar_wait(&parts_full, (nt - 1) & 1);
@@ -447,6 +468,11 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  if (tid >= 64 && tid < 192) {                                 // constant atoms of the accumulator-initialising MMA
+    const uint32_t v2 = tid < 128 ? kMagicElemA2 : kMagicElemB2;
+    sts128(smem_u32(smem + L::off_c) + (tid - 64) * 16, v2, v2, v2, v2);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -470,7 +496,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const float sdo_f = __half2float(p.s_do[head_row0 / 128 + tq]);
       const float lse = p.lse[qrow];
       const float dlt = p.delta[qrow];
-      const float c_s = sq_f * sk_f * p.qk_scale;
+      const float c_s = magic_scale(sq_f * sk_f * p.qk_scale);
       const float c_dp = sdo_f * sv_f;
       mbar_wait(&sd_full, ph);
       tc_fence_after();
@@ -480,8 +506,11 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       float amax_p = 0.f, amax_ds = 0.f;
       __half2 amax_ph = __float2half2_rn(0.f);
       float2 rs2acc = make_float2(0.f, 0.f);
-      const float2 cs2 = make_float2(c_s, c_s), nlse2 = make_float2(10.0f - lse, 10.0f - lse);
-      const float2 cdp2 = make_float2(c_dp * kPs, c_dp * kPs), ndlt2 = make_float2(-dlt * kPs, -dlt * kPs);
+      // magic accumulators: TMEM holds kMagic + x as a float; the scales carry 22 significant bits, so kMagic * scale is
+      // exact and (kMagic + x) * scale - kMagic * scale is one rounding of x * scale
+      const float nlse = 10.0f - lse, cdpk = magic_scale(c_dp * kPs);
+      const float2 cs2 = make_float2(c_s, c_s), nbs2 = make_float2(-kMagic * c_s, -kMagic * c_s);
+      const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(-dlt * kPs - kMagic * cdpk, -dlt * kPs - kMagic * cdpk);
       auto pass1 = [&](auto masked) {                                // masked: the diagonal tile of a causal head
   #pragma unroll
       for (int ch = 0; ch < CW / 16; ++ch) {
@@ -491,8 +520,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_ld_wait();
   #pragma unroll
         for (int c = 0; c < 16; c += 2) {
-          const __half2 h = __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cs2));
-          const float2 e = __fadd2_rn(__half22float2(h), nlse2);
+          const __half2 h = __float22half2_rn(__ffma2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), cs2, nbs2));
+          const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+          const float2 e = make_float2(fhadd_lo(hu, nlse), fhadd_hi(hu, nlse));           // float(logit) - lse + 10: one FHADD each
           float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));                     // 1024 * P
           if (decltype(masked)::value) {                                 // strict causal: keep key < query (same tile: col < row)
             const int col = half * CW + ch * 16 + c;
@@ -502,7 +532,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           const __half2 pr = __float22half2_rn(pp);
           pk[ch * 8 + c / 2] = pr;
           amax_ph = __hmax2(amax_ph, pr);
-          const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdp2, ndlt2));
+          const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), cdp2, ndlt2));
           amax_ds = fmaxf(amax_ds, fmaxf(fabsf(d.x), fabsf(d.y)));
           rs2acc = __fadd2_rn(rs2acc, d);
         }
@@ -536,7 +566,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (tid == 0) {                                              // tile scales for the drain role (read after parts_full(t))
         sc_ring[ph][0] = sdo_f * sP;
         sc_ring[ph][1] = sdS * sq_f * p.sm_scale;
-        sc_ring[ph][2] = sdS * sk_f * p.sm_scale;
+        sc_ring[ph][2] = magic_scale(sdS * sk_f * p.sm_scale);
       }
       // the P tile and this dS buffer were last read by dV/dK of tile t-1 (dS[ph] also by dQ of t-2, which completed
       // before sd_full(t) was signalled)
@@ -544,7 +574,8 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
       //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
       const uint32_t ds_tile = smem_base + L::off_ds + ph * (128 * 128);
-      const float2 cdpi2 = make_float2(c_dp * kPs * inv_ds, c_dp * kPs * inv_ds), ndlti2 = make_float2(-dlt * kPs * inv_ds, -dlt * kPs * inv_ds);
+      const float cdpi = magic_scale(c_dp * kPs * inv_ds);
+      const float2 cdpi2 = make_float2(cdpi, cdpi), ndlti2 = make_float2(-dlt * kPs * inv_ds - kMagic * cdpi, -dlt * kPs * inv_ds - kMagic * cdpi);
       const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
       {                                                              // RN: the rounding mode is an instruction modifier
   #pragma unroll
@@ -561,7 +592,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               const int c = q4 * 4 + e;
               const float2 pp = __half22float2(pk[ch * 8 + c / 2]);                  // 1024 * P from pass 1
               // dS / s_dS = P * (dP*c_dp - delta) / s_dS with 1/s_dS (and the 1/1024) folded into the FFMA2 constants
-              const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__int2float_rn((int)r2[c]), __int2float_rn((int)r2[c + 1])), cdpi2, ndlti2));
+              const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), cdpi2, ndlti2));
               // P >= 0: low byte of the biased sum = trunc(P / sP), or its nearest-even rounding in accuracy mode
               const float2 pq = RN ? __ffma2_rn(pp, invp2, magic2) : __ffma2_rz(pp, invp2, magic2);
               bp[e] = __float_as_uint(pq.x);
@@ -570,7 +601,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
               bd[e + 1] = (uint32_t)(RN ? __float2int_rn(dq.y) : __float2int_rz(dq.y));
             }
             wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
-            wd[q4] = pack_low_bytes(bd[0], bd[1], bd[2], bd[3]);
+            wd[q4] = pack_sat_s8x4((int)bd[0], (int)bd[1], (int)bd[2], (int)bd[3]);
           }
           const uint32_t off = swz128(row, half * CW + ch * 16);
           sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
@@ -589,6 +620,10 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128);     // S, dP: A, B K-major, N = 128
     constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);       // dV, dK: A^T (MN-major), B MN-major, N = D
     constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);       // dQ: A K-major, B MN-major
+    // "magic" accumulators (qa_ptx.cuh): a kind::f16 MMA over two constant atoms sets an accumulator to kMagic before the
+    // kind::i8 MMAs add to it; all sixteen 8-row groups read the same 1 KB atom (SBO = 0)
+    constexpr uint32_t id_c128 = umma_idesc(1, 0, 0, 0, 0, 128, 128), id_cD = umma_idesc(1, 0, 0, 0, 0, 128, D);
+    const uint64_t cdesc_a = umma_smem_desc(smem_u32(smem + L::off_c), 16, 0, kLay), cdesc_b = umma_smem_desc(smem_u32(smem + L::off_c + 1024), 16, 0, kLay);
     const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
     const uint32_t a_p = smem_u32(smem + L::off_p), a_ds0 = smem_u32(smem + L::off_ds);
     auto load_qdo = [&](int tile, int st) {
@@ -598,32 +633,37 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     };
     auto issue_s = [&](int st) {                                     // S = Q K^T (issued one barrier ahead of dP: the S columns
       const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);          // are free as soon as pass 1 is over)
+      umma_f16_ss(tbase + 0, cdesc_a, cdesc_b, id_c128, 0);                     // S = kMagic (qa_ptx.cuh)
   #pragma unroll
       for (int k = 0; k < D / 32; ++k)
-        umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, k > 0);
+        umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, 1);
     };
     auto issue_dp = [&](int st) {                                    // dP = dO V^T; the commit also covers the earlier S MMAs
       const uint32_t a_do = smem_u32(smem + L::off_do + st * L::kTile);
+      umma_f16_ss(tbase + 128, cdesc_a, cdesc_b, id_c128, 0);                   // dP = kMagic
   #pragma unroll
       for (int k = 0; k < D / 32; ++k)
-        umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, k > 0);
+        umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, 1);
       umma_commit(&sd_full);
     };
     auto issue_dv_dk = [&](int st, int dsb) {                        // dV = P^T dO, dK = dS^T Q (contraction over query rows)
       const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
       const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+      umma_f16_ss(tbase + 256, cdesc_a, cdesc_b, id_cD, 0);                     // dV, dK partials = kMagic
+      umma_f16_ss(tbase + 384, cdesc_a, cdesc_b, id_cD, 0);
   #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
-        umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, k > 0);
+        umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, 1);
+        umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, 1);
       }
       umma_commit(&parts_full);
     };
     auto issue_dq = [&](int dsb) {                                   // dQ = dS K (contraction over keys) -> cols 256..
       const uint32_t a_ds = a_ds0 + dsb * (128 * 128);
+      umma_f16_ss(tbase + 256, cdesc_a, cdesc_b, id_cD, 0);                     // dQ partial = kMagic
   #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, k > 0);
+        umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, 1);
       umma_commit(&dq_full);
     };
 
@@ -640,6 +680,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     float2 dv_acc[DH / 2], dk_acc[DH / 2];                        // fp32x2: FFMA2 / FMUL2 / FADD2 halve the issue slots
 #pragma unroll
     for (int d = 0; d < DH / 2; ++d) { dv_acc[d] = make_float2(0.f, 0.f); dk_acc[d] = make_float2(0.f, 0.f); }
+    const float2 nM2 = make_float2(-kMagic, -kMagic);
     auto drain_dv_dk = [&](float c_dv, float c_dk) {
   #pragma unroll
       for (int ch = 0; ch < DH / 16; ++ch) {
@@ -649,9 +690,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tmem_ld_wait();
   #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          dv_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r[2 * c]), __int2float_rn((int)r[2 * c + 1])),
+          dv_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), nM2),
                                           make_float2(c_dv, c_dv), dv_acc[ch * 8 + c]);
-          dk_acc[ch * 8 + c] = __ffma2_rn(make_float2(__int2float_rn((int)r2[2 * c]), __int2float_rn((int)r2[2 * c + 1])),
+          dk_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1])), nM2),
                                           make_float2(c_dk, c_dk), dk_acc[ch * 8 + c]);
         }
       }
@@ -666,9 +707,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const uint32_t atom = smem_base + L::off_dq + (col >> 5) * (128 * 128);
   #pragma unroll
         for (int c = 0; c < 16; c += 4) {
-          const float2 cq2 = make_float2(c_dq, c_dq);
-          const float2 o01 = __fmul2_rn(make_float2(__int2float_rn((int)r[c]), __int2float_rn((int)r[c + 1])), cq2);
-          const float2 o23 = __fmul2_rn(make_float2(__int2float_rn((int)r[c + 2]), __int2float_rn((int)r[c + 3])), cq2);
+          const float2 cq2 = make_float2(c_dq, c_dq), nbq2 = make_float2(-kMagic * c_dq, -kMagic * c_dq);   // c_dq: 22 significant bits
+          const float2 o01 = __ffma2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), cq2, nbq2);
+          const float2 o23 = __ffma2_rn(make_float2(__uint_as_float(r[c + 2]), __uint_as_float(r[c + 3])), cq2, nbq2);
           sts128f(atom + swz128(row, ((col & 31) + c) * 4), o01.x, o01.y, o23.x, o23.y);
         }
       }

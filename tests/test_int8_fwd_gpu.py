@@ -84,3 +84,35 @@ def test_int8_fwd_against_real_reference_fixture(golden_dir):
     assert torch.equal(out[5].cpu(), sq) and torch.equal(out[6].cpu(), sk) and torch.equal(out[7].cpu(), sv)
     assert (out[0].cpu().float().reshape(-1) - O_ref.float().reshape(-1)).abs().max() < 5e-3
     assert (out[1].cpu().float() - lse_ref.float()).abs().max() < 4e-2
+
+
+@pytest.mark.parametrize("ring", [False, True])
+def test_int8_fwd_running_max_jump_beyond_fp32_range(ring):
+    """A late key whose logit exceeds every earlier one by more than 126 log2 units: the rescale factor exp2(m - m') is
+    exactly 0 in the kernel (ex2.approx.ftz), so the O accumulator must drop everything accumulated so far, consistently
+    with l and lse (the lazy rescale used to skip the update).  Plain path and ring-state continuation."""
+    from oracle import int8_ref
+    from quantizedattention_b200 import ops
+    B, H, S, D = 1, 2, 256, 128
+    g = torch.Generator().manual_seed(5)
+    q = torch.full((B, H, S, D), 3.0).to(torch.float16)
+    k = (0.01 * torch.randn(B, H, S, D, generator=g)).to(torch.float16)
+    k[:, :, 128 + 17] = 3.0                                      # one key in the LAST tile: logit ~ 147 in the log2 domain
+    v = torch.randn(B, H, S, D, generator=g).to(torch.float16)
+    ref = int8_ref.int8_fwd(q, k, v, 128, 128, per_head=True, return_lse32=True)
+    qi, sq = ops.quant_block(q.cuda(), 128); ki, sk = ops.quant_block(k.cuda(), 128); vi, sv = ops.quant_block(v.cuda(), 128)
+    BH = B * H
+    if not ring:
+        O, _, lse32 = ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, BH, S, S, D, 128, 128)
+    else:                                                        # two K/V shards of one tile each, state carried between them
+        kv = lambda t, r: t.view(BH, S, D)[:, r * 128:(r + 1) * 128].contiguous().view(-1, D)
+        sc = lambda t, r: t.view(BH, 2)[:, r].contiguous()
+        st = ops.int8_fwd_prequant(qi, kv(ki, 0), kv(vi, 0), sq, sc(sk, 0), sc(sv, 0), BH, S, 128, D, 128, 128, ring_state=True)
+        O, _, lse32 = ops.int8_fwd_prequant(qi, kv(ki, 1), kv(vi, 1), sq, sc(sk, 1), sc(sv, 1), BH, S, 128, D, 128, 128, state_in=st)
+    torch.cuda.synchronize()
+    # every row attends (numerically only) to the one large key: O = its de-quantised V row
+    assert torch.isfinite(O.float()).all()
+    assert (O.cpu().float() - ref[0].reshape(-1, D).float()).abs().max() < 5e-3
+    assert (lse32.cpu() - ref[10]).abs().max() < 2e-3
+    expect = v[:, :, 128 + 17].float().reshape(BH, 1, D).expand(BH, S, D).reshape(-1, D)
+    assert (O.cpu().float() - expect).abs().max() < 5e-2

@@ -1,0 +1,77 @@
+// Instruction-throughput microbenchmark for sm_100a (development tool): clocks per warp-instruction per SM sub-partition
+// for the instructions the int8 attention kernels are built from, with 1 / 2 / 4 warps per sub-partition.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench/ubench tools/ubench/ubench.cu ; run: tools/ubench/ubench
+#include <cuda_fp16.h>
+#include <cstdio>
+#include <cstdint>
+
+#define ITERS 256
+#define UNROLL 16
+
+template <int OP>
+__global__ void bench(long long* out, float seed) {
+  float a[UNROLL], b[UNROLL];
+  float2 a2[UNROLL];
+  uint32_t u[UNROLL], w[UNROLL];
+#pragma unroll
+  for (int i = 0; i < UNROLL; ++i) { a[i] = seed + i + threadIdx.x * 1e-3f; b[i] = seed * 0.5f + i; a2[i] = make_float2(a[i], b[i]); u[i] = __float_as_uint(a[i]) ^ (i * 977); w[i] = u[i] * 3; }
+  const float c = seed * 1.0001f, d = seed * 0.37f;
+  const float2 c2 = make_float2(c, c), d2 = make_float2(d, d);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < UNROLL; ++i) {
+      if (OP == 0) a[i] = fmaf(a[i], c, d);                                                  // FFMA (2 reg + ... )
+      if (OP == 1) a2[i] = __ffma2_rn(a2[i], c2, d2);                                         // FFMA2, scalar-ish operands
+      if (OP == 2) a2[i] = __fadd2_rn(a2[i], d2);                                             // FADD2
+      if (OP == 3) a2[i] = __fmul2_rz(a2[i], c2);                                             // FMUL2.RZ
+      if (OP == 4) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));                   // MUFU.EX2
+      if (OP == 5) asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(a[i]) : "r"(u[i]));           // I2FP
+      if (OP == 6) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, lo, %2;}" : "=f"(a[i]) : "r"(u[i]), "f"(a[i]));   // FHADD
+      if (OP == 7) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(b[i]));   // F2FP pack (depends on nothing new)
+      if (OP == 8) asm volatile("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %0;" : "+r"(u[i]) : "r"(w[i]), "r"(w[(i + 1) % UNROLL]));   // I2IP
+      if (OP == 9) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(u[i]) : "r"(w[i]));     // PRMT
+      if (OP == 10) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));                // MUFU.EX2 f16x2
+      if (OP == 11) asm volatile("{.reg .f16x2 t; mov.b32 t, %0; max.f16x2 t, t, %1; mov.b32 %0, t;}" : "+r"(u[i]) : "r"(w[i]));   // HMNMX2
+      if (OP == 12) a2[i] = __ffma2_rn(a2[i], a2[(i + 1) % UNROLL], a2[(i + 2) % UNROLL]);     // FFMA2 with 3 full register pairs
+      if (OP == 13) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(w[i]), "r"(w[(i + 3) % UNROLL]));   // HFMA2
+      if (OP == 14) asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(u[i]) : "f"(a[i]));        // F2I.TRUNC
+      if (OP == 15) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); a2[i] = __ffma2_rn(a2[i], c2, d2); a2[i] = __fadd2_rn(a2[i], d2); }   // MUFU + 2 packed ops (overlap?)
+      if (OP == 16) a[i] = a[i] * c;                                                          // FMUL
+      if (OP == 17) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(a[i]) : "r"(u[i]));   // HADD2.F32 convert
+    }
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+  uint32_t su = 0;
+#pragma unroll
+  for (int i = 0; i < UNROLL; ++i) { s += a[i] + b[i] + a2[i].x + a2[i].y; su ^= u[i] ^ w[i]; }
+  if (s == 12345.678f || su == 0x12345u) out[1000] = 1;
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+}
+
+template <int OP>
+void run(const char* name, long long* d) {
+  printf("%-28s", name);
+  for (int warps : {4, 8, 16, 32}) {   // 1, 2, 4, 8 warps per sub-partition
+    bench<OP><<<1, warps * 32>>>(d, 1.25f);
+    cudaDeviceSynchronize();
+    bench<OP><<<1, warps * 32>>>(d, 1.25f);
+    cudaDeviceSynchronize();
+    long long t;
+    cudaMemcpy(&t, d, 8, cudaMemcpyDeviceToHost);
+    const double per = (double)t / (ITERS * UNROLL) / (warps / 4);   // clocks per warp-instruction per sub-partition
+    printf("  %dw/smsp: %6.2f", warps / 4, per * ((OP == 15) ? 1.0 / 3 : 1.0));
+  }
+  printf("\n");
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 8192 * 8);
+  run<0>("FFMA", d); run<16>("FMUL", d); run<1>("FFMA2 (scalar c,d)", d); run<12>("FFMA2 (3 pairs)", d); run<2>("FADD2", d); run<3>("FMUL2.RZ", d);
+  run<4>("MUFU.EX2 f32", d); run<10>("MUFU.EX2 f16x2", d); run<5>("I2FP", d); run<6>("FHADD", d); run<17>("HADD2.F32 cvt", d); run<7>("F2FP pack", d);
+  run<8>("I2IP", d); run<9>("PRMT", d); run<11>("HMNMX2", d); run<13>("HFMA2", d); run<14>("F2I.TRUNC", d); run<15>("MUFU+FFMA2+FADD2 (per instr)", d);
+  return 0;
+}
