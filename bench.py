@@ -13,8 +13,16 @@ value  : whole-job TOPS (4+10)*B*H*S^2*D ops per step per GPU, inputs resident i
 e2e    : same metric through the public host-staged API (quantizedattention_b200.host_pipeline) with pinned HOST
          buffers: H2D of q/k/v/dO and D2H of O/dq/dk/dv inside the timed region, pipelined over head chunks on three
          CUDA streams.
-Multi-GPU: batch x head sharding, no collective on the data path; every rank runs the full per-GPU workload
-(weak scaling), time = max over ranks.
+Multi-GPU: batch x head sharding, no collective on the data path.  The headline `value` keeps the per-GPU workload fixed
+(weak scaling: every rank runs the full configs[2] shape, time = max over ranks); the same JSON line also carries
+  strong_scaling : configs[2] split over the ranks (256 / N heads per GPU), total TOPS
+  ring_kv        : (N > 1) BASELINE configs[4], int8 long-context forward B=1 H=32 S=131072 D=128 sequence-sharded over the
+                   ranks with the NCCL ring (send/recv of the int8 K/V shard overlapped with the kernel): total TOPS,
+                   per-step kernel and transfer times, how much of the transfer the kernel hides
+  other_paths    : (N = 1) the other BASELINE configs at kernel level: int8 fwd configs[0], bf16 fwd S=8k D=128,
+                   bf16 fwd+bwd configs[1], JVP configs[3], each with its fraction of the in-run measured tensor peak
+  peaks_in_run   : torch._int_mm / bf16 matmul 8192^3 best-of-10 on THIS box, the roofline denominators
+  pcie           : full-duplex pinned-copy bandwidth of all ranks at once = the floor of `e2e`
 """
 from __future__ import annotations
 
@@ -42,12 +50,165 @@ def peaks():
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
-    int8 = None
-    try:
-        int8 = json.load(open(os.path.join(ROOT, "profiles", "r01_peaks.json"))).get("int8_tops_int_mm")
-    except Exception:  # noqa: BLE001
-        pass
-    return p, int8
+    return p
+
+
+def measure_peaks(dev):
+    """Dense tensor peaks of this box, same method as MEASURED_PEAKS.json (best of 10 at 8192^3): int8 through
+    torch._int_mm (cuBLASLt), bf16 through torch.matmul.  Library calls are used here as the yardstick only."""
+    n = 8192
+    out = {}
+    a8 = torch.randint(-127, 127, (n, n), dtype=torch.int8, device=dev)
+    b8 = torch.randint(-127, 127, (n, n), dtype=torch.int8, device=dev)
+    a16 = torch.randn(n, n, dtype=torch.bfloat16, device=dev)
+    b16 = torch.randn(n, n, dtype=torch.bfloat16, device=dev)
+    for name, fn in (("int8_tops", lambda: torch._int_mm(a8, b8)), ("bf16_tflops", lambda: a16 @ b16)):
+        try:
+            for _ in range(3):
+                fn()
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        except Exception as e:  # noqa: BLE001
+            out[name] = None
+            out[name + "_error"] = str(e)[:80]
+    return out
+
+
+def timeit(fn, warm=3, it=7):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(it):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def other_paths(dev, pk):
+    """Kernel-level numbers of the other BASELINE configs on one GPU (CUDA events around the public call, inputs in HBM)."""
+    from quantizedattention_b200 import attention_bf16 as Bf
+    from quantizedattention_b200 import attention_int8 as A
+    from quantizedattention_b200 import attention_jvp as J
+    from quantizedattention_b200 import ops
+    res = {}
+    i8, b16 = pk.get("int8_tops"), pk.get("bf16_tflops")
+    frac = lambda v, d: (v / d) if d else None
+    g = torch.Generator(device=dev).manual_seed(7)
+    rn = lambda *sh, dt=torch.float16: torch.randn(*sh, generator=g, device=dev, dtype=torch.float32).to(dt)
+    # configs[0]: int8 fwd B=1 H=8 S=1024 D=64 (64 CTAs on 148 SMs: latency-bound, reported as time)
+    q, k, v = [rn(1, 8, 1024, 64) for _ in range(3)]
+    with torch.no_grad():
+        ms = timeit(lambda: A.sage_attention_3_int8(q, k, v), it=20)
+    qi, sq = ops.quant_block(q, 128); ki, sk = ops.quant_block(k, 128); vi, sv = ops.quant_block(v, 128)
+    msk = timeit(lambda: ops.int8_fwd_prequant(qi, ki, vi, sq, sk, sv, 8, 1024, 1024, 64), it=20)
+    res["int8_fwd_cfg1_B1H8S1024D64"] = {"ms_call": ms, "ms_kernel": msk, "TOPS_kernel": 4.0 * 8 * 1024 * 1024 * 64 / (msk * 1e-3) / 1e12}
+    # bf16 forward at S = 8k, D = 128 (north_star target shape), B*H = 64
+    q, k = [rn(2, 32, 8192, 128) for _ in range(2)]
+    v = rn(2, 32, 8192, 128, dt=torch.bfloat16)
+    ms = timeit(lambda: ops.bf16_fwd(q, k, v, False))
+    t = 4.0 * 64 * 8192 * 8192 * 128 / (ms * 1e-3) / 1e12
+    res["bf16_fwd_S8192_D128"] = {"ms": ms, "TFLOPS": t, "frac_of_bf16_peak_in_run": frac(t, b16)}
+    del q, k, v
+    # configs[1]: bf16 fwd + bwd B=4 H=16 S=4096 D=128 causal (FLOPs counted at half the dense convention)
+    q, k = [rn(4, 16, 4096, 128) for _ in range(2)]
+    v = rn(4, 16, 4096, 128, dt=torch.bfloat16)
+    dO = rn(4, 16, 4096, 128, dt=torch.float32)
+    msf = timeit(lambda: ops.bf16_fwd(q, k, v, True))
+    O, lse = ops.bf16_fwd(q, k, v, True)
+    ops.TIMING = []
+    timeit(lambda: ops.bf16_bwd(q, k, v, O, lse, True, dO))
+    kt = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "bf16_bwd")
+    ops.TIMING = None
+    msb = kt[len(kt) // 2]
+    ff, fb = 0.5 * 4 * 64 * 4096 * 4096 * 128, 0.5 * 10 * 64 * 4096 * 4096 * 128
+    res["bf16_cfg2_B4H16S4096D128_causal"] = {"fwd_ms": msf, "fwd_TFLOPS": ff / (msf * 1e-3) / 1e12, "fwd_frac": frac(ff / (msf * 1e-3) / 1e12, b16),
+                                              "bwd_kernel_ms": msb, "bwd_TFLOPS": fb / (msb * 1e-3) / 1e12,
+                                              "bwd_frac": frac(fb / (msb * 1e-3) / 1e12, b16), "flops": "causal = half of dense"}
+    del q, k, v, dO, O, lse
+    # configs[3]: JVP B=16 H=16 S=4096 D=64 (kernel time; the call also casts six fp32 tensors to bf16)
+    t6 = [rn(16, 16, 4096, 64, dt=torch.float32) for _ in range(6)]
+    ops.TIMING = []
+    msc = timeit(lambda: J.helion_attention_jvp_forward_fp32(*t6), it=5)
+    kt = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "jvp_fwd")
+    ops.TIMING = None
+    msk = kt[len(kt) // 2]
+    fj = 12.0 * 256 * 4096 * 4096 * 64
+    res["jvp_cfg4_B16H16S4096D64"] = {"ms_call": msc, "ms_kernel": msk, "TFLOPS_kernel": fj / (msk * 1e-3) / 1e12,
+                                      "frac_of_bf16_peak_in_run": frac(fj / (msk * 1e-3) / 1e12, b16)}
+    del t6
+    torch.cuda.empty_cache()
+    return res
+
+
+def pcie_duplex(dev, barrier, world, dist):
+    """Full-duplex pinned host<->device copy of 512 MiB each way, all ranks at once: GB/s per direction per GPU (min over
+    ranks) = what the host can feed; e2e cannot beat bytes / this."""
+    n = 1 << 29
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def both():
+        for s, (dst, src) in ((s1, (d_in, h_in)), (s2, (h_out, d_out))):
+            with torch.cuda.stream(s):
+                s.wait_stream(torch.cuda.current_stream())
+                dst.copy_(src, non_blocking=True)
+        for s in (s1, s2):
+            torch.cuda.current_stream().wait_stream(s)
+
+    both(); barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        both()
+    b.record(); barrier()
+    t = torch.tensor([a.elapsed_time(b) / 3], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"duplex_GBs_each_way_per_gpu": n / t.item() / 1e6, "ranks_at_once": world}
+
+
+def ring_record(dev, world, rank, barrier, dist):
+    """BASELINE configs[4]: int8 forward B=1 H=32 S=131072 D=128, sequence-sharded ring KV over NCCL send/recv."""
+    from quantizedattention_b200.parallel import ring_int8_attention_fwd
+    B, H, S, D = 1, 32, 131072, 128
+    Sl = S // world
+    g = torch.Generator(device=dev).manual_seed(1005 + rank)
+    ql, kl, vl = [torch.randn(B, H, Sl, D, generator=g, device=dev, dtype=torch.float16) for _ in range(3)]
+    ring_int8_attention_fwd(ql, kl, vl)                                   # warm-up (NCCL channels, allocator)
+    barrier()
+    iters, timing = 2, []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ring_int8_attention_fwd(ql, kl, vl, timing=timing)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kern = [k0.elapsed_time(k1) for (_, k0, k1, _, _) in timing]
+    comm = [c0.elapsed_time(c1) for (_, _, _, c0, c1) in timing if c0 is not None]
+    hidden = [max(0.0, min(c0.elapsed_time(c1), k0.elapsed_time(k1))) for (_, k0, k1, c0, c1) in timing if c0 is not None]
+    shard_bytes = 2 * B * H * Sl * D + 2 * 2 * B * H * (Sl // 128)        # int8 K + V shard and their fp16 scales
+    avg = lambda xs: sum(xs) / max(1, len(xs))
+    ops_total = 4.0 * B * H * S * S * D
+    del ql, kl, vl
+    torch.cuda.empty_cache()
+    return {"workload": "int8 fwd B=1 H=32 S=131072 D=128, sequence-sharded ring KV (BASELINE configs[4])", "n_gpus": world,
+            "ms_per_pass": t.item(), "TOPS_total": ops_total / (t.item() * 1e-3) / 1e12,
+            "includes": "K token-sum all-reduce, Q/K/V quantisation, %d ring steps" % world,
+            "per_step_kernel_ms": avg(kern), "per_step_sendrecv_ms": avg(comm), "sendrecv_bytes_per_step": shard_bytes,
+            "sendrecv_GBs": shard_bytes / (avg(comm) * 1e-3) / 1e9 if comm else None,
+            "sendrecv_hidden_by_kernel_frac": (sum(hidden) / sum(comm)) if comm else None,
+            "limiter": "compute (the transfer of a step is shorter than its kernel and runs on a side stream)"
+                       if comm and avg(comm) < avg(kern) else "NCCL send/recv of the K/V shard"}
 
 
 class ClockSampler:
@@ -140,6 +301,8 @@ def main():
     ap.add_argument("--cpu-heads", type=int, default=96, help="heads in the cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ring", action="store_true", help="skip the configs[4] ring-KV record at N > 1")
+    ap.add_argument("--no-other-paths", action="store_true", help="skip the kernel-level records of the other configs at N = 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -160,7 +323,11 @@ def main():
             pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
         except Exception:  # noqa: BLE001
             pass
-        dist.init_process_group("nccl", device_id=dev)
+        try:                                    # NCCL's send/recv kernels must not queue behind the attention CTAs that fill
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # every SM: high-priority streams take the next free SM
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        except Exception:  # noqa: BLE001
+            dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
@@ -205,6 +372,31 @@ def main():
     ms_step = t_ms.item() / K
     value = ops_step * world / (ms_step * 1e-3) / 1e12
 
+    # ---- strong scaling: configs[2] split over the ranks (256 / world heads per GPU), same timing rules
+    strong = None
+    if world > 1 and (B * H) % world == 0:
+        hs = B * H // world
+        qs, ks, vs, dOs = [t.view(1, B * H, S, D)[:, :hs] for t in (q, k, v, dO)]
+
+        def step_s():
+            qr, kr, vr = qs.detach().requires_grad_(), ks.detach().requires_grad_(), vs.detach().requires_grad_()
+            A.sage_attention_3_int8(qr, kr, vr).backward(dOs)
+
+        for _ in range(W):
+            step_s()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(K):
+            step_s()
+        g1.record()
+        barrier()
+        ts = torch.tensor([g0.elapsed_time(g1) / K], device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"workload": "configs[2] split over the ranks", "heads_per_gpu": hs, "ms_per_step": ts.item(),
+                  "value": ops_step / (ts.item() * 1e-3) / 1e12, "unit": "TOPS",
+                  "input_bytes_per_gpu": 4 * hs * S * D * 2, "l2": "inputs %.0f MiB per GPU per step > 126 MB L2" % (4 * hs * S * D * 2 / 2 ** 20)}
+
     # ---- timed region 2 (e2e): host buffers -> device -> public API -> results back to pinned host memory
     e2e = None
     if not args.no_e2e:
@@ -232,14 +424,42 @@ def main():
         e2e = {"value": ops_step * world / (te.item() / Ke * 1e-3) / 1e12, "unit": "TOPS",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": Ke}
 
+    pcie = None
+    if not args.no_e2e:
+        del pipe, outs_host
+        pcie = pcie_duplex(dev, barrier, world, dist)
+    del q, k, v, dO, host
+    torch.cuda.empty_cache()
+    ring = None
+    if world > 1 and not args.no_ring:
+        try:
+            ring = ring_record(dev, world, rank, barrier, dist)
+        except Exception as e:  # noqa: BLE001
+            ring = {"error": str(e)[:200]}
+    pk = measure_peaks(dev) if rank == 0 else {}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    mp, int8_peak = peaks()
+    mp = peaks()
+    int8_peak = pk.get("int8_tops")
+    others = None
+    if world == 1 and not args.no_other_paths:
+        try:
+            others = other_paths(dev, pk)
+        except Exception as e:  # noqa: BLE001
+            others = {"error": str(e)[:200]}
     avg = lambda xs: sum(xs) / len(xs)
     bwd_ms, fwd_ms = avg(kt["int8_bwd"]), avg(kt["int8_fwd"])
+    peak_src = "int8 dense measured IN THIS RUN: torch._int_mm 8192^3 best-of-10 (MEASURED_PEAKS.json has bf16 only: burst x2 = %.0f)" % (2 * mp.get("bf16_tflops", 0))
+    if not int8_peak:
+        try:
+            int8_peak = json.load(open(os.path.join(ROOT, "profiles", "r01_peaks.json"))).get("int8_tops_int_mm")
+            peak_src = "int8 dense: torch._int_mm 8192^3 best-of-10 on this pool (profiles/r01_peaks.json); the in-run probe failed"
+        except Exception:  # noqa: BLE001
+            pass
     peak = int8_peak or 2.0 * mp.get("bf16_tflops", 1590.0)
     traffic = None                      # dram__bytes_read + dram__bytes_write per launch from the ncu --set full capture
     try:
@@ -248,14 +468,14 @@ def main():
         pass
     roof = {"bound": "tensor", "kernel": "int8_bwd_ws_kernel<128>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
             "peak": peak, "unit": "TFLOP/s", "traffic": traffic,
-            "peak_source": "int8 dense: torch._int_mm 8192^3 best-of-10 on this pool (profiles/r01_peaks.json); "
-                           "MEASURED_PEAKS.json has no int8 entry (its bf16 burst x2 = %.0f)" % (2 * mp.get("bf16_tflops", 0)),
+            "peak_source": peak_src,
             "share_of_step": bwd_ms / ms_step,
-            "note": "binding unit is not the tensor pipe: per (128 x 128) tile the int8 MMAs take ~2.5k of ~6.7k clk; the "
-                    "rest is the reference's per-tile re-quantisation on the CUDA cores (two passes, ~24 instructions per "
-                    "logit, 384 KB of int32 TMEM drains per tile).  The kernel is warp-specialised: 8 quantise warps "
-                    "(96 registers) and 8 drain warps (160 registers, fp32 dV/dK accumulators) share the register file",
-            "other_kernels": {"int8_fwd_kernel<128,2,3>": {"ms": fwd_ms, "achieved": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12,
+            "note": "binding unit is not the tensor pipe: per (128 x 128) tile the int8 MMAs take ~2.8k of ~6.3k clk; the rest is "
+                    "the reference's per-tile re-quantisation on the CUDA cores (two passes: 16 exp2 + 16 float->int per clock "
+                    "and SM on the XU pipe, 384 KB of TMEM drains per tile).  Warp-specialised: 8 quantise warps (96 registers) "
+                    "and 8 drain warps (160 registers, fp32 dV/dK accumulators); accumulators start at 1.5*2^23 so no "
+                    "int->float conversion is executed (DESIGN.md 4)",
+            "other_kernels": {"int8_fwd_kernel<128,2,3,magic>": {"ms": fwd_ms, "achieved": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12,
                                                            "frac": OPS_FWD(B, H, S, D) / (fwd_ms * 1e-3) / 1e12 / peak}}}
     roof["frac"] = roof["achieved"] / peak
 
@@ -280,6 +500,7 @@ def main():
         "per_gpu_tops": value / world, "frac_of_int8_peak_measured": value / world / peak,
         "frac_of_int8_peak_spec_4500": value / world / 4500.0,
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "strong_scaling": strong, "ring_kv": ring, "other_paths": others, "peaks_in_run": pk, "pcie": pcie,
         "gpu_launches": 10 * K,   # k_mean x2, quant x4 (q, k, v, dO), int8 fwd, delta, int8 bwd, dQ finalize
     }))
     if world > 1:

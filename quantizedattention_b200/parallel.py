@@ -7,7 +7,10 @@ over NVLink 5 / NVSwitch on the GPU box; gloo on CPU in the tests).
     [r*S/g, (r+1)*S/g).  One tiny all-reduce (K token sums, [B,H,1,D] fp32) makes every rank smooth K with the same
     global mean; then g steps: attend the local queries to the K/V shard currently held, continuing the SAME
     online-softmax state (m, l, O) across steps, while the int8 K/V shard + its scales travel to the next rank with
-    batched isend/irecv on a side stream (double-buffered, overlapping the kernel).
+    batched isend/irecv on a side stream (double-buffered, overlapping the kernel).  The attention kernel keeps one CTA
+    on every SM, so create the NCCL process group with high-priority streams
+    (`ProcessGroupNCCL.Options(is_high_priority_stream=True)`, as bench.py does): NCCL's send/recv CTAs then take the
+    next SM an attention CTA leaves instead of queueing behind the whole grid.
 """
 from __future__ import annotations
 
@@ -64,9 +67,13 @@ class CudaRingKernels(RingInt8Kernels):
                                      state_in=state, want_lse32=True)
 
 
-def ring_int8_attention_fwd(q, k, v, Bq: int = 128, Bkv: int = 128, group=None, kernels: RingInt8Kernels | None = None):
+def ring_int8_attention_fwd(q, k, v, Bq: int = 128, Bkv: int = 128, group=None, kernels: RingInt8Kernels | None = None,
+                            timing: list | None = None):
     """Sequence-sharded int8 attention forward.  q, k, v: this rank's fp16 [B,H,S/g,D] shards (rank order = sequence
-    order).  Returns (O fp16 [B,H,S/g,D], lse fp16 [B*H*S/g], lse32, k_mean fp16 [B,H,1,D])."""
+    order).  Returns (O fp16 [B,H,S/g,D], lse fp16 [B*H*S/g], lse32, k_mean fp16 [B,H,1,D]).
+    timing: pass a list to collect one (step, compute_start, compute_end, comm_start, comm_end) tuple of CUDA events per
+    ring step (comm events are None on the last step): bench.py reports the kernel time, the send/recv time and how much
+    of the latter the kernel hides."""
     kernels = kernels or CudaRingKernels()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -91,19 +98,36 @@ def ring_int8_attention_fwd(q, k, v, Bq: int = 128, Bkv: int = 128, group=None, 
             if comm_stream is not None:
                 comm_stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(comm_stream):
+                    if timing is not None:
+                        ev_c0 = torch.cuda.Event(enable_timing=True); ev_c0.record()
                     reqs = dist.batch_isend_irecv(ops_)
             else:
                 reqs = dist.batch_isend_irecv(ops_)
         last = step == world - 1
+        if timing is not None and use_cuda:
+            ev_k0 = torch.cuda.Event(enable_timing=True); ev_k0.record()
         res = kernels.attend(q_i8, sq, cur, state, BH, Sl, Sl, D, Bq, Bkv, last)
+        if timing is not None and use_cuda:
+            ev_k1 = torch.cuda.Event(enable_timing=True); ev_k1.record()
         if last:
             out = res
         else:
             state = res
-        for r in reqs:
-            r.wait()
         if comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(comm_stream)
+            ev_c1 = None
+            with torch.cuda.stream(comm_stream):               # the side stream waits for the transfers, the kernel does not
+                for r in reqs:
+                    r.wait()
+                if timing is not None and nxt is not None:
+                    ev_c1 = torch.cuda.Event(enable_timing=True); ev_c1.record()
+            if timing is not None:
+                timing.append((step, ev_k0, ev_k1, ev_c0 if ev_c1 is not None else None, ev_c1))
+            torch.cuda.current_stream().wait_stream(comm_stream)   # the next step's kernel reads the received shard
+        else:
+            for r in reqs:
+                r.wait()
+            if timing is not None and use_cuda:
+                timing.append((step, ev_k0, ev_k1, None, None))
         if nxt is not None:
             cur = nxt
     O, lse16, lse32 = out

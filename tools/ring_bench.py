@@ -19,7 +19,11 @@ def main():
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    try:                                        # NCCL's send/recv kernels must not queue behind the attention CTAs that fill every SM
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    except Exception:  # noqa: BLE001
+        dist.init_process_group("nccl", device_id=dev)
     if mode == "check":
         B, H, S, D = 1, 4, 4096, 128
     else:
