@@ -28,6 +28,13 @@ extern "C" {
 int qa_version(void);
 const char* qa_last_error(void);
 
+/* Bytes of the caller-owned workspace an op needs (the library never allocates device memory). */
+#define QA_WS_K_MEAN 0             /* qa_k_mean / qa_k_token_sum `workspace` */
+#define QA_WS_INT8_BWD_DQ 1        /* qa_int8_bwd `dq_ws_f32` (zero-initialised by the caller) */
+#define QA_WS_INT8_BWD_ROWSUM 2    /* qa_int8_bwd `rowsum_ws_f32` (zero-initialised by the caller) */
+#define QA_WS_JVP_BF16_OPERANDS 3  /* the six bf16 operand copies qa_jvp_fwd reads (made with qa_cast_f32) */
+size_t qa_workspace_bytes(int op, int B, int H, int S, int D);
+
 /* ---- int8 path pre-passes (replace the per-tile-pair recomputation inside attention_int8.py:178-195, 241-247) ---- */
 
 /* K-smoothing mean, attention_int8.py:24-25 under LEDGER I-1: mean over tokens per (b,h), fp32 accumulate, fp16 out

@@ -19,6 +19,7 @@ SIGNATURES = {
     "qa_version": (c_int, []),
     "qa_last_error": (ctypes.c_char_p, []),
     "qa_k_mean_workspace_bytes": (c_size_t, [c_int] * 4),
+    "qa_workspace_bytes": (c_size_t, [c_int] * 5),
     "qa_k_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_quant_block": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_k_token_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),

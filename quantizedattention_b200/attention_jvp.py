@@ -2,16 +2,14 @@
 
   helion_attention_jvp_forward_fp32(q,k,v,tq,tk,tv) -> (O, tO, lse)     attention_jvp.py:33-195
   baseline_pytorch_attention(q,k,v)                                     attention_jvp.py:197-215
-plus (LEDGER J-1, north_star "forward-mode-AD-compatible callables") `jvp_attention(q,k,v)`, a
-torch.autograd.Function with a `jvp` staticmethod so that torch.func.jvp / torch.autograd.forward_ad route
-through the fused kernel.
+plus (LEDGER J-1, north_star "forward-mode-AD-compatible callables") `jvp_attention(q,k,v)`: under torch.func.jvp /
+torch.autograd.forward_ad it takes the tangents off its dual inputs and returns a dual output from ONE fused launch.
 """
 from __future__ import annotations
 
 import math
 
 import torch
-from torch.autograd import Function
 
 from . import ops
 
@@ -33,36 +31,24 @@ def baseline_pytorch_attention(q, k, v):
     return torch.matmul(p, v)
 
 
-class _JvpAttention(Function):
-    """O = softmax(q k^T / sqrt(d)) v with a fused forward-mode rule (no reverse-mode rule: the reference has none)."""
+def jvp_attention(q, k, v):
+    """Forward-mode-AD-compatible attention O = softmax(q k^T / sqrt(d)) v (LEDGER J-1).
 
-    @staticmethod
-    def forward(q, k, v):
+        O, tO = torch.func.jvp(jvp_attention, (q, k, v), (tq, tk, tv))
+        with fwAD.dual_level(): out = jvp_attention(fwAD.make_dual(q, tq), ...);  O, tO = fwAD.unpack_dual(out)
+
+    ONE launch of the fused kernel produces both O and tO (attention_jvp.py:129-190 carries the tangents through the same
+    tiles): the inputs' tangents are taken off the dual tensors here, the kernel runs below any functorch level, and the
+    result goes back as a dual tensor.  Inputs without a tangent count as zero tangents; without any tangent the call is
+    a plain forward.  There is no reverse-mode rule (the reference has none): use flash_atten_2_bf16 for training."""
+    import torch.autograd.forward_ad as fwAD
+    duals = [fwAD.unpack_dual(t) for t in (q, k, v)]
+    tangents = [d.tangent for d in duals]
+    if all(t is None for t in tangents):
         zeros = torch.zeros_like
         O, _, _ = ops.jvp_fwd(q, k, v, zeros(q), zeros(k), zeros(v))
         return O
-
-    # TODO(perf): a primal-only launch would skip the three tangent contractions; forward() is only reached when the
-    # caller asks for O without tangents, the fused O + tO path is jvp() below.
-
-    @staticmethod
-    def setup_context(ctx, inputs, output):
-        ctx.save_for_forward(*inputs)
-
-    @staticmethod
-    def jvp(ctx, tq, tk, tv):
-        q, k, v = ctx.saved_tensors
-        uq, uk, uv = ops._unwrap(q), ops._unwrap(k), ops._unwrap(v)
-        with ops._raw_mode():
-            z = lambda t, ref: torch.zeros_like(ref) if t is None else ops._unwrap(t)
-            _, tO, _ = ops.jvp_fwd(uq, uk, uv, z(tq, uq), z(tk, uk), z(tv, uv))
-        return tO
-
-    @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError("jvp_attention is forward-mode only; use flash_atten_2_bf16 for reverse mode")
-
-
-def jvp_attention(q, k, v):
-    """Forward-mode-AD-compatible attention: `torch.func.jvp(jvp_attention, (q,k,v), (tq,tk,tv))` -> (O, tO)."""
-    return _JvpAttention.apply(q, k, v)
+    primals = [d.primal for d in duals]
+    tangents = [torch.zeros_like(p) if t is None else t for p, t in zip(primals, tangents)]
+    O, tO, _ = ops.jvp_fwd(*[p.detach() for p in primals], *[t.detach() for t in tangents])   # unwraps functorch levels itself
+    return fwAD.make_dual(O, tO)

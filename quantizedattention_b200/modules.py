@@ -1,0 +1,93 @@
+"""Layout adapters and `nn.Module` wrappers around the three drop-in paths.
+
+The reference (and the kernels) use contiguous `[B, H, S, D]`; most model code carries `[B, S, H, D]` (what
+`F.scaled_dot_product_attention` callers get from a fused QKV projection before their transpose).  The adapters below
+accept either layout, run the kernels on a `[B, H, S, D]` contiguous view (one transposing copy per tensor when the input
+is `bshd`; none when it already is `bhsd`), and return the output in the caller's layout.  Nothing here computes
+attention: every path ends in the C-ABI kernels.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import attention_bf16, attention_int8, attention_jvp
+
+_LAYOUTS = ("bhsd", "bshd")
+
+
+def _to_bhsd(t: torch.Tensor, layout: str) -> torch.Tensor:
+    if layout not in _LAYOUTS:
+        raise ValueError('layout must be "bhsd" ([B,H,S,D], the reference layout) or "bshd" ([B,S,H,D])')
+    if t.dim() != 4:
+        raise ValueError("attention inputs are 4-D")
+    return t.contiguous() if layout == "bhsd" else t.transpose(1, 2).contiguous()
+
+
+def _from_bhsd(t: torch.Tensor, layout: str) -> torch.Tensor:
+    return t if layout == "bhsd" else t.transpose(1, 2)
+
+
+def sage_attention_int8(q, k, v, causal: bool = False, layout: str = "bshd", **tunables):
+    """`sage_attention_3_int8` (attention_int8.py:434-451) for `[B,S,H,D]` (default) or `[B,H,S,D]` fp16 tensors;
+    differentiable.  **tunables: Bq=, Bkv=, rounding= (see attention_int8)."""
+    o = attention_int8.sage_attention_3_int8(*[_to_bhsd(t, layout) for t in (q, k, v)], causal=causal, **tunables)
+    return _from_bhsd(o, layout)
+
+
+def flash_attention_bf16(q, k, v, causal: bool = False, layout: str = "bshd"):
+    """`flash_atten_2_bf16` (attention_bf16.py:87-105): q, k fp16, v bf16 -> O fp32, in the caller's layout."""
+    o = attention_bf16.flash_atten_2_bf16(*[_to_bhsd(t, layout) for t in (q, k, v)], bool(causal))
+    return _from_bhsd(o, layout)
+
+
+def jvp_attention(q, k, v, layout: str = "bshd"):
+    """`attention_jvp.jvp_attention` (forward-mode-AD attention, fp32) in the caller's layout."""
+    return _from_bhsd(attention_jvp.jvp_attention(*[_to_bhsd(t, layout) for t in (q, k, v)]), layout)
+
+
+class SageAttention3Int8(nn.Module):
+    """Drop-in attention core: `forward(q, k, v)` -> O (fp16), SageAttention3-style int8 forward and backward."""
+
+    def __init__(self, causal: bool = False, layout: str = "bshd", Bq: int | None = None, Bkv: int | None = None,
+                 rounding: str | None = None):
+        super().__init__()
+        if layout not in _LAYOUTS:
+            raise ValueError('layout must be "bhsd" or "bshd"')
+        self.causal, self.layout = causal, layout
+        self.tunables = {k: v for k, v in (("Bq", Bq), ("Bkv", Bkv), ("rounding", rounding)) if v is not None}
+
+    def forward(self, q, k, v):
+        return sage_attention_int8(q, k, v, self.causal, self.layout, **self.tunables)
+
+    def extra_repr(self):
+        return f"causal={self.causal}, layout={self.layout!r}, tunables={self.tunables}"
+
+
+class FlashAttentionBF16(nn.Module):
+    """`forward(q_fp16, k_fp16, v_bf16)` -> O fp32: bias-corrected bf16 flash attention with its recompute backward."""
+
+    def __init__(self, causal: bool = False, layout: str = "bshd"):
+        super().__init__()
+        if layout not in _LAYOUTS:
+            raise ValueError('layout must be "bhsd" or "bshd"')
+        self.causal, self.layout = causal, layout
+
+    def forward(self, q, k, v):
+        return flash_attention_bf16(q, k, v, self.causal, self.layout)
+
+    def extra_repr(self):
+        return f"causal={self.causal}, layout={self.layout!r}"
+
+
+class JvpAttention(nn.Module):
+    """`forward(q, k, v)` -> O fp32; under torch.func.jvp / forward_ad the tangent comes from the same fused launch."""
+
+    def __init__(self, layout: str = "bshd"):
+        super().__init__()
+        if layout not in _LAYOUTS:
+            raise ValueError('layout must be "bhsd" or "bshd"')
+        self.layout = layout
+
+    def forward(self, q, k, v):
+        return jvp_attention(q, k, v, self.layout)

@@ -6,6 +6,7 @@ registered backward formulas, so the attention calls survive `torch.compile(full
 
     qattn::sage_int8_fwd / qattn::sage_int8_bwd   ->  sage_attention_3_int8_op(q, k, v)
     qattn::flash_bf16_fwd / qattn::flash_bf16_bwd ->  flash_atten_2_bf16_op(q, k, v, causal)
+    qattn::jvp_fwd                                 ->  attention_jvp_op(q, k, v, tq, tk, tv) -> (O, tO, lse)
 
 Numerics are those of `attention_int8.sage_attention_3_int8` / `attention_bf16.flash_atten_2_bf16` (same kernels, the
 block sizes and rounding mode current at call time are baked in as integer arguments).
@@ -131,3 +132,22 @@ flash_bf16_fwd.register_autograd(_flash_backward, setup_context=_flash_setup)
 def flash_atten_2_bf16_op(q_fp16: _T, k_fp16: _T, v_bf16: _T, causal: bool) -> _T:
     """`flash_atten_2_bf16` (attention_bf16.py:87-105) as a traceable operator: O fp32 [B,H,S,D]."""
     return flash_bf16_fwd(q_fp16, k_fp16, v_bf16, causal)[0]
+
+
+# ------------------------------------------------------------------------------------------------ forward-mode JVP attention
+@torch.library.custom_op("qattn::jvp_fwd", mutates_args=())
+def jvp_fwd(q: _T, k: _T, v: _T, tq: _T, tk: _T, tv: _T) -> Tuple[_T, _T, _T]:
+    """helion_attention_jvp_forward_fp32 (attention_jvp.py:33-195): (O, tO fp32 [B,H,S,D], lse fp32 [B*H,S])."""
+    return ops.jvp_fwd(q, k, v, tq, tk, tv)
+
+
+@jvp_fwd.register_fake
+def _(q, k, v, tq, tk, tv):
+    B, H, S, D = q.shape
+    f32 = lambda *sh: q.new_empty(sh, dtype=torch.float32)
+    return f32(B, H, S, D), f32(B, H, S, D), f32(B * H, S)
+
+
+def attention_jvp_op(q: _T, k: _T, v: _T, tq: _T, tk: _T, tv: _T) -> Tuple[_T, _T, _T]:
+    """The reference's JVP kernel function as a traceable operator (survives torch.compile(fullgraph=True))."""
+    return jvp_fwd(q, k, v, tq, tk, tv)
