@@ -810,6 +810,314 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward for quantisation blocks smaller than the MMA tile: Bq, Bkv in {32, 64, 128} (the reference's tunables,
+// PowerOfTwoFragment(32, 256, 32), attention_int8.py:155-158; 32/32 is its untuned default).  The 128 x 128 tile then
+// holds (128/Bq) x (128/Bkv) quantisation blocks of P and dS, each with its own scale (attention_int8.py:363-365,
+// 403-405), dO and Q have one scale per Bq rows, K and V one per Bkv keys.  S and dP scale per (row block, key block) and
+// stay one MMA each; the three contractions whose scales change ALONG the reduction axis are issued one quantisation
+// block at a time (dV, dK: over the query-row blocks; dQ: over the key blocks) - each a subset of the k-steps of the
+// full-tile MMA into a freshly initialised accumulator - and drained with the scale of that block and of the thread's own
+// row.  Correctness-first schedule: the phases of a tile pair run one after the other (no cross-tile software pipeline),
+// 8 warps, thread = (row, column half).  Same numerics as int8_bwd_kernel otherwise (magic accumulators, fp16-carried P).
+// ---------------------------------------------------------------------------------------------------------
+template <int D, bool RN>
+__global__ void __launch_bounds__(256, 1)
+int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                    const __grid_constant__ CUtensorMap tm_dq, Int8BwdParams p, int BQ, int BK) {
+  using L = Int8BwdSmem<D>;
+  constexpr int DH = D / 2, CW = 64, NT = 256;
+  constexpr uint32_t kLay = (D == 128) ? kSwz128 : kSwz64;
+  constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t kv_full, qdo_full, mma_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t amax_p_s[2][4][4], amax_ds_s[2][4][4];     // float bits (values >= 0): atomicMax on the bit pattern
+  __shared__ float rowsum_ds[2][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool leader = (tid == 0);
+  const int bh = blockIdx.y, j = blockIdx.x;
+  const int nq = p.S / 128;
+  const int NRB = 128 / BQ, NCB = 128 / BK;
+  const size_t head_row0 = (size_t)bh * p.S;
+
+  if (leader) {
+    mbar_init(&kv_full, 1); mbar_init(&qdo_full, 1); mbar_init(&mma_done, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) { (&amax_p_s[0][0][0])[tid] = 0u; (&amax_ds_s[0][0][0])[tid] = 0u; }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  if (tid >= 64 && tid < 192) {                                 // constant atoms of the accumulator-initialising MMA
+    const uint32_t v2 = tid < 128 ? kMagicElemA2 : kMagicElemB2;
+    sts128(smem_u32(smem + L::off_c) + (tid - 64) * 16, v2, v2, v2, v2);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+
+  constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128);
+  constexpr uint32_t id_t = umma_idesc(2, 1, 1, 1, 1, 128, D);
+  constexpr uint32_t id_q = umma_idesc(2, 1, 1, 0, 1, 128, D);
+  constexpr uint32_t id_c128 = umma_idesc(1, 0, 0, 0, 0, 128, 128), id_cD = umma_idesc(1, 0, 0, 0, 0, 128, D);
+  const uint64_t cdesc_a = umma_smem_desc(smem_u32(smem + L::off_c), 16, 0, kLay), cdesc_b = umma_smem_desc(smem_u32(smem + L::off_c + 1024), 16, 0, kLay);
+  const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v);
+  const uint32_t a_q = smem_u32(smem + L::off_q), a_do = smem_u32(smem + L::off_do);
+  const uint32_t a_p = smem_u32(smem + L::off_p), a_ds = smem_u32(smem + L::off_ds);
+
+  if (leader) {
+    mbar_expect_tx(&kv_full, 2 * L::kTile);
+    tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
+    tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
+    mbar_wait(&kv_full, 0);
+  }
+
+  const int half = warp >> 2;
+  const int row = (warp & 3) * 32 + lane;                       // query row (S, dP, dQ) or key (dV, dK)
+  const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+  const int rb = row / BQ;                                      // row block of this thread's QUERY row
+  const int kb = row / BK;                                      // key block of this thread's KEY row
+  float sk_c[4], sv_c[4];                                       // scales of the key blocks of this k-tile
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    sk_c[c] = c < NCB ? __half2float(p.sk[(head_row0 + (size_t)j * 128) / BK + c]) : 0.f;
+    sv_c[c] = c < NCB ? __half2float(p.sv[(head_row0 + (size_t)j * 128) / BK + c]) : 0.f;
+  }
+  float2 dv_acc[DH / 2], dk_acc[DH / 2];
+#pragma unroll
+  for (int d = 0; d < DH / 2; ++d) { dv_acc[d] = make_float2(0.f, 0.f); dk_acc[d] = make_float2(0.f, 0.f); }
+  const float2 nM2 = make_float2(-kMagic, -kMagic);
+  constexpr float kPs = 1.0f / 1024.0f;
+  uint32_t n_mma = 0;                                           // completed phases of mma_done (same count in every thread)
+
+  for (int t = 0; t < nq; ++t) {
+    const uint32_t ab = t & 1;                                   // amax buffer of this tile
+    const size_t qrow = head_row0 + (size_t)t * 128 + row;
+    const size_t qblk0 = (head_row0 + (size_t)t * 128) / BQ;
+    const float sq_f = __half2float(p.sq[qblk0 + rb]);
+    const float sdo_f = __half2float(p.s_do[qblk0 + rb]);
+    const float lse = p.lse[qrow];
+    const float dlt = p.delta[qrow];
+    if (leader) {
+      mbar_expect_tx(&qdo_full, 2 * L::kTile);
+      tma_load_2d(smem + L::off_q, &tm_q, &qdo_full, 0, (int)head_row0 + t * 128);
+      tma_load_2d(smem + L::off_do, &tm_do, &qdo_full, 0, (int)head_row0 + t * 128);
+      mbar_wait(&qdo_full, t & 1);
+      umma_f16_ss(tbase + 0, cdesc_a, cdesc_b, id_c128, 0);
+      umma_f16_ss(tbase + 128, cdesc_a, cdesc_b, id_c128, 0);
+#pragma unroll
+      for (int k = 0; k < D / 32; ++k) {
+        umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, 1);
+        umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, 1);
+      }
+      umma_commit(&mma_done);
+    }
+    mbar_wait(&mma_done, n_mma & 1); ++n_mma;
+    tc_fence_after();
+    // ---- pass 1: P (carried as fp16 of 1024 * P), block amax of P and |dS|, row sum of dS
+    __half2 pk[CW / 2];
+    float am_p[2] = {0.f, 0.f}, am_ds[2] = {0.f, 0.f};            // this thread's (up to two) key blocks
+    float2 rs2acc = make_float2(0.f, 0.f);
+    const float nlse = 10.0f - lse;
+    const int cb_first = (half * CW) / BK;
+#pragma unroll
+    for (int ch = 0; ch < CW / 16; ++ch) {
+      const int cb = (half * CW + ch * 16) / BK;                 // a 16-column chunk lies inside one key block (Bkv >= 32)
+      const float c_s = magic_scale(sq_f * sk_c[cb & 3] * p.qk_scale);
+      const float cdpk = magic_scale(sdo_f * sv_c[cb & 3] * kPs);
+      const float2 cs2 = make_float2(c_s, c_s), nbs2 = make_float2(-kMagic * c_s, -kMagic * c_s);
+      const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(-dlt * kPs - kMagic * cdpk, -dlt * kPs - kMagic * cdpk);
+      uint32_t r[16], r2[16];
+      tmem_ld16(lane_addr + half * CW + ch * 16, r);
+      tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
+      tmem_ld_wait();
+      float mp = 0.f, md = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        const __half2 h = __float22half2_rn(__ffma2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), cs2, nbs2));
+        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+        const float2 pp = make_float2(ex2_approx(fhadd_lo(hu, nlse)), ex2_approx(fhadd_hi(hu, nlse)));     // 1024 * P
+        const __half2 pr = __float22half2_rn(pp);
+        pk[ch * 8 + c / 2] = pr;
+        mp = fmaxf(mp, fmaxf(__low2float(pr), __high2float(pr)));
+        const float2 d = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), cdp2, ndlt2));
+        md = fmaxf(md, fmaxf(fabsf(d.x), fabsf(d.y)));
+        rs2acc = __fadd2_rn(rs2acc, d);
+      }
+      am_p[cb - cb_first] = fmaxf(am_p[cb - cb_first], mp);
+      am_ds[cb - cb_first] = fmaxf(am_ds[cb - cb_first], md);
+    }
+    // the 32 rows of a warp share one row block (Bq >= 32): warp maximum, then one shared-memory atomic per block
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        am_p[i] = fmaxf(am_p[i], __shfl_xor_sync(0xffffffffu, am_p[i], o));
+        am_ds[i] = fmaxf(am_ds[i], __shfl_xor_sync(0xffffffffu, am_ds[i], o));
+      }
+      if (lane == 0 && cb_first + i < NCB && (i == 0 || BK == 32)) {
+        atomicMax(&amax_p_s[ab][rb][cb_first + i], __float_as_uint(am_p[i]));
+        atomicMax(&amax_ds_s[ab][rb][cb_first + i], __float_as_uint(am_ds[i]));
+      }
+    }
+    rowsum_ds[half][row] = rs2acc.x + rs2acc.y;
+    tc_fence_before();
+    named_bar_sync(1, NT);                                       // block maxima complete; S / dP read by everybody
+    if (tid < 16) { (&amax_p_s[ab ^ 1][0][0])[tid] = 0u; (&amax_ds_s[ab ^ 1][0][0])[tid] = 0u; }   // for the next tile
+    if (half == 0 && p.rowsum != nullptr) atomicAdd(p.rowsum + qrow, rowsum_ds[0][row] + rowsum_ds[1][row]);
+    // ---- pass 2: quantise P and dS with the scale of their block, store both tiles ([q row][128 key bytes], swizzled)
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < CW / 16; ++ch) {
+      const int cb = (half * CW + ch * 16) / BK;
+      const float amp = __uint_as_float(amax_p_s[ab][rb][cb]), amd = __uint_as_float(amax_ds_s[ab][rb][cb]);
+      const float inv_p = amp > 0.f ? __fdividef(127.0f, amp) : 0.f;
+      const float inv_ds = amd > 0.f ? __fdividef(127.0f, amd) : 0.f;
+      const float cdpi = magic_scale(sdo_f * sv_c[cb & 3] * kPs * inv_ds);
+      const float2 cdpi2 = make_float2(cdpi, cdpi), ndlti2 = make_float2(-dlt * kPs * inv_ds - kMagic * cdpi, -dlt * kPs * inv_ds - kMagic * cdpi);
+      const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
+      uint32_t r2[16];
+      tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
+      tmem_ld_wait();
+      uint32_t wp[4], wd[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t bp[4];
+        int bd[4];
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const int c = q4 * 4 + e;
+          const float2 pp = __half22float2(pk[ch * 8 + c / 2]);
+          const float2 dq = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), cdpi2, ndlti2));
+          const float2 pq = RN ? __ffma2_rn(pp, invp2, magic2) : __ffma2_rz(pp, invp2, magic2);
+          bp[e] = __float_as_uint(pq.x);
+          bp[e + 1] = __float_as_uint(pq.y);
+          bd[e] = RN ? __float2int_rn(dq.x) : __float2int_rz(dq.x);
+          bd[e + 1] = RN ? __float2int_rn(dq.y) : __float2int_rz(dq.y);
+        }
+        wp[q4] = pack_low_bytes(bp[0], bp[1], bp[2], bp[3]);
+        wd[q4] = pack_sat_s8x4(bd[0], bd[1], bd[2], bd[3]);
+      }
+      const uint32_t off = swz128(row, half * CW + ch * 16);
+      sts128(smem_base + L::off_p + off, wp[0], wp[1], wp[2], wp[3]);
+      sts128(smem_base + L::off_ds + off, wd[0], wd[1], wd[2], wd[3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(2, NT);                                       // P / dS tiles stored; dP read by everybody
+    // ---- dV_j += P^T dO, dK_j += dS^T Q: one query-row block at a time (the scales change along the contraction)
+    for (int qb = 0; qb < NRB; ++qb) {
+      if (leader) {
+        tc_fence_after();
+        umma_f16_ss(tbase + 256, cdesc_a, cdesc_b, id_cD, 0);
+        umma_f16_ss(tbase + 384, cdesc_a, cdesc_b, id_cD, 0);
+        for (int k = qb * (BQ / 32); k < (qb + 1) * (BQ / 32); ++k) {
+          umma_i8_ss(tbase + 256, umma_smem_desc(a_p + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_do + k * 32 * D, 16, kSbo, kLay), id_t, 1);
+          umma_i8_ss(tbase + 384, umma_smem_desc(a_ds + k * 4096, 16, 1024, kSwz128), umma_smem_desc(a_q + k * 32 * D, 16, kSbo, kLay), id_t, 1);
+        }
+        umma_commit(&mma_done);
+      }
+      mbar_wait(&mma_done, n_mma & 1); ++n_mma;
+      tc_fence_after();
+      // this thread's row is a KEY here: block (qb, kb)
+      const float c_dv = __half2float(p.s_do[qblk0 + qb]) * __uint_as_float(amax_p_s[ab][qb][kb]) * (kPs / 127.0f);
+      const float c_dk = __uint_as_float(amax_ds_s[ab][qb][kb]) * (1.0f / 127.0f) * __half2float(p.sq[qblk0 + qb]) * p.sm_scale;
+#pragma unroll
+      for (int ch = 0; ch < DH / 16; ++ch) {
+        uint32_t r[16], r2[16];
+        tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
+        tmem_ld16(lane_addr + 384 + half * DH + ch * 16, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dv_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), nM2),
+                                          make_float2(c_dv, c_dv), dv_acc[ch * 8 + c]);
+          dk_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r2[2 * c]), __uint_as_float(r2[2 * c + 1])), nM2),
+                                          make_float2(c_dk, c_dk), dk_acc[ch * 8 + c]);
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(1, NT);                                     // partial columns drained by everybody
+    }
+    // ---- dQ_t += dS K: one key block at a time; this thread's row is a QUERY row: block (rb, cb)
+    float2 dq_acc[DH / 2];
+#pragma unroll
+    for (int d = 0; d < DH / 2; ++d) dq_acc[d] = make_float2(0.f, 0.f);
+    for (int cb = 0; cb < NCB; ++cb) {
+      if (leader) {
+        tc_fence_after();
+        umma_f16_ss(tbase + 256, cdesc_a, cdesc_b, id_cD, 0);
+        for (int k = cb * (BK / 32); k < (cb + 1) * (BK / 32); ++k)
+          umma_i8_ss(tbase + 256, umma_smem_desc(a_ds + k * 32, 16, 1024, kSwz128), umma_smem_desc(a_k + k * 32 * D, 16, kSbo, kLay), id_q, 1);
+        umma_commit(&mma_done);
+      }
+      mbar_wait(&mma_done, n_mma & 1); ++n_mma;
+      tc_fence_after();
+      const float c_dq = __uint_as_float(amax_ds_s[ab][rb][cb]) * (1.0f / 127.0f) * __half2float(p.sk[(head_row0 + (size_t)j * 128) / BK + cb]) * p.sm_scale;
+#pragma unroll
+      for (int ch = 0; ch < DH / 16; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + 256 + half * DH + ch * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          dq_acc[ch * 8 + c] = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1])), nM2),
+                                          make_float2(c_dq, c_dq), dq_acc[ch * 8 + c]);
+      }
+      tc_fence_before();
+      named_bar_sync(2, NT);
+    }
+    // ---- dQ tile -> fp32 staging (swizzled 32-float atoms) -> TMA reduce-add into the workspace
+    if (leader) tma_store_wait_read();                           // the previous tile's reduce-add has read the staging tile
+    named_bar_sync(1, NT);
+#pragma unroll
+    for (int ch = 0; ch < DH / 16; ++ch) {
+      const int col = half * DH + ch * 16;
+      const uint32_t atom = smem_base + L::off_dq + (col >> 5) * (128 * 128);
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        sts128f(atom + swz128(row, ((col & 31) + c) * 4), dq_acc[ch * 8 + c / 2].x, dq_acc[ch * 8 + c / 2].y, dq_acc[ch * 8 + c / 2 + 1].x,
+                dq_acc[ch * 8 + c / 2 + 1].y);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(2, NT);
+    if (leader) {
+#pragma unroll
+      for (int a = 0; a < D / 32; ++a)
+        tma_reduce_add_2d(&tm_dq, smem + L::off_dq + a * (128 * 128), a * 32, (int)head_row0 + t * 128);
+      tma_store_commit();
+    }
+  }
+  if (leader) tma_store_wait_all();
+  // ---- epilogue: dK_j, dV_j rows (row = key) in fp16
+  const size_t krow = head_row0 + (size_t)j * 128 + row;
+  __half* dk_dst = p.dk + krow * D + half * DH;
+  __half* dv_dst = p.dv + krow * D + half * DH;
+#pragma unroll
+  for (int d = 0; d < DH; d += 8) {
+    uint4 a, b;
+    __half2 t2;
+    t2 = __float22half2_rn(dk_acc[d / 2]); a.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2 + 1]); a.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2 + 2]); a.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dk_acc[d / 2 + 3]); a.w = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2]); b.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2 + 1]); b.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2 + 2]); b.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __float22half2_rn(dv_acc[d / 2 + 3]); b.w = *reinterpret_cast<uint32_t*>(&t2);
+    *reinterpret_cast<uint4*>(dk_dst + d) = a;
+    *reinterpret_cast<uint4*>(dv_dst + d) = b;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tbase);
+}
+
 // Causal row 0 of every head attends uniformly to all S keys (LEDGER B-1): dV[k] += dO[0] / S for every key k; dQ and
 // dK get nothing from it (its P is exactly 0 inside the fused kernel).  dO[0] is taken de-quantised (do_i8 * s_dO).
 template <int D>
@@ -864,6 +1172,31 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   return qa_check_launch("qa_int8_bwd");
 }
 
+template <int D, bool RN>
+static int launch_int8_bwd_blk(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
+                               const Int8BwdParams& p, int BH, int Bq, int Bkv, cudaStream_t st) {
+  using L = Int8BwdSmem<D>;
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  const int sw = (D == 128) ? 3 : 2;
+  uint64_t dims[2] = {(uint64_t)D, (uint64_t)BH * p.S};
+  uint64_t str[1] = {(uint64_t)D};
+  uint32_t box[2] = {(uint32_t)D, 128};
+  int rc;
+  if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+  if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+  if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+  if ((rc = qa_make_tmap(&tdo, do_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+  uint64_t strq[1] = {(uint64_t)D * 4};
+  uint32_t boxq[2] = {32, 128};
+  if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
+  auto kern = int8_bwd_blk_kernel<D, RN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  dim3 grid(p.S / 128, BH);
+  kern<<<grid, 256, L::total, st>>>(tq, tk, tv, tdo, tdq, p, Bq, Bkv);
+  return qa_check_launch("qa_int8_bwd");
+}
+
 }  // namespace qa
 
 using namespace qa;
@@ -889,7 +1222,10 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
   const bool ws = (flags & QA_FLAG_BWD_8WARP) == 0;     // warp-specialised kernel unless the caller asks for the 8-warp one
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: D must be 64 or 128");
-  if (Bq != 128 || Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: Bq = Bkv = 128 required");
+  const bool blk = (Bq != 128 || Bkv != 128);                    // quantisation blocks smaller than the MMA tile
+  if ((Bq != 32 && Bq != 64 && Bq != 128) || (Bkv != 32 && Bkv != 64 && Bkv != 128))
+    return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: Bq and Bkv must be 32, 64 or 128");
+  if (blk && causal) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: causal is built for Bq = Bkv = 128");
   if (BH <= 0 || S <= 0 || S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S must be a positive multiple of 128");
   if ((long long)BH * S >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: BH * S must be below 2^31 (TMA coordinates)");
   if (!q_i8 || !k_i8 || !v_i8 || !do_i8 || !sq || !sk || !sv || !s_do || !lse_f32 || !delta_f32 || !dq_ws_f32 || !dk_f16 || !dv_f16)
@@ -909,6 +1245,12 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
+  if (blk) {
+    if (rounding) return D == 128 ? launch_int8_bwd_blk<128, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st)
+                                  : launch_int8_bwd_blk<64, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st);
+    return D == 128 ? launch_int8_bwd_blk<128, false>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st)
+                    : launch_int8_bwd_blk<64, false>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st);
+  }
   if (ws) {
     int rc;
 #define QA_WS(DD, RNN, CC) launch_int8_bwd<DD, 2, RNN, CC, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
