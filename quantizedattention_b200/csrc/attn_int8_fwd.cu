@@ -114,8 +114,11 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // TMEM buffers: NSPLIT == 1: S[2] at 0/128, Opart[2] at 256/384.  NSPLIT == 2: S[3] at 0/128/256 (Q K^T runs two tiles
   // ahead, so the logit warps never wait for the tensor pipe behind a P V) and a single Opart at 384 (the drain of tile
   // j is shorter than a tile period, P V of tile j+1 waits for it).
-  constexpr int kSBuf = (NSPLIT == 2) ? 3 : 2, kOBuf = (NSPLIT == 2) ? 1 : 2;
-  constexpr uint32_t kOCol = kSBuf * 128;
+  // BN == 256 (Bkv = 256, the reference tunable's upper end): one 256-column S buffer, the logits are recomputed in pass 2
+  constexpr int kSBuf = (NSPLIT == 2) ? 3 : (BN > 128 ? 1 : 2), kOBuf = (NSPLIT == 2) ? 1 : 2;
+  constexpr int kSStride = BN > 128 ? BN : 128;                // TMEM columns between S buffers
+  constexpr uint32_t kOCol = kSBuf * kSStride;
+  constexpr bool kKeep = (NC <= 128);                          // keep the packed fp16 logits in registers between the passes
   static_assert(NSPLIT == 1 || BN == 128, "the two-stage softmax is laid out for 128-key tiles");
   static_assert(!MG || NSPLIT == 2, "magic accumulators are built into the two-stage kernel");
   constexpr uint32_t kLayoutQK = (D == 128) ? kSwz128 : kSwz64;   // rows of D bytes
@@ -260,7 +263,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float c = sq_f * sk_f * p.qk_scale;
       const float2 c2 = make_float2(c, c);
       if (warp == 0) QA_TL(0);
-      __half2 sh[NC / 2];
+      __half2 sh[kKeep ? NC / 2 : 1];
       __half rmax = __float2half_rn(0.f);
       float4 prm = make_float4(0.f, 0.f, 0.f, 0.f);
       if (NSPLIT == 2) {
@@ -285,13 +288,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int ch = 0; ch < NC / 32; ++ch) {
           uint32_t r[32];
-          tmem_ld32(lane_addr + sb * 128 + c0 + ch * 32, r);
+          tmem_ld32(lane_addr + sb * kSStride + c0 + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
             const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
             const __half2 h = __float22half2_rn(a);
-            sh[ch * 16 + i] = h;
+            if (kKeep) sh[ch * 16 + i] = h;
             mx2 = __hmax2(mx2, h);
           }
         }
@@ -325,12 +328,20 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < NC / 32; ++g) {
           uint32_t w[8];
+          uint32_t rr[32];
+          if (!kKeep) {                                            // wide tile: S is read again, the logits recomputed
+            tmem_ld32(lane_addr + sb * kSStride + c0 + g * 32, rr);
+            tmem_ld_wait();
+          }
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             uint32_t bytes[4];
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
-              const float2 f = __half22float2(__hsub2(sh[g * 16 + q4 * 2 + h2], m2));   // fp16 subtraction (:211-213)
+              const int e2 = q4 * 2 + h2;                          // pair of columns inside the 32-column group
+              const __half2 hl = kKeep ? sh[kKeep ? g * 16 + e2 : 0]
+                                       : __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)rr[2 * e2]), __int2float_rn((int)rr[2 * e2 + 1])), c2));
+              const float2 f = __half22float2(__hsub2(hl, m2));   // fp16 subtraction (:211-213)
               const float2 pp = make_float2(ex2_approx(f.x), ex2_approx(f.y));
               ls2 = __fadd2_rn(ls2, pp);
               // low byte of the biased sum = trunc(P/sp) (reference) or its nearest-even rounding (accuracy mode)
@@ -340,7 +351,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             w[q4] = pack_low_bytes(bytes[0], bytes[1], bytes[2], bytes[3]);
           }
-          tmem_st8(lane_addr + sb * 128 + kPOff + c0 / 4 + g * 8, w);
+          tmem_st8(lane_addr + sb * kSStride + kPOff + c0 / 4 + g * 8, w);
         }
       }
       tmem_st_wait();
@@ -609,7 +620,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < kBN / 32; ++k) {
           const uint64_t bd = umma_smem_desc(v_addr + k * 32 * D, 16, kSboQK, kLayoutQK);
-          umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * 128 + kPOff + k * 8, bd, idesc_pv, MG || k > 0);
+          umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * kSStride + kPOff + k * 8, bd, idesc_pv, MG || k > 0);
         }
         umma_commit(&o_full[ob]);
         umma_commit(&v_empty[s]);
@@ -619,12 +630,12 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&k_full[s], (j / STAGES) & 1);
         QA_TLX(j < 64, j, 9);
         const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
-        if (MG) umma_f16_ss(tbase + sb * 128, cdesc_a, cdesc_b, idesc_cqk, 0);             // S = kMagic
+        if (MG) umma_f16_ss(tbase + sb * kSStride, cdesc_a, cdesc_b, idesc_cqk, 0);             // S = kMagic
 #pragma unroll
         for (int k = 0; k < D / 32; ++k) {
           const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, kSboQK, kLayoutQK);
           const uint64_t bd = umma_smem_desc(k_addr + k * 32, 16, kSboQK, kLayoutQK);
-          umma_i8_ss(tbase + sb * 128, ad, bd, idesc_qk, MG || k > 0);
+          umma_i8_ss(tbase + sb * kSStride, ad, bd, idesc_qk, MG || k > 0);
         }
         umma_commit(&s_full[sb]);
         umma_commit(&k_empty[s]);
@@ -722,7 +733,7 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   const int rounding = (flags & QA_FLAG_NEAREST) ? 1 : 0;
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: D must be 64 or 128");
-  if (Bkv != 32 && Bkv != 64 && Bkv != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 32, 64 or 128");
+  if (Bkv != 32 && Bkv != 64 && Bkv != 128 && Bkv != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bkv must be 32, 64, 128 or 256");
   if (Bq != 32 && Bq != 64 && Bq != 128 && Bq != 256) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Bq must be 32/64/128/256");
   if (Sq % 128 || Sk % Bkv || Sq % Bq) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Sq must be a multiple of 128 (and of Bq), Sk of Bkv");
   if (((uintptr_t)q_i8 | (uintptr_t)k_i8 | (uintptr_t)v_i8 | (uintptr_t)O | (uintptr_t)o_acc) & 15)
@@ -771,6 +782,8 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
                        : launch_int8_fwd<64, 1, 4, 128>(q_i8, k_i8, v_i8, p, BH, st);
   }
   if (rounding == 1) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nearest rounding needs Bkv = 128");
+  if (Bkv == 256) return D == 128 ? launch_int8_fwd<128, 1, 2, 256>(q_i8, k_i8, v_i8, p, BH, st)
+                                  : launch_int8_fwd<64, 1, 2, 256>(q_i8, k_i8, v_i8, p, BH, st);
   if (Bkv == 64) return D == 128 ? launch_int8_fwd<128, 1, 4, 64>(q_i8, k_i8, v_i8, p, BH, st)
                                  : launch_int8_fwd<64, 1, 4, 64>(q_i8, k_i8, v_i8, p, BH, st);
   return D == 128 ? launch_int8_fwd<128, 1, 4, 32>(q_i8, k_i8, v_i8, p, BH, st)

@@ -47,7 +47,8 @@ def test_int8_fwd_matches_oracle(shape, Bq, nsplit):
 
 
 @pytest.mark.parametrize("shape,Bq,Bkv", [((1, 2, 256, 128), 32, 32), ((2, 2, 256, 64), 32, 32), ((1, 2, 512, 128), 64, 64),
-                                          ((1, 1, 256, 64), 128, 64), ((1, 2, 256, 128), 256, 32)])
+                                          ((1, 1, 256, 64), 128, 64), ((1, 2, 256, 128), 256, 32),
+                                          ((1, 2, 512, 128), 128, 256), ((2, 1, 512, 64), 64, 256), ((1, 2, 768, 128), 256, 256)])
 def test_int8_fwd_reference_default_block_sizes(shape, Bq, Bkv):
     """Bkv = 32 / 64: the reference's untuned default tunables (PowerOfTwoFragment(32, 256, 32), attention_int8.py:155-158)."""
     from oracle import int8_ref
