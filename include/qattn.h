@@ -76,6 +76,14 @@ int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, cons
                       void* l_out_fp32, const void* o_acc_in_fp32, const void* m_in_fp32, const void* l_in_fp32, int BH,
                       int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int flags, void* stream);
 
+/* Ragged sequences (the reference's hl.tile clamps the last tile, attention_int8.py:170,176): the buffers are zero-padded
+ * per head to Sk (a multiple of 128 and of Bkv), keys [Sk_valid, Sk) have weight exactly 0 and k-tiles without a valid key
+ * are skipped.  qa_int8_fwd_state == qa_int8_fwd_ragged with Sk_valid = Sk.  Non-causal only. */
+int qa_int8_fwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq_fp16, const void* sk_fp16,
+                       const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, void* o_acc_fp32, void* m_out_fp32,
+                       void* l_out_fp32, const void* o_acc_in_fp32, const void* m_in_fp32, const void* l_in_fp32, int BH,
+                       int Sq, int Sk, int Sk_valid, int D, int Bq, int Bkv, int nsplit, int flags, void* stream);
+
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;
  * 1: fp32 dO/O and, if dO_bf16 != NULL, a bf16 copy of dO in the same pass. */
@@ -85,13 +93,19 @@ int qa_bwd_delta(const void* dO, const void* O, void* delta_f32, void* dO_bf16, 
 int qa_cast_f32(const void* in_f32, void* out, long long n, int out_dtype, void* stream);
 
 /* ---- int8 backward: helion_atten_int8_hl_dot_bwd, attention_int8.py:268-432 under the 8-LEDGER contract ----
- * Bq = Bkv = 128.  dq_ws: zero-initialised fp32 [BH*S, D] accumulator; rowsum_ws: zero-initialised fp32 [BH*S]
+ * Bq, Bkv in {32, 64, 128} (causal: 128 / 128).  dq_ws: zero-initialised fp32 [BH*S, D] accumulator; rowsum_ws: zero-initialised fp32 [BH*S]
  * accumulator of rowsum(dS) for the K-smoothing term (NULL when K was not smoothed); dk, dv fp16.
  * qa_int8_bwd_finalize turns the two workspaces into dq = fp16(dq_ws + sm_scale * rowsum * k_mean[b,h]). */
 int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq_fp16,
                 const void* sk_fp16, const void* sv_fp16, const void* s_do_fp16, const void* lse_f32,
                 const void* delta_f32, void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
                 int D, int Bq, int Bkv, int flags, void* stream);
+/* Same for a ragged sequence padded to S: rows [S_valid, S) of every head are padding (dO rows zero); padded keys get
+ * P = 0, k-tiles and query tiles without a valid row are skipped (their dk / dv rows are not written). */
+int qa_int8_bwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq_fp16,
+                       const void* sk_fp16, const void* sv_fp16, const void* s_do_fp16, const void* lse_f32,
+                       const void* delta_f32, void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
+                       int S_valid, int D, int Bq, int Bkv, int flags, void* stream);
 int qa_int8_bwd_finalize(const void* dq_ws_f32, const void* rowsum_ws_f32, const void* k_mean_f16, void* dq_f16, int BH,
                          int S, int D, void* stream);
 

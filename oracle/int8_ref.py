@@ -80,7 +80,7 @@ def _imm(a_i8: torch.Tensor, b_i8: torch.Tensor) -> torch.Tensor:
 # forward -- attention_int8.py:170-257
 # --------------------------------------------------------------------------------------
 def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
-             return_lse32: bool = False, rounding: str = "trunc", causal: bool = False):
+             return_lse32: bool = False, rounding: str = "trunc", causal: bool = False, s_valid: int | None = None):
     """Returns the reference 10-tuple
         (O fp16 [B,H,S,D], lse fp16 [N], q_i8 [N,D], k_i8_T [D,N], v_i8 [N,D],
          sq [N/Bq], sk [N/Bkv], sv [N/Bkv], Bq, Bkv)
@@ -91,6 +91,9 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
     row sums run over the visible keys only; a (row, tile) pair without a visible key contributes nothing; row 0 of a
     head, which sees no key at all, is the uniform average over ALL keys of the de-quantised V with
     lse = -128 + log2(S) (LEDGER B-1, what the baseline's finite fill value produces).
+    s_valid (ragged sequences; the reference's hl.tile clamps the last tile, attention_int8.py:170,176): q, k, v are
+    zero-padded per head to a multiple of the block sizes, keys >= s_valid have weight exactly 0 and k-tiles without a
+    valid key are skipped; rows >= s_valid of the outputs are padding.
     """
     B, H, S, D = q.shape
     N = B * H * S
@@ -114,12 +117,15 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
     l = torch.full((G, L, 1), 1.0, dtype=torch.float32)                 # :173 (init 1.0)
     m = torch.full((G, L, 1), float("-inf"), dtype=torch.float16)       # :174
 
-    for j in range(L // Bkv):
+    for j in range(L // Bkv if s_valid is None else -(-s_valid // Bkv)):
         ks = slice(j * Bkv, (j + 1) * Bkv)
         acc = _imm(qg, kg[:, ks].transpose(1, 2))                        # :197
         skj = sk_g[:, j].view(G, 1, 1).float()
         S32 = acc.to(torch.float32) * sq_rows * skj * qk_scale           # :200
         S16 = S32.to(torch.float16)                                      # :203
+        if s_valid is not None:
+            pad = torch.arange(j * Bkv, (j + 1) * Bkv) >= s_valid
+            S16 = torch.where(pad[None, None, :], torch.tensor(float("-inf"), dtype=torch.float16), S16)
         if causal:
             assert per_head
             keep = torch.arange(L)[:, None] > torch.arange(j * Bkv, (j + 1) * Bkv)[None, :]     # strict: key < query
@@ -258,7 +264,7 @@ def quant_tile_fp32(x: torch.Tensor, rounding: str = "trunc"):
 
 
 def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv, rounding: str = "trunc",
-                      causal: bool = False):
+                      causal: bool = False, s_valid: int | None = None):
     """CONTRACT backward (what the CUDA kernel implements; LEDGER I-1,5,6,7,8,9,10,12,15).
 
     Per (b,h); k-tile j, q-tile i:
@@ -310,6 +316,8 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
             acc = _imm(qi, kj.transpose(1, 2))
             S16 = (acc.to(torch.float32) * sqg[:, i, None, None] * skg[:, j, None, None] * qk_scale).to(torch.float16)
             P = torch.exp2(S16.to(torch.float32) - lse32[:, i])
+            if s_valid is not None:                                # padded keys of a ragged sequence: P = 0
+                P = torch.where((torch.arange(j * Bkv, (j + 1) * Bkv) >= s_valid)[None, None, :], torch.zeros_like(P), P)
             if causal:
                 keep = torch.arange(i * Bq, (i + 1) * Bq)[:, None] > torch.arange(j * Bkv, (j + 1) * Bkv)[None, :]
                 P = torch.where(keep, P, torch.zeros_like(P))

@@ -25,6 +25,8 @@ SIGNATURES = {
     "qa_k_token_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_int8_fwd_state": (c_int, [c_void_p] * 15 + [c_int] * 8 + [c_void_p]),
     "qa_int8_fwd": (c_int, [c_void_p] * 12 + [c_int] * 8 + [c_void_p]),
+    "qa_int8_fwd_ragged": (c_int, [c_void_p] * 15 + [c_int] * 9 + [c_void_p]),
+    "qa_int8_bwd_ragged": (c_int, [c_void_p] * 14 + [c_int] * 7 + [c_void_p]),
     "qa_int8_bwd": (c_int, [c_void_p] * 14 + [c_int] * 6 + [c_void_p]),
     "qa_int8_bwd_finalize": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "qa_bwd_delta": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]),

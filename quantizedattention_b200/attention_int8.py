@@ -84,16 +84,68 @@ def _check_fp16(*ts):
             raise TypeError("int8 attention takes fp16 q, k, v")
 
 
+def _ceil_to(x: int, m: int) -> int:
+    return -(-x // m) * m
+
+
+def _pad_tokens(t, Sp: int):
+    """[B,H,S,D] -> zero-padded [B,H,Sp,D] (a copy only when S != Sp)."""
+    B, H, S, D = t.shape
+    if S == Sp:
+        return t
+    out = t.new_zeros((B, H, Sp, D))
+    out[:, :, :S] = t
+    return out
+
+
+def _pad_rows(t, BH: int, S: int, Sp: int):
+    """Per-head rows: [BH*S, ...] -> zero-padded [BH*Sp, ...]."""
+    if S == Sp:
+        return t
+    rest = t.shape[1:]
+    out = t.new_zeros((BH, Sp) + rest)
+    out[:, :S] = t.reshape((BH, S) + rest)
+    return out.reshape((BH * Sp,) + rest)
+
+
+def _cut_rows(t, BH: int, S: int, Sp: int):
+    """Inverse of _pad_rows: keep the first S of every head's Sp rows."""
+    if S == Sp:
+        return t
+    rest = t.shape[1:]
+    return t.reshape((BH, Sp) + rest)[:, :S].reshape((BH * S,) + rest)
+
+
 def _fwd_tensors(q_fp16, k_fp16, v_fp16, k_mean, Bq, Bkv, rounding, causal):
-    """Quantise (K optionally smoothed) and run the fused forward.  Returns everything either wrapper needs."""
+    """Quantise (K optionally smoothed) and run the fused forward.  Returns everything either wrapper needs.
+    Ragged sequence lengths (S not a multiple of 128 / of the block sizes; the reference's hl.tile clamps the last tile,
+    attention_int8.py:170,176): the tensors are zero-padded per head, the kernel gives the padded keys weight exactly 0
+    (qa_int8_fwd_ragged) and the padding is cut off again: the returned tensors have the caller's S."""
     batch, head, q_tokens, D = q_fp16.shape
     k_tokens = k_fp16.shape[2]
-    q_i8, sq = ops.quant_block(q_fp16, Bq, rounding=rounding)
-    k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean, rows_per_head=k_tokens if k_mean is not None else None, rounding=rounding)
-    v_i8, sv = ops.quant_block(v_fp16, Bkv, rounding=rounding)
-    O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, batch * head, q_tokens, k_tokens, D, Bq, Bkv,
-                                            nsplit=_CFG["nsplit"], want_lse32=True, rounding=rounding, causal=causal)
-    return O.view(batch, head, q_tokens, D), lse16, lse32, q_i8, k_i8, v_i8, sq, sk, sv
+    BH = batch * head
+    Sp, Skp = _ceil_to(q_tokens, max(128, Bq)), _ceil_to(k_tokens, max(128, Bkv))
+    ragged = (Sp != q_tokens) or (Skp != k_tokens)
+    if not ragged:
+        q_i8, sq = ops.quant_block(q_fp16, Bq, rounding=rounding)
+        k_i8, sk = ops.quant_block(k_fp16, Bkv, mean=k_mean, rows_per_head=k_tokens if k_mean is not None else None, rounding=rounding)
+        v_i8, sv = ops.quant_block(v_fp16, Bkv, rounding=rounding)
+        O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, q_tokens, k_tokens, D, Bq, Bkv,
+                                                nsplit=_CFG["nsplit"], want_lse32=True, rounding=rounding, causal=causal)
+        return O.view(batch, head, q_tokens, D), lse16, lse32, q_i8, k_i8, v_i8, sq, sk, sv
+    if causal:
+        raise ValueError("causal int8 attention needs S to be a multiple of 128")
+    k_s = k_fp16 if k_mean is None else k_fp16 - k_mean            # fp16, one rounding (attention_int8.py:25); padding stays 0
+    q_i8, sq = ops.quant_block(_pad_tokens(q_fp16, Sp), Bq, rounding=rounding)
+    k_i8, sk = ops.quant_block(_pad_tokens(k_s, Skp), Bkv, rounding=rounding)
+    v_i8, sv = ops.quant_block(_pad_tokens(v_fp16, Skp), Bkv, rounding=rounding)
+    O, lse16, lse32 = ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sp, Skp, D, Bq, Bkv, nsplit=_CFG["nsplit"],
+                                            want_lse32=True, rounding=rounding, sk_valid=k_tokens)
+    nbq, nbk = -(-q_tokens // Bq), -(-k_tokens // Bkv)             # blocks per head the reference's clamped tiles produce
+    cut = lambda t, S_, Sp_: _cut_rows(t, BH, S_, Sp_).contiguous()
+    return (cut(O, q_tokens, Sp).view(batch, head, q_tokens, D), cut(lse16, q_tokens, Sp), cut(lse32, q_tokens, Sp),
+            cut(q_i8, q_tokens, Sp), cut(k_i8, k_tokens, Skp), cut(v_i8, k_tokens, Skp),
+            cut(sq, nbq, Sp // Bq), cut(sk, nbk, Skp // Bkv), cut(sv, nbk, Skp // Bkv))
 
 
 def helion_atten_int8_hl_dot_fwd(q_fp16_input, k_fp16_input, v_fp16_input, _want_lse32: bool = False, causal: bool = False,
@@ -135,6 +187,7 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
     Returns (dq, dk, dv) fp16 [B,H,S,D]."""
     batch, head, q_tokens, head_dim = O_input_fp16.shape
     N = batch * head * q_tokens
+    BH, S = batch * head, q_tokens
     assert q_bh_int8.shape == (N, head_dim) and k_bh_int8_T.shape == (head_dim, N), "q/k int8 shapes"
     _, _, rounding = _resolve(Bq, Bkv, rounding)
     k_i8 = k_bh_int8_T.t()
@@ -143,18 +196,29 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
     dO = dO_input_fp16.contiguous()
     if dO.dtype != torch.float16:
         dO = dO.to(torch.float16)
-    delta = ops.bwd_delta(dO, O_input_fp16)
-    do_i8, s_do = ops.quant_block(dO, Bq, rounding=rounding)
+    O = O_input_fp16.contiguous()
     lse32 = lse_input_fp16.to(torch.float32).contiguous()
+    q_i8, v_i8, sq, sk, sv = q_bh_int8.contiguous(), v_bh_int8.contiguous(), sq_bh_fp16, sk_bh_fp16, sv_bh_fp16
+    Sp = _ceil_to(S, max(128, Bq, Bkv))
+    if Sp != S:                                                    # ragged: back to the zero-padded layout the kernels take
+        if causal:
+            raise ValueError("causal int8 attention needs S to be a multiple of 128")
+        pad = lambda t, S_, Sp_: _pad_rows(t, BH, S_, Sp_)
+        dO, O = pad(dO.view(N, head_dim), S, Sp), pad(O.view(N, head_dim), S, Sp)
+        q_i8, k_i8, v_i8, lse32 = pad(q_i8, S, Sp), pad(k_i8, S, Sp), pad(v_i8, S, Sp), pad(lse32, S, Sp)
+        sq, sk, sv = pad(sq, -(-S // Bq), Sp // Bq), pad(sk, -(-S // Bkv), Sp // Bkv), pad(sv, -(-S // Bkv), Sp // Bkv)
+    delta = ops.bwd_delta(dO, O)
+    do_i8, s_do = ops.quant_block(dO, Bq, rounding=rounding)
     km = None
     if k_mean_bh_fp16 is not None:
         assert k_mean_bh_fp16.numel() == batch * head * head_dim, "k_mean must be the per-head token mean [B,H,1,D]"
         km = k_mean_bh_fp16.to(torch.float16).contiguous()
-    dq, dk, dv = ops.int8_bwd_prequant(q_bh_int8.contiguous(), k_i8, v_bh_int8.contiguous(), do_i8, sq_bh_fp16,
-                                       sk_bh_fp16, sv_bh_fp16, s_do, lse32, delta, km, batch * head, q_tokens, head_dim,
-                                       Bq, Bkv, rounding=rounding, causal=causal, kernel=kernel)
+    dq, dk, dv = ops.int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, km, BH, Sp, head_dim,
+                                       Bq, Bkv, rounding=rounding, causal=causal, kernel=kernel,
+                                       s_valid=S if Sp != S else None)
     shp = (batch, head, q_tokens, head_dim)
-    return dq.view(shp), dk.view(shp), dv.view(shp)
+    cut = lambda t: _cut_rows(t, BH, S, Sp).contiguous().view(shp)
+    return cut(dq), cut(dk), cut(dv)
 
 
 class _SageInt8Fn(Function):

@@ -39,6 +39,7 @@ struct Int8BwdParams {
   float* rowsum;                       // [BH*S] fp32, zero-initialised: sum over k-tiles of rowsum(dS) (null without K smoothing)
   __half *dk, *dv;                     // [BH*S, D] fp16
   int S;
+  int S_valid;                         // rows [S_valid, S) of every head are padding (ragged sequence): padded keys get P = 0
   float sm_scale, qk_scale;
   long long* dbg;                      // optional timeline buffer [tile][2 warps][16] of SM clock stamps (tools/timeline_bwd.py)
 };
@@ -80,7 +81,8 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool leader = (tid == 0);
   const int bh = blockIdx.y, j = blockIdx.x;
-  const int nq = p.S / 128;
+  const int nq = (p.S_valid + 127) / 128;                       // fully padded query tiles are skipped
+  const int ktail = p.S_valid - j * 128;                        // valid keys of this k-tile (>= 128 unless it is the ragged last one)
   // CAUSAL (strict mask, key < query): k-tile j meets the query tiles j .. nq-1; `t` below is the position in
   // that sequence (pipeline stages and barrier parities), t0 + t the query tile
   const int t0 = CAUSAL ? j : 0;
@@ -224,7 +226,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const size_t qrow = head_row0 + (size_t)tq * 128 + row;
     const float sq_f = __half2float(p.sq[head_row0 / 128 + tq]);
     const float sdo_f = __half2float(p.s_do[head_row0 / 128 + tq]);
-    const float lse = p.lse[qrow];
+    const float lse = (tq * 128 + row < p.S_valid) ? p.lse[qrow] : INFINITY;     // padded query rows of a ragged sequence: P = 0
     const float dlt = p.delta[qrow];
     const float c_s = magic_scale(sq_f * sk_f * p.qk_scale);
     const float c_dp = sdo_f * sv_f;
@@ -247,7 +249,7 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float nlse = 10.0f - lse, cdpk = magic_scale(c_dp * kPs);
     const float2 cs2 = make_float2(c_s, c_s), nbs2 = make_float2(-kMagic * c_s, -kMagic * c_s);
     const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(-dlt * kPs - kMagic * cdpk, -dlt * kPs - kMagic * cdpk);
-    auto pass1 = [&](auto masked) {                                // masked: the diagonal tile of a causal head
+    auto pass1 = [&](auto masked, auto tail) {                     // masked: the diagonal tile of a causal head; tail: ragged last k-tile
 #pragma unroll
     for (int ch = 0; ch < CW / 16; ++ch) {
       uint32_t r[16], r2[16];
@@ -265,6 +267,11 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (col >= row) pp.x = 0.f;
           if (col + 1 >= row) pp.y = 0.f;
         }
+        if (decltype(tail)::value) {                                   // padding keys of a ragged sequence
+          const int col = half * CW + ch * 16 + c;
+          if (col >= ktail) pp.x = 0.f;
+          if (col + 1 >= ktail) pp.y = 0.f;
+        }
         const __half2 pr = __float22half2_rn(pp);
         pk[ch * 8 + c / 2] = pr;
         amax_ph = __hmax2(amax_ph, pr);
@@ -274,7 +281,9 @@ int8_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     };
-    if (CAUSAL && t == 0) pass1(std::true_type{}); else pass1(std::false_type{});
+    if (CAUSAL && t == 0) pass1(std::true_type{}, std::false_type{});
+    else if (!CAUSAL && ktail < 128) pass1(std::false_type{}, std::true_type{});
+    else pass1(std::false_type{}, std::false_type{});
     amax_p = fmaxf(__low2float(amax_ph), __high2float(amax_ph));                       // of the rounded 1024 * P
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -457,7 +466,8 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   // 256: Q/dO loads, dQ, dV/dK;  288: S and dP of the next tile;  320: the TMA reduce-add of the dQ staging tile
   const bool leader = (tid == 256), leader_sdp = (tid == 288), leader_red = (tid == 320);
   const int bh = blockIdx.y, j = blockIdx.x;
-  const int nq = p.S / 128;
+  const int nq = (p.S_valid + 127) / 128;                       // fully padded query tiles are skipped
+  const int ktail = p.S_valid - j * 128;                        // valid keys of this k-tile (>= 128 unless it is the ragged last one)
   const int t0 = CAUSAL ? j : 0;                                // causal: k-tile j meets the query tiles j .. nq-1
   const int nt = nq - t0;
   const size_t head_row0 = (size_t)bh * p.S;
@@ -494,7 +504,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const size_t qrow = head_row0 + (size_t)tq * 128 + row;
       const float sq_f = __half2float(p.sq[head_row0 / 128 + tq]);
       const float sdo_f = __half2float(p.s_do[head_row0 / 128 + tq]);
-      const float lse = p.lse[qrow];
+      const float lse = (tq * 128 + row < p.S_valid) ? p.lse[qrow] : INFINITY;   // padded query rows of a ragged sequence: P = 0
       const float dlt = p.delta[qrow];
       const float c_s = magic_scale(sq_f * sk_f * p.qk_scale);
       const float c_dp = sdo_f * sv_f;
@@ -511,7 +521,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const float nlse = 10.0f - lse, cdpk = magic_scale(c_dp * kPs);
       const float2 cs2 = make_float2(c_s, c_s), nbs2 = make_float2(-kMagic * c_s, -kMagic * c_s);
       const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(-dlt * kPs - kMagic * cdpk, -dlt * kPs - kMagic * cdpk);
-      auto pass1 = [&](auto masked) {                                // masked: the diagonal tile of a causal head
+      auto pass1 = [&](auto masked, auto tail) {                     // masked: the diagonal tile of a causal head; tail: ragged last k-tile
   #pragma unroll
       for (int ch = 0; ch < CW / 16; ++ch) {
         uint32_t r[16], r2[16];
@@ -529,6 +539,11 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             if (col >= row) pp.x = 0.f;
             if (col + 1 >= row) pp.y = 0.f;
           }
+          if (decltype(tail)::value) {                                   // padding keys of a ragged sequence
+            const int col = half * CW + ch * 16 + c;
+            if (col >= ktail) pp.x = 0.f;
+            if (col + 1 >= ktail) pp.y = 0.f;
+          }
           const __half2 pr = __float22half2_rn(pp);
           pk[ch * 8 + c / 2] = pr;
           amax_ph = __hmax2(amax_ph, pr);
@@ -538,7 +553,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         }
       }
       };
-      if (CAUSAL && t == 0) pass1(std::true_type{}); else pass1(std::false_type{});
+      if (CAUSAL && t == 0) pass1(std::true_type{}, std::false_type{});
+    else if (!CAUSAL && ktail < 128) pass1(std::false_type{}, std::true_type{});
+    else pass1(std::false_type{}, std::false_type{});
       amax_p = fmaxf(__low2float(amax_ph), __high2float(amax_ph));                       // of the rounded 1024 * P
   #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -840,7 +857,8 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool leader = (tid == 0);
   const int bh = blockIdx.y, j = blockIdx.x;
-  const int nq = p.S / 128;
+  const int nq = (p.S_valid + 127) / 128;                       // fully padded query tiles are skipped
+  const int ktail = p.S_valid - j * 128;                        // valid keys of this k-tile (>= 128 unless it is the ragged last one)
   const int NRB = 128 / BQ, NCB = 128 / BK;
   const size_t head_row0 = (size_t)bh * p.S;
 
@@ -897,11 +915,12 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   for (int t = 0; t < nq; ++t) {
     const uint32_t ab = t & 1;                                   // amax buffer of this tile
+    const int tq = t;
     const size_t qrow = head_row0 + (size_t)t * 128 + row;
     const size_t qblk0 = (head_row0 + (size_t)t * 128) / BQ;
     const float sq_f = __half2float(p.sq[qblk0 + rb]);
     const float sdo_f = __half2float(p.s_do[qblk0 + rb]);
-    const float lse = p.lse[qrow];
+    const float lse = (tq * 128 + row < p.S_valid) ? p.lse[qrow] : INFINITY;     // padded query rows of a ragged sequence: P = 0
     const float dlt = p.delta[qrow];
     if (leader) {
       mbar_expect_tx(&qdo_full, 2 * L::kTile);
@@ -941,7 +960,12 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int c = 0; c < 16; c += 2) {
         const __half2 h = __float22half2_rn(__ffma2_rn(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), cs2, nbs2));
         const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
-        const float2 pp = make_float2(ex2_approx(fhadd_lo(hu, nlse)), ex2_approx(fhadd_hi(hu, nlse)));     // 1024 * P
+        float2 pp = make_float2(ex2_approx(fhadd_lo(hu, nlse)), ex2_approx(fhadd_hi(hu, nlse)));     // 1024 * P
+        if (ktail < 128) {                                           // padding keys of a ragged sequence
+          const int col = half * CW + ch * 16 + c;
+          if (col >= ktail) pp.x = 0.f;
+          if (col + 1 >= ktail) pp.y = 0.f;
+        }
         const __half2 pr = __float22half2_rn(pp);
         pk[ch * 8 + c / 2] = pr;
         mp = fmaxf(mp, fmaxf(__low2float(pr), __high2float(pr)));
@@ -1157,7 +1181,7 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   uint64_t strq[1] = {(uint64_t)D * 4};
   uint32_t boxq[2] = {32, 128};
   if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
-  dim3 grid(p.S / 128, BH);
+  dim3 grid((p.S_valid + 127) / 128, BH);                        // k-tiles without a valid key are not launched
   if (WS) {                                                        // warp-specialised: 8 quantise + 8 drain warps
     auto kern = int8_bwd_ws_kernel<D, RN, CAUSAL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
@@ -1192,7 +1216,7 @@ static int launch_int8_bwd_blk(const void* q_i8, const void* k_i8, const void* v
   auto kern = int8_bwd_blk_kernel<D, RN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  dim3 grid(p.S / 128, BH);
+  dim3 grid((p.S_valid + 127) / 128, BH);                        // k-tiles without a valid key are not launched
   kern<<<grid, 256, L::total, st>>>(tq, tk, tv, tdo, tdq, p, Bq, Bkv);
   return qa_check_launch("qa_int8_bwd");
 }
@@ -1213,10 +1237,13 @@ extern "C" int qa_debug_set_int8_bwd_timeline(void* buf) {
 }
 #endif
 
-extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
-                           const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
-                           void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
-                           int Bq, int Bkv, int flags, void* stream) {
+extern "C" int qa_int8_bwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
+                                  const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
+                                  void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int S_valid,
+                                  int D, int Bq, int Bkv, int flags, void* stream) {
+  if (S_valid <= 0 || S_valid > S || S - S_valid >= 128)
+    return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: S_valid must be in (S - 128, S] (pad to the next multiple of 128 only)");
+  if (S_valid != S && (flags & QA_FLAG_CAUSAL)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: ragged sequences are built for the non-causal kernels");
   if (flags & ~(QA_FLAG_NEAREST | QA_FLAG_CAUSAL | QA_FLAG_BWD_8WARP)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd: unknown flag bits");
   const int rounding = (flags & QA_FLAG_NEAREST) ? 1 : 0;
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
@@ -1236,7 +1263,7 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv; p.s_do = (const __half*)s_do;
   p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32; p.rowsum = (float*)rowsum_ws_f32;
   p.dk = (__half*)dk_f16; p.dv = (__half*)dv_f16;
-  p.S = S;
+  p.S = S; p.S_valid = S_valid;
 #ifdef QA_DEV_TIMELINE
   p.dbg = (long long*)g_int8_bwd_dbg;
 #else
@@ -1280,4 +1307,12 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
                     : launch_int8_bwd<64, 2, true>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
   return D == 128 ? launch_int8_bwd<128, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st)
                   : launch_int8_bwd<64, 2>(q_i8, k_i8, v_i8, do_i8, dq_ws_f32, p, BH, st);
+}
+
+extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, const void* sq,
+                           const void* sk, const void* sv, const void* s_do, const void* lse_f32, const void* delta_f32,
+                           void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D,
+                           int Bq, int Bkv, int flags, void* stream) {
+  return qa_int8_bwd_ragged(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse_f32, delta_f32, rowsum_ws_f32, dq_ws_f32, dk_f16,
+                            dv_f16, BH, S, S, D, Bq, Bkv, flags, stream);
 }

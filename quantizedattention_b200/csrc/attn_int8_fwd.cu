@@ -61,6 +61,7 @@ struct Int8FwdParams {
   const float* l_in;
   const float* O_acc_in;
   int Sq, Sk, Bq;
+  int Sk_valid;          // keys [Sk_valid, Sk) of every head are padding (ragged sequence, hl.tile clamps the last tile: attention_int8.py:170,176): weight exactly 0
   float qk_scale;
   long long* dbg;        // optional timeline buffer [tile][16] of SM clock stamps written by CTA (0,0) (tools/timeline.py)
 };
@@ -148,7 +149,8 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                        : pwarp;
   // CAUSAL (strict mask, key < query): a query tile visits the k-tiles up to its own; heaviest tiles first
   const int bh = blockIdx.y, q0 = (CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * kBM;
-  const int nk = CAUSAL ? min(p.Sk / kBN, q0 / kBN + 1) : p.Sk / kBN;
+  const int nk = CAUSAL ? min(p.Sk / kBN, q0 / kBN + 1) : (p.Sk_valid + kBN - 1) / kBN;   // tiles beyond the last valid key are skipped
+  const int ktail = p.Sk_valid - (nk - 1) * kBN;               // valid keys of the last tile (== kBN unless the sequence is ragged)
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -293,7 +295,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
             const float2 a = __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
-            const __half2 h = __float22half2_rn(a);
+            __half2 h = __float22half2_rn(a);
+            if (j == nk - 1 && ktail < kBN) {                      // padding keys of a ragged sequence
+              const int col = c0 + ch * 32 + 2 * i;
+              const __half ninf = __float2half_rn(-INFINITY);
+              if (col >= ktail) h = __halves2half2(ninf, __high2half(h));
+              if (col + 1 >= ktail) h = __halves2half2(__low2half(h), ninf);
+            }
             if (kKeep) sh[ch * 16 + i] = h;
             mx2 = __hmax2(mx2, h);
           }
@@ -339,8 +347,14 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const int e2 = q4 * 2 + h2;                          // pair of columns inside the 32-column group
-              const __half2 hl = kKeep ? sh[kKeep ? g * 16 + e2 : 0]
-                                       : __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)rr[2 * e2]), __int2float_rn((int)rr[2 * e2 + 1])), c2));
+              __half2 hl = kKeep ? sh[kKeep ? g * 16 + e2 : 0]
+                                 : __float22half2_rn(__fmul2_rn(make_float2(__int2float_rn((int)rr[2 * e2]), __int2float_rn((int)rr[2 * e2 + 1])), c2));
+              if (!kKeep && j == nk - 1 && ktail < kBN) {
+                const int col = c0 + g * 32 + 2 * e2;
+                const __half ninf = __float2half_rn(-INFINITY);
+                if (col >= ktail) hl = __halves2half2(ninf, __high2half(hl));
+                if (col + 1 >= ktail) hl = __halves2half2(__low2half(hl), ninf);
+              }
               const float2 f = __half22float2(__hsub2(hl, m2));   // fp16 subtraction (:211-213)
               const float2 pp = make_float2(ex2_approx(f.x), ex2_approx(f.y));
               ls2 = __fadd2_rn(ls2, pp);
@@ -388,7 +402,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       if (qd == 0) QA_TL(13);
       __half2 mx2 = __float2half2_rn(-INFINITY);
-      auto pass1 = [&](auto masked) {                              // masked: the diagonal tile of a causal head
+      auto pass1 = [&](auto masked, auto tail) {                   // masked: the diagonal tile of a causal head; tail: ragged last tile
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {                          // 32 columns in, 16 columns (32 packed pairs) out
           const uint32_t src = lane_addr + sb * 128 + ch * 32;
@@ -408,13 +422,21 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               if (col >= row) h = __halves2half2(ninf, __high2half(h));
               if (col + 1 >= row) h = __halves2half2(__low2half(h), ninf);
             }
+            if (decltype(tail)::value) {                           // padding keys of a ragged sequence
+              const int col = ch * 32 + 2 * i;
+              const __half ninf = __float2half_rn(-INFINITY);
+              if (col >= ktail) h = __halves2half2(ninf, __high2half(h));
+              if (col + 1 >= ktail) h = __halves2half2(__low2half(h), ninf);
+            }
             mx2 = __hmax2(mx2, h);
             w[i] = *reinterpret_cast<uint32_t*>(&h);
           }
           tmem_st16(dst, w);
         }
       };
-      if (CAUSAL && j * kBN == q0) pass1(std::true_type{}); else pass1(std::false_type{});
+      if (CAUSAL && j * kBN == q0) pass1(std::true_type{}, std::false_type{});
+      else if (!CAUSAL && j == nk - 1 && ktail < kBN) pass1(std::false_type{}, std::true_type{});
+      else pass1(std::false_type{}, std::false_type{});
       const __half rmax = __hmax(__low2half(mx2), __high2half(mx2));
       const __half m_new = __hmax(m16, rmax);
       float rescale = ex2_approx(__half2float(__hsub(m16, m_new)));             // fp16 subtraction (:217-219)
@@ -725,10 +747,13 @@ extern "C" int qa_debug_set_int8_fwd_timeline(void* buf) {
 // Forward over pre-quantised operands.  q_i8 [BH*Sq, D], k_i8 / v_i8 [BH*Sk, D] int8 row-major; sq [BH*Sq/Bq],
 // sk / sv [BH*Sk/Bkv] fp16.  Outputs: O fp16 [BH*Sq, D], lse16 fp16 [BH*Sq], lse32 fp32 [BH*Sq] (optional).
 // Ring mode (o_acc != NULL): writes unnormalised fp32 O plus (m, l) per row instead of O / lse.
-extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
-                                 const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
-                                 const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int D,
-                                 int Bq, int Bkv, int nsplit, int flags, void* stream) {
+extern "C" int qa_int8_fwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
+                                  const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
+                                  const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int Sk_valid,
+                                  int D, int Bq, int Bkv, int nsplit, int flags, void* stream) {
+  if (Sk_valid <= 0 || Sk_valid > Sk) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: Sk_valid must be in (0, Sk]");
+  if (Sk - Sk_valid >= (Bkv > 128 ? Bkv : 128)) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: pad the sequence to the NEXT multiple of max(128, Bkv) only");
+  if (Sk_valid != Sk && (flags & QA_FLAG_CAUSAL)) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: ragged sequences are built for the non-causal kernels");
   if (flags & ~(QA_FLAG_NEAREST | QA_FLAG_CAUSAL)) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: unknown flag bits");
   const int rounding = (flags & QA_FLAG_NEAREST) ? 1 : 0;
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
@@ -743,7 +768,7 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
   p.O = (__half*)O; p.lse16 = (__half*)lse16; p.lse32 = (float*)lse32;
   p.O_acc_out = (float*)o_acc; p.m_out = (float*)m_out; p.l_out = (float*)l_out;
   p.O_acc_in = (const float*)o_acc_in; p.m_in = (const float*)m_in; p.l_in = (const float*)l_in;
-  p.Sq = Sq; p.Sk = Sk; p.Bq = Bq;
+  p.Sq = Sq; p.Sk = Sk; p.Bq = Bq; p.Sk_valid = Sk_valid;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
 #ifdef QA_DEV_TIMELINE
   p.dbg = (long long*)g_int8_fwd_dbg;
@@ -790,9 +815,17 @@ extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void*
                   : launch_int8_fwd<64, 1, 4, 32>(q_i8, k_i8, v_i8, p, BH, st);
 }
 
+extern "C" int qa_int8_fwd_state(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
+                                 const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
+                                 const void* o_acc_in, const void* m_in, const void* l_in, int BH, int Sq, int Sk, int D,
+                                 int Bq, int Bkv, int nsplit, int flags, void* stream) {
+  return qa_int8_fwd_ragged(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, o_acc_in, m_in, l_in, BH, Sq, Sk,
+                            Sk, D, Bq, Bkv, nsplit, flags, stream);
+}
+
 extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const void* sq, const void* sk,
                            const void* sv, void* O, void* lse16, void* lse32, void* o_acc, void* m_out, void* l_out,
                            int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int flags, void* stream) {
-  return qa_int8_fwd_state(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, nullptr, nullptr, nullptr, BH,
-                           Sq, Sk, D, Bq, Bkv, nsplit, flags, stream);
+  return qa_int8_fwd_ragged(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, nullptr, nullptr, nullptr, BH,
+                            Sq, Sk, Sk, D, Bq, Bkv, nsplit, flags, stream);
 }

@@ -91,3 +91,27 @@ class JvpAttention(nn.Module):
 
     def forward(self, q, k, v):
         return jvp_attention(q, k, v, self.layout)
+
+
+def sage_attention_int8_varlen(q, k, v, cu_seqlens, **tunables):
+    """Variable-length (packed) int8 attention, the flash-attn calling convention: q, k, v fp16 `[total_tokens, H, D]`,
+    `cu_seqlens` int `[n_seq + 1]` (host tensor / list: cumulative sequence starts), every sequence attends to itself
+    (non-causal, like the reference's int8 kernel).  Returns O fp16 `[total_tokens, H, D]`; differentiable.
+
+    Sequences of equal length share one launch; a sequence length need not be a multiple of 128 (ragged last tile,
+    attention_int8.py:170,176): `sage_attention_3_int8` pads per head and the kernels give the padding weight 0."""
+    cu = [int(x) for x in (cu_seqlens.tolist() if hasattr(cu_seqlens, "tolist") else cu_seqlens)]
+    if len(cu) < 2 or cu[0] != 0 or cu[-1] != q.shape[0] or any(b <= a for a, b in zip(cu, cu[1:])):
+        raise ValueError("cu_seqlens must start at 0, increase strictly and end at total_tokens")
+    if q.dim() != 3 or k.shape != q.shape or v.shape != q.shape:
+        raise ValueError("q, k, v must share one [total_tokens, H, D] shape")
+    by_len = {}
+    for b in range(len(cu) - 1):
+        by_len.setdefault(cu[b + 1] - cu[b], []).append(cu[b])
+    out = torch.empty_like(q)
+    for length, starts in by_len.items():
+        idx = torch.cat([torch.arange(s0, s0 + length, device=q.device) for s0 in starts])
+        take = lambda t: t.index_select(0, idx).view(len(starts), length, *t.shape[1:]).transpose(1, 2).contiguous()   # [n,H,L,D]
+        o = attention_int8.sage_attention_3_int8(take(q), take(k), take(v), **tunables)
+        out = out.index_copy(0, idx, o.transpose(1, 2).reshape(len(starts) * length, *q.shape[1:]))
+    return out

@@ -119,12 +119,13 @@ def k_token_sum(k: torch.Tensor) -> torch.Tensor:
 
 
 def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=128, nsplit=0, want_lse32=True,
-                      ring_state=False, state_in=None, rounding: str = "trunc", causal: bool = False):
+                      ring_state=False, state_in=None, rounding: str = "trunc", causal: bool = False, sk_valid: int | None = None):
     """Fused int8 attention forward over pre-quantised operands (qa_int8_fwd).
     nsplit: 0 = the default kernel for the tile (Bkv = 128: two-stage softmax with magic accumulators); 1 = single-stage
     softmax (one thread per row); 2 = two-stage softmax without magic accumulators (kept for A/B comparison).
     Returns (O fp16 [BH*Sq, D], lse16 [BH*Sq], lse32 or None); with ring_state=True returns the unnormalised
-    (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead."""
+    (O_acc fp32 [BH*Sq, D], m fp32 [BH*Sq], l fp32 [BH*Sq]) of this K/V shard instead.
+    sk_valid: ragged sequence zero-padded per head to Sk: keys >= sk_valid have weight 0 (qa_int8_fwd_ragged)."""
     _need_cuda(q_i8, k_i8, v_i8, sq, sk, sv)
     dev = q_i8.device
     L = _lib.lib()
@@ -140,10 +141,11 @@ def int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq=128, Bkv=1
         o_acc = m = l = None
     si = state_in if state_in is not None else (None, None, None)       # (o_acc, m, l) of the earlier K/V shards
     with torch.cuda.device(dev), _timed("int8_fwd"):
-        _lib.check(L.qa_int8_fwd_state(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk),
-                                       _lib.ptr(sv), _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc),
-                                       _lib.ptr(m), _lib.ptr(l), _lib.ptr(si[0]), _lib.ptr(si[1]), _lib.ptr(si[2]),
-                                       BH, Sq, Sk, D, Bq, Bkv, nsplit, _flags(rounding, causal), _lib.cur_stream()), "qa_int8_fwd")
+        _lib.check(L.qa_int8_fwd_ragged(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(sq), _lib.ptr(sk),
+                                        _lib.ptr(sv), _lib.ptr(O), _lib.ptr(lse16), _lib.ptr(lse32), _lib.ptr(o_acc),
+                                        _lib.ptr(m), _lib.ptr(l), _lib.ptr(si[0]), _lib.ptr(si[1]), _lib.ptr(si[2]),
+                                        BH, Sq, Sk, Sk if sk_valid is None else int(sk_valid), D, Bq, Bkv, nsplit,
+                                        _flags(rounding, causal), _lib.cur_stream()), "qa_int8_fwd")
     if ring_state:
         return o_acc, m, l
     return O, lse16, lse32
@@ -180,7 +182,7 @@ def cast_f32(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128,
-                      rounding: str = "trunc", causal: bool = False, kernel: str = "ws"):
+                      rounding: str = "trunc", causal: bool = False, kernel: str = "ws", s_valid: int | None = None):
     """Fused int8 backward over pre-quantised operands (qa_int8_bwd).  Returns (dq, dk, dv) fp16 [BH*S, D].
     kernel: "ws" = the warp-specialised kernel (default), "8warp" = the 8-warp kernel (QA_FLAG_BWD_8WARP)."""
     if kernel not in ("ws", "8warp"):
@@ -190,18 +192,19 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
     dev = q_i8.device
     dq_ws = torch.zeros((BH * S, D), dtype=torch.float32, device=dev)
     rowsum_ws = torch.zeros((BH * S,), dtype=torch.float32, device=dev) if k_mean is not None else None
-    dk = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
-    dv = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    alloc = torch.empty if s_valid is None else torch.zeros     # ragged: k-tiles without a valid key are not written
+    dk = alloc((BH * S, D), dtype=torch.float16, device=dev)
+    dv = alloc((BH * S, D), dtype=torch.float16, device=dev)
     dq = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
     if k_mean is not None:
         k_mean = k_mean.contiguous()
     L = _lib.lib()
     with torch.cuda.device(dev):
         with _timed("int8_bwd"):
-            _lib.check(L.qa_int8_bwd(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
-                                     _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(rowsum_ws),
-                                     _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D, Bq, Bkv, flags, _lib.cur_stream()),
-                       "qa_int8_bwd")
+            _lib.check(L.qa_int8_bwd_ragged(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_i8), _lib.ptr(do_i8), _lib.ptr(sq), _lib.ptr(sk),
+                                            _lib.ptr(sv), _lib.ptr(s_do), _lib.ptr(lse32), _lib.ptr(delta), _lib.ptr(rowsum_ws),
+                                            _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, S if s_valid is None else int(s_valid),
+                                            D, Bq, Bkv, flags, _lib.cur_stream()), "qa_int8_bwd")
         _lib.check(L.qa_int8_bwd_finalize(_lib.ptr(dq_ws), _lib.ptr(rowsum_ws), _lib.ptr(k_mean), _lib.ptr(dq), BH, S, D,
                                           _lib.cur_stream()), "qa_int8_bwd_finalize")
     return dq, dk, dv
