@@ -51,6 +51,7 @@ int qa_k_token_sum(const void* k_fp16, void* sum_f32, void* workspace, size_t ws
 /* Per-block int8 quantisation, attention_int8.py:178-186 (Q), :188-195 (K), :241-247 (V), :369-374 (dO):
  * scale = fp16(amax|block| / 127); value = trunc(fp16(x / scale)); block = blk rows x D.  Bit-exact with the reference
  * arithmetic.  mean_fp16 != NULL subtracts the per-head mean first (fp16, one rounding): K-smoothing fused in.
+ * rounding: 2 = fp8: e4m3 codes with scale = fp16(amax / 448) (qa_fp8_fwd).
  * rounding: 0 = truncate toward zero, the reference's `.to(torch.int8)` (attention_int8.py:183); 1 = round half to even,
  * the opt-in accuracy mode (removes the truncation bias; not bit-comparable with the reference by construction).
  * qa_int8_fwd / qa_int8_bwd take it as bit 0 of their `flags` (QA_FLAG_NEAREST); bit 1 (QA_FLAG_CAUSAL) selects the
@@ -83,6 +84,12 @@ int qa_int8_fwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, con
                        const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, void* o_acc_fp32, void* m_out_fp32,
                        void* l_out_fp32, const void* o_acc_in_fp32, const void* m_in_fp32, const void* l_in_fp32, int BH,
                        int Sq, int Sk, int Sk_valid, int D, int Bq, int Bkv, int nsplit, int flags, void* stream);
+
+/* ---- fp8 (e4m3) forward, SURVEY.md 8f.4 (the reference names it, README.md:48-54, but ships no code): the int8
+ * pipeline with e4m3 operands (qa_quant_block rounding = 2: scale = amax / 448), tcgen05 kind::f8f6f4, fp32 TMEM
+ * accumulators; Bq = Bkv = 128.  O fp16 [BH*Sq, D], lse fp16 / fp32 [BH*Sq] (lse32 optional). */
+int qa_fp8_fwd(const void* q_e4m3, const void* k_e4m3, const void* v_e4m3, const void* sq_fp16, const void* sk_fp16,
+               const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, int BH, int Sq, int Sk, int D, void* stream);
 
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;

@@ -98,7 +98,11 @@ struct Int8FwdRoles {
   static constexpr int kTmaWarp = kDrain0 + kNumDrain, kMmaWarp = kTmaWarp + 1;
 };
 
-template <int D, int NSPLIT, int STAGES, int BN, bool RN, bool CAUSAL, bool MG, int NDR>
+// FP8 (only with the MG kernel structure): Q, K, V and P are e4m3 (scale = amax / 448 instead of / 127,
+// round to nearest), the contractions are tcgen05 kind::f8f6f4 with fp32 accumulation, so the accumulators are floats
+// already: no initialising MMA, no magic constant; everything else (fp16 logits, fp16 running maximum, per-row P scale per
+// k-tile, per-tile V scale, fp32 O in registers) is the int8 pipeline.
+template <int D, int NSPLIT, int STAGES, int BN, bool RN, bool CAUSAL, bool MG, int NDR, bool FP8>
 __global__ void __launch_bounds__((Int8FwdRoles<NSPLIT, NDR>::kThreads), 1)
 int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, Int8FwdParams p) {
@@ -122,6 +126,9 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr bool kKeep = (NC <= 128);                          // keep the packed fp16 logits in registers between the passes
   static_assert(NSPLIT == 1 || BN == 128, "the two-stage softmax is laid out for 128-key tiles");
   static_assert(!MG || NSPLIT == 2, "magic accumulators are built into the two-stage kernel");
+  static_assert(!FP8 || (MG && NDR == 1 && !CAUSAL), "the fp8 forward reuses the structure of the magic two-stage kernel");
+  constexpr bool kInit = MG && !FP8;                           // accumulators initialised to kMagic by a kind::f16 MMA
+  constexpr float kQMax = FP8 ? 448.0f : 127.0f;               // largest quantised magnitude of P
   constexpr uint32_t kLayoutQK = (D == 128) ? kSwz128 : kSwz64;   // rows of D bytes
   constexpr uint32_t kSboQK = (D == 128) ? 1024 : 512;
 
@@ -167,7 +174,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == R::kMmaWarp) tmem_alloc<512>(&tmem_base_s);
-  if (MG) {                                                      // constant operand tiles: every fp16 element = 1024 (A) / 768 (B)
+  if (kInit) {                                                   // constant operand tiles: every fp16 element = 1024 (A) / 768 (B)
     const uint32_t c_addr = smem_u32(smem + L::off_c);
     if (tid < 64) sts128(c_addr + tid * 16, kMagicElemA2, kMagicElemA2, kMagicElemA2, kMagicElemA2);
     else if (tid < 128) sts128(c_addr + tid * 16, kMagicElemB2, kMagicElemB2, kMagicElemB2, kMagicElemB2);
@@ -237,9 +244,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               const float2 y1 = make_float2(ex2_approx(fhadd_lo(h1, kk)), ex2_approx(fhadd_hi(h1, kk)));
               ys2 = __fadd2_rn(ys2, y0);
               ys2 = __fadd2_rn(ys2, y1);
-              const float2 q0 = RN ? __fmul2_rn(y0, tiny2) : __fmul2_rz(y0, tiny2);
-              const float2 q1 = RN ? __fmul2_rn(y1, tiny2) : __fmul2_rz(y1, tiny2);
-              w[q4] = pack_sat_s8x4(__float_as_int(q0.x), __float_as_int(q0.y), __float_as_int(q1.x), __float_as_int(q1.y));
+              if (FP8) {                                             // y in [0, 448] -> e4m3, round to nearest, saturating
+                w[q4] = cvt_e4m3x2(y0.x, y0.y) | (cvt_e4m3x2(y1.x, y1.y) << 16);
+              } else {
+                const float2 q0 = RN ? __fmul2_rn(y0, tiny2) : __fmul2_rz(y0, tiny2);
+                const float2 q1 = RN ? __fmul2_rn(y1, tiny2) : __fmul2_rz(y1, tiny2);
+                w[q4] = pack_sat_s8x4(__float_as_int(q0.x), __float_as_int(q0.y), __float_as_int(q1.x), __float_as_int(q1.y));
+              }
             }
             tmem_st8(lane_addr + sb * 128 + kPOff + hf * 16 + g * 8, w);
           }
@@ -413,8 +424,9 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {                          // packed fp32x2 multiply (FMUL2): half the issue slots
-            const float2 a = MG ? __ffma2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nb2)   // (kMagic + x) * c - kMagic * c
-                                : __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
+            const float2 a = FP8 ? __fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2)        // fp32 accumulator
+                             : MG ? __ffma2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nb2)   // (kMagic + x) * c - kMagic * c
+                                  : __fmul2_rn(make_float2(__int2float_rn((int)r[2 * i]), __int2float_rn((int)r[2 * i + 1])), c2);
             __half2 h = __float22half2_rn(a);
             if (decltype(masked)::value) {                         // strict causal: keep key < query (same tile: col < row)
               const int col = ch * 32 + 2 * i;
@@ -449,9 +461,10 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       m16 = m_new;
       if (MG) {                                       // (rescale, exponent offset of y = P / sp, sp, sp * sv)
         const float dsp = __half2float(__hsub(rmax, m_new));
-        const float kk = (CAUSAL && __hisinf(rmax)) ? 0.f : (6.988684686772166f + 2.0e-6f) - dsp;   // log2(127) + eps: the row maximum quantises to 127
+        // log2(127) + eps (fp8: log2(448)): the row maximum quantises to the largest code
+        const float kk = (CAUSAL && __hisinf(rmax)) ? 0.f : (FP8 ? 8.807354922057604f : 6.988684686772166f + 2.0e-6f) - dsp;
         prm_m[j & 3][row] = (CAUSAL && __hisinf(m_new)) ? __float2half_rn(0.f) : m_new;
-        prm_s[j & 3][row] = make_float4(rescale, kk, sp_e * (1.0f / 127.0f), sp_e * (1.0f / 127.0f) * __half2float(sv_p[j]));
+        prm_s[j & 3][row] = make_float4(rescale, kk, sp_e * (1.0f / kQMax), sp_e * (1.0f / kQMax) * __half2float(sv_p[j]));
       } else
       prm_s[j & 3][row] = make_float4(rescale, inv_sp, (CAUSAL && __hisinf(m_new)) ? 0.f : __half2float(m_new),
                                       sp_e * (1.0f / 127.0f) * __half2float(sv_p[j]));
@@ -537,6 +550,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             acc2[grp * 32 + i].y = fmaf(__uint_as_float(r[2 * i + 1]), c_eff, acc2[grp * 32 + i].y);
           }
         }
+        if (!FP8) {
         // ... and the kMagic * c part, identical for every column of the row, is summed on the side and taken out every
         // fourth tile (so that it never outgrows the accumulated values by more than ~2^10: the subtraction then costs
         // < 2^-13 of relative precision, below the fp16 rounding of O)
@@ -546,6 +560,7 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < DCx / 2; ++i) acc2[i] = __fadd2_rn(acc2[i], nb2);
           bias = 0.f;
+        }
         }
       } else
 #pragma unroll
@@ -622,8 +637,9 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // =========================== MMA issuer ===========================
     if (NSPLIT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc(2, 1, 1, 0, 0, kBM, kBN);          // s32 += s8 x s8, both K-major
-      constexpr uint32_t idesc_pv = umma_idesc(2, 1, 1, 0, 1, kBM, D);            // B = V: MN-major
+      // int8: s32 += s8 x s8; fp8: f32 += e4m3 x e4m3 (format 0).  Q, K K-major; B = V MN-major
+      constexpr uint32_t idesc_qk = FP8 ? umma_idesc(1, 0, 0, 0, 0, kBM, kBN) : umma_idesc(2, 1, 1, 0, 0, kBM, kBN);
+      constexpr uint32_t idesc_pv = FP8 ? umma_idesc(1, 0, 0, 0, 1, kBM, D) : umma_idesc(2, 1, 1, 0, 1, kBM, D);
       const uint32_t q_addr = smem_u32(smem + L::off_q);
       // accumulator initialisation (MG): D = A B^T over K = 16 fp16 elements of the constant tiles = kMagic everywhere
       constexpr uint32_t idesc_cqk = umma_idesc(1, 0, 0, 0, 0, kBM, kBN), idesc_cpv = umma_idesc(1, 0, 0, 0, 0, kBM, D);
@@ -638,11 +654,12 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         QA_TLX(t < 64, t, 11);   // PV issue
         const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kVBytes);
-        if (MG) umma_f16_ss(tbase + kOCol + ob * 128, cdesc_a, cdesc_b, idesc_cpv, 0);     // Opart = kMagic
+        if (kInit) umma_f16_ss(tbase + kOCol + ob * 128, cdesc_a, cdesc_b, idesc_cpv, 0);  // Opart = kMagic
 #pragma unroll
         for (int k = 0; k < kBN / 32; ++k) {
           const uint64_t bd = umma_smem_desc(v_addr + k * 32 * D, 16, kSboQK, kLayoutQK);
-          umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * kSStride + kPOff + k * 8, bd, idesc_pv, MG || k > 0);
+          if (FP8) umma_f8_ts(tbase + kOCol + ob * 128, tbase + sb * kSStride + kPOff + k * 8, bd, idesc_pv, k > 0);
+          else umma_i8_ts(tbase + kOCol + ob * 128, tbase + sb * kSStride + kPOff + k * 8, bd, idesc_pv, kInit || k > 0);
         }
         umma_commit(&o_full[ob]);
         umma_commit(&v_empty[s]);
@@ -652,12 +669,13 @@ int8_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&k_full[s], (j / STAGES) & 1);
         QA_TLX(j < 64, j, 9);
         const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kKBytes);
-        if (MG) umma_f16_ss(tbase + sb * kSStride, cdesc_a, cdesc_b, idesc_cqk, 0);             // S = kMagic
+        if (kInit) umma_f16_ss(tbase + sb * kSStride, cdesc_a, cdesc_b, idesc_cqk, 0);          // S = kMagic
 #pragma unroll
         for (int k = 0; k < D / 32; ++k) {
           const uint64_t ad = umma_smem_desc(q_addr + k * 32, 16, kSboQK, kLayoutQK);
           const uint64_t bd = umma_smem_desc(k_addr + k * 32, 16, kSboQK, kLayoutQK);
-          umma_i8_ss(tbase + sb * kSStride, ad, bd, idesc_qk, MG || k > 0);
+          if (FP8) umma_f8_ss(tbase + sb * kSStride, ad, bd, idesc_qk, k > 0);
+          else umma_i8_ss(tbase + sb * kSStride, ad, bd, idesc_qk, kInit || k > 0);
         }
         umma_commit(&s_full[sb]);
         umma_commit(&k_empty[s]);
@@ -708,7 +726,7 @@ __global__ void __launch_bounds__(512) int8_row0_fixup_kernel(const int8_t* __re
   }
 }
 
-template <int D, int NSPLIT, int STAGES, int BN, bool RN = false, bool CAUSAL = false, bool MG = false, int NDR = 1>
+template <int D, int NSPLIT, int STAGES, int BN, bool RN = false, bool CAUSAL = false, bool MG = false, int NDR = 1, bool FP8 = false>
 static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8, const Int8FwdParams& p, int BH,
                            cudaStream_t st) {
   using L = Int8FwdSmem<D, NSPLIT, STAGES, BN>;
@@ -722,7 +740,7 @@ static int launch_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
   if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
   if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, str, boxk, sw))) return rc;
-  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN, CAUSAL, MG, NDR>;
+  auto kern = int8_fwd_kernel<D, NSPLIT, STAGES, BN, RN, CAUSAL, MG, NDR, FP8>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / kBM, BH);
@@ -828,4 +846,24 @@ extern "C" int qa_int8_fwd(const void* q_i8, const void* k_i8, const void* v_i8,
                            int BH, int Sq, int Sk, int D, int Bq, int Bkv, int nsplit, int flags, void* stream) {
   return qa_int8_fwd_ragged(q_i8, k_i8, v_i8, sq, sk, sv, O, lse16, lse32, o_acc, m_out, l_out, nullptr, nullptr, nullptr, BH,
                             Sq, Sk, Sk, D, Bq, Bkv, nsplit, flags, stream);
+}
+
+// fp8 (e4m3) forward over pre-quantised operands: q / k / v bytes are e4m3 produced by qa_quant_block with
+// rounding = 2 (scale = amax / 448), Bq = Bkv = 128.  Same outputs as qa_int8_fwd (normal mode).  Forward only.
+extern "C" int qa_fp8_fwd(const void* q_e4m3, const void* k_e4m3, const void* v_e4m3, const void* sq, const void* sk,
+                          const void* sv, void* O, void* lse16, void* lse32, int BH, int Sq, int Sk, int D, void* stream) {
+  if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp8_fwd: D must be 64 or 128");
+  if (BH <= 0 || Sq <= 0 || Sk <= 0 || Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp8_fwd: Sq, Sk must be positive multiples of 128");
+  if (!q_e4m3 || !k_e4m3 || !v_e4m3 || !sq || !sk || !sv || !O || !lse16) return qa_fail(QA_ERR_SHAPE, "qa_fp8_fwd: null pointer");
+  if (((uintptr_t)q_e4m3 | (uintptr_t)k_e4m3 | (uintptr_t)v_e4m3 | (uintptr_t)O) & 15) return qa_fail(QA_ERR_ALIGN, "qa_fp8_fwd: 16-byte alignment required");
+  Int8FwdParams p;
+  p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sv;
+  p.O = (__half*)O; p.lse16 = (__half*)lse16; p.lse32 = (float*)lse32;
+  p.O_acc_out = nullptr; p.m_out = nullptr; p.l_out = nullptr; p.O_acc_in = nullptr; p.m_in = nullptr; p.l_in = nullptr;
+  p.Sq = Sq; p.Sk = Sk; p.Bq = 128; p.Sk_valid = Sk;
+  p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  p.dbg = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  return D == 128 ? launch_int8_fwd<128, 2, 3, 128, true, false, true, 1, true>(q_e4m3, k_e4m3, v_e4m3, p, BH, st)
+                  : launch_int8_fwd<64, 2, 4, 128, true, false, true, 1, true>(q_e4m3, k_e4m3, v_e4m3, p, BH, st);
 }

@@ -157,6 +157,22 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// kind::f8f6f4 (a_fmt / b_fmt in the instruction descriptor: 0 = e4m3, 1 = e5m2), fp32 accumulation; 8-bit operands use
+// the same shared-memory / TMEM operand layouts as kind::i8 (one byte per element, K = 32 per instruction)
+__device__ __forceinline__ void umma_f8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -287,6 +303,12 @@ __device__ __forceinline__ uint32_t pack_sat_s8x4(int w0, int w1, int w2, int w3
   asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(w3), "r"(w2), "r"(0));
   asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(o) : "r"(w1), "r"(w0), "r"(t));
   return o;
+}
+// two fp32 -> two e4m3 (round to nearest even, saturating), lo in the low byte
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(r) : "f"(lo), "f"(hi));
+  return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

@@ -75,6 +75,19 @@ __device__ __forceinline__ int quant_one(float x, float s, float y, bool nearest
   return nearest ? __float2int_rn(qh) : (int)qh;
 }
 
+// fp8 (e4m3) variant of the same rule (the reference's "SageAttention3" headline it does not ship,
+// README.md:48-54): scale = fp16(amax / 448), value = e4m3(RN(fp16(x / scale))), saturating.  Two values per PTX cvt.
+__device__ __forceinline__ uint32_t quant_e4m3x2(float x0, float x1, float s, float y) {
+  float q0 = x0 * y, q1 = x1 * y;
+  q0 = __fmaf_rn(__fmaf_rn(-s, q0, x0), y, q0);
+  q1 = __fmaf_rn(__fmaf_rn(-s, q1, x1), y, q1);
+  q0 = __half2float(__float2half_rn(q0));
+  q1 = __half2float(__float2half_rn(q1));
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(r) : "f"(q0), "f"(q1));   // first source operand -> upper byte
+  return r;
+}
+
 template <int ITERS>
 __global__ void __launch_bounds__(256) quant_block_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
                                                           int8_t* __restrict__ out, __half* __restrict__ scales,
@@ -115,7 +128,7 @@ __global__ void __launch_bounds__(256) quant_block_kernel(const __half* __restri
 #pragma unroll
   for (int w = 1; w < 8; ++w) am = fmaxf(am, wmax[w]);
 
-  const __half s_h = __float2half_rn(__fdiv_rn(am, 127.f));     // fp16 amax / 127, RN
+  const __half s_h = __float2half_rn(__fdiv_rn(am, rounding == 2 ? 448.f : 127.f));     // fp16 amax / 127 (e4m3: / 448), RN
   const float s = __half2float(s_h);
   if (threadIdx.x == 0) scales[b] = s_h;
   const bool zero = (s == 0.f);                                 // LEDGER I-4: all-zero block -> 0
@@ -124,6 +137,19 @@ __global__ void __launch_bounds__(256) quant_block_kernel(const __half* __restri
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+    if (rounding == 2) {                                        // e4m3
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h[j]);
+        w[j] = zero ? 0u : quant_e4m3x2(f.x, f.y, s, y);
+      }
+      uint2 o;
+      o.x = w[0] | (w[1] << 16);
+      o.y = w[2] | (w[3] << 16);
+      __stcs(dst + threadIdx.x + i * 256, o);
+      continue;
+    }
     int q[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -181,7 +207,7 @@ extern "C" size_t qa_k_mean_workspace_bytes(int B, int H, int S, int D) {
 // rounding: 0 = toward zero (the reference), 1 = nearest even (accuracy mode).
 extern "C" int qa_quant_block(const void* x_fp16, const void* mean_fp16, void* out_i8, void* scales_fp16, long long n_rows,
                               int D, int blk, int rows_per_head, int rounding, void* stream) {
-  if (rounding != 0 && rounding != 1) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: rounding must be 0 (toward zero) or 1 (nearest)");
+  if (rounding < 0 || rounding > 2) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: rounding must be 0 (toward zero), 1 (nearest) or 2 (fp8 e4m3)");
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: D must be 64 or 128");
   if (blk != 32 && blk != 64 && blk != 128 && blk != 256) return qa_fail(QA_ERR_SHAPE, "qa_quant_block: blk must be 32/64/128/256");
   if (n_rows % blk != 0 || (mean_fp16 && rows_per_head % blk != 0))

@@ -75,6 +75,7 @@ def k_mean(k: torch.Tensor) -> torch.Tensor:
 
 
 ROUNDING = {"trunc": 0, "nearest": 1}       # int8 rounding of the quantisers: the reference truncates (LEDGER I-3)
+QUANT_MODES = {"trunc": 0, "nearest": 1, "e4m3": 2}   # qa_quant_block `rounding`: 2 = fp8 e4m3 codes (scale = amax / 448)
 FLAG_NEAREST, FLAG_CAUSAL, FLAG_BWD_8WARP = 1, 2, 4      # `flags` of qa_int8_fwd / qa_int8_bwd (include/qattn.h)
 
 
@@ -99,7 +100,7 @@ def quant_block(x: torch.Tensor, blk: int, mean: torch.Tensor | None = None, row
     L = _lib.lib()
     with torch.cuda.device(x.device):
         _lib.check(L.qa_quant_block(_lib.ptr(x2), _lib.ptr(mean), _lib.ptr(out), _lib.ptr(scales), N, D, blk,
-                                    rows_per_head or N, ROUNDING[rounding], _lib.cur_stream()), "qa_quant_block")
+                                    rows_per_head or N, QUANT_MODES[rounding], _lib.cur_stream()), "qa_quant_block")
     return out, scales
 
 

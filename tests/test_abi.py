@@ -53,7 +53,8 @@ def test_argument_validation_needs_no_gpu():
     assert L.qa_quant_block(z, z, z, z, 128, 96, 32, 128, 0, z) == -1         # D not in {64,128}
     assert b"D must be" in L.qa_last_error()
     assert L.qa_quant_block(z, z, z, z, 100, 64, 32, 128, 0, z) == -1         # rows not a multiple of blk
-    assert L.qa_quant_block(z, z, z, z, 128, 64, 32, 128, 2, z) == -1         # rounding in {0, 1}
+    assert L.qa_quant_block(z, z, z, z, 128, 64, 32, 128, 3, z) == -1         # rounding in {0, 1, 2}
+    assert L.qa_fp8_fwd(*([z] * 9), 1, 100, 128, 128, z) == -1                # fp8 forward: S % 128
     assert L.qa_int8_fwd(*([z] * 12), 1, 128, 128, 128, 128, 16, 1, 0, z) == -1  # Bkv in {32,64,128,256}
     assert L.qa_int8_bwd(*([z] * 14), 1, 128, 128, 32, 128, 0, z) == -1       # Bq = Bkv = 128
     assert L.qa_bf16_fwd(*([z] * 5), 1, 100, 128, 128, 0, 1, z) == -1         # S % 128
