@@ -55,8 +55,14 @@ struct Int8BwdParams {
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 5) && t < 64) \
       p.dbg[(t * 2 + (warp != 0)) * 16 + (slot)] = clock64();                                                 \
   } while (0)
+#define QA_TLW(role, slot)                                                                                    \
+  do {                                                                                                        \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && t < 64)                        \
+      p.dbg[(t * 2 + (role)) * 16 + (slot)] = clock64();                                                      \
+  } while (0)
 #else
 #define QA_TLB(slot) do { } while (0)
+#define QA_TLW(role, slot) do { } while (0)
 #endif
 
 template <int D, int NG, bool RN, bool CAUSAL>
@@ -508,8 +514,10 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       const float dlt = p.delta[qrow];
       const float c_s = magic_scale(sq_f * sk_f * p.qk_scale);
       const float c_dp = sdo_f * sv_f;
+      if (warp == 0) QA_TLW(0, 0);
       mbar_wait(&sd_full, ph);
       tc_fence_after();
+      if (warp == 0) QA_TLW(0, 1);
       // ---- pass 1: P = exp2(fp16 logit - lse), kept as packed fp16 of 1024 * P (11-bit mantissa, no subnormals down to
       //      P = 6e-8) so that pass 2 needs no second exp2; tile amax of P and |dS|, row sum of dS
       __half2 pk[CW / 2];
@@ -565,7 +573,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (lane == 0) { red_p[ph][rw] = amax_p; red_ds[ph][rw] = amax_ds; }
       rowsum_ds[ph][half][row] = rs2acc.x + rs2acc.y;
 
+      if (warp == 0) QA_TLW(0, 2);
       named_bar_sync(3, NT);                                       // amax partials of the 8 quantise warps visible
+      if (warp == 0) QA_TLW(0, 3);
       if (tid == 0) { tc_fence_before(); mbar_arrive(&s_free); }   // every quantise warp is past pass 1: the S columns are free
       // ---- tile-wide amax of P and |dS| (per-[Bq,Bkv]-tile quantisation, attention_int8.py:363-365, 403-405)
       amax_p = red_p[ph][0]; amax_ds = red_ds[ph][0];
@@ -588,6 +598,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       // the P tile and this dS buffer were last read by dV/dK of tile t-1 (dS[ph] also by dQ of t-2, which completed
       // before sd_full(t) was signalled)
       if (t > 0) mbar_wait(&parts_full, (t - 1) & 1);
+      if (warp == 0) QA_TLW(0, 4);
       // ---- pass 2: recompute P / dS from the packed logits, quantise (truncate toward zero), store both tiles as
       //      [q row][128 key bytes], 128B-swizzled (A operands of dV / dK (transposed) and dQ); dS is double-buffered
       const uint32_t ds_tile = smem_base + L::off_ds + ph * (128 * 128);
@@ -630,6 +641,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full);
+      if (warp == 0) QA_TLW(0, 5);
     }
   } else {
     // =========================== drain role: accumulators, dQ staging, TMA / MMA issue ===========================
@@ -741,6 +753,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     for (int t = 0; t < nt; ++t) {
       const uint32_t ph = t & 1;
       const int tq = t0 + t;
+      if (warp == 8) QA_TLW(1, 6);
       if (leader && t + 1 < nt) {                                  // next Q / dO tile: its stage was last read by dV/dK of t-1
         if (t > 0) mbar_wait(&parts_full, (t - 1) & 1);
         load_qdo(tq + 1, (t + 1) & 1);
@@ -749,13 +762,16 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (t > 0) {                                                 // dV / dK partials of tile t-1
         mbar_wait(&parts_full, (t - 1) & 1);
         tc_fence_after();
+        if (warp == 8) QA_TLW(1, 7);
         const float c_dv_prev = sc_ring[(t - 1) & 1][0], c_dk_prev = sc_ring[(t - 1) & 1][1];
         c_dq_prev = sc_ring[(t - 1) & 1][2];
         drain_dv_dk(c_dv_prev, c_dk_prev);
+        if (warp == 8) QA_TLW(1, 8);
       }
       tc_fence_before();
       if (leader_red) tma_store_wait_read();                       // the dQ staging tile may be rewritten after this barrier
       named_bar_sync(1, NT);                                      // dV/dK partial columns drained by the whole role
+      if (warp == 8) QA_TLW(1, 9);
       if (leader && t > 0) { tc_fence_after(); issue_dq((t - 1) & 1); }
       if (leader_sdp && t + 1 < nt) {                              // S of the next tile as soon as pass 1 of this one is over
         mbar_wait(&s_free, ph);
@@ -763,14 +779,18 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
         issue_s((t + 1) & 1);
       }
+      if (warp == 8) QA_TLW(1, 10);
       if (t > 0) {                                                 // dQ partial of tile t-1 -> staging tile
         mbar_wait(&dq_full, (t - 1) & 1);
         tc_fence_after();
+        if (warp == 8) QA_TLW(1, 11);
         drain_dq(c_dq_prev);
+        if (warp == 8) QA_TLW(1, 12);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(2, NT);                                      // staging tile complete, dQ partial columns drained
+      if (warp == 8) QA_TLW(1, 13);
       if (leader_red && t > 0) reduce_dq(tq - 1);
       if (leader_sdp && t + 1 < nt) {                              // dP of the next tile once pass 2 has released its columns
         mbar_wait(&pds_full, ph);
@@ -780,7 +800,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (leader) {
         mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored
         tc_fence_after();
+        QA_TLW(1, 14);
         issue_dv_dk(t & 1, ph);
+        QA_TLW(1, 15);
       }
     }
     // ---- pipeline tail: last tile's dV / dK / dQ

@@ -5,9 +5,12 @@ Per-q-tile timeline of one CTA of the int8 backward (SM clock stamps of the lead
 slots: 0 loop top | 1 S/dP ready | 2 pass 1 done | 3 dV/dK partial ready | 4 dV/dK drained | 5 barrier 1 passed |
        6 dQ issued (leader) | 7 pass 2 done | 8 dQ partial ready | 9 dQ drained | 10 barrier 2 passed |
        11 S/dP(t+1) issued (leader) | 12 dV/dK issued (leader) = end of iteration"""
+import os
 import sys
 
-import torch
+os.environ["QA_DEV_LIB"] = "1"      # every call goes through libqattn_dev.so (kernels with timeline hooks)
+
+import torch  # noqa: E402
 
 sys.path.insert(0, ".")
 from quantizedattention_b200 import _lib, ops  # noqa: E402
@@ -28,7 +31,6 @@ ops.int8_bwd_prequant(*args)
 torch.cuda.synchronize()
 L.qa_debug_set_int8_bwd_timeline(None)
 t = buf.view(64, 2, 16).cpu()
-import os
 if os.environ.get("QA_INT8_BWD_WS", "1") != "0":        # warp-specialised kernel: quantise warp 1 (slots 0-5), leader warp 8 (6-15)
     qn = ["top", "S_rdy", "pass1", "amax_bar", "P_free", "pass2"]
     dn = ["top", "dVK_rdy", "dVK_drn", "bar1", "dQ+S_iss", "dQ_rdy", "dQ_drn", "bar2", "pds_ok", "iss_end"]
