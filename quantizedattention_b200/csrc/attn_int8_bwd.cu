@@ -642,6 +642,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full);
       if (warp == 0) QA_TLW(0, 5);
+      QA_TLW(0, 6 + warp);                                         // pass-2 end of every quantise warp (skew between them)
     }
   } else {
     // =========================== drain role: accumulators, dQ staging, TMA / MMA issue ===========================
@@ -798,7 +799,9 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         issue_dp((t + 1) & 1);                                     // its commit (sd_full) also covers the S MMAs above
       }
       if (leader) {
+        QA_TLW(1, 0);
         mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored
+        QA_TLW(1, 1);
         tc_fence_after();
         QA_TLW(1, 14);
         issue_dv_dk(t & 1, ph);

@@ -8,6 +8,9 @@
 
 namespace qa {
 
+#ifndef QA_MBAR_HINT_NS
+#define QA_MBAR_HINT_NS 0x989680u   // suspend-time hint of mbarrier.try_wait (ns)
+#endif
 #ifndef QA_SPIN_LIMIT
 #define QA_SPIN_LIMIT (1u << 14)   // bounded mbarrier waits (each up to ~10 ms): a protocol bug traps instead of hanging
 #endif
@@ -48,7 +51,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(QA_MBAR_HINT_NS)
       : "memory");
   return ok != 0;
 }

@@ -39,11 +39,19 @@ if os.environ.get("QA_INT8_BWD_WS", "1") != "0":        # warp-specialised kerne
     for j in range(20, 28):
         t0 = int(t[j, 0, 0])
         print(f"{j:4d} " + " ".join(f"{int(t[j, 0, s]) - t0:8d}" for s in range(6)) + f" {int(t[j + 1, 0, 0]) - t0:8d}")
+    print("pass-2 end of quantise warps 0..7 (relative to warp 0 loop top)")
+    for j in range(20, 28):
+        t0 = int(t[j, 0, 0])
+        print(f"{j:4d} " + " ".join(f"{int(t[j, 0, 6 + w]) - t0:8d}" for w in range(8)))
     print("leader warp 8 (drain role) - relative to the quantise warp's loop top of the same tile")
     print("tile " + " ".join(f"{n:>8s}" for n in dn) + "     iter")
     for j in range(20, 28):
         t0 = int(t[j, 0, 0])
         print(f"{j:4d} " + " ".join(f"{int(t[j, 1, s]) - t0:8d}" for s in range(6, 16)) + f" {int(t[j + 1, 1, 6]) - int(t[j, 1, 6]):8d}")
+    print("leader: before pds_full wait / after wait / after fence / issue end (relative to the quantise loop top)")
+    for j in range(20, 28):
+        t0 = int(t[j, 0, 0])
+        print(f"{j:4d} " + " ".join(f"{int(t[j, 1, s]) - t0:8d}" for s in (0, 1, 14, 15)))
     print("cycles per tile:", (int(t[52, 0, 0]) - int(t[20, 0, 0])) / 32)
     sys.exit(0)
 names = ["top", "S_rdy", "pass1", "dVK_rdy", "dVK_drn", "bar1", "dQ_iss", "pass2", "dQ_rdy", "dQ_drn", "bar2", "SdP_iss", "dVK_iss"]
