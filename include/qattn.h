@@ -113,6 +113,13 @@ int qa_int8_bwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, con
                        const void* sk_fp16, const void* sv_fp16, const void* s_do_fp16, const void* lse_f32,
                        const void* delta_f32, void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S,
                        int S_valid, int D, int Bq, int Bkv, int flags, void* stream);
+/* SageBwd option: dP = dO V^T from the UNQUANTISED fp16 dO and V (tcgen05 kind::f16, fp32 accumulation)
+ * instead of the int8 product the reference uses (attention_int8.py:380-384); the other four contractions stay int8.
+ * Bq, Bkv in {32, 64, 128}; non-causal; S a multiple of 128.  flags: QA_FLAG_NEAREST only. */
+int qa_int8_bwd_sage(const void* q_i8, const void* k_i8, const void* v_fp16, const void* do_i8, const void* do_fp16,
+                     const void* sq_fp16, const void* sk_fp16, const void* s_do_fp16, const void* lse_f32, const void* delta_f32,
+                     void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D, int Bq, int Bkv,
+                     int flags, void* stream);
 int qa_int8_bwd_finalize(const void* dq_ws_f32, const void* rowsum_ws_f32, const void* k_mean_f16, void* dq_f16, int BH,
                          int S, int D, void* stream);
 

@@ -264,7 +264,7 @@ def quant_tile_fp32(x: torch.Tensor, rounding: str = "trunc"):
 
 
 def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bkv, rounding: str = "trunc",
-                      causal: bool = False, s_valid: int | None = None):
+                      causal: bool = False, s_valid: int | None = None, v_fp16=None):
     """CONTRACT backward (what the CUDA kernel implements; LEDGER I-1,5,6,7,8,9,10,12,15).
 
     Per (b,h); k-tile j, q-tile i:
@@ -323,7 +323,10 @@ def int8_bwd_contract(dO, q_i8, sq, k_i8_T, k_mean, sk, v_i8, sv, O, lse, Bq, Bk
                 P = torch.where(keep, P, torch.zeros_like(P))
             P_i8, sP = quant_tile_fp32(P, rounding)
             dv[:, j] += _imm(P_i8.transpose(1, 2), dO_i8[:, i]).to(torch.float32) * s_dO[:, i, None, None] * sP
-            dP = _imm(dO_i8[:, i], vj.transpose(1, 2)).to(torch.float32) * s_dO[:, i, None, None] * svg[:, j, None, None]
+            if v_fp16 is None:
+                dP = _imm(dO_i8[:, i], vj.transpose(1, 2)).to(torch.float32) * s_dO[:, i, None, None] * svg[:, j, None, None]
+            else:                                                  # SageBwd option: dO V^T from the fp16 tensors
+                dP = torch.matmul(dOg[:, i].float(), v_fp16.reshape(G, nk, Bkv, D)[:, j].float().transpose(1, 2))
             dS = P * (dP - delta[:, i])
             dS_i8, s_dS = quant_tile_fp32(dS, rounding)
             dq[:, i] += _imm(dS_i8, kj).to(torch.float32) * s_dS * skg[:, j, None, None] * sm_scale \

@@ -28,6 +28,7 @@ SIGNATURES = {
     "qa_int8_fwd_ragged": (c_int, [c_void_p] * 15 + [c_int] * 9 + [c_void_p]),
     "qa_int8_bwd_ragged": (c_int, [c_void_p] * 14 + [c_int] * 7 + [c_void_p]),
     "qa_int8_bwd": (c_int, [c_void_p] * 14 + [c_int] * 6 + [c_void_p]),
+    "qa_int8_bwd_sage": (c_int, [c_void_p] * 14 + [c_int] * 6 + [c_void_p]),
     "qa_fp8_fwd": (c_int, [c_void_p] * 9 + [c_int] * 4 + [c_void_p]),
     "qa_int8_bwd_finalize": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "qa_bwd_delta": (c_int, [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]),

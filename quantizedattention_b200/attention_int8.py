@@ -180,10 +180,12 @@ def baseline_pytorch_attention(q, k, v, head_dim, causal):
 
 def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8_T, k_mean_bh_fp16, sk_bh_fp16,
                                  v_bh_int8, sv_bh_fp16, O_input_fp16, lse_input_fp16, Bq: int, Bkv: int, causal: bool = False,
-                                 *, rounding: str | None = None, kernel: str = "ws"):
+                                 *, rounding: str | None = None, kernel: str = "ws", v_fp16=None):
     """Quantised backward (attention_int8.py:268-432 under the 8-LEDGER contract).  Same argument order as the
     reference; `k_mean` is the per-head token mean [B,H,1,D]; `lse` may be the fp16 tensor the forward returned
     or an fp32 copy (LEDGER I-15).  `kernel`: "ws" (warp-specialised, default) or "8warp".
+    `v_fp16` (the unquantised V, [B,H,S,D] fp16) selects the SageBwd option: dP = dO V^T is then computed in
+    fp16 from the unquantised dO and V instead of the int8 product the reference uses (attention_int8.py:380-384).
     Returns (dq, dk, dv) fp16 [B,H,S,D]."""
     batch, head, q_tokens, head_dim = O_input_fp16.shape
     N = batch * head * q_tokens
@@ -213,6 +215,15 @@ def helion_atten_int8_hl_dot_bwd(dO_input_fp16, q_bh_int8, sq_bh_fp16, k_bh_int8
     if k_mean_bh_fp16 is not None:
         assert k_mean_bh_fp16.numel() == batch * head * head_dim, "k_mean must be the per-head token mean [B,H,1,D]"
         km = k_mean_bh_fp16.to(torch.float16).contiguous()
+    if v_fp16 is not None:                                         # SageBwd: dO V^T stays in fp16
+        if causal or Sp != S:
+            raise ValueError("the SageBwd option is built for non-causal attention with S a multiple of 128")
+        if v_fp16.dtype != torch.float16 or v_fp16.shape != O_input_fp16.shape:
+            raise TypeError("v_fp16 must be the fp16 [B,H,S,D] value tensor of the forward")
+        dq, dk, dv = ops.int8_bwd_sage(q_i8, k_i8, v_fp16.contiguous().view(N, head_dim), do_i8, dO.view(N, head_dim), sq, sk, s_do,
+                                       lse32, delta, km, BH, S, head_dim, Bq, Bkv, rounding=rounding)
+        shp = (batch, head, q_tokens, head_dim)
+        return dq.view(shp), dk.view(shp), dv.view(shp)
     dq, dk, dv = ops.int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, km, BH, Sp, head_dim,
                                        Bq, Bkv, rounding=rounding, causal=causal, kernel=kernel,
                                        s_valid=S if Sp != S else None)
@@ -227,7 +238,7 @@ class _SageInt8Fn(Function):
     rounding mode and the mask are explicit arguments."""
 
     @staticmethod
-    def forward(q_fp16, k_fp16, v_fp16, causal, Bq, Bkv, rounding):
+    def forward(q_fp16, k_fp16, v_fp16, causal, Bq, Bkv, rounding, sage_bwd=False):
         k_mean_fp16 = ops.k_mean(k_fp16)                                       # K-smoothing (LEDGER I-1)
         O, lse16, lse32, q_i8, k_i8, v_i8, sq, sk, sv = _fwd_tensors(q_fp16, k_fp16, v_fp16, k_mean_fp16, Bq, Bkv, rounding, causal)
         return (O, lse16, k_mean_fp16, q_i8, k_i8.t(), v_i8, sq, sk, sv, Bq, Bkv, lse32)
@@ -237,18 +248,21 @@ class _SageInt8Fn(Function):
         O_fp16, l_bh_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, Bq, Bkv, lse32 = output
         ctx.mark_non_differentiable(l_bh_fp16, k_mean_fp16, sq, sk, sv, lse32)
         ctx.set_materialize_grads(False)       # do not allocate zero grads for the auxiliary outputs
-        ctx.save_for_backward(O_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32)
+        sage_bwd = bool(inputs[7]) if len(inputs) > 7 else False
+        ctx.save_for_backward(O_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv,
+                              inputs[2] if sage_bwd else None,       # SageBwd keeps the unquantised V for dO V^T
+                              lse32)
         ctx.args = (Bq, Bkv, bool(inputs[3]), inputs[6])
 
     @staticmethod
     def backward(ctx, dO_fp16, *_ignored):
         Bq, Bkv, causal, rounding = ctx.args
         if dO_fp16 is None:
-            return (None,) * 7
-        O_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, lse32 = ctx.saved_tensors
+            return (None,) * 8
+        O_fp16, k_mean_fp16, q_bh_int8, k_bh_int8_T, v_bh_int8, sq, sk, sv, v_sage, lse32 = ctx.saved_tensors
         dq, dk, dv = helion_atten_int8_hl_dot_bwd(dO_fp16, q_bh_int8, sq, k_bh_int8_T, k_mean_fp16, sk, v_bh_int8, sv,
-                                                  O_fp16, lse32, Bq, Bkv, causal=causal, rounding=rounding)
-        return dq, dk, dv, None, None, None, None
+                                                  O_fp16, lse32, Bq, Bkv, causal=causal, rounding=rounding, v_fp16=v_sage)
+        return dq, dk, dv, None, None, None, None, None
 
 
 class SageAttention3_Int8_autograd_function(Function):
@@ -260,12 +274,12 @@ class SageAttention3_Int8_autograd_function(Function):
 
     @classmethod
     def apply(cls, q_fp16, k_fp16, v_fp16, causal: bool = False, *, Bq: int | None = None, Bkv: int | None = None,
-              rounding: str | None = None):
+              rounding: str | None = None, sage_bwd: bool = False):
         _check_fp16(q_fp16, k_fp16, v_fp16)
         Bq, Bkv, rounding = _resolve(Bq, Bkv, rounding)
         if causal:
             _warn_causal()
-        return _SageInt8Fn.apply(q_fp16, k_fp16, v_fp16, bool(causal), Bq, Bkv, rounding)[:11]
+        return _SageInt8Fn.apply(q_fp16, k_fp16, v_fp16, bool(causal), Bq, Bkv, rounding, bool(sage_bwd))[:11]
 
     @staticmethod
     def forward(q_fp16, k_fp16, v_fp16, causal=False):
@@ -294,9 +308,12 @@ class SageAttention3_Int8_autograd_function(Function):
 
 
 def sage_attention_3_int8(q_fp16, k_fp16, v_fp16, causal: bool = False, *, Bq: int | None = None, Bkv: int | None = None,
-                          rounding: str | None = None):
+                          rounding: str | None = None, sage_bwd: bool = False):
     """attention_int8.py:434-451: returns O fp16 [B,H,S,D], differentiable w.r.t. q, k, v.
     `causal=True` (absent in the reference's int8 kernel) applies the strict mask of the reference's own
     `baseline_pytorch_attention(..., causal=True)`: key < query, row 0 of a head = uniform average over all keys (a
-    one-time warning says so).  Bq / Bkv / rounding: per-call tunables (default: the module defaults)."""
-    return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16, causal, Bq=Bq, Bkv=Bkv, rounding=rounding)[0]
+    one-time warning says so).  Bq / Bkv / rounding: per-call tunables (default: the module defaults).
+    sage_bwd=True: the backward keeps dO V^T in fp16 (SageAttention3's SageBwd) instead of quantising it as
+    the reference does; it costs the fp16 V in the saved context and runs the (slower) block kernel."""
+    return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16, causal, Bq=Bq, Bkv=Bkv, rounding=rounding,
+                                                       sage_bwd=sage_bwd)[0]

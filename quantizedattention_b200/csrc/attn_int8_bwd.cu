@@ -32,6 +32,26 @@ struct Int8BwdSmem {
   static constexpr int total = off_c + 2 * 1024 + 1024;
 };
 
+// Shared memory of the block kernel in SageBwd mode (dP = dO V^T kept in fp16): no int8 V tile, one stage
+// of Q / dO, one dS buffer, plus the fp16 V tile of this k-tile and the fp16 dO tile of the current query tile
+// ([128 rows][64 columns] 128B-swizzled atoms, as the bf16 kernels lay out their operands).
+template <int D>
+struct Int8BwdSageSmem {
+  static constexpr int kTile = 128 * D;              // int8 [128][D]
+  static constexpr int kTile16 = 128 * D * 2;        // fp16 [128][D] as D/64 atoms of 16 KB
+  static constexpr int off_k = 0;
+  static constexpr int off_q = off_k + kTile;
+  static constexpr int off_do = off_q + kTile;
+  static constexpr int off_p = off_do + kTile;
+  static constexpr int off_ds = off_p + 128 * 128;
+  static constexpr int off_dq = off_ds + 128 * 128;  // fp32 [128 q][D] staging for the TMA reduce-add
+  static constexpr int off_c = off_dq + 128 * D * 4;
+  static constexpr int off_v16 = off_c + 2 * 1024;
+  static constexpr int off_do16 = off_v16 + kTile16;
+  static constexpr int total = off_do16 + kTile16 + 1024;
+  static constexpr int off_v = off_k;                // unused in this mode (kept so that shared code compiles)
+};
+
 struct Int8BwdParams {
   const __half *sq, *sk, *sv, *s_do;   // per-128-block fp16 scales
   const float* lse;                    // [BH*S] fp32 log2-sum-exp2
@@ -863,12 +883,18 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // row.  Correctness-first schedule: the phases of a tile pair run one after the other (no cross-tile software pipeline),
 // 8 warps, thread = (row, column half).  Same numerics as int8_bwd_kernel otherwise (magic accumulators, fp16-carried P).
 // ---------------------------------------------------------------------------------------------------------
-template <int D, bool RN>
+// SAGE (SageBwd): dP = dO V^T is NOT quantised - SageAttention3 keeps this one contraction in fp16
+// because dP - delta cancels catastrophically (the reference quantises it too, attention_int8.py:380-384).  tm_v / tm_do16
+// then describe the fp16 V and dO tensors, the MMA is kind::f16 with fp32 accumulation and pass 1 / pass 2 read dP as a
+// float; dV = P^T dO still uses the int8 dO.
+template <int D, bool RN, bool SAGE>
 __global__ void __launch_bounds__(256, 1)
 int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                    const __grid_constant__ CUtensorMap tm_dq, Int8BwdParams p, int BQ, int BK) {
-  using L = Int8BwdSmem<D>;
+                    const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_do16, Int8BwdParams p,
+                    int BQ, int BK) {
+  using L = std::conditional_t<SAGE, Int8BwdSageSmem<D>, Int8BwdSmem<D>>;
+  constexpr int kAtoms16 = D / 64, kAtom16 = 128 * 128;          // fp16 operand atoms ([128][64] x 2 B)
   constexpr int DH = D / 2, CW = 64, NT = 256;
   constexpr uint32_t kLay = (D == 128) ? kSwz128 : kSwz64;
   constexpr uint32_t kSbo = (D == 128) ? 1024 : 512;
@@ -914,9 +940,17 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t a_p = smem_u32(smem + L::off_p), a_ds = smem_u32(smem + L::off_ds);
 
   if (leader) {
-    mbar_expect_tx(&kv_full, 2 * L::kTile);
-    tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
-    tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
+    if (SAGE) {
+      mbar_expect_tx(&kv_full, L::kTile + 128 * D * 2);
+      tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
+#pragma unroll
+      for (int a = 0; a < kAtoms16; ++a)                           // fp16 V tile, one [128][64] atom per 64 columns
+        tma_load_2d(smem + L::off_c + 2048 + a * kAtom16, &tm_v, &kv_full, a * 64, (int)head_row0 + j * 128);
+    } else {
+      mbar_expect_tx(&kv_full, 2 * L::kTile);
+      tma_load_2d(smem + L::off_k, &tm_k, &kv_full, 0, (int)head_row0 + j * 128);
+      tma_load_2d(smem + L::off_v, &tm_v, &kv_full, 0, (int)head_row0 + j * 128);
+    }
     mbar_wait(&kv_full, 0);
   }
 
@@ -948,16 +982,30 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const float lse = (tq * 128 + row < p.S_valid) ? p.lse[qrow] : INFINITY;     // padded query rows of a ragged sequence: P = 0
     const float dlt = p.delta[qrow];
     if (leader) {
-      mbar_expect_tx(&qdo_full, 2 * L::kTile);
+      mbar_expect_tx(&qdo_full, 2 * L::kTile + (SAGE ? 128 * D * 2 : 0));
       tma_load_2d(smem + L::off_q, &tm_q, &qdo_full, 0, (int)head_row0 + t * 128);
       tma_load_2d(smem + L::off_do, &tm_do, &qdo_full, 0, (int)head_row0 + t * 128);
+      if (SAGE) {
+#pragma unroll
+        for (int a = 0; a < kAtoms16; ++a)
+          tma_load_2d(smem + L::off_c + 2048 + 128 * D * 2 + a * kAtom16, &tm_do16, &qdo_full, a * 64, (int)head_row0 + t * 128);
+      }
       mbar_wait(&qdo_full, t & 1);
       umma_f16_ss(tbase + 0, cdesc_a, cdesc_b, id_c128, 0);
-      umma_f16_ss(tbase + 128, cdesc_a, cdesc_b, id_c128, 0);
+      if (!SAGE) umma_f16_ss(tbase + 128, cdesc_a, cdesc_b, id_c128, 0);
 #pragma unroll
       for (int k = 0; k < D / 32; ++k) {
         umma_i8_ss(tbase + 0, umma_smem_desc(a_q + k * 32, 16, kSbo, kLay), umma_smem_desc(a_k + k * 32, 16, kSbo, kLay), id_s, 1);
-        umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, 1);
+        if (!SAGE) umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, 1);
+      }
+      if (SAGE) {                                                  // dP = dO V^T in fp16 (fp32 accumulation): 16 columns of D per MMA
+        constexpr uint32_t id_dp16 = umma_idesc(1, 0, 0, 0, 0, 128, 128);
+        const uint32_t a_v16 = smem_base + L::off_c + 2048, a_do16 = a_v16 + 128 * D * 2;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t o = (k >> 2) * kAtom16 + (k & 3) * 32;
+          umma_f16_ss(tbase + 128, umma_smem_desc(a_do16 + o, 16, 1024, kSwz128), umma_smem_desc(a_v16 + o, 16, 1024, kSwz128), id_dp16, k > 0);
+        }
       }
       umma_commit(&mma_done);
     }
@@ -973,9 +1021,10 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int ch = 0; ch < CW / 16; ++ch) {
       const int cb = (half * CW + ch * 16) / BK;                 // a 16-column chunk lies inside one key block (Bkv >= 32)
       const float c_s = magic_scale(sq_f * sk_c[cb & 3] * p.qk_scale);
-      const float cdpk = magic_scale(sdo_f * sv_c[cb & 3] * kPs);
+      const float cdpk = SAGE ? kPs : magic_scale(sdo_f * sv_c[cb & 3] * kPs);      // SAGE: dP is the fp32 accumulator itself
       const float2 cs2 = make_float2(c_s, c_s), nbs2 = make_float2(-kMagic * c_s, -kMagic * c_s);
-      const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(-dlt * kPs - kMagic * cdpk, -dlt * kPs - kMagic * cdpk);
+      const float dpb = SAGE ? -dlt * kPs : -dlt * kPs - kMagic * cdpk;
+      const float2 cdp2 = make_float2(cdpk, cdpk), ndlt2 = make_float2(dpb, dpb);
       uint32_t r[16], r2[16];
       tmem_ld16(lane_addr + half * CW + ch * 16, r);
       tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
@@ -1027,8 +1076,9 @@ int8_bwd_blk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const float amp = __uint_as_float(amax_p_s[ab][rb][cb]), amd = __uint_as_float(amax_ds_s[ab][rb][cb]);
       const float inv_p = amp > 0.f ? __fdividef(127.0f, amp) : 0.f;
       const float inv_ds = amd > 0.f ? __fdividef(127.0f, amd) : 0.f;
-      const float cdpi = magic_scale(sdo_f * sv_c[cb & 3] * kPs * inv_ds);
-      const float2 cdpi2 = make_float2(cdpi, cdpi), ndlti2 = make_float2(-dlt * kPs * inv_ds - kMagic * cdpi, -dlt * kPs * inv_ds - kMagic * cdpi);
+      const float cdpi = SAGE ? kPs * inv_ds : magic_scale(sdo_f * sv_c[cb & 3] * kPs * inv_ds);
+      const float dpbi = SAGE ? -dlt * kPs * inv_ds : -dlt * kPs * inv_ds - kMagic * cdpi;
+      const float2 cdpi2 = make_float2(cdpi, cdpi), ndlti2 = make_float2(dpbi, dpbi);
       const float2 invp2 = make_float2(inv_p, inv_p), magic2 = make_float2(8388608.0f, 8388608.0f);
       uint32_t r2[16];
       tmem_ld16(lane_addr + 128 + half * CW + ch * 16, r2);
@@ -1221,11 +1271,12 @@ static int launch_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
   return qa_check_launch("qa_int8_bwd");
 }
 
-template <int D, bool RN>
+template <int D, bool RN, bool SAGE = false>
 static int launch_int8_bwd_blk(const void* q_i8, const void* k_i8, const void* v_i8, const void* do_i8, void* dq_ws,
-                               const Int8BwdParams& p, int BH, int Bq, int Bkv, cudaStream_t st) {
-  using L = Int8BwdSmem<D>;
-  CUtensorMap tq, tk, tv, tdo, tdq;
+                               const Int8BwdParams& p, int BH, int Bq, int Bkv, cudaStream_t st, const void* v_f16 = nullptr,
+                               const void* do_f16 = nullptr) {
+  using L = std::conditional_t<SAGE, Int8BwdSageSmem<D>, Int8BwdSmem<D>>;
+  CUtensorMap tq, tk, tv, tdo, tdq, tdo16;
   const int sw = (D == 128) ? 3 : 2;
   uint64_t dims[2] = {(uint64_t)D, (uint64_t)BH * p.S};
   uint64_t str[1] = {(uint64_t)D};
@@ -1233,16 +1284,24 @@ static int launch_int8_bwd_blk(const void* q_i8, const void* k_i8, const void* v
   int rc;
   if ((rc = qa_make_tmap(&tq, q_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tk, k_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
-  if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
   if ((rc = qa_make_tmap(&tdo, do_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+  uint64_t str16[1] = {(uint64_t)D * 2};
+  uint32_t box16[2] = {64, 128};
+  if (SAGE) {                                                      // fp16 V and dO: [128][64] atoms, 128B swizzle
+    if ((rc = qa_make_tmap(&tv, v_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dims, str16, box16, 3))) return rc;
+    if ((rc = qa_make_tmap(&tdo16, do_f16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dims, str16, box16, 3))) return rc;
+  } else {
+    if ((rc = qa_make_tmap(&tv, v_i8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dims, str, box, sw))) return rc;
+    tdo16 = tdo;
+  }
   uint64_t strq[1] = {(uint64_t)D * 4};
   uint32_t boxq[2] = {32, 128};
   if ((rc = qa_make_tmap(&tdq, dq_ws, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strq, boxq, 3))) return rc;
-  auto kern = int8_bwd_blk_kernel<D, RN>;
+  auto kern = int8_bwd_blk_kernel<D, RN, SAGE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid((p.S_valid + 127) / 128, BH);                        // k-tiles without a valid key are not launched
-  kern<<<grid, 256, L::total, st>>>(tq, tk, tv, tdo, tdq, p, Bq, Bkv);
+  kern<<<grid, 256, L::total, st>>>(tq, tk, tv, tdo, tdq, tdo16, p, Bq, Bkv);
   return qa_check_launch("qa_int8_bwd");
 }
 
@@ -1340,4 +1399,36 @@ extern "C" int qa_int8_bwd(const void* q_i8, const void* k_i8, const void* v_i8,
                            int Bq, int Bkv, int flags, void* stream) {
   return qa_int8_bwd_ragged(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse_f32, delta_f32, rowsum_ws_f32, dq_ws_f32, dk_f16,
                             dv_f16, BH, S, S, D, Bq, Bkv, flags, stream);
+}
+
+// SageBwd option: the same backward with dP = dO V^T computed from the UNQUANTISED fp16 dO and V
+// (tcgen05 kind::f16, fp32 accumulation) instead of the int8 product the reference uses (attention_int8.py:380-384); every
+// other contraction stays int8.  Runs the block kernel (any Bq, Bkv in {32, 64, 128}); non-causal, S a multiple of 128.
+extern "C" int qa_int8_bwd_sage(const void* q_i8, const void* k_i8, const void* v_f16, const void* do_i8, const void* do_f16,
+                                const void* sq, const void* sk, const void* s_do, const void* lse_f32, const void* delta_f32,
+                                void* rowsum_ws_f32, void* dq_ws_f32, void* dk_f16, void* dv_f16, int BH, int S, int D, int Bq,
+                                int Bkv, int flags, void* stream) {
+  if (flags & ~QA_FLAG_NEAREST) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_sage: only QA_FLAG_NEAREST is accepted");
+  if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_sage: D must be 64 or 128");
+  if ((Bq != 32 && Bq != 64 && Bq != 128) || (Bkv != 32 && Bkv != 64 && Bkv != 128))
+    return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_sage: Bq and Bkv must be 32, 64 or 128");
+  if (BH <= 0 || S <= 0 || S % 128) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_sage: S must be a positive multiple of 128");
+  if ((long long)BH * S >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_sage: BH * S must be below 2^31");
+  if (!q_i8 || !k_i8 || !v_f16 || !do_i8 || !do_f16 || !sq || !sk || !s_do || !lse_f32 || !delta_f32 || !dq_ws_f32 || !dk_f16 || !dv_f16)
+    return qa_fail(QA_ERR_SHAPE, "qa_int8_bwd_sage: null pointer (only rowsum_ws may be NULL)");
+  if (((uintptr_t)q_i8 | (uintptr_t)k_i8 | (uintptr_t)v_f16 | (uintptr_t)do_i8 | (uintptr_t)do_f16 | (uintptr_t)dq_ws_f32 | (uintptr_t)dk_f16 | (uintptr_t)dv_f16) & 15)
+    return qa_fail(QA_ERR_ALIGN, "qa_int8_bwd_sage: 16-byte alignment required");
+  Int8BwdParams p;
+  p.sq = (const __half*)sq; p.sk = (const __half*)sk; p.sv = (const __half*)sk; p.s_do = (const __half*)s_do;   // sv unused
+  p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32; p.rowsum = (float*)rowsum_ws_f32;
+  p.dk = (__half*)dk_f16; p.dv = (__half*)dv_f16;
+  p.S = S; p.S_valid = S; p.dbg = nullptr;
+  p.sm_scale = (float)(1.0 / sqrt((double)D));
+  p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & QA_FLAG_NEAREST)
+    return D == 128 ? launch_int8_bwd_blk<128, true, true>(q_i8, k_i8, nullptr, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st, v_f16, do_f16)
+                    : launch_int8_bwd_blk<64, true, true>(q_i8, k_i8, nullptr, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st, v_f16, do_f16);
+  return D == 128 ? launch_int8_bwd_blk<128, false, true>(q_i8, k_i8, nullptr, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st, v_f16, do_f16)
+                  : launch_int8_bwd_blk<64, false, true>(q_i8, k_i8, nullptr, do_i8, dq_ws_f32, p, BH, Bq, Bkv, st, v_f16, do_f16);
 }

@@ -211,6 +211,32 @@ def int8_bwd_prequant(q_i8, k_i8, v_i8, do_i8, sq, sk, sv, s_do, lse32, delta, k
     return dq, dk, dv
 
 
+def int8_bwd_sage(q_i8, k_i8, v_fp16, do_i8, dO_fp16, sq, sk, s_do, lse32, delta, k_mean, BH, S, D, Bq=128, Bkv=128,
+                  rounding: str = "trunc"):
+    """SageBwd backward (qa_int8_bwd_sage): dP = dO V^T in fp16 from the unquantised tensors, everything else int8.
+    v_fp16, dO_fp16: [BH*S, D] fp16.  Returns (dq, dk, dv) fp16 [BH*S, D]."""
+    _need_cuda(q_i8, k_i8, v_fp16, do_i8, dO_fp16)
+    assert v_fp16.dtype == torch.float16 and dO_fp16.dtype == torch.float16
+    dev = q_i8.device
+    dq_ws = torch.zeros((BH * S, D), dtype=torch.float32, device=dev)
+    rowsum_ws = torch.zeros((BH * S,), dtype=torch.float32, device=dev) if k_mean is not None else None
+    dk = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    dv = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    dq = torch.empty((BH * S, D), dtype=torch.float16, device=dev)
+    if k_mean is not None:
+        k_mean = k_mean.contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        with _timed("int8_bwd_sage"):
+            _lib.check(L.qa_int8_bwd_sage(_lib.ptr(q_i8), _lib.ptr(k_i8), _lib.ptr(v_fp16.contiguous()), _lib.ptr(do_i8),
+                                          _lib.ptr(dO_fp16.contiguous()), _lib.ptr(sq), _lib.ptr(sk), _lib.ptr(s_do), _lib.ptr(lse32),
+                                          _lib.ptr(delta), _lib.ptr(rowsum_ws), _lib.ptr(dq_ws), _lib.ptr(dk), _lib.ptr(dv), BH, S, D,
+                                          Bq, Bkv, _flags(rounding, False), _lib.cur_stream()), "qa_int8_bwd_sage")
+        _lib.check(L.qa_int8_bwd_finalize(_lib.ptr(dq_ws), _lib.ptr(rowsum_ws), _lib.ptr(k_mean), _lib.ptr(dq), BH, S, D,
+                                          _lib.cur_stream()), "qa_int8_bwd_finalize")
+    return dq, dk, dv
+
+
 def bf16_fwd_key_step(Sq: int, nsplit: int = 0) -> int:
     """Keys per online-softmax step of the kernel qa_bf16_fwd dispatches to: the running maximum (and its bias
     correction) advances once per step, so an oracle comparison at rounding level must use the same `tile_k`.

@@ -95,3 +95,34 @@ def test_int8_default_tunables_train_end_to_end():
     for name, a, b in zip("qkv", (qh, kh, vh), (qf, kf, vf)):
         cs, rl = _cos(a.grad.cpu(), b.grad), _rel(a.grad.cpu(), b.grad)
         assert cs > 0.995 and rl < 0.13, (name, cs, rl)     # survey probe at 32/32: cos 0.9985-0.9991, rel 0.07-0.09
+
+
+@pytest.mark.parametrize("shape,Bq,Bkv", [((1, 2, 256, 128), 128, 128), ((2, 2, 512, 64), 128, 128), ((1, 2, 256, 128), 32, 32)])
+def test_int8_bwd_sagebwd_option(shape, Bq, Bkv):
+    """dP = dO V^T kept in fp16 (SageAttention3's SageBwd) - against the oracle with the same option, and
+    closer to fp32 autograd than the fully quantised backward."""
+    from oracle import int8_ref
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_int8 as A
+    B, H, S, D = shape
+    g = torch.Generator().manual_seed(3500 + S + D + Bq)
+    q, k, v, dO = [torch.randn(shape, generator=g).to(torch.float16) for _ in range(4)]
+    out = A.SageAttention3_Int8_autograd_function.apply(q.cuda(), k.cuda(), v.cuda(), Bq=Bq, Bkv=Bkv)
+    O, lse16, kmean, q_i8, k_i8_T, v_i8, sq, sk, sv, bq, bkv = out
+    c = lambda t: t.cpu()
+    ref = int8_ref.int8_bwd_contract(dO, c(q_i8), c(sq), c(k_i8_T), c(kmean), c(sk), c(v_i8), c(sv), c(O), c(lse16), Bq, Bkv, v_fp16=v)
+    got = A.helion_atten_int8_hl_dot_bwd(dO.cuda(), q_i8, sq, k_i8_T, kmean, sk, v_i8, sv, O, lse16, Bq, Bkv, v_fp16=v.cuda())
+    torch.cuda.synchronize()
+    for name, a, b in zip(("dq", "dk", "dv"), got, ref):
+        assert _cos(a.cpu(), b) > 0.9995 and _rel(a.cpu(), b) < 3e-2, (name, _cos(a.cpu(), b), _rel(a.cpu(), b))
+    # accuracy: the option must not be worse than the fully quantised backward against fp32 autograd
+    qf, kf, vf = [t.float().requires_grad_() for t in (q, k, v)]
+    baseline_pytorch_attention(qf, kf, vf, D, False).backward(dO.float())
+    plain = A.helion_atten_int8_hl_dot_bwd(dO.cuda(), q_i8, sq, k_i8_T, kmean, sk, v_i8, sv, O, lse16, Bq, Bkv)
+    for name, a, b, r in zip(("dq", "dk"), got[:2], plain[:2], (qf.grad, kf.grad)):
+        assert _rel(a.cpu(), r) <= _rel(b.cpu(), r) * 1.02, (name, _rel(a.cpu(), r), _rel(b.cpu(), r))
+    # through autograd
+    qh, kh, vh = [t.cuda().requires_grad_() for t in (q, k, v)]
+    A.sage_attention_3_int8(qh, kh, vh, Bq=Bq, Bkv=Bkv, sage_bwd=True).backward(dO.cuda())
+    # (the autograd path recomputes P from the fp32 lse, the direct call above from the fp16 one the reference returns)
+    assert _rel(kh.grad, got[1]) < 2e-2 and _rel(vh.grad, got[2]) < 2e-2 and _rel(qh.grad, got[0]) < 2e-2
