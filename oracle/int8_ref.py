@@ -163,10 +163,13 @@ def int8_fwd(q, k_smooth, v, Bq: int = 32, Bkv: int = 32, per_head: bool = True,
     return out
 
 
-def int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bkv, last):
+def int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bkv, last, causal_diag: bool = False):
     """One ring step on pre-quantised operands: the tile loop of `int8_fwd` (attention_int8.py:176-250) over one K/V
     shard, continuing the online-softmax state (O_acc fp32 [BH*Sq,D], m fp32 (holding an fp16 value), l fp32).
-    last=False -> new state; last=True -> (O fp16 [BH*Sq,D], lse16, lse32) as :252-257."""
+    last=False -> new state; last=True -> (O fp16 [BH*Sq,D], lse16, lse32) as :252-257.
+    causal_diag=True (the diagonal chunk of a causal ring, Sq == Sk): strict mask key < query inside the chunk with weight
+    exactly 0, as `int8_fwd(causal=True)`; a row without a visible key keeps its state (row 0 of a fresh chunk: O = 0,
+    m = -inf, l = 1) - the row-0 rule of LEDGER B-1 is applied by the caller."""
     qk_scale = (1.0 / math.sqrt(D)) * LOG2E
     qg, kg, vg = q_i8.view(BH, Sq, D), k_i8.view(BH, Sk, D), v_i8.view(BH, Sk, D)
     sq_rows = sq.view(BH, Sq // Bq).repeat_interleave(Bq, dim=1)[..., None].float()
@@ -183,15 +186,27 @@ def int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bk
         ks = slice(j * Bkv, (j + 1) * Bkv)
         S16 = (_imm(qg, kg[:, ks].transpose(1, 2)).to(torch.float32) * sq_rows * sk_g[:, j].view(BH, 1, 1).float()
                * qk_scale).to(torch.float16)
+        if causal_diag:
+            keep = torch.arange(Sq)[:, None] > torch.arange(j * Bkv, (j + 1) * Bkv)[None, :]
+            if not bool(keep.any()):
+                continue                                                # tile above the diagonal: skipped
+            S16 = torch.where(keep, S16, torch.tensor(float("-inf"), dtype=torch.float16))
         row_max = torch.amax(S16, -1, keepdim=True)
         m_new = torch.max(m, row_max)
         P = torch.exp2((S16 - m_new).to(torch.float32))
         rescale = torch.exp2((m - m_new).to(torch.float32))
+        if causal_diag:                                                 # (-inf) - (-inf): nothing visible yet / in this tile
+            P = torch.where(keep, P, torch.zeros_like(P))
+            rescale = torch.where(torch.isinf(m_new), torch.ones_like(rescale), rescale)
         m = m_new
         l = l * rescale + torch.sum(P, -1, keepdim=True)
         O = O * rescale
         sp = torch.exp2((row_max - m).to(torch.float32)) / 127
-        P_i8 = (P / sp).to(torch.int8)
+        Pq = P / sp
+        if causal_diag:
+            Pq = torch.where(torch.isinf(row_max), torch.zeros_like(Pq), Pq)
+            sp = torch.where(torch.isinf(row_max), torch.zeros_like(sp), sp)
+        P_i8 = Pq.to(torch.int8)
         O = O + _imm(P_i8, vg[:, ks]).to(torch.float32) * sp * sv_g[:, j].view(BH, 1, 1).float()
     if not last:
         return O.reshape(BH * Sq, D), m.float().reshape(-1), l.reshape(-1)

@@ -798,11 +798,14 @@ extern "C" int qa_int8_fwd_ragged(const void* q_i8, const void* k_i8, const void
   // magic accumulators (A/B comparison).  Bkv = 128 defaults to the two-stage kernel with magic accumulators.
   if (nsplit < 0 || nsplit > 3) return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: nsplit must be 0, 1, 2 or 3");
   if (causal) {                                                  // instantiated for the tuned tile only
-    if (Bkv != 128 || Bq != 128 || nsplit == 1 || rounding || Sq != Sk || o_acc != nullptr || o_acc_in != nullptr)
-      return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: causal needs Sq == Sk, Bq = Bkv = 128, the two-stage kernel, truncation, no ring state");
+    if (Bkv != 128 || Bq != 128 || nsplit == 1 || rounding || Sq != Sk || o_acc_in != nullptr)
+      return qa_fail(QA_ERR_SHAPE, "qa_int8_fwd: causal needs Sq == Sk, Bq = Bkv = 128, the two-stage kernel, truncation, no incoming state");
     int rc = D == 128 ? launch_int8_fwd<128, 2, 3, 128, false, true, true>(q_i8, k_i8, v_i8, p, BH, st)
                       : launch_int8_fwd<64, 2, 4, 128, false, true, true>(q_i8, k_i8, v_i8, p, BH, st);
     if (rc) return rc;
+    // state-out mode (o_acc != NULL; the diagonal chunk of a causal ring): a row without a visible key leaves the fresh state
+    // (O = 0, m = -inf, l = 1) and the caller owns the row-0 rule, which needs the V of EVERY rank
+    if (o_acc != nullptr) return QA_OK;
     if (D == 128) int8_row0_fixup_kernel<128><<<BH, 512, 0, st>>>((const int8_t*)v_i8, p.sv, p.O, p.lse16, p.lse32, Sq);
     else int8_row0_fixup_kernel<64><<<BH, 512, 0, st>>>((const int8_t*)v_i8, p.sv, p.O, p.lse16, p.lse32, Sq);
     return qa_check_launch("qa_int8_fwd(causal row 0)");

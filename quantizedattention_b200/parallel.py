@@ -50,6 +50,13 @@ class RingInt8Kernels:
         (None or (O_acc, m, l)).  last=False -> new state; last=True -> (O fp16, lse16, lse32)."""
         raise NotImplementedError
 
+    def attend_causal_diag(self, q_i8, sq, kv, BH, S, D):
+        """The diagonal chunk of a causal ring: strict mask key < query inside the chunk, fresh state in, state out."""
+        raise NotImplementedError
+
+    def v_token_sum(self, v_i8, sv, BH, S, D, Bkv):               # -> fp32 [BH, D]: sum over tokens of the de-quantised V
+        return (v_i8.view(BH, S // Bkv, Bkv, D).float() * sv.view(BH, S // Bkv, 1, 1).float()).sum(dim=(1, 2))
+
 
 class CudaRingKernels(RingInt8Kernels):
     def token_sum(self, k):
@@ -65,6 +72,11 @@ class CudaRingKernels(RingInt8Kernels):
         k_i8, v_i8, sk, sv = kv
         return ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, Sq, Sk, D, Bq, Bkv, ring_state=not last,
                                      state_in=state, want_lse32=True)
+
+    def attend_causal_diag(self, q_i8, sq, kv, BH, S, D):
+        from . import ops
+        k_i8, v_i8, sk, sv = kv
+        return ops.int8_fwd_prequant(q_i8, k_i8, v_i8, sq, sk, sv, BH, S, S, D, 128, 128, ring_state=True, causal=True)
 
 
 def ring_int8_attention_fwd(q, k, v, Bq: int = 128, Bkv: int = 128, group=None, kernels: RingInt8Kernels | None = None,
@@ -132,3 +144,106 @@ def ring_int8_attention_fwd(q, k, v, Bq: int = 128, Bkv: int = 128, group=None, 
             cur = nxt
     O, lse16, lse32 = out
     return O.view(B, H, Sl, D), lse16, lse32, k_mean
+
+
+def zigzag_chunks(rank: int, world: int):
+    """Chunk ids (of 2 * world equal chunks of the sequence) a rank owns under zig-zag sharding: (rank, 2*world-1-rank).
+    Every rank then has the same amount of causal work."""
+    return rank, 2 * world - 1 - rank
+
+
+def ring_int8_attention_fwd_causal(q, k, v, group=None, kernels: RingInt8Kernels | None = None):
+    """Causal int8 attention forward, sequence-sharded with zig-zag chunks (causal ring for long-context
+    training).  The sequence is cut into 2g chunks; rank r owns chunks r and 2g-1-r, and passes q, k, v as
+    fp16 [B,H,2*Sc,D] = [chunk r | chunk 2g-1-r].  The mask is the strict one of the reference's baseline (key < query,
+    attention_int8.py:465-473; global row 0 = uniform average over all keys of the de-quantised V, LEDGER B-1).
+    Bq = Bkv = 128.  Returns (O fp16 [B,H,2*Sc,D] in the same chunk order, lse32 fp32 [B*H, 2*Sc], k_mean).
+
+    Per ring step a rank holds the K/V chunks (c, 2g-1-c) of rank c = r - step: for c < r both of its query chunks attend
+    chunk c in full; for c > r only its late query chunk attends both; its own pair is the diagonal case (strict mask
+    inside the two diagonal chunks).  Every (query chunk, K/V chunk) product continues the same online-softmax state in
+    the kernel, so nothing is merged on the host; chunk pairs above the diagonal are never launched."""
+    kernels = kernels or CudaRingKernels()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B, H, S2, D = q.shape
+    Sc, BH = S2 // 2, B * H
+    if S2 % 256:
+        raise ValueError("every zig-zag chunk must be a multiple of 128 tokens")
+    k_mean = global_k_mean(k, S2 * world, kernels.token_sum, group)
+    halves = lambda t: (t[:, :, :Sc].contiguous(), t[:, :, Sc:].contiguous())
+    qa, qb = [kernels.quant(x, 128) for x in halves(q)]
+    (ka, ska), (kb, skb) = [kernels.quant(x, 128, mean=k_mean, rows_per_head=Sc) for x in halves(k)]
+    (va, sva), (vb, svb) = [kernels.quant(x, 128) for x in halves(v)]
+    cur = (ka, va, ska, sva, kb, vb, skb, svb)                       # K/V chunk pair currently held (own pair first)
+    # global row 0 (LEDGER B-1): sum over ALL tokens of the de-quantised V
+    vsum = kernels.v_token_sum(va, sva, BH, Sc, D, 128) + kernels.v_token_sum(vb, svb, BH, Sc, D, 128)
+    if dist.is_initialized() and world > 1:
+        dist.all_reduce(vsum, op=dist.ReduceOp.SUM, group=group)
+    use_cuda = q.is_cuda
+    comm_stream = torch.cuda.Stream(device=q.device) if (use_cuda and world > 1) else None
+    st_a = st_b = None
+    out_a = out_b = None
+    for step in range(world):
+        src = (rank - step) % world                                 # owner of the K/V pair held in this step
+        nxt, reqs = None, []
+        if step + 1 < world:
+            nxt = tuple(torch.empty_like(t) for t in cur)
+            send_to, recv_from = (rank + 1) % world, (rank - 1) % world
+            g_rank = (lambda r_: dist.get_global_rank(group, r_)) if group else (lambda r_: r_)
+            ops_ = [dist.P2POp(dist.isend, t, g_rank(send_to), group) for t in cur]
+            ops_ += [dist.P2POp(dist.irecv, t, g_rank(recv_from), group) for t in nxt]
+            if comm_stream is not None:
+                comm_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(comm_stream):
+                    reqs = dist.batch_isend_irecv(ops_)
+            else:
+                reqs = dist.batch_isend_irecv(ops_)
+        kv_lo, kv_hi = cur[:4], cur[4:]                             # chunks src and 2g-1-src
+        # which call is the LAST one of each query chunk: chunk a ends at step = rank (src = 0), chunk b at the last step
+        last_a = (step == rank)
+        last_b = (step == world - 1)
+        if step == 0:                                               # own pair: the two diagonal chunks and (b, a) in full
+            st_a = kernels.attend_causal_diag(qa[0], qa[1], kv_lo, BH, Sc, D)
+            if last_a:                                              # rank 0: chunk 0 sees nothing else; normalise its state
+                out_a = _finish_state(st_a)
+            st_b = kernels.attend_causal_diag(qb[0], qb[1], kv_hi, BH, Sc, D)
+            res = kernels.attend(qb[0], qb[1], kv_lo, st_b, BH, Sc, Sc, D, 128, 128, last_b)
+            st_b, out_b = (None, res) if last_b else (res, None)
+        elif src < rank:                                            # an earlier rank's pair: both query chunks see chunk src
+            res = kernels.attend(qa[0], qa[1], kv_lo, st_a, BH, Sc, Sc, D, 128, 128, last_a)
+            st_a, out_a = (None, res) if last_a else (res, out_a)
+            res = kernels.attend(qb[0], qb[1], kv_lo, st_b, BH, Sc, Sc, D, 128, 128, last_b)
+            st_b, out_b = (None, res) if last_b else (res, None)
+        else:                                                       # a later rank's pair: only the late query chunk, both chunks
+            st_b = kernels.attend(qb[0], qb[1], kv_lo, st_b, BH, Sc, Sc, D, 128, 128, False)
+            res = kernels.attend(qb[0], qb[1], kv_hi, st_b, BH, Sc, Sc, D, 128, 128, last_b)
+            st_b, out_b = (None, res) if last_b else (res, None)
+        if comm_stream is not None:
+            with torch.cuda.stream(comm_stream):
+                for r_ in reqs:
+                    r_.wait()
+            torch.cuda.current_stream().wait_stream(comm_stream)
+        else:
+            for r_ in reqs:
+                r_.wait()
+        if nxt is not None:
+            cur = nxt
+    Oa, _, lsa = out_a
+    Ob, _, lsb = out_b
+    O = torch.cat([Oa.view(B, H, Sc, D), Ob.view(B, H, Sc, D)], dim=2)
+    lse = torch.cat([lsa.view(BH, Sc), lsb.view(BH, Sc)], dim=1)
+    if rank == 0:                                                   # global row 0 sees no key: uniform average over all keys
+        import math
+        S_tot = S2 * world
+        O[:, :, 0] = (vsum / S_tot).view(B, H, D).to(O.dtype)
+        lse[:, 0] = -128.0 + math.log2(S_tot)
+    return O, lse, k_mean
+
+
+def _finish_state(state):
+    """(O_acc, m, l) -> (O fp16, lse16, lse32): the normalisation the kernel applies on a `last` call, for the one chunk
+    whose only product is a diagonal one (chunk 0 of rank 0)."""
+    o_acc, m, l = state
+    lse32 = m + torch.log2(l)
+    return (o_acc / l[:, None]).to(torch.float16), lse32.to(torch.float16), lse32

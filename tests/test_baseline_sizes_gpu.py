@@ -66,11 +66,12 @@ def test_bf16_bwd_cfg2_causal_matches_contract_oracle():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the NCCL ring needs at least two GPUs on the box")
-def test_ring_kv_nccl_matches_single_device():
+@pytest.mark.parametrize("mode", ["check", "check_causal"])
+def test_ring_kv_nccl_matches_single_device(mode):
     n = 2 if torch.cuda.device_count() < 4 else 4
     port = 29700 + os.getpid() % 200
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tools", "ring_bench.py"), "check"]
+           "--master-port", str(port + (7 if mode == "check_causal" else 0)), os.path.join(ROOT, "tools", "ring_bench.py"), mode]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])

@@ -24,6 +24,15 @@ class OracleRingKernels:
         return int8_ref.int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, state, BH, Sq, Sk, D, Bq, Bkv, last)
 
 
+    def attend_causal_diag(self, q_i8, sq, kv, BH, S, D):
+        from oracle import int8_ref
+        k_i8, v_i8, sk, sv = kv
+        return int8_ref.int8_attend_state(q_i8, sq, k_i8, v_i8, sk, sv, None, BH, S, S, D, 128, 128, False, causal_diag=True)
+
+    def v_token_sum(self, v_i8, sv, BH, S, D, Bkv):
+        return (v_i8.view(BH, S // Bkv, Bkv, D).float() * sv.view(BH, S // Bkv, 1, 1).float()).sum(dim=(1, 2))
+
+
 def _full_inputs():
     g = torch.Generator().manual_seed(123)
     q, k, v = [torch.randn(1, 2, 512, 64, generator=g).to(torch.float16) for _ in range(3)]
@@ -97,3 +106,41 @@ def test_shard_validation():
     from quantizedattention_b200.parallel import shard_batch_heads
     with pytest.raises(ValueError):
         shard_batch_heads(torch.zeros(1, 3, 128, 64), 0, 2)
+
+
+def _zigzag_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from quantizedattention_b200.parallel import ring_int8_attention_fwd_causal, zigzag_chunks
+    q, k, v = _full_inputs()
+    Sc = q.shape[2] // (2 * world)
+    a, b = zigzag_chunks(rank, world)
+    take = lambda t: torch.cat([t[:, :, a * Sc:(a + 1) * Sc], t[:, :, b * Sc:(b + 1) * Sc]], dim=2).contiguous()
+    O, lse, km = ring_int8_attention_fwd_causal(take(q), take(k), take(v), kernels=OracleRingKernels())
+    ret[rank] = (O, lse, km)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_causal_zigzag_ring_world2_matches_single_device():
+    """causal ring with zig-zag sharding (rank r owns chunks r and 2g-1-r) against the single-device causal
+    oracle on the whole sequence (strict mask, global row 0 = uniform average over all keys)."""
+    from oracle import int8_ref
+    world, port = 2, 30700 + (os.getpid() % 500)
+    ret = mp.Manager().dict()
+    mp.spawn(_zigzag_worker, args=(world, port, ret), nprocs=world, join=True)
+    q, k, v = _full_inputs()
+    B, H, S, D = q.shape
+    Sc = S // (2 * world)
+    full = int8_ref.sage_forward(q, k, v, 128, 128, causal=True)
+    ref_lse = int8_ref.int8_fwd(q, int8_ref.smooth_k(k, full[2]), v, 128, 128, return_lse32=True, causal=True)[10].view(B * H, S)
+    O = torch.empty_like(full[0])
+    lse = torch.empty(B * H, S)
+    for r in range(world):
+        for half, c in enumerate((r, 2 * world - 1 - r)):
+            O[:, :, c * Sc:(c + 1) * Sc] = ret[r][0][:, :, half * Sc:(half + 1) * Sc]
+            lse[:, c * Sc:(c + 1) * Sc] = ret[r][1][:, half * Sc:(half + 1) * Sc]
+    assert torch.equal(ret[0][2], ret[1][2])
+    assert (O.float() - full[0].float()).abs().max() < 6e-3           # per-chunk state continuation: tolerance, not bitwise
+    assert (lse - ref_lse).abs().max() < 3e-2

@@ -41,3 +41,23 @@ def test_ring_state_continuation_matches_single_shot(D, Bkv):
     st = int8_ref.int8_attend_state(c(q_i8), c(sq), *[c(t) for t in shards[1][2]], None, BH, Sl, Sl, D, 128, Bkv, False)
     Oo, _, _ = int8_ref.int8_attend_state(c(q_i8), c(sq), *[c(t) for t in shards[0][2]], st, BH, Sl, Sl, D, 128, Bkv, True)
     assert (outs[1].reshape(-1, D).float() - Oo.float()).abs().max() < 5e-3
+
+
+@pytest.mark.parametrize("D", [64, 128])
+def test_causal_chunk_continuation_matches_single_shot(D):
+    """The building blocks of the zig-zag causal ring on one device (world 1: the rank owns chunks 0 and 1 = the whole
+    sequence): diagonal chunk with state out, then the late query chunk continues over the early K/V chunk; against the
+    single-shot causal kernel's oracle."""
+    from oracle import int8_ref
+    from quantizedattention_b200.parallel import ring_int8_attention_fwd_causal
+    g = torch.Generator().manual_seed(23 + D)
+    B, H, S = 1, 2, 512
+    q, k, v = [torch.randn(B, H, S, D, generator=g).to(torch.float16) for _ in range(3)]
+    k = (k.float() + 0.5).to(torch.float16)
+    O, lse, km = ring_int8_attention_fwd_causal(q.cuda(), k.cuda(), v.cuda())
+    torch.cuda.synchronize()
+    full = int8_ref.sage_forward(q, k, v, 128, 128, causal=True)
+    assert torch.equal(km.cpu(), full[2])
+    assert (O.cpu().float() - full[0].float()).abs().max() < 6e-3
+    ref_lse = int8_ref.int8_fwd(q, int8_ref.smooth_k(k, full[2]), v, 128, 128, return_lse32=True, causal=True)[10].view(B * H, S)
+    assert (lse.cpu() - ref_lse).abs().max() < 3e-2

@@ -1,6 +1,7 @@
 """Multi-GPU runs (launch with torchrun, one rank per GPU):
   ring   : BASELINE configs[4] -- int8 long-context forward B=1 H=32 S=131072 D=128, sequence-sharded ring KV
   check  : small ring problem compared against the single-device kernel (parity of the NCCL ring on real GPUs)
+  check_causal : the zig-zag causal ring (rank r owns chunks r and 2g-1-r) against the single-device causal kernel
 Prints one JSON line from rank 0."""
 import json
 import os
@@ -24,6 +25,23 @@ def main():
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     except Exception:  # noqa: BLE001
         dist.init_process_group("nccl", device_id=dev)
+    if mode == "check_causal":
+        from quantizedattention_b200.parallel import ring_int8_attention_fwd_causal, zigzag_chunks
+        B, H, S, D = 1, 4, 4096, 128
+        g = torch.Generator().manual_seed(1006)
+        q, k, v = [torch.randn(B, H, S, D, generator=g).to(torch.float16) for _ in range(3)]
+        Sc = S // (2 * world)
+        a, b = zigzag_chunks(rank, world)
+        take = lambda t: torch.cat([t[:, :, a * Sc:(a + 1) * Sc], t[:, :, b * Sc:(b + 1) * Sc]], dim=2).contiguous().to(dev)
+        O, lse, _ = ring_int8_attention_fwd_causal(take(q), take(k), take(v))
+        ref = A.sage_attention_3_int8(q.to(dev), k.to(dev), v.to(dev), causal=True)
+        mine = torch.cat([ref[:, :, a * Sc:(a + 1) * Sc], ref[:, :, b * Sc:(b + 1) * Sc]], dim=2)
+        err = (O.float() - mine.float()).abs().max()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"mode": mode, "n_gpus": world, "S": S, "max_abs_vs_single_device": err.item(), "ok": bool(err.item() < 6e-3)}))
+        dist.destroy_process_group()
+        return
     if mode == "check":
         B, H, S, D = 1, 4, 4096, 128
     else:
