@@ -463,7 +463,7 @@ def main():
     peak = int8_peak or 2.0 * mp.get("bf16_tflops", 1590.0)
     traffic = None                      # dram__bytes_read + dram__bytes_write per launch from the ncu --set full capture
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["int8_bwd_kernel_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["int8_bwd_kernel_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
     roof = {"bound": "tensor", "kernel": "int8_bwd_ws_kernel<128>", "achieved": OPS_BWD(B, H, S, D) / (bwd_ms * 1e-3) / 1e12,
