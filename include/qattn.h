@@ -136,6 +136,12 @@ int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, voi
 int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
                 const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
                 int causal, void* stream);
+/* Same with the kernel explicit.  variant 0 (what qa_bf16_bwd runs): D = 128 -> the warp-specialised kernel (logits
+ * computed transposed, P fed to the tensor core from TMEM, dQ^T drained with coalesced reductions); D = 64 -> the
+ * phase-sequential kernel.  variant 1: the phase-sequential kernel for every D. */
+int qa_bf16_bwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                   const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
+                   int causal, int variant, void* stream);
 
 /* ---- JVP: helion_attention_jvp_forward_fp32, attention_jvp.py:33-195 (operands pre-cast to bf16); D in {64,128} ---- */
 int qa_jvp_fwd(const void* q_bf16, const void* tq_bf16, const void* k_bf16, const void* tk_bf16, const void* v_bf16,

@@ -263,24 +263,51 @@ static int launch_bf16_bwd(const void* q, const void* k, const void* v, const vo
   return r;
 }
 
+// attn_bf16_bwd2.cu: warp-specialised kernel, D = 128
+int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* lse, const float* delta,
+                       float* dq, float* dk, float* dv, int BH, int S, int causal, cudaStream_t st);
+
 }  // namespace qa
 
 using namespace qa;
 
 // q, k fp16; v bf16; dO_bf16 = bf16 copy of dO (from qa_bwd_delta); dO_f32 the original; lse, delta fp32 [BH*S];
 // dq (zero-initialised), dk, dv: fp32 [BH*S, D].
-extern "C" int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
-                           const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
-                           int D, int causal, void* stream) {
+// variant 0: default (D = 128: warp-specialised kernel with transposed logits, attn_bf16_bwd2.cu; D = 64: the phase-sequential
+// kernel above); variant 1: the phase-sequential kernel for every D.
+extern "C" int qa_bf16_bwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                              const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
+                              int D, int causal, int variant, void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: D must be 64 or 128");
-  if (S % 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: S must be a multiple of 128");
+  if (S % 128 || S <= 0 || BH <= 0) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: S must be a positive multiple of 128");
+  if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: variant must be 0 or 1");
+  const void* ptrs[] = {q_f16, k_f16, v_bf16, dO_bf16, lse_f32, delta_f32, dq_f32, dk_f32, dv_f32};
+  for (const void* ptr : ptrs)
+    if (!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15)) return qa_fail(QA_ERR_ALIGN, "qa_bf16_bwd: null or not 16-byte aligned pointer");
+  if (causal && !dO_f32) return qa_fail(QA_ERR_ALIGN, "qa_bf16_bwd: causal needs dO_f32");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128 && variant == 0) {
+    int r = launch_bf16_bwd_ws(q_f16, k_f16, v_bf16, dO_bf16, (const float*)lse_f32, (const float*)delta_f32, (float*)dq_f32,
+                               (float*)dk_f32, (float*)dv_f32, BH, S, causal, st);
+    if (r || !causal) return r;
+    dim3 g2((S + 1) / 2, BH);
+    bf16_bwd_row0_fixup_kernel<<<g2, 256, 0, st>>>((const float*)dO_f32, (float*)dv_f32, S, D);
+    return qa_check_launch("qa_bf16_bwd(row0)");
+  }
   Bf16BwdParams p;
   p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32;
   p.dq = (float*)dq_f32; p.dk = (float*)dk_f32; p.dv = (float*)dv_f32;
   p.S = S; p.causal = causal;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
-  cudaStream_t st = (cudaStream_t)stream;
   return D == 128 ? launch_bf16_bwd<128, 1>(q_f16, k_f16, v_bf16, dO_bf16, (const float*)dO_f32, p, BH, st)
                   : launch_bf16_bwd<64, 2>(q_f16, k_f16, v_bf16, dO_bf16, (const float*)dO_f32, p, BH, st);
+}
+
+// q, k fp16; v bf16; dO_bf16 = bf16 copy of dO (from qa_bwd_delta); dO_f32 the original; lse, delta fp32 [BH*S];
+// dq (zero-initialised), dk, dv: fp32 [BH*S, D].
+extern "C" int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                           const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
+                           int D, int causal, void* stream) {
+  return qa_bf16_bwd_ex(q_f16, k_f16, v_bf16, dO_bf16, dO_f32, lse_f32, delta_f32, dq_f32, dk_f32, dv_f32, BH, S, D, causal, 0, stream);
 }

@@ -288,9 +288,9 @@ def jvp_fwd(q, k, v, tq, tk, tv, nsplit: int = 2):
     return O, tO, lse
 
 
-def bf16_bwd(q, k, v, O, lse, causal: bool, dO):
-    """Recompute backward of the bf16 path (qa_bwd_delta + qa_bf16_bwd).  q,k fp16; v bf16; O, dO fp32 [B,H,S,D];
-    lse fp32 [B*H,S].  Returns fp32 (dq, dk, dv) [B,H,S,D]."""
+def bf16_bwd(q, k, v, O, lse, causal: bool, dO, variant: int = 0):
+    """Recompute backward of the bf16 path (qa_bwd_delta + qa_bf16_bwd_ex).  q,k fp16; v bf16; O, dO fp32 [B,H,S,D];
+    lse fp32 [B*H,S].  Returns fp32 (dq, dk, dv) [B,H,S,D].  variant: 0 = default kernels, 1 = phase-sequential kernel."""
     _need_cuda(q, k, v, O, lse, dO)
     B, H, S, D = q.shape
     assert k.shape[2] == S, "backward is self-attention only (LEDGER I-11)"
@@ -304,7 +304,7 @@ def bf16_bwd(q, k, v, O, lse, causal: bool, dO):
     dv = torch.empty_like(dq)
     L = _lib.lib()
     with torch.cuda.device(q.device), _timed("bf16_bwd"):
-        _lib.check(L.qa_bf16_bwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dO_bf16), _lib.ptr(dO), _lib.ptr(lse),
-                                 _lib.ptr(delta), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), B * H, S, D, 1 if causal else 0,
-                                 _lib.cur_stream()), "qa_bf16_bwd")
+        _lib.check(L.qa_bf16_bwd_ex(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dO_bf16), _lib.ptr(dO), _lib.ptr(lse),
+                                    _lib.ptr(delta), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), B * H, S, D, 1 if causal else 0,
+                                    int(variant), _lib.cur_stream()), "qa_bf16_bwd")
     return dq, dk, dv
