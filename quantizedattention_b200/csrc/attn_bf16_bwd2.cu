@@ -1,6 +1,7 @@
 // Warp-specialised recompute backward of the bf16 path for D = 128 (reference
 // attention_bf16.py:361-444 under the 8-LEDGER contract B-4..B-8).  Same arithmetic as bf16_bwd_kernel
-// (attn_bf16_bwd.cu): P rounded to bf16 for dV, dS = P*(dP - delta) from the fp32 P rounded to fp16, fp32 accumulation.
+// (attn_bf16_bwd.cu): P rounded to bf16 for dV, dS = P*(dP - delta) in fp16 (P and dP - delta rounded to fp16, product
+// rounded to fp16: 3 x 2^-12 relative where the sequential kernel has 2^-12), fp32 accumulation.
 //
 // One CTA = one 128-key tile j of one (batch, head), looping over the query tiles i (k-outer, as the reference).  The
 // logits are computed TRANSPOSED so that the probabilities can feed the tensor core from TMEM:
@@ -8,12 +9,12 @@
 //   dP^T = V_j dO_i^T       (bf16)  -> TMEM B
 //   dV_j += P^T dO_i        (bf16)  P^T read from TMEM (written over S^T by the compute warps)  -> TMEM, resident
 //   dK_j += dS^T Q_i        (fp16)  dS^T from shared memory (K-major A)                          -> TMEM, resident
-//   dQ_i^T = K_j^T dS^T     (fp16)  both operands MN-major, -> TMEM B [lane = d, column = query]: a drain warp's
-//                                   red.global.add then covers 32 consecutive floats of one dQ row (one 128 B line)
-// Shared memory: K, V, two stages of Q and dO, dS^T = 7 x 32 KB (P never touches shared memory: that is what makes
-// room for the second Q / dO stage at D = 128).
-// Roles (16 warps, setmaxnreg): warps 0..3 drain dQ^T, 4..11 compute P^T and dS^T (two per TMEM lane quadrant, 64 query
-// columns each), 12 issues tcgen05.mma, 13 issues TMA.  Issue order of the MMA warp per query tile n:
+//   dQ_i  = dS K_j          (fp16)  dS^T as MN-major A, K as MN-major B -> TMEM B [lane = query, column = d], staged
+//                                   through shared memory and added to global dQ by TMA reduce-add
+// Shared memory (7 x 32 KB): K, V, two stages of Q, one of dO (its life ends with dV, early in the tile), dS^T, the dQ
+// staging tile.  P never touches shared memory.  The dV / dK epilogue reuses the Q / dO / dS^T space for TMA stores.
+// Roles (16 warps, setmaxnreg): warps 0..3 drain dQ, 4..11 compute P^T and dS^T (two per TMEM lane quadrant, 64 query
+// columns each), 12 issues tcgen05.mma, 13 issues the TMA loads.  Issue order of the MMA warp per query tile n:
 //   dV(n) | S(n+1) | dQ(n), dK(n) | dP(n+1)
 // so that the compute warps' dS(n) phase runs under dV(n) / S(n+1), their P(n+1) phase under dQ(n) / dK(n), and the dQ
 // drain under dK(n).
@@ -25,41 +26,60 @@ namespace qa {
 struct Bf16BwdParams2 {
   const float* lse;      // [BH*S] log2 domain
   const float* delta;    // [BH*S]
-  float *dq, *dk, *dv;   // fp32 [BH*S, D]; dq zero-initialised by the caller
   int S, causal;
   float sm_scale, qk_scale;
+  long long* dbg;        // development library only: [CTA][64] globaltimer stamps (tools/timeline_bf16_bwd.py)
 };
+
+#ifdef QA_DEV_TIMELINE
+#define QA_TL2(slot)                                                                                      \
+  do {                                                                                                    \
+    if (p.dbg != nullptr) {                                                                               \
+      long long t_;                                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
+      p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = t_;                            \
+    }                                                                                                     \
+  } while (0)
+#else
+#define QA_TL2(slot) do { } while (0)
+#endif
 
 struct Bf16Bwd2Smem {
   static constexpr int kTile = 128 * 128 * 2;
   static constexpr int off_k = 0;
   static constexpr int off_v = kTile;
-  static constexpr int off_q = 2 * kTile;          // 2 stages
-  static constexpr int off_do = 4 * kTile;         // 2 stages
-  static constexpr int off_ds = 6 * kTile;
+  static constexpr int off_q = 2 * kTile;          // 2 stages; epilogue: dV staging (64 KB fp32)
+  static constexpr int off_do = 4 * kTile;         // 1 stage;  epilogue: dK staging (64 KB fp32, with the dS^T tile)
+  static constexpr int off_ds = 5 * kTile;
+  static constexpr int off_st = 6 * kTile;         // dQ staging: two [128 query][32 d] fp32 atoms (128 B swizzle)
   static constexpr int off_ld = 7 * kTile;         // [stage][lse | delta][128] fp32
   static constexpr int off_bar = off_ld + 2048;
   static constexpr int used = off_bar + 160;
   static constexpr int total = 232448;             // everything an SM has; the align-up pad must fit in total - used
 };
 
-enum Bf16Bwd2Bar { KV_FULL = 0, Q_FULL0, Q_FULL1, DO_FULL0, DO_FULL1, Q_FREE0, Q_FREE1, DO_FREE0, DO_FREE1, S_FULL, P_READY,
-                   DP_FULL, DS_READY, DS_FREE, DQ_FULL, DQ_FREE, ACC_FULL, kNumBars };
+enum Bf16Bwd2Bar { KV_FULL = 0, Q_FULL0, Q_FULL1, DO_FULL, Q_FREE0, Q_FREE1, DO_FREE, S_FULL, P_READY, DP_FULL, DS_READY, DS_FREE,
+                   DQ_FULL, DQ_FREE, ACC_FULL, kNumBars };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void red_add_f32(float* addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
 }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 __global__ void __launch_bounds__(512, 1)
 bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, Bf16BwdParams2 p) {
+                   const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dk,
+                   const __grid_constant__ CUtensorMap tm_dv, Bf16BwdParams2 p) {
   using L = Bf16Bwd2Smem;
   constexpr int D = 128;
-  constexpr int kAtom = 128 * 128;                     // one 64-column (128 B) swizzle atom column of 128 rows
+  constexpr int kAtom = 128 * 128;                     // 128 rows x 128 B: one swizzle-atom column (64 x 16 bit or 32 x fp32)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   if ((int)(smem - smem_raw) > L::total - L::used) __trap();
@@ -75,6 +95,10 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const size_t head_row0 = (size_t)bh * p.S;
 
   if (tid == 0) {
+    QA_TL2(0);
+#ifdef QA_DEV_TIMELINE
+    if (p.dbg != nullptr) { uint32_t sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + 15] = sm_; }
+#endif
     for (int b = 0; b < kNumBars; ++b) mbar_init(&bars[b], (b == P_READY || b == DS_READY) ? 8 : (b == DQ_FREE ? 4 : 1));
     fence_mbar_init();
   }
@@ -83,139 +107,180 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_base_s;
+  const uint32_t smem_base = smem_u32(smem);
+  if (tid == 0) QA_TL2(1);
   constexpr uint32_t tA = 0, tB = 128, tDV = 256, tDK = 384;
 
   if (warp < 4) {
-    // =========================== dQ^T drain: lane = d, column = query ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    const int d = warp * 32 + lane;
+    // =========================== dQ drain: lane = query, column = d ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int qrow = warp * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16) + tB;
     const float sm = p.sm_scale;
     for (int n = 0; n < nt; ++n) {
-      float* dst = p.dq + (head_row0 + (size_t)(i0 + n) * 128) * D + d;
+      const int r0 = (int)head_row0 + (i0 + n) * 128 + warp * 32;
+      uint32_t r[128];
       mbar_wait(&bars[DQ_FULL], n & 1);
       tc_fence_after();
+      if (tid == 0 && n == 4) QA_TL2(26);
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t r[64];
-        tmem_ld64(lane_addr + ch * 64, r);
-        tmem_ld_wait();
-        if (ch == 1) {                                 // TMEM B is free for dP of the next tile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[DQ_FREE]);
+      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();                               // every dQ column is in registers: TMEM B is free for dP of the next tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[DQ_FREE]);
+      if (tid == 0 && n == 4) QA_TL2(27);
+      // each warp stages its own 32 query rows ([32 rows][32 d] fp32 = 4 KB of a swizzled atom) and reduces them itself
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t atom = smem_base + L::off_st + (c & 1) * kAtom;
+        if (lane == 0) tma_store_wait_read1();         // this warp's reduce-add of two rounds ago has read the atom rows
+        __syncwarp();
+#pragma unroll
+        for (int x = 0; x < 32; x += 4)
+          sts128f(atom + swz128(qrow, x * 4), __uint_as_float(r[c * 32 + x]) * sm, __uint_as_float(r[c * 32 + x + 1]) * sm,
+                  __uint_as_float(r[c * 32 + x + 2]) * sm, __uint_as_float(r[c * 32 + x + 3]) * sm);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tm_dq, smem + L::off_st + (c & 1) * kAtom + warp * 4096, c * 32, r0);
+          tma_store_commit();
         }
-#pragma unroll
-        for (int c = 0; c < 64; ++c) red_add_f32(dst + (size_t)(ch * 64 + c) * D, __uint_as_float(r[c]) * sm);
       }
+      if (tid == 0 && n == 4) QA_TL2(28);
     }
+    if (lane == 0) tma_store_wait_read();
+    if (tid == 0) QA_TL2(13);
   } else if (warp < 12) {
     // =========================== compute: P^T (-> TMEM) and dS^T (-> shared memory) ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int cw = warp - 4;
     const int quad = cw & 3, half = cw >> 2;
     const int row = quad * 32 + lane;                  // key inside the tile = TMEM lane
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
-    const uint32_t ds_base = smem_u32(smem) + L::off_ds + half * kAtom;
+    const uint32_t ds_base = smem_base + L::off_ds + half * kAtom;
     const float qk = p.qk_scale;
     for (int n = 0; n < nt; ++n) {
       const int st = n & 1;
       const uint32_t ph = n & 1;
       const bool diag = p.causal && (n == 0);          // i == j: the only tile that needs the mask
-      const float* lse_t = ld_s + st * 256 + half * 64;
-      const float* dl_t = lse_t + 128;
-      float pf[64];
+      const uint32_t lse_a = smem_base + L::off_ld + (st * 256 + half * 64) * 4;
+      const uint32_t dl_a = lse_a + 512;
+      __half2 pk[32];                                  // P as packed fp16 (kept for the dS phase)
       mbar_wait(&bars[Q_FULL0 + st], (n >> 1) & 1);    // lse / delta of this tile have landed
       mbar_wait(&bars[S_FULL], ph);
       tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t rs[32], w[16];
-        tmem_ld32(lane_addr + tA + half * 64 + ch * 32, rs);
+      if (tid == 128 && n == 0) QA_TL2(7);
+      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 0);
+      {
+        uint32_t rs[64];
+        tmem_ld32(lane_addr + tA + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
+        tmem_ld32(lane_addr + tA + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(lse_t + ch * 32 + c);
-          float e0 = ex2_approx(fmaf(__uint_as_float(rs[c + 0]), qk, -l4.x));     // attention_bf16.py:391-392
-          float e1 = ex2_approx(fmaf(__uint_as_float(rs[c + 1]), qk, -l4.y));
-          float e2 = ex2_approx(fmaf(__uint_as_float(rs[c + 2]), qk, -l4.z));
-          float e3 = ex2_approx(fmaf(__uint_as_float(rs[c + 3]), qk, -l4.w));
-          if (diag) {                                  // strict causal: key < query keeps its weight (row 0 of the head: fixup kernel)
-            const int q0 = half * 64 + ch * 32 + c;
-            if (row >= q0 + 0) e0 = 0.f;
-            if (row >= q0 + 1) e1 = 0.f;
-            if (row >= q0 + 2) e2 = 0.f;
-            if (row >= q0 + 3) e3 = 0.f;
+        for (int ch = 0; ch < 4; ++ch) {               // 16 queries per TMEM store
+          uint32_t w[8];
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            const int x = ch * 16 + c;
+            const float4 l4 = lds128f(lse_a + x * 4);
+            float e0 = ex2_approx(fmaf(__uint_as_float(rs[x + 0]), qk, -l4.x));     // attention_bf16.py:391-392
+            float e1 = ex2_approx(fmaf(__uint_as_float(rs[x + 1]), qk, -l4.y));
+            float e2 = ex2_approx(fmaf(__uint_as_float(rs[x + 2]), qk, -l4.z));
+            float e3 = ex2_approx(fmaf(__uint_as_float(rs[x + 3]), qk, -l4.w));
+            if (diag) {                                // strict causal: key < query keeps its weight (row 0 of the head: fixup kernel)
+              const int q0 = half * 64 + x;
+              if (row >= q0 + 0) e0 = 0.f;
+              if (row >= q0 + 1) e1 = 0.f;
+              if (row >= q0 + 2) e2 = 0.f;
+              if (row >= q0 + 3) e3 = 0.f;
+            }
+            pk[x / 2 + 0] = __floats2half2_rn(e0, e1);
+            pk[x / 2 + 1] = __floats2half2_rn(e2, e3);
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(e0, e1), b1 = __floats2bfloat162_rn(e2, e3);
+            w[c / 2 + 0] = *reinterpret_cast<uint32_t*>(&b0);
+            w[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&b1);
           }
-          pf[ch * 32 + c + 0] = e0; pf[ch * 32 + c + 1] = e1; pf[ch * 32 + c + 2] = e2; pf[ch * 32 + c + 3] = e3;
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(e0, e1), b1 = __floats2bfloat162_rn(e2, e3);
-          w[c / 2 + 0] = *reinterpret_cast<uint32_t*>(&b0);
-          w[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&b1);
+          tmem_st8(lane_addr + tA + half * 64 + ch * 8, w);   // bf16 pairs over the S^T columns this warp has already read
         }
-        tmem_st16(lane_addr + tA + half * 64 + ch * 16, w);   // bf16 pairs over the S^T columns this warp has already read
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[P_READY]);
+      if (tid == 128 && n == 0) QA_TL2(8);
+      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 1);
 
       mbar_wait(&bars[DP_FULL], ph);
       tc_fence_after();
-      if (n > 0) mbar_wait(&bars[DS_FREE], (n - 1) & 1);       // dQ / dK of the previous tile have read the dS^T buffer
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t rp[32];
-        tmem_ld32(lane_addr + tB + half * 64 + ch * 32, rp);
+      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 2);
+      {
+        uint32_t rp[64];
+        tmem_ld32(lane_addr + tB + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&rp[0]));
+        tmem_ld32(lane_addr + tB + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rp[32]));
+        if (n > 0) mbar_wait(&bars[DS_FREE], (n - 1) & 1);     // dQ / dK of the previous tile have read the dS^T buffer
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 8; ++g) {                  // 8 queries = one 16 B store
           uint32_t wd[4];
 #pragma unroll
           for (int e = 0; e < 4; e += 2) {
-            const int c = g * 8 + e * 2;
-            const float4 d4 = *reinterpret_cast<const float4*>(dl_t + ch * 32 + c);
-            const float s0 = pf[ch * 32 + c + 0] * (__uint_as_float(rp[c + 0]) - d4.x);     // dS = P * (dP - delta)
-            const float s1 = pf[ch * 32 + c + 1] * (__uint_as_float(rp[c + 1]) - d4.y);
-            const float s2 = pf[ch * 32 + c + 2] * (__uint_as_float(rp[c + 2]) - d4.z);
-            const float s3 = pf[ch * 32 + c + 3] * (__uint_as_float(rp[c + 3]) - d4.w);
-            __half2 h0 = __floats2half2_rn(s0, s1), h1 = __floats2half2_rn(s2, s3);
+            const int x = g * 8 + e * 2;
+            const float4 d4 = lds128f(dl_a + x * 4);
+            // dS = P * (dP - delta): both factors rounded to fp16, product rounded to fp16 (3 x 2^-12 relative)
+            const __half2 t01 = __floats2half2_rn(__uint_as_float(rp[x + 0]) - d4.x, __uint_as_float(rp[x + 1]) - d4.y);
+            const __half2 t23 = __floats2half2_rn(__uint_as_float(rp[x + 2]) - d4.z, __uint_as_float(rp[x + 3]) - d4.w);
+            __half2 h0 = __hmul2(pk[x / 2 + 0], t01), h1 = __hmul2(pk[x / 2 + 1], t23);
             wd[e + 0] = *reinterpret_cast<uint32_t*>(&h0);
             wd[e + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          sts128(ds_base + swz128(row, (ch * 32 + g * 8) * 2), wd[0], wd[1], wd[2], wd[3]);
+          sts128(ds_base + swz128(row, g * 16), wd[0], wd[1], wd[2], wd[3]);
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[DS_READY]);
+      if (tid == 128 && n == 0) QA_TL2(9);
+      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 3);
+      if (tid == 128 && n == nt - 1) QA_TL2(10);
     }
-    // ---- epilogue: dV_j, dK_j accumulators from TMEM (lane = key)
+    // ---- epilogue: dV_j, dK_j accumulators (lane = key) -> swizzled fp32 staging over the Q / dO / dS^T tiles -> TMA store
     mbar_wait(&bars[ACC_FULL], 0);
     tc_fence_after();
-    const size_t krow = head_row0 + (size_t)j * 128 + row;
-    float* dv_dst = p.dv + krow * D + half * 64;
-    float* dk_dst = p.dk + krow * D + half * 64;
+    if (tid == 128) QA_TL2(11);
     const float sm = p.sm_scale;
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + tDV + half * 64 + ch * 32, r);
+    for (int m = 0; m < 2; ++m) {
+      uint32_t r[64];
+      tmem_ld32(lane_addr + (m ? tDK : tDV) + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(lane_addr + (m ? tDK : tDV) + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
       tmem_ld_wait();
+      const float sc = m ? sm : 1.0f;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4)
-        *reinterpret_cast<float4*>(dv_dst + ch * 32 + c) =
-            make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-      tmem_ld32(lane_addr + tDK + half * 64 + ch * 32, r);
-      tmem_ld_wait();
+      for (int a = 0; a < 2; ++a) {
+        const uint32_t atom = smem_base + (m ? L::off_do : L::off_q) + (half * 2 + a) * kAtom;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4)
-        *reinterpret_cast<float4*>(dk_dst + ch * 32 + c) =
-            make_float4(__uint_as_float(r[c]) * sm, __uint_as_float(r[c + 1]) * sm, __uint_as_float(r[c + 2]) * sm,
-                        __uint_as_float(r[c + 3]) * sm);
+        for (int c = 0; c < 32; c += 4)
+          sts128f(atom + swz128(row, c * 4), __uint_as_float(r[a * 32 + c]) * sc, __uint_as_float(r[a * 32 + c + 1]) * sc,
+                  __uint_as_float(r[a * 32 + c + 2]) * sc, __uint_as_float(r[a * 32 + c + 3]) * sc);
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(3, 256);
+    if (tid == 128) {
+      const int k0 = (int)head_row0 + j * 128;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        tma_store_2d(&tm_dv, smem + L::off_q + a * kAtom, a * 32, k0);
+        tma_store_2d(&tm_dk, smem + L::off_do + a * kAtom, a * 32, k0);
+      }
+      tma_store_commit();
+      tma_store_wait_read();
+      QA_TL2(12);
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 12) {
       // =========================== tcgen05.mma issue ===========================
       if (elect_one()) {
@@ -223,8 +288,9 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         constexpr uint32_t id_dp = umma_idesc(1, 1, 1, 0, 0, 128, 128);     // dP^T: bf16, V x dO
         constexpr uint32_t id_dv = umma_idesc(1, 1, 1, 0, 1, 128, D);       // dV  : bf16, P^T (TMEM) x dO (MN-major)
         constexpr uint32_t id_dk = umma_idesc(1, 0, 0, 0, 1, 128, D);       // dK  : f16, dS^T (K-major) x Q (MN-major)
-        constexpr uint32_t id_dq = umma_idesc(1, 0, 0, 1, 1, 128, 128);     // dQ^T: f16, K^T (MN-major) x dS^T (MN-major)
+        constexpr uint32_t id_dq = umma_idesc(1, 0, 0, 1, 1, 128, D);       // dQ  : f16, dS^T (MN-major: M = query) x K (MN-major)
         const uint32_t a_k = smem_u32(smem + L::off_k), a_v = smem_u32(smem + L::off_v), a_ds = smem_u32(smem + L::off_ds);
+        const uint32_t a_do = smem_u32(smem + L::off_do);
         auto issue_s = [&](int st) {
           const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);
 #pragma unroll
@@ -234,8 +300,7 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           umma_commit(&bars[S_FULL]);
         };
-        auto issue_dp = [&](int st) {
-          const uint32_t a_do = smem_u32(smem + L::off_do + st * L::kTile);
+        auto issue_dp = [&]() {
 #pragma unroll
           for (int k = 0; k < D / 16; ++k) {
             const uint32_t o = (k >> 2) * kAtom + (k & 3) * 32;
@@ -246,30 +311,39 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         mbar_wait(&bars[KV_FULL], 0);
         mbar_wait(&bars[Q_FULL0], 0);
         tc_fence_after();
+        QA_TL2(2);
         issue_s(0);
-        mbar_wait(&bars[DO_FULL0], 0);
-        issue_dp(0);
+        mbar_wait(&bars[DO_FULL], 0);
+        issue_dp();
         for (int n = 0; n < nt; ++n) {
           const int st = n & 1;
-          const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile), a_do = smem_u32(smem + L::off_do + st * L::kTile);
+          const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);
           mbar_wait(&bars[P_READY], n & 1);
           tc_fence_after();
+          if (n == 0) QA_TL2(3);
+          if (n == 1) QA_TL2(5);
+          if (n == 2) QA_TL2(6);
+          if (n == 4) QA_TL2(16);
+          if (n == 5) QA_TL2(21);
 #pragma unroll
           for (int k = 0; k < 8; ++k)                           // contraction over the 128 queries, 16 per instruction
             umma_f16_ts(tbase + tDV, tbase + tA + (k >> 2) * 64 + (k & 3) * 8, umma_smem_desc(a_do + k * 2048, kAtom, 1024, kSwz128),
                         id_dv, (n > 0) || (k > 0));
-          umma_commit(&bars[DO_FREE0 + st]);
+          umma_commit(&bars[DO_FREE]);
           if (n + 1 < nt) {
             mbar_wait(&bars[Q_FULL0 + (st ^ 1)], ((n + 1) >> 1) & 1);
             tc_fence_after();
             issue_s(st ^ 1);                                    // overwrites P^T(n): tcgen05.mma of one thread execute in order
           }
+          if (n == 4) QA_TL2(17);
           mbar_wait(&bars[DS_READY], n & 1);
           tc_fence_after();
+          if (n == 0) QA_TL2(4);
+          if (n == 4) QA_TL2(18);
 #pragma unroll
           for (int k = 0; k < 8; ++k)                           // contraction over the 128 keys
-            umma_f16_ss(tbase + tB, umma_smem_desc(a_k + k * 2048, kAtom, 1024, kSwz128),
-                        umma_smem_desc(a_ds + k * 2048, kAtom, 1024, kSwz128), id_dq, k > 0);
+            umma_f16_ss(tbase + tB, umma_smem_desc(a_ds + k * 2048, kAtom, 1024, kSwz128),
+                        umma_smem_desc(a_k + k * 2048, kAtom, 1024, kSwz128), id_dq, k > 0);
           umma_commit(&bars[DQ_FULL]);
 #pragma unroll
           for (int k = 0; k < 8; ++k)                           // contraction over the 128 queries
@@ -277,18 +351,20 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                         umma_smem_desc(a_q + k * 2048, kAtom, 1024, kSwz128), id_dk, (n > 0) || (k > 0));
           umma_commit(&bars[Q_FREE0 + st]);
           umma_commit(&bars[DS_FREE]);
+          if (n == 4) QA_TL2(19);
           if (n + 1 < nt) {
-            mbar_wait(&bars[DO_FULL0 + (st ^ 1)], ((n + 1) >> 1) & 1);
+            mbar_wait(&bars[DO_FULL], (n + 1) & 1);
             mbar_wait(&bars[DQ_FREE], n & 1);
             tc_fence_after();
-            issue_dp(st ^ 1);
+            if (n == 4) QA_TL2(20);
+            issue_dp();
           }
         }
         umma_commit(&bars[ACC_FULL]);
       }
       __syncwarp();
     } else if (warp == 13) {
-      // =========================== TMA issue ===========================
+      // =========================== TMA loads ===========================
       if (elect_one()) {
         mbar_expect_tx(&bars[KV_FULL], 2 * L::kTile);
 #pragma unroll
@@ -305,10 +381,10 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_q + st * L::kTile + a * kAtom, &tm_q, &bars[Q_FULL0 + st], a * 64, r0);
           bulk_load_1d(ld_s + st * 256, p.lse + r0, 512, &bars[Q_FULL0 + st]);
           bulk_load_1d(ld_s + st * 256 + 128, p.delta + r0, 512, &bars[Q_FULL0 + st]);
-          if (n >= 2) mbar_wait(&bars[DO_FREE0 + st], ((n >> 1) - 1) & 1);
-          mbar_expect_tx(&bars[DO_FULL0 + st], L::kTile);
+          if (n >= 1) mbar_wait(&bars[DO_FREE], (n - 1) & 1);  // dV of the previous tile, the last reader of the dO tile
+          mbar_expect_tx(&bars[DO_FULL], L::kTile);
 #pragma unroll
-          for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_do + st * L::kTile + a * kAtom, &tm_do, &bars[DO_FULL0 + st], a * 64, r0);
+          for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_do + a * kAtom, &tm_do, &bars[DO_FULL], a * 64, r0);
         }
       }
       __syncwarp();
@@ -317,29 +393,51 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 12) tmem_dealloc<512>(tbase);
+  if (tid == 0) QA_TL2(14);
 }
+
+#ifdef QA_DEV_TIMELINE
+static void* g_bf16_bwd_dbg = nullptr;
+// Development library only (include/qattn_dev.h, tools/timeline_bf16_bwd.py): per-CTA globaltimer stamps of subsequent
+// qa_bf16_bwd launches ([CTAs][64] int64); NULL = off.
+extern "C" int qa_debug_set_bf16_bwd_timeline(void* buf) {
+  g_bf16_bwd_dbg = buf;
+  return 0;
+}
+#endif
 
 int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* lse, const float* delta,
                        float* dq, float* dk, float* dv, int BH, int S, int causal, cudaStream_t st) {
   using L = Bf16Bwd2Smem;
   constexpr int D = 128;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
   uint64_t dims[2] = {(uint64_t)D, (uint64_t)BH * S};
   uint64_t str[1] = {(uint64_t)D * 2};
   uint32_t box[2] = {64, 128};
+  uint64_t str32[1] = {(uint64_t)D * 4};
+  uint32_t box32[2] = {32, 128};
+  uint32_t boxq[2] = {32, 32};                        // dQ: one drain warp's 32 query rows
   int rc;
   if ((rc = qa_make_tmap(&tq, q, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tdo, do_bf16, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
+  if ((rc = qa_make_tmap(&tdq, dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, boxq, 3))) return rc;
+  if ((rc = qa_make_tmap(&tdk, dk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, box32, 3))) return rc;
+  if ((rc = qa_make_tmap(&tdv, dv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, box32, 3))) return rc;
   Bf16BwdParams2 p;
-  p.lse = lse; p.delta = delta; p.dq = dq; p.dk = dk; p.dv = dv; p.S = S; p.causal = causal;
+  p.lse = lse; p.delta = delta; p.S = S; p.causal = causal;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+#ifdef QA_DEV_TIMELINE
+  p.dbg = (long long*)g_bf16_bwd_dbg;
+#else
+  p.dbg = nullptr;
+#endif
   cudaError_t e = cudaFuncSetAttribute(bf16_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(S / 128, BH);
-  bf16_bwd_ws_kernel<<<grid, 512, L::total, st>>>(tq, tk, tv, tdo, p);
+  bf16_bwd_ws_kernel<<<grid, 512, L::total, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   return qa_check_launch("qa_bf16_bwd(ws)");
 }
 

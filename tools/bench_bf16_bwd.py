@@ -30,6 +30,15 @@ def run(B, H, S, D, causal, variant):
 
 if __name__ == "__main__":
     out = []
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":       # 37 heads: whole waves of 148 CTAs; time per wave = overhead + tiles * t_tile
+        for S in (1024, 2048, 4096, 8192):
+            r = run(1, 37, S, 128, 0, 0)
+            waves = 37 * (S // 128) / 148
+            r["us_per_wave"] = r["ms_kernel"] * 1e3 / waves
+            r["tiles_per_cta"] = S // 128
+            out.append(r)
+        print(json.dumps(out, indent=1))
+        sys.exit(0)
     for variant in (0, 1):
         out.append(run(4, 16, 4096, 128, 1, variant))
         out.append(run(1, 32, 8192, 128, 0, variant))
