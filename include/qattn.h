@@ -133,6 +133,10 @@ int qa_bf16_fwd(const void* q_f16, const void* k_f16, const void* v_bf16, void* 
  * maximum, qa_bf16_fwd uses 8. */
 int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH, int Sq,
                    int Sk, int D, int causal, int nsplit, float rescale_tau, void* stream);
+/* Ragged sequences (the reference's hl.tile clamps the last tile, attention_bf16.py:170,201): buffers zero-padded per head
+ * to Sq / Sk (multiples of 128); keys [Sk_valid, Sk) have weight exactly 0; Sk - 128 < Sk_valid <= Sk. */
+int qa_bf16_fwd_ragged(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH, int Sq,
+                       int Sk, int Sk_valid, int D, int causal, int nsplit, float rescale_tau, void* stream);
 int qa_bf16_bwd(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
                 const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
                 int causal, void* stream);
@@ -143,10 +147,22 @@ int qa_bf16_bwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, con
                    const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S, int D,
                    int causal, int variant, void* stream);
 
+/* Same for a ragged sequence padded to S: rows [S_valid, S) are padding.  The caller pads dO (and O) with zeros and lse with a
+ * large finite value, so padded query rows get P = 0; padded keys get P = 0 in the kernel. */
+int qa_bf16_bwd_ragged(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                       const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
+                       int S_valid, int D, int causal, int variant, void* stream);
+
 /* ---- JVP: helion_attention_jvp_forward_fp32, attention_jvp.py:33-195 (operands pre-cast to bf16); D in {64,128} ---- */
 int qa_jvp_fwd(const void* q_bf16, const void* tq_bf16, const void* k_bf16, const void* tk_bf16, const void* v_bf16,
                const void* tv_bf16, void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit,
                void* stream);
+
+/* Ragged sequences (attention_jvp.py:120,137): buffers zero-padded per head to Sq / Sk (multiples of 128), keys
+ * [Sk_valid, Sk) have weight exactly 0. */
+int qa_jvp_fwd_ragged(const void* q_bf16, const void* tq_bf16, const void* k_bf16, const void* tk_bf16, const void* v_bf16,
+                      const void* tv_bf16, void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int Sk_valid, int D,
+                      int nsplit, void* stream);
 
 #ifdef __cplusplus
 }

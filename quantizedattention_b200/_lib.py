@@ -35,9 +35,12 @@ SIGNATURES = {
     "qa_cast_f32": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "qa_bf16_fwd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "qa_bf16_fwd_ex": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_float, c_void_p]),
+    "qa_bf16_fwd_ragged": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
     "qa_jvp_fwd": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
+    "qa_jvp_fwd_ragged": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_void_p]),
     "qa_bf16_bwd": (c_int, [c_void_p] * 10 + [c_int] * 4 + [c_void_p]),
     "qa_bf16_bwd_ex": (c_int, [c_void_p] * 10 + [c_int] * 5 + [c_void_p]),
+    "qa_bf16_bwd_ragged": (c_int, [c_void_p] * 10 + [c_int] * 6 + [c_void_p]),
 }
 
 

@@ -33,6 +33,7 @@ struct Bf16BwdParams {
   const float* delta;    // [BH*S]
   float *dq, *dk, *dv;   // fp32 [BH*S, D]; dq zero-initialised by the caller
   int S, causal;
+  int S_valid;           // rows [S_valid, S) of every head are zero padding (ragged sequence): padded keys get P = 0
   float sm_scale, qk_scale;
 };
 
@@ -138,6 +139,7 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float lse = p.lse[qrow];
       const float dlt = p.delta[qrow];
       const bool diag = p.causal && (i == j);
+      const bool tailk = (j + 1) * 128 > p.S_valid;            // this CTA's key tile is the ragged last one
       mbar_wait(&sd_full, ph);
       tc_fence_after();
       const float2 qk2 = make_float2(p.qk_scale, p.qk_scale), nlse2 = make_float2(-lse, -lse), ndlt2 = make_float2(-dlt, -dlt);
@@ -158,8 +160,8 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               float2 pv = make_float2(ex2_approx(ex.x), ex2_approx(ex.y));                       // :391-392
               if (decltype(masked)::value) {
                 const int key = j * 128 + half * 64 + ch * 32 + c;
-                if ((diag && key >= qi) || qi == 0) pv.x = 0.f;                                  // strict causal, weight 0; row 0: fixup
-                if ((diag && key + 1 >= qi) || qi == 0) pv.y = 0.f;
+                if ((diag && key >= qi) || (p.causal && qi == 0) || key >= p.S_valid) pv.x = 0.f;          // strict causal, weight 0; row 0: fixup
+                if ((diag && key + 1 >= qi) || (p.causal && qi == 0) || key + 1 >= p.S_valid) pv.y = 0.f;  // ragged: padded keys
               }
               const float2 ds = __fmul2_rn(pv, __fadd2_rn(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), ndlt2));   // dS = P*(dP - delta)
               __nv_bfloat162 pb = __float22bfloat162_rn(pv);
@@ -173,7 +175,7 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       };
-      if (p.causal && (diag || i == 0)) compute(std::true_type{}); else compute(std::false_type{});
+      if ((p.causal && (diag || i == 0)) || tailk) compute(std::true_type{}); else compute(std::false_type{});
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -228,10 +230,10 @@ bf16_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 // causal row 0 attends uniformly to ALL keys (LEDGER B-1): dV[k] += dO[0] / S for every key, no dS.
-__global__ void bf16_bwd_row0_fixup_kernel(const float* __restrict__ dO, float* __restrict__ dv, int S, int D) {
+__global__ void bf16_bwd_row0_fixup_kernel(const float* __restrict__ dO, float* __restrict__ dv, int S, int S_valid, int D) {
   const int bh = blockIdx.y;
   const int k = blockIdx.x * (blockDim.x / D) + threadIdx.x / D, d = threadIdx.x % D;
-  if (k < S) dv[((size_t)bh * S + k) * D + d] += dO[(size_t)bh * S * D + d] / (float)S;
+  if (k < S_valid) dv[((size_t)bh * S + k) * D + d] += dO[(size_t)bh * S * D + d] / (float)S_valid;
 }
 
 template <int D, int STAGES>
@@ -257,7 +259,7 @@ static int launch_bf16_bwd(const void* q, const void* k, const void* v, const vo
   if (p.causal) {
     const int kpb = 256 / D;
     dim3 g2((p.S + kpb - 1) / kpb, BH);
-    bf16_bwd_row0_fixup_kernel<<<g2, 256, 0, st>>>(dO_f32, p.dv, p.S, D);
+    bf16_bwd_row0_fixup_kernel<<<g2, 256, 0, st>>>(dO_f32, p.dv, p.S, p.S_valid, D);
     r = qa_check_launch("qa_bf16_bwd(row0)");
   }
   return r;
@@ -265,7 +267,7 @@ static int launch_bf16_bwd(const void* q, const void* k, const void* v, const vo
 
 // attn_bf16_bwd2.cu: warp-specialised kernel, D = 128
 int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* lse, const float* delta,
-                       float* dq, float* dk, float* dv, int BH, int S, int causal, cudaStream_t st);
+                       float* dq, float* dk, float* dv, int BH, int S, int S_valid, int causal, cudaStream_t st);
 
 }  // namespace qa
 
@@ -275,11 +277,14 @@ using namespace qa;
 // dq (zero-initialised), dk, dv: fp32 [BH*S, D].
 // variant 0: default (D = 128: warp-specialised kernel with transposed logits, attn_bf16_bwd2.cu; D = 64: the phase-sequential
 // kernel above); variant 1: the phase-sequential kernel for every D.
-extern "C" int qa_bf16_bwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
-                              const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
-                              int D, int causal, int variant, void* stream) {
+// Ragged sequences: buffers zero-padded per head to S (a multiple of 128); rows [S_valid, S) are padding: the caller pads dO
+// with zeros and lse with a large finite value (P = 0 for padded query rows), padded keys get P = 0 in the kernel.
+extern "C" int qa_bf16_bwd_ragged(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                                  const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
+                                  int S_valid, int D, int causal, int variant, void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: D must be 64 or 128");
   if (S % 128 || S <= 0 || BH <= 0) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: S must be a positive multiple of 128");
+  if (S_valid <= S - 128 || S_valid > S) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: S_valid must lie in (S - 128, S]");
   if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_bf16_bwd: variant must be 0 or 1");
   const void* ptrs[] = {q_f16, k_f16, v_bf16, dO_bf16, lse_f32, delta_f32, dq_f32, dk_f32, dv_f32};
   for (const void* ptr : ptrs)
@@ -288,20 +293,27 @@ extern "C" int qa_bf16_bwd_ex(const void* q_f16, const void* k_f16, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128 && variant == 0) {
     int r = launch_bf16_bwd_ws(q_f16, k_f16, v_bf16, dO_bf16, (const float*)lse_f32, (const float*)delta_f32, (float*)dq_f32,
-                               (float*)dk_f32, (float*)dv_f32, BH, S, causal, st);
+                               (float*)dk_f32, (float*)dv_f32, BH, S, S_valid, causal, st);
     if (r || !causal) return r;
     dim3 g2((S + 1) / 2, BH);
-    bf16_bwd_row0_fixup_kernel<<<g2, 256, 0, st>>>((const float*)dO_f32, (float*)dv_f32, S, D);
+    bf16_bwd_row0_fixup_kernel<<<g2, 256, 0, st>>>((const float*)dO_f32, (float*)dv_f32, S, S_valid, D);
     return qa_check_launch("qa_bf16_bwd(row0)");
   }
   Bf16BwdParams p;
   p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32;
   p.dq = (float*)dq_f32; p.dk = (float*)dk_f32; p.dv = (float*)dv_f32;
-  p.S = S; p.causal = causal;
+  p.S = S; p.S_valid = S_valid; p.causal = causal;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   return D == 128 ? launch_bf16_bwd<128, 1>(q_f16, k_f16, v_bf16, dO_bf16, (const float*)dO_f32, p, BH, st)
                   : launch_bf16_bwd<64, 2>(q_f16, k_f16, v_bf16, dO_bf16, (const float*)dO_f32, p, BH, st);
+}
+
+extern "C" int qa_bf16_bwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, const void* dO_bf16, const void* dO_f32,
+                              const void* lse_f32, const void* delta_f32, void* dq_f32, void* dk_f32, void* dv_f32, int BH, int S,
+                              int D, int causal, int variant, void* stream) {
+  return qa_bf16_bwd_ragged(q_f16, k_f16, v_bf16, dO_bf16, dO_f32, lse_f32, delta_f32, dq_f32, dk_f32, dv_f32, BH, S, S, D, causal,
+                            variant, stream);
 }
 
 // q, k fp16; v bf16; dO_bf16 = bf16 copy of dO (from qa_bwd_delta); dO_f32 the original; lse, delta fp32 [BH*S];

@@ -27,6 +27,7 @@ struct Bf16BwdParams2 {
   const float* lse;      // [BH*S] log2 domain
   const float* delta;    // [BH*S]
   int S, causal;
+  int S_valid;           // rows [S_valid, S) of every head are zero padding (ragged sequence): padded keys get P = 0
   float sm_scale, qk_scale;
   long long* dbg;        // development library only: [CTA][64] globaltimer stamps (tools/timeline_bf16_bwd.py)
 };
@@ -160,10 +161,12 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     const uint32_t ds_base = smem_base + L::off_ds + half * kAtom;
     const float qk = p.qk_scale;
+    const bool tailk = (j + 1) * 128 > p.S_valid;      // this CTA's key tile is the ragged last one
+    const bool keypad = j * 128 + row >= p.S_valid;    // this thread's key is padding: P = 0
     for (int n = 0; n < nt; ++n) {
       const int st = n & 1;
       const uint32_t ph = n & 1;
-      const bool diag = p.causal && (n == 0);          // i == j: the only tile that needs the mask
+      const bool diag = (p.causal && (n == 0)) || tailk;   // i == j needs the causal mask; the ragged last key tile the key mask
       const uint32_t lse_a = smem_base + L::off_ld + (st * 256 + half * 64) * 4;
       const uint32_t dl_a = lse_a + 512;
       __half2 pk[32];                                  // P as packed fp16 (kept for the dS phase)
@@ -189,11 +192,11 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             float e2 = ex2_approx(fmaf(__uint_as_float(rs[x + 2]), qk, -l4.z));
             float e3 = ex2_approx(fmaf(__uint_as_float(rs[x + 3]), qk, -l4.w));
             if (diag) {                                // strict causal: key < query keeps its weight (row 0 of the head: fixup kernel)
-              const int q0 = half * 64 + x;
-              if (row >= q0 + 0) e0 = 0.f;
-              if (row >= q0 + 1) e1 = 0.f;
-              if (row >= q0 + 2) e2 = 0.f;
-              if (row >= q0 + 3) e3 = 0.f;
+              const int q0 = (p.causal && n == 0) ? half * 64 + x : 0x7fffff00;
+              if (row >= q0 + 0 || keypad) e0 = 0.f;
+              if (row >= q0 + 1 || keypad) e1 = 0.f;
+              if (row >= q0 + 2 || keypad) e2 = 0.f;
+              if (row >= q0 + 3 || keypad) e3 = 0.f;
             }
             pk[x / 2 + 0] = __floats2half2_rn(e0, e1);
             pk[x / 2 + 1] = __floats2half2_rn(e2, e3);
@@ -407,7 +410,7 @@ extern "C" int qa_debug_set_bf16_bwd_timeline(void* buf) {
 #endif
 
 int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* lse, const float* delta,
-                       float* dq, float* dk, float* dv, int BH, int S, int causal, cudaStream_t st) {
+                       float* dq, float* dk, float* dv, int BH, int S, int S_valid, int causal, cudaStream_t st) {
   using L = Bf16Bwd2Smem;
   constexpr int D = 128;
   CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
@@ -426,7 +429,7 @@ int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* 
   if ((rc = qa_make_tmap(&tdk, dk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, box32, 3))) return rc;
   if ((rc = qa_make_tmap(&tdv, dv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, box32, 3))) return rc;
   Bf16BwdParams2 p;
-  p.lse = lse; p.delta = delta; p.S = S; p.causal = causal;
+  p.lse = lse; p.delta = delta; p.S = S; p.S_valid = S_valid; p.causal = causal;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
 #ifdef QA_DEV_TIMELINE

@@ -31,6 +31,7 @@ struct Bf16FwdParams {
   float* O;        // [BH*Sq, D] fp32
   float* lse;      // [BH*Sq] fp32
   int Sq, Sk, causal;
+  int Sk_valid;        // keys [Sk_valid, Sk) of every head are zero padding (ragged sequence): weight exactly 0
   float qk_scale;
   float rescale_tau;   // see qa_bf16_fwd_ex
 };
@@ -69,7 +70,8 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int bh = blockIdx.y;
   const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;        // heaviest (latest) causal tiles first
   const int q0 = qt * 128;
-  const int nk = p.causal ? min(p.Sk / 128, qt + 1) : p.Sk / 128;
+  const int nkv = (p.Sk_valid + 127) / 128;                    // k-tiles without a valid key are skipped
+  const int nk = p.causal ? min(nkv, qt + 1) : nkv;
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -105,6 +107,8 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t ph = (j >> 1) & 1;
       const uint32_t pph = (PBUF == 2) ? ph : (j & 1);
       const bool diag = p.causal && (j == qt);
+      const bool tail = (j + 1) * 128 > p.Sk_valid;                // ragged last k-tile
+      const int klim = diag ? min(grow, p.Sk_valid) : p.Sk_valid;  // first key without weight
       mbar_wait(&s_full[b], ph);
       tc_fence_after();
       // ---- pass 1: u = bf16(bf16(S) * qk_scale), masked; per-thread top-2
@@ -119,10 +123,10 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             uint32_t u = pack_bf16(__uint_as_float(r[2 * i]) * p.qk_scale, __uint_as_float(r[2 * i + 1]) * p.qk_scale);   // u = bf16(S * qk_scale)
-            if (decltype(masked)::value) {                         // strict causal: keep key < query
+            if (decltype(masked)::value) {                         // strict causal: keep key < query; ragged: keep key < Sk_valid
               const int key = j * 128 + c0 + ch * 32 + 2 * i;
-              if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
-              if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+              if (key >= klim) u = (u & 0xffff0000u) | 0xff80u;
+              if (key + 1 >= klim) u = (u & 0x0000ffffu) | 0xff800000u;
             }
             u2[ch * 16 + i] = u;
             const __nv_bfloat162 x = as_bf2(u);
@@ -131,7 +135,7 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       };
-      if (diag) pass1(std::true_type{}); else pass1(std::false_type{});
+      if (diag || tail) pass1(std::true_type{}); else pass1(std::false_type{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
@@ -318,13 +322,13 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // (LEDGER B-1).  grid = BH, block = 1024 threads: D/8 threads across the head dim (16-byte loads), the rest across keys.
 template <int D>
 __global__ void __launch_bounds__(1024) bf16_row0_fixup_kernel(const __nv_bfloat16* __restrict__ v, float* __restrict__ O,
-                                                              float* __restrict__ lse, int Sq, int Sk) {
+                                                              float* __restrict__ lse, int Sq, int Sk, int Sk_valid) {
   constexpr int TX = D / 8, TY = 1024 / TX;
   __shared__ float red[TY][D + 1];
   const int bh = blockIdx.x, tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const uint4* base = reinterpret_cast<const uint4*>(v + (size_t)bh * Sk * D);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int k = ty; k < Sk; k += TY) {
+  for (int k = ty; k < Sk_valid; k += TY) {
     const uint4 t = __ldg(base + (size_t)k * TX + tx);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
@@ -336,14 +340,14 @@ __global__ void __launch_bounds__(1024) bf16_row0_fixup_kernel(const __nv_bfloat
   if (threadIdx.x < D) {
     float s = 0.f;
     for (int r = 0; r < TY; ++r) s += red[r][threadIdx.x];
-    O[(size_t)bh * Sq * D + threadIdx.x] = s / (float)Sk;
-    if (threadIdx.x == 0) lse[(size_t)bh * Sq] = -128.0f + log2f((float)Sk);
+    O[(size_t)bh * Sq * D + threadIdx.x] = s / (float)Sk_valid;
+    if (threadIdx.x == 0) lse[(size_t)bh * Sq] = -128.0f + log2f((float)Sk_valid);
   }
 }
 
-static int launch_row0_fixup(const void* v, float* O, float* lse, int BH, int Sq, int Sk, int D, cudaStream_t st) {
-  if (D == 128) bf16_row0_fixup_kernel<128><<<BH, 1024, 0, st>>>((const __nv_bfloat16*)v, O, lse, Sq, Sk);
-  else bf16_row0_fixup_kernel<64><<<BH, 1024, 0, st>>>((const __nv_bfloat16*)v, O, lse, Sq, Sk);
+static int launch_row0_fixup(const void* v, float* O, float* lse, int BH, int Sq, int Sk, int Sk_valid, int D, cudaStream_t st) {
+  if (D == 128) bf16_row0_fixup_kernel<128><<<BH, 1024, 0, st>>>((const __nv_bfloat16*)v, O, lse, Sq, Sk, Sk_valid);
+  else bf16_row0_fixup_kernel<64><<<BH, 1024, 0, st>>>((const __nv_bfloat16*)v, O, lse, Sq, Sk, Sk_valid);
   return qa_check_launch("qa_bf16_fwd(row0)");
 }
 
@@ -365,37 +369,41 @@ static int launch_bf16_fwd(const void* q, const void* k, const void* v, const Bf
   kern<<<grid, 128 * NSPLIT + 192, L::total, st>>>(tq, tk, tv, p);
   int r = qa_check_launch("qa_bf16_fwd");
   if (r) return r;
-  if (p.causal) r = launch_row0_fixup(v, p.O, p.lse, BH, p.Sq, p.Sk, D, st);
+  if (p.causal) r = launch_row0_fixup(v, p.O, p.lse, BH, p.Sq, p.Sk, p.Sk_valid, D, st);
   return r;
 }
 
 // two-query-tile variant (attn_bf16_fwd2.cu)
 template <int D, int STAGES>
-int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
-                     float qk_scale, float rescale_tau, cudaStream_t st);
+int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int Sk_valid,
+                     int causal, float qk_scale, float rescale_tau, cudaStream_t st);
 
 }  // namespace qa
 
 using namespace qa;
 
 // q, k: fp16 [BH*S, D]; v: bf16 [BH*Sk, D]; O: fp32 [BH*Sq, D]; lse: fp32 [BH*Sq] (log2-sum-exp2).
-extern "C" int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH,
-                              int Sq, int Sk, int D, int causal, int nsplit, float rescale_tau, void* stream) {
+// Ragged sequences (the reference's hl.tile clamps the last tile, attention_bf16.py:170,201): the buffers are zero-padded
+// per head to Sq / Sk (multiples of 128); keys [Sk_valid, Sk) have weight exactly 0.
+extern "C" int qa_bf16_fwd_ragged(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH,
+                                  int Sq, int Sk, int Sk_valid, int D, int causal, int nsplit, float rescale_tau, void* stream) {
   if (!(rescale_tau >= 0.f && rescale_tau <= 16.f)) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: rescale_tau must be in [0, 16]");
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: D must be 64 or 128");
-  if (Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: Sq, Sk must be multiples of 128");
+  if (Sq % 128 || Sk % 128 || Sq <= 0 || Sk <= 0 || BH <= 0) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: Sq, Sk must be positive multiples of 128");
+  if (Sk_valid <= Sk - 128 || Sk_valid > Sk) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: Sk_valid must lie in (Sk - 128, Sk]");
   if (causal && Sq != Sk) return qa_fail(QA_ERR_SHAPE, "qa_bf16_fwd: causal needs Sq == Sk");
+  if (!q_f16 || !k_f16 || !v_bf16 || !O_f32 || !lse_f32) return qa_fail(QA_ERR_ALIGN, "qa_bf16_fwd: null pointer");
   if (((uintptr_t)q_f16 | (uintptr_t)k_f16 | (uintptr_t)v_bf16 | (uintptr_t)O_f32) & 15)
     return qa_fail(QA_ERR_ALIGN, "qa_bf16_fwd: 16-byte alignment required");
   Bf16FwdParams p;
-  p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.rescale_tau = rescale_tau;
+  p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid; p.causal = causal; p.rescale_tau = rescale_tau;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
   if ((nsplit == 0 || nsplit == 3) && Sq % 256 == 0) {           // default schedule: two query tiles per CTA, P and O in TMEM
-    int rc = D == 128 ? launch_bf16_fwd2<128, 2>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, rescale_tau, st)
-                      : launch_bf16_fwd2<64, 3>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, causal, p.qk_scale, rescale_tau, st);
+    int rc = D == 128 ? launch_bf16_fwd2<128, 2>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, Sk_valid, causal, p.qk_scale, rescale_tau, st)
+                      : launch_bf16_fwd2<64, 3>(q_f16, k_f16, v_bf16, p.O, p.lse, BH, Sq, Sk, Sk_valid, causal, p.qk_scale, rescale_tau, st);
     if (rc) return rc;
-    if (causal) rc = launch_row0_fixup(v_bf16, p.O, p.lse, BH, Sq, Sk, D, st);
+    if (causal) rc = launch_row0_fixup(v_bf16, p.O, p.lse, BH, Sq, Sk, Sk_valid, D, st);
     return rc;
   }
   if (nsplit == 0 || nsplit == 3) nsplit = 2;
@@ -403,6 +411,11 @@ extern "C" int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* 
                                    : launch_bf16_fwd<128, 1, 2, 1>(q_f16, k_f16, v_bf16, p, BH, st);
   return nsplit == 2 ? launch_bf16_fwd<64, 2, 3, 2>(q_f16, k_f16, v_bf16, p, BH, st)
                      : launch_bf16_fwd<64, 1, 3, 2>(q_f16, k_f16, v_bf16, p, BH, st);
+}
+
+extern "C" int qa_bf16_fwd_ex(const void* q_f16, const void* k_f16, const void* v_bf16, void* O_f32, void* lse_f32, int BH,
+                              int Sq, int Sk, int D, int causal, int nsplit, float rescale_tau, void* stream) {
+  return qa_bf16_fwd_ragged(q_f16, k_f16, v_bf16, O_f32, lse_f32, BH, Sq, Sk, Sk, D, causal, nsplit, rescale_tau, stream);
 }
 
 // Default schedule and the default lazy-rescale threshold (8 log2 units, i.e. P <= 256).

@@ -33,6 +33,7 @@ struct Bf16Fwd2Params {
   float* O;
   float* lse;
   int Sq, Sk, causal;
+  int Sk_valid;        // keys [Sk_valid, Sk) of every head are zero padding (ragged sequence): weight exactly 0
   float qk_scale;
   float rescale_tau;   // adopt a new running maximum only when it exceeds the current one by more than this (log2 units)
 };
@@ -63,7 +64,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int bh = blockIdx.y;
   const int pt = (int)gridDim.x - 1 - (int)blockIdx.x;           // pair of query tiles; heaviest causal pairs first
   const int q0 = pt * 256;
-  const int nk_full = p.Sk / 128;
+  const int nk_full = (p.Sk_valid + 127) / 128;                   // k-tiles without a valid key are skipped
   // per query tile: number of k-tiles that contain at least one visible key (strict causal: key < query)
   const int nkx[2] = {p.causal ? min(nk_full, 2 * pt + 1) : nk_full, p.causal ? min(nk_full, 2 * pt + 2) : nk_full};
   const int nk = nkx[1];
@@ -99,6 +100,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int t = 0; t < nst; ++t) {
       const int j = t >> 1, b = t & 1;
       const bool diag = p.causal && (j == qt);
+      const bool tail = (t + 1) * 64 > p.Sk_valid;                 // ragged: this 64-key step holds padding
+      const int klim = diag ? min(grow, p.Sk_valid) : p.Sk_valid;  // first key without weight
       const uint32_t sb_addr = s_addr + b * 64;
       mbar_wait(&s_full[x][b], j & 1);
       tc_fence_after();
@@ -115,10 +118,10 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int i = 0; i < 16; ++i) {
             const __nv_bfloat162 ub = __float22bfloat162_rn(__fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), qk2));
             uint32_t u = bf2u(ub);                                 // u = bf16(S * qk_scale), one FMUL2 + one pack per pair
-            if (decltype(masked)::value) {                         // strict causal: keep key < query
+            if (decltype(masked)::value) {                         // strict causal: keep key < query; ragged: key < Sk_valid
               const int key = t * 64 + ch * 32 + 2 * i;
-              if (key >= grow) u = (u & 0xffff0000u) | 0xff80u;
-              if (key + 1 >= grow) u = (u & 0x0000ffffu) | 0xff800000u;
+              if (key >= klim) u = (u & 0xffff0000u) | 0xff80u;
+              if (key + 1 >= klim) u = (u & 0x0000ffffu) | 0xff800000u;
             }
             u2[ch * 16 + i] = u;
             const __nv_bfloat162 xv = u2bf(u);
@@ -127,7 +130,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         }
       };
-      if (diag) pass1(std::true_type{}); else pass1(std::false_type{});
+      if (diag || tail) pass1(std::true_type{}); else pass1(std::false_type{});
       const __nv_bfloat16 a1 = __low2bfloat16(t1), b1 = __high2bfloat16(t1), a2 = __low2bfloat16(t2), b2 = __high2bfloat16(t2);
       const __nv_bfloat16 top1 = __hmax(a1, b1);
       const __nv_bfloat16 top2 = __hmax(__hmin(a1, b1), __hmax(a2, b2));
@@ -291,8 +294,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 template <int D, int STAGES>
-int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int causal,
-                     float qk_scale, float rescale_tau, cudaStream_t st) {
+int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int Sk_valid,
+                     int causal, float qk_scale, float rescale_tau, cudaStream_t st) {
 
   using L = Bf16Fwd2Smem<D, STAGES>;
   CUtensorMap tq, tk, tv;
@@ -304,7 +307,7 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   Bf16Fwd2Params p;
-  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.causal = causal; p.qk_scale = qk_scale; p.rescale_tau = rescale_tau;
+  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid; p.causal = causal; p.qk_scale = qk_scale; p.rescale_tau = rescale_tau;
   auto kern = bf16_fwd2_kernel<D, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
@@ -313,7 +316,7 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   return qa_check_launch("qa_bf16_fwd(2 query tiles)");
 }
 
-template int launch_bf16_fwd2<128, 2>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, float, cudaStream_t);
-template int launch_bf16_fwd2<64, 3>(const void*, const void*, const void*, float*, float*, int, int, int, int, float, float, cudaStream_t);
+template int launch_bf16_fwd2<128, 2>(const void*, const void*, const void*, float*, float*, int, int, int, int, int, float, float, cudaStream_t);
+template int launch_bf16_fwd2<64, 3>(const void*, const void*, const void*, float*, float*, int, int, int, int, int, float, float, cudaStream_t);
 
 }  // namespace qa

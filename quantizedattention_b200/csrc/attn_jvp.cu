@@ -31,6 +31,7 @@ struct JvpSmem {
 struct JvpParams {
   float *O, *tO, *lse;
   int Sq, Sk;
+  int Sk_valid;          // keys [Sk_valid, Sk) of every head are zero padding (ragged sequence): weight exactly 0
   float sm_scale, qk_scale;
 };
 
@@ -66,7 +67,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * 128;
-  const int nk = p.Sk / BN;
+  const int nk = (p.Sk_valid + BN - 1) / BN;                  // k-tiles without a valid key are skipped
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -103,6 +104,11 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         uint32_t r[32];
         tmem_ld32(lane_addr + c0 + ch * 32, r);
         tmem_ld_wait();
+        if ((j + 1) * BN > p.Sk_valid) {                          // ragged last k-tile: padded keys get logit -inf, weight 0
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (j * BN + c0 + ch * 32 + i >= p.Sk_valid) r[i] = 0xff800000u;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sreg[ch * 32 + i] = r[i]; mx = fmaxf(mx, __uint_as_float(r[i])); }
       }
@@ -323,18 +329,28 @@ static int launch_jvp(const void* const* in6, const JvpParams& p, int BH, cudaSt
 using namespace qa;
 
 // q, tq: bf16 [BH*Sq, D]; k, tk, v, tv: bf16 [BH*Sk, D]; O, tO: fp32 [BH*Sq, D]; lse: fp32 [BH*Sq].
-extern "C" int qa_jvp_fwd(const void* q, const void* tq, const void* k, const void* tk, const void* v, const void* tv,
-                          void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit, void* stream) {
+// Ragged sequences (hl.tile clamps the last tile, attention_jvp.py:120,137): buffers zero-padded per head to Sq / Sk
+// (multiples of 128), keys [Sk_valid, Sk) have weight exactly 0.
+extern "C" int qa_jvp_fwd_ragged(const void* q, const void* tq, const void* k, const void* tk, const void* v, const void* tv,
+                                 void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int Sk_valid, int D, int nsplit,
+                                 void* stream) {
   if (D != 64 && D != 128) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: D must be 64 or 128");
-  if (Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: Sq, Sk must be multiples of 128");
+  if (Sq % 128 || Sk % 128 || Sq <= 0 || Sk <= 0 || BH <= 0) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: Sq, Sk must be positive multiples of 128");
+  if (Sk_valid <= Sk - 128 || Sk_valid > Sk) return qa_fail(QA_ERR_SHAPE, "qa_jvp_fwd: Sk_valid must lie in (Sk - 128, Sk]");
   const void* in6[6] = {q, tq, k, tk, v, tv};
   for (int i = 0; i < 6; ++i)
-    if ((uintptr_t)in6[i] & 15) return qa_fail(QA_ERR_ALIGN, "qa_jvp_fwd: 16-byte alignment required");
+    if (!in6[i] || ((uintptr_t)in6[i] & 15)) return qa_fail(QA_ERR_ALIGN, "qa_jvp_fwd: null or not 16-byte aligned pointer");
+  if (!O_f32 || !tO_f32 || !lse_f32) return qa_fail(QA_ERR_ALIGN, "qa_jvp_fwd: null output pointer");
   JvpParams p;
-  p.O = (float*)O_f32; p.tO = (float*)tO_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk;
+  p.O = (float*)O_f32; p.tO = (float*)tO_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128) return nsplit == 1 ? launch_jvp<128, 1, 64>(in6, p, BH, st) : launch_jvp<128, 2, 64>(in6, p, BH, st);
   return nsplit == 2 ? launch_jvp<64, 2, 128>(in6, p, BH, st) : launch_jvp<64, 1, 128>(in6, p, BH, st);
+}
+
+extern "C" int qa_jvp_fwd(const void* q, const void* tq, const void* k, const void* tk, const void* v, const void* tv,
+                          void* O_f32, void* tO_f32, void* lse_f32, int BH, int Sq, int Sk, int D, int nsplit, void* stream) {
+  return qa_jvp_fwd_ragged(q, tq, k, tk, v, tv, O_f32, tO_f32, lse_f32, BH, Sq, Sk, Sk, D, nsplit, stream);
 }

@@ -244,67 +244,94 @@ def bf16_fwd_key_step(Sq: int, nsplit: int = 0) -> int:
     return 64 if (nsplit in (0, 3) and Sq % 256 == 0) else 128
 
 
+def _pad_seq(t, Sp: int, value: float = 0.0):
+    """[B,H,S,D] (or [B*H,S]) -> zero-padded along the token axis to Sp (ragged sequences: the kernels mask keys >= S)."""
+    dim = 2 if t.dim() == 4 else 1
+    S = t.shape[dim]
+    if S == Sp:
+        return t.contiguous()
+    shape = list(t.shape)
+    shape[dim] = Sp
+    out = torch.full(shape, value, dtype=t.dtype, device=t.device)
+    out.narrow(dim, 0, S).copy_(t)
+    return out
+
+
+def _ceil128(S: int) -> int:
+    return (S + 127) // 128 * 128
+
+
 BF16_RESCALE_TAU = 8.0      # default lazy-rescale threshold of qa_bf16_fwd (log2 units); 0 = the reference's step-by-step maximum
 
 
 def bf16_fwd(q, k, v, causal: bool, nsplit: int = 0, rescale_tau: float | None = None):
-    """Bias-corrected bf16 flash attention forward (qa_bf16_fwd / qa_bf16_fwd_ex).  q,k fp16, v bf16 [B,H,S,D] ->
-    (O fp32 [B,H,Sq,D], lse fp32 [B*H,Sq])."""
+    """Bias-corrected bf16 flash attention forward (qa_bf16_fwd_ragged).  q,k fp16, v bf16 [B,H,S,D] ->
+    (O fp32 [B,H,Sq,D], lse fp32 [B*H,Sq]).  Sequence lengths that are not multiples of 128 (the reference's clamped last
+    hl.tile) are zero-padded here and masked in the kernel."""
     _need_cuda(q, k, v)
     B, H, Sq, D = q.shape
     Sk = k.shape[2]
-    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-    O = torch.empty((B, H, Sq, D), dtype=torch.float32, device=q.device)
-    lse = torch.empty((B * H, Sq), dtype=torch.float32, device=q.device)
+    Sqp, Skp = _ceil128(Sq), _ceil128(Sk)
+    q, k, v = _pad_seq(q, Sqp), _pad_seq(k, Skp), _pad_seq(v, Skp)
+    O = torch.empty((B, H, Sqp, D), dtype=torch.float32, device=q.device)
+    lse = torch.empty((B * H, Sqp), dtype=torch.float32, device=q.device)
     L = _lib.lib()
     with torch.cuda.device(q.device), _timed("bf16_fwd"):
-        if rescale_tau is None:
-            rc = L.qa_bf16_fwd(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
-                               1 if causal else 0, nsplit, _lib.cur_stream())
-        else:
-            rc = L.qa_bf16_fwd_ex(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
-                                  1 if causal else 0, nsplit, float(rescale_tau), _lib.cur_stream())
+        rc = L.qa_bf16_fwd_ragged(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(O), _lib.ptr(lse), B * H, Sqp, Skp, Sk, D,
+                                  1 if causal else 0, nsplit, float(BF16_RESCALE_TAU if rescale_tau is None else rescale_tau),
+                                  _lib.cur_stream())
         _lib.check(rc, "qa_bf16_fwd")
+    if Sqp != Sq:
+        O, lse = O[:, :, :Sq].contiguous(), lse[:, :Sq].contiguous()
     return O, lse
 
 
 def jvp_fwd(q, k, v, tq, tk, tv, nsplit: int = 2):
-    """Forward-mode JVP attention (qa_jvp_fwd).  Six fp32 [B,H,S,D] tensors -> (O, tO fp32 [B,H,Sq,D], lse [B*H,Sq]).
-    Operands are rounded to bf16 for the tensor cores (fp32 accumulation)."""
+    """Forward-mode JVP attention (qa_jvp_fwd_ragged).  Six fp32 [B,H,S,D] tensors -> (O, tO fp32 [B,H,Sq,D], lse [B*H,Sq]).
+    Operands are rounded to bf16 for the tensor cores (fp32 accumulation).  Sequence lengths that are not
+    multiples of 128 are zero-padded here and masked in the kernel."""
     q, k, v, tq, tk, tv = [_unwrap(t) for t in (q, k, v, tq, tk, tv)]
     _need_cuda(q, k, v, tq, tk, tv)
     with _raw_mode():
         B, H, Sq, D = q.shape
         Sk = k.shape[2]
+        Sqp, Skp = _ceil128(Sq), _ceil128(Sk)
         b16 = [cast_f32(t, torch.bfloat16) if t.dtype == torch.float32 else t.to(torch.bfloat16).contiguous()
                for t in (q, tq, k, tk, v, tv)]
-        O = torch.empty((B, H, Sq, D), dtype=torch.float32, device=q.device)
+        b16 = [_pad_seq(t, Sqp if i < 2 else Skp) for i, t in enumerate(b16)]
+        O = torch.empty((B, H, Sqp, D), dtype=torch.float32, device=q.device)
         tO = torch.empty_like(O)
-        lse = torch.empty((B * H, Sq), dtype=torch.float32, device=q.device)
+        lse = torch.empty((B * H, Sqp), dtype=torch.float32, device=q.device)
         L = _lib.lib()
         with torch.cuda.device(q.device), _timed("jvp_fwd"):
-            _lib.check(L.qa_jvp_fwd(*[_lib.ptr(t) for t in b16], _lib.ptr(O), _lib.ptr(tO), _lib.ptr(lse), B * H, Sq, Sk, D,
-                                    nsplit, _lib.cur_stream()), "qa_jvp_fwd")
+            _lib.check(L.qa_jvp_fwd_ragged(*[_lib.ptr(t) for t in b16], _lib.ptr(O), _lib.ptr(tO), _lib.ptr(lse), B * H, Sqp, Skp,
+                                           Sk, D, nsplit, _lib.cur_stream()), "qa_jvp_fwd")
+        if Sqp != Sq:
+            O, tO, lse = O[:, :, :Sq].contiguous(), tO[:, :, :Sq].contiguous(), lse[:, :Sq].contiguous()
     return O, tO, lse
 
 
 def bf16_bwd(q, k, v, O, lse, causal: bool, dO, variant: int = 0):
-    """Recompute backward of the bf16 path (qa_bwd_delta + qa_bf16_bwd_ex).  q,k fp16; v bf16; O, dO fp32 [B,H,S,D];
-    lse fp32 [B*H,S].  Returns fp32 (dq, dk, dv) [B,H,S,D].  variant: 0 = default kernels, 1 = phase-sequential kernel."""
+    """Recompute backward of the bf16 path (qa_bwd_delta + qa_bf16_bwd_ragged).  q,k fp16; v bf16; O, dO fp32 [B,H,S,D];
+    lse fp32 [B*H,S].  Returns fp32 (dq, dk, dv) [B,H,S,D].  variant: 0 = default kernels, 1 = phase-sequential kernel.
+    Ragged S: every operand is zero-padded to a multiple of 128, lse with a large value (P = 0 for the padded query rows)."""
     _need_cuda(q, k, v, O, lse, dO)
     B, H, S, D = q.shape
     assert k.shape[2] == S, "backward is self-attention only (LEDGER I-11)"
-    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-    dO = dO.to(torch.float32).contiguous()
-    O = O.to(torch.float32).contiguous()
-    lse = lse.to(torch.float32).contiguous()
+    Sp = _ceil128(S)
+    q, k, v = _pad_seq(q, Sp), _pad_seq(k, Sp), _pad_seq(v, Sp)
+    dO = _pad_seq(dO.to(torch.float32), Sp)
+    O = _pad_seq(O.to(torch.float32), Sp)
+    lse = _pad_seq(lse.to(torch.float32).view(B * H, S), Sp, 1.0e30)
     delta, dO_bf16 = bwd_delta(dO, O, want_bf16_copy=True)
-    dq = torch.zeros((B, H, S, D), dtype=torch.float32, device=q.device)
+    dq = torch.zeros((B, H, Sp, D), dtype=torch.float32, device=q.device)
     dk = torch.empty_like(dq)
     dv = torch.empty_like(dq)
     L = _lib.lib()
     with torch.cuda.device(q.device), _timed("bf16_bwd"):
-        _lib.check(L.qa_bf16_bwd_ex(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dO_bf16), _lib.ptr(dO), _lib.ptr(lse),
-                                    _lib.ptr(delta), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), B * H, S, D, 1 if causal else 0,
-                                    int(variant), _lib.cur_stream()), "qa_bf16_bwd")
+        _lib.check(L.qa_bf16_bwd_ragged(_lib.ptr(q), _lib.ptr(k), _lib.ptr(v), _lib.ptr(dO_bf16), _lib.ptr(dO), _lib.ptr(lse),
+                                        _lib.ptr(delta), _lib.ptr(dq), _lib.ptr(dk), _lib.ptr(dv), B * H, Sp, S, D,
+                                        1 if causal else 0, int(variant), _lib.cur_stream()), "qa_bf16_bwd")
+    if Sp != S:
+        dq, dk, dv = [t[:, :, :S].contiguous() for t in (dq, dk, dv)]
     return dq, dk, dv

@@ -61,6 +61,9 @@ def test_argument_validation_needs_no_gpu():
     assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, -1.0, z) == -1  # rescale_tau outside [0, 16]
     assert L.qa_bf16_fwd_ex(*([z] * 5), 1, 128, 128, 128, 0, 0, 32.0, z) == -1
     assert L.qa_jvp_fwd(*([z] * 9), 1, 128, 128, 96, 1, z) == -1              # D in {64,128}
+    assert L.qa_bf16_fwd_ragged(*([z] * 5), 1, 128, 256, 100, 128, 0, 0, 8.0, z) == -1   # Sk_valid in (Sk - 128, Sk]
+    assert L.qa_jvp_fwd_ragged(*([z] * 9), 1, 128, 128, 0, 128, 1, z) == -1
+    assert L.qa_bf16_bwd_ragged(*([z] * 10), 1, 256, 300, 128, 0, 0, z) == -1
 
 
 def test_no_cpu_fallback_and_no_oracle_in_product():
