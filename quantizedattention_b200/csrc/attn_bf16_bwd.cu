@@ -266,8 +266,8 @@ static int launch_bf16_bwd(const void* q, const void* k, const void* v, const vo
 }
 
 // attn_bf16_bwd2.cu: warp-specialised kernel, D = 128
-int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* lse, const float* delta,
-                       float* dq, float* dk, float* dv, int BH, int S, int S_valid, int causal, cudaStream_t st);
+int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* dO_f32, const float* lse,
+                       const float* delta, float* dq, float* dk, float* dv, int BH, int S, int S_valid, int causal, cudaStream_t st);
 
 }  // namespace qa
 
@@ -292,12 +292,10 @@ extern "C" int qa_bf16_bwd_ragged(const void* q_f16, const void* k_f16, const vo
   if (causal && !dO_f32) return qa_fail(QA_ERR_ALIGN, "qa_bf16_bwd: causal needs dO_f32");
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128 && variant == 0) {
-    int r = launch_bf16_bwd_ws(q_f16, k_f16, v_bf16, dO_bf16, (const float*)lse_f32, (const float*)delta_f32, (float*)dq_f32,
-                               (float*)dk_f32, (float*)dv_f32, BH, S, S_valid, causal, st);
-    if (r || !causal) return r;
-    dim3 g2((S + 1) / 2, BH);
-    bf16_bwd_row0_fixup_kernel<<<g2, 256, 0, st>>>((const float*)dO_f32, (float*)dv_f32, S, S_valid, D);
-    return qa_check_launch("qa_bf16_bwd(row0)");
+    if (causal && (reinterpret_cast<uintptr_t>(dO_f32) & 15)) return qa_fail(QA_ERR_ALIGN, "qa_bf16_bwd: dO_f32 not 16-byte aligned");
+    // causal row 0 (uniform weight on every key, LEDGER B-1) is added in the kernel's dV write-back: no fix-up pass
+    return launch_bf16_bwd_ws(q_f16, k_f16, v_bf16, dO_bf16, (const float*)dO_f32, (const float*)lse_f32, (const float*)delta_f32,
+                              (float*)dq_f32, (float*)dk_f32, (float*)dv_f32, BH, S, S_valid, causal, st);
   }
   Bf16BwdParams p;
   p.lse = (const float*)lse_f32; p.delta = (const float*)delta_f32;

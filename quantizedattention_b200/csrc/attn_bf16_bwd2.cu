@@ -3,8 +3,9 @@
 // (attn_bf16_bwd.cu): P rounded to bf16 for dV, dS = P*(dP - delta) in fp16 (P and dP - delta rounded to fp16, product
 // rounded to fp16: 3 x 2^-12 relative where the sequential kernel has 2^-12), fp32 accumulation.
 //
-// One CTA = one 128-key tile j of one (batch, head), looping over the query tiles i (k-outer, as the reference).  The
-// logits are computed TRANSPOSED so that the probabilities can feed the tensor core from TMEM:
+// Work item = one 128-key tile j of one (batch, head), looping over the query tiles i (k-outer, as the reference); a
+// CTA that has finished its item takes over the item of a CTA that has not started yet (cluster launch control), so the
+// dV / dK write-back of one item and the loads of the next overlap.  The logits are computed TRANSPOSED so that the probabilities can feed the tensor core from TMEM:
 //   S^T  = K_j Q_i^T        (fp16)  -> TMEM A   [lane = key, column = query]
 //   dP^T = V_j dO_i^T       (bf16)  -> TMEM B
 //   dV_j += P^T dO_i        (bf16)  P^T read from TMEM (written over S^T by the compute warps)  -> TMEM, resident
@@ -12,8 +13,8 @@
 //   dQ_i  = dS K_j          (fp16)  dS^T as MN-major A, K as MN-major B -> TMEM B [lane = query, column = d], staged
 //                                   through shared memory and added to global dQ by TMA reduce-add
 // Shared memory (7 x 32 KB): K, V, two stages of Q, one of dO (its life ends with dV, early in the tile), dS^T, the dQ
-// staging tile.  P never touches shared memory.  The dV / dK epilogue reuses the Q / dO / dS^T space for TMA stores.
-// Roles (16 warps, setmaxnreg): warps 0..3 drain dQ, 4..11 compute P^T and dS^T (two per TMEM lane quadrant, 64 query
+// staging tile (dQ reduce-adds and the dV / dK stores of a finished item).  P never touches shared memory.
+// Roles (16 warps, setmaxnreg): warps 0..3 drain dQ (and dV / dK at the end of an item), 4..11 compute P^T and dS^T (two per TMEM lane quadrant, 64 query
 // columns each), 12 issues tcgen05.mma, 13 issues the TMA loads.  Issue order of the MMA warp per query tile n:
 //   dV(n) | S(n+1) | dQ(n), dK(n) | dP(n+1)
 // so that the compute warps' dS(n) phase runs under dV(n) / S(n+1), their P(n+1) phase under dQ(n) / dK(n), and the dQ
@@ -26,10 +27,11 @@ namespace qa {
 struct Bf16BwdParams2 {
   const float* lse;      // [BH*S] log2 domain
   const float* delta;    // [BH*S]
-  int S, causal;
+  const float* dO_f32;   // [BH*S, D] (causal only): row 0 of a head attends uniformly to all keys (LEDGER B-1), dV[k] += dO[0] / S
+  int S, causal, BH;
   int S_valid;           // rows [S_valid, S) of every head are zero padding (ragged sequence): padded keys get P = 0
   float sm_scale, qk_scale;
-  long long* dbg;        // development library only: [CTA][64] globaltimer stamps (tools/timeline_bf16_bwd.py)
+  long long* dbg;        // development library only: [item = head * key tiles + key tile][64] globaltimer stamps (tools/timeline_bf16_bwd.py)
 };
 
 #ifdef QA_DEV_TIMELINE
@@ -38,7 +40,7 @@ struct Bf16BwdParams2 {
     if (p.dbg != nullptr) {                                                                               \
       long long t_;                                                                                       \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
-      p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + (slot)] = t_;                            \
+      p.dbg[((size_t)it.bh * nkt + it.j) * 64 + (slot)] = t_;                            \
     }                                                                                                     \
   } while (0)
 #else
@@ -49,18 +51,19 @@ struct Bf16Bwd2Smem {
   static constexpr int kTile = 128 * 128 * 2;
   static constexpr int off_k = 0;
   static constexpr int off_v = kTile;
-  static constexpr int off_q = 2 * kTile;          // 2 stages; epilogue: dV staging (64 KB fp32)
-  static constexpr int off_do = 4 * kTile;         // 1 stage;  epilogue: dK staging (64 KB fp32, with the dS^T tile)
+  static constexpr int off_q = 2 * kTile;          // 2 stages
+  static constexpr int off_do = 4 * kTile;         // 1 stage
   static constexpr int off_ds = 5 * kTile;
-  static constexpr int off_st = 6 * kTile;         // dQ staging: two [128 query][32 d] fp32 atoms (128 B swizzle)
+  static constexpr int off_st = 6 * kTile;         // output staging: two [128 rows][32 d] fp32 atoms (128 B swizzle)
   static constexpr int off_ld = 7 * kTile;         // [stage][lse | delta][128] fp32
   static constexpr int off_bar = off_ld + 2048;
-  static constexpr int used = off_bar + 160;
+  static constexpr int off_clc = off_bar + 192;    // two 16-byte cluster-launch-control responses
+  static constexpr int used = off_clc + 32;
   static constexpr int total = 232448;             // everything an SM has; the align-up pad must fit in total - used
 };
 
 enum Bf16Bwd2Bar { KV_FULL = 0, Q_FULL0, Q_FULL1, DO_FULL, Q_FREE0, Q_FREE1, DO_FREE, S_FULL, P_READY, DP_FULL, DS_READY, DS_FREE,
-                   DQ_FULL, DQ_FREE, ACC_FULL, kNumBars };
+                   DQ_FULL, DQ_FREE, ACC_FULL, ACC_FREE, CLC_FULL0, CLC_FULL1, CLC_FREE0, CLC_FREE1, kNumBars };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -72,6 +75,45 @@ __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   return v;
 }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// Work item = one CTA of the launch grid (order: bf16_bwd2_item).  A running CTA does not exit after its item: it asks
+// the hardware to cancel a CTA that has not started yet (cluster launch control) and processes that CTA's item next, which
+// keeps the hardware's dynamic load balance and lets the write-back of one item overlap the loads of the next.
+struct Bf16Bwd2Item { int j, bh, i0, nt; };
+constexpr int kBf16BwdHeadGroup = 16;
+// Launch order (blockIdx.x = w): groups of 16 heads; inside a group key tile j outermost (causal: heaviest first), head innermost.
+// The CTAs running together then stream the Q / dO tiles of at most ~16 heads (L2 resident), and the last group still ends on
+// its lightest items.
+__device__ __forceinline__ Bf16Bwd2Item bf16_bwd2_item(int w, int BH, int nkt, int nq, int causal) {
+  const int per_group = kBf16BwdHeadGroup * nkt;
+  const int full = BH / kBf16BwdHeadGroup;
+  int g = w / per_group, hg = kBf16BwdHeadGroup;
+  if (g >= full) { g = full; hg = BH - full * kBf16BwdHeadGroup; }
+  const int rem = w - g * per_group;
+  Bf16Bwd2Item it;
+  it.j = rem / hg;
+  it.bh = g * kBf16BwdHeadGroup + (rem - it.j * hg);
+  it.i0 = causal ? it.j : 0;                           // query tiles before the diagonal see none of these keys
+  it.nt = nq - it.i0;
+  return it;
+}
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_saddr, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+               ::"r"(resp_saddr), "r"(smem_u32(bar)) : "memory");
+}
+// true: a pending CTA was cancelled, x is its blockIdx.x
+__device__ __forceinline__ bool clc_read(uint32_t resp_saddr, int& x) {
+  uint32_t ok, cx = 0, cy = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%3];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %2, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, _, _}, r;\n\t}"
+      : "+r"(cx), "+r"(cy), "=r"(ok) : "r"(resp_saddr) : "memory");
+  x = (int)cx;
+  return ok != 0;
+}
 
 __global__ void __launch_bounds__(512, 1)
 bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -89,18 +131,12 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(smem + L::off_bar + kNumBars * 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y, j = blockIdx.x;
   const int nq = p.S / 128;
-  const int i0 = p.causal ? j : 0;                     // query tiles before the diagonal see none of these keys
-  const int nt = nq - i0;
-  const size_t head_row0 = (size_t)bh * p.S;
+  const int nkt = (p.S_valid + 127) / 128;
 
   if (tid == 0) {
-    QA_TL2(0);
-#ifdef QA_DEV_TIMELINE
-    if (p.dbg != nullptr) { uint32_t sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 + 15] = sm_; }
-#endif
-    for (int b = 0; b < kNumBars; ++b) mbar_init(&bars[b], (b == P_READY || b == DS_READY) ? 8 : (b == DQ_FREE ? 4 : 1));
+    for (int b = 0; b < kNumBars; ++b)
+      mbar_init(&bars[b], (b == P_READY || b == DS_READY) ? 8 : ((b == DQ_FREE || b == ACC_FREE) ? 4 : ((b == CLC_FREE0 || b == CLC_FREE1) ? 13 : 1)));
     fence_mbar_init();
   }
   if (warp == 12) tmem_alloc<512>(tmem_base_s);
@@ -109,49 +145,92 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_after();
   const uint32_t tbase = *tmem_base_s;
   const uint32_t smem_base = smem_u32(smem);
-  if (tid == 0) QA_TL2(1);
   constexpr uint32_t tA = 0, tB = 128, tDV = 256, tDK = 384;
+  const uint32_t clc_a = smem_base + L::off_clc;
+  // Barrier phases run on two counters kept identically by every role: T = tiles so far (all items), I = items so far.
+  // After item I every consumer warp reads the response of query I (slot I & 1) and releases the slot.
+  auto next_item = [&](uint32_t I, Bf16Bwd2Item& it, bool whole_warp) -> bool {   // whole_warp = false: a single elected thread
+    const int s = I & 1;
+    int x;
+    mbar_wait(&bars[CLC_FULL0 + s], (I >> 1) & 1);
+    const bool ok = clc_read(clc_a + s * 16, x);
+    fence_proxy_async_smem();                          // the slot is written next through the async proxy
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive(&bars[CLC_FREE0 + s]);
+    if (ok) it = bf16_bwd2_item(x, p.BH, nkt, nq, p.causal);
+    return ok;
+  };
 
   if (warp < 4) {
-    // =========================== dQ drain: lane = query, column = d ===========================
+    // =========================== drain: dQ of every tile, dV / dK of every item (lane = row, column = d) ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int qrow = warp * 32 + lane;
-    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16) + tB;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
     const float sm = p.sm_scale;
-    for (int n = 0; n < nt; ++n) {
-      const int r0 = (int)head_row0 + (i0 + n) * 128 + warp * 32;
-      uint32_t r[128];
-      mbar_wait(&bars[DQ_FULL], n & 1);
-      tc_fence_after();
-      if (tid == 0 && n == 4) QA_TL2(26);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
-      tmem_ld_wait();
-      tc_fence_before();                               // every dQ column is in registers: TMEM B is free for dP of the next tile
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[DQ_FREE]);
-      if (tid == 0 && n == 4) QA_TL2(27);
-      // each warp stages its own 32 query rows ([32 rows][32 d] fp32 = 4 KB of a swizzled atom) and reduces them itself
+    // each warp stages its own 32 rows ([32 rows][32 d] fp32 = 4 KB of a swizzled atom) and issues its own TMA operation
+    auto stage_out = [&](const uint32_t (&r)[128], float sc, const CUtensorMap* tm, int row0, bool reduce, const float* add, float addsc) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t atom = smem_base + L::off_st + (c & 1) * kAtom;
-        if (lane == 0) tma_store_wait_read1();         // this warp's reduce-add of two rounds ago has read the atom rows
+        if (lane == 0) tma_store_wait_read1();         // this warp's operation of two rounds ago has read the atom rows
         __syncwarp();
 #pragma unroll
-        for (int x = 0; x < 32; x += 4)
-          sts128f(atom + swz128(qrow, x * 4), __uint_as_float(r[c * 32 + x]) * sm, __uint_as_float(r[c * 32 + x + 1]) * sm,
-                  __uint_as_float(r[c * 32 + x + 2]) * sm, __uint_as_float(r[c * 32 + x + 3]) * sm);
+        for (int x = 0; x < 32; x += 4) {
+          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (add != nullptr) a4 = __ldg(reinterpret_cast<const float4*>(add + c * 32 + x));
+          sts128f(atom + swz128(qrow, x * 4), fmaf(a4.x, addsc, __uint_as_float(r[c * 32 + x]) * sc),
+                  fmaf(a4.y, addsc, __uint_as_float(r[c * 32 + x + 1]) * sc), fmaf(a4.z, addsc, __uint_as_float(r[c * 32 + x + 2]) * sc),
+                  fmaf(a4.w, addsc, __uint_as_float(r[c * 32 + x + 3]) * sc));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_reduce_add_2d(&tm_dq, smem + L::off_st + (c & 1) * kAtom + warp * 4096, c * 32, r0);
+          const void* src = smem + L::off_st + (c & 1) * kAtom + warp * 4096;
+          if (reduce) tma_reduce_add_2d(tm, src, c * 32, row0); else tma_store_2d(tm, src, c * 32, row0);
           tma_store_commit();
         }
       }
-      if (tid == 0 && n == 4) QA_TL2(28);
+    };
+    uint32_t T = 0;
+    Bf16Bwd2Item it = bf16_bwd2_item(blockIdx.x, p.BH, nkt, nq, p.causal);
+    for (uint32_t I = 0;; ++I) {
+      const int head_row0 = it.bh * p.S;
+      for (int n = 0; n < it.nt; ++n, ++T) {
+        uint32_t r[128];
+        mbar_wait(&bars[DQ_FULL], T & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + tB + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+        tmem_ld_wait();
+        tc_fence_before();                             // every dQ column is in registers: TMEM B is free for the next dP
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[DQ_FREE]);
+        stage_out(r, sm, &tm_dq, head_row0 + (it.i0 + n) * 128 + warp * 32, true, nullptr, 0.f);
+      }
+      // ---- dV_j, dK_j of the finished item (lane = key)
+      mbar_wait(&bars[ACC_FULL], I & 1);
+      tc_fence_after();
+      if (tid == 0) QA_TL2(11);
+      const int k0 = head_row0 + it.j * 128 + warp * 32;
+      {
+        uint32_t r[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + tDV + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+        tmem_ld_wait();
+        // causal: query row 0 of the head has weight 1 / S on every key (LEDGER B-1; its P is masked to 0 in the tiles above)
+        stage_out(r, 1.0f, &tm_dv, k0, false, p.causal ? p.dO_f32 + (size_t)head_row0 * D : nullptr, 1.0f / (float)p.S_valid);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(lane_addr + tDK + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+        tmem_ld_wait();
+        tc_fence_before();                             // both accumulators are in registers: the next item may overwrite them
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[ACC_FREE]);
+        stage_out(r, sm, &tm_dk, k0, false, nullptr, 0.f);
+      }
+      if (tid == 0) QA_TL2(12);
+      if (!next_item(I, it, true)) break;
     }
     if (lane == 0) tma_store_wait_read();
-    if (tid == 0) QA_TL2(13);
   } else if (warp < 12) {
     // =========================== compute: P^T (-> TMEM) and dS^T (-> shared memory) ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
@@ -161,126 +240,90 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     const uint32_t ds_base = smem_base + L::off_ds + half * kAtom;
     const float qk = p.qk_scale;
-    const bool tailk = (j + 1) * 128 > p.S_valid;      // this CTA's key tile is the ragged last one
-    const bool keypad = j * 128 + row >= p.S_valid;    // this thread's key is padding: P = 0
-    for (int n = 0; n < nt; ++n) {
-      const int st = n & 1;
-      const uint32_t ph = n & 1;
-      const bool diag = (p.causal && (n == 0)) || tailk;   // i == j needs the causal mask; the ragged last key tile the key mask
-      const uint32_t lse_a = smem_base + L::off_ld + (st * 256 + half * 64) * 4;
-      const uint32_t dl_a = lse_a + 512;
-      __half2 pk[32];                                  // P as packed fp16 (kept for the dS phase)
-      mbar_wait(&bars[Q_FULL0 + st], (n >> 1) & 1);    // lse / delta of this tile have landed
-      mbar_wait(&bars[S_FULL], ph);
-      tc_fence_after();
-      if (tid == 128 && n == 0) QA_TL2(7);
-      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 0);
-      {
-        uint32_t rs[64];
-        tmem_ld32(lane_addr + tA + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
-        tmem_ld32(lane_addr + tA + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
-        tmem_ld_wait();
+    uint32_t T = 0;
+    Bf16Bwd2Item it = bf16_bwd2_item(blockIdx.x, p.BH, nkt, nq, p.causal);
+    for (uint32_t I = 0;; ++I) {
+      const bool tailk = (it.j + 1) * 128 > p.S_valid;   // this key tile is the ragged last one
+      const bool keypad = it.j * 128 + row >= p.S_valid; // this thread's key is padding: P = 0
+      for (int n = 0; n < it.nt; ++n, ++T) {
+        const int st = T & 1;
+        const uint32_t ph = T & 1;
+        const bool cdiag = p.causal && (n == 0);       // i == j needs the causal mask
+        const bool masked = cdiag || tailk;            // the ragged last key tile needs the key mask
+        const uint32_t lse_a = smem_base + L::off_ld + (st * 256 + half * 64) * 4;
+        const uint32_t dl_a = lse_a + 512;
+        __half2 pk[32];                                // P as packed fp16 (kept for the dS phase)
+        mbar_wait(&bars[Q_FULL0 + st], (T >> 1) & 1);  // lse / delta of this tile have landed
+        mbar_wait(&bars[S_FULL], ph);
+        tc_fence_after();
+        {
+          uint32_t rs[64];
+          tmem_ld32(lane_addr + tA + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&rs[0]));
+          tmem_ld32(lane_addr + tA + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rs[32]));
+          tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {               // 16 queries per TMEM store
-          uint32_t w[8];
+          for (int ch = 0; ch < 4; ++ch) {             // 16 queries per TMEM store
+            uint32_t w[8];
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            const int x = ch * 16 + c;
-            const float4 l4 = lds128f(lse_a + x * 4);
-            float e0 = ex2_approx(fmaf(__uint_as_float(rs[x + 0]), qk, -l4.x));     // attention_bf16.py:391-392
-            float e1 = ex2_approx(fmaf(__uint_as_float(rs[x + 1]), qk, -l4.y));
-            float e2 = ex2_approx(fmaf(__uint_as_float(rs[x + 2]), qk, -l4.z));
-            float e3 = ex2_approx(fmaf(__uint_as_float(rs[x + 3]), qk, -l4.w));
-            if (diag) {                                // strict causal: key < query keeps its weight (row 0 of the head: fixup kernel)
-              const int q0 = (p.causal && n == 0) ? half * 64 + x : 0x7fffff00;
-              if (row >= q0 + 0 || keypad) e0 = 0.f;
-              if (row >= q0 + 1 || keypad) e1 = 0.f;
-              if (row >= q0 + 2 || keypad) e2 = 0.f;
-              if (row >= q0 + 3 || keypad) e3 = 0.f;
+            for (int c = 0; c < 16; c += 4) {
+              const int x = ch * 16 + c;
+              const float4 l4 = lds128f(lse_a + x * 4);
+              float e0 = ex2_approx(fmaf(__uint_as_float(rs[x + 0]), qk, -l4.x));     // attention_bf16.py:391-392
+              float e1 = ex2_approx(fmaf(__uint_as_float(rs[x + 1]), qk, -l4.y));
+              float e2 = ex2_approx(fmaf(__uint_as_float(rs[x + 2]), qk, -l4.z));
+              float e3 = ex2_approx(fmaf(__uint_as_float(rs[x + 3]), qk, -l4.w));
+              if (masked) {                            // strict causal: key < query keeps its weight (row 0 of the head: fixup kernel)
+                const int q0 = cdiag ? half * 64 + x : 0x7fffff00;
+                if (row >= q0 + 0 || keypad) e0 = 0.f;
+                if (row >= q0 + 1 || keypad) e1 = 0.f;
+                if (row >= q0 + 2 || keypad) e2 = 0.f;
+                if (row >= q0 + 3 || keypad) e3 = 0.f;
+              }
+              pk[x / 2 + 0] = __floats2half2_rn(e0, e1);
+              pk[x / 2 + 1] = __floats2half2_rn(e2, e3);
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(e0, e1), b1 = __floats2bfloat162_rn(e2, e3);
+              w[c / 2 + 0] = *reinterpret_cast<uint32_t*>(&b0);
+              w[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&b1);
             }
-            pk[x / 2 + 0] = __floats2half2_rn(e0, e1);
-            pk[x / 2 + 1] = __floats2half2_rn(e2, e3);
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(e0, e1), b1 = __floats2bfloat162_rn(e2, e3);
-            w[c / 2 + 0] = *reinterpret_cast<uint32_t*>(&b0);
-            w[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&b1);
+            tmem_st8(lane_addr + tA + half * 64 + ch * 8, w);   // bf16 pairs over the S^T columns this warp has already read
           }
-          tmem_st8(lane_addr + tA + half * 64 + ch * 8, w);   // bf16 pairs over the S^T columns this warp has already read
         }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[P_READY]);
-      if (tid == 128 && n == 0) QA_TL2(8);
-      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 1);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[P_READY]);
 
-      mbar_wait(&bars[DP_FULL], ph);
-      tc_fence_after();
-      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 2);
-      {
-        uint32_t rp[64];
-        tmem_ld32(lane_addr + tB + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&rp[0]));
-        tmem_ld32(lane_addr + tB + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rp[32]));
-        if (n > 0) mbar_wait(&bars[DS_FREE], (n - 1) & 1);     // dQ / dK of the previous tile have read the dS^T buffer
-        tmem_ld_wait();
+        mbar_wait(&bars[DP_FULL], ph);
+        tc_fence_after();
+        {
+          uint32_t rp[64];
+          tmem_ld32(lane_addr + tB + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&rp[0]));
+          tmem_ld32(lane_addr + tB + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&rp[32]));
+          if (T > 0) mbar_wait(&bars[DS_FREE], (T - 1) & 1);     // dQ / dK of the previous tile have read the dS^T buffer
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {                  // 8 queries = one 16 B store
-          uint32_t wd[4];
+          for (int g = 0; g < 8; ++g) {                // 8 queries = one 16 B store
+            uint32_t wd[4];
 #pragma unroll
-          for (int e = 0; e < 4; e += 2) {
-            const int x = g * 8 + e * 2;
-            const float4 d4 = lds128f(dl_a + x * 4);
-            // dS = P * (dP - delta): both factors rounded to fp16, product rounded to fp16 (3 x 2^-12 relative)
-            const __half2 t01 = __floats2half2_rn(__uint_as_float(rp[x + 0]) - d4.x, __uint_as_float(rp[x + 1]) - d4.y);
-            const __half2 t23 = __floats2half2_rn(__uint_as_float(rp[x + 2]) - d4.z, __uint_as_float(rp[x + 3]) - d4.w);
-            __half2 h0 = __hmul2(pk[x / 2 + 0], t01), h1 = __hmul2(pk[x / 2 + 1], t23);
-            wd[e + 0] = *reinterpret_cast<uint32_t*>(&h0);
-            wd[e + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            for (int e = 0; e < 4; e += 2) {
+              const int x = g * 8 + e * 2;
+              const float4 d4 = lds128f(dl_a + x * 4);
+              // dS = P * (dP - delta): both factors rounded to fp16, product rounded to fp16 (3 x 2^-12 relative)
+              const __half2 t01 = __floats2half2_rn(__uint_as_float(rp[x + 0]) - d4.x, __uint_as_float(rp[x + 1]) - d4.y);
+              const __half2 t23 = __floats2half2_rn(__uint_as_float(rp[x + 2]) - d4.z, __uint_as_float(rp[x + 3]) - d4.w);
+              __half2 h0 = __hmul2(pk[x / 2 + 0], t01), h1 = __hmul2(pk[x / 2 + 1], t23);
+              wd[e + 0] = *reinterpret_cast<uint32_t*>(&h0);
+              wd[e + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+            sts128(ds_base + swz128(row, g * 16), wd[0], wd[1], wd[2], wd[3]);
           }
-          sts128(ds_base + swz128(row, g * 16), wd[0], wd[1], wd[2], wd[3]);
         }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[DS_READY]);
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[DS_READY]);
-      if (tid == 128 && n == 0) QA_TL2(9);
-      if (lane == 0 && n == 4) QA_TL2(32 + cw * 4 + 3);
-      if (tid == 128 && n == nt - 1) QA_TL2(10);
-    }
-    // ---- epilogue: dV_j, dK_j accumulators (lane = key) -> swizzled fp32 staging over the Q / dO / dS^T tiles -> TMA store
-    mbar_wait(&bars[ACC_FULL], 0);
-    tc_fence_after();
-    if (tid == 128) QA_TL2(11);
-    const float sm = p.sm_scale;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      uint32_t r[64];
-      tmem_ld32(lane_addr + (m ? tDK : tDV) + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-      tmem_ld32(lane_addr + (m ? tDK : tDV) + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-      tmem_ld_wait();
-      const float sc = m ? sm : 1.0f;
-#pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const uint32_t atom = smem_base + (m ? L::off_do : L::off_q) + (half * 2 + a) * kAtom;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          sts128f(atom + swz128(row, c * 4), __uint_as_float(r[a * 32 + c]) * sc, __uint_as_float(r[a * 32 + c + 1]) * sc,
-                  __uint_as_float(r[a * 32 + c + 2]) * sc, __uint_as_float(r[a * 32 + c + 3]) * sc);
-      }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(3, 256);
-    if (tid == 128) {
-      const int k0 = (int)head_row0 + j * 128;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        tma_store_2d(&tm_dv, smem + L::off_q + a * kAtom, a * 32, k0);
-        tma_store_2d(&tm_dk, smem + L::off_do + a * kAtom, a * 32, k0);
-      }
-      tma_store_commit();
-      tma_store_wait_read();
-      QA_TL2(12);
+      if (!next_item(I, it, true)) break;
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -311,83 +354,106 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
           }
           umma_commit(&bars[DP_FULL]);
         };
-        mbar_wait(&bars[KV_FULL], 0);
-        mbar_wait(&bars[Q_FULL0], 0);
-        tc_fence_after();
-        QA_TL2(2);
-        issue_s(0);
-        mbar_wait(&bars[DO_FULL], 0);
-        issue_dp();
-        for (int n = 0; n < nt; ++n) {
-          const int st = n & 1;
-          const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);
-          mbar_wait(&bars[P_READY], n & 1);
+        uint32_t T = 0;
+        Bf16Bwd2Item it = bf16_bwd2_item(blockIdx.x, p.BH, nkt, nq, p.causal);
+        for (uint32_t I = 0;; ++I) {
+          QA_TL2(0);
+#ifdef QA_DEV_TIMELINE
+          if (p.dbg != nullptr) p.dbg[((size_t)it.bh * nkt + it.j) * 64 + 14] = (long long)blockIdx.x + 1;
+#endif
+          // first tile of the item: S(0) over the P^T of the previous item's last tile (its dV was issued before, in order),
+          // dP(0) once the previous item's last dQ has left TMEM B
+          mbar_wait(&bars[KV_FULL], I & 1);
+          mbar_wait(&bars[Q_FULL0 + (T & 1)], (T >> 1) & 1);
           tc_fence_after();
-          if (n == 0) QA_TL2(3);
-          if (n == 1) QA_TL2(5);
-          if (n == 2) QA_TL2(6);
-          if (n == 4) QA_TL2(16);
-          if (n == 5) QA_TL2(21);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)                           // contraction over the 128 queries, 16 per instruction
-            umma_f16_ts(tbase + tDV, tbase + tA + (k >> 2) * 64 + (k & 3) * 8, umma_smem_desc(a_do + k * 2048, kAtom, 1024, kSwz128),
-                        id_dv, (n > 0) || (k > 0));
-          umma_commit(&bars[DO_FREE]);
-          if (n + 1 < nt) {
-            mbar_wait(&bars[Q_FULL0 + (st ^ 1)], ((n + 1) >> 1) & 1);
-            tc_fence_after();
-            issue_s(st ^ 1);                                    // overwrites P^T(n): tcgen05.mma of one thread execute in order
-          }
-          if (n == 4) QA_TL2(17);
-          mbar_wait(&bars[DS_READY], n & 1);
+          QA_TL2(2);
+          issue_s(T & 1);
+          mbar_wait(&bars[DO_FULL], T & 1);
+          if (T > 0) mbar_wait(&bars[DQ_FREE], (T - 1) & 1);
           tc_fence_after();
-          if (n == 0) QA_TL2(4);
-          if (n == 4) QA_TL2(18);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)                           // contraction over the 128 keys
-            umma_f16_ss(tbase + tB, umma_smem_desc(a_ds + k * 2048, kAtom, 1024, kSwz128),
-                        umma_smem_desc(a_k + k * 2048, kAtom, 1024, kSwz128), id_dq, k > 0);
-          umma_commit(&bars[DQ_FULL]);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)                           // contraction over the 128 queries
-            umma_f16_ss(tbase + tDK, umma_smem_desc(a_ds + (k >> 2) * kAtom + (k & 3) * 32, 16, 1024, kSwz128),
-                        umma_smem_desc(a_q + k * 2048, kAtom, 1024, kSwz128), id_dk, (n > 0) || (k > 0));
-          umma_commit(&bars[Q_FREE0 + st]);
-          umma_commit(&bars[DS_FREE]);
-          if (n == 4) QA_TL2(19);
-          if (n + 1 < nt) {
-            mbar_wait(&bars[DO_FULL], (n + 1) & 1);
-            mbar_wait(&bars[DQ_FREE], n & 1);
+          issue_dp();
+          for (int n = 0; n < it.nt; ++n, ++T) {
+            const int st = T & 1;
+            const uint32_t a_q = smem_u32(smem + L::off_q + st * L::kTile);
+            mbar_wait(&bars[P_READY], T & 1);
+            if (n == 0 && I > 0) mbar_wait(&bars[ACC_FREE], (I - 1) & 1);   // the drain warps hold dV / dK of the previous item
             tc_fence_after();
-            if (n == 4) QA_TL2(20);
-            issue_dp();
+            if (n == 0) QA_TL2(3);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)                           // contraction over the 128 queries, 16 per instruction
+              umma_f16_ts(tbase + tDV, tbase + tA + (k >> 2) * 64 + (k & 3) * 8, umma_smem_desc(a_do + k * 2048, kAtom, 1024, kSwz128),
+                          id_dv, (n > 0) || (k > 0));
+            umma_commit(&bars[DO_FREE]);
+            if (n + 1 < it.nt) {
+              mbar_wait(&bars[Q_FULL0 + (st ^ 1)], ((T + 1) >> 1) & 1);
+              tc_fence_after();
+              issue_s(st ^ 1);                                    // overwrites P^T(n): tcgen05.mma of one thread execute in order
+            }
+            mbar_wait(&bars[DS_READY], T & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)                           // contraction over the 128 keys
+              umma_f16_ss(tbase + tB, umma_smem_desc(a_ds + k * 2048, kAtom, 1024, kSwz128),
+                          umma_smem_desc(a_k + k * 2048, kAtom, 1024, kSwz128), id_dq, k > 0);
+            umma_commit(&bars[DQ_FULL]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)                           // contraction over the 128 queries
+              umma_f16_ss(tbase + tDK, umma_smem_desc(a_ds + (k >> 2) * kAtom + (k & 3) * 32, 16, 1024, kSwz128),
+                          umma_smem_desc(a_q + k * 2048, kAtom, 1024, kSwz128), id_dk, (n > 0) || (k > 0));
+            umma_commit(&bars[Q_FREE0 + st]);
+            umma_commit(&bars[DS_FREE]);
+            if (n + 1 < it.nt) {
+              mbar_wait(&bars[DO_FULL], (T + 1) & 1);
+              mbar_wait(&bars[DQ_FREE], T & 1);
+              tc_fence_after();
+              issue_dp();
+            }
           }
+          umma_commit(&bars[ACC_FULL]);                           // every MMA of the item is complete: K / V may be replaced
+          if (!next_item(I, it, false)) break;
         }
-        umma_commit(&bars[ACC_FULL]);
       }
       __syncwarp();
     } else if (warp == 13) {
       // =========================== TMA loads ===========================
       if (elect_one()) {
-        mbar_expect_tx(&bars[KV_FULL], 2 * L::kTile);
+        uint32_t T = 0;
+        Bf16Bwd2Item it = bf16_bwd2_item(blockIdx.x, p.BH, nkt, nq, p.causal);
+        for (uint32_t I = 0;; ++I) {
+          const int head_row0 = it.bh * p.S;
+          {                                                       // query I: claim the item after this one
+            const int s = I & 1;
+            if (I >= 2) mbar_wait(&bars[CLC_FREE0 + s], ((I >> 1) - 1) & 1);
+            mbar_expect_tx(&bars[CLC_FULL0 + s], 16);
+            clc_try_cancel(clc_a + s * 16, &bars[CLC_FULL0 + s]);
+          }
+          for (int n = 0; n < it.nt; ++n, ++T) {
+            const int st = T & 1;
+            const int r0 = head_row0 + (it.i0 + n) * 128;
+            if (T >= 2) mbar_wait(&bars[Q_FREE0 + st], ((T >> 1) - 1) & 1);
+            mbar_expect_tx(&bars[Q_FULL0 + st], L::kTile + 1024);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          tma_load_2d(smem + L::off_k + a * kAtom, &tm_k, &bars[KV_FULL], a * 64, (int)head_row0 + j * 128);
-          tma_load_2d(smem + L::off_v + a * kAtom, &tm_v, &bars[KV_FULL], a * 64, (int)head_row0 + j * 128);
-        }
-        for (int n = 0; n < nt; ++n) {
-          const int st = n & 1;
-          const int r0 = (int)head_row0 + (i0 + n) * 128;
-          if (n >= 2) mbar_wait(&bars[Q_FREE0 + st], ((n >> 1) - 1) & 1);
-          mbar_expect_tx(&bars[Q_FULL0 + st], L::kTile + 1024);
+            for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_q + st * L::kTile + a * kAtom, &tm_q, &bars[Q_FULL0 + st], a * 64, r0);
+            bulk_load_1d(ld_s + st * 256, p.lse + r0, 512, &bars[Q_FULL0 + st]);
+            bulk_load_1d(ld_s + st * 256 + 128, p.delta + r0, 512, &bars[Q_FULL0 + st]);
+            if (T >= 1) mbar_wait(&bars[DO_FREE], (T - 1) & 1);  // dV of the previous tile, the last reader of the dO tile
+            mbar_expect_tx(&bars[DO_FULL], L::kTile);
 #pragma unroll
-          for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_q + st * L::kTile + a * kAtom, &tm_q, &bars[Q_FULL0 + st], a * 64, r0);
-          bulk_load_1d(ld_s + st * 256, p.lse + r0, 512, &bars[Q_FULL0 + st]);
-          bulk_load_1d(ld_s + st * 256 + 128, p.delta + r0, 512, &bars[Q_FULL0 + st]);
-          if (n >= 1) mbar_wait(&bars[DO_FREE], (n - 1) & 1);  // dV of the previous tile, the last reader of the dO tile
-          mbar_expect_tx(&bars[DO_FULL], L::kTile);
+            for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_do + a * kAtom, &tm_do, &bars[DO_FULL], a * 64, r0);
+            if (n == 0) {                                         // K / V after the first Q / dO tile: they wait for the previous item
+              if (I > 0) mbar_wait(&bars[ACC_FULL], (I - 1) & 1);
+              mbar_expect_tx(&bars[KV_FULL], 2 * L::kTile);
 #pragma unroll
-          for (int a = 0; a < 2; ++a) tma_load_2d(smem + L::off_do + a * kAtom, &tm_do, &bars[DO_FULL], a * 64, r0);
+              for (int a = 0; a < 2; ++a) {
+                tma_load_2d(smem + L::off_k + a * kAtom, &tm_k, &bars[KV_FULL], a * 64, head_row0 + it.j * 128);
+                tma_load_2d(smem + L::off_v + a * kAtom, &tm_v, &bars[KV_FULL], a * 64, head_row0 + it.j * 128);
+              }
+            }
+          }
+          int x;
+          mbar_wait(&bars[CLC_FULL0 + (I & 1)], (I >> 1) & 1);
+          if (!clc_read(clc_a + (I & 1) * 16, x)) break;
+          it = bf16_bwd2_item(x, p.BH, nkt, nq, p.causal);
         }
       }
       __syncwarp();
@@ -396,7 +462,6 @@ bf16_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 12) tmem_dealloc<512>(tbase);
-  if (tid == 0) QA_TL2(14);
 }
 
 #ifdef QA_DEV_TIMELINE
@@ -409,8 +474,8 @@ extern "C" int qa_debug_set_bf16_bwd_timeline(void* buf) {
 }
 #endif
 
-int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* lse, const float* delta,
-                       float* dq, float* dk, float* dv, int BH, int S, int S_valid, int causal, cudaStream_t st) {
+int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* do_bf16, const float* dO_f32, const float* lse,
+                       const float* delta, float* dq, float* dk, float* dv, int BH, int S, int S_valid, int causal, cudaStream_t st) {
   using L = Bf16Bwd2Smem;
   constexpr int D = 128;
   CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
@@ -418,18 +483,17 @@ int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* 
   uint64_t str[1] = {(uint64_t)D * 2};
   uint32_t box[2] = {64, 128};
   uint64_t str32[1] = {(uint64_t)D * 4};
-  uint32_t box32[2] = {32, 128};
-  uint32_t boxq[2] = {32, 32};                        // dQ: one drain warp's 32 query rows
+  uint32_t boxq[2] = {32, 32};                        // dQ / dK / dV: one drain warp's 32 rows x 32 columns
   int rc;
   if ((rc = qa_make_tmap(&tq, q, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tdo, do_bf16, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dims, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tdq, dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, boxq, 3))) return rc;
-  if ((rc = qa_make_tmap(&tdk, dk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, box32, 3))) return rc;
-  if ((rc = qa_make_tmap(&tdv, dv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, box32, 3))) return rc;
+  if ((rc = qa_make_tmap(&tdk, dk, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, boxq, 3))) return rc;
+  if ((rc = qa_make_tmap(&tdv, dv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, str32, boxq, 3))) return rc;
   Bf16BwdParams2 p;
-  p.lse = lse; p.delta = delta; p.S = S; p.S_valid = S_valid; p.causal = causal;
+  p.lse = lse; p.delta = delta; p.dO_f32 = dO_f32; p.S = S; p.S_valid = S_valid; p.causal = causal; p.BH = BH;
   p.sm_scale = (float)(1.0 / sqrt((double)D));
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
 #ifdef QA_DEV_TIMELINE
@@ -439,7 +503,7 @@ int launch_bf16_bwd_ws(const void* q, const void* k, const void* v, const void* 
 #endif
   cudaError_t e = cudaFuncSetAttribute(bf16_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  dim3 grid(S / 128, BH);
+  dim3 grid(((S_valid + 127) / 128) * BH);             // one CTA per item; running CTAs take over the items of pending ones
   bf16_bwd_ws_kernel<<<grid, 512, L::total, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, p);
   return qa_check_launch("qa_bf16_bwd(ws)");
 }
