@@ -19,7 +19,7 @@ Multi-GPU: batch x head sharding, no collective on the data path.  The headline 
   ring_kv        : (N > 1) BASELINE configs[4], int8 long-context forward B=1 H=32 S=131072 D=128 sequence-sharded over the
                    ranks with the NCCL ring (send/recv of the int8 K/V shard overlapped with the kernel): total TOPS,
                    per-step kernel and transfer times, how much of the transfer the kernel hides
-  other_paths    : (N = 1) the other BASELINE configs at kernel level: int8 fwd configs[0], bf16 fwd S=8k D=128,
+  other_paths    : (N = 1) the other BASELINE configs at kernel level: int8 fwd configs[0], bf16 fwd / bwd S=8k D=128,
                    bf16 fwd+bwd configs[1], JVP configs[3], each with its fraction of the in-run measured tensor peak
   peaks_in_run   : torch._int_mm / bf16 matmul 8192^3 best-of-10 on THIS box, the roofline denominators
   pcie           : full-duplex pinned-copy bandwidth of all ranks at once = the floor of `e2e`
@@ -131,6 +131,19 @@ def other_paths(dev, pk):
     res["bf16_cfg2_B4H16S4096D128_causal"] = {"fwd_ms": msf, "fwd_TFLOPS": ff / (msf * 1e-3) / 1e12, "fwd_frac": frac(ff / (msf * 1e-3) / 1e12, b16),
                                               "bwd_kernel_ms": msb, "bwd_TFLOPS": fb / (msb * 1e-3) / 1e12,
                                               "bwd_frac": frac(fb / (msb * 1e-3) / 1e12, b16), "flops": "causal = half of dense"}
+    del q, k, v, dO, O, lse
+    # bf16 backward at S = 8k, D = 128, non-causal, B*H = 32 (kernel time)
+    q, k = [rn(1, 32, 8192, 128) for _ in range(2)]
+    v = rn(1, 32, 8192, 128, dt=torch.bfloat16)
+    dO = rn(1, 32, 8192, 128, dt=torch.float32)
+    O, lse = ops.bf16_fwd(q, k, v, False)
+    ops.TIMING = []
+    timeit(lambda: ops.bf16_bwd(q, k, v, O, lse, False, dO))
+    kt = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "bf16_bwd")
+    ops.TIMING = None
+    msb = kt[len(kt) // 2]
+    t = 10.0 * 32 * 8192 * 8192 * 128 / (msb * 1e-3) / 1e12
+    res["bf16_bwd_S8192_D128"] = {"kernel_ms": msb, "TFLOPS": t, "frac_of_bf16_peak_in_run": frac(t, b16)}
     del q, k, v, dO, O, lse
     # configs[3]: JVP B=16 H=16 S=4096 D=64 (kernel time; the call also casts six fp32 tensors to bf16)
     t6 = [rn(16, 16, 4096, 64, dt=torch.float32) for _ in range(6)]

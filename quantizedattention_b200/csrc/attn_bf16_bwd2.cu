@@ -80,19 +80,19 @@ __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.
 // the hardware to cancel a CTA that has not started yet (cluster launch control) and processes that CTA's item next, which
 // keeps the hardware's dynamic load balance and lets the write-back of one item overlap the loads of the next.
 struct Bf16Bwd2Item { int j, bh, i0, nt; };
-constexpr int kBf16BwdHeadGroup = 16;
-// Launch order (blockIdx.x = w): groups of 16 heads; inside a group key tile j outermost (causal: heaviest first), head innermost.
-// The CTAs running together then stream the Q / dO tiles of at most ~16 heads (L2 resident), and the last group still ends on
-// its lightest items.
+// Launch order (blockIdx.x = w): groups of G heads; inside a group key tile j outermost, head innermost.  Causal: G = 16, so
+// that every group starts with its heaviest items and the last group still ends on its lightest ones, while the CTAs running
+// together stream the Q / dO tiles of at most 16 heads (L2 resident).  Non-causal (equal items): G = 1, one head at a time.
 __device__ __forceinline__ Bf16Bwd2Item bf16_bwd2_item(int w, int BH, int nkt, int nq, int causal) {
-  const int per_group = kBf16BwdHeadGroup * nkt;
-  const int full = BH / kBf16BwdHeadGroup;
-  int g = w / per_group, hg = kBf16BwdHeadGroup;
-  if (g >= full) { g = full; hg = BH - full * kBf16BwdHeadGroup; }
+  const int G = causal ? 16 : 1;
+  const int per_group = G * nkt;
+  const int full = BH / G;
+  int g = w / per_group, hg = G;
+  if (g >= full) { g = full; hg = BH - full * G; }
   const int rem = w - g * per_group;
   Bf16Bwd2Item it;
   it.j = rem / hg;
-  it.bh = g * kBf16BwdHeadGroup + (rem - it.j * hg);
+  it.bh = g * G + (rem - it.j * hg);
   it.i0 = causal ? it.j : 0;                           // query tiles before the diagonal see none of these keys
   it.nt = nq - it.i0;
   return it;

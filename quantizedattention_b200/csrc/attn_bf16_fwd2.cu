@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t bf2u(__nv_bfloat162 v) { return *reinterpret
 template <int D, int STAGES>
 __global__ void __launch_bounds__(320, 1)
 bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, Bf16Fwd2Params p) {
+                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, Bf16Fwd2Params p) {
   using L = Bf16Fwd2Smem<D, STAGES>;
   constexpr int kDAtoms = D / 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -190,18 +190,38 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tc_fence_after();
     const size_t gr = (size_t)bh * p.Sq + grow;
     const float inv_l = 1.0f / l;
-    float* dst = p.O + gr * D;
+    // O rows go out through TMA stores: each warp stages its 32 rows as [32 rows][32 floats] swizzled slices (4 KB) in the
+    // shared memory of this tile's Q (every S MMA of the tile has completed), two rounds
+    constexpr int SL = L::kTile / 16384;                          // slices per warp and round
+    const int w4 = warp & 3;
 #pragma unroll
-    for (int ch = 0; ch < D / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(o_addr + ch * 32, r);
-      tmem_ld_wait();
+    for (int rd = 0; rd < (D / 32) / SL; ++rd) {
+      if (rd > 0) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(dst + ch * 32 + i) =
-            make_float4(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l, __uint_as_float(r[i + 2]) * inv_l,
-                        __uint_as_float(r[i + 3]) * inv_l);
+      for (int sl = 0; sl < SL; ++sl) {
+        uint32_t r[32];
+        tmem_ld32(o_addr + (rd * SL + sl) * 32, r);
+        tmem_ld_wait();
+        const uint32_t base = smem_u32(smem) + L::off_q + x * L::kTile + (sl * 4 + w4) * 4096;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          sts128f(base + swz128(lane, i * 4), __uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l,
+                  __uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int sl = 0; sl < SL; ++sl)
+          tma_store_2d(&tm_o, smem + L::off_q + x * L::kTile + (sl * 4 + w4) * 4096, (rd * SL + sl) * 32,
+                       bh * p.Sq + q0 + x * 128 + w4 * 32);
+        tma_store_commit();
+      }
     }
+    if (lane == 0) tma_store_wait_read();
     p.lse[gr] = __bfloat162float(m_bf) + log2f(l);                             // attention_bf16.py:288
   } else if (warp == 8) {
     // =========================== TMA producer ===========================
@@ -298,11 +318,14 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
                      int causal, float qk_scale, float rescale_tau, cudaStream_t st) {
 
   using L = Bf16Fwd2Smem<D, STAGES>;
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, to;
   uint64_t dq[2] = {(uint64_t)D, (uint64_t)BH * Sq}, dk[2] = {(uint64_t)D, (uint64_t)BH * Sk};
   uint64_t str[1] = {(uint64_t)D * 2};
   uint32_t box[2] = {64, 128};
+  uint64_t stro[1] = {(uint64_t)D * 4};
+  uint32_t boxo[2] = {32, 32};                         // one warp's 32 rows x 32 fp32 columns of O
   int rc;
+  if ((rc = qa_make_tmap(&to, O, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dq, stro, boxo, 3))) return rc;
   if ((rc = qa_make_tmap(&tq, q, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dq, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
@@ -312,7 +335,7 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(Sq / 256, BH);
-  kern<<<grid, 320, L::total, st>>>(tq, tk, tv, p);
+  kern<<<grid, 320, L::total, st>>>(tq, tk, tv, to, p);
   return qa_check_launch("qa_bf16_fwd(2 query tiles)");
 }
 
