@@ -16,8 +16,10 @@ int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
 /* Development aid: per-k-tile SM-clock stamps of CTA (0,0) of the next qa_int8_fwd launches ([64][16] int64); NULL = off */
 int qa_debug_set_int8_fwd_timeline(void* buf);
 int qa_debug_set_int8_bwd_timeline(void* buf_i64_64x2x16);   /* same for qa_int8_bwd: leader warp and warp 5, per q-tile */
-/* per-CTA globaltimer stamps ([CTAs][16] int64, slot 15 = SM id) of the next qa_bf16_bwd launches (D = 128 kernel) */
+/* per-item globaltimer stamps ([head * key tiles + key tile][64] int64) of the next qa_bf16_bwd launches (D = 128 kernel) */
 int qa_debug_set_bf16_bwd_timeline(void* buf);
+/* per-CTA globaltimer stamps ([CTAs][16] int64, slot 15 = SM id) of the next qa_bf16_fwd launches (two-tile kernel) */
+int qa_debug_set_bf16_fwd_timeline(void* buf);
 /* TMEM -> register read bandwidth (tcgen05.ld.32x32b.x32 streamed by every warp): measured ceiling of the drains */
 int qa_probe_tmem_bw(void* sink, int blocks, int threads, int iters, void* stream);
 /* shape: 0 = 32x32b.x32, 1 = 16x256b.x8, 2 = 16x128b.x16, 3 = 16x64b.x32; depth = loads in flight per warp (1, 2) */

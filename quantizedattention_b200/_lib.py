@@ -49,6 +49,7 @@ DEV_SIGNATURES = {
     "qa_debug_set_int8_fwd_timeline": (c_int, [c_void_p]),
     "qa_debug_set_int8_bwd_timeline": (c_int, [c_void_p]),
     "qa_debug_set_bf16_bwd_timeline": (c_int, [c_void_p]),
+    "qa_debug_set_bf16_fwd_timeline": (c_int, [c_void_p]),
     "qa_probe_tmem_bw": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "qa_probe_tmem_bw_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "qa_probe_mma": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_uint] + [c_int] * 6 + [c_void_p]),

@@ -80,19 +80,10 @@ __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.
 // the hardware to cancel a CTA that has not started yet (cluster launch control) and processes that CTA's item next, which
 // keeps the hardware's dynamic load balance and lets the write-back of one item overlap the loads of the next.
 struct Bf16Bwd2Item { int j, bh, i0, nt; };
-// Launch order (blockIdx.x = w): groups of G heads; inside a group key tile j outermost, head innermost.  Causal: G = 16, so
-// that every group starts with its heaviest items and the last group still ends on its lightest ones, while the CTAs running
-// together stream the Q / dO tiles of at most 16 heads (L2 resident).  Non-causal (equal items): G = 1, one head at a time.
+// Launch order (blockIdx.x = w): qa_group_order with G = 16 for causal heads (key tile 0 is the heaviest), G = 1 otherwise.
 __device__ __forceinline__ Bf16Bwd2Item bf16_bwd2_item(int w, int BH, int nkt, int nq, int causal) {
-  const int G = causal ? 16 : 1;
-  const int per_group = G * nkt;
-  const int full = BH / G;
-  int g = w / per_group, hg = G;
-  if (g >= full) { g = full; hg = BH - full * G; }
-  const int rem = w - g * per_group;
   Bf16Bwd2Item it;
-  it.j = rem / hg;
-  it.bh = g * G + (rem - it.j * hg);
+  qa_group_order(w, BH, nkt, causal ? 16 : 1, it.j, it.bh);
   it.i0 = causal ? it.j : 0;                           // query tiles before the diagonal see none of these keys
   it.nt = nq - it.i0;
   return it;

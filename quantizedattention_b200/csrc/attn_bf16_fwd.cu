@@ -30,7 +30,7 @@ struct Bf16FwdSmem {
 struct Bf16FwdParams {
   float* O;        // [BH*Sq, D] fp32
   float* lse;      // [BH*Sq] fp32
-  int Sq, Sk, causal;
+  int Sq, Sk, causal, BH;
   int Sk_valid;        // keys [Sk_valid, Sk) of every head are zero padding (ragged sequence): weight exactly 0
   float qk_scale;
   float rescale_tau;   // see qa_bf16_fwd_ex
@@ -67,8 +67,10 @@ bf16_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ float m_fin[128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y;
-  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;        // heaviest (latest) causal tiles first
+  const int nqt = p.Sq / 128;
+  int rank, bh;
+  qa_group_order((int)blockIdx.x, p.BH, nqt, p.causal ? 16 : 1, rank, bh);
+  const int qt = nqt - 1 - rank;                               // heaviest (latest) causal tiles first
   const int q0 = qt * 128;
   const int nkv = (p.Sk_valid + 127) / 128;                    // k-tiles without a valid key are skipped
   const int nk = p.causal ? min(nkv, qt + 1) : nkv;
@@ -365,7 +367,7 @@ static int launch_bf16_fwd(const void* q, const void* k, const void* v, const Bf
   auto kern = bf16_fwd_kernel<D, NSPLIT, STAGES, PBUF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  dim3 grid(p.Sq / 128, BH);
+  dim3 grid((p.Sq / 128) * BH);                       // order: qa_group_order
   kern<<<grid, 128 * NSPLIT + 192, L::total, st>>>(tq, tk, tv, p);
   int r = qa_check_launch("qa_bf16_fwd");
   if (r) return r;
@@ -396,7 +398,7 @@ extern "C" int qa_bf16_fwd_ragged(const void* q_f16, const void* k_f16, const vo
   if (((uintptr_t)q_f16 | (uintptr_t)k_f16 | (uintptr_t)v_bf16 | (uintptr_t)O_f32) & 15)
     return qa_fail(QA_ERR_ALIGN, "qa_bf16_fwd: 16-byte alignment required");
   Bf16FwdParams p;
-  p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid; p.causal = causal; p.rescale_tau = rescale_tau;
+  p.O = (float*)O_f32; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid; p.causal = causal; p.BH = BH; p.rescale_tau = rescale_tau;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   cudaStream_t st = (cudaStream_t)stream;
   if ((nsplit == 0 || nsplit == 3) && Sq % 256 == 0) {           // default schedule: two query tiles per CTA, P and O in TMEM

@@ -32,11 +32,25 @@ struct Bf16Fwd2Smem {
 struct Bf16Fwd2Params {
   float* O;
   float* lse;
-  int Sq, Sk, causal;
+  int Sq, Sk, causal, BH;
   int Sk_valid;        // keys [Sk_valid, Sk) of every head are zero padding (ragged sequence): weight exactly 0
   float qk_scale;
   float rescale_tau;   // adopt a new running maximum only when it exceeds the current one by more than this (log2 units)
+  long long* dbg;      // development library only: [CTA][16] globaltimer stamps (tools/timeline_bf16_fwd.py)
 };
+
+#ifdef QA_DEV_TIMELINE
+#define QA_TLF(slot)                                                                                      \
+  do {                                                                                                    \
+    if (p.dbg != nullptr) {                                                                               \
+      long long t_;                                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
+      p.dbg[(size_t)blockIdx.x * 16 + (slot)] = t_;                            \
+    }                                                                                                     \
+  } while (0)
+#else
+#define QA_TLF(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ float bf2_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf2_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
@@ -61,8 +75,10 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y;
-  const int pt = (int)gridDim.x - 1 - (int)blockIdx.x;           // pair of query tiles; heaviest causal pairs first
+  const int npair = p.Sq / 256;
+  int rank, bh;
+  qa_group_order((int)blockIdx.x, p.BH, npair, p.causal ? 16 : 1, rank, bh);
+  const int pt = npair - 1 - rank;                                // pair of query tiles; heaviest causal pairs first
   const int q0 = pt * 256;
   const int nk_full = (p.Sk_valid + 127) / 128;                   // k-tiles without a valid key are skipped
   // per query tile: number of k-tiles that contain at least one visible key (strict causal: key < query)
@@ -70,6 +86,10 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int nk = nkx[1];
 
   if (tid == 0) {
+    QA_TLF(0);
+#ifdef QA_DEV_TIMELINE
+    if (p.dbg != nullptr) { uint32_t sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); p.dbg[(size_t)blockIdx.x * 16 + 15] = sm_; }
+#endif
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
@@ -83,6 +103,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
+  if (tid == 0) QA_TLF(1);
 
   if (warp < 8) {
     // =========================== softmax warpgroups: warps 0-3 -> tile A, 4-7 -> tile B ===========================
@@ -105,6 +126,8 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint32_t sb_addr = s_addr + b * 64;
       mbar_wait(&s_full[x][b], j & 1);
       tc_fence_after();
+      if (lane == 0 && (warp & 3) == 0 && t == 0) QA_TLF(2 + x);
+      if (lane == 0 && (warp & 3) == 0 && t == 4) QA_TLF(4 + x);
       // ---- pass 1: u = bf16(S * qk_scale), masked; top-2 of the row segment
       uint32_t u2[32];
       __nv_bfloat162 t1 = u2bf(ninf2), t2 = u2bf(ninf2);
@@ -185,9 +208,11 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x][b]);
     }
+    if (lane == 0 && (warp & 3) == 0) QA_TLF(6 + x);
     // ---- epilogue: O / l and the log2-LSE, straight from the resident accumulator
     mbar_wait(&o_full[x][(nst - 1) & 1], ((nst - 1) >> 1) & 1);
     tc_fence_after();
+    if (lane == 0 && (warp & 3) == 0) QA_TLF(8 + x);
     const size_t gr = (size_t)bh * p.Sq + grow;
     const float inv_l = 1.0f / l;
     // O rows go out through TMA stores: each warp stages its 32 rows as [32 rows][32 floats] swizzled slices (4 KB) in the
@@ -223,6 +248,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     if (lane == 0) tma_store_wait_read();
     p.lse[gr] = __bfloat162float(m_bf) + log2f(l);                             // attention_bf16.py:288
+    if (lane == 0 && (warp & 3) == 0) QA_TLF(10 + x);
   } else if (warp == 8) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
@@ -311,7 +337,18 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc<512>(tbase);
+  if (tid == 0) QA_TLF(12);
 }
+
+#ifdef QA_DEV_TIMELINE
+static void* g_bf16_fwd_dbg = nullptr;
+// Development library only (include/qattn_dev.h, tools/timeline_bf16_fwd.py): per-CTA globaltimer stamps of subsequent
+// qa_bf16_fwd launches of the two-tile kernel ([CTAs][16] int64); NULL = off.
+extern "C" int qa_debug_set_bf16_fwd_timeline(void* buf) {
+  g_bf16_fwd_dbg = buf;
+  return 0;
+}
+#endif
 
 template <int D, int STAGES>
 int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, float* lse, int BH, int Sq, int Sk, int Sk_valid,
@@ -330,11 +367,16 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
   if ((rc = qa_make_tmap(&tk, k, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   if ((rc = qa_make_tmap(&tv, v, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, dk, str, box, 3))) return rc;
   Bf16Fwd2Params p;
-  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid; p.causal = causal; p.qk_scale = qk_scale; p.rescale_tau = rescale_tau;
+  p.O = O; p.lse = lse; p.Sq = Sq; p.Sk = Sk; p.Sk_valid = Sk_valid; p.causal = causal; p.BH = BH; p.qk_scale = qk_scale; p.rescale_tau = rescale_tau;
+#ifdef QA_DEV_TIMELINE
+  p.dbg = (long long*)g_bf16_fwd_dbg;
+#else
+  p.dbg = nullptr;
+#endif
   auto kern = bf16_fwd2_kernel<D, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  dim3 grid(Sq / 256, BH);
+  dim3 grid((Sq / 256) * BH);                         // order: qa_group_order
   kern<<<grid, 320, L::total, st>>>(tq, tk, tv, to, p);
   return qa_check_launch("qa_bf16_fwd(2 query tiles)");
 }

@@ -323,4 +323,18 @@ __device__ __host__ __forceinline__ uint32_t swz128(uint32_t row, uint32_t byte_
   return row * 128u + ((((byte_in_row >> 4) ^ (row & 7u)) << 4) | (byte_in_row & 15u));
 }
 
+
+// Launch order of (tile, head) work for causal attention: blockIdx.x = w enumerates groups of G heads; inside a group the
+// tile rank r (0 = heaviest) is outermost and the head innermost.  With G = 16 every group starts with its heaviest tiles and
+// the last group still ends on its lightest ones (the hardware hands CTAs out in order), while the CTAs running together
+// touch at most 16 heads' K / V or Q / dO streams.  G = 1 is plain head-major order.
+__device__ __forceinline__ void qa_group_order(int w, int n_heads, int n_tiles, int G, int& rank, int& head) {
+  const int per_group = G * n_tiles;
+  const int full = n_heads / G;
+  int g = w / per_group, hg = G;
+  if (g >= full) { g = full; hg = n_heads - full * G; }
+  const int rem = w - g * per_group;
+  rank = rem / hg;
+  head = g * G + (rem - rank * hg);
+}
 }  // namespace qa
