@@ -489,7 +489,8 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   const bool quant_role = warp < 8;
   const int rw = warp & 7;                                      // warp index inside the role
   // Three issuing threads in the drain role, on different SM sub-partitions (a tcgen05.mma / TMA issue blocks its thread):
-  // 256: Q/dO loads, dQ, dV/dK;  288: S and dP of the next tile;  320: the TMA reduce-add of the dQ staging tile
+  // 256: Q/dO loads, dQ, dV/dK;  288: S of the next tile;  320: the TMA reduce-add of the dQ staging tile.  dP of the next tile is
+  // issued by thread 0 (quantise role) as soon as that role has released the dP columns
   const bool leader = (tid == 256), leader_sdp = (tid == 288), leader_red = (tid == 320);
   const int bh = blockIdx.y, j = blockIdx.x;
   const int nq = (p.S_valid + 127) / 128;                       // fully padded query tiles are skipped
@@ -500,7 +501,8 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 
   if (tid == 0) {
     mbar_init(&kv_full, 1); mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
-    mbar_init(&sd_full, 1); mbar_init(&parts_full, 1); mbar_init(&dq_full, 1); mbar_init(&pds_full, 8); mbar_init(&s_free, 1);
+    mbar_init(&sd_full, 2);                                // the S commit (drain role) + the dP commit (quantise role)
+    mbar_init(&parts_full, 1); mbar_init(&dq_full, 1); mbar_init(&pds_full, 8); mbar_init(&s_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_s);
@@ -663,6 +665,26 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (lane == 0) mbar_arrive(&pds_full);
       if (warp == 0) QA_TLW(0, 5);
       QA_TLW(0, 6 + warp);                                         // pass-2 end of every quantise warp (skew between them)
+      if (warp == 0) {
+        // dP of the next tile is issued from the role that waits for it, as soon as every quantise warp has released the dP
+        // columns (pds_full), instead of when the drain role comes round to it (a tcgen05.mma issue blocks its thread until
+        // the tensor pipe takes the instruction: here it blocks a warp that has nothing else to do)
+        if (lane == 0 && t + 1 < nt) {
+          constexpr uint32_t id_s = umma_idesc(2, 1, 1, 0, 0, 128, 128), id_c128 = umma_idesc(1, 0, 0, 0, 0, 128, 128);
+          const int st = (t + 1) & 1;
+          mbar_wait(&pds_full, ph);
+          mbar_wait(&qdo_full[st], ((t + 1) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_do = smem_u32(smem + L::off_do + st * L::kTile), a_v = smem_u32(smem + L::off_v);
+          umma_f16_ss(tbase + 128, umma_smem_desc(smem_u32(smem + L::off_c), 16, 0, kLay), umma_smem_desc(smem_u32(smem + L::off_c + 1024), 16, 0, kLay),
+                      id_c128, 0);                                  // dP = kMagic
+  #pragma unroll
+          for (int k = 0; k < D / 32; ++k)
+            umma_i8_ss(tbase + 128, umma_smem_desc(a_do + k * 32, 16, kSbo, kLay), umma_smem_desc(a_v + k * 32, 16, kSbo, kLay), id_s, 1);
+          umma_commit(&sd_full);
+        }
+        __syncwarp();
+      }
     }
   } else {
     // =========================== drain role: accumulators, dQ staging, TMA / MMA issue ===========================
@@ -725,6 +747,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       mbar_wait(&kv_full, 0);
       mbar_wait(&qdo_full[0], 0);
       issue_s(0);
+      umma_commit(&sd_full);
       issue_dp(0);
     }
     float2 dv_acc[DH / 2], dk_acc[DH / 2];                        // fp32x2: FFMA2 / FMUL2 / FADD2 halve the issue slots
@@ -799,6 +822,7 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc_fence_after();
         mbar_wait(&qdo_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
         issue_s((t + 1) & 1);
+        umma_commit(&sd_full);                                     // second arrival: the dP commit of the quantise role
       }
       if (warp == 8) QA_TLW(1, 10);
       if (t > 0) {                                                 // dQ partial of tile t-1 -> staging tile
@@ -813,11 +837,6 @@ int8_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       named_bar_sync(2, NT);                                      // staging tile complete, dQ partial columns drained
       if (warp == 8) QA_TLW(1, 13);
       if (leader_red && t > 0) reduce_dq(tq - 1);
-      if (leader_sdp && t + 1 < nt) {                              // dP of the next tile once pass 2 has released its columns
-        mbar_wait(&pds_full, ph);
-        tc_fence_after();
-        issue_dp((t + 1) & 1);                                     // its commit (sd_full) also covers the S MMAs above
-      }
       if (leader) {
         QA_TLW(1, 0);
         mbar_wait(&pds_full, ph);                                  // P / dS tiles of tile t stored
