@@ -61,18 +61,22 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 __device__ __forceinline__ __nv_bfloat162 u2bf(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
 __device__ __forceinline__ uint32_t bf2u(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
-template <int D, int STAGES>
-__global__ void __launch_bounds__(320, 1)
+template <int D, int STAGES, int KS>
+__global__ void __launch_bounds__(576, 1)
 bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, Bf16Fwd2Params p) {
   using L = Bf16Fwd2Smem<D, STAGES>;
   constexpr int kDAtoms = D / 64;
+  constexpr int NB = 128 / KS;                                   // S / P buffers per query tile: steps of KS keys
+  static_assert(KS == 64 || KS == 128, "keys per softmax step");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
   __shared__ uint64_t s_full[2][2], p_full[2][2], o_full[2][2], o_ready[2][2];   // [query tile][S buffer]: a softmax warp may run up to two steps ahead
                                                                                    // of the issuer, so every barrier is per buffer (a single one aliases parities)
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t xtop[2][2][2][128];      // [query tile][step parity][column half][row]: packed (top1, top2) bf16
+  __shared__ float xl[2][128];                 // row sums of column half 1
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int npair = p.Sq / 256;
@@ -93,56 +97,60 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x][0], 1); mbar_init(&s_full[x][1], 1); mbar_init(&p_full[x][0], 4); mbar_init(&p_full[x][1], 4);
-      mbar_init(&o_full[x][0], 1); mbar_init(&o_full[x][1], 1); mbar_init(&o_ready[x][0], 4); mbar_init(&o_ready[x][1], 4);
+      mbar_init(&s_full[x][0], 1); mbar_init(&s_full[x][1], 1); mbar_init(&p_full[x][0], 8); mbar_init(&p_full[x][1], 8);
+      mbar_init(&o_full[x][0], 1); mbar_init(&o_full[x][1], 1); mbar_init(&o_ready[x][0], 8); mbar_init(&o_ready[x][1], 8);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(&tmem_base_s);
+  if (warp == 17) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
   if (tid == 0) QA_TLF(1);
 
-  if (warp < 8) {
-    // =========================== softmax warpgroups: warps 0-3 -> tile A, 4-7 -> tile B ===========================
-    const int x = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t s_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + x * 128;
-    const uint32_t o_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + 256 + x * 128;
+  if (warp < 16) {
+    // =========================== softmax warps: 0-7 -> tile A, 8-15 -> tile B; two warps per 32-row group, ===========================
+    // each with half of the step's key columns (one warp per row was the limiter once S moved to N = 128 instructions: the
+    // softmax of one tile has to fit in the tensor-pipe time of the other tile)
+    const int x = warp >> 3, hf = (warp >> 2) & 1, qd = warp & 3;
+    constexpr int KH = KS / 2;                                     // key columns per warp and step
+    const int row = qd * 32 + lane;
+    const uint32_t s_addr = tbase + ((uint32_t)(qd * 32) << 16) + x * 128;
+    const uint32_t o_addr = tbase + ((uint32_t)(qd * 32) << 16) + 256 + x * 128;
     const int grow = q0 + x * 128 + row;                          // query index inside the head
     const int qt = 2 * pt + x;                                    // this tile's diagonal k-tile
-    const int nst = 2 * nkx[x];                                   // 64-key steps of this query tile
+    const int nst = NB * nkx[x];                                  // KS-key steps of this query tile
     __nv_bfloat16 m_bf = __float2bfloat16(-INFINITY);
-    float l = 1.0f;                                               // attention_bf16.py:198
+    float l = hf == 0 ? 1.0f : 0.0f;                              // attention_bf16.py:198 (the two column halves add up)
     const uint32_t ninf2 = 0xff80ff80u;
     const float2 qk2 = make_float2(p.qk_scale, p.qk_scale);
     for (int t = 0; t < nst; ++t) {
-      const int j = t >> 1, b = t & 1;
+      const int j = t / NB, b = t % NB;
+      const uint32_t bph = (t / NB) & 1;                           // phase of this step's barriers (one per buffer)
       const bool diag = p.causal && (j == qt);
-      const bool tail = (t + 1) * 64 > p.Sk_valid;                 // ragged: this 64-key step holds padding
+      const bool tail = (t + 1) * KS > p.Sk_valid;                 // ragged: this step holds padding
       const int klim = diag ? min(grow, p.Sk_valid) : p.Sk_valid;  // first key without weight
-      const uint32_t sb_addr = s_addr + b * 64;
-      mbar_wait(&s_full[x][b], j & 1);
+      const uint32_t sb_addr = s_addr + b * KS;
+      mbar_wait(&s_full[x][b], bph);
       tc_fence_after();
-      if (lane == 0 && (warp & 3) == 0 && t == 0) QA_TLF(2 + x);
-      if (lane == 0 && (warp & 3) == 0 && t == 4) QA_TLF(4 + x);
-      // ---- pass 1: u = bf16(S * qk_scale), masked; top-2 of the row segment
-      uint32_t u2[32];
+      if (lane == 0 && qd == 0 && hf == 0 && t == 0) QA_TLF(2 + x);
+      if (lane == 0 && qd == 0 && hf == 0 && t == 4) QA_TLF(4 + x);
+      // ---- pass 1: u = bf16(S * qk_scale), masked; top-2 of this warp's column half
+      uint32_t u2[KH / 2];
       __nv_bfloat162 t1 = u2bf(ninf2), t2 = u2bf(ninf2);
       auto pass1 = [&](auto masked) {                              // two instantiations: the mask costs nothing off-diagonal
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+        for (int ch = 0; ch < KH / 32; ++ch) {
           uint32_t r[32];
-          tmem_ld32(sb_addr + ch * 32, r);
+          tmem_ld32(sb_addr + hf * KH + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const __nv_bfloat162 ub = __float22bfloat162_rn(__fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), qk2));
             uint32_t u = bf2u(ub);                                 // u = bf16(S * qk_scale), one FMUL2 + one pack per pair
             if (decltype(masked)::value) {                         // strict causal: keep key < query; ragged: key < Sk_valid
-              const int key = t * 64 + ch * 32 + 2 * i;
+              const int key = t * KS + hf * KH + ch * 32 + 2 * i;
               if (key >= klim) u = (u & 0xffff0000u) | 0xff80u;
               if (key + 1 >= klim) u = (u & 0x0000ffffu) | 0xff800000u;
             }
@@ -155,8 +163,17 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       };
       if (diag || tail) pass1(std::true_type{}); else pass1(std::false_type{});
       const __nv_bfloat16 a1 = __low2bfloat16(t1), b1 = __high2bfloat16(t1), a2 = __low2bfloat16(t2), b2 = __high2bfloat16(t2);
-      const __nv_bfloat16 top1 = __hmax(a1, b1);
-      const __nv_bfloat16 top2 = __hmax(__hmin(a1, b1), __hmax(a2, b2));
+      __nv_bfloat16 top1 = __hmax(a1, b1);
+      __nv_bfloat16 top2 = __hmax(__hmin(a1, b1), __hmax(a2, b2));
+      {                                                            // top-2 of the whole row: exchange with the warp of the other half
+        __nv_bfloat162 mine = __halves2bfloat162(top1, top2);
+        xtop[x][t & 1][hf][row] = bf2u(mine);
+        named_bar_sync(1 + x * 4 + qd, 64);
+        const __nv_bfloat162 oth = u2bf(xtop[x][t & 1][hf ^ 1][row]);
+        const __nv_bfloat16 o1 = __low2bfloat16(oth), o2 = __high2bfloat16(oth);
+        top2 = __hmax(__hmin(top1, o1), __hmax(top2, o2));
+        top1 = __hmax(top1, o1);
+      }
       // ---- bias-corrected running max (attention_bf16.py:236-264, predicate in the scaled domain)
       __nv_bfloat16 m_new = __hmax(m_bf, top1);
       const __nv_bfloat16 thr = __float2bfloat16(__bfloat162float(m_new) - 1e-3f);
@@ -170,55 +187,65 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const float resc = __bfloat162float(__float2bfloat16(ex2_approx(__bfloat162float(__hsub(m_bf, m_new)))));
       m_bf = m_new;
       if (t > 0 && __any_sync(0xffffffffu, resc != 1.0f)) {       // O *= rescale (:280): rare with the lazy maximum
-        mbar_wait(&o_full[x][b ^ 1], ((t - 1) >> 1) & 1);        // P V of step t-1 has landed in TMEM
+        mbar_wait(&o_full[x][(t - 1) % NB], ((t - 1) / NB) & 1); // P V of step t-1 has landed in TMEM
         tc_fence_after();
         const float2 rs2 = make_float2(resc, resc);
 #pragma unroll
-        for (int ch = 0; ch < D / 32; ++ch) {
+        for (int ch = 0; ch < D / 64; ++ch) {                      // this warp's half of the D columns
           uint32_t r[32];
-          tmem_ld32(o_addr + ch * 32, r);
+          tmem_ld32(o_addr + hf * (D / 2) + ch * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 o2 = __fmul2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), rs2);
             r[i] = __float_as_uint(o2.x); r[i + 1] = __float_as_uint(o2.y);
           }
-          tmem_st32(o_addr + ch * 32, r);
+          tmem_st32(o_addr + hf * (D / 2) + ch * 32, r);
         }
         tmem_st_wait();
         tc_fence_before();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_ready[x][b]);                 // the MMA warp may accumulate step t into O
-      // ---- pass 2: P = bf16(exp2(bf16(u - m'))) written back over the S columns (2 per column), l += sum(P)
+      // ---- pass 2: P = bf16(exp2(bf16(u - m'))) written back over the S columns (2 per column), l += sum(P).  Both warps
+      //      of the row group are past pass 1 (the exchange above), so the P columns of the other half may be overwritten.
       const __nv_bfloat162 m2 = __bfloat162bfloat162(m_new);
       float2 ls2 = make_float2(0.f, 0.f);
-      uint32_t w[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const uint32_t d = bf2u(__hsub2(u2bf(u2[i]), m2));
-        const uint32_t pp = pack2_bf16(ex2_approx(bf2_lo(d)), ex2_approx(bf2_hi(d)));
-        ls2 = __fadd2_rn(ls2, make_float2(bf2_lo(pp), bf2_hi(pp)));
-        w[i] = pp;
+      for (int g = 0; g < KH / 64 + (KH < 64 ? 1 : 0); ++g) {
+        constexpr int NW = KH < 64 ? KH / 2 : 32;
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const uint32_t d = bf2u(__hsub2(u2bf(u2[g * 32 + i]), m2));
+          const uint32_t pp = pack2_bf16(ex2_approx(bf2_lo(d)), ex2_approx(bf2_hi(d)));
+          ls2 = __fadd2_rn(ls2, make_float2(bf2_lo(pp), bf2_hi(pp)));
+          w[i] = pp;
+        }
+        if constexpr (NW == 32) tmem_st32(sb_addr + hf * (KH / 2) + g * 32, w);
+        else tmem_st16(sb_addr + hf * (KH / 2), w);
       }
-      tmem_st32(sb_addr, w);
       tmem_st_wait();
       l = l * resc + (ls2.x + ls2.y);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x][b]);
     }
-    if (lane == 0 && (warp & 3) == 0) QA_TLF(6 + x);
-    // ---- epilogue: O / l and the log2-LSE, straight from the resident accumulator
-    mbar_wait(&o_full[x][(nst - 1) & 1], ((nst - 1) >> 1) & 1);
+    if (lane == 0 && qd == 0 && hf == 0) QA_TLF(6 + x);
+    // ---- epilogue (the warps of column half 0): O / l and the log2-LSE, straight from the resident accumulator
+    if (hf == 1) xl[x][row] = l;
+    named_bar_sync(1 + x * 4 + qd, 64);
+    if (hf == 0) {
+    l += xl[x][row];
+    mbar_wait(&o_full[x][(nst - 1) % NB], ((nst - 1) / NB) & 1);
     tc_fence_after();
-    if (lane == 0 && (warp & 3) == 0) QA_TLF(8 + x);
+    if (lane == 0 && qd == 0) QA_TLF(8 + x);
     const size_t gr = (size_t)bh * p.Sq + grow;
     const float inv_l = 1.0f / l;
     // O rows go out through TMA stores: each warp stages its 32 rows as [32 rows][32 floats] swizzled slices (4 KB) in the
     // shared memory of this tile's Q (every S MMA of the tile has completed), two rounds
     constexpr int SL = L::kTile / 16384;                          // slices per warp and round
-    const int w4 = warp & 3;
+    const int w4 = qd;
 #pragma unroll
     for (int rd = 0; rd < (D / 32) / SL; ++rd) {
       if (rd > 0) {
@@ -248,8 +275,9 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     if (lane == 0) tma_store_wait_read();
     p.lse[gr] = __bfloat162float(m_bf) + log2f(l);                             // attention_bf16.py:288
-    if (lane == 0 && (warp & 3) == 0) QA_TLF(10 + x);
-  } else if (warp == 8) {
+    if (lane == 0 && qd == 0) QA_TLF(10 + x);
+    }
+  } else if (warp == 16) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
@@ -277,43 +305,44 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   } else {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc(1, 0, 0, 0, 0, 128, 64);         // f32 += f16 x f16, K-major, 64 keys
+      constexpr uint32_t idesc_qk = umma_idesc(1, 0, 0, 0, 0, 128, KS);         // f32 += f16 x f16, K-major, KS keys
       constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // f32 += bf16 (TMEM) x bf16 (V MN-major)
-      auto issue_qk = [&](int x, int t) {                                        // S_x[t&1] = Q_x K_step(t)^T
-        const int s = (t >> 1) % STAGES, h = t & 1;
+      auto issue_qk = [&](int x, int t) {                                        // S_x[t % NB] = Q_x K_step(t)^T
+        const int s = (t / NB) % STAGES, h = t % NB;
         const uint32_t q_addr = smem_u32(smem + L::off_q + x * L::kTile);
-        const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile) + h * (64 * 128);   // rows 64.. of every 64-column atom
+        const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile) + h * (KS * 128);   // rows h * KS .. of every 64-column atom
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t o = (k >> 2) * kAtom2 + (k & 3) * 32;
-          umma_f16_ss(tbase + x * 128 + h * 64, umma_smem_desc(q_addr + o, 16, 1024, kSwz128), umma_smem_desc(k_addr + o, 16, 1024, kSwz128),
+          umma_f16_ss(tbase + x * 128 + h * KS, umma_smem_desc(q_addr + o, 16, 1024, kSwz128), umma_smem_desc(k_addr + o, 16, 1024, kSwz128),
                       idesc_qk, k > 0);
         }
         umma_commit(&s_full[x][h]);
       };
       auto issue_pv = [&](int x, int t) {                                        // O_x += P_x V_step(t), P from TMEM
-        const int s = (t >> 1) % STAGES, h = t & 1;
-        mbar_wait(&p_full[x][h], (t >> 1) & 1);
-        mbar_wait(&o_ready[x][h], (t >> 1) & 1);
+        const int s = (t / NB) % STAGES, h = t % NB;
+        mbar_wait(&p_full[x][h], (t / NB) & 1);
+        mbar_wait(&o_ready[x][h], (t / NB) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile) + h * (4 * 2048);
+        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile) + h * ((KS / 16) * 2048);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ts(tbase + 256 + x * 128, tbase + x * 128 + h * 64 + k * 8, umma_smem_desc(v_addr + k * 2048, kAtom2, 1024, kSwz128),
+        for (int k = 0; k < KS / 16; ++k)
+          umma_f16_ts(tbase + 256 + x * 128, tbase + x * 128 + h * KS + k * 8, umma_smem_desc(v_addr + k * 2048, kAtom2, 1024, kSwz128),
                       idesc_pv, (t > 0) || (k > 0));
         umma_commit(&o_full[x][h]);
       };
-      const int nst[2] = {2 * nkx[0], 2 * nkx[1]};
+      const int nst[2] = {NB * nkx[0], NB * nkx[1]};
       mbar_wait(&q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      issue_qk(0, 1);
-      issue_qk(1, 1);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        issue_qk(0, b);
+        issue_qk(1, b);
+      }
       umma_commit(&k_empty[0]);
-      for (int t = 0; t < 2 * nk; ++t) {
-        const int j = t >> 1, h = t & 1;
+      for (int t = 0; t < NB * nk; ++t) {
+        const int j = t / NB, h = t % NB;
         const bool more = (j + 1 < nk);
         if (h == 0) {
           mbar_wait(&v_full[j % STAGES], (j / STAGES) & 1);
@@ -324,10 +353,10 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int x = 0; x < 2; ++x) {
           if (t < nst[x]) {
             issue_pv(x, t);
-            if (t + 2 < nst[x]) issue_qk(x, t + 2);               // behind P V in the in-order pipe: P_x(t) is consumed first
+            if (t + NB < nst[x]) issue_qk(x, t + NB);             // behind P V in the in-order pipe: P_x(t) is consumed first
           }
         }
-        if (h == 1) {
+        if (h == NB - 1) {
           umma_commit(&v_empty[j % STAGES]);
           if (more) umma_commit(&k_empty[(j + 1) % STAGES]);
         }
@@ -336,7 +365,7 @@ bf16_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tbase);
+  if (warp == 17) tmem_dealloc<512>(tbase);
   if (tid == 0) QA_TLF(12);
 }
 
@@ -373,11 +402,11 @@ int launch_bf16_fwd2(const void* q, const void* k, const void* v, float* O, floa
 #else
   p.dbg = nullptr;
 #endif
-  auto kern = bf16_fwd2_kernel<D, STAGES>;
+  auto kern = bf16_fwd2_kernel<D, STAGES, 128>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid((Sq / 256) * BH);                         // order: qa_group_order
-  kern<<<grid, 320, L::total, st>>>(tq, tk, tv, to, p);
+  kern<<<grid, 576, L::total, st>>>(tq, tk, tv, to, p);
   return qa_check_launch("qa_bf16_fwd(2 query tiles)");
 }
 

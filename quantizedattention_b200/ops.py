@@ -238,10 +238,11 @@ def int8_bwd_sage(q_i8, k_i8, v_fp16, do_i8, dO_fp16, sq, sk, s_do, lse32, delta
 
 
 def bf16_fwd_key_step(Sq: int, nsplit: int = 0) -> int:
-    """Keys per online-softmax step of the kernel qa_bf16_fwd dispatches to: the running maximum (and its bias
+    """Keys per online-softmax step of the kernels qa_bf16_fwd dispatches to (128 for both since the two-tile kernel moved
+    from 64-key to 128-key steps: a tcgen05.mma with N = 64 costs as much as one with N = 128, profiles/r02_mma_rate.txt): the running maximum (and its bias
     correction) advances once per step, so an oracle comparison at rounding level must use the same `tile_k`.
     The reference's own default is 32 (attention_bf16.py:139); the choice is mathematically neutral."""
-    return 64 if (nsplit in (0, 3) and Sq % 256 == 0) else 128
+    return 128
 
 
 def _pad_seq(t, Sp: int, value: float = 0.0):
