@@ -91,6 +91,22 @@ int qa_int8_fwd_ragged(const void* q_i8, const void* k_i8, const void* v_i8, con
 int qa_fp8_fwd(const void* q_e4m3, const void* k_e4m3, const void* v_e4m3, const void* sq_fp16, const void* sk_fp16,
                const void* sv_fp16, void* O_fp16, void* lse_fp16, void* lse_fp32, int BH, int Sq, int Sk, int D, void* stream);
 
+/* ---- NVFP4 (microscaling) forward, SURVEY.md 8f.4 (README.md:48-54 of the reference names FP4 microscaling as the
+ * SageAttention3 feature; it ships no code for it): tcgen05 kind::mxf4nvf4.block_scale.block16 for both contractions.
+ * Two-level scales: sg = amax_head / 2688 (fp32 [BH]), sf = e4m3(amax_blk16 / 6 / sg), code = e2m1_rn(x / (sf * sg));
+ * D = 128, S % 128 == 0.  Q, K: blocks of 16 along D, codes [BH*S, D/2] bytes (element 2i in the low nibble); V: blocks of
+ * 16 KEYS, codes transposed [BH, D, S/2].  Scale factors in the tcgen05.cp atom layout: per 128-row tile and 64-element
+ * K step 512 bytes, byte 16*(r%32) + 4*(r/32) + s = row r, block s.  amax_ws: [BH] fp32 scratch.  mean_fp16 (or NULL):
+ * per-head K token mean subtracted first (one fp16 rounding), as in the int8 path. */
+int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH, int S,
+                      int D, void* stream);
+int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, void* sg_f32, int BH, int S, int D, void* stream);
+/* O fp16 [BH*Sq, D], lse fp32 [BH*Sq] (log2 domain); P is microscaled per row and 16 keys inside the kernel
+ * (sfp = e4m3(amax * 448), code = e2m1_rn(P * 2688 / sfp)); the fp32 accumulator spans all k-tiles. */
+int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq_f32, const void* k4, const void* sfk, const void* sgk_f32,
+               const void* vt4, const void* sfv, const void* sgv_f32, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk, int D,
+               void* stream);
+
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;
  * 1: fp32 dO/O and, if dO_bf16 != NULL, a bf16 copy of dO in the same pass. */

@@ -13,6 +13,13 @@ extern "C" {
 int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, void* d_out, int a_lbo, int a_sbo,
                  int a_layout, int a_kstep_bytes, int b_lbo, int b_sbo, int b_layout, int b_kstep_bytes, unsigned idesc,
                  int kind, int n_mma, int n_cols, int a_in_tmem, int a_tmem_cols, int a_tmem_kstep_cols, void* stream);
+/* block-scaled (microscaling) variant: packed e2m1 operands, scale factors staged shared memory -> TMEM by tcgen05.cp.
+ * kind: 0 = mxf4nvf4.block16 (ue4m3), 1 = mxf4.block32 (ue8m0), 2 = mxf8f6f4.block32 */
+int qa_probe_mma_bs(const void* a_img, int a_bytes, const void* b_img, int b_bytes, const void* sfa_img, int sfa_bytes,
+                    const void* sfb_img, int sfb_bytes, void* d_out, int a_lbo, int a_sbo, int a_layout, int a_kstep_bytes,
+                    int b_lbo, int b_sbo, int b_layout, int b_kstep_bytes, unsigned idesc, int kind, int n_mma, int n_cols,
+                    int sfa_cols_per_mma, int sfb_cols_per_mma, int a_in_tmem, int a_tmem_cols, int a_tmem_kstep_cols,
+                    void* stream);
 /* Development aid: per-k-tile SM-clock stamps of CTA (0,0) of the next qa_int8_fwd launches ([64][16] int64); NULL = off */
 int qa_debug_set_int8_fwd_timeline(void* buf);
 int qa_debug_set_int8_bwd_timeline(void* buf_i64_64x2x16);   /* same for qa_int8_bwd: leader warp and warp 5, per q-tile */

@@ -1,0 +1,102 @@
+"""NVFP4 (microscaling) SageAttention3-style forward - the feature the reference's README names as the
+SageAttention3 headline but does not implement (README.md:48-54):
+
+  sage_attention_3_fp4(q, k, v) -> O fp16 [B,H,S,D]                    forward only (inference)
+  quantise_fp4(q, k, v)         -> Fp4Operands (codes, scale-factor atoms, per-head scales, k_mean)
+  fp4_fwd_prequant(ops)         -> (O fp16 [B,H,S,D], lse fp32 [B*H, S], log2 domain)
+
+Q, K (mean-smoothed) and V are quantised to e2m1 with one e4m3 scale per 16 elements along the contraction axis (D for
+Q / K, keys for V, which is stored transposed) and one fp32 scale per head; P is microscaled per row and 16 keys inside
+the kernel.  Both contractions run on tcgen05 `kind::mxf4nvf4.block_scale` with fp32 accumulation in TMEM.
+D = 128, S a multiple of 128.  Contract and tolerances: oracle/fp4_ref.py, tests/test_fp4_fwd_gpu.py.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, ops
+
+
+@dataclass
+class Fp4Operands:
+    q4: torch.Tensor      # uint8 [B*H*Sq, D/2]
+    sfq: torch.Tensor     # uint8 [B*H*Sq/128, D/64, 512]
+    sgq: torch.Tensor     # fp32 [B*H]
+    k4: torch.Tensor
+    sfk: torch.Tensor
+    sgk: torch.Tensor
+    vt4: torch.Tensor     # uint8 [B*H, D, Sk/2]
+    sfv: torch.Tensor     # uint8 [B*H*Sk/128, 2, 512]
+    sgv: torch.Tensor
+    k_mean: torch.Tensor | None
+    shape: tuple          # (B, H, Sq, Sk, D)
+
+
+def _check(q, k, v):
+    for t in (q, k, v):
+        if t.dtype != torch.float16:
+            raise TypeError("fp4 attention takes fp16 q, k, v")
+        if not t.is_cuda:
+            raise RuntimeError("fp4 attention needs CUDA tensors (there is no CPU fallback)")
+    B, H, Sq, D = q.shape
+    Sk = k.shape[2]
+    if D != 128:
+        raise ValueError("fp4 attention is built for head dimension 128")
+    if Sq % 128 or Sk % 128:
+        raise ValueError("fp4 attention needs sequence lengths that are multiples of 128")
+    assert k.shape == v.shape and k.shape[:2] == q.shape[:2] and k.shape[3] == D
+    return B, H, Sq, Sk, D
+
+
+def _quant_rows(x, mean, BH, S, D):
+    dev = x.device
+    codes = torch.empty((BH * S, D // 2), dtype=torch.uint8, device=dev)
+    sf = torch.empty((BH * S // 128, D // 64, 512), dtype=torch.uint8, device=dev)
+    sg = torch.empty((BH,), dtype=torch.float32, device=dev)
+    ws = torch.empty((BH,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev), ops._timed("fp4_quant_rows"):
+        _lib.check(L.qa_fp4_quant_rows(_lib.ptr(x), _lib.ptr(mean) if mean is not None else None, _lib.ptr(ws), _lib.ptr(codes),
+                                       _lib.ptr(sf), _lib.ptr(sg), BH, S, D, _lib.cur_stream()), "qa_fp4_quant_rows")
+    return codes, sf, sg
+
+
+def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
+    B, H, Sq, Sk, D = _check(q_fp16, k_fp16, v_fp16)
+    BH = B * H
+    q, k, v = q_fp16.contiguous(), k_fp16.contiguous(), v_fp16.contiguous()
+    k_mean = ops.k_mean(k) if smooth_k else None                      # fp16 [B,H,1,D]
+    q4, sfq, sgq = _quant_rows(q, None, BH, Sq, D)
+    k4, sfk, sgk = _quant_rows(k, k_mean, BH, Sk, D)
+    dev = q.device
+    vt4 = torch.empty((BH, D, Sk // 2), dtype=torch.uint8, device=dev)
+    sfv = torch.empty((BH * Sk // 128, 2, 512), dtype=torch.uint8, device=dev)
+    sgv = torch.empty((BH,), dtype=torch.float32, device=dev)
+    ws = torch.empty((BH,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev), ops._timed("fp4_quant_vt"):
+        _lib.check(L.qa_fp4_quant_vt(_lib.ptr(v), _lib.ptr(ws), _lib.ptr(vt4), _lib.ptr(sfv), _lib.ptr(sgv), BH, Sk, D,
+                                     _lib.cur_stream()), "qa_fp4_quant_vt")
+    return Fp4Operands(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, k_mean, (B, H, Sq, Sk, D))
+
+
+def fp4_fwd_prequant(o: Fp4Operands):
+    B, H, Sq, Sk, D = o.shape
+    dev = o.q4.device
+    O = torch.empty((B * H * Sq, D), dtype=torch.float16, device=dev)
+    lse = torch.empty((B * H * Sq,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev), ops._timed("fp4_fwd"):
+        _lib.check(L.qa_fp4_fwd(_lib.ptr(o.q4), _lib.ptr(o.sfq), _lib.ptr(o.sgq), _lib.ptr(o.k4), _lib.ptr(o.sfk), _lib.ptr(o.sgk),
+                                _lib.ptr(o.vt4), _lib.ptr(o.sfv), _lib.ptr(o.sgv), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
+                                _lib.cur_stream()), "qa_fp4_fwd")
+    return O.view(B, H, Sq, D), lse.view(B * H, Sq)
+
+
+def sage_attention_3_fp4(q_fp16, k_fp16, v_fp16):
+    """O = softmax(q k^T / sqrt(d)) v through the NVFP4 pipeline, K smoothed with its per-head token mean.  Forward only:
+    the result does not require grad."""
+    with torch.no_grad():
+        return fp4_fwd_prequant(quantise_fp4(q_fp16, k_fp16, v_fp16))[0]

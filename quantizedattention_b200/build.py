@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libqattn.so")
 LIB_DEV = os.path.join(HERE, "libqattn_dev.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["host.cu", "quant.cu", "attn_int8_fwd.cu", "attn_bf16_fwd.cu", "attn_bf16_fwd2.cu", "attn_jvp.cu", "attn_int8_bwd.cu",
-           "attn_bf16_bwd.cu", "attn_bf16_bwd2.cu", "prepass.cu"]
+           "attn_bf16_bwd.cu", "attn_bf16_bwd2.cu", "prepass.cu", "quant_fp4.cu", "attn_fp4_fwd.cu"]
 DEV_SOURCES = ["probe.cu"]
 
 

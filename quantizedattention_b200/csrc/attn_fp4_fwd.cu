@@ -1,0 +1,284 @@
+// NVFP4 (microscaling) attention forward for sm_100a (the SageAttention3 headline feature the reference
+// names but does not ship, /root/reference/README.md:48-54).  Contract: oracle/fp4_ref.py.
+//
+// Both contractions run on tcgen05.mma kind::mxf4nvf4.block_scale.block16 (e2m1 operands, one ue4m3 scale per 16 elements
+// along the contraction axis, fp32 accumulation in TMEM); the operand, scale-factor and instruction-descriptor conventions
+// were pinned on the hardware by qa_probe_mma_bs (tests/test_probe_gpu.py, profiles/r02_fp4_probe.txt).
+//   S = Q4 K4^T      A = Q tile, B = K tile: rows of D/2 = 64 bytes, 64-byte swizzle, two K = 64 steps; scale factors of Q / K
+//                    arrive as 512-byte atoms by TMA and are copied shared memory -> TMEM by tcgen05.cp.32x128b.warpx4
+//   O += P4 V4       A = P from TMEM (TS mode: 8 e2m1 per 32-bit column, written by the softmax warps over the S columns),
+//                    B = V^T tile [D rows, 128 keys] (V is stored transposed: 4-bit operands are K-major only);
+//                    P's scale factors go through a shared-memory atom and tcgen05.cp (they must be replicated over
+//                    the four TMEM lane quadrants, which a thread cannot write)
+// Because the microscales travel with the operands, the fp32 accumulator spans k-tiles (unlike the int8 / fp8 path, whose
+// per-tile P and V scales force a drain every k-tile): O stays resident in TMEM and is rescaled only when a row maximum moves.
+// One CTA = one 128-row query tile of one head.  Warps 0-3: softmax (thread = row), 4: TMA producer, 5: MMA issuer.
+// TMEM (512 columns): S[2] at 0 / 128, O at 256, scale factors from 384: Q 8, K 2 x 8, V 2 x 8, P 2 x 8 columns.
+#include "qa_ptx.cuh"
+#include "qa_host.h"
+#include <cuda_fp4.h>
+#include <cuda_fp8.h>
+
+namespace qa {
+
+constexpr int kFp4D = 128;
+
+template <int STAGES>
+struct Fp4FwdSmem {
+  static constexpr int kTile = 128 * 64;                       // 128 rows x 128 e2m1 = 8 KB
+  static constexpr int kSf = 1024;                             // two 512-byte scale-factor atoms (K steps of 64)
+  static constexpr int off_q = 0;
+  static constexpr int off_k = off_q + kTile;
+  static constexpr int off_v = off_k + STAGES * kTile;
+  static constexpr int off_sfq = off_v + STAGES * kTile;
+  static constexpr int off_sfk = off_sfq + kSf;
+  static constexpr int off_sfv = off_sfk + STAGES * kSf;
+  static constexpr int off_sfp = off_sfv + STAGES * kSf;       // [2] written by the softmax warps
+  static constexpr int total = off_sfp + 2 * kSf + 1024;       // + alignment slack
+};
+
+struct Fp4FwdParams {
+  const float *sgq, *sgk, *sgv;      // [BH] second-level scales
+  __half* O;                         // [BH*Sq, 128] fp16
+  float* lse;                        // [BH*Sq] log2 domain
+  int Sq, Sk;
+  float qk_scale;                    // sm_scale * log2(e)
+};
+
+__device__ __forceinline__ void tmem_cp_sf(uint32_t taddr, uint32_t saddr) {   // one 512-byte atom -> 4 TMEM columns, all lane quadrants
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(umma_smem_desc(saddr, 0, 128, kSwzNone)) : "memory");
+}
+__device__ __forceinline__ float fp4_e4m3_to_float(uint32_t c) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)c, __NV_E4M3);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+__device__ __forceinline__ uint32_t fp4_pack8(const float* y, float s) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w |= (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(y[2 * i] * s, y[2 * i + 1] * s), __NV_E2M1, cudaRoundNearest) << (8 * i);
+  return w;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+               const __grid_constant__ CUtensorMap tm_vt, const __grid_constant__ CUtensorMap tm_sfq,
+               const __grid_constant__ CUtensorMap tm_sfk, const __grid_constant__ CUtensorMap tm_sfv, Fp4FwdParams p) {
+  using L = Fp4FwdSmem<STAGES>;
+  constexpr int D = kFp4D;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full[2], p_full[2], o_full[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, q0 = blockIdx.x * 128;
+  const int nk = p.Sk / 128;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  constexpr uint32_t kSfQ = 384, kSfK = 392, kSfV = 408, kSfP = 424;     // TMEM columns of the scale factors
+
+  if (warp < 4) {
+    // =========================== softmax warps: thread = query row ===========================
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;           // accumulator -> log2-domain logit
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nk; ++j) {
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
+      float u[128];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t r[64];
+        tmem_ld64(lane_addr + sb * 128 + ch * 64, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { u[ch * 64 + i] = __uint_as_float(r[i]) * c; mx = fmaxf(mx, u[ch * 64 + i]); }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float resc = ex2_approx(m - m_new);                     // 0 on the first tile (m = -inf)
+      m = m_new;
+      if (j > 0 && __any_sync(0xffffffffu, resc != 1.0f)) {        // O *= 2^(m - m'): only when a row maximum of this warp moved
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);       // P V of tile j-1 has landed in TMEM
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + 256 + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
+          tmem_st32(lane_addr + 256 + ch * 32, r);
+        }
+      }
+      // ---- P = exp2(u - m'), microscaled per 16 keys: sfp = e4m3(amax * 448), P4 = e2m1(P * 2688 / sfp)
+      float lsum = 0.f;
+      uint32_t pw[16], sfw[2] = {0u, 0u};
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        float pe[16];
+        float am = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { pe[e] = ex2_approx(u[b * 16 + e] - m_new); am = fmaxf(am, pe[e]); lsum += pe[e]; }
+        const uint32_t sc = (uint32_t)__nv_cvt_float_to_fp8(am * 448.0f, __NV_SATFINITE, __NV_E4M3);
+        const float sf = fp4_e4m3_to_float(sc);
+        const float inv = sf > 0.f ? __fdividef(2688.0f, sf) : 0.f;
+        pw[2 * b] = fp4_pack8(pe, inv);
+        pw[2 * b + 1] = fp4_pack8(pe + 8, inv);
+        sfw[b >> 2] |= sc << (8 * (b & 3));
+      }
+      l = l * resc + lsum;
+      tmem_st16(lane_addr + sb * 128, pw);                         // P over the first 16 S columns (8 keys per column)
+      // scale factors of P: one 32-bit word (4 blocks) per K step into the atom layout; tcgen05.cp replicates it over the lanes
+      uint8_t* sfp = smem + L::off_sfp + sb * L::kSf;
+      *reinterpret_cast<uint32_t*>(sfp + 16 * lane + 4 * warp) = sfw[0];
+      *reinterpret_cast<uint32_t*>(sfp + 512 + 16 * lane + 4 * warp) = sfw[1];
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+    }
+    // ---- epilogue: O * sgv / (2688 * l), log2-LSE
+    mbar_wait(&o_full[(nk - 1) & 1], ((nk - 1) >> 1) & 1);
+    tc_fence_after();
+    const size_t gr = (size_t)bh * p.Sq + q0 + row;
+    const float sc_o = __fdividef(p.sgv[bh], 2688.0f * l);
+    __half* dst = p.O + gr * D;
+#pragma unroll
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(lane_addr + 256 + ch * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 o;
+        __half2 t;
+        t = __floats2half2_rn(__uint_as_float(r[i]) * sc_o, __uint_as_float(r[i + 1]) * sc_o); o.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(__uint_as_float(r[i + 2]) * sc_o, __uint_as_float(r[i + 3]) * sc_o); o.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(__uint_as_float(r[i + 4]) * sc_o, __uint_as_float(r[i + 5]) * sc_o); o.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(__uint_as_float(r[i + 6]) * sc_o, __uint_as_float(r[i + 7]) * sc_o); o.w = *reinterpret_cast<uint32_t*>(&t);
+        *reinterpret_cast<uint4*>(dst + ch * 32 + i) = o;
+      }
+    }
+    p.lse[gr] = m + log2f(l);
+  } else if (warp == 4) {
+    // =========================== TMA producer ===========================
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt);
+      mbar_expect_tx(&q_full, L::kTile + L::kSf);
+      tma_load_2d(smem + L::off_q, &tm_q, &q_full, 0, bh * p.Sq + q0);
+      tma_load_2d(smem + L::off_sfq, &tm_sfq, &q_full, 0, (bh * p.Sq + q0) / 128);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j % STAGES;
+        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * L::kTile + 2 * L::kSf);
+        tma_load_2d(smem + L::off_k + s * L::kTile, &tm_k, &kv_full[s], 0, bh * p.Sk + j * 128);
+        tma_load_2d(smem + L::off_sfk + s * L::kSf, &tm_sfk, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+        tma_load_2d(smem + L::off_v + s * L::kTile, &tm_vt, &kv_full[s], j * 64, bh * D);
+        tma_load_2d(smem + L::off_sfv + s * L::kSf, &tm_sfv, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // e2m1 x e2m1, K-major, ue4m3 scales, N = 128 (keys / D)
+      const uint32_t q_addr = smem_u32(smem + L::off_q);
+      auto issue_s = [&](int j) {                                                  // S[j & 1] = Q K_j^T
+        const int s = j % STAGES, sb = j & 1;
+        mbar_wait(&kv_full[s], (j / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile), sfk = smem_u32(smem + L::off_sfk + s * L::kSf);
+        tmem_cp_sf(tbase + kSfK + sb * 8, sfk);
+        tmem_cp_sf(tbase + kSfK + sb * 8 + 4, sfk + 512);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_nvf4_ss(tbase + sb * 128, umma_smem_desc(q_addr + k * 32, 16, 512, kSwz64), umma_smem_desc(k_addr + k * 32, 16, 512, kSwz64),
+                       idesc, tbase + kSfQ + k * 4, tbase + kSfK + sb * 8 + k * 4, k > 0);
+        umma_commit(&s_full[sb]);
+      };
+      mbar_wait(&q_full, 0);
+      tc_fence_after();
+      tmem_cp_sf(tbase + kSfQ, smem_u32(smem + L::off_sfq));
+      tmem_cp_sf(tbase + kSfQ + 4, smem_u32(smem + L::off_sfq) + 512);
+      issue_s(0);
+      for (int j = 0; j < nk; ++j) {
+        const int s = j % STAGES, sb = j & 1;
+        if (j + 1 < nk) issue_s(j + 1);           // overwrites the buffer that held P(j-1): P V(j-1) is ahead of it in the in-order pipe
+        mbar_wait(&p_full[sb], (j >> 1) & 1);     // P, its scale factors and any rescale of O are in place
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile), sfv = smem_u32(smem + L::off_sfv + s * L::kSf);
+        const uint32_t sfp = smem_u32(smem + L::off_sfp + sb * L::kSf);
+        tmem_cp_sf(tbase + kSfP + sb * 8, sfp);
+        tmem_cp_sf(tbase + kSfP + sb * 8 + 4, sfp + 512);
+        tmem_cp_sf(tbase + kSfV + sb * 8, sfv);
+        tmem_cp_sf(tbase + kSfV + sb * 8 + 4, sfv + 512);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)                                               // O += P_j V_j, keys 64k .. 64k + 63
+          umma_nvf4_ts(tbase + 256, tbase + sb * 128 + k * 8, umma_smem_desc(v_addr + k * 32, 16, 512, kSwz64), idesc,
+                       tbase + kSfP + sb * 8 + k * 4, tbase + kSfV + sb * 8 + k * 4, (j > 0) || (k > 0));
+        umma_commit(&o_full[sb]);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tbase);
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+// q4, k4: [BH*S, 64] bytes (e2m1 pairs); vt4: [BH, 128, Sk/2] bytes; sf*: 512-byte atoms, 2 per 128-row tile; sg*: [BH] fp32
+// (all produced by qa_fp4_quant_rows / qa_fp4_quant_vt).  O: fp16 [BH*Sq, 128]; lse: fp32 [BH*Sq] (log2 domain).
+extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
+                          const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
+                          int D, void* stream) {
+  if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: D must be 128");
+  if (BH <= 0 || Sq <= 0 || Sk <= 0 || Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: Sq, Sk must be positive multiples of 128");
+  if ((long long)BH * Sq >= (1ll << 31) || (long long)BH * Sk >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: BH * S must stay below 2^31");
+  const void* ptrs[11] = {q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, O_fp16, lse_f32};
+  for (int i = 0; i < 11; ++i) {
+    if (!ptrs[i]) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: null pointer");
+    if (i != 2 && i != 5 && i != 8 && i != 10 && ((uintptr_t)ptrs[i] & 15)) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: 16-byte alignment required");
+  }
+  constexpr int STAGES = 4;
+  using L = Fp4FwdSmem<STAGES>;
+  CUtensorMap tq, tk, tv, tsq, tsk, tsv;
+  int rc;
+  uint64_t dq[2] = {64, (uint64_t)BH * Sq}, dk[2] = {64, (uint64_t)BH * Sk}, dv[2] = {(uint64_t)Sk / 2, (uint64_t)BH * 128};
+  uint64_t s64[1] = {64}, sv[1] = {(uint64_t)Sk / 2}, ssf[1] = {1024};
+  uint32_t box[2] = {64, 128}, boxsf[2] = {256, 1};
+  uint64_t dsq[2] = {256, (uint64_t)BH * Sq / 128}, dsk[2] = {256, (uint64_t)BH * Sk / 128};
+  if ((rc = qa_make_tmap(&tq, q4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dq, s64, box, 2))) return rc;
+  if ((rc = qa_make_tmap(&tk, k4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dk, s64, box, 2))) return rc;
+  if ((rc = qa_make_tmap(&tv, vt4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dv, sv, box, 2))) return rc;
+  if ((rc = qa_make_tmap(&tsq, sfq, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dsq, ssf, boxsf, 0))) return rc;
+  if ((rc = qa_make_tmap(&tsk, sfk, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dsk, ssf, boxsf, 0))) return rc;
+  if ((rc = qa_make_tmap(&tsv, sfv, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dsk, ssf, boxsf, 0))) return rc;
+  Fp4FwdParams p;
+  p.sgq = (const float*)sgq; p.sgk = (const float*)sgk; p.sgv = (const float*)sgv;
+  p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk;
+  p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  auto kern = fp4_fwd_kernel<STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  kern<<<dim3(Sq / 128, BH), 192, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+  return qa_check_launch("qa_fp4_fwd");
+}

@@ -11,6 +11,7 @@
 // tile in registers between the max pass and the exp pass, so steady-state TMEM->register traffic is S + tS only.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
+#include <type_traits>
 
 namespace qa {
 
@@ -99,19 +100,22 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       tc_fence_after();
       float mx = -INFINITY;
       uint32_t sreg[NC];                                          // S row segment stays in registers between the passes
+      auto load_s = [&](auto tail) {                               // two instantiations: the key mask costs nothing on full tiles
 #pragma unroll
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + c0 + ch * 32, r);
-        tmem_ld_wait();
-        if ((j + 1) * BN > p.Sk_valid) {                          // ragged last k-tile: padded keys get logit -inf, weight 0
+        for (int ch = 0; ch < NC / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + c0 + ch * 32, r);
+          tmem_ld_wait();
+          if (decltype(tail)::value) {                            // ragged last k-tile: padded keys get logit -inf, weight 0
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (j * BN + c0 + ch * 32 + i >= p.Sk_valid) r[i] = 0xff800000u;
+            for (int i = 0; i < 32; ++i)
+              if (j * BN + c0 + ch * 32 + i >= p.Sk_valid) r[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { sreg[ch * 32 + i] = r[i]; mx = fmaxf(mx, __uint_as_float(r[i])); }
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { sreg[ch * 32 + i] = r[i]; mx = fmaxf(mx, __uint_as_float(r[i])); }
-      }
+      };
+      if ((j + 1) * BN > p.Sk_valid) load_s(std::true_type{}); else load_s(std::false_type{});
       if (NSPLIT == 2) {
         xmax[ph][split][row] = mx;
         named_bar_sync(1 + (warp & 3), 32 * NSPLIT);   // only the warps that share these 32 rows meet

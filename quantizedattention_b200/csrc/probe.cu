@@ -109,6 +109,108 @@ __global__ void __launch_bounds__(128) probe_tma_kernel(const __grid_constant__ 
   for (int i = tid; i < bytes; i += 128) out[i] = smem[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Block-scaled MMA probe (NVFP4 / MXFP4 microscaling): stages host-built images of A, B (packed e2m1,
+// two per byte) and of the scale factors, copies the scale factors shared memory -> TMEM with tcgen05.cp.32x128b.warpx4
+// (one 512-byte atom = 32 rows x 16 bytes -> 4 TMEM columns, replicated over the four lane quadrants), issues
+// tcgen05.mma.kind::mxf4nvf4.block_scale and dumps the fp32 accumulator.
+//   sf atom (512 B):  byte 16 * (r % 32) + 4 * (r / 32) + s  =  scale of row r, K block s of this MMA (K = 64: s < 4)
+// ---------------------------------------------------------------------------------------------------------
+struct ProbeMmaBsParams {
+  const uint8_t *a_img, *b_img, *sfa_img, *sfb_img;
+  uint32_t* d_out;
+  int a_bytes, b_bytes, sfa_bytes, sfb_bytes;
+  int a_lbo, a_sbo, a_layout, a_kstep_bytes;
+  int b_lbo, b_sbo, b_layout, b_kstep_bytes;
+  uint32_t idesc;
+  int kind;               // 0 = mxf4nvf4 block16 (ue4m3 scales, K = 64), 1 = mxf4 block32 (ue8m0, K = 64), 2 = mxf8f6f4 block32 (K = 32)
+  int n_mma, n_cols;
+  int sfa_cols_per_mma, sfb_cols_per_mma;   // TMEM columns (and 128-byte quarter atoms) the scale factors advance per MMA
+  int a_in_tmem, a_tmem_cols, a_tmem_kstep_cols;
+};
+
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
+__global__ void __launch_bounds__(128) probe_mma_bs_kernel(ProbeMmaBsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  auto up = [](int v) { return (v + 1023) / 1024 * 1024; };
+  uint8_t* sa = smem;
+  uint8_t* sb = sa + up(p.a_in_tmem ? 0 : p.a_bytes);
+  uint8_t* sfa = sb + up(p.b_bytes);
+  uint8_t* sfb = sfa + up(p.sfa_bytes);
+  auto stage = [&](uint8_t* dst, const uint8_t* src, int bytes) {
+    for (int i = tid * 16; i < bytes; i += 128 * 16) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+  };
+  if (!p.a_in_tmem) stage(sa, p.a_img, p.a_bytes);
+  stage(sb, p.b_img, p.b_bytes);
+  stage(sfa, p.sfa_img, p.sfa_bytes);
+  stage(sfb, p.sfb_img, p.sfb_bytes);
+  fence_proxy_async_smem();
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+  const uint32_t a_col0 = 256, sfa_col0 = 384, sfb_col0 = 448;
+
+  if (p.a_in_tmem) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(p.a_img) + (size_t)tid * p.a_tmem_cols;
+    for (int c = 0; c < p.a_tmem_cols; c += 8) {
+      uint32_t r[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = row[c + i];
+      tmem_st8(lane_addr + a_col0 + c, r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  if (tid == 0) {
+    // scale factors: 512-byte atoms (32 rows x 16 B, 8-row core matrices 128 B apart), one tcgen05.cp per atom -> 4 columns
+    for (int i = 0; i < p.sfa_bytes / 512; ++i)
+      tmem_cp_32x128b_warpx4(tbase + sfa_col0 + 4 * i, umma_smem_desc(smem_u32(sfa) + 512 * i, 0, 128, kSwzNone));
+    for (int i = 0; i < p.sfb_bytes / 512; ++i)
+      tmem_cp_32x128b_warpx4(tbase + sfb_col0 + 4 * i, umma_smem_desc(smem_u32(sfb) + 512 * i, 0, 128, kSwzNone));
+    for (int k = 0; k < p.n_mma; ++k) {                       // tcgen05.cp and tcgen05.mma execute in issue order
+      const uint64_t bd = umma_smem_desc(smem_u32(sb) + k * p.b_kstep_bytes, p.b_lbo, p.b_sbo, p.b_layout);
+      const uint32_t acc = k > 0, tsfa = tbase + sfa_col0 + k * p.sfa_cols_per_mma, tsfb = tbase + sfb_col0 + k * p.sfb_cols_per_mma;
+      if (p.a_in_tmem) {
+        const uint32_t at = tbase + a_col0 + k * p.a_tmem_kstep_cols;
+        umma_nvf4_ts(tbase, at, bd, p.idesc, tsfa, tsfb, acc);
+      } else {
+        const uint64_t ad = umma_smem_desc(smem_u32(sa) + k * p.a_kstep_bytes, p.a_lbo, p.a_sbo, p.a_layout);
+        if (p.kind == 0) umma_nvf4_ss(tbase, ad, bd, p.idesc, tsfa, tsfb, acc);
+        else if (p.kind == 1) umma_mxf4_ss(tbase, ad, bd, p.idesc, tsfa, tsfb, acc);
+        else umma_mxf8_ss(tbase, ad, bd, p.idesc, tsfa, tsfb, acc);
+      }
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < p.n_cols; c += 8) {
+    uint32_t r[8];
+    tmem_ld8(lane_addr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p.d_out[(size_t)tid * p.n_cols + c + i] = r[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
 }  // namespace qa
 
 using namespace qa;
@@ -130,6 +232,31 @@ extern "C" int qa_probe_mma(const void* a_img, int a_bytes, const void* b_img, i
   cudaFuncSetAttribute(probe_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   probe_mma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
   return qa_check_launch("qa_probe_mma");
+}
+
+extern "C" int qa_probe_mma_bs(const void* a_img, int a_bytes, const void* b_img, int b_bytes, const void* sfa_img, int sfa_bytes,
+                               const void* sfb_img, int sfb_bytes, void* d_out, int a_lbo, int a_sbo, int a_layout,
+                               int a_kstep_bytes, int b_lbo, int b_sbo, int b_layout, int b_kstep_bytes, unsigned idesc, int kind,
+                               int n_mma, int n_cols, int sfa_cols_per_mma, int sfb_cols_per_mma, int a_in_tmem, int a_tmem_cols,
+                               int a_tmem_kstep_cols, void* stream) {
+  ProbeMmaBsParams p;
+  p.a_img = (const uint8_t*)a_img; p.b_img = (const uint8_t*)b_img; p.sfa_img = (const uint8_t*)sfa_img; p.sfb_img = (const uint8_t*)sfb_img;
+  p.d_out = (uint32_t*)d_out;
+  p.a_bytes = a_bytes; p.b_bytes = b_bytes; p.sfa_bytes = sfa_bytes; p.sfb_bytes = sfb_bytes;
+  p.a_lbo = a_lbo; p.a_sbo = a_sbo; p.a_layout = a_layout; p.a_kstep_bytes = a_kstep_bytes;
+  p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.b_layout = b_layout; p.b_kstep_bytes = b_kstep_bytes;
+  p.idesc = idesc; p.kind = kind; p.n_mma = n_mma; p.n_cols = n_cols;
+  p.sfa_cols_per_mma = sfa_cols_per_mma; p.sfb_cols_per_mma = sfb_cols_per_mma;
+  p.a_in_tmem = a_in_tmem; p.a_tmem_cols = a_tmem_cols; p.a_tmem_kstep_cols = a_tmem_kstep_cols;
+  if (n_cols % 8 || n_cols > 256 || (a_bytes & 15) || (b_bytes & 15) || (sfa_bytes % 512) || (sfb_bytes % 512) || sfa_bytes > 8192 ||
+      sfb_bytes > 8192)
+    return qa_fail(QA_ERR_SHAPE, "qa_probe_mma_bs: bad sizes");
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  size_t smem = 1024 + up(a_in_tmem ? 0 : a_bytes) + up(b_bytes) + up(sfa_bytes) + up(sfb_bytes);
+  if (smem > 200 * 1024) return qa_fail(QA_ERR_SHAPE, "qa_probe_mma_bs: images too large");
+  cudaFuncSetAttribute(probe_mma_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_mma_bs_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  return qa_check_launch("qa_probe_mma_bs");
 }
 
 // elem_bytes in {1,2,4}; dims/box innermost-first; strides in bytes for dims >= 1.

@@ -197,6 +197,29 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Block-scaled kinds (microscaling): the scale factors of A and B live in TMEM (copied there with tcgen05.cp); idesc is
+// the block-scaled instruction descriptor (umma_idesc_bs).  mxf4nvf4.block16: e2m1 x e2m1, ue4m3 scale per 16 elements,
+// K = 64; mxf4.block32: ue8m0 scale per 32 elements, K = 64; mxf8f6f4.block32: K = 32.
+#define QA_UMMA_BS(NAME, KIND, AOP, ACON, ATYPE)                                                                                  \
+  __device__ __forceinline__ void NAME(uint32_t d_tmem, ATYPE a, uint64_t b_desc, uint32_t idesc, uint32_t sfa_tmem,             \
+                                       uint32_t sfb_tmem, uint32_t accum) {                                                      \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                               \
+                 "tcgen05.mma.cta_group::1.kind::" KIND " [%0], " AOP ", %2, %3, [%5], [%6], p;\n\t}"                             \
+                 ::"r"(d_tmem), ACON(a), "l"(b_desc), "r"(idesc), "r"(accum), "r"(sfa_tmem), "r"(sfb_tmem)                       \
+                 : "memory");                                                                                                     \
+  }
+QA_UMMA_BS(umma_nvf4_ss, "mxf4nvf4.block_scale.block16", "%1", "l", uint64_t)
+QA_UMMA_BS(umma_nvf4_ts, "mxf4nvf4.block_scale.block16", "[%1]", "r", uint32_t)
+QA_UMMA_BS(umma_mxf4_ss, "mxf4.block_scale.block32", "%1", "l", uint64_t)
+QA_UMMA_BS(umma_mxf8_ss, "mxf8f6f4.block_scale", "%1", "l", uint64_t)
+#undef QA_UMMA_BS
+// Block-scaled instruction descriptor: formats for the mxf4 kinds: e2m1 = 1 (mxf8f6f4: e4m3 0, e5m2 1, e2m1 5);
+// sf_fmt 0 = ue4m3, 1 = ue8m0; a_sf_id / b_sf_id select the byte of the 32-bit scale column (0 when all four are used).
+__host__ __device__ constexpr uint32_t umma_idesc_bs(uint32_t a_fmt, uint32_t b_fmt, uint32_t a_major, uint32_t b_major, uint32_t M,
+                                                     uint32_t N, uint32_t sf_fmt, uint32_t a_sf_id = 0, uint32_t b_sf_id = 0) {
+  return (b_sf_id << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) | (sf_fmt << 23) |
+         ((M >> 4) << 24) | (a_sf_id << 29);
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

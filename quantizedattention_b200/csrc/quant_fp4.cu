@@ -1,0 +1,187 @@
+// NVFP4 (microscaling) quantisation pre-passes of the fp4 forward (the SageAttention3 headline the
+// reference names, /root/reference/README.md:48-54, and does not ship).  HBM-bound: 2 B/elem read, 0.5 B/elem + 1/16 B/elem
+// of scales written (+ 2 B/elem for the per-head amax pass).
+//
+// Two-level scaling (the NVFP4 recipe): per head  sg = amax_head / (6 * 448)  (fp32), per block of 16 elements along the
+// CONTRACTION axis  sf = e4m3_rn(amax_blk / 6 / sg)  in [0, 448],  value = e2m1_rn(x / (sf * sg))  in [-6, 6]; all
+// arithmetic IEEE fp32 (no fast-math), so the codes and scales are bit-exact against oracle/fp4_ref.py.
+//   Q, K : blocks along D (contraction of Q K^T); codes [B*H*S, D/2] bytes, element 2i in the low nibble of byte i.
+//   V    : blocks along the KEY axis (contraction of P V); codes stored transposed [B*H, D, S/2] because tcgen05
+//          kind::mxf4nvf4 takes 4-bit operands K-major only.
+// Scale factors are written in the layout tcgen05.cp.32x128b.warpx4 expects (profiles/r02_fp4_probe.txt): per 128-row
+// tile and per 64-element K step one 512-byte atom, byte 16 * (r % 32) + 4 * (r / 32) + s = scale of row r, block s.
+#include "qa_ptx.cuh"
+#include "qa_host.h"
+#include <cuda_fp4.h>
+#include <cuda_fp8.h>
+
+namespace qa {
+
+__device__ __forceinline__ float e4m3_to_float(uint8_t c) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)c, __NV_E4M3);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+__device__ __forceinline__ uint8_t float_to_e4m3(float x) { return (uint8_t)__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3); }
+__device__ __forceinline__ uint32_t pack_e2m1x8(const float (&y)[8]) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w |= (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(y[2 * i], y[2 * i + 1]), __NV_E2M1, cudaRoundNearest) << (8 * i);
+  return w;
+}
+
+// amax over a head of |x - mean| (fp16 rounding of the difference, as the smoothed K of the int8 path).  grid = (chunks, BH)
+__global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
+                                                            float* __restrict__ amax, int S, int D) {
+  const int bh = blockIdx.y;
+  const size_t n8 = (size_t)S * D / 8;
+  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)bh * S * D);
+  const int dv = D / 8;
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
+    uint4 v = __ldg(base + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    const int d0 = (int)(i % dv) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const __half t = mean ? __hsub(h[e], mean[(size_t)bh * D + d0 + e]) : h[e];
+      m = fmaxf(m, fabsf(__half2float(t)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    atomicMax(reinterpret_cast<int*>(amax + bh), __float_as_int(m));       // non-negative floats order like ints
+  }
+}
+
+// Q / K: one thread per 16-element block along D.  CTA = 128 rows x (D/16) blocks = one scale-factor tile.
+template <int D>
+__global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
+                                                                      const float* __restrict__ amax, uint8_t* __restrict__ codes,
+                                                                      uint8_t* __restrict__ sf, float* __restrict__ sg_out, int S) {
+  constexpr int NB = D / 16;
+  const int tile = blockIdx.x;                                   // 128-row tile over B*H*S
+  const int r = threadIdx.x / NB, b = threadIdx.x % NB;
+  const size_t row = (size_t)tile * 128 + r;
+  const int bh = (int)(row / S);
+  const float sg = __fdiv_rn(amax[bh], 2688.0f);
+  if (sg_out != nullptr && row % S == 0 && b == 0) sg_out[bh] = sg;
+  const uint4* src = reinterpret_cast<const uint4*>(x + row * D + b * 16);
+  float v[16];
+  float am = 0.f;
+#pragma unroll
+  for (int hv = 0; hv < 2; ++hv) {
+    uint4 u = __ldg(src + hv);
+    const __half* h = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const __half t = mean ? __hsub(h[e], mean[(size_t)bh * D + b * 16 + hv * 8 + e]) : h[e];
+      v[hv * 8 + e] = __half2float(t);
+      am = fmaxf(am, fabsf(v[hv * 8 + e]));
+    }
+  }
+  uint8_t sc = 0;
+  float scale = 0.f;
+  if (sg > 0.f) {
+    sc = float_to_e4m3(__fdiv_rn(__fdiv_rn(am, 6.0f), sg));
+    scale = __fmul_rn(e4m3_to_float(sc), sg);
+  }
+  uint32_t w[2];
+#pragma unroll
+  for (int hv = 0; hv < 2; ++hv) {
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = scale > 0.f ? __fdiv_rn(v[hv * 8 + e], scale) : 0.f;
+    w[hv] = pack_e2m1x8(y);
+  }
+  *reinterpret_cast<uint2*>(codes + row * (D / 2) + b * 8) = make_uint2(w[0], w[1]);
+  // scale-factor atoms of this tile: K step = b / 4, block s = b % 4
+  sf[(size_t)tile * (NB / 4) * 512 + (b / 4) * 512 + 16 * (r % 32) + 4 * (r / 32) + (b % 4)] = sc;
+}
+
+// V: CTA = one 128-key tile of one head, transposed through shared memory; thread = (d, block of 16 keys)
+template <int D>
+__global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restrict__ v, const float* __restrict__ amax,
+                                                           uint8_t* __restrict__ codes_t, uint8_t* __restrict__ sf,
+                                                           float* __restrict__ sg_out, int S) {
+  __shared__ __half tile[128][D + 8];                            // +8 halves: 16-byte row skew against bank conflicts
+  const int bh = blockIdx.y, j = blockIdx.x;
+  const float sg = __fdiv_rn(amax[bh], 2688.0f);
+  if (sg_out != nullptr && j == 0 && threadIdx.x == 0) sg_out[bh] = sg;
+  const uint4* src = reinterpret_cast<const uint4*>(v + ((size_t)bh * S + (size_t)j * 128) * D);
+  for (int i = threadIdx.x; i < 128 * D / 8; i += 256) {
+    const int rr = i / (D / 8), c8 = i % (D / 8);
+    *reinterpret_cast<uint4*>(&tile[rr][c8 * 8]) = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < D * 8; it += 256) {
+    const int b = it / D, d = it % D;                             // consecutive threads read consecutive d of one key row: no bank conflicts
+    float x[16];
+    float am = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { x[e] = __half2float(tile[b * 16 + e][d]); am = fmaxf(am, fabsf(x[e])); }
+    uint8_t sc = 0;
+    float scale = 0.f;
+    if (sg > 0.f) {
+      sc = float_to_e4m3(__fdiv_rn(__fdiv_rn(am, 6.0f), sg));
+      scale = __fmul_rn(e4m3_to_float(sc), sg);
+    }
+    uint32_t w[2];
+#pragma unroll
+    for (int hv = 0; hv < 2; ++hv) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = scale > 0.f ? __fdiv_rn(x[hv * 8 + e], scale) : 0.f;
+      w[hv] = pack_e2m1x8(y);
+    }
+    *reinterpret_cast<uint2*>(codes_t + ((size_t)bh * D + d) * (S / 2) + (size_t)j * 64 + b * 8) = make_uint2(w[0], w[1]);
+    // rows of the B operand of P V are the D output columns; K step = b / 4 (64 keys), block s = b % 4
+    sf[((size_t)bh * (S / 128) + j) * 1024 + (b / 4) * 512 + 16 * (d % 32) + 4 * (d / 32) + (b % 4)] = sc;
+  }
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+// x: [BH, S, D] fp16; mean: [BH, D] fp16 or NULL (K smoothing); amax_ws: [BH] fp32 scratch (overwritten);
+// codes: [BH*S, D/2] bytes; sf: [BH*S/128][D/64][512] bytes; sg: [BH] fp32.  D = 128, S % 128 == 0.
+extern "C" int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH,
+                                 int S, int D, void* stream) {
+  if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_rows: D must be 128");
+  if (BH <= 0 || S <= 0 || S % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_rows: S must be a positive multiple of 128");
+  if (!x_fp16 || !amax_ws || !codes || !sf || !sg_f32) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_rows: null pointer");
+  if (((uintptr_t)x_fp16 | (uintptr_t)codes | (uintptr_t)sf) & 15) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_rows: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * sizeof(float), st);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
+  fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, D);
+  fp4_quant_rows_kernel<128><<<(unsigned)((size_t)BH * S / 128), 1024, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16,
+                                                                              (const float*)amax_ws, (uint8_t*)codes, (uint8_t*)sf,
+                                                                              (float*)sg_f32, S);
+  return qa_check_launch("qa_fp4_quant_rows");
+}
+
+// v: [BH, S, D] fp16 -> codes_t: [BH, D, S/2] bytes (transposed), sf: [BH*S/128][2][512] bytes, sg: [BH] fp32
+extern "C" int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, void* sg_f32, int BH, int S, int D,
+                               void* stream) {
+  if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_vt: D must be 128");
+  if (BH <= 0 || S <= 0 || S % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_vt: S must be a positive multiple of 128");
+  if (!v_fp16 || !amax_ws || !codes_t || !sf || !sg_f32) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_vt: null pointer");
+  if (((uintptr_t)v_fp16 | (uintptr_t)codes_t | (uintptr_t)sf) & 15) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_vt: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * sizeof(float), st);
+  if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
+  const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
+  fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, D);
+  fp4_quant_vt_kernel<128><<<dim3(S / 128, BH), 256, 0, st>>>((const __half*)v_fp16, (const float*)amax_ws, (uint8_t*)codes_t,
+                                                              (uint8_t*)sf, (float*)sg_f32, S);
+  return qa_check_launch("qa_fp4_quant_vt");
+}

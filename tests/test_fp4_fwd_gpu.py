@@ -1,0 +1,76 @@
+"""NVFP4 (microscaling) forward: bit-exact e2m1 codes, e4m3 block scales (in the tcgen05.cp atom layout) and
+per-head scales against the eager definition (oracle/fp4_ref.py); O / lse of the kernel against the definition run on the
+same quantised operands; quantisation-level agreement with fp32 attention math."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _stats(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return (a - b).abs().max().item(), torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+
+
+def _inputs(shape, seed, kind="randn"):
+    g = torch.Generator().manual_seed(seed)
+    q, k, v = [torch.randn(shape, generator=g) for _ in range(3)]
+    if kind == "offset":                     # large per-channel offset on K (exercises the smoothing), logits scaled up
+        k = k + 4.0 * torch.randn(1, shape[1], 1, shape[3], generator=g)
+        q = q * 2.0
+    if kind == "zeros":                      # all-zero 16-blocks, an all-zero V head and tiny magnitudes
+        q[:, :, :, 16:32] = 0
+        v[:, 0] = 0
+        k = k * 1e-3
+    return [t.to(torch.float16) for t in (q, k, v)]
+
+
+@pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((2, 2, 512, 128), "offset"), ((1, 2, 384, 128), "zeros")])
+def test_fp4_quantisation_is_bit_exact(shape, kind):
+    from oracle import fp4_ref
+    from quantizedattention_b200 import attention_fp4 as F
+    q, k, v = _inputs(shape, 400 + shape[2], kind)
+    o = F.quantise_fp4(q.cuda(), k.cuda(), v.cuda())
+    torch.cuda.synchronize()
+    ref = fp4_ref.quantise_inputs(q, k, v)
+    assert torch.equal(o.k_mean.cpu().view(ref["k_mean"].shape), ref["k_mean"])
+    for name in ("sgq", "sgk", "sgv"):
+        assert torch.equal(getattr(o, name).cpu(), ref[name]), name
+    for name in ("sfq", "sfk", "sfv"):
+        assert torch.equal(getattr(o, name).cpu(), ref[name]), name
+    for name in ("q4", "k4", "vt4"):
+        assert torch.equal(getattr(o, name).cpu(), ref[name]), name
+
+
+@pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((1, 4, 1024, 128), "randn"), ((2, 2, 512, 128), "offset"),
+                                        ((1, 2, 384, 128), "zeros")])
+def test_fp4_fwd_matches_definition_and_fp32_math(shape, kind):
+    from oracle import fp4_ref
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_fp4 as F
+    q, k, v = _inputs(shape, 500 + shape[2], kind)
+    O, lse = F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()))
+    torch.cuda.synchronize()
+    Oref, lse_ref, _ = fp4_ref.fp4_fwd(q, k, v)
+    fin = torch.isfinite(Oref.float())
+    assert torch.isfinite(O.float().cpu()[fin]).all()
+    mx, cos = _stats(O.cpu()[fin], Oref[fin])
+    assert mx < 1e-2 and cos > 0.9995, (mx, cos)         # ex2.approx and reciprocal-multiply flip a few e2m1 roundings of P
+    assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
+    if kind != "zeros":
+        base = baseline_pytorch_attention(q.float(), k.float(), v.float(), shape[3], False)
+        mx, cos = _stats(O.cpu(), base)
+        assert cos > (0.95 if kind == "offset" else 0.975), (mx, cos)   # 4-bit operands: quantisation-level agreement only (sharper softmax: lower)
+
+
+def test_sage_attention_3_fp4_validates():
+    from quantizedattention_b200 import attention_fp4 as F
+    q = torch.randn(1, 2, 256, 128, device="cuda", dtype=torch.float16)
+    O = F.sage_attention_3_fp4(q, q, q)
+    assert O.shape == q.shape and O.dtype == torch.float16 and not O.requires_grad
+    with pytest.raises(TypeError):
+        F.sage_attention_3_fp4(q.float(), q.float(), q.float())
+    with pytest.raises(ValueError):
+        F.sage_attention_3_fp4(q[:, :, :200], q[:, :, :200], q[:, :, :200])
+    with pytest.raises(ValueError):
+        F.sage_attention_3_fp4(q[..., :64].contiguous(), q[..., :64].contiguous(), q[..., :64].contiguous())

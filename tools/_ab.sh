@@ -3,6 +3,6 @@
 cp quantizedattention_b200/libqattn.so /tmp/keep.so
 for f in gpurun_in_*.so; do
   cp "$f" quantizedattention_b200/libqattn.so
-  echo "== $f"; timeout 300 python "$@" 2>&1 | grep -E "ms_call|TOPS|ms_kernel|passed|failed|Error|error" | head -12
+  echo "== $f"; timeout 300 python "$@" 2>&1 | grep -E -A4 "ms_call|TOPS|ms_kernel|passed|failed|Error|error|checksums" | head -40
 done
 cp /tmp/keep.so quantizedattention_b200/libqattn.so
