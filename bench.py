@@ -156,6 +156,29 @@ def other_paths(dev, pk):
     res["jvp_cfg4_B16H16S4096D64"] = {"ms_call": msc, "ms_kernel": msk, "TFLOPS_kernel": fj / (msk * 1e-3) / 1e12,
                                       "frac_of_bf16_peak_in_run": frac(fj / (msk * 1e-3) / 1e12, b16)}
     del t6
+    # fp8 (e4m3) and NVFP4 (microscaling) forwards, B*H = 64, S = 8192, D = 128 (kernel time, operands pre-quantised)
+    from quantizedattention_b200 import attention_fp4 as F4
+    from quantizedattention_b200 import attention_fp8 as F8
+    q, k, v = [rn(2, 32, 8192, 128) for _ in range(3)]
+    fl = 4.0 * 64 * 8192 * 8192 * 128
+    with torch.no_grad():
+        ops.TIMING = []
+        timeit(lambda: F8.helion_atten_fp8_fwd(q, k, v), it=5)
+        kt = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "fp8_fwd")
+        ms8 = kt[len(kt) // 2]
+        o4 = F4.quantise_fp4(q, k, v)
+        ops.TIMING = []
+        timeit(lambda: F4.fp4_fwd_prequant(o4), it=5)
+        timeit(lambda: F4.quantise_fp4(q, k, v), it=5)
+        med = lambda name: (lambda x: x[len(x) // 2])(sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == name))
+        ms4, msq, msv = med("fp4_fwd"), med("fp4_quant_rows"), med("fp4_quant_vt")
+        ops.TIMING = None
+    nb = 64 * 8192 * 128 * (2 + 2 + 0.5 + 1.0 / 16)        # amax pass + quantise pass reads, codes + block scales written
+    res["fp8_fwd_S8192_D128"] = {"kernel_ms": ms8, "TFLOPS": fl / (ms8 * 1e-3) / 1e12}
+    res["fp4_fwd_S8192_D128"] = {"kernel_ms": ms4, "TFLOPS": fl / (ms4 * 1e-3) / 1e12, "quant_qk_GBs": nb / (msq * 1e-3) / 1e9,
+                                 "quant_vt_GBs": nb / (msv * 1e-3) / 1e9,
+                                 "note": "tcgen05 kind::mxf4nvf4.block_scale for both contractions; TFLOPS = 4 S^2 D convention"}
+    del q, k, v, o4
     torch.cuda.empty_cache()
     return res
 

@@ -12,7 +12,9 @@
 //                    the four TMEM lane quadrants, which a thread cannot write)
 // Because the microscales travel with the operands, the fp32 accumulator spans k-tiles (unlike the int8 / fp8 path, whose
 // per-tile P and V scales force a drain every k-tile): O stays resident in TMEM and is rescaled only when a row maximum moves.
-// One CTA = one 128-row query tile of one head.  Warps 0-3: softmax (thread = row), 4: TMA producer, 5: MMA issuer.
+// One CTA = one 128-row query tile of one head.  Warps 0-7: softmax (two per 32-row group, 64 keys of the tile each; the row
+// maxima meet through shared memory), 8-11: correction (rescale of O, off the softmax warps' critical path), 12: TMA producer,
+// 13: MMA issuer.
 // TMEM (512 columns): S[2] at 0 / 128, O at 256, scale factors from 384: Q 8, K 2 x 8, V 2 x 8, P 2 x 8 columns.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
@@ -52,16 +54,22 @@ __device__ __forceinline__ float fp4_e4m3_to_float(uint32_t c) {
   const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)c, __NV_E4M3);
   return __half2float(*reinterpret_cast<const __half*>(&h));
 }
-__device__ __forceinline__ uint32_t fp4_pack8(const float* y, float s) {
-  uint32_t w = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    w |= (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(y[2 * i] * s, y[2 * i + 1] * s), __NV_E2M1, cudaRoundNearest) << (8 * i);
+// eight floats -> eight e2m1 codes in one word (element 0 in the low nibble), round to nearest even, saturating
+__device__ __forceinline__ uint32_t fp4_pack8(const float2 (&y)[4]) {
+  uint32_t w;
+  asm("{\n\t.reg .b8 t0, t1, t2, t3;\n\t"
+      "cvt.rn.satfinite.e2m1x2.f32 t0, %2, %1;\n\t"
+      "cvt.rn.satfinite.e2m1x2.f32 t1, %4, %3;\n\t"
+      "cvt.rn.satfinite.e2m1x2.f32 t2, %6, %5;\n\t"
+      "cvt.rn.satfinite.e2m1x2.f32 t3, %8, %7;\n\t"
+      "mov.b32 %0, {t0, t1, t2, t3};\n\t}"
+      : "=r"(w)
+      : "f"(y[0].x), "f"(y[0].y), "f"(y[1].x), "f"(y[1].y), "f"(y[2].x), "f"(y[2].y), "f"(y[3].x), "f"(y[3].y));
   return w;
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(512, 1)
 fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_vt, const __grid_constant__ CUtensorMap tm_sfq,
                const __grid_constant__ CUtensorMap tm_sfk, const __grid_constant__ CUtensorMap tm_sfv, Fp4FwdParams p) {
@@ -70,7 +78,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full[2], p_full[2], o_full[2];
+  __shared__ uint64_t sc_full[2], sc_empty[2], o_ready[2];     // softmax -> correction (rescale factors), correction -> MMA
+  __shared__ float row_sc[2][128];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float xmax[2][2][128];            // [tile parity][column half][row]: raw row maxima exchanged inside a row group
+  __shared__ float xl[2][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * 128;
@@ -79,104 +91,167 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (tid == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&o_full[b], 1);
+      mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], 4); mbar_init(&o_ready[b], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(&tmem_base_s);
+  if (warp == 13) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
   constexpr uint32_t kSfQ = 384, kSfK = 392, kSfV = 408, kSfP = 424;     // TMEM columns of the scale factors
 
-  if (warp < 4) {
-    // =========================== softmax warps: thread = query row ===========================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
-    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;           // accumulator -> log2-domain logit
+  if (warp < 8) {
+    // =========================== softmax warps: two per 32-row group, 64 of the tile's 128 keys each ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");           // whole warpgroups: 8 x 168 + 8 x 88 registers per lane = 2048
+    const int qd = warp & 3, hf = warp >> 2;                      // TMEM lane quadrant (= warp % 4), column half
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
+    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;           // accumulator -> log2-domain logit (c >= 0)
+    const float2 c2 = make_float2(c, c);
     float m = -INFINITY, l = 0.f;
+    uint32_t r[64];                                               // this thread's 64 raw logits of the current tile
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    tmem_ld64(lane_addr + hf * 64, r);
     for (int j = 0; j < nk; ++j) {
       const int sb = j & 1;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
-      tc_fence_after();
-      float u[128];
-      float mx = -INFINITY;
+      tmem_ld_wait();                                             // issued during the previous tile's quantise phase
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t r[64];
-        tmem_ld64(lane_addr + sb * 128 + ch * 64, r);
-        tmem_ld_wait();
+      for (int i = 0; i < 64; i += 8)
 #pragma unroll
-        for (int i = 0; i < 64; ++i) { u[ch * 64 + i] = __uint_as_float(r[i]) * c; mx = fmaxf(mx, u[ch * 64 + i]); }
-      }
-      const float m_new = fmaxf(m, mx);
+        for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(r[i + 2 * a]), __uint_as_float(r[i + 2 * a + 1])));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      xmax[sb][hf][row] = mx;
+      named_bar_sync(1 + qd, 64);                                 // the two warps of the row group: both have read their S columns
+      mx = fmaxf(mx, xmax[sb][hf ^ 1][row]);
+      const float m_new = fmaxf(m, mx * c);
       const float resc = ex2_approx(m - m_new);                     // 0 on the first tile (m = -inf)
       m = m_new;
-      if (j > 0 && __any_sync(0xffffffffu, resc != 1.0f)) {        // O *= 2^(m - m'): only when a row maximum of this warp moved
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);       // P V of tile j-1 has landed in TMEM
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < D / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + 256 + ch * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * resc);
-          tmem_st32(lane_addr + 256 + ch * 32, r);
-        }
+      if (j > 0 && hf == 0) {                                      // O *= 2^(m - m') is the correction warps' job: publish the factor
+        const int k = j - 1, sl = k & 1;
+        mbar_wait(&sc_empty[sl], ((k >> 1) & 1) ^ 1);
+        row_sc[sl][row] = resc;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_full[sl]);
       }
-      // ---- P = exp2(u - m'), microscaled per 16 keys: sfp = e4m3(amax * 448), P4 = e2m1(P * 2688 / sfp)
-      float lsum = 0.f;
-      uint32_t pw[16], sfw[2] = {0u, 0u};
+      // ---- P = exp2(S c - m'), microscaled per 16 keys: sfp = e4m3(amax * 448), P4 = e2m1(P * 2688 / sfp)
+      const float2 nm2 = make_float2(-m_new, -m_new);
+      float2 ls2 = make_float2(0.f, 0.f);
+      float2 pe[32];
+      float am[4];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        float pe[16];
-        float am = 0.f;
+      for (int b = 0; b < 4; ++b) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { pe[e] = ex2_approx(u[b * 16 + e] - m_new); am = fmaxf(am, pe[e]); lsum += pe[e]; }
-        const uint32_t sc = (uint32_t)__nv_cvt_float_to_fp8(am * 448.0f, __NV_SATFINITE, __NV_E4M3);
+        for (int e = 0; e < 8; ++e) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[b * 16 + 2 * e]), __uint_as_float(r[b * 16 + 2 * e + 1])), c2, nm2);
+          pe[b * 8 + e] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          if (e & 1) a1 = fmaxf(a1, fmaxf(pe[b * 8 + e].x, pe[b * 8 + e].y)); else a0 = fmaxf(a0, fmaxf(pe[b * 8 + e].x, pe[b * 8 + e].y));
+          ls2 = __fadd2_rn(ls2, pe[b * 8 + e]);
+        }
+        am[b] = fmaxf(a0, a1);
+      }
+      l = l * resc + (ls2.x + ls2.y);
+      if (j + 1 < nk) {                                            // the raw logits are consumed: fetch the next tile's behind the quantise phase
+        mbar_wait(&s_full[sb ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        tmem_ld64(lane_addr + (sb ^ 1) * 128 + hf * 64, r);
+      }
+      uint32_t pw[8], sfw = 0u;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t sc = (uint32_t)__nv_cvt_float_to_fp8(am[b] * 448.0f, __NV_SATFINITE, __NV_E4M3);
         const float sf = fp4_e4m3_to_float(sc);
         const float inv = sf > 0.f ? __fdividef(2688.0f, sf) : 0.f;
-        pw[2 * b] = fp4_pack8(pe, inv);
-        pw[2 * b + 1] = fp4_pack8(pe + 8, inv);
-        sfw[b >> 2] |= sc << (8 * (b & 3));
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float2 y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = __fmul2_rn(pe[b * 8 + h8 * 4 + i], inv2);
+          pw[2 * b + h8] = fp4_pack8(y);
+        }
+        sfw |= sc << (8 * b);
       }
-      l = l * resc + lsum;
-      tmem_st16(lane_addr + sb * 128, pw);                         // P over the first 16 S columns (8 keys per column)
-      // scale factors of P: one 32-bit word (4 blocks) per K step into the atom layout; tcgen05.cp replicates it over the lanes
-      uint8_t* sfp = smem + L::off_sfp + sb * L::kSf;
-      *reinterpret_cast<uint32_t*>(sfp + 16 * lane + 4 * warp) = sfw[0];
-      *reinterpret_cast<uint32_t*>(sfp + 512 + 16 * lane + 4 * warp) = sfw[1];
+      tmem_st8(lane_addr + sb * 128 + hf * 8, pw);                 // P over the first 16 S columns (8 keys per column): K step hf
+      // scale factors of P: this thread's 4 blocks are one 32-bit word of the K step's atom; tcgen05.cp replicates it over the lanes
+      *reinterpret_cast<uint32_t*>(smem + L::off_sfp + sb * L::kSf + hf * 512 + 16 * lane + 4 * qd) = sfw;
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
-    // ---- epilogue: O * sgv / (2688 * l), log2-LSE
+    // ---- epilogue: O * sgv / (2688 * l), log2-LSE; each warp writes its half of the D columns
+    xl[hf][row] = l;
+    named_bar_sync(1 + qd, 64);
+    l += xl[hf ^ 1][row];
     mbar_wait(&o_full[(nk - 1) & 1], ((nk - 1) >> 1) & 1);
     tc_fence_after();
     const size_t gr = (size_t)bh * p.Sq + q0 + row;
     const float sc_o = __fdividef(p.sgv[bh], 2688.0f * l);
-    __half* dst = p.O + gr * D;
+    __half* dst = p.O + gr * D + hf * (D / 2);
 #pragma unroll
-    for (int ch = 0; ch < D / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(lane_addr + 256 + ch * 32, r);
+    for (int ch = 0; ch < D / 64; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(lane_addr + 256 + hf * (D / 2) + ch * 32, o);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
-        uint4 o;
+        uint4 v;
         __half2 t;
-        t = __floats2half2_rn(__uint_as_float(r[i]) * sc_o, __uint_as_float(r[i + 1]) * sc_o); o.x = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2half2_rn(__uint_as_float(r[i + 2]) * sc_o, __uint_as_float(r[i + 3]) * sc_o); o.y = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2half2_rn(__uint_as_float(r[i + 4]) * sc_o, __uint_as_float(r[i + 5]) * sc_o); o.z = *reinterpret_cast<uint32_t*>(&t);
-        t = __floats2half2_rn(__uint_as_float(r[i + 6]) * sc_o, __uint_as_float(r[i + 7]) * sc_o); o.w = *reinterpret_cast<uint32_t*>(&t);
-        *reinterpret_cast<uint4*>(dst + ch * 32 + i) = o;
+        t = __floats2half2_rn(__uint_as_float(o[i]) * sc_o, __uint_as_float(o[i + 1]) * sc_o); v.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(__uint_as_float(o[i + 2]) * sc_o, __uint_as_float(o[i + 3]) * sc_o); v.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(__uint_as_float(o[i + 4]) * sc_o, __uint_as_float(o[i + 5]) * sc_o); v.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(__uint_as_float(o[i + 6]) * sc_o, __uint_as_float(o[i + 7]) * sc_o); v.w = *reinterpret_cast<uint32_t*>(&t);
+        *reinterpret_cast<uint4*>(dst + ch * 32 + i) = v;
       }
     }
-    p.lse[gr] = m + log2f(l);
-  } else if (warp == 4) {
+    if (hf == 0) p.lse[gr] = m + log2f(l);
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // =========================== correction warps (thread = row): O *= 2^(m - m') between P V(j-1) and P V(j) ===========================
+    // Off the softmax warps' critical path: they never wait for the tensor pipe; the rescale happens only when a row maximum
+    // of the warp's 32 rows moved (most early tiles, few late ones).
+    const int qd = warp & 3, row = qd * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
+    for (int j = 1; j < nk; ++j) {
+      const int k = j - 1, sl = k & 1;
+      mbar_wait(&sc_full[sl], (k >> 1) & 1);
+      const float resc = row_sc[sl][row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sc_empty[sl]);
+      if (__any_sync(0xffffffffu, resc != 1.0f)) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);       // P V of tile j-1 has landed in TMEM
+        tc_fence_after();
+        const float2 rs2 = make_float2(resc, resc);
+#pragma unroll
+        for (int ch = 0; ch < D / 64; ++ch) {
+          uint32_t o[64];
+          tmem_ld64(lane_addr + 256 + ch * 64, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            const float2 t = __fmul2_rn(make_float2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), rs2);
+            o[i] = __float_as_uint(t.x); o[i + 1] = __float_as_uint(t.y);
+          }
+          tmem_st32(lane_addr + 256 + ch * 64, *reinterpret_cast<uint32_t (*)[32]>(&o[0]));
+          tmem_st32(lane_addr + 256 + ch * 64 + 32, *reinterpret_cast<uint32_t (*)[32]>(&o[32]));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_ready[j & 1]);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");            // warps 12-15 (14, 15 idle): one instruction for the warpgroup
+    if (warp == 12) {
     // =========================== TMA producer ===========================
     if (elect_one()) {
       tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt);
@@ -193,7 +268,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tma_load_2d(smem + L::off_sfv + s * L::kSf, &tm_sfv, &kv_full[s], 0, bh * (p.Sk / 128) + j);
       }
     }
-  } else {
+  } else if (warp == 13) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // e2m1 x e2m1, K-major, ue4m3 scales, N = 128 (keys / D)
@@ -219,7 +294,8 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       for (int j = 0; j < nk; ++j) {
         const int s = j % STAGES, sb = j & 1;
         if (j + 1 < nk) issue_s(j + 1);           // overwrites the buffer that held P(j-1): P V(j-1) is ahead of it in the in-order pipe
-        mbar_wait(&p_full[sb], (j >> 1) & 1);     // P, its scale factors and any rescale of O are in place
+        mbar_wait(&p_full[sb], (j >> 1) & 1);     // P and its scale factors are in place
+        if (j > 0) mbar_wait(&o_ready[sb], ((j - 1) >> 1) & 1);   // ... and O carries the rescale of this tile
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile), sfv = smem_u32(smem + L::off_sfv + s * L::kSf);
         const uint32_t sfp = smem_u32(smem + L::off_sfp + sb * L::kSf);
@@ -235,10 +311,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         umma_commit(&kv_empty[s]);
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tbase);
+  if (warp == 13) tmem_dealloc<512>(tbase);
 }
 
 }  // namespace qa
@@ -279,6 +356,6 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   auto kern = fp4_fwd_kernel<STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  kern<<<dim3(Sq / 128, BH), 192, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+  kern<<<dim3(Sq / 128, BH), 512, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
   return qa_check_launch("qa_fp4_fwd");
 }

@@ -216,6 +216,41 @@ def bf16_Amn_2atoms_lbo1024_sbo8192():
     return _at16(1024, 8192)
 
 
+# ------------------------------------------------------------------ NVFP4 block-scaled (kind::mxf4nvf4.block_scale.block16)
+def _nvf4(ts):
+    rng = np.random.default_rng(11)
+    n_mma, N = 2, 128
+    K = 64 * n_mma
+    ac, bc = rng.integers(0, 16, (128, K)), rng.integers(0, 16, (N, K))
+    sfa = rng.integers(0x28, 0x48, (128, K // 16)).astype(np.uint8)           # ue4m3 codes around 1.0
+    sfb = rng.integers(0x28, 0x48, (N, K // 16)).astype(np.uint8)
+    A, B = pm.E2M1[ac].astype(np.float64), pm.E2M1[bc].astype(np.float64)
+    f = lambda b: torch.from_numpy(b.copy()).view(torch.float8_e4m3fn).float().numpy().astype(np.float64)
+    fa, fb = f(sfa), f(sfb)
+    ref = np.zeros((128, N))
+    for blk in range(K // 16):
+        sl = slice(16 * blk, 16 * blk + 16)
+        ref += (A[:, sl] @ B[:, sl].T) * fa[:, blk:blk + 1] * fb[:, blk][None, :]
+    ide = pm.idesc_bs(1, 1, 128, N, 0)
+    b_img = pm.image_rows(pm.pack_nibbles(bc), 4)                            # rows of 64 bytes, 64-byte swizzle
+    if ts:                                                                   # A from TMEM: 8 e2m1 per 32-bit column
+        a_words = pm.pack_nibbles(ac).view(np.uint32).reshape(128, K // 8)
+        got = pm.run_mma_bs(a_words, b_img, pm.sf_atoms(sfa), pm.sf_atoms(sfb), N, n_mma, ide, a_in_tmem=1, a_tmem_cols=K // 8)
+    else:
+        got = pm.run_mma_bs(pm.image_rows(pm.pack_nibbles(ac), 4), b_img, pm.sf_atoms(sfa), pm.sf_atoms(sfb), N, n_mma, ide)
+    return float(np.abs(got - ref).max() / np.abs(ref).max())
+
+
+@case
+def nvf4_blockscaled_ss_sw64():
+    return _nvf4(False)
+
+
+@case
+def nvf4_blockscaled_ts():
+    return _nvf4(True)
+
+
 if __name__ == "__main__":
     for name in sys.argv[1:]:
         r = CASES[name]()

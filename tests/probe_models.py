@@ -63,3 +63,38 @@ def run_tma(src: torch.Tensor, elem_bytes, dims, strides_bytes, box, swizzle, co
     _lib.check(rc, "qa_probe_tma", L)
     torch.cuda.synchronize()
     return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------ block-scaled (NVFP4) probe
+E2M1 = np.array([0, 0.5, 1, 1.5, 2, 3, 4, 6, -0.0, -0.5, -1, -1.5, -2, -3, -4, -6], dtype=np.float32)
+
+
+def idesc_bs(a_fmt, b_fmt, M, N, sf_fmt, a_major=0, b_major=0, a_sf=0, b_sf=0):
+    """Block-scaled instruction descriptor (csrc/qa_ptx.cuh umma_idesc_bs)."""
+    return ((b_sf << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) | (sf_fmt << 23)
+            | ((M >> 4) << 24) | (a_sf << 29))
+
+
+def pack_nibbles(codes):
+    """[rows, K] e2m1 codes -> [rows, K/2] bytes, element 2i in the low nibble."""
+    return (codes[:, 0::2] | (codes[:, 1::2] << 4)).astype(np.uint8)
+
+
+def sf_atoms(sf):
+    """[128, 4 * n] ue4m3 bytes -> n atoms of 512 B: byte 16 * (r % 32) + 4 * (r / 32) + s = scale of row r, block 4k + s."""
+    n = sf.shape[1] // 4
+    return np.ascontiguousarray(sf.reshape(4, 32, n, 4).transpose(2, 1, 0, 3)).reshape(-1)
+
+
+def run_mma_bs(a_img, b_img, sfa_img, sfb_img, n_cols, n_mma, idesc_v, *, kind=0, a_in_tmem=0, a_tmem_cols=0, a_kcols=8, lay=4,
+               sbo=512, kstep=32):
+    L = _lib.dev_lib()
+    g = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).reshape(-1)).cuda()
+    a, b, fa, fb = g(a_img), g(b_img), g(sfa_img), g(sfb_img)
+    d = torch.zeros((128, n_cols), dtype=torch.float32, device="cuda")
+    rc = L.qa_probe_mma_bs(_lib.ptr(a), a.numel(), _lib.ptr(b), b.numel(), _lib.ptr(fa), fa.numel(), _lib.ptr(fb), fb.numel(),
+                           _lib.ptr(d), 16, sbo, lay, kstep, 16, sbo, lay, kstep, ctypes.c_uint(idesc_v), kind, n_mma, n_cols, 4, 4,
+                           a_in_tmem, a_tmem_cols, a_kcols, _lib.cur_stream())
+    _lib.check(rc, "qa_probe_mma_bs", L)
+    torch.cuda.synchronize()
+    return d.cpu().numpy()

@@ -66,7 +66,7 @@ def test_umma_layout_cases():
     _save()
     print(json.dumps(res, indent=1))
     ok = lambda v: (v is True) or (isinstance(v, float) and v < 2e-2)
-    for must in ("i8_kmajor_sw128", "i8_kmajor_sw64", "f16_kmajor_sw128"):
+    for must in ("i8_kmajor_sw128", "i8_kmajor_sw64", "f16_kmajor_sw128", "nvf4_blockscaled_ss_sw64", "nvf4_blockscaled_ts"):
         assert ok(res.get(must)), res
     assert any(ok(v) for k, v in res.items() if k.startswith("i8_Bmn_sw128")), res
     assert any(ok(v) for k, v in res.items() if k.startswith("bf16_Bmn_2atoms")), res

@@ -1,4 +1,4 @@
-"""Small single-kernel targets for ncu.  Usage: python tools/prof_target.py bf16_fwd|jvp|int8_fwd"""
+"""Small single-kernel targets for ncu.  Usage: python tools/prof_target.py bf16_fwd|jvp|int8_fwd|bf16_bwd|int8_bwd|fp4_fwd"""
 import sys
 
 import torch
@@ -42,5 +42,11 @@ elif which == "int8_bwd":
     delta = ops.bwd_delta(dO.view(-1, D), O)
     for _ in range(3):
         ops.int8_bwd_prequant(qi, ki, vi, doi, sq, sk, sv, sdo, lse32, delta, None, BH, S, D)
+elif which == "fp4_fwd":
+    from quantizedattention_b200 import attention_fp4 as F4
+    q, k, v = [torch.randn(1, 37, 8192, 128, device="cuda", dtype=torch.float16) for _ in range(3)]   # 16 waves of 148 CTAs
+    o = F4.quantise_fp4(q, k, v)
+    for _ in range(3):
+        F4.fp4_fwd_prequant(o)
 torch.cuda.synchronize()
 print("ok")

@@ -39,6 +39,10 @@ __global__ void bench(long long* out, float seed) {
       if (OP == 14) asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(u[i]) : "f"(a[i]));        // F2I.TRUNC
       if (OP == 15) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); a2[i] = __ffma2_rn(a2[i], c2, d2); a2[i] = __fadd2_rn(a2[i], d2); }   // MUFU + 2 packed ops (overlap?)
       if (OP == 16) a[i] = a[i] * c;                                                          // FMUL
+      if (OP == 18) { asm volatile("{.reg .b8 t; cvt.rn.satfinite.e2m1x2.f32 t, %1, %2; cvt.u32.u8 %0, t;}" : "=r"(u[i]) : "f"(a[i]), "f"(b[i])); a[i] = __uint_as_float(u[i] + 0x3f800000u); }   // F2FP e2m1x2 + IADD (loop-carried)
+      if (OP == 19) { asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(b[i])); a[i] = __uint_as_float((u[i] & 0xffffu) + 0x3f800000u); }   // F2FP f16x2 + LOP + IADD (loop-carried)
+      if (OP == 20) { asm volatile("{.reg .b16 t; cvt.rn.satfinite.e4m3x2.f32 t, %1, %2; cvt.u32.u16 %0, t;}" : "=r"(u[i]) : "f"(a[i]), "f"(b[i])); a[i] = __uint_as_float(u[i] + 0x3f800000u); }   // F2FP e4m3x2 + IADD
+      if (OP == 21) { u[i] = u[i] + 0x3f800000u + w[i]; }   // IADD3 alone
       if (OP == 17) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(a[i]) : "r"(u[i]));   // HADD2.F32 convert
     }
   }
@@ -73,5 +77,6 @@ int main() {
   run<0>("FFMA", d); run<16>("FMUL", d); run<1>("FFMA2 (scalar c,d)", d); run<12>("FFMA2 (3 pairs)", d); run<2>("FADD2", d); run<3>("FMUL2.RZ", d);
   run<4>("MUFU.EX2 f32", d); run<10>("MUFU.EX2 f16x2", d); run<5>("I2FP", d); run<6>("FHADD", d); run<17>("HADD2.F32 cvt", d); run<7>("F2FP pack", d);
   run<8>("I2IP", d); run<9>("PRMT", d); run<11>("HMNMX2", d); run<13>("HFMA2", d); run<14>("F2I.TRUNC", d); run<15>("MUFU+FFMA2+FADD2 (per instr)", d);
+  run<18>("F2FP.E2M1x2 + IADD", d); run<19>("F2FP.F16x2 + LOP + IADD", d); run<20>("F2FP.E4M3x2 + IADD", d); run<21>("IADD3", d);
   return 0;
 }
