@@ -6,7 +6,7 @@ CUDA kernels (csrc/quant_fp4.cu, csrc/attn_fp4_fwd.cu) implement:
 
   two-level scale   sg = amax_head / 2688 (fp32),  sf = e4m3_rn(amax_blk16 / 6 / sg),  x4 = e2m1_rn(x / (sf * sg))
                     Q, K (K minus its token mean first, one fp16 rounding): blocks of 16 along D;  V: blocks of 16 KEYS
-  logits (log2)     u = float(Q4 K4^T with block scales) * (sgq * sgk * sm_scale * log2 e)           per 128-key tile
+  logits (log2)     u = float(Q4 K4^T with block scales) * (sgq * sgk * sm_scale * log2 e)           per step of 64 / 128 keys
   online softmax    m' = max(m, rowmax u),  P = exp2(u - m'),  l = l * 2^(m - m') + sum P              fp32
   P microscaling    sfp = e4m3_rn(amax_blk16(P) * 448),  P4 = e2m1_rn(P * 2688 / sfp)                  per row, 16 keys
   O                 O = O * 2^(m - m') + (P4 sfp)(V4 sfv);   out = O * sgv / (2688 * l),  lse = m' + log2 l
@@ -85,8 +85,9 @@ def quantise_inputs(q, k, v):
             "sgq": sgq, "sgk": sgk, "sgv": sgv}
 
 
-def fp4_fwd(q, k, v):
-    """q, k, v fp16 [B,H,S,D] -> (O fp16 [B,H,S,D], lse fp32 [B*H, S] (log2 domain), quantised operands)."""
+def fp4_fwd(q, k, v, step: int = 64):
+    """q, k, v fp16 [B,H,S,D] -> (O fp16 [B,H,S,D], lse fp32 [B*H, S] (log2 domain), quantised operands).
+    step: keys per online-softmax step (64: the default two-CTA kernel; 128: the one-CTA kernel)."""
     B, H, S, D = q.shape
     G = B * H
     qi = quantise_inputs(q, k, v)
@@ -96,18 +97,18 @@ def fp4_fwd(q, k, v):
     O = torch.zeros((G, S, D))
     l = torch.zeros((G, S, 1))
     m = torch.full((G, S, 1), float("-inf"))
-    for j in range(S // 128):
-        ks = slice(j * 128, (j + 1) * 128)
+    for j in range(S // step):
+        ks = slice(j * step, (j + 1) * step)
         u = torch.matmul(qd, kd[:, ks].transpose(1, 2)) * c
         m_new = torch.max(m, u.amax(-1, keepdim=True))
         P = torch.exp2(u - m_new)
         resc = torch.exp2(m - m_new)
         l = l * resc + P.sum(-1, keepdim=True)
-        Pb = P.reshape(G, S, 8, 16)
+        Pb = P.reshape(G, S, step // 16, 16)
         sfp_v, _ = e4m3_rn(Pb.amax(-1) * 448.0)
         y = torch.where(sfp_v[..., None] > 0, Pb * 2688.0 / sfp_v[..., None], torch.zeros_like(Pb))
         pq, _ = e2m1_rn(y)
-        Pd = (pq * sfp_v[..., None]).reshape(G, S, 128)
+        Pd = (pq * sfp_v[..., None]).reshape(G, S, step)
         O = O * resc + torch.matmul(Pd, vd[:, ks])
         m = m_new
     out = O * (qi["sgv"].view(G, 1, 1) / 2688.0) / l

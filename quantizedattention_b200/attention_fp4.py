@@ -82,7 +82,8 @@ def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
     return Fp4Operands(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, k_mean, (B, H, Sq, Sk, D))
 
 
-def fp4_fwd_prequant(o: Fp4Operands):
+def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0):
+    """variant 0: two CTAs per SM, 64-key online-softmax steps (default); 1: one CTA per SM, 128-key tiles."""
     B, H, Sq, Sk, D = o.shape
     dev = o.q4.device
     O = torch.empty((B * H * Sq, D), dtype=torch.float16, device=dev)
@@ -91,7 +92,7 @@ def fp4_fwd_prequant(o: Fp4Operands):
     with torch.cuda.device(dev), ops._timed("fp4_fwd"):
         _lib.check(L.qa_fp4_fwd(_lib.ptr(o.q4), _lib.ptr(o.sfq), _lib.ptr(o.sgq), _lib.ptr(o.k4), _lib.ptr(o.sfk), _lib.ptr(o.sgk),
                                 _lib.ptr(o.vt4), _lib.ptr(o.sfv), _lib.ptr(o.sgv), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
-                                _lib.cur_stream()), "qa_fp4_fwd")
+                                int(variant), _lib.cur_stream()), "qa_fp4_fwd")
     return O.view(B, H, Sq, D), lse.view(B * H, Sq)
 
 

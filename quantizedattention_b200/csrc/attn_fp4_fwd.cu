@@ -318,15 +318,279 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (warp == 13) tmem_dealloc<512>(tbase);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Default variant: TWO CTAs per SM.  The one-CTA kernel above is bound by the latency chain of its softmax warps (wait for
+// the logits, TMEM load, maximum, exp2, microscale, TMEM store, fences: ~2.3k clocks per 128-key tile with every unit below
+// 50 %, profiles/r02_fp4_fwd_ncu.txt), and its two warps per row group run in lock step.  Two independent CTAs on an SM
+// interleave those chains.  To fit, a CTA owns 256 TMEM columns and 64 KB of shared memory and advances in steps of 64 keys:
+//   TMEM: S [0,64)  P[2] [64,80)  scale factors Q [80,88) K[2] [88,104) V[2] [104,120) P[2] [120,128)  O [128,256)
+//   S = Q K_h^T is an N = 64 MMA; the scales of keys 64h.. are columns 2h, 2h + 1 of the tile's 128-row atom (probe case
+//   nvf4_blockscaled_n64_upper_half); P V is one K = 64 MMA per step.  S is single-buffered: the issuer refills it as soon as
+//   the softmax warps hold the logits in registers (s_free); P and its scale factors are double-buffered.
+// 12 warps: 0-3 softmax (thread = row, setmaxnreg 128), 4-7 correction, 8 TMA producer, 9 MMA issuer, 10-11 idle.
+// ---------------------------------------------------------------------------------------------------------
+template <int STAGES>
+struct Fp4Fwd2Smem {
+  static constexpr int kTile = 128 * 64;
+  static constexpr int kSf = 1024;
+  static constexpr int off_q = 0;
+  static constexpr int off_k = off_q + kTile;
+  static constexpr int off_v = off_k + STAGES * kTile;
+  static constexpr int off_sfq = off_v + STAGES * kTile;
+  static constexpr int off_sfk = off_sfq + kSf;
+  static constexpr int off_sfv = off_sfk + STAGES * kSf;
+  static constexpr int off_sfp = off_sfv + STAGES * kSf;       // [2] x 512 B
+  static constexpr int total = off_sfp + 1024 + 1024;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(384, 2)
+fp4_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_vt, const __grid_constant__ CUtensorMap tm_sfq,
+                const __grid_constant__ CUtensorMap tm_sfk, const __grid_constant__ CUtensorMap tm_sfv, Fp4FwdParams p) {
+  using L = Fp4Fwd2Smem<STAGES>;
+  constexpr int D = kFp4D;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full, s_free, p_full[2], o_full[2];
+  __shared__ uint64_t sc_full[2], sc_empty[2], o_ready[2];
+  __shared__ float row_sc[2][128];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y, q0 = blockIdx.x * 128;
+  const int nk = p.Sk / 128, nst = 2 * nk;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&s_full, 1); mbar_init(&s_free, 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1);
+      mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], 4); mbar_init(&o_ready[b], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<256>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  constexpr uint32_t kP = 64, kSfQ = 80, kSfK = 88, kSfV = 104, kSfP = 120, kO = 128;
+
+  if (warp < 4) {
+    // =========================== softmax warps: thread = query row, 64 keys per step ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");           // 4 x 128 + 8 x 56 registers per lane = 960 = 12 x 80
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;
+    const float2 c2 = make_float2(c, c);
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < nst; ++t) {
+      const int pb = t & 1;
+      mbar_wait(&s_full, pb);
+      tc_fence_after();
+      uint32_t r[64];
+      tmem_ld64(lane_addr, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free);                        // the logits are in registers: S may be refilled
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 64; i += 8)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(r[i + 2 * a]), __uint_as_float(r[i + 2 * a + 1])));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = fmaxf(m, mx * c);
+      const float resc = ex2_approx(m - m_new);
+      m = m_new;
+      if (t > 0) {                                                 // O *= 2^(m - m') is the correction warps' job
+        const int k = t - 1, sl = k & 1;
+        mbar_wait(&sc_empty[sl], ((k >> 1) & 1) ^ 1);
+        row_sc[sl][row] = resc;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sc_full[sl]);
+      }
+      const float2 nm2 = make_float2(-m_new, -m_new);
+      float2 ls2 = make_float2(0.f, 0.f);
+      uint32_t pw[8], sfw = 0u;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float2 pe[8];
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[b * 16 + 2 * e]), __uint_as_float(r[b * 16 + 2 * e + 1])), c2, nm2);
+          pe[e] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          if (e & 1) a1 = fmaxf(a1, fmaxf(pe[e].x, pe[e].y)); else a0 = fmaxf(a0, fmaxf(pe[e].x, pe[e].y));
+          ls2 = __fadd2_rn(ls2, pe[e]);
+        }
+        const uint32_t sc = (uint32_t)__nv_cvt_float_to_fp8(fmaxf(a0, a1) * 448.0f, __NV_SATFINITE, __NV_E4M3);
+        const float sf = fp4_e4m3_to_float(sc);
+        const float inv = sf > 0.f ? __fdividef(2688.0f, sf) : 0.f;
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          float2 y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = __fmul2_rn(pe[h8 * 4 + i], inv2);
+          pw[2 * b + h8] = fp4_pack8(y);
+        }
+        sfw |= sc << (8 * b);
+      }
+      l = l * resc + (ls2.x + ls2.y);
+      tmem_st8(lane_addr + kP + 8 * pb, pw);
+      *reinterpret_cast<uint32_t*>(smem + L::off_sfp + pb * 512 + 16 * lane + 4 * warp) = sfw;
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[pb]);
+    }
+    // ---- epilogue: O * sgv / (2688 * l), log2-LSE
+    mbar_wait(&o_full[(nst - 1) & 1], ((nst - 1) >> 1) & 1);
+    tc_fence_after();
+    const size_t gr = (size_t)bh * p.Sq + q0 + row;
+    const float sc_o = __fdividef(p.sgv[bh], 2688.0f * l);
+    __half* dst = p.O + gr * D;
+#pragma unroll
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(lane_addr + kO + ch * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 v;
+        __half2 h2;
+        h2 = __floats2half2_rn(__uint_as_float(o[i]) * sc_o, __uint_as_float(o[i + 1]) * sc_o); v.x = *reinterpret_cast<uint32_t*>(&h2);
+        h2 = __floats2half2_rn(__uint_as_float(o[i + 2]) * sc_o, __uint_as_float(o[i + 3]) * sc_o); v.y = *reinterpret_cast<uint32_t*>(&h2);
+        h2 = __floats2half2_rn(__uint_as_float(o[i + 4]) * sc_o, __uint_as_float(o[i + 5]) * sc_o); v.z = *reinterpret_cast<uint32_t*>(&h2);
+        h2 = __floats2half2_rn(__uint_as_float(o[i + 6]) * sc_o, __uint_as_float(o[i + 7]) * sc_o); v.w = *reinterpret_cast<uint32_t*>(&h2);
+        *reinterpret_cast<uint4*>(dst + ch * 32 + i) = v;
+      }
+    }
+    p.lse[gr] = m + log2f(l);
+  } else if (warp < 8) {
+    // =========================== correction warps: O *= 2^(m - m') between P V(t-1) and P V(t) ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int qd = warp & 3, row = qd * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
+    for (int t = 1; t < nst; ++t) {
+      const int k = t - 1, sl = k & 1;
+      mbar_wait(&sc_full[sl], (k >> 1) & 1);
+      const float resc = row_sc[sl][row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sc_empty[sl]);
+      if (__any_sync(0xffffffffu, resc != 1.0f)) {
+        mbar_wait(&o_full[(t - 1) & 1], ((t - 1) >> 1) & 1);
+        tc_fence_after();
+        const float2 rs2 = make_float2(resc, resc);
+#pragma unroll
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(lane_addr + kO + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = __fmul2_rn(make_float2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), rs2);
+            o[i] = __float_as_uint(x.x); o[i + 1] = __float_as_uint(x.y);
+          }
+          tmem_st32(lane_addr + kO + ch * 32, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_ready[t & 1]);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");            // warps 8-11 (10, 11 idle): one instruction for the warpgroup
+    if (warp == 8) {
+      // =========================== TMA producer ===========================
+      if (elect_one()) {
+        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt);
+        mbar_expect_tx(&q_full, L::kTile + L::kSf);
+        tma_load_2d(smem + L::off_q, &tm_q, &q_full, 0, bh * p.Sq + q0);
+        tma_load_2d(smem + L::off_sfq, &tm_sfq, &q_full, 0, (bh * p.Sq + q0) / 128);
+        for (int j = 0; j < nk; ++j) {
+          const int s = j % STAGES;
+          mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * L::kTile + 2 * L::kSf);
+          tma_load_2d(smem + L::off_k + s * L::kTile, &tm_k, &kv_full[s], 0, bh * p.Sk + j * 128);
+          tma_load_2d(smem + L::off_sfk + s * L::kSf, &tm_sfk, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+          tma_load_2d(smem + L::off_v + s * L::kTile, &tm_vt, &kv_full[s], j * 64, bh * D);
+          tma_load_2d(smem + L::off_sfv + s * L::kSf, &tm_sfv, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+        }
+      }
+    } else if (warp == 9) {
+      // =========================== MMA issuer ===========================
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = umma_idesc_bs(1, 1, 0, 0, 128, 64, 0);       // S step: N = 64 keys
+        constexpr uint32_t idesc_o = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);      // O: N = D
+        const uint32_t q_addr = smem_u32(smem + L::off_q);
+        auto issue_s = [&](int t) {                                                // S = Q K_(step t)^T
+          const int j = t >> 1, h = t & 1, s = j % STAGES, jb = j & 1;
+          if (h == 0) {
+            mbar_wait(&kv_full[s], (j / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t sfk = smem_u32(smem + L::off_sfk + s * L::kSf);
+            tmem_cp_sf(tbase + kSfK + jb * 8, sfk);
+            tmem_cp_sf(tbase + kSfK + jb * 8 + 4, sfk + 512);
+          }
+          const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile) + h * (64 * 64);   // rows 64h .. 64h + 63
+#pragma unroll
+          for (int kd = 0; kd < 2; ++kd)
+            umma_nvf4_ss(tbase, umma_smem_desc(q_addr + kd * 32, 16, 512, kSwz64), umma_smem_desc(k_addr + kd * 32, 16, 512, kSwz64), idesc_s,
+                         tbase + kSfQ + kd * 4, tbase + kSfK + jb * 8 + kd * 4 + 2 * h, kd > 0);
+          umma_commit(&s_full);
+        };
+        mbar_wait(&q_full, 0);
+        tc_fence_after();
+        tmem_cp_sf(tbase + kSfQ, smem_u32(smem + L::off_sfq));
+        tmem_cp_sf(tbase + kSfQ + 4, smem_u32(smem + L::off_sfq) + 512);
+        issue_s(0);
+        for (int t = 0; t < nst; ++t) {
+          const int j = t >> 1, h = t & 1, s = j % STAGES, jb = j & 1, pb = t & 1;
+          if (t + 1 < nst) {
+            mbar_wait(&s_free, pb);               // every softmax warp holds S(t) in registers
+            tc_fence_after();
+            issue_s(t + 1);
+          }
+          mbar_wait(&p_full[pb], (t >> 1) & 1);
+          if (t > 0) mbar_wait(&o_ready[pb], ((t - 1) >> 1) & 1);
+          tc_fence_after();
+          if (h == 0) {
+            const uint32_t sfv = smem_u32(smem + L::off_sfv + s * L::kSf);
+            tmem_cp_sf(tbase + kSfV + jb * 8, sfv);
+            tmem_cp_sf(tbase + kSfV + jb * 8 + 4, sfv + 512);
+          }
+          tmem_cp_sf(tbase + kSfP + pb * 4, smem_u32(smem + L::off_sfp + pb * 512));
+          const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile) + h * 32;         // keys 64h .. of every D row
+          umma_nvf4_ts(tbase + kO, tbase + kP + 8 * pb, umma_smem_desc(v_addr, 16, 512, kSwz64), idesc_o, tbase + kSfP + pb * 4,
+                       tbase + kSfV + jb * 8 + 4 * h, t > 0);
+          umma_commit(&o_full[pb]);
+          if (h == 1) umma_commit(&kv_empty[s]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<256>(tbase);
+}
+
 }  // namespace qa
 
 using namespace qa;
 
 // q4, k4: [BH*S, 64] bytes (e2m1 pairs); vt4: [BH, 128, Sk/2] bytes; sf*: 512-byte atoms, 2 per 128-row tile; sg*: [BH] fp32
 // (all produced by qa_fp4_quant_rows / qa_fp4_quant_vt).  O: fp16 [BH*Sq, 128]; lse: fp32 [BH*Sq] (log2 domain).
+// variant 0: two CTAs per SM, 64-key steps (default); 1: one CTA per SM, 128-key tiles.
 extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
                           const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
-                          int D, void* stream) {
+                          int D, int variant, void* stream) {
   if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: D must be 128");
   if (BH <= 0 || Sq <= 0 || Sk <= 0 || Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: Sq, Sk must be positive multiples of 128");
   if ((long long)BH * Sq >= (1ll << 31) || (long long)BH * Sk >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: BH * S must stay below 2^31");
@@ -335,6 +599,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
     if (!ptrs[i]) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: null pointer");
     if (i != 2 && i != 5 && i != 8 && i != 10 && ((uintptr_t)ptrs[i] & 15)) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: 16-byte alignment required");
   }
+  if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: variant must be 0 (two CTAs per SM, 64-key steps) or 1 (one CTA per SM)");
   constexpr int STAGES = 4;
   using L = Fp4FwdSmem<STAGES>;
   CUtensorMap tq, tk, tv, tsq, tsk, tsv;
@@ -353,6 +618,14 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   p.sgq = (const float*)sgq; p.sgk = (const float*)sgk; p.sgv = (const float*)sgv;
   p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  if (variant == 0) {
+    using L2 = Fp4Fwd2Smem<3>;
+    auto kern2 = fp4_fwd2_kernel<3>;
+    cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::total);
+    if (e2 != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e2));
+    kern2<<<dim3(Sq / 128, BH), 384, L2::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+    return qa_check_launch("qa_fp4_fwd");
+  }
   auto kern = fp4_fwd_kernel<STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));

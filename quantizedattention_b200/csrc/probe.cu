@@ -126,7 +126,7 @@ struct ProbeMmaBsParams {
   uint32_t idesc;
   int kind;               // 0 = mxf4nvf4 block16 (ue4m3 scales, K = 64), 1 = mxf4 block32 (ue8m0, K = 64), 2 = mxf8f6f4 block32 (K = 32)
   int n_mma, n_cols;
-  int sfa_cols_per_mma, sfb_cols_per_mma;   // TMEM columns (and 128-byte quarter atoms) the scale factors advance per MMA
+  int sfa_cols_per_mma, sfb_cols_per_mma;   // TMEM columns the scale factors advance per MMA; bits 8.. of sfb_cols_per_mma: first column offset of B's scales
   int a_in_tmem, a_tmem_cols, a_tmem_kstep_cols;
 };
 
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) probe_mma_bs_kernel(ProbeMmaBsParams p) {
       tmem_cp_32x128b_warpx4(tbase + sfb_col0 + 4 * i, umma_smem_desc(smem_u32(sfb) + 512 * i, 0, 128, kSwzNone));
     for (int k = 0; k < p.n_mma; ++k) {                       // tcgen05.cp and tcgen05.mma execute in issue order
       const uint64_t bd = umma_smem_desc(smem_u32(sb) + k * p.b_kstep_bytes, p.b_lbo, p.b_sbo, p.b_layout);
-      const uint32_t acc = k > 0, tsfa = tbase + sfa_col0 + k * p.sfa_cols_per_mma, tsfb = tbase + sfb_col0 + k * p.sfb_cols_per_mma;
+      const uint32_t acc = k > 0, tsfa = tbase + sfa_col0 + k * p.sfa_cols_per_mma, tsfb = tbase + sfb_col0 + (p.sfb_cols_per_mma >> 8) + k * (p.sfb_cols_per_mma & 0xff);
       if (p.a_in_tmem) {
         const uint32_t at = tbase + a_col0 + k * p.a_tmem_kstep_cols;
         umma_nvf4_ts(tbase, at, bd, p.idesc, tsfa, tsfb, acc);

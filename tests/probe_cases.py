@@ -242,6 +242,49 @@ def _nvf4(ts):
 
 
 @case
+def nvf4_blockscaled_n64():
+    """N = 64 (a 64-key step): the B scale factors are the first two columns (rows 0..63) of their own atom."""
+    rng = np.random.default_rng(12)
+    n_mma, N = 2, 64
+    K = 64 * n_mma
+    ac, bc = rng.integers(0, 16, (128, K)), rng.integers(0, 16, (N, K))
+    sfa = rng.integers(0x28, 0x48, (128, K // 16)).astype(np.uint8)
+    sfb = rng.integers(0x28, 0x48, (N, K // 16)).astype(np.uint8)
+    A, B = pm.E2M1[ac].astype(np.float64), pm.E2M1[bc].astype(np.float64)
+    f = lambda b: torch.from_numpy(b.copy()).view(torch.float8_e4m3fn).float().numpy().astype(np.float64)
+    fa, fb = f(sfa), f(sfb)
+    ref = np.zeros((128, N))
+    for blk in range(K // 16):
+        sl = slice(16 * blk, 16 * blk + 16)
+        ref += (A[:, sl] @ B[:, sl].T) * fa[:, blk:blk + 1] * fb[:, blk][None, :]
+    sfb_pad = np.concatenate([sfb, np.zeros((64, K // 16), dtype=np.uint8)])
+    got = pm.run_mma_bs(pm.image_rows(pm.pack_nibbles(ac), 4), pm.image_rows(pm.pack_nibbles(bc), 4), pm.sf_atoms(sfa), pm.sf_atoms(sfb_pad), N,
+                        n_mma, pm.idesc_bs(1, 1, 128, N, 0))
+    return float(np.abs(got - ref).max() / np.abs(ref).max())
+
+
+@case
+def nvf4_blockscaled_n64_upper_half():
+    """N = 64 on keys 64..127 of a 128-key tile: B's scales are columns 2, 3 of the tile's 128-row atom (TMEM address + 2)."""
+    rng = np.random.default_rng(13)
+    n_mma, N = 2, 64
+    K = 64 * n_mma
+    ac, bc = rng.integers(0, 16, (128, K)), rng.integers(0, 16, (128, K))
+    sfa = rng.integers(0x28, 0x48, (128, K // 16)).astype(np.uint8)
+    sfb = rng.integers(0x28, 0x48, (128, K // 16)).astype(np.uint8)
+    A, B = pm.E2M1[ac].astype(np.float64), pm.E2M1[bc[64:]].astype(np.float64)
+    f = lambda b: torch.from_numpy(b.copy()).view(torch.float8_e4m3fn).float().numpy().astype(np.float64)
+    fa, fb = f(sfa), f(sfb[64:])
+    ref = np.zeros((128, N))
+    for blk in range(K // 16):
+        sl = slice(16 * blk, 16 * blk + 16)
+        ref += (A[:, sl] @ B[:, sl].T) * fa[:, blk:blk + 1] * fb[:, blk][None, :]
+    got = pm.run_mma_bs(pm.image_rows(pm.pack_nibbles(ac), 4), pm.image_rows(pm.pack_nibbles(bc[64:]), 4), pm.sf_atoms(sfa), pm.sf_atoms(sfb), N,
+                        n_mma, pm.idesc_bs(1, 1, 128, N, 0), sfb_col_offset=2)
+    return float(np.abs(got - ref).max() / np.abs(ref).max())
+
+
+@case
 def nvf4_blockscaled_ss_sw64():
     return _nvf4(False)
 

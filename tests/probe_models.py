@@ -87,13 +87,13 @@ def sf_atoms(sf):
 
 
 def run_mma_bs(a_img, b_img, sfa_img, sfb_img, n_cols, n_mma, idesc_v, *, kind=0, a_in_tmem=0, a_tmem_cols=0, a_kcols=8, lay=4,
-               sbo=512, kstep=32):
+               sbo=512, kstep=32, sfb_col_offset=0):
     L = _lib.dev_lib()
     g = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).reshape(-1)).cuda()
     a, b, fa, fb = g(a_img), g(b_img), g(sfa_img), g(sfb_img)
     d = torch.zeros((128, n_cols), dtype=torch.float32, device="cuda")
     rc = L.qa_probe_mma_bs(_lib.ptr(a), a.numel(), _lib.ptr(b), b.numel(), _lib.ptr(fa), fa.numel(), _lib.ptr(fb), fb.numel(),
-                           _lib.ptr(d), 16, sbo, lay, kstep, 16, sbo, lay, kstep, ctypes.c_uint(idesc_v), kind, n_mma, n_cols, 4, 4,
+                           _lib.ptr(d), 16, sbo, lay, kstep, 16, sbo, lay, kstep, ctypes.c_uint(idesc_v), kind, n_mma, n_cols, 4, 4 | (sfb_col_offset << 8),
                            a_in_tmem, a_tmem_cols, a_kcols, _lib.cur_stream())
     _lib.check(rc, "qa_probe_mma_bs", L)
     torch.cuda.synchronize()

@@ -42,16 +42,17 @@ def test_fp4_quantisation_is_bit_exact(shape, kind):
         assert torch.equal(getattr(o, name).cpu(), ref[name]), name
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((1, 4, 1024, 128), "randn"), ((2, 2, 512, 128), "offset"),
                                         ((1, 2, 384, 128), "zeros")])
-def test_fp4_fwd_matches_definition_and_fp32_math(shape, kind):
+def test_fp4_fwd_matches_definition_and_fp32_math(shape, kind, variant):
     from oracle import fp4_ref
     from oracle.baseline import baseline_pytorch_attention
     from quantizedattention_b200 import attention_fp4 as F
     q, k, v = _inputs(shape, 500 + shape[2], kind)
-    O, lse = F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()))
+    O, lse = F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()), variant=variant)
     torch.cuda.synchronize()
-    Oref, lse_ref, _ = fp4_ref.fp4_fwd(q, k, v)
+    Oref, lse_ref, _ = fp4_ref.fp4_fwd(q, k, v, step=64 if variant == 0 else 128)
     fin = torch.isfinite(Oref.float())
     assert torch.isfinite(O.float().cpu()[fin]).all()
     mx, cos = _stats(O.cpu()[fin], Oref[fin])
