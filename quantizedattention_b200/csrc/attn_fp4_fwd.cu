@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t fp4_pack8(const float2 (&y)[4]) {
 }
 
 template <int STAGES>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(640, 1)
 fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_vt, const __grid_constant__ CUtensorMap tm_sfq,
                const __grid_constant__ CUtensorMap tm_sfk, const __grid_constant__ CUtensorMap tm_sfv, Fp4FwdParams p) {
@@ -77,12 +77,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   constexpr int D = kFp4D;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full[2], p_full[2], o_full[2];
-  __shared__ uint64_t sc_full[2], sc_empty[2], o_ready[2];     // softmax -> correction (rescale factors), correction -> MMA
-  __shared__ float row_sc[2][128];
+  __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full[2], p_full[2], o_full[2], o_ready[2], fin_full;
+  __shared__ uint64_t mx_full[8][4];          // [tile & 7][row group]: running maximum and rescale factor of the tile are published
+  __shared__ float2 prm[8][128];              // (m', 2^(m - m')) per row; a slot is rewritten eight tiles later
+  __shared__ float l_part[2][128];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float xmax[2][2][128];            // [tile parity][column half][row]: raw row maxima exchanged inside a row group
-  __shared__ float xl[2][128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * 128;
@@ -91,115 +90,127 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (tid == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&o_full[b], 1);
-      mbar_init(&sc_full[b], 4); mbar_init(&sc_empty[b], 4); mbar_init(&o_ready[b], 4);
-    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_ready[b], 4); }
+    for (int r = 0; r < 8; ++r)
+      for (int qd = 0; qd < 4; ++qd) mbar_init(&mx_full[r][qd], 1);
+    mbar_init(&fin_full, 8);
     fence_mbar_init();
   }
-  if (warp == 13) tmem_alloc<512>(&tmem_base_s);
+  if (warp == 17) tmem_alloc<512>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
   constexpr uint32_t kSfQ = 384, kSfK = 392, kSfV = 408, kSfP = 424;     // TMEM columns of the scale factors
+  const int qd = warp & 3;                                        // TMEM lane quadrant of this warp
+  const int row = qd * 32 + lane;
+  const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
 
   if (warp < 8) {
-    // =========================== softmax warps: two per 32-row group, 64 of the tile's 128 keys each ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");           // whole warpgroups: 8 x 168 + 8 x 88 registers per lane = 2048
-    const int qd = warp & 3, hf = warp >> 2;                      // TMEM lane quadrant (= warp % 4), column half
-    const int row = qd * 32 + lane;
-    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
-    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;           // accumulator -> log2-domain logit (c >= 0)
+    // =========================== exp warps: exp2 + microscaling, the XU-bound stage ===========================
+    // The two exp warps of a 32-row group are DE-PHASED: warp e handles the tiles j = e (mod 2), all 128 keys, so that one of
+    // them is in its XU-bound inner loop (MUFU.EX2, F2FP) while the other waits, loads or hands P over.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");           // 8 x 136 + 4 x 88 + 4 x 80 + 4 x 40 = 1920 = 20 x 96
+    const int e = warp >> 2;
+    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;
     const float2 c2 = make_float2(c, c);
-    float m = -INFINITY, l = 0.f;
-    uint32_t r[64];                                               // this thread's 64 raw logits of the current tile
-    mbar_wait(&s_full[0], 0);
-    tc_fence_after();
-    tmem_ld64(lane_addr + hf * 64, r);
-    for (int j = 0; j < nk; ++j) {
+    float l = 0.f;
+    for (int j = e; j < nk; j += 2) {
       const int sb = j & 1;
-      tmem_ld_wait();                                             // issued during the previous tile's quantise phase
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < 64; i += 8)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(r[i + 2 * a]), __uint_as_float(r[i + 2 * a + 1])));
-      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      xmax[sb][hf][row] = mx;
-      named_bar_sync(1 + qd, 64);                                 // the two warps of the row group: both have read their S columns
-      mx = fmaxf(mx, xmax[sb][hf ^ 1][row]);
-      const float m_new = fmaxf(m, mx * c);
-      const float resc = ex2_approx(m - m_new);                     // 0 on the first tile (m = -inf)
-      m = m_new;
-      if (j > 0 && hf == 0) {                                      // O *= 2^(m - m') is the correction warps' job: publish the factor
-        const int k = j - 1, sl = k & 1;
-        mbar_wait(&sc_empty[sl], ((k >> 1) & 1) ^ 1);
-        row_sc[sl][row] = resc;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sc_full[sl]);
-      }
-      // ---- P = exp2(S c - m'), microscaled per 16 keys: sfp = e4m3(amax * 448), P4 = e2m1(P * 2688 / sfp)
-      const float2 nm2 = make_float2(-m_new, -m_new);
+      mbar_wait(&mx_full[j & 7][qd], (j >> 3) & 1);
+      tc_fence_after();
+      const float2 pr = prm[j & 7][row];
+      float resc = pr.y;
+      if (j >= 2) resc *= prm[(j - 1) & 7][row].y;                 // the tile the other exp warp of this row group handled
+      const float2 nm2 = make_float2(-pr.x, -pr.x);
       float2 ls2 = make_float2(0.f, 0.f);
-      float2 pe[32];
-      float am[4];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        float a0 = 0.f, a1 = 0.f;
+      for (int hf = 0; hf < 2; ++hf) {                             // 64 keys (one K step of P V) at a time
+        uint32_t r[64];
+        tmem_ld64(lane_addr + sb * 128 + hf * 64, r);
+        tmem_ld_wait();
+        uint32_t pw[8], sfw = 0u;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[b * 16 + 2 * e]), __uint_as_float(r[b * 16 + 2 * e + 1])), c2, nm2);
-          pe[b * 8 + e] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
-          if (e & 1) a1 = fmaxf(a1, fmaxf(pe[b * 8 + e].x, pe[b * 8 + e].y)); else a0 = fmaxf(a0, fmaxf(pe[b * 8 + e].x, pe[b * 8 + e].y));
-          ls2 = __fadd2_rn(ls2, pe[b * 8 + e]);
+        for (int b = 0; b < 4; ++b) {
+          float2 pe[8];
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[b * 16 + 2 * i]), __uint_as_float(r[b * 16 + 2 * i + 1])), c2, nm2);
+            pe[i] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            if (i & 1) a1 = fmaxf(a1, fmaxf(pe[i].x, pe[i].y)); else a0 = fmaxf(a0, fmaxf(pe[i].x, pe[i].y));
+            ls2 = __fadd2_rn(ls2, pe[i]);
+          }
+          const uint32_t sc = (uint32_t)__nv_cvt_float_to_fp8(fmaxf(a0, a1) * 448.0f, __NV_SATFINITE, __NV_E4M3);
+          const float sf = fp4_e4m3_to_float(sc);
+          const float inv = sf > 0.f ? __fdividef(2688.0f, sf) : 0.f;
+          const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            float2 y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = __fmul2_rn(pe[h8 * 4 + i], inv2);
+            pw[2 * b + h8] = fp4_pack8(y);
+          }
+          sfw |= sc << (8 * b);
         }
-        am[b] = fmaxf(a0, a1);
+        tmem_st8(lane_addr + sb * 128 + hf * 8, pw);               // P over S columns [8 hf, 8 hf + 8): this warp's logits are in registers
+        *reinterpret_cast<uint32_t*>(smem + L::off_sfp + sb * L::kSf + hf * 512 + 16 * lane + 4 * qd) = sfw;
       }
       l = l * resc + (ls2.x + ls2.y);
-      if (j + 1 < nk) {                                            // the raw logits are consumed: fetch the next tile's behind the quantise phase
-        mbar_wait(&s_full[sb ^ 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        tmem_ld64(lane_addr + (sb ^ 1) * 128 + hf * 64, r);
-      }
-      uint32_t pw[8], sfw = 0u;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t sc = (uint32_t)__nv_cvt_float_to_fp8(am[b] * 448.0f, __NV_SATFINITE, __NV_E4M3);
-        const float sf = fp4_e4m3_to_float(sc);
-        const float inv = sf > 0.f ? __fdividef(2688.0f, sf) : 0.f;
-        const float2 inv2 = make_float2(inv, inv);
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          float2 y[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = __fmul2_rn(pe[b * 8 + h8 * 4 + i], inv2);
-          pw[2 * b + h8] = fp4_pack8(y);
-        }
-        sfw |= sc << (8 * b);
-      }
-      tmem_st8(lane_addr + sb * 128 + hf * 8, pw);                 // P over the first 16 S columns (8 keys per column): K step hf
-      // scale factors of P: this thread's 4 blocks are one 32-bit word of the K step's atom; tcgen05.cp replicates it over the lanes
-      *reinterpret_cast<uint32_t*>(smem + L::off_sfp + sb * L::kSf + hf * 512 + 16 * lane + 4 * qd) = sfw;
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
-    // ---- epilogue: O * sgv / (2688 * l), log2-LSE; each warp writes its half of the D columns
-    xl[hf][row] = l;
-    named_bar_sync(1 + qd, 64);
-    l += xl[hf ^ 1][row];
+    if (nk > 0 && ((nk - 1) & 1) != e) {                           // the last tile belonged to the other warp: its rescale
+      mbar_wait(&mx_full[(nk - 1) & 7][qd], ((nk - 1) >> 3) & 1);
+      l *= prm[(nk - 1) & 7][row].y;
+    }
+    l_part[e][row] = l;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&fin_full);
+  } else if (warp < 12) {
+    // =========================== maximum warps (thread = row): running maximum of every tile, ahead of the exp warps ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const float c = p.sgq[bh] * p.sgk[bh] * p.qk_scale;           // >= 0: the maximum commutes with the scaling
+    float m = -INFINITY;
+    for (int j = 0; j < nk; ++j) {
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t r[64];
+        tmem_ld64(lane_addr + sb * 128 + ch * 64, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 64; i += 8)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(r[i + 2 * a]), __uint_as_float(r[i + 2 * a + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float m_new = fmaxf(m, mx * c);
+      prm[j & 7][row] = make_float2(m_new, ex2_approx(m - m_new));  // rescale factor 0 on the first tile (m = -inf)
+      m = m_new;
+      tc_fence_before();                                           // the exp warps overwrite these columns with P
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mx_full[j & 7][qd]);
+    }
+    // ---- epilogue: O * sgv / (2688 * l), log2-LSE
+    mbar_wait(&fin_full, 0);
+    const float l = l_part[0][row] + l_part[1][row];
     mbar_wait(&o_full[(nk - 1) & 1], ((nk - 1) >> 1) & 1);
     tc_fence_after();
     const size_t gr = (size_t)bh * p.Sq + q0 + row;
     const float sc_o = __fdividef(p.sgv[bh], 2688.0f * l);
-    __half* dst = p.O + gr * D + hf * (D / 2);
+    __half* dst = p.O + gr * D;
 #pragma unroll
-    for (int ch = 0; ch < D / 64; ++ch) {
+    for (int ch = 0; ch < D / 32; ++ch) {
       uint32_t o[32];
-      tmem_ld32(lane_addr + 256 + hf * (D / 2) + ch * 32, o);
+      tmem_ld32(lane_addr + 256 + ch * 32, o);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
@@ -212,36 +223,28 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         *reinterpret_cast<uint4*>(dst + ch * 32 + i) = v;
       }
     }
-    if (hf == 0) p.lse[gr] = m + log2f(l);
-  } else if (warp < 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    p.lse[gr] = m + log2f(l);
+  } else if (warp < 16) {
     // =========================== correction warps (thread = row): O *= 2^(m - m') between P V(j-1) and P V(j) ===========================
-    // Off the softmax warps' critical path: they never wait for the tensor pipe; the rescale happens only when a row maximum
-    // of the warp's 32 rows moved (most early tiles, few late ones).
-    const int qd = warp & 3, row = qd * 32 + lane;
-    const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     for (int j = 1; j < nk; ++j) {
-      const int k = j - 1, sl = k & 1;
-      mbar_wait(&sc_full[sl], (k >> 1) & 1);
-      const float resc = row_sc[sl][row];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sc_empty[sl]);
-      if (__any_sync(0xffffffffu, resc != 1.0f)) {
+      mbar_wait(&mx_full[j & 7][qd], (j >> 3) & 1);
+      const float resc = prm[j & 7][row].y;
+      if (__any_sync(0xffffffffu, resc != 1.0f)) {                 // only when a row maximum of the warp's 32 rows moved
         mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);       // P V of tile j-1 has landed in TMEM
         tc_fence_after();
         const float2 rs2 = make_float2(resc, resc);
 #pragma unroll
-        for (int ch = 0; ch < D / 64; ++ch) {
-          uint32_t o[64];
-          tmem_ld64(lane_addr + 256 + ch * 64, o);
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(lane_addr + 256 + ch * 32, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 64; i += 2) {
+          for (int i = 0; i < 32; i += 2) {
             const float2 t = __fmul2_rn(make_float2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), rs2);
             o[i] = __float_as_uint(t.x); o[i + 1] = __float_as_uint(t.y);
           }
-          tmem_st32(lane_addr + 256 + ch * 64, *reinterpret_cast<uint32_t (*)[32]>(&o[0]));
-          tmem_st32(lane_addr + 256 + ch * 64 + 32, *reinterpret_cast<uint32_t (*)[32]>(&o[32]));
+          tmem_st32(lane_addr + 256 + ch * 32, o);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -250,74 +253,88 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       if (lane == 0) mbar_arrive(&o_ready[j & 1]);
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");            // warps 12-15 (14, 15 idle): one instruction for the warpgroup
-    if (warp == 12) {
-    // =========================== TMA producer ===========================
-    if (elect_one()) {
-      tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt);
-      mbar_expect_tx(&q_full, L::kTile + L::kSf);
-      tma_load_2d(smem + L::off_q, &tm_q, &q_full, 0, bh * p.Sq + q0);
-      tma_load_2d(smem + L::off_sfq, &tm_sfq, &q_full, 0, (bh * p.Sq + q0) / 128);
-      for (int j = 0; j < nk; ++j) {
-        const int s = j % STAGES;
-        mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * L::kTile + 2 * L::kSf);
-        tma_load_2d(smem + L::off_k + s * L::kTile, &tm_k, &kv_full[s], 0, bh * p.Sk + j * 128);
-        tma_load_2d(smem + L::off_sfk + s * L::kSf, &tm_sfk, &kv_full[s], 0, bh * (p.Sk / 128) + j);
-        tma_load_2d(smem + L::off_v + s * L::kTile, &tm_vt, &kv_full[s], j * 64, bh * D);
-        tma_load_2d(smem + L::off_sfv + s * L::kSf, &tm_sfv, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");            // warps 16-19 (18, 19 idle): one instruction for the warpgroup
+    if (warp == 16) {
+      // =========================== TMA producer ===========================
+      if (elect_one()) {
+        tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_vt);
+        mbar_expect_tx(&q_full, L::kTile + L::kSf);
+        tma_load_2d(smem + L::off_q, &tm_q, &q_full, 0, bh * p.Sq + q0);
+        tma_load_2d(smem + L::off_sfq, &tm_sfq, &q_full, 0, (bh * p.Sq + q0) / 128);
+        for (int j = 0; j < nk; ++j) {
+          const int s = j % STAGES;
+          mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * L::kTile + 2 * L::kSf);
+          tma_load_2d(smem + L::off_k + s * L::kTile, &tm_k, &kv_full[s], 0, bh * p.Sk + j * 128);
+          tma_load_2d(smem + L::off_sfk + s * L::kSf, &tm_sfk, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+          tma_load_2d(smem + L::off_v + s * L::kTile, &tm_vt, &kv_full[s], j * 64, bh * D);
+          tma_load_2d(smem + L::off_sfv + s * L::kSf, &tm_sfv, &kv_full[s], 0, bh * (p.Sk / 128) + j);
+        }
       }
-    }
-  } else if (warp == 13) {
-    // =========================== MMA issuer ===========================
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // e2m1 x e2m1, K-major, ue4m3 scales, N = 128 (keys / D)
-      const uint32_t q_addr = smem_u32(smem + L::off_q);
-      auto issue_s = [&](int j) {                                                  // S[j & 1] = Q K_j^T
-        const int s = j % STAGES, sb = j & 1;
-        mbar_wait(&kv_full[s], (j / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile), sfk = smem_u32(smem + L::off_sfk + s * L::kSf);
-        tmem_cp_sf(tbase + kSfK + sb * 8, sfk);
-        tmem_cp_sf(tbase + kSfK + sb * 8 + 4, sfk + 512);
+    } else if (warp == 17) {
+      // =========================== MMA issuer ===========================
+      // A tcgen05.cp costs the issuing thread ~100 clk (tools/ubench/cp_rate.cu), as much as an MMA, so the scale factors of K
+      // (two tiles ahead) and V (one tile ahead) are staged into their double-buffered TMEM columns while the softmax works:
+      // between P(j) and the logits of tile j+2 only the two copies of P's scales and four MMAs remain.
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // e2m1 x e2m1, K-major, ue4m3 scales, N = 128 (keys / D)
+        const uint32_t q_addr = smem_u32(smem + L::off_q);
+        auto stage_sfk = [&](int j) {                                                // scale factors of K_j -> TMEM (after kv_full(j))
+          const int s = j % STAGES;
+          mbar_wait(&kv_full[s], (j / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sfk = smem_u32(smem + L::off_sfk + s * L::kSf);
+          tmem_cp_sf(tbase + kSfK + (j & 1) * 8, sfk);
+          tmem_cp_sf(tbase + kSfK + (j & 1) * 8 + 4, sfk + 512);
+        };
+        auto stage_sfv = [&](int j) {                                                // scale factors of V_j -> TMEM (kv_full(j) already seen)
+          const uint32_t sfv = smem_u32(smem + L::off_sfv + (j % STAGES) * L::kSf);
+          tmem_cp_sf(tbase + kSfV + (j & 1) * 8, sfv);
+          tmem_cp_sf(tbase + kSfV + (j & 1) * 8 + 4, sfv + 512);
+        };
+        auto issue_s = [&](int j) {                                                  // S[j & 1] = Q K_j^T
+          const int s = j % STAGES, sb = j & 1;
+          const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile);
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_nvf4_ss(tbase + sb * 128, umma_smem_desc(q_addr + k * 32, 16, 512, kSwz64), umma_smem_desc(k_addr + k * 32, 16, 512, kSwz64),
-                       idesc, tbase + kSfQ + k * 4, tbase + kSfK + sb * 8 + k * 4, k > 0);
-        umma_commit(&s_full[sb]);
-      };
-      mbar_wait(&q_full, 0);
-      tc_fence_after();
-      tmem_cp_sf(tbase + kSfQ, smem_u32(smem + L::off_sfq));
-      tmem_cp_sf(tbase + kSfQ + 4, smem_u32(smem + L::off_sfq) + 512);
-      issue_s(0);
-      for (int j = 0; j < nk; ++j) {
-        const int s = j % STAGES, sb = j & 1;
-        if (j + 1 < nk) issue_s(j + 1);           // overwrites the buffer that held P(j-1): P V(j-1) is ahead of it in the in-order pipe
-        mbar_wait(&p_full[sb], (j >> 1) & 1);     // P and its scale factors are in place
-        if (j > 0) mbar_wait(&o_ready[sb], ((j - 1) >> 1) & 1);   // ... and O carries the rescale of this tile
+          for (int k = 0; k < 2; ++k)
+            umma_nvf4_ss(tbase + sb * 128, umma_smem_desc(q_addr + k * 32, 16, 512, kSwz64), umma_smem_desc(k_addr + k * 32, 16, 512, kSwz64),
+                         idesc, tbase + kSfQ + k * 4, tbase + kSfK + sb * 8 + k * 4, k > 0);
+          umma_commit(&s_full[sb]);
+        };
+        mbar_wait(&q_full, 0);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile), sfv = smem_u32(smem + L::off_sfv + s * L::kSf);
-        const uint32_t sfp = smem_u32(smem + L::off_sfp + sb * L::kSf);
-        tmem_cp_sf(tbase + kSfP + sb * 8, sfp);
-        tmem_cp_sf(tbase + kSfP + sb * 8 + 4, sfp + 512);
-        tmem_cp_sf(tbase + kSfV + sb * 8, sfv);
-        tmem_cp_sf(tbase + kSfV + sb * 8 + 4, sfv + 512);
+        tmem_cp_sf(tbase + kSfQ, smem_u32(smem + L::off_sfq));
+        tmem_cp_sf(tbase + kSfQ + 4, smem_u32(smem + L::off_sfq) + 512);
+        stage_sfk(0);
+        issue_s(0);
+        if (nk > 1) { stage_sfk(1); issue_s(1); }
+        stage_sfv(0);
+        for (int j = 0; j < nk; ++j) {
+          const int s = j % STAGES, sb = j & 1;
+          if (j + 2 < nk) stage_sfk(j + 2);         // K scales buffer j & 1: S(j) is complete (its softmax is running)
+          if (j + 1 < nk) stage_sfv(j + 1);         // V scales buffer (j+1) & 1: P V(j-1) is ahead in the in-order pipe
+          mbar_wait(&p_full[sb], (j >> 1) & 1);     // P and its scale factors are in place
+          if (j > 0) mbar_wait(&o_ready[sb], ((j - 1) >> 1) & 1);   // ... and O carries the rescale of this tile
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(smem + L::off_v + s * L::kTile);
+          const uint32_t sfp = smem_u32(smem + L::off_sfp + sb * L::kSf);
+          tmem_cp_sf(tbase + kSfP + sb * 8, sfp);
+          tmem_cp_sf(tbase + kSfP + sb * 8 + 4, sfp + 512);
 #pragma unroll
-        for (int k = 0; k < 2; ++k)                                               // O += P_j V_j, keys 64k .. 64k + 63
-          umma_nvf4_ts(tbase + 256, tbase + sb * 128 + k * 8, umma_smem_desc(v_addr + k * 32, 16, 512, kSwz64), idesc,
-                       tbase + kSfP + sb * 8 + k * 4, tbase + kSfV + sb * 8 + k * 4, (j > 0) || (k > 0));
-        umma_commit(&o_full[sb]);
-        umma_commit(&kv_empty[s]);
+          for (int k = 0; k < 2; ++k)                                               // O += P_j V_j, keys 64k .. 64k + 63
+            umma_nvf4_ts(tbase + 256, tbase + sb * 128 + k * 8, umma_smem_desc(v_addr + k * 32, 16, 512, kSwz64), idesc,
+                         tbase + kSfP + sb * 8 + k * 4, tbase + kSfV + sb * 8 + k * 4, (j > 0) || (k > 0));
+          umma_commit(&o_full[sb]);
+          umma_commit(&kv_empty[s]);
+          if (j + 2 < nk) issue_s(j + 2);           // refills the buffer whose P was just consumed (in-order pipe)
+        }
       }
-    }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) tmem_dealloc<512>(tbase);
+  if (warp == 17) tmem_dealloc<512>(tbase);
 }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // Default variant: TWO CTAs per SM.  The one-CTA kernel above is bound by the latency chain of its softmax warps (wait for
@@ -629,6 +646,6 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   auto kern = fp4_fwd_kernel<STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  kern<<<dim3(Sq / 128, BH), 512, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+  kern<<<dim3(Sq / 128, BH), 640, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
   return qa_check_launch("qa_fp4_fwd");
 }
