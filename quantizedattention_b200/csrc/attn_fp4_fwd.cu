@@ -15,7 +15,7 @@
 // One CTA = one 128-row query tile of one head.  Warps 0-7: softmax (two per 32-row group, 64 keys of the tile each; the row
 // maxima meet through shared memory), 8-11: correction (rescale of O, off the softmax warps' critical path), 12: TMA producer,
 // 13: MMA issuer.
-// TMEM (512 columns): S[2] at 0 / 128, O at 256, scale factors from 384: Q 8, K 2 x 8, V 2 x 8, P 2 x 8 columns.
+// TMEM (512 columns): S[2] at 0 / 128, O at 256, scale factors from 384: Q 8, K 2 x 8, V 2 x 8, P 2 x 8 columns, P[2] at 440 / 456.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
 #include <cuda_fp4.h>
@@ -77,7 +77,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   constexpr int D = kFp4D;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full[2], p_full[2], o_full[2], o_ready[2], fin_full;
+  __shared__ uint64_t q_full, kv_full[STAGES], kv_empty[STAGES], s_full[2], s_free[2], p_full[2], o_full[2], o_ready[2], fin_full;
   __shared__ uint64_t mx_full[8][4];          // [tile & 7][row group]: running maximum and rescale factor of the tile are published
   __shared__ float2 prm[8][128];              // (m', 2^(m - m')) per row; a slot is rewritten eight tiles later
   __shared__ float l_part[2][128];
@@ -90,7 +90,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (tid == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_ready[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 4); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_ready[b], 4); }
     for (int r = 0; r < 8; ++r)
       for (int qd = 0; qd < 4; ++qd) mbar_init(&mx_full[r][qd], 1);
     mbar_init(&fin_full, 8);
@@ -102,6 +102,8 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
   constexpr uint32_t kSfQ = 384, kSfK = 392, kSfV = 408, kSfP = 424;     // TMEM columns of the scale factors
+  constexpr uint32_t kP = 440;                                   // P[2]: 16 columns each (128 e2m1 per row), separate from S so that an S buffer
+                                                                 // is refilled as soon as the exp warps hold its logits in registers
   const int qd = warp & 3;                                        // TMEM lane quadrant of this warp
   const int row = qd * 32 + lane;
   const uint32_t lane_addr = tbase + ((uint32_t)(qd * 32) << 16);
@@ -129,6 +131,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         uint32_t r[64];
         tmem_ld64(lane_addr + sb * 128 + hf * 64, r);
         tmem_ld_wait();
+        if (hf == 1) {                                             // both halves of the logits are in registers: S[sb] may be refilled
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[sb]);
+        }
         uint32_t pw[8], sfw = 0u;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -154,7 +161,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           }
           sfw |= sc << (8 * b);
         }
-        tmem_st8(lane_addr + sb * 128 + hf * 8, pw);               // P over S columns [8 hf, 8 hf + 8): this warp's logits are in registers
+        if (hf == 0 && j >= 2) {                                   // P[sb] and its scale-factor atom were last read by P V of tile j-2
+          mbar_wait(&o_full[sb], ((j - 2) >> 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st8(lane_addr + kP + sb * 16 + hf * 8, pw);
         *reinterpret_cast<uint32_t*>(smem + L::off_sfp + sb * L::kSf + hf * 512 + 16 * lane + 4 * qd) = sfw;
       }
       l = l * resc + (ls2.x + ls2.y);
@@ -313,6 +324,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           const int s = j % STAGES, sb = j & 1;
           if (j + 2 < nk) stage_sfk(j + 2);         // K scales buffer j & 1: S(j) is complete (its softmax is running)
           if (j + 1 < nk) stage_sfv(j + 1);         // V scales buffer (j+1) & 1: P V(j-1) is ahead in the in-order pipe
+          if (j + 2 < nk) {                         // S of tile j+2 as soon as the exp warps hold the logits of tile j: the maximum
+            mbar_wait(&s_free[sb], (j >> 1) & 1);   // warps run a whole tile ahead of the exp warps
+            tc_fence_after();
+            issue_s(j + 2);
+          }
           mbar_wait(&p_full[sb], (j >> 1) & 1);     // P and its scale factors are in place
           if (j > 0) mbar_wait(&o_ready[sb], ((j - 1) >> 1) & 1);   // ... and O carries the rescale of this tile
           tc_fence_after();
@@ -322,11 +338,10 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           tmem_cp_sf(tbase + kSfP + sb * 8 + 4, sfp + 512);
 #pragma unroll
           for (int k = 0; k < 2; ++k)                                               // O += P_j V_j, keys 64k .. 64k + 63
-            umma_nvf4_ts(tbase + 256, tbase + sb * 128 + k * 8, umma_smem_desc(v_addr + k * 32, 16, 512, kSwz64), idesc,
+            umma_nvf4_ts(tbase + 256, tbase + kP + sb * 16 + k * 8, umma_smem_desc(v_addr + k * 32, 16, 512, kSwz64), idesc,
                          tbase + kSfP + sb * 8 + k * 4, tbase + kSfV + sb * 8 + k * 4, (j > 0) || (k > 0));
           umma_commit(&o_full[sb]);
           umma_commit(&kv_empty[s]);
-          if (j + 2 < nk) issue_s(j + 2);           // refills the buffer whose P was just consumed (in-order pipe)
         }
       }
     }
