@@ -103,8 +103,8 @@ int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, 
 int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, void* sg_f32, int BH, int S, int D, void* stream);
 /* O fp16 [BH*Sq, D], lse fp32 [BH*Sq] (log2 domain); P is microscaled per row and 16 keys inside the kernel
  * (sfp = e4m3(amax * 448), code = e2m1_rn(P * 2688 / sfp)); the fp32 accumulator spans all k-tiles.
- * variant 0 (default): two CTAs per SM, 64-key steps; 1: one CTA per SM, 128-key tiles (same numerics up to the step size
- * of the online softmax). */
+ * variant 0 (default): one CTA per SM, 128-key tiles, running-maximum warps a tile ahead of two alternating exp warps per
+ * row group; 1: two CTAs per SM, 64-key steps (same numerics up to the step size of the online softmax). */
 int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq_f32, const void* k4, const void* sfk, const void* sgk_f32,
                const void* vt4, const void* sfv, const void* sgv_f32, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk, int D,
                int variant, void* stream);

@@ -85,9 +85,9 @@ def quantise_inputs(q, k, v):
             "sgq": sgq, "sgk": sgk, "sgv": sgv}
 
 
-def fp4_fwd(q, k, v, step: int = 64):
+def fp4_fwd(q, k, v, step: int = 128):
     """q, k, v fp16 [B,H,S,D] -> (O fp16 [B,H,S,D], lse fp32 [B*H, S] (log2 domain), quantised operands).
-    step: keys per online-softmax step (64: the default two-CTA kernel; 128: the one-CTA kernel)."""
+    step: keys per online-softmax step (128: the default kernel; 64: the two-CTA variant)."""
     B, H, S, D = q.shape
     G = B * H
     qi = quantise_inputs(q, k, v)

@@ -83,7 +83,7 @@ def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
 
 
 def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0):
-    """variant 0: two CTAs per SM, 64-key online-softmax steps (default); 1: one CTA per SM, 128-key tiles."""
+    """variant 0 (default): one CTA per SM, 128-key tiles, de-phased exp warps; 1: two CTAs per SM, 64-key online-softmax steps."""
     B, H, Sq, Sk, D = o.shape
     dev = o.q4.device
     O = torch.empty((B * H * Sq, D), dtype=torch.float16, device=dev)

@@ -12,9 +12,9 @@
 //                    the four TMEM lane quadrants, which a thread cannot write)
 // Because the microscales travel with the operands, the fp32 accumulator spans k-tiles (unlike the int8 / fp8 path, whose
 // per-tile P and V scales force a drain every k-tile): O stays resident in TMEM and is rescaled only when a row maximum moves.
-// One CTA = one 128-row query tile of one head.  Warps 0-7: softmax (two per 32-row group, 64 keys of the tile each; the row
-// maxima meet through shared memory), 8-11: correction (rescale of O, off the softmax warps' critical path), 12: TMA producer,
-// 13: MMA issuer.
+// One CTA = one 128-row query tile of one head.
+// One-CTA variant (variant 1), 20 warps: 0-7 exp (two per 32-row group, alternating tiles: the XU-bound stage), 8-11 running maximum
+// (a tile ahead) and epilogue, 12-15 correction (rescale of O), 16 TMA producer, 17 / 18 MMA issuers (P V / Q K^T), 19 idle.
 // TMEM (512 columns): S[2] at 0 / 128, O at 256, scale factors from 384: Q 8, K 2 x 8, V 2 x 8, P 2 x 8 columns, P[2] at 440 / 456.
 #include "qa_ptx.cuh"
 #include "qa_host.h"
@@ -89,7 +89,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }   // K side + V side
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_free[b], 4); mbar_init(&p_full[b], 4); mbar_init(&o_full[b], 1); mbar_init(&o_ready[b], 4); }
     for (int r = 0; r < 8; ++r)
       for (int qd = 0; qd < 4; ++qd) mbar_init(&mx_full[r][qd], 1);
@@ -264,7 +264,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       if (lane == 0) mbar_arrive(&o_ready[j & 1]);
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");            // warps 16-19 (18, 19 idle): one instruction for the warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");            // warps 16-19 (19 idle): one instruction for the warpgroup
     if (warp == 16) {
       // =========================== TMA producer ===========================
       if (elect_one()) {
@@ -282,53 +282,49 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           tma_load_2d(smem + L::off_sfv + s * L::kSf, &tm_sfv, &kv_full[s], 0, bh * (p.Sk / 128) + j);
         }
       }
-    } else if (warp == 17) {
-      // =========================== MMA issuer ===========================
-      // A tcgen05.cp costs the issuing thread ~100 clk (tools/ubench/cp_rate.cu), as much as an MMA, so the scale factors of K
-      // (two tiles ahead) and V (one tile ahead) are staged into their double-buffered TMEM columns while the softmax works:
-      // between P(j) and the logits of tile j+2 only the two copies of P's scales and four MMAs remain.
+    } else if (warp == 18) {
+      // =========================== MMA issuer 1: S = Q K^T ===========================
+      // Two issuing threads: the logits run ahead as far as the S buffers allow (gated only by s_free), independent of the
+      // thread below, which spends most of its time waiting for P.  A tcgen05.cp costs the issuing thread ~100 clk
+      // (tools/ubench/cp_rate.cu), as much as an MMA.
       if (elect_one()) {
-        constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // e2m1 x e2m1, K-major, ue4m3 scales, N = 128 (keys / D)
+        constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // e2m1 x e2m1, K-major, ue4m3 scales, N = 128 keys
         const uint32_t q_addr = smem_u32(smem + L::off_q);
-        auto stage_sfk = [&](int j) {                                                // scale factors of K_j -> TMEM (after kv_full(j))
-          const int s = j % STAGES;
+        mbar_wait(&q_full, 0);
+        tc_fence_after();
+        tmem_cp_sf(tbase + kSfQ, smem_u32(smem + L::off_sfq));
+        tmem_cp_sf(tbase + kSfQ + 4, smem_u32(smem + L::off_sfq) + 512);
+        for (int j = 0; j < nk; ++j) {
+          const int s = j % STAGES, sb = j & 1;
+          if (j >= 2) mbar_wait(&s_free[sb], ((j - 2) >> 1) & 1);   // the exp warps hold the logits of tile j-2 (so S(j-2) is complete too)
           mbar_wait(&kv_full[s], (j / STAGES) & 1);
           tc_fence_after();
-          const uint32_t sfk = smem_u32(smem + L::off_sfk + s * L::kSf);
-          tmem_cp_sf(tbase + kSfK + (j & 1) * 8, sfk);
-          tmem_cp_sf(tbase + kSfK + (j & 1) * 8 + 4, sfk + 512);
-        };
-        auto stage_sfv = [&](int j) {                                                // scale factors of V_j -> TMEM (kv_full(j) already seen)
-          const uint32_t sfv = smem_u32(smem + L::off_sfv + (j % STAGES) * L::kSf);
-          tmem_cp_sf(tbase + kSfV + (j & 1) * 8, sfv);
-          tmem_cp_sf(tbase + kSfV + (j & 1) * 8 + 4, sfv + 512);
-        };
-        auto issue_s = [&](int j) {                                                  // S[j & 1] = Q K_j^T
-          const int s = j % STAGES, sb = j & 1;
-          const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile);
+          const uint32_t k_addr = smem_u32(smem + L::off_k + s * L::kTile), sfk = smem_u32(smem + L::off_sfk + s * L::kSf);
+          tmem_cp_sf(tbase + kSfK + sb * 8, sfk);
+          tmem_cp_sf(tbase + kSfK + sb * 8 + 4, sfk + 512);
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_nvf4_ss(tbase + sb * 128, umma_smem_desc(q_addr + k * 32, 16, 512, kSwz64), umma_smem_desc(k_addr + k * 32, 16, 512, kSwz64),
                          idesc, tbase + kSfQ + k * 4, tbase + kSfK + sb * 8 + k * 4, k > 0);
           umma_commit(&s_full[sb]);
+          umma_commit(&kv_empty[s]);                // K side of the stage (the V side: issuer 2)
+        }
+      }
+    } else if (warp == 17) {
+      // =========================== MMA issuer 2: O += P V ===========================
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc_bs(1, 1, 0, 0, 128, 128, 0);          // N = D
+        auto stage_sfv = [&](int j) {                                                // scale factors of V_j -> TMEM, one tile ahead
+          mbar_wait(&kv_full[j % STAGES], (j / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sfv = smem_u32(smem + L::off_sfv + (j % STAGES) * L::kSf);
+          tmem_cp_sf(tbase + kSfV + (j & 1) * 8, sfv);
+          tmem_cp_sf(tbase + kSfV + (j & 1) * 8 + 4, sfv + 512);
         };
-        mbar_wait(&q_full, 0);
-        tc_fence_after();
-        tmem_cp_sf(tbase + kSfQ, smem_u32(smem + L::off_sfq));
-        tmem_cp_sf(tbase + kSfQ + 4, smem_u32(smem + L::off_sfq) + 512);
-        stage_sfk(0);
-        issue_s(0);
-        if (nk > 1) { stage_sfk(1); issue_s(1); }
         stage_sfv(0);
         for (int j = 0; j < nk; ++j) {
           const int s = j % STAGES, sb = j & 1;
-          if (j + 2 < nk) stage_sfk(j + 2);         // K scales buffer j & 1: S(j) is complete (its softmax is running)
-          if (j + 1 < nk) stage_sfv(j + 1);         // V scales buffer (j+1) & 1: P V(j-1) is ahead in the in-order pipe
-          if (j + 2 < nk) {                         // S of tile j+2 as soon as the exp warps hold the logits of tile j: the maximum
-            mbar_wait(&s_free[sb], (j >> 1) & 1);   // warps run a whole tile ahead of the exp warps
-            tc_fence_after();
-            issue_s(j + 2);
-          }
+          if (j + 1 < nk) stage_sfv(j + 1);         // buffer (j+1) & 1: P V(j-1) is ahead of it in this thread's order
           mbar_wait(&p_full[sb], (j >> 1) & 1);     // P and its scale factors are in place
           if (j > 0) mbar_wait(&o_ready[sb], ((j - 1) >> 1) & 1);   // ... and O carries the rescale of this tile
           tc_fence_after();
@@ -352,10 +348,9 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Default variant: TWO CTAs per SM.  The one-CTA kernel above is bound by the latency chain of its softmax warps (wait for
-// the logits, TMEM load, maximum, exp2, microscale, TMEM store, fences: ~2.3k clocks per 128-key tile with every unit below
-// 50 %, profiles/r02_fp4_fwd_ncu.txt), and its two warps per row group run in lock step.  Two independent CTAs on an SM
-// interleave those chains.  To fit, a CTA owns 256 TMEM columns and 64 KB of shared memory and advances in steps of 64 keys:
+// Variant 1: TWO CTAs per SM, a simpler schedule kept for comparison (1010 - 1030 TFLOPS vs 1060 of the kernel above): four
+// softmax warps (thread = row) do maximum, exp2 and microscaling in one pass; two independent CTAs on an SM interleave their
+// latency chains.  To fit, a CTA owns 256 TMEM columns and 64 KB of shared memory and advances in steps of 64 keys:
 //   TMEM: S [0,64)  P[2] [64,80)  scale factors Q [80,88) K[2] [88,104) V[2] [104,120) P[2] [120,128)  O [128,256)
 //   S = Q K_h^T is an N = 64 MMA; the scales of keys 64h.. are columns 2h, 2h + 1 of the tile's 128-row atom (probe case
 //   nvf4_blockscaled_n64_upper_half); P V is one K = 64 MMA per step.  S is single-buffered: the issuer refills it as soon as
@@ -619,7 +614,7 @@ using namespace qa;
 
 // q4, k4: [BH*S, 64] bytes (e2m1 pairs); vt4: [BH, 128, Sk/2] bytes; sf*: 512-byte atoms, 2 per 128-row tile; sg*: [BH] fp32
 // (all produced by qa_fp4_quant_rows / qa_fp4_quant_vt).  O: fp16 [BH*Sq, 128]; lse: fp32 [BH*Sq] (log2 domain).
-// variant 0: two CTAs per SM, 64-key steps (default); 1: one CTA per SM, 128-key tiles.
+// variant 0 (default): one CTA per SM, de-phased exp warps, 128-key tiles; 1: two CTAs per SM, 64-key steps.
 extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
                           const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
                           int D, int variant, void* stream) {
@@ -631,7 +626,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
     if (!ptrs[i]) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: null pointer");
     if (i != 2 && i != 5 && i != 8 && i != 10 && ((uintptr_t)ptrs[i] & 15)) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: 16-byte alignment required");
   }
-  if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: variant must be 0 (two CTAs per SM, 64-key steps) or 1 (one CTA per SM)");
+  if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: variant must be 0 (one CTA per SM, de-phased exp warps, 128-key tiles) or 1 (two CTAs per SM, 64-key steps)");
   constexpr int STAGES = 4;
   using L = Fp4FwdSmem<STAGES>;
   CUtensorMap tq, tk, tv, tsq, tsk, tsv;
@@ -650,7 +645,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   p.sgq = (const float*)sgq; p.sgk = (const float*)sgk; p.sgv = (const float*)sgv;
   p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
-  if (variant == 0) {
+  if (variant == 1) {
     using L2 = Fp4Fwd2Smem<3>;
     auto kern2 = fp4_fwd2_kernel<3>;
     cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::total);

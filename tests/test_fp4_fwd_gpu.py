@@ -52,7 +52,7 @@ def test_fp4_fwd_matches_definition_and_fp32_math(shape, kind, variant):
     q, k, v = _inputs(shape, 500 + shape[2], kind)
     O, lse = F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()), variant=variant)
     torch.cuda.synchronize()
-    Oref, lse_ref, _ = fp4_ref.fp4_fwd(q, k, v, step=64 if variant == 0 else 128)
+    Oref, lse_ref, _ = fp4_ref.fp4_fwd(q, k, v, step=128 if variant == 0 else 64)
     fin = torch.isfinite(Oref.float())
     assert torch.isfinite(O.float().cpu()[fin]).all()
     mx, cos = _stats(O.cpu()[fin], Oref[fin])

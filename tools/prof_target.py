@@ -47,6 +47,6 @@ elif which == "fp4_fwd":
     q, k, v = [torch.randn(1, 37, 8192, 128, device="cuda", dtype=torch.float16) for _ in range(3)]   # 16 waves of 148 CTAs
     o = F4.quantise_fp4(q, k, v)
     for _ in range(3):
-        F4.fp4_fwd_prequant(o)
+        F4.fp4_fwd_prequant(o, variant=int(__import__('os').environ.get('QA_FP4_VARIANT', '0')))
 torch.cuda.synchronize()
 print("ok")
