@@ -46,6 +46,32 @@ def jvp_attention(q, k, v, layout: str = "bshd"):
     return _from_bhsd(attention_jvp.jvp_attention(*[_to_bhsd(t, layout) for t in (q, k, v)]), layout)
 
 
+def sage_attention_lowp(q, k, v, precision: str = "fp4", layout: str = "bshd"):
+    """Inference-only SageAttention3-style forward in fp8 (e4m3) or NVFP4 (`precision` = "fp8" | "fp4"; fp4: D = 128) for
+    `[B,S,H,D]` (default) or `[B,H,S,D]` fp16 tensors; the result does not require grad."""
+    from . import attention_fp4, attention_fp8
+    if precision not in ("fp8", "fp4"):
+        raise ValueError('precision must be "fp8" or "fp4"')
+    fn = attention_fp4.sage_attention_3_fp4 if precision == "fp4" else attention_fp8.sage_attention_3_fp8
+    return _from_bhsd(fn(*[_to_bhsd(t, layout) for t in (q, k, v)]), layout)
+
+
+class SageAttention3LowPrecision(nn.Module):
+    """`sage_attention_lowp` as a module (inference): `SageAttention3LowPrecision("fp4")(q, k, v)`."""
+
+    def __init__(self, precision: str = "fp4", layout: str = "bshd"):
+        super().__init__()
+        if precision not in ("fp8", "fp4"):
+            raise ValueError('precision must be "fp8" or "fp4"')
+        self.precision, self.layout = precision, layout
+
+    def forward(self, q, k, v):
+        return sage_attention_lowp(q, k, v, self.precision, self.layout)
+
+    def extra_repr(self):
+        return f"precision={self.precision!r}, layout={self.layout!r}"
+
+
 class SageAttention3Int8(nn.Module):
     """Drop-in attention core: `forward(q, k, v)` -> O (fp16), SageAttention3-style int8 forward and backward."""
 

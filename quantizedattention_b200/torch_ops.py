@@ -7,6 +7,7 @@ registered backward formulas, so the attention calls survive `torch.compile(full
     qattn::sage_int8_fwd / qattn::sage_int8_bwd   ->  sage_attention_3_int8_op(q, k, v)
     qattn::flash_bf16_fwd / qattn::flash_bf16_bwd ->  flash_atten_2_bf16_op(q, k, v, causal)
     qattn::jvp_fwd                                 ->  attention_jvp_op(q, k, v, tq, tk, tv) -> (O, tO, lse)
+    qattn::sage_fp8_fwd / qattn::sage_fp4_fwd      ->  sage_attention_3_fp8_op / sage_attention_3_fp4_op(q, k, v)   (inference)
 
 Numerics are those of `attention_int8.sage_attention_3_int8` / `attention_bf16.flash_atten_2_bf16` (same kernels, the
 block sizes and rounding mode current at call time are baked in as integer arguments).
@@ -151,3 +152,36 @@ def _(q, k, v, tq, tk, tv):
 def attention_jvp_op(q: _T, k: _T, v: _T, tq: _T, tk: _T, tv: _T) -> Tuple[_T, _T, _T]:
     """The reference's JVP kernel function as a traceable operator (survives torch.compile(fullgraph=True))."""
     return jvp_fwd(q, k, v, tq, tk, tv)
+
+
+# ------------------------------------------------------------------------------------------------ fp8 / NVFP4 forwards (inference)
+@torch.library.custom_op("qattn::sage_fp8_fwd", mutates_args=())
+def sage_fp8_fwd(q: _T, k: _T, v: _T) -> _T:
+    """attention_fp8.sage_attention_3_fp8: O fp16 [B,H,S,D] through the e4m3 pipeline (no gradient)."""
+    from . import attention_fp8
+    return attention_fp8.sage_attention_3_fp8(q, k, v)
+
+
+@sage_fp8_fwd.register_fake
+def _(q, k, v):
+    return q.new_empty(q.shape, dtype=torch.float16)
+
+
+@torch.library.custom_op("qattn::sage_fp4_fwd", mutates_args=())
+def sage_fp4_fwd(q: _T, k: _T, v: _T) -> _T:
+    """attention_fp4.sage_attention_3_fp4: O fp16 [B,H,S,D] through the NVFP4 pipeline (D = 128; no gradient)."""
+    from . import attention_fp4
+    return attention_fp4.sage_attention_3_fp4(q, k, v)
+
+
+@sage_fp4_fwd.register_fake
+def _(q, k, v):
+    return q.new_empty(q.shape, dtype=torch.float16)
+
+
+def sage_attention_3_fp8_op(q_fp16: _T, k_fp16: _T, v_fp16: _T) -> _T:
+    return sage_fp8_fwd(q_fp16, k_fp16, v_fp16)
+
+
+def sage_attention_3_fp4_op(q_fp16: _T, k_fp16: _T, v_fp16: _T) -> _T:
+    return sage_fp4_fwd(q_fp16, k_fp16, v_fp16)

@@ -64,3 +64,21 @@ def test_opcheck_schemas_and_fake_kernels():
     torch.library.opcheck(T.flash_bf16_fwd, (q, k, vb, True), test_utils=tests)
     O, lse = T.flash_bf16_fwd(q, k, vb, True)
     torch.library.opcheck(T.flash_bf16_bwd, (q, k, vb, O, lse, True, dO), test_utils=tests)
+
+
+def test_lowp_ops_and_modules_match_and_compile():
+    """fp8 / NVFP4 forwards as custom ops (fullgraph-compilable, opcheck-clean) and through the layout adapters."""
+    from quantizedattention_b200 import attention_fp4, attention_fp8, modules
+    from quantizedattention_b200 import torch_ops as T
+    q, k, v, _ = _inputs((1, 2, 256, 128), 11)
+    for op, ref in ((T.sage_attention_3_fp4_op, attention_fp4.sage_attention_3_fp4), (T.sage_attention_3_fp8_op, attention_fp8.sage_attention_3_fp8)):
+        cf = torch.compile(lambda q, k, v: op(q * 1.0, k, v) * 2.0, backend="aot_eager", fullgraph=True)
+        assert torch.equal(cf(q, k, v) / 2.0, ref(q, k, v))
+    torch.library.opcheck(T.sage_fp4_fwd, (q, k, v), test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(T.sage_fp8_fwd, (q, k, v), test_utils=("test_schema", "test_faketensor"))
+    for prec, ref in (("fp4", attention_fp4.sage_attention_3_fp4), ("fp8", attention_fp8.sage_attention_3_fp8)):
+        m = modules.SageAttention3LowPrecision(prec, layout="bshd")
+        got = m(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+        assert got.shape == (1, 256, 2, 128) and torch.equal(got.transpose(1, 2), ref(q, k, v))
+    with pytest.raises(ValueError):
+        modules.sage_attention_lowp(q, k, v, precision="int3")
