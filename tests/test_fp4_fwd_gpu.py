@@ -75,3 +75,28 @@ def test_sage_attention_3_fp4_validates():
         F.sage_attention_3_fp4(q[:, :, :200], q[:, :, :200], q[:, :, :200])
     with pytest.raises(ValueError):
         F.sage_attention_3_fp4(q[..., :64].contiguous(), q[..., :64].contiguous(), q[..., :64].contiguous())
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fp4_fwd_at_baseline_sequence_length(variant):
+    """S = 8192, D = 128 (the metric's shape): every barrier phase, stage wrap and scale-factor tile of the benchmark run is
+    exercised; quantised operands bit-exact, O / lse against the definition with the bars of the small shapes."""
+    import os
+    from oracle import fp4_ref
+    from quantizedattention_b200 import attention_fp4 as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    shape = (1, 2, 8192, 128)
+    g = torch.Generator().manual_seed(8192 + variant)
+    q, k, v = [torch.randn(shape, generator=g).to(torch.float16) for _ in range(3)]
+    k = (k.float() + 0.5).to(torch.float16)
+    o = F.quantise_fp4(q.cuda(), k.cuda(), v.cuda())
+    O, lse = F.fp4_fwd_prequant(o, variant=variant)
+    O2, _ = F.fp4_fwd_prequant(o, variant=variant)
+    torch.cuda.synchronize()
+    assert torch.equal(O, O2)                                         # run-to-run bit equality
+    Oref, lse_ref, ref = fp4_ref.fp4_fwd(q, k, v, step=128 if variant == 0 else 64)
+    for name in ("q4", "k4", "vt4", "sfq", "sfk", "sfv", "sgq", "sgk", "sgv"):
+        assert torch.equal(getattr(o, name).cpu(), ref[name]), name
+    mx, cos = _stats(O.cpu(), Oref)
+    assert mx < 1e-2 and cos > 0.9995, (mx, cos)
+    assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
