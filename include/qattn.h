@@ -96,7 +96,8 @@ int qa_fp8_fwd(const void* q_e4m3, const void* k_e4m3, const void* v_e4m3, const
  * Two-level scales: sg = amax_head / 2688 (fp32 [BH]), sf = e4m3(amax_blk16 / 6 / sg), code = e2m1_rn(x / (sf * sg));
  * D = 128, S % 128 == 0.  Q, K: blocks of 16 along D, codes [BH*S, D/2] bytes (element 2i in the low nibble); V: blocks of
  * 16 KEYS, codes transposed [BH, D, S/2].  Scale factors in the tcgen05.cp atom layout: per 128-row tile and 64-element
- * K step 512 bytes, byte 16*(r%32) + 4*(r/32) + s = row r, block s.  amax_ws: [BH] fp32 scratch.  mean_fp16 (or NULL):
+ * K step 512 bytes, byte 16*(r%32) + 4*(r/32) + s = row r, block s.  amax_ws: 2*BH 32-bit words of scratch (the head amax
+ * is formed inside the one-pass kernel: atomicMax + arrival counter per head).  mean_fp16 (or NULL):
  * per-head K token mean subtracted first (one fp16 rounding), as in the int8 path. */
 int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH, int S,
                       int D, void* stream);

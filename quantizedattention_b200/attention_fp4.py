@@ -55,7 +55,7 @@ def _quant_rows(x, mean, BH, S, D):
     codes = torch.empty((BH * S, D // 2), dtype=torch.uint8, device=dev)
     sf = torch.empty((BH * S // 128, D // 64, 512), dtype=torch.uint8, device=dev)
     sg = torch.empty((BH,), dtype=torch.float32, device=dev)
-    ws = torch.empty((BH,), dtype=torch.float32, device=dev)
+    ws = torch.empty((2 * BH,), dtype=torch.float32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev), ops._timed("fp4_quant_rows"):
         _lib.check(L.qa_fp4_quant_rows(_lib.ptr(x), _lib.ptr(mean) if mean is not None else None, _lib.ptr(ws), _lib.ptr(codes),
@@ -74,7 +74,7 @@ def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
     vt4 = torch.empty((BH, D, Sk // 2), dtype=torch.uint8, device=dev)
     sfv = torch.empty((BH * Sk // 128, 2, 512), dtype=torch.uint8, device=dev)
     sgv = torch.empty((BH,), dtype=torch.float32, device=dev)
-    ws = torch.empty((BH,), dtype=torch.float32, device=dev)
+    ws = torch.empty((2 * BH,), dtype=torch.float32, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev), ops._timed("fp4_quant_vt"):
         _lib.check(L.qa_fp4_quant_vt(_lib.ptr(v), _lib.ptr(ws), _lib.ptr(vt4), _lib.ptr(sfv), _lib.ptr(sgv), BH, Sk, D,

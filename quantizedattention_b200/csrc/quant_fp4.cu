@@ -1,6 +1,9 @@
 // NVFP4 (microscaling) quantisation pre-passes of the fp4 forward (the SageAttention3 headline the
-// reference names, /root/reference/README.md:48-54, and does not ship).  HBM-bound: 2 B/elem read, 0.5 B/elem + 1/16 B/elem
-// of scales written (+ 2 B/elem for the per-head amax pass).
+// reference names, /root/reference/README.md:48-54, and does not ship).  HBM-bound: 2 B/elem read, 0.5 B/elem + 1/16 B/elem of
+// scales written, + 2 B/elem for the per-head amax pass of Q / K.  For V (and optionally Q / K) the per-head amax the two-level
+// scale needs is produced inside the same kernel: every CTA keeps its tile in shared memory / registers, publishes the tile's amax with atomicMax, counts itself in and waits until all CTAs of its head have
+// done so (CTAs are dispatched in blockIdx order and a head's CTAs are contiguous, so the earliest incomplete head is always
+// fully resident: the wait cannot deadlock), then quantises from the data it already holds.
 //
 // Two-level scaling (the NVFP4 recipe): per head  sg = amax_head / (6 * 448)  (fp32), per block of 16 elements along the
 // CONTRACTION axis  sf = e4m3_rn(amax_blk / 6 / sg)  in [0, 448],  value = e2m1_rn(x / (sf * sg))  in [-6, 6]; all
@@ -30,7 +33,8 @@ __device__ __forceinline__ uint32_t pack_e2m1x8(const float (&y)[8]) {
   return w;
 }
 
-// amax over a head of |x - mean| (fp16 rounding of the difference, as the smoothed K of the int8 path).  grid = (chunks, BH)
+// Two-pass fallback (a head with more 128-row tiles than the GPU has SMs cannot be guaranteed resident, so its CTAs must not
+// wait for each other): amax over a head of |x - mean| (fp16 rounding of the difference).  grid = (chunks, BH)
 __global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
                                                             float* __restrict__ amax, int S, int D) {
   const int bh = blockIdx.y;
@@ -60,18 +64,40 @@ __global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __rest
   }
 }
 
+// Head-wide amax inside one kernel: CTA-reduce `m`, atomicMax into amax[bh] (non-negative floats order like ints), count this
+// CTA in and spin until all `ncta` CTAs of the head have arrived.  Returns the head's amax to every thread.
+__device__ __forceinline__ float fp4_head_amax_sync(float m, float* amax, unsigned* count, int bh, unsigned ncta, float* red) {
+  if (count == nullptr) return amax[bh];                         // two-pass mode: fp4_head_amax_kernel ran before
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    atomicMax(reinterpret_cast<int*>(amax + bh), __float_as_int(m));
+    __threadfence();
+    atomicAdd(count + bh, 1u);
+    while (atomicAdd(count + bh, 0u) < ncta) __nanosleep(64);
+    __threadfence();
+    red[0] = __int_as_float(atomicMax(reinterpret_cast<int*>(amax + bh), 0));     // coherent read of the final value
+  }
+  __syncthreads();
+  return red[0];
+}
+
 // Q / K: one thread per 16-element block along D.  CTA = 128 rows x (D/16) blocks = one scale-factor tile.
 template <int D>
 __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
-                                                                      const float* __restrict__ amax, uint8_t* __restrict__ codes,
-                                                                      uint8_t* __restrict__ sf, float* __restrict__ sg_out, int S) {
+                                                                      float* __restrict__ amax, unsigned* __restrict__ count,
+                                                                      uint8_t* __restrict__ codes, uint8_t* __restrict__ sf,
+                                                                      float* __restrict__ sg_out, int S) {
   constexpr int NB = D / 16;
-  const int tile = blockIdx.x;                                   // 128-row tile over B*H*S
+  __shared__ float red[32];
+  const int tile = blockIdx.x;                                   // 128-row tile over B*H*S: the S / 128 tiles of a head are contiguous
   const int r = threadIdx.x / NB, b = threadIdx.x % NB;
   const size_t row = (size_t)tile * 128 + r;
   const int bh = (int)(row / S);
-  const float sg = __fdiv_rn(amax[bh], 2688.0f);
-  if (sg_out != nullptr && row % S == 0 && b == 0) sg_out[bh] = sg;
   const uint4* src = reinterpret_cast<const uint4*>(x + row * D + b * 16);
   float v[16];
   float am = 0.f;
@@ -86,6 +112,8 @@ __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __ha
       am = fmaxf(am, fabsf(v[hv * 8 + e]));
     }
   }
+  const float sg = __fdiv_rn(fp4_head_amax_sync(am, amax, count, bh, (unsigned)(S / 128), red), 2688.0f);
+  if (sg_out != nullptr && row % S == 0 && b == 0) sg_out[bh] = sg;
   uint8_t sc = 0;
   float scale = 0.f;
   if (sg > 0.f) {
@@ -107,19 +135,25 @@ __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __ha
 
 // V: CTA = one 128-key tile of one head, transposed through shared memory; thread = (d, block of 16 keys)
 template <int D>
-__global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restrict__ v, const float* __restrict__ amax,
-                                                           uint8_t* __restrict__ codes_t, uint8_t* __restrict__ sf,
-                                                           float* __restrict__ sg_out, int S) {
+__global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restrict__ v, float* __restrict__ amax,
+                                                           unsigned* __restrict__ count, uint8_t* __restrict__ codes_t,
+                                                           uint8_t* __restrict__ sf, float* __restrict__ sg_out, int S) {
   __shared__ __half tile[128][D + 8];                            // +8 halves: 16-byte row skew against bank conflicts
-  const int bh = blockIdx.y, j = blockIdx.x;
-  const float sg = __fdiv_rn(amax[bh], 2688.0f);
-  if (sg_out != nullptr && j == 0 && threadIdx.x == 0) sg_out[bh] = sg;
+  __shared__ float red[32];
+  const int nt = S / 128;
+  const int bh = blockIdx.x / nt, j = blockIdx.x % nt;           // 1-D grid, a head's tiles contiguous (see fp4_head_amax_sync)
   const uint4* src = reinterpret_cast<const uint4*>(v + ((size_t)bh * S + (size_t)j * 128) * D);
+  float tm = 0.f;
   for (int i = threadIdx.x; i < 128 * D / 8; i += 256) {
     const int rr = i / (D / 8), c8 = i % (D / 8);
-    *reinterpret_cast<uint4*>(&tile[rr][c8 * 8]) = __ldg(src + i);
+    const uint4 u = __ldg(src + i);
+    *reinterpret_cast<uint4*>(&tile[rr][c8 * 8]) = u;
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h2[e]); tm = fmaxf(tm, fmaxf(fabsf(f.x), fabsf(f.y))); }
   }
-  __syncthreads();
+  const float sg = __fdiv_rn(fp4_head_amax_sync(tm, amax, count, bh, (unsigned)nt, red), 2688.0f);   // (its barriers also publish the tile)
+  if (sg_out != nullptr && j == 0 && threadIdx.x == 0) sg_out[bh] = sg;
   for (int it = threadIdx.x; it < D * 8; it += 256) {
     const int b = it / D, d = it % D;                             // consecutive threads read consecutive d of one key row: no bank conflicts
     float x[16];
@@ -150,7 +184,13 @@ __global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restr
 
 using namespace qa;
 
-// x: [BH, S, D] fp16; mean: [BH, D] fp16 or NULL (K smoothing); amax_ws: [BH] fp32 scratch (overwritten);
+static int fp4_sm_count() {                                       // SMs of the current device (the residency bound of the one-pass mode)
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+// x: [BH, S, D] fp16; mean: [BH, D] fp16 or NULL (K smoothing); amax_ws: 2 * BH 32-bit words of scratch (overwritten);
 // codes: [BH*S, D/2] bytes; sf: [BH*S/128][D/64][512] bytes; sg: [BH] fp32.  D = 128, S % 128 == 0.
 extern "C" int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH,
                                  int S, int D, void* stream) {
@@ -159,17 +199,23 @@ extern "C" int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void
   if (!x_fp16 || !amax_ws || !codes || !sf || !sg_f32) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_rows: null pointer");
   if (((uintptr_t)x_fp16 | (uintptr_t)codes | (uintptr_t)sf) & 15) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_rows: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * 8, st);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
-  fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, D);
+  // Two passes for Q / K: with 1024-thread CTAs only two fit on an SM, and CTAs that wait for the rest of their head leave too few
+  // loads in flight (measured: 0.18 ms in one pass vs 0.125 ms in two at B*H = 64, S = 8192); the V kernel (256 threads, tile in
+  // shared memory) gains from the single pass (0.105 -> 0.099 ms)
+  const bool one_pass = false;
+  if (!one_pass) {
+    const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
+    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, D);
+  }
   fp4_quant_rows_kernel<128><<<(unsigned)((size_t)BH * S / 128), 1024, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16,
-                                                                              (const float*)amax_ws, (uint8_t*)codes, (uint8_t*)sf,
-                                                                              (float*)sg_f32, S);
+                                                                              (float*)amax_ws, one_pass ? (unsigned*)amax_ws + BH : nullptr,
+                                                                              (uint8_t*)codes, (uint8_t*)sf, (float*)sg_f32, S);
   return qa_check_launch("qa_fp4_quant_rows");
 }
 
-// v: [BH, S, D] fp16 -> codes_t: [BH, D, S/2] bytes (transposed), sf: [BH*S/128][2][512] bytes, sg: [BH] fp32
+// v: [BH, S, D] fp16 -> codes_t: [BH, D, S/2] bytes (transposed), sf: [BH*S/128][2][512] bytes, sg: [BH] fp32; amax_ws: 2 * BH words
 extern "C" int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, void* sg_f32, int BH, int S, int D,
                                void* stream) {
   if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_vt: D must be 128");
@@ -177,11 +223,15 @@ extern "C" int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t,
   if (!v_fp16 || !amax_ws || !codes_t || !sf || !sg_f32) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_vt: null pointer");
   if (((uintptr_t)v_fp16 | (uintptr_t)codes_t | (uintptr_t)sf) & 15) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_vt: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * 8, st);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
-  fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, D);
-  fp4_quant_vt_kernel<128><<<dim3(S / 128, BH), 256, 0, st>>>((const __half*)v_fp16, (const float*)amax_ws, (uint8_t*)codes_t,
-                                                              (uint8_t*)sf, (float*)sg_f32, S);
+  const bool one_pass = S / 128 <= fp4_sm_count();
+  if (!one_pass) {
+    const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
+    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, D);
+  }
+  fp4_quant_vt_kernel<128><<<(unsigned)((size_t)BH * (S / 128)), 256, 0, st>>>((const __half*)v_fp16, (float*)amax_ws,
+                                                                             one_pass ? (unsigned*)amax_ws + BH : nullptr, (uint8_t*)codes_t,
+                                                                             (uint8_t*)sf, (float*)sg_f32, S);
   return qa_check_launch("qa_fp4_quant_vt");
 }

@@ -25,7 +25,9 @@ def _inputs(shape, seed, kind="randn"):
     return [t.to(torch.float16) for t in (q, k, v)]
 
 
-@pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((2, 2, 512, 128), "offset"), ((1, 2, 384, 128), "zeros")])
+@pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((2, 2, 512, 128), "offset"), ((1, 2, 384, 128), "zeros"),
+                                        ((1, 3, 8192, 128), "offset"),        # V in one pass: the 64 CTAs of a head wait for each other
+                                        ((1, 1, 20480, 128), "randn")])       # 160 tiles per head > 148 SMs: V falls back to two passes
 def test_fp4_quantisation_is_bit_exact(shape, kind):
     from oracle import fp4_ref
     from quantizedattention_b200 import attention_fp4 as F

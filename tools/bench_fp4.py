@@ -26,7 +26,7 @@ def run(B=2, H=32, S=8192, D=128, variant=0):
     ops.TIMING = None
     nbytes = B * H * S * D * 2.5625
     return {"BH": B * H, "S": S, "variant": variant, "ms_kernel": ms, "TFLOPS": 4.0 * B * H * S * S * D / ms / 1e9, "quant_rows_ms": mq,
-            "quant_rows_GBs": (nbytes + B * H * S * D * 2) / mq / 1e6, "quant_vt_ms": mv, "quant_vt_GBs": (nbytes + B * H * S * D * 2) / mv / 1e6}
+            "quant_rows_GBs": (nbytes + B * H * S * D * 2) / mq / 1e6, "quant_vt_ms": mv, "quant_vt_GBs": nbytes / mv / 1e6}
 
 
 if __name__ == "__main__":
