@@ -260,21 +260,24 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc(1, 1, 1, 0, 0, 128, BN);         // bf16 x bf16 -> f32, K-major
       constexpr uint32_t idesc_pv = umma_idesc(1, 1, 1, 0, 1, 128, D);          // B MN-major
+      constexpr uint32_t idesc_pv2 = umma_idesc(1, 1, 1, 0, 1, 128, 2 * D);     // B = [V | tV]: 2 D columns
+      static_assert(L::kTile == kDAtoms * L::kKAtom, "tV must continue V's N atoms");
       const uint32_t q_addr = smem_u32(smem + L::off_q), tq_addr = q_addr + L::kTileQ;
-      const uint32_t v_addr = smem_u32(smem + L::off_v), tv_addr = v_addr + L::kTile;
+      const uint32_t v_addr = smem_u32(smem + L::off_v);           // tV follows at v_addr + L::kTile
       auto issue_pv = [&](int t) {
         const uint32_t ph = t & 1;
         mbar_wait(&v_full, ph);
         if (t > 0) mbar_wait(&o_ready, (t - 1) & 1);              // accumulators rescaled (if needed) for tile t
         mbar_wait(&p_full, ph);
         tc_fence_after();
+        // A TS-mode MMA costs ~153 clk whatever its N (profiles/r02_mma_rate.txt), and this kernel is bound by them (D = 64: 24 of
+        // them per tile).  V and tV are adjacent in shared memory with the same layout (tV = V + one tile = the next N atoms of an
+        // MN-major B operand) and O / AB are adjacent in TMEM, so [O | AB] += P [V | tV] is ONE instruction with N = 2 D.
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           const uint64_t vd = umma_smem_desc(v_addr + k * 2048, L::kKAtom, 1024, kSwz128);
-          const uint64_t tvd = umma_smem_desc(tv_addr + k * 2048, L::kKAtom, 1024, kSwz128);
-          umma_f16_ts(tbase + 256, tbase + kPCol + k * 8, vd, idesc_pv, (t > 0) || (k > 0));       // O  += P V
-          umma_f16_ts(tbase + 256 + D, tbase + kPCol + k * 8, tvd, idesc_pv, (t > 0) || (k > 0));  // AB += P tV
-          umma_f16_ts(tbase + 256 + D, tbase + kHCol + k * 8, vd, idesc_pv, 1);                    //     + H V
+          umma_f16_ts(tbase + 256, tbase + kPCol + k * 8, vd, idesc_pv2, (t > 0) || (k > 0));      // [O | AB] += P [V | tV]
+          umma_f16_ts(tbase + 256 + D, tbase + kHCol + k * 8, vd, idesc_pv, 1);                    //  AB      += H V
         }
         umma_commit(&o_full);
         umma_commit(&v_empty);
