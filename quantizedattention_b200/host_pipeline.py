@@ -21,7 +21,7 @@ from . import attention_int8 as A
 class HostStagedSageAttention:
     """Reusable pipeline object (device staging buffers and streams are allocated once per shape)."""
 
-    def __init__(self, device=None, heads_per_chunk: int = 32, slots: int = 3):
+    def __init__(self, device=None, heads_per_chunk: int = 8, slots: int = 3):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.heads_per_chunk = heads_per_chunk
         self.slots = max(2, slots)                                 # device staging slots for the inputs
@@ -47,9 +47,13 @@ class HostStagedSageAttention:
         dev = self.device
         n_in = 4 if with_grad else 3
         self.hc = hc
-        # chunk schedule: the first H2D and the last D2H cannot overlap anything, so the edge chunks are small
-        # (hc/4, 3hc/4, hc, ..., hc, 3hc/4, hc/4) when there are enough heads for that
-        if hc % 4 == 0 and BH >= 4 * hc:
+        # chunk schedule: the first H2D and the last D2H cannot overlap anything, and the D2H lane runs one chunk (+ its compute)
+        # behind the H2D lane, so the edge chunks taper geometrically (hc/8, hc/8, hc/4, hc/2, hc, ..., hc, hc/2, hc/4, hc/8, hc/8)
+        # when there are enough heads for that: the un-overlapped head and tail of a step shrink to the copies of hc/8 heads
+        if hc % 8 == 0 and BH >= 4 * hc:
+            up = [hc // 8, hc // 8, hc // 4, hc // 2]
+            sizes = up + [hc] * (BH // hc - 2) + up[::-1]
+        elif hc % 4 == 0 and BH >= 4 * hc:
             sizes = [hc // 4, 3 * hc // 4] + [hc] * (BH // hc - 2) + [3 * hc // 4, hc // 4]
         else:
             sizes = [hc] * (BH // hc)
@@ -161,7 +165,7 @@ class HostStagedSageAttention:
 _DEFAULT = {}
 
 
-def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 32, device=None):
+def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 8, device=None):
     """Functional form of HostStagedSageAttention (one cached pipeline per device and chunk size).
     Returns O, or (O, dq, dk, dv) when dO is given; the copies are asynchronous on the current stream's timeline:
     synchronise (or record an event) before reading the host results."""
