@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--cpu-heads", type=int, default=96, help="heads in the cpu_baseline sample of our arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-heads-per-chunk", type=int, default=16, help="head chunk of the host-staged pipeline (e2e); 8 / 16 / 32 measured inside this script: 601 / 616 / 585 TOPS")
     ap.add_argument("--no-ring", action="store_true", help="skip the configs[4] ring-KV record at N > 1")
     ap.add_argument("--no-other-paths", action="store_true", help="skip the kernel-level records of the other configs at N = 1")
     args = ap.parse_args()
@@ -453,7 +454,7 @@ def main():
         outs_host = [torch.empty(B, H, S, D, dtype=torch.float16).pin_memory() for _ in range(4)]
 
         from quantizedattention_b200.host_pipeline import HostStagedSageAttention
-        pipe = HostStagedSageAttention(dev, heads_per_chunk=8, slots=3)       # 8 heads per chunk, tapered edges: 46.8 ms vs 54.2 (32, untapered)
+        pipe = HostStagedSageAttention(dev, heads_per_chunk=args.e2e_heads_per_chunk, slots=3)       # 8 heads per chunk, tapered edges: 46.8 ms vs 54.2 (32, untapered)
 
         def step_e2e():                                             # H2D / forward+backward / D2H pipelined over head chunks
             pipe(host[0], host[1], host[2], host[3], out=outs_host)

@@ -21,7 +21,7 @@ from . import attention_int8 as A
 class HostStagedSageAttention:
     """Reusable pipeline object (device staging buffers and streams are allocated once per shape)."""
 
-    def __init__(self, device=None, heads_per_chunk: int = 8, slots: int = 3):
+    def __init__(self, device=None, heads_per_chunk: int = 16, slots: int = 3):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.heads_per_chunk = heads_per_chunk
         self.slots = max(2, slots)                                 # device staging slots for the inputs
@@ -165,7 +165,7 @@ class HostStagedSageAttention:
 _DEFAULT = {}
 
 
-def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 8, device=None):
+def sage_attention_3_int8_host(q, k, v, dO=None, out=None, heads_per_chunk: int = 16, device=None):
     """Functional form of HostStagedSageAttention (one cached pipeline per device and chunk size).
     Returns O, or (O, dq, dk, dv) when dO is given; the copies are asynchronous on the current stream's timeline:
     synchronise (or record an event) before reading the host results."""
