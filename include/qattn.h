@@ -105,10 +105,12 @@ int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, 
 /* O fp16 [BH*Sq, D], lse fp32 [BH*Sq] (log2 domain); P is microscaled per row and 16 keys inside the kernel
  * (sfp = e4m3(amax * 448), code = e2m1_rn(P * 2688 / sfp)); the fp32 accumulator spans all k-tiles.
  * variant 0 (default): one CTA per SM, 128-key tiles, running-maximum warps a tile ahead of two alternating exp warps per
- * row group; 1: two CTAs per SM, 64-key steps (same numerics up to the step size of the online softmax). */
+ * row group; 1: two CTAs per SM, 64-key steps (same numerics up to the step size of the online softmax).
+ * flags: QA_FLAG_CAUSAL (variant 0, Sq == Sk) = the strict mask of the reference's baseline, as on the int8 path: key < query,
+ * row 0 of a head = uniform average over all keys of the de-quantised V, lse = -128 + log2(S). */
 int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq_f32, const void* k4, const void* sfk, const void* sgk_f32,
                const void* vt4, const void* sfv, const void* sgv_f32, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk, int D,
-               int variant, void* stream);
+               int variant, int flags, void* stream);
 
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;

@@ -85,9 +85,11 @@ def quantise_inputs(q, k, v):
             "sgq": sgq, "sgk": sgk, "sgv": sgv}
 
 
-def fp4_fwd(q, k, v, step: int = 128):
+def fp4_fwd(q, k, v, step: int = 128, causal: bool = False):
     """q, k, v fp16 [B,H,S,D] -> (O fp16 [B,H,S,D], lse fp32 [B*H, S] (log2 domain), quantised operands).
-    step: keys per online-softmax step (128: the default kernel; 64: the two-CTA variant)."""
+    step: keys per online-softmax step (128: the default kernel; 64: the two-CTA variant).  causal: the STRICT mask of the
+    reference's baseline (key < query, attention_int8.py:465-473); row 0 of a head = average of the de-quantised V over all keys,
+    lse = -128 + log2 S (the int8 path's convention)."""
     B, H, S, D = q.shape
     G = B * H
     qi = quantise_inputs(q, k, v)
@@ -100,9 +102,15 @@ def fp4_fwd(q, k, v, step: int = 128):
     for j in range(S // step):
         ks = slice(j * step, (j + 1) * step)
         u = torch.matmul(qd, kd[:, ks].transpose(1, 2)) * c
+        if causal:
+            keep = (torch.arange(j * step, (j + 1) * step)[None, :] < torch.arange(S)[:, None])[None]
+            u = torch.where(keep, u, torch.full_like(u, float("-inf")))
         m_new = torch.max(m, u.amax(-1, keepdim=True))
         P = torch.exp2(u - m_new)
         resc = torch.exp2(m - m_new)
+        if causal:
+            P = torch.where(keep, P, torch.zeros_like(P))                      # (row 0: (-inf) - (-inf))
+            resc = torch.where(torch.isinf(m_new), torch.ones_like(resc), resc)
         l = l * resc + P.sum(-1, keepdim=True)
         Pb = P.reshape(G, S, step // 16, 16)
         sfp_v, _ = e4m3_rn(Pb.amax(-1) * 448.0)
@@ -113,4 +121,7 @@ def fp4_fwd(q, k, v, step: int = 128):
         m = m_new
     out = O * (qi["sgv"].view(G, 1, 1) / 2688.0) / l
     lse = (m + torch.log2(l)).reshape(G, S)
+    if causal:
+        out[:, 0] = qi["vd"].mean(dim=1)
+        lse[:, 0] = -128.0 + math.log2(S)
     return out.to(torch.float16).reshape(B, H, S, D), lse, qi

@@ -1,7 +1,7 @@
 """NVFP4 (microscaling) SageAttention3-style forward - the feature the reference's README names as the
 SageAttention3 headline but does not implement (README.md:48-54):
 
-  sage_attention_3_fp4(q, k, v) -> O fp16 [B,H,S,D]                    forward only (inference)
+  sage_attention_3_fp4(q, k, v, causal=False) -> O fp16 [B,H,S,D]      forward only (inference)
   quantise_fp4(q, k, v)         -> Fp4Operands (codes, scale-factor atoms, per-head scales, k_mean)
   fp4_fwd_prequant(ops)         -> (O fp16 [B,H,S,D], lse fp32 [B*H, S], log2 domain)
 
@@ -82,7 +82,7 @@ def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
     return Fp4Operands(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, k_mean, (B, H, Sq, Sk, D))
 
 
-def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0):
+def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0, causal: bool = False):
     """variant 0 (default): one CTA per SM, 128-key tiles, de-phased exp warps; 1: two CTAs per SM, 64-key online-softmax steps."""
     B, H, Sq, Sk, D = o.shape
     dev = o.q4.device
@@ -92,12 +92,13 @@ def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0):
     with torch.cuda.device(dev), ops._timed("fp4_fwd"):
         _lib.check(L.qa_fp4_fwd(_lib.ptr(o.q4), _lib.ptr(o.sfq), _lib.ptr(o.sgq), _lib.ptr(o.k4), _lib.ptr(o.sfk), _lib.ptr(o.sgk),
                                 _lib.ptr(o.vt4), _lib.ptr(o.sfv), _lib.ptr(o.sgv), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, D,
-                                int(variant), _lib.cur_stream()), "qa_fp4_fwd")
+                                int(variant), 2 if causal else 0, _lib.cur_stream()), "qa_fp4_fwd")
     return O.view(B, H, Sq, D), lse.view(B * H, Sq)
 
 
-def sage_attention_3_fp4(q_fp16, k_fp16, v_fp16):
+def sage_attention_3_fp4(q_fp16, k_fp16, v_fp16, causal: bool = False):
     """O = softmax(q k^T / sqrt(d)) v through the NVFP4 pipeline, K smoothed with its per-head token mean.  Forward only:
-    the result does not require grad."""
+    the result does not require grad.  causal=True is the STRICT mask of the reference's baseline (key < query; row 0 of a
+    head = average over all keys), exactly as attention_int8.sage_attention_3_int8(causal=True)."""
     with torch.no_grad():
-        return fp4_fwd_prequant(quantise_fp4(q_fp16, k_fp16, v_fp16))[0]
+        return fp4_fwd_prequant(quantise_fp4(q_fp16, k_fp16, v_fp16), causal=causal)[0]

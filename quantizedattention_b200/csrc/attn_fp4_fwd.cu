@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t fp4_pack8(const float2 (&y)[4]) {
   return w;
 }
 
-template <int STAGES>
+template <int STAGES, bool CAUSAL>
 __global__ void __launch_bounds__(640, 1)
 fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_vt, const __grid_constant__ CUtensorMap tm_sfq,
@@ -84,8 +84,12 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y, q0 = blockIdx.x * 128;
-  const int nk = p.Sk / 128;
+  // CAUSAL: the strict mask of the reference's baseline (key < query, attention_int8.py:465-473), as on the int8 path: a query
+  // tile meets the k-tiles up to its own (heaviest tiles first); row 0 of a head sees no key and is written by fp4_row0_fixup_kernel
+  // (causal grid = (heads, query tiles): all heads' heaviest tiles are dispatched first)
+  const int bh = CAUSAL ? blockIdx.x : blockIdx.y, q0 = (CAUSAL ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.x) * 128;
+  const int nk = CAUSAL ? min(p.Sk / 128, q0 / 128 + 1) : p.Sk / 128;
+  const int jd = q0 / 128;                                       // CAUSAL: the diagonal k-tile (local column < local row is visible)
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
@@ -145,6 +149,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           for (int i = 0; i < 8; ++i) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(r[b * 16 + 2 * i]), __uint_as_float(r[b * 16 + 2 * i + 1])), c2, nm2);
             pe[i] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+            if (CAUSAL && j == jd) {                               // diagonal tile: keep key < query
+              const int col = hf * 64 + b * 16 + 2 * i;
+              if (col >= row) pe[i].x = 0.f;
+              if (col + 1 >= row) pe[i].y = 0.f;
+            }
             if (i & 1) a1 = fmaxf(a1, fmaxf(pe[i].x, pe[i].y)); else a0 = fmaxf(a0, fmaxf(pe[i].x, pe[i].y));
             ls2 = __fadd2_rn(ls2, pe[i]);
           }
@@ -197,14 +206,20 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         uint32_t r[64];
         tmem_ld64(lane_addr + sb * 128 + ch * 64, r);
         tmem_ld_wait();
+        if (CAUSAL && j == jd) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (ch * 64 + i >= row) r[i] = 0xff800000u;             // masked logit: -inf
+        }
 #pragma unroll
         for (int i = 0; i < 64; i += 8)
 #pragma unroll
           for (int a = 0; a < 4; ++a) mx4[a] = fmaxf(mx4[a], fmaxf(__uint_as_float(r[i + 2 * a]), __uint_as_float(r[i + 2 * a + 1])));
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m, mx * c);
-      prm[j & 7][row] = make_float2(m_new, ex2_approx(m - m_new));  // rescale factor 0 on the first tile (m = -inf)
+      const float m_new = fmaxf(m, (CAUSAL && mx == -INFINITY) ? -INFINITY : mx * c);   // (a row without a visible key: -inf * 0 would be NaN)
+      // rescale factor: 0 on the first tile (m = -inf); 1 while a causal row has not seen any key yet ((-inf) - (-inf))
+      prm[j & 7][row] = make_float2(m_new, (CAUSAL && m_new == -INFINITY) ? 1.0f : ex2_approx(m - m_new));
       m = m_new;
       tc_fence_before();                                           // the exp warps overwrite these columns with P
       __syncwarp();
@@ -218,6 +233,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const size_t gr = (size_t)bh * p.Sq + q0 + row;
     const float sc_o = __fdividef(p.sgv[bh], 2688.0f * l);
     __half* dst = p.O + gr * D;
+    const bool row0 = CAUSAL && q0 + row == 0;                     // no visible key (l = 0): written by fp4_row0_fixup_kernel
 #pragma unroll
     for (int ch = 0; ch < D / 32; ++ch) {
       uint32_t o[32];
@@ -231,10 +247,10 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         t = __floats2half2_rn(__uint_as_float(o[i + 2]) * sc_o, __uint_as_float(o[i + 3]) * sc_o); v.y = *reinterpret_cast<uint32_t*>(&t);
         t = __floats2half2_rn(__uint_as_float(o[i + 4]) * sc_o, __uint_as_float(o[i + 5]) * sc_o); v.z = *reinterpret_cast<uint32_t*>(&t);
         t = __floats2half2_rn(__uint_as_float(o[i + 6]) * sc_o, __uint_as_float(o[i + 7]) * sc_o); v.w = *reinterpret_cast<uint32_t*>(&t);
-        *reinterpret_cast<uint4*>(dst + ch * 32 + i) = v;
+        if (!row0) *reinterpret_cast<uint4*>(dst + ch * 32 + i) = v;
       }
     }
-    p.lse[gr] = m + log2f(l);
+    if (!row0) p.lse[gr] = m + log2f(l);
   } else if (warp < 16) {
     // =========================== correction warps (thread = row): O *= 2^(m - m') between P V(j-1) and P V(j) ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
@@ -345,6 +361,37 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 17) tmem_dealloc<512>(tbase);
+}
+
+// Causal row 0 of every head sees no key: the reference's baseline (finite fill value) makes it the uniform average over ALL keys
+// of V, here of the de-quantised V (as int8_row0_fixup_kernel); lse = -128 + log2(S).  grid = BH, thread = output column d.
+__global__ void __launch_bounds__(128) fp4_row0_fixup_kernel(const uint8_t* __restrict__ vt4, const uint8_t* __restrict__ sfv,
+                                                             const float* __restrict__ sgv, __half* O, float* lse, int S) {
+  __shared__ float lut[16];
+  if (threadIdx.x < 16) {
+    const float mag[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+    lut[threadIdx.x] = (threadIdx.x & 8) ? -mag[threadIdx.x & 7] : mag[threadIdx.x & 7];
+  }
+  __syncthreads();
+  const int bh = blockIdx.x, d = threadIdx.x;
+  const uint8_t* rowp = vt4 + ((size_t)bh * kFp4D + d) * (S / 2);
+  float acc = 0.f;
+  for (int j = 0; j < S / 128; ++j) {
+    const uint8_t* sf = sfv + ((size_t)bh * (S / 128) + j) * 1024 + 16 * (d % 32) + 4 * (d / 32);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const uint2 w = *reinterpret_cast<const uint2*>(rowp + (size_t)j * 64 + b * 8);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum += lut[(w.x >> (4 * i)) & 15];
+        sum += lut[(w.y >> (4 * i)) & 15];
+      }
+      acc = fmaf(sum, fp4_e4m3_to_float(sf[(b / 4) * 512 + (b % 4)]), acc);
+    }
+  }
+  O[(size_t)bh * S * kFp4D + d] = __float2half_rn(acc * sgv[bh] / (float)S);
+  if (d == 0) lse[(size_t)bh * S] = -128.0f + log2f((float)S);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -615,9 +662,10 @@ using namespace qa;
 // q4, k4: [BH*S, 64] bytes (e2m1 pairs); vt4: [BH, 128, Sk/2] bytes; sf*: 512-byte atoms, 2 per 128-row tile; sg*: [BH] fp32
 // (all produced by qa_fp4_quant_rows / qa_fp4_quant_vt).  O: fp16 [BH*Sq, 128]; lse: fp32 [BH*Sq] (log2 domain).
 // variant 0 (default): one CTA per SM, de-phased exp warps, 128-key tiles; 1: two CTAs per SM, 64-key steps.
+// flags: QA_FLAG_CAUSAL = the strict causal mask of the reference's baseline (key < query; row 0 of a head = average over all keys).
 extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
                           const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
-                          int D, int variant, void* stream) {
+                          int D, int variant, int flags, void* stream) {
   if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: D must be 128");
   if (BH <= 0 || Sq <= 0 || Sk <= 0 || Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: Sq, Sk must be positive multiples of 128");
   if ((long long)BH * Sq >= (1ll << 31) || (long long)BH * Sk >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: BH * S must stay below 2^31");
@@ -627,6 +675,9 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
     if (i != 2 && i != 5 && i != 8 && i != 10 && ((uintptr_t)ptrs[i] & 15)) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: 16-byte alignment required");
   }
   if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: variant must be 0 (one CTA per SM, de-phased exp warps, 128-key tiles) or 1 (two CTAs per SM, 64-key steps)");
+  const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
+  if (flags & ~QA_FLAG_CAUSAL) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: unknown flag");
+  if (causal && (Sq != Sk || variant != 0 || Sq / 128 > 65535)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: causal needs Sq == Sk (at most 65535 query tiles) and variant 0");
   constexpr int STAGES = 4;
   using L = Fp4FwdSmem<STAGES>;
   CUtensorMap tq, tk, tv, tsq, tsk, tsv;
@@ -653,9 +704,14 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
     kern2<<<dim3(Sq / 128, BH), 384, L2::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
     return qa_check_launch("qa_fp4_fwd");
   }
-  auto kern = fp4_fwd_kernel<STAGES>;
+  auto kern = causal ? fp4_fwd_kernel<STAGES, true> : fp4_fwd_kernel<STAGES, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  kern<<<dim3(Sq / 128, BH), 640, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+  kern<<<causal ? dim3(BH, Sq / 128) : dim3(Sq / 128, BH), 640, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+  if (causal) {
+    int rc2 = qa_check_launch("qa_fp4_fwd");
+    if (rc2) return rc2;
+    fp4_row0_fixup_kernel<<<BH, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)vt4, (const uint8_t*)sfv, p.sgv, p.O, p.lse, Sk);
+  }
   return qa_check_launch("qa_fp4_fwd");
 }

@@ -46,30 +46,34 @@ def jvp_attention(q, k, v, layout: str = "bshd"):
     return _from_bhsd(attention_jvp.jvp_attention(*[_to_bhsd(t, layout) for t in (q, k, v)]), layout)
 
 
-def sage_attention_lowp(q, k, v, precision: str = "fp4", layout: str = "bshd"):
+def sage_attention_lowp(q, k, v, precision: str = "fp4", layout: str = "bshd", causal: bool = False):
     """Inference-only SageAttention3-style forward in fp8 (e4m3) or NVFP4 (`precision` = "fp8" | "fp4"; fp4: D = 128) for
-    `[B,S,H,D]` (default) or `[B,H,S,D]` fp16 tensors; the result does not require grad."""
+    `[B,S,H,D]` (default) or `[B,H,S,D]` fp16 tensors; the result does not require grad.  causal (fp4 only): the strict mask
+    of the reference's baseline, see attention_fp4.sage_attention_3_fp4."""
     from . import attention_fp4, attention_fp8
     if precision not in ("fp8", "fp4"):
         raise ValueError('precision must be "fp8" or "fp4"')
-    fn = attention_fp4.sage_attention_3_fp4 if precision == "fp4" else attention_fp8.sage_attention_3_fp8
-    return _from_bhsd(fn(*[_to_bhsd(t, layout) for t in (q, k, v)]), layout)
+    if causal and precision != "fp4":
+        raise ValueError("the fp8 forward has no causal mode")
+    bhsd = [_to_bhsd(t, layout) for t in (q, k, v)]
+    o = attention_fp4.sage_attention_3_fp4(*bhsd, causal=causal) if precision == "fp4" else attention_fp8.sage_attention_3_fp8(*bhsd)
+    return _from_bhsd(o, layout)
 
 
 class SageAttention3LowPrecision(nn.Module):
     """`sage_attention_lowp` as a module (inference): `SageAttention3LowPrecision("fp4")(q, k, v)`."""
 
-    def __init__(self, precision: str = "fp4", layout: str = "bshd"):
+    def __init__(self, precision: str = "fp4", layout: str = "bshd", causal: bool = False):
         super().__init__()
         if precision not in ("fp8", "fp4"):
             raise ValueError('precision must be "fp8" or "fp4"')
-        self.precision, self.layout = precision, layout
+        self.precision, self.layout, self.causal = precision, layout, causal
 
     def forward(self, q, k, v):
-        return sage_attention_lowp(q, k, v, self.precision, self.layout)
+        return sage_attention_lowp(q, k, v, self.precision, self.layout, self.causal)
 
     def extra_repr(self):
-        return f"precision={self.precision!r}, layout={self.layout!r}"
+        return f"precision={self.precision!r}, layout={self.layout!r}, causal={self.causal}"
 
 
 class SageAttention3Int8(nn.Module):

@@ -168,14 +168,14 @@ def _(q, k, v):
 
 
 @torch.library.custom_op("qattn::sage_fp4_fwd", mutates_args=())
-def sage_fp4_fwd(q: _T, k: _T, v: _T) -> _T:
+def sage_fp4_fwd(q: _T, k: _T, v: _T, causal: bool) -> _T:
     """attention_fp4.sage_attention_3_fp4: O fp16 [B,H,S,D] through the NVFP4 pipeline (D = 128; no gradient)."""
     from . import attention_fp4
-    return attention_fp4.sage_attention_3_fp4(q, k, v)
+    return attention_fp4.sage_attention_3_fp4(q, k, v, causal)
 
 
 @sage_fp4_fwd.register_fake
-def _(q, k, v):
+def _(q, k, v, causal):
     return q.new_empty(q.shape, dtype=torch.float16)
 
 
@@ -183,5 +183,5 @@ def sage_attention_3_fp8_op(q_fp16: _T, k_fp16: _T, v_fp16: _T) -> _T:
     return sage_fp8_fwd(q_fp16, k_fp16, v_fp16)
 
 
-def sage_attention_3_fp4_op(q_fp16: _T, k_fp16: _T, v_fp16: _T) -> _T:
-    return sage_fp4_fwd(q_fp16, k_fp16, v_fp16)
+def sage_attention_3_fp4_op(q_fp16: _T, k_fp16: _T, v_fp16: _T, causal: bool = False) -> _T:
+    return sage_fp4_fwd(q_fp16, k_fp16, v_fp16, causal)

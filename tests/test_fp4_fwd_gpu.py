@@ -102,3 +102,25 @@ def test_fp4_fwd_at_baseline_sequence_length(variant):
     mx, cos = _stats(O.cpu(), Oref)
     assert mx < 1e-2 and cos > 0.9995, (mx, cos)
     assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 256, 128), (2, 2, 1024, 128)])
+def test_fp4_fwd_causal_matches_definition_and_baseline(shape):
+    """Strict causal mask (key < query; row 0 = average over all keys), as on the int8 path."""
+    from oracle import fp4_ref
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_fp4 as F
+    q, k, v = _inputs(shape, 700 + shape[2], "randn")
+    O, lse = F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()), causal=True)
+    torch.cuda.synchronize()
+    Oref, lse_ref, _ = fp4_ref.fp4_fwd(q, k, v, step=128, causal=True)
+    assert torch.isfinite(O.float()).all()
+    mx, cos = _stats(O.cpu(), Oref)
+    assert mx < 2e-2 and cos > 0.9995, (mx, cos)             # early rows have few keys: single e2m1 flips weigh more
+    assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
+    base = baseline_pytorch_attention(q.float(), k.float(), v.float(), shape[3], True)
+    assert (O[:, :, 0].cpu().float() - base[:, :, 0]).abs().max().item() < 0.1      # row 0: mean of V, quantised
+    mx, cos = _stats(O.cpu(), base)
+    assert cos > 0.97, (mx, cos)
+    with pytest.raises(RuntimeError):
+        F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()), variant=1, causal=True)

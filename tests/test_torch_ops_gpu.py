@@ -74,7 +74,9 @@ def test_lowp_ops_and_modules_match_and_compile():
     for op, ref in ((T.sage_attention_3_fp4_op, attention_fp4.sage_attention_3_fp4), (T.sage_attention_3_fp8_op, attention_fp8.sage_attention_3_fp8)):
         cf = torch.compile(lambda q, k, v: op(q * 1.0, k, v) * 2.0, backend="aot_eager", fullgraph=True)
         assert torch.equal(cf(q, k, v) / 2.0, ref(q, k, v))
-    torch.library.opcheck(T.sage_fp4_fwd, (q, k, v), test_utils=("test_schema", "test_faketensor"))
+    torch.library.opcheck(T.sage_fp4_fwd, (q, k, v, True), test_utils=("test_schema", "test_faketensor"))
+    assert torch.equal(T.sage_attention_3_fp4_op(q, k, v, causal=True), attention_fp4.sage_attention_3_fp4(q, k, v, causal=True))
+    assert torch.equal(modules.SageAttention3LowPrecision("fp4", layout="bhsd", causal=True)(q, k, v), attention_fp4.sage_attention_3_fp4(q, k, v, causal=True))
     torch.library.opcheck(T.sage_fp8_fwd, (q, k, v), test_utils=("test_schema", "test_faketensor"))
     for prec, ref in (("fp4", attention_fp4.sage_attention_3_fp4), ("fp8", attention_fp8.sage_attention_3_fp8)):
         m = modules.SageAttention3LowPrecision(prec, layout="bshd")
