@@ -43,7 +43,7 @@ struct Fp4FwdParams {
   const float *sgq, *sgk, *sgv;      // [BH] second-level scales
   __half* O;                         // [BH*Sq, 128] fp16
   float* lse;                        // [BH*Sq] log2 domain
-  int Sq, Sk;
+  int Sq, Sk, BH;
   float qk_scale;                    // sm_scale * log2(e)
 };
 
@@ -86,8 +86,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // CAUSAL: the strict mask of the reference's baseline (key < query, attention_int8.py:465-473), as on the int8 path: a query
   // tile meets the k-tiles up to its own (heaviest tiles first); row 0 of a head sees no key and is written by fp4_row0_fixup_kernel
-  // (causal grid = (heads, query tiles): all heads' heaviest tiles are dispatched first)
-  const int bh = CAUSAL ? blockIdx.x : blockIdx.y, q0 = (CAUSAL ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.x) * 128;
+  // (causal: 1-D grid in groups of 16 heads, inside a group the heaviest tiles of all its heads first - global heaviest-first
+  //  would spread the K / V working set of the running CTAs over every head and out of the L2)
+  int rank_ = 0, head_ = 0;
+  if (CAUSAL) qa_group_order((int)blockIdx.x, p.BH, p.Sq / 128, 16, rank_, head_);
+  const int bh = CAUSAL ? head_ : (int)blockIdx.y, q0 = (CAUSAL ? p.Sq / 128 - 1 - rank_ : (int)blockIdx.x) * 128;
   const int nk = CAUSAL ? min(p.Sk / 128, q0 / 128 + 1) : p.Sk / 128;
   const int jd = q0 / 128;                                       // CAUSAL: the diagonal k-tile (local column < local row is visible)
 
@@ -677,7 +680,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: variant must be 0 (one CTA per SM, de-phased exp warps, 128-key tiles) or 1 (two CTAs per SM, 64-key steps)");
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
   if (flags & ~QA_FLAG_CAUSAL) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: unknown flag");
-  if (causal && (Sq != Sk || variant != 0 || Sq / 128 > 65535)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: causal needs Sq == Sk (at most 65535 query tiles) and variant 0");
+  if (causal && (Sq != Sk || variant != 0)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: causal needs Sq == Sk and variant 0");
   constexpr int STAGES = 4;
   using L = Fp4FwdSmem<STAGES>;
   CUtensorMap tq, tk, tv, tsq, tsk, tsv;
@@ -694,7 +697,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   if ((rc = qa_make_tmap(&tsv, sfv, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dsk, ssf, boxsf, 0))) return rc;
   Fp4FwdParams p;
   p.sgq = (const float*)sgq; p.sgk = (const float*)sgk; p.sgv = (const float*)sgv;
-  p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk;
+  p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.BH = BH;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   if (variant == 1) {
     using L2 = Fp4Fwd2Smem<3>;
@@ -707,7 +710,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   auto kern = causal ? fp4_fwd_kernel<STAGES, true> : fp4_fwd_kernel<STAGES, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  kern<<<causal ? dim3(BH, Sq / 128) : dim3(Sq / 128, BH), 640, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
+  kern<<<causal ? dim3((unsigned)((size_t)BH * (Sq / 128))) : dim3(Sq / 128, BH), 640, L::total, (cudaStream_t)stream>>>(tq, tk, tv, tsq, tsk, tsv, p);
   if (causal) {
     int rc2 = qa_check_launch("qa_fp4_fwd");
     if (rc2) return rc2;

@@ -6,9 +6,10 @@ import torch
 sys.path.insert(0, ".")
 from quantizedattention_b200 import attention_fp4 as F, ops  # noqa: E402
 
-q, k, v = [torch.randn(2, 32, 8192, 128, device="cuda", dtype=torch.float16) for _ in range(3)]
-o = F.quantise_fp4(q, k, v)
-for c in (False, True):
+for B in (2, 8):
+  q, k, v = [torch.randn(B, 32, 8192, 128, device="cuda", dtype=torch.float16) for _ in range(3)]
+  o = F.quantise_fp4(q, k, v)
+  for c in (False, True):
     for _ in range(3):
         F.fp4_fwd_prequant(o, causal=c)
     ops.TIMING = []
@@ -17,4 +18,4 @@ for c in (False, True):
     torch.cuda.synchronize()
     t = sorted(a.elapsed_time(b) for n, a, b in ops.TIMING if n == "fp4_fwd")[3]
     ops.TIMING = None
-    print("causal", c, "ms", round(t, 3), "TFLOPS (causal = half of dense)", round((0.5 if c else 1) * 4 * 64 * 8192 * 8192 * 128 / t / 1e9, 1))
+    print("B*H", B * 32, "causal", c, "ms", round(t, 3), "TFLOPS (causal = half of dense)", round((0.5 if c else 1) * 4 * B * 32 * 8192 * 8192 * 128 / t / 1e9, 1))
