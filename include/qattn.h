@@ -101,6 +101,10 @@ int qa_fp8_fwd(const void* q_e4m3, const void* k_e4m3, const void* v_e4m3, const
  * per-head K token mean subtracted first (one fp16 rounding), as in the int8 path. */
 int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH, int S,
                       int D, void* stream);
+/* Ragged sequences (zero-padded per head to S, a multiple of 128): rows [S_valid, S) of every head stay zero after the smoothing
+ * and do not enter the head amax; qa_fp4_fwd_ragged gives the keys [Sk_valid, Sk) weight exactly 0 (variant 0). */
+int qa_fp4_quant_rows_ragged(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH,
+                             int S, int S_valid, int D, void* stream);
 int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, void* sg_f32, int BH, int S, int D, void* stream);
 /* O fp16 [BH*Sq, D], lse fp32 [BH*Sq] (log2 domain); P is microscaled per row and 16 keys inside the kernel
  * (sfp = e4m3(amax * 448), code = e2m1_rn(P * 2688 / sfp)); the fp32 accumulator spans all k-tiles.
@@ -111,6 +115,9 @@ int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t, void* sf, 
 int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq_f32, const void* k4, const void* sfk, const void* sgk_f32,
                const void* vt4, const void* sfv, const void* sgv_f32, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk, int D,
                int variant, int flags, void* stream);
+int qa_fp4_fwd_ragged(const void* q4, const void* sfq, const void* sgq_f32, const void* k4, const void* sfk, const void* sgk_f32,
+                      const void* vt4, const void* sfv, const void* sgv_f32, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
+                      int Sk_valid, int D, int variant, int flags, void* stream);
 
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;

@@ -70,10 +70,14 @@ def sf_atoms(sf: torch.Tensor) -> torch.Tensor:
 
 def quantise_inputs(q, k, v):
     """fp16 [B,H,S,D] -> dict of the quantised operands exactly as the CUDA pre-passes emit them."""
-    B, H, S, D = q.shape
+    B, H, S_valid, D = q.shape
     G = B * H
-    k_mean = k.float().mean(dim=2, keepdim=True).to(torch.float16)                 # LEDGER I-1
+    k_mean = k.float().mean(dim=2, keepdim=True).to(torch.float16)                 # LEDGER I-1 (over the valid keys)
     ks = (k - k_mean)                                                              # one fp16 rounding
+    S = (S_valid + 127) // 128 * 128                                               # ragged: zero rows up to the next tile boundary
+    if S != S_valid:                                                               # (zeros change no amax and no block scale)
+        pad = lambda t: torch.cat([t, t.new_zeros((B, H, S - S_valid, D))], dim=2)
+        q, ks, v = pad(q), pad(ks), pad(v)
     qd, qc, qsf, sgq = quant_nvfp4(q.reshape(G, S, D).float())
     kd, kc, ksf, sgk = quant_nvfp4(ks.reshape(G, S, D).float())
     vd_t, vc_t, vsf, sgv = quant_nvfp4(v.reshape(G, S, D).float().transpose(1, 2).contiguous())   # [G, D, S]: blocks along keys
@@ -90,8 +94,9 @@ def fp4_fwd(q, k, v, step: int = 128, causal: bool = False):
     step: keys per online-softmax step (128: the default kernel; 64: the two-CTA variant).  causal: the STRICT mask of the
     reference's baseline (key < query, attention_int8.py:465-473); row 0 of a head = average of the de-quantised V over all keys,
     lse = -128 + log2 S (the int8 path's convention)."""
-    B, H, S, D = q.shape
+    B, H, S_valid, D = q.shape
     G = B * H
+    S = (S_valid + 127) // 128 * 128
     qi = quantise_inputs(q, k, v)
     qd, kd, vd = qi["qd"] / qi["sgq"].view(G, 1, 1).clamp_min(1e-38), qi["kd"] / qi["sgk"].view(G, 1, 1).clamp_min(1e-38), \
         qi["vd"] / qi["sgv"].view(G, 1, 1).clamp_min(1e-38)                       # the tensor core sees code * sf only
@@ -102,13 +107,15 @@ def fp4_fwd(q, k, v, step: int = 128, causal: bool = False):
     for j in range(S // step):
         ks = slice(j * step, (j + 1) * step)
         u = torch.matmul(qd, kd[:, ks].transpose(1, 2)) * c
+        keep = (torch.arange(j * step, (j + 1) * step) < S_valid)[None, None, :].expand(1, S, step)     # ragged: padding keys
         if causal:
-            keep = (torch.arange(j * step, (j + 1) * step)[None, :] < torch.arange(S)[:, None])[None]
+            keep = keep & (torch.arange(j * step, (j + 1) * step)[None, :] < torch.arange(S)[:, None])[None]
+        if causal or S != S_valid:
             u = torch.where(keep, u, torch.full_like(u, float("-inf")))
         m_new = torch.max(m, u.amax(-1, keepdim=True))
         P = torch.exp2(u - m_new)
         resc = torch.exp2(m - m_new)
-        if causal:
+        if causal or S != S_valid:
             P = torch.where(keep, P, torch.zeros_like(P))                      # (row 0: (-inf) - (-inf))
             resc = torch.where(torch.isinf(m_new), torch.ones_like(resc), resc)
         l = l * resc + P.sum(-1, keepdim=True)
@@ -122,6 +129,6 @@ def fp4_fwd(q, k, v, step: int = 128, causal: bool = False):
     out = O * (qi["sgv"].view(G, 1, 1) / 2688.0) / l
     lse = (m + torch.log2(l)).reshape(G, S)
     if causal:
-        out[:, 0] = qi["vd"].mean(dim=1)
-        lse[:, 0] = -128.0 + math.log2(S)
-    return out.to(torch.float16).reshape(B, H, S, D), lse, qi
+        out[:, 0] = qi["vd"].sum(dim=1) / S_valid
+        lse[:, 0] = -128.0 + math.log2(S_valid)
+    return out[:, :S_valid].to(torch.float16).reshape(B, H, S_valid, D), lse[:, :S_valid], qi

@@ -44,6 +44,7 @@ struct Fp4FwdParams {
   __half* O;                         // [BH*Sq, 128] fp16
   float* lse;                        // [BH*Sq] log2 domain
   int Sq, Sk, BH;
+  int Sk_valid;                      // keys [Sk_valid, Sk) of every head are zero padding (ragged sequence): weight exactly 0
   float qk_scale;                    // sm_scale * log2(e)
 };
 
@@ -91,7 +92,9 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   int rank_ = 0, head_ = 0;
   if (CAUSAL) qa_group_order((int)blockIdx.x, p.BH, p.Sq / 128, 16, rank_, head_);
   const int bh = CAUSAL ? head_ : (int)blockIdx.y, q0 = (CAUSAL ? p.Sq / 128 - 1 - rank_ : (int)blockIdx.x) * 128;
-  const int nk = CAUSAL ? min(p.Sk / 128, q0 / 128 + 1) : p.Sk / 128;
+  const int nk_valid = (p.Sk_valid + 127) / 128;                  // ragged: k-tiles without a valid key are skipped
+  const int nk = CAUSAL ? min(nk_valid, q0 / 128 + 1) : nk_valid;
+  const int ktail = p.Sk_valid - (nk_valid - 1) * 128;           // valid keys of the last tile (128 unless the sequence is ragged)
   const int jd = q0 / 128;                                       // CAUSAL: the diagonal k-tile (local column < local row is visible)
 
   if (tid == 0) {
@@ -157,6 +160,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               if (col >= row) pe[i].x = 0.f;
               if (col + 1 >= row) pe[i].y = 0.f;
             }
+            if (ktail < 128 && j == nk_valid - 1) {                // ragged last tile: padding keys have weight 0
+              const int col = hf * 64 + b * 16 + 2 * i;
+              if (col >= ktail) pe[i].x = 0.f;
+              if (col + 1 >= ktail) pe[i].y = 0.f;
+            }
             if (i & 1) a1 = fmaxf(a1, fmaxf(pe[i].x, pe[i].y)); else a0 = fmaxf(a0, fmaxf(pe[i].x, pe[i].y));
             ls2 = __fadd2_rn(ls2, pe[i]);
           }
@@ -213,6 +221,11 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 64; ++i)
             if (ch * 64 + i >= row) r[i] = 0xff800000u;             // masked logit: -inf
+        }
+        if (ktail < 128 && j == nk_valid - 1) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (ch * 64 + i >= ktail) r[i] = 0xff800000u;           // padding key
         }
 #pragma unroll
         for (int i = 0; i < 64; i += 8)
@@ -369,7 +382,7 @@ fp4_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 // Causal row 0 of every head sees no key: the reference's baseline (finite fill value) makes it the uniform average over ALL keys
 // of V, here of the de-quantised V (as int8_row0_fixup_kernel); lse = -128 + log2(S).  grid = BH, thread = output column d.
 __global__ void __launch_bounds__(128) fp4_row0_fixup_kernel(const uint8_t* __restrict__ vt4, const uint8_t* __restrict__ sfv,
-                                                             const float* __restrict__ sgv, __half* O, float* lse, int S) {
+                                                             const float* __restrict__ sgv, __half* O, float* lse, int S, int S_valid) {
   __shared__ float lut[16];
   if (threadIdx.x < 16) {
     const float mag[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
@@ -393,8 +406,8 @@ __global__ void __launch_bounds__(128) fp4_row0_fixup_kernel(const uint8_t* __re
       acc = fmaf(sum, fp4_e4m3_to_float(sf[(b / 4) * 512 + (b % 4)]), acc);
     }
   }
-  O[(size_t)bh * S * kFp4D + d] = __float2half_rn(acc * sgv[bh] / (float)S);
-  if (d == 0) lse[(size_t)bh * S] = -128.0f + log2f((float)S);
+  O[(size_t)bh * S * kFp4D + d] = __float2half_rn(acc * sgv[bh] / (float)S_valid);     // padded V rows are zero
+  if (d == 0) lse[(size_t)bh * S] = -128.0f + log2f((float)S_valid);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -666,9 +679,9 @@ using namespace qa;
 // (all produced by qa_fp4_quant_rows / qa_fp4_quant_vt).  O: fp16 [BH*Sq, 128]; lse: fp32 [BH*Sq] (log2 domain).
 // variant 0 (default): one CTA per SM, de-phased exp warps, 128-key tiles; 1: two CTAs per SM, 64-key steps.
 // flags: QA_FLAG_CAUSAL = the strict causal mask of the reference's baseline (key < query; row 0 of a head = average over all keys).
-extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
-                          const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
-                          int D, int variant, int flags, void* stream) {
+extern "C" int qa_fp4_fwd_ragged(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
+                                 const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
+                                 int Sk_valid, int D, int variant, int flags, void* stream) {
   if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: D must be 128");
   if (BH <= 0 || Sq <= 0 || Sk <= 0 || Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: Sq, Sk must be positive multiples of 128");
   if ((long long)BH * Sq >= (1ll << 31) || (long long)BH * Sk >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: BH * S must stay below 2^31");
@@ -678,6 +691,8 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
     if (i != 2 && i != 5 && i != 8 && i != 10 && ((uintptr_t)ptrs[i] & 15)) return qa_fail(QA_ERR_ALIGN, "qa_fp4_fwd: 16-byte alignment required");
   }
   if (variant < 0 || variant > 1) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: variant must be 0 (one CTA per SM, de-phased exp warps, 128-key tiles) or 1 (two CTAs per SM, 64-key steps)");
+  if (Sk_valid <= Sk - 128 || Sk_valid > Sk) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: Sk_valid must lie in (Sk - 128, Sk]");
+  if (Sk_valid != Sk && variant != 0) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: ragged sequences need variant 0");
   const bool causal = (flags & QA_FLAG_CAUSAL) != 0;
   if (flags & ~QA_FLAG_CAUSAL) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: unknown flag");
   if (causal && (Sq != Sk || variant != 0)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: causal needs Sq == Sk and variant 0");
@@ -697,7 +712,7 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   if ((rc = qa_make_tmap(&tsv, sfv, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dsk, ssf, boxsf, 0))) return rc;
   Fp4FwdParams p;
   p.sgq = (const float*)sgq; p.sgk = (const float*)sgk; p.sgv = (const float*)sgv;
-  p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.BH = BH;
+  p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.BH = BH; p.Sk_valid = Sk_valid;
   p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
   if (variant == 1) {
     using L2 = Fp4Fwd2Smem<3>;
@@ -714,7 +729,13 @@ extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, cons
   if (causal) {
     int rc2 = qa_check_launch("qa_fp4_fwd");
     if (rc2) return rc2;
-    fp4_row0_fixup_kernel<<<BH, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)vt4, (const uint8_t*)sfv, p.sgv, p.O, p.lse, Sk);
+    fp4_row0_fixup_kernel<<<BH, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)vt4, (const uint8_t*)sfv, p.sgv, p.O, p.lse, Sk, Sk_valid);
   }
   return qa_check_launch("qa_fp4_fwd");
+}
+
+extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
+                          const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
+                          int D, int variant, int flags, void* stream) {
+  return qa_fp4_fwd_ragged(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, O_fp16, lse_f32, BH, Sq, Sk, Sk, D, variant, flags, stream);
 }

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t pack_e2m1x8(const float (&y)[8]) {
 // Two-pass fallback (a head with more 128-row tiles than the GPU has SMs cannot be guaranteed resident, so its CTAs must not
 // wait for each other): amax over a head of |x - mean| (fp16 rounding of the difference).  grid = (chunks, BH)
 __global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
-                                                            float* __restrict__ amax, int S, int D) {
+                                                            float* __restrict__ amax, int S, int D, int S_valid) {
   const int bh = blockIdx.y;
   const size_t n8 = (size_t)S * D / 8;
   const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)bh * S * D);
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __rest
     uint4 v = __ldg(base + i);
     const __half* h = reinterpret_cast<const __half*>(&v);
     const int d0 = (int)(i % dv) * 8;
+    if ((int)(i / dv) >= S_valid) continue;                      // padding rows of a ragged sequence count as zeros
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const __half t = mean ? __hsub(h[e], mean[(size_t)bh * D + d0 + e]) : h[e];
@@ -91,7 +92,7 @@ template <int D>
 __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
                                                                       float* __restrict__ amax, unsigned* __restrict__ count,
                                                                       uint8_t* __restrict__ codes, uint8_t* __restrict__ sf,
-                                                                      float* __restrict__ sg_out, int S) {
+                                                                      float* __restrict__ sg_out, int S, int S_valid) {
   constexpr int NB = D / 16;
   __shared__ float red[32];
   const int tile = blockIdx.x;                                   // 128-row tile over B*H*S: the S / 128 tiles of a head are contiguous
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __ha
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const __half t = mean ? __hsub(h[e], mean[(size_t)bh * D + b * 16 + hv * 8 + e]) : h[e];
-      v[hv * 8 + e] = __half2float(t);
+      v[hv * 8 + e] = ((int)(row % S) < S_valid) ? __half2float(t) : 0.f;      // padding rows stay zero after the smoothing
       am = fmaxf(am, fabsf(v[hv * 8 + e]));
     }
   }
@@ -192,8 +193,9 @@ static int fp4_sm_count() {                                       // SMs of the 
 
 // x: [BH, S, D] fp16; mean: [BH, D] fp16 or NULL (K smoothing); amax_ws: 2 * BH 32-bit words of scratch (overwritten);
 // codes: [BH*S, D/2] bytes; sf: [BH*S/128][D/64][512] bytes; sg: [BH] fp32.  D = 128, S % 128 == 0.
-extern "C" int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH,
-                                 int S, int D, void* stream) {
+extern "C" int qa_fp4_quant_rows_ragged(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32,
+                                        int BH, int S, int S_valid, int D, void* stream) {
+  if (S_valid <= 0 || S_valid > S) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_rows: S_valid must lie in (0, S]");
   if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_rows: D must be 128");
   if (BH <= 0 || S <= 0 || S % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_quant_rows: S must be a positive multiple of 128");
   if (!x_fp16 || !amax_ws || !codes || !sf || !sg_f32) return qa_fail(QA_ERR_ALIGN, "qa_fp4_quant_rows: null pointer");
@@ -207,12 +209,17 @@ extern "C" int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void
   const bool one_pass = false;
   if (!one_pass) {
     const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
-    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, D);
+    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, D, S_valid);
   }
   fp4_quant_rows_kernel<128><<<(unsigned)((size_t)BH * S / 128), 1024, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16,
                                                                               (float*)amax_ws, one_pass ? (unsigned*)amax_ws + BH : nullptr,
-                                                                              (uint8_t*)codes, (uint8_t*)sf, (float*)sg_f32, S);
+                                                                              (uint8_t*)codes, (uint8_t*)sf, (float*)sg_f32, S, S_valid);
   return qa_check_launch("qa_fp4_quant_rows");
+}
+
+extern "C" int qa_fp4_quant_rows(const void* x_fp16, const void* mean_fp16, void* amax_ws, void* codes, void* sf, void* sg_f32, int BH,
+                                 int S, int D, void* stream) {
+  return qa_fp4_quant_rows_ragged(x_fp16, mean_fp16, amax_ws, codes, sf, sg_f32, BH, S, S, D, stream);
 }
 
 // v: [BH, S, D] fp16 -> codes_t: [BH, D, S/2] bytes (transposed), sf: [BH*S/128][2][512] bytes, sg: [BH] fp32; amax_ws: 2 * BH words
@@ -228,7 +235,7 @@ extern "C" int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t,
   const bool one_pass = S / 128 <= fp4_sm_count();
   if (!one_pass) {
     const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
-    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, D);
+    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, D, S);
   }
   fp4_quant_vt_kernel<128><<<(unsigned)((size_t)BH * (S / 128)), 256, 0, st>>>((const __half*)v_fp16, (float*)amax_ws,
                                                                              one_pass ? (unsigned*)amax_ws + BH : nullptr, (uint8_t*)codes_t,

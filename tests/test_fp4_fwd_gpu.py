@@ -26,6 +26,7 @@ def _inputs(shape, seed, kind="randn"):
 
 
 @pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((2, 2, 512, 128), "offset"), ((1, 2, 384, 128), "zeros"),
+                                        ((1, 2, 200, 128), "offset"), ((2, 1, 333, 128), "randn"),      # ragged: zero padding to 256 / 384
                                         ((1, 3, 8192, 128), "offset"),        # V in one pass: the 64 CTAs of a head wait for each other
                                         ((1, 1, 20480, 128), "randn")])       # 160 tiles per head > 148 SMs: V falls back to two passes
 def test_fp4_quantisation_is_bit_exact(shape, kind):
@@ -73,8 +74,6 @@ def test_sage_attention_3_fp4_validates():
     assert O.shape == q.shape and O.dtype == torch.float16 and not O.requires_grad
     with pytest.raises(TypeError):
         F.sage_attention_3_fp4(q.float(), q.float(), q.float())
-    with pytest.raises(ValueError):
-        F.sage_attention_3_fp4(q[:, :, :200], q[:, :, :200], q[:, :, :200])
     with pytest.raises(ValueError):
         F.sage_attention_3_fp4(q[..., :64].contiguous(), q[..., :64].contiguous(), q[..., :64].contiguous())
 
@@ -124,3 +123,21 @@ def test_fp4_fwd_causal_matches_definition_and_baseline(shape):
     assert cos > 0.97, (mx, cos)
     with pytest.raises(RuntimeError):
         F.fp4_fwd_prequant(F.quantise_fp4(q.cuda(), k.cuda(), v.cuda()), variant=1, causal=True)
+
+
+@pytest.mark.parametrize("S,causal", [(200, False), (333, True), (129, False), (1000, True)])
+def test_fp4_fwd_ragged_sequence_lengths(S, causal):
+    """Sequence lengths that are not multiples of 128 (the reference's hl.tile clamps its last tile): zero padding per head,
+    padded keys masked in the kernel, padded K rows kept at zero by the quantiser."""
+    from oracle import fp4_ref
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_fp4 as F
+    q, k, v = _inputs((1, 2, S, 128), 900 + S, "offset")
+    O = F.sage_attention_3_fp4(q.cuda(), k.cuda(), v.cuda(), causal=causal)
+    torch.cuda.synchronize()
+    assert O.shape == (1, 2, S, 128)
+    Oref, _, _ = fp4_ref.fp4_fwd(q, k, v, step=128, causal=causal)
+    mx, cos = _stats(O.cpu(), Oref)
+    assert torch.isfinite(O.float()).all() and mx < 2e-2 and cos > 0.9995, (mx, cos)
+    base = baseline_pytorch_attention(q.float(), k.float(), v.float(), 128, causal)
+    assert _stats(O.cpu(), base)[1] > 0.95
