@@ -117,7 +117,7 @@ int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq_f32, const void*
                int variant, int flags, void* stream);
 int qa_fp4_fwd_ragged(const void* q4, const void* sfq, const void* sgq_f32, const void* k4, const void* sfk, const void* sgk_f32,
                       const void* vt4, const void* sfv, const void* sgv_f32, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
-                      int Sk_valid, int D, int variant, int flags, void* stream);
+                      int Sk_valid, int D, int variant, int flags, float sm_scale /* <= 0: 1/sqrt(D) */, void* stream);
 
 /* ---- backward pre/post passes ---- */
 /* delta = rowsum(dO * O) fp32 (attention_int8.py:397-398, attention_bf16.py:416).  in_dtype 0: fp16 dO/O;

@@ -97,11 +97,14 @@ def fp4_fwd(q, k, v, step: int = 128, causal: bool = False):
     B, H, S_valid, D = q.shape
     G = B * H
     S = (S_valid + 127) // 128 * 128
+    sm_scale = 1.0 / math.sqrt(D)
+    if D == 64:                                                                    # runs with 64 zero columns (block scales unaffected)
+        q, k, v = [torch.nn.functional.pad(t, (0, 64)) for t in (q, k, v)]
     qi = quantise_inputs(q, k, v)
     qd, kd, vd = qi["qd"] / qi["sgq"].view(G, 1, 1).clamp_min(1e-38), qi["kd"] / qi["sgk"].view(G, 1, 1).clamp_min(1e-38), \
         qi["vd"] / qi["sgv"].view(G, 1, 1).clamp_min(1e-38)                       # the tensor core sees code * sf only
-    c = (qi["sgq"] * qi["sgk"]).view(G, 1, 1) * ((1.0 / math.sqrt(D)) * LOG2E)
-    O = torch.zeros((G, S, D))
+    c = (qi["sgq"] * qi["sgk"]).view(G, 1, 1) * (sm_scale * LOG2E)
+    O = torch.zeros((G, S, qi["vd"].shape[-1]))
     l = torch.zeros((G, S, 1))
     m = torch.full((G, S, 1), float("-inf"))
     for j in range(S // step):
@@ -131,4 +134,4 @@ def fp4_fwd(q, k, v, step: int = 128, causal: bool = False):
     if causal:
         out[:, 0] = qi["vd"].sum(dim=1) / S_valid
         lse[:, 0] = -128.0 + math.log2(S_valid)
-    return out[:, :S_valid].to(torch.float16).reshape(B, H, S_valid, D), lse[:, :S_valid], qi
+    return out[:, :S_valid, :D].to(torch.float16).reshape(B, H, S_valid, D), lse[:, :S_valid], qi

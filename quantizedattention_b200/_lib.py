@@ -32,7 +32,7 @@ SIGNATURES = {
     "qa_fp8_fwd": (c_int, [c_void_p] * 9 + [c_int] * 4 + [c_void_p]),
     "qa_fp4_quant_rows": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
     "qa_fp4_quant_rows_ragged": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
-    "qa_fp4_fwd_ragged": (c_int, [c_void_p] * 11 + [c_int] * 7 + [c_void_p]),
+    "qa_fp4_fwd_ragged": (c_int, [c_void_p] * 11 + [c_int] * 7 + [c_float, c_void_p]),
     "qa_fp4_quant_vt": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "qa_fp4_fwd": (c_int, [c_void_p] * 11 + [c_int] * 6 + [c_void_p]),
     "qa_int8_bwd_finalize": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),

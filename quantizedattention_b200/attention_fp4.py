@@ -8,7 +8,7 @@ SageAttention3 headline but does not implement (README.md:48-54):
 Q, K (mean-smoothed) and V are quantised to e2m1 with one e4m3 scale per 16 elements along the contraction axis (D for
 Q / K, keys for V, which is stored transposed) and one fp32 scale per head; P is microscaled per row and 16 keys inside
 the kernel.  Both contractions run on tcgen05 `kind::mxf4nvf4.block_scale` with fp32 accumulation in TMEM.
-D = 128; sequence lengths that are not multiples of 128 are zero-padded here and masked in the kernel.  Contract and tolerances: oracle/fp4_ref.py, tests/test_fp4_fwd_gpu.py.
+D = 128 (64 runs zero-padded to 128 columns); sequence lengths that are not multiples of 128 are zero-padded here and masked in the kernel.  Contract and tolerances: oracle/fp4_ref.py, tests/test_fp4_fwd_gpu.py.
 """
 from __future__ import annotations
 
@@ -33,6 +33,7 @@ class Fp4Operands:
     k_mean: torch.Tensor | None
     shape: tuple          # (B, H, Sq, Sk, D): the PADDED lengths (multiples of 128) the buffers are laid out for
     valid: tuple = None   # (Sq_valid, Sk_valid): the caller's sequence lengths (ragged sequences are zero-padded per head)
+    head_dim: int = 128   # the caller's head dimension (64: the operands carry 64 zero columns, sm_scale stays 1/sqrt(64))
 
 
 def _check(q, k, v):
@@ -43,8 +44,8 @@ def _check(q, k, v):
             raise RuntimeError("fp4 attention needs CUDA tensors (there is no CPU fallback)")
     B, H, Sq, D = q.shape
     Sk = k.shape[2]
-    if D != 128:
-        raise ValueError("fp4 attention is built for head dimension 128")
+    if D not in (64, 128):
+        raise ValueError("fp4 attention is built for head dimensions 128 and 64 (64 runs zero-padded to 128)")
     if Sq <= 0 or Sk <= 0:
         raise ValueError("fp4 attention needs non-empty sequences")
     assert k.shape == v.shape and k.shape[:2] == q.shape[:2] and k.shape[3] == D
@@ -66,9 +67,11 @@ def _quant_rows(x, mean, BH, S, D, S_valid=None):
 
 
 def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
-    B, H, Sq_v, Sk_v, D = _check(q_fp16, k_fp16, v_fp16)
-    BH = B * H
+    B, H, Sq_v, Sk_v, D_v = _check(q_fp16, k_fp16, v_fp16)
+    BH, D = B * H, 128
     q, k, v = q_fp16.contiguous(), k_fp16.contiguous(), v_fp16.contiguous()
+    if D_v != D:                                                      # head dimension 64: zero columns change neither Q K^T nor the
+        q, k, v = [torch.nn.functional.pad(t, (0, D - D_v)) for t in (q, k, v)]   # block scales; the extra O columns are dropped
     k_mean = ops.k_mean(k) if smooth_k else None                      # fp16 [B,H,1,D], over the valid keys
     # ragged sequences (the reference's hl.tile clamps its last tile): zero padding per head to a multiple of 128; the padded
     # K rows stay zero after the smoothing and the kernel gives the padded keys weight 0
@@ -85,7 +88,7 @@ def quantise_fp4(q_fp16, k_fp16, v_fp16, smooth_k: bool = True) -> Fp4Operands:
     with torch.cuda.device(dev), ops._timed("fp4_quant_vt"):
         _lib.check(L.qa_fp4_quant_vt(_lib.ptr(v), _lib.ptr(ws), _lib.ptr(vt4), _lib.ptr(sfv), _lib.ptr(sgv), BH, Sk, D,
                                      _lib.cur_stream()), "qa_fp4_quant_vt")
-    return Fp4Operands(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, k_mean, (B, H, Sq, Sk, D), (Sq_v, Sk_v))
+    return Fp4Operands(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, k_mean, (B, H, Sq, Sk, D), (Sq_v, Sk_v), D_v)
 
 
 def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0, causal: bool = False):
@@ -101,10 +104,10 @@ def fp4_fwd_prequant(o: Fp4Operands, variant: int = 0, causal: bool = False):
     with torch.cuda.device(dev), ops._timed("fp4_fwd"):
         _lib.check(L.qa_fp4_fwd_ragged(_lib.ptr(o.q4), _lib.ptr(o.sfq), _lib.ptr(o.sgq), _lib.ptr(o.k4), _lib.ptr(o.sfk), _lib.ptr(o.sgk),
                                        _lib.ptr(o.vt4), _lib.ptr(o.sfv), _lib.ptr(o.sgv), _lib.ptr(O), _lib.ptr(lse), B * H, Sq, Sk, Sk_v, D,
-                                       int(variant), 2 if causal else 0, _lib.cur_stream()), "qa_fp4_fwd")
+                                       int(variant), 2 if causal else 0, float(o.head_dim) ** -0.5, _lib.cur_stream()), "qa_fp4_fwd")
     O, lse = O.view(B, H, Sq, D), lse.view(B * H, Sq)
-    if Sq_v != Sq:
-        O, lse = O[:, :, :Sq_v].contiguous(), lse[:, :Sq_v].contiguous()
+    if Sq_v != Sq or o.head_dim != D:
+        O, lse = O[:, :, :Sq_v, :o.head_dim].contiguous(), lse[:, :Sq_v].contiguous()
     return O, lse
 
 

@@ -681,7 +681,7 @@ using namespace qa;
 // flags: QA_FLAG_CAUSAL = the strict causal mask of the reference's baseline (key < query; row 0 of a head = average over all keys).
 extern "C" int qa_fp4_fwd_ragged(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
                                  const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
-                                 int Sk_valid, int D, int variant, int flags, void* stream) {
+                                 int Sk_valid, int D, int variant, int flags, float sm_scale, void* stream) {
   if (D != 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: D must be 128");
   if (BH <= 0 || Sq <= 0 || Sk <= 0 || Sq % 128 || Sk % 128) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: Sq, Sk must be positive multiples of 128");
   if ((long long)BH * Sq >= (1ll << 31) || (long long)BH * Sk >= (1ll << 31)) return qa_fail(QA_ERR_SHAPE, "qa_fp4_fwd: BH * S must stay below 2^31");
@@ -713,7 +713,8 @@ extern "C" int qa_fp4_fwd_ragged(const void* q4, const void* sfq, const void* sg
   Fp4FwdParams p;
   p.sgq = (const float*)sgq; p.sgk = (const float*)sgk; p.sgv = (const float*)sgv;
   p.O = (__half*)O_fp16; p.lse = (float*)lse_f32; p.Sq = Sq; p.Sk = Sk; p.BH = BH; p.Sk_valid = Sk_valid;
-  p.qk_scale = (float)((1.0 / sqrt((double)D)) * 1.44269504);
+  // sm_scale <= 0: 1 / sqrt(D).  (A head dimension of 64 runs as D = 128 with zero-padded columns and sm_scale = 1/8.)
+  p.qk_scale = sm_scale > 0.f ? sm_scale * 1.44269504f : (float)((1.0 / sqrt((double)D)) * 1.44269504);
   if (variant == 1) {
     using L2 = Fp4Fwd2Smem<3>;
     auto kern2 = fp4_fwd2_kernel<3>;
@@ -737,5 +738,5 @@ extern "C" int qa_fp4_fwd_ragged(const void* q4, const void* sfq, const void* sg
 extern "C" int qa_fp4_fwd(const void* q4, const void* sfq, const void* sgq, const void* k4, const void* sfk, const void* sgk,
                           const void* vt4, const void* sfv, const void* sgv, void* O_fp16, void* lse_f32, int BH, int Sq, int Sk,
                           int D, int variant, int flags, void* stream) {
-  return qa_fp4_fwd_ragged(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, O_fp16, lse_f32, BH, Sq, Sk, Sk, D, variant, flags, stream);
+  return qa_fp4_fwd_ragged(q4, sfq, sgq, k4, sfk, sgk, vt4, sfv, sgv, O_fp16, lse_f32, BH, Sq, Sk, Sk, D, variant, flags, 0.f, stream);
 }

@@ -75,7 +75,7 @@ def test_sage_attention_3_fp4_validates():
     with pytest.raises(TypeError):
         F.sage_attention_3_fp4(q.float(), q.float(), q.float())
     with pytest.raises(ValueError):
-        F.sage_attention_3_fp4(q[..., :64].contiguous(), q[..., :64].contiguous(), q[..., :64].contiguous())
+        F.sage_attention_3_fp4(q[..., :32].contiguous(), q[..., :32].contiguous(), q[..., :32].contiguous())
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -141,3 +141,19 @@ def test_fp4_fwd_ragged_sequence_lengths(S, causal):
     assert torch.isfinite(O.float()).all() and mx < 2e-2 and cos > 0.9995, (mx, cos)
     base = baseline_pytorch_attention(q.float(), k.float(), v.float(), 128, causal)
     assert _stats(O.cpu(), base)[1] > 0.95
+
+
+@pytest.mark.parametrize("shape,causal", [((1, 8, 1024, 64), False), ((2, 3, 300, 64), True)])
+def test_fp4_fwd_head_dim_64(shape, causal):
+    """The reference's D = 64 shapes (configs[0]: B=1 H=8 S=1024 D=64) run with zero-padded head columns and sm_scale = 1/8."""
+    from oracle import fp4_ref
+    from oracle.baseline import baseline_pytorch_attention
+    from quantizedattention_b200 import attention_fp4 as F
+    q, k, v = _inputs(shape, 64 + shape[2], "randn")
+    O = F.sage_attention_3_fp4(q.cuda(), k.cuda(), v.cuda(), causal=causal)
+    torch.cuda.synchronize()
+    assert O.shape == shape
+    Oref, _, _ = fp4_ref.fp4_fwd(q, k, v, step=128, causal=causal)
+    mx, cos = _stats(O.cpu(), Oref)
+    assert mx < 2e-2 and cos > 0.9995, (mx, cos)
+    assert _stats(O.cpu(), baseline_pytorch_attention(q.float(), k.float(), v.float(), 64, causal))[1] > 0.97
