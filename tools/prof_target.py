@@ -48,5 +48,10 @@ elif which == "fp4_fwd":
     o = F4.quantise_fp4(q, k, v)
     for _ in range(3):
         F4.fp4_fwd_prequant(o, variant=int(__import__('os').environ.get('QA_FP4_VARIANT', '0')))
+elif which == "fp4_quant":
+    from quantizedattention_b200 import attention_fp4 as F4
+    q, k, v = [torch.randn(2, 32, 8192, 128, device="cuda", dtype=torch.float16) for _ in range(3)]
+    for _ in range(3):
+        F4.quantise_fp4(q, k, v)
 torch.cuda.synchronize()
 print("ok")
