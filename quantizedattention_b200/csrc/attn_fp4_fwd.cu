@@ -6,14 +6,15 @@
 // were pinned on the hardware by qa_probe_mma_bs (tests/test_probe_gpu.py, profiles/r02_fp4_probe.txt).
 //   S = Q4 K4^T      A = Q tile, B = K tile: rows of D/2 = 64 bytes, 64-byte swizzle, two K = 64 steps; scale factors of Q / K
 //                    arrive as 512-byte atoms by TMA and are copied shared memory -> TMEM by tcgen05.cp.32x128b.warpx4
-//   O += P4 V4       A = P from TMEM (TS mode: 8 e2m1 per 32-bit column, written by the softmax warps over the S columns),
+//   O += P4 V4       A = P from TMEM (TS mode: 8 e2m1 per 32-bit column, written by the exp warps into P's own columns),
 //                    B = V^T tile [D rows, 128 keys] (V is stored transposed: 4-bit operands are K-major only);
 //                    P's scale factors go through a shared-memory atom and tcgen05.cp (they must be replicated over
 //                    the four TMEM lane quadrants, which a thread cannot write)
 // Because the microscales travel with the operands, the fp32 accumulator spans k-tiles (unlike the int8 / fp8 path, whose
 // per-tile P and V scales force a drain every k-tile): O stays resident in TMEM and is rescaled only when a row maximum moves.
-// One CTA = one 128-row query tile of one head.
-// One-CTA variant (variant 1), 20 warps: 0-7 exp (two per 32-row group, alternating tiles: the XU-bound stage), 8-11 running maximum
+// One CTA = one 128-row query tile of one head.  Options: strict causal mask (tile skipping, diagonal masking, row-0 fix-up),
+// ragged key lengths (Sk_valid), sm_scale.
+// Default kernel (variant 0), 20 warps: 0-7 exp (two per 32-row group, alternating tiles: the XU-bound stage), 8-11 running maximum
 // (a tile ahead) and epilogue, 12-15 correction (rescale of O), 16 TMA producer, 17 / 18 MMA issuers (P V / Q K^T), 19 idle.
 // TMEM (512 columns): S[2] at 0 / 128, O at 256, scale factors from 384: Q 8, K 2 x 8, V 2 x 8, P 2 x 8 columns, P[2] at 440 / 456.
 #include "qa_ptx.cuh"
