@@ -315,5 +315,13 @@ def sage_attention_3_int8(q_fp16, k_fp16, v_fp16, causal: bool = False, *, Bq: i
     one-time warning says so).  Bq / Bkv / rounding: per-call tunables (default: the module defaults).
     sage_bwd=True: the backward keeps dO V^T in fp16 (SageAttention3's SageBwd) instead of quantising it as
     the reference does; it costs the fp16 V in the saved context and runs the (slower) block kernel."""
+    if not (torch.is_grad_enabled() and (q_fp16.requires_grad or k_fp16.requires_grad or v_fp16.requires_grad)):
+        # inference: the same kernels without the autograd.Function machinery (its per-call argument binding costs more host time
+        # than the kernels of a small problem take on the GPU)
+        _check_fp16(q_fp16, k_fp16, v_fp16)
+        Bq, Bkv, rounding = _resolve(Bq, Bkv, rounding)
+        if causal:
+            _warn_causal()
+        return _SageInt8Fn.forward(q_fp16, k_fp16, v_fp16, bool(causal), Bq, Bkv, rounding)[0]
     return SageAttention3_Int8_autograd_function.apply(q_fp16, k_fp16, v_fp16, causal, Bq=Bq, Bkv=Bkv, rounding=rounding,
                                                        sage_bwd=sage_bwd)[0]
