@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t jpack_bf16(float a, float b) {
 }
 
 template <int D, int NSPLIT, int BN>
-__global__ void __launch_bounds__(128 * NSPLIT + 192, 1)
+__global__ void __launch_bounds__(NSPLIT == 2 ? 512 : 320, 1)
 jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_tq,
                const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_tk,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_tv, JvpParams p) {
@@ -52,6 +52,9 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   constexpr int kSoftWarps = 4 * NSPLIT;
   constexpr int kProdWarp = kSoftWarps + 4;
   constexpr int kMmaWarp = kSoftWarps + 5;
+  // NSPLIT == 2: 16 warps (the last two idle, so that every warpgroup is complete for setmaxnreg): the softmax warps take 168
+  // registers and hold S and tS of their columns, which frees the S / tS columns for Q K^T of the next tile right after the loads
+  constexpr bool kEarly = (NSPLIT == 2);
   constexpr int kDAtoms = D / 64;
   // TMEM: S [0,BN)  tS [128,128+BN)  O [256,256+D)  AB [256+D,256+2D); P / H (BN/2 columns each) use what is left:
   // D = 64 (BN = 128): [384,448) / [448,512);  D = 128 (BN = 64): [64,96) / [192,224)
@@ -88,6 +91,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   const uint32_t tbase = tmem_base_s;
 
   if (warp < kSoftWarps) {
+    if (kEarly) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");         // 8 x 168 + 8 x 88 registers per lane = 2048
     // =========================== softmax warps ===========================
     const int split = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
@@ -116,6 +120,23 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
       };
       if ((j + 1) * BN > p.Sk_valid) load_s(std::true_type{}); else load_s(std::false_type{});
+      // NSPLIT == 2: tS of this thread's columns also moves to registers now, so that the S / tS columns are free for Q K^T of the
+      // next tile while this tile's exponentials are still being computed (the kernel was a serial chain softmax -> Q K^T ->
+      // softmax with every unit below 40 %, profiles/r02_jvp_ncu.txt)
+      uint32_t treg[kEarly ? NC : 1];
+      if (kEarly) {
+#pragma unroll
+        for (int ch = 0; ch < NC / 32; ++ch) {
+          uint32_t rt[32];
+          tmem_ld32(lane_addr + 128 + c0 + ch * 32, rt);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) treg[(kEarly ? ch * 32 : 0) + (kEarly ? i : 0)] = rt[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty);
+      }
       if (NSPLIT == 2) {
         xmax[ph][split][row] = mx;
         named_bar_sync(1 + (warp & 3), 32 * NSPLIT);   // only the warps that share these 32 rows meet
@@ -137,9 +158,12 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       // of the three accumulating MMAs (TS mode): no swizzled shared-memory stores, no proxy fence
 #pragma unroll
       for (int ch = 0; ch < NC / 32; ++ch) {
-        uint32_t rt[32];
-        tmem_ld32(lane_addr + 128 + c0 + ch * 32, rt);
-        tmem_ld_wait();
+        uint32_t rl[32];
+        if (!kEarly) {
+          tmem_ld32(lane_addr + 128 + c0 + ch * 32, rl);
+          tmem_ld_wait();
+        }
+        const uint32_t* rt = kEarly ? &treg[kEarly ? ch * 32 : 0] : rl;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t wp[8], wh[8];
@@ -165,7 +189,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       l = l * resc + lsum;                                        // :165
       racc = racc * resc + hsum;                                  // :178
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&s_empty); mbar_arrive(&p_full); }
+      if (lane == 0) { if (!kEarly) mbar_arrive(&s_empty); mbar_arrive(&p_full); }
     }
     l_part[split][row] = l;
     r_part[split][row] = racc;
@@ -173,6 +197,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     __syncwarp();
     if (lane == 0) mbar_arrive(&fin_full);
   } else if (warp < kProdWarp) {
+    if (kEarly) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // =========================== correction warpgroup (4 warps, thread = row) ===========================
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
@@ -228,7 +253,10 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
     }
     p.lse[gr] = m_fin[row] + log2f(l);                            // :183
+  } else if (kEarly && warp > kMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");                      // idle warps of the last warpgroup
   } else if (warp == kProdWarp) {
+    if (kEarly) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // =========================== TMA producer ===========================
     if (elect_one()) {
       mbar_expect_tx(&q_full, 2 * L::kTileQ);
@@ -256,6 +284,7 @@ jvp_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
     }
   } else {
+    if (kEarly) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc(1, 1, 1, 0, 0, 128, BN);         // bf16 x bf16 -> f32, K-major
@@ -327,7 +356,7 @@ static int launch_jvp(const void* const* in6, const JvpParams& p, int BH, cudaSt
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
   dim3 grid(p.Sq / 128, BH);
-  kern<<<grid, 128 * NSPLIT + 192, L::total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  kern<<<grid, NSPLIT == 2 ? 512 : 320, L::total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   return qa_check_launch("qa_jvp_fwd");
 }
 
