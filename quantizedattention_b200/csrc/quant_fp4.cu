@@ -7,7 +7,7 @@
 //
 // Two-level scaling (the NVFP4 recipe): per head  sg = amax_head / (6 * 448)  (fp32), per block of 16 elements along the
 // CONTRACTION axis  sf = e4m3_rn(amax_blk / 6 / sg)  in [0, 448],  value = e2m1_rn(x / (sf * sg))  in [-6, 6]; all
-// arithmetic IEEE fp32 (no fast-math), so the codes and scales are bit-exact against oracle/fp4_ref.py.
+// arithmetic IEEE fp32 (no fast-math; quant_e2m1x8 reproduces the IEEE quotient's code without dividing), so the codes and scales are bit-exact against oracle/fp4_ref.py.
 //   Q, K : blocks along D (contraction of Q K^T); codes [B*H*S, D/2] bytes, element 2i in the low nibble of byte i.
 //   V    : blocks along the KEY axis (contraction of P V); codes stored transposed [B*H, D, S/2] because tcgen05
 //          kind::mxf4nvf4 takes 4-bit operands K-major only.
@@ -33,26 +33,49 @@ __device__ __forceinline__ uint32_t pack_e2m1x8(const float (&y)[8]) {
   return w;
 }
 
-// Two-pass fallback (a head with more 128-row tiles than the GPU has SMs cannot be guaranteed resident, so its CTAs must not
-// wait for each other): amax over a head of |x - mean| (fp16 rounding of the difference).  grid = (chunks, BH)
-__global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
-                                                            float* __restrict__ amax, int S, int D, int S_valid) {
-  const int bh = blockIdx.y;
-  const size_t n8 = (size_t)S * D / 8;
-  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)bh * S * D);
-  const int dv = D / 8;
-  float m = 0.f;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (size_t)gridDim.x * 256) {
-    uint4 v = __ldg(base + i);
-    const __half* h = reinterpret_cast<const __half*>(&v);
-    const int d0 = (int)(i % dv) * 8;
-    if ((int)(i / dv) >= S_valid) continue;                      // padding rows of a ragged sequence count as zeros
+// e2m1_rn(fl(v / scale)) for 8 values, without the 8 IEEE divisions: the quotient is bracketed by v * r (1 -+ 2^-20) with r an
+// approximate reciprocal (error of r, of the two products and of the IEEE quotient itself together < 2^-21 relative, so the
+// IEEE quotient lies strictly inside the bracket) and the conversion is monotonic: when both ends give the same eight codes
+// the IEEE quotient gives them too.  Otherwise (a rounding threshold inside a 2^-19-wide window: ~1e-5 of the elements) the
+// block is redone with the divisions.  The result is bit-identical to the division form in every case.
+__device__ __forceinline__ uint32_t quant_e2m1x8(const float* v, float scale) {
+  if (!(scale > 0.f)) return 0u;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(scale));
+  const float rl = __fmul_rn(r, 1.0f - 0x1p-20f), rh = __fmul_rn(r, 1.0f + 0x1p-20f);
+  float a[8], b[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const __half t = mean ? __hsub(h[e], mean[(size_t)bh * D + d0 + e]) : h[e];
-      m = fmaxf(m, fabsf(__half2float(t)));
-    }
+  for (int e = 0; e < 8; ++e) { a[e] = __fmul_rn(v[e], rl); b[e] = __fmul_rn(v[e], rh); }
+  const uint32_t lo = pack_e2m1x8(a), hi = pack_e2m1x8(b);
+  if (lo == hi && scale >= 0x1p-100f) return lo;                  // (a tiny scale would overflow the reciprocal)
+  float y[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) y[e] = __fdiv_rn(v[e], scale);
+  return pack_e2m1x8(y);
+}
+
+// Two-pass fallback (a head with more 128-row tiles than the GPU has SMs cannot be guaranteed resident, so its CTAs must not
+// wait for each other): amax over a head of |x - mean| (fp16 rounding of the difference; abs and max are exact in fp16, so the
+// reduction stays in half2).  grid = (chunks, BH); the grid stride is a multiple of D / 8, so a thread keeps its 8 columns.
+template <int D>
+__global__ void __launch_bounds__(256) fp4_head_amax_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
+                                                            float* __restrict__ amax, int S, int S_valid) {
+  constexpr unsigned DV = D / 8;
+  const int bh = blockIdx.y;
+  const unsigned n8 = (unsigned)S_valid * DV;                    // padding rows of a ragged sequence count as zeros
+  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)bh * S * D);
+  const unsigned i0 = blockIdx.x * 256u + threadIdx.x;
+  uint4 mu = make_uint4(0u, 0u, 0u, 0u);                          // x - (+0) = x
+  if (mean != nullptr) mu = __ldg(reinterpret_cast<const uint4*>(mean + (size_t)bh * D) + (i0 % DV));
+  const __half2* mu2 = reinterpret_cast<const __half2*>(&mu);
+  __half2 m2 = __float2half2_rn(0.f);
+  for (unsigned i = i0; i < n8; i += gridDim.x * 256u) {
+    const uint4 v = __ldg(base + i);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m2 = __hmax2(m2, __habs2(__hsub2(h2[e], mu2[e])));
   }
+  float m = fmaxf(__low2float(m2), __high2float(m2));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __shared__ float red[8];
@@ -95,26 +118,34 @@ __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __ha
                                                                       float* __restrict__ sg_out, int S, int S_valid) {
   constexpr int NB = D / 16;
   __shared__ float red[32];
-  const int tile = blockIdx.x;                                   // 128-row tile over B*H*S: the S / 128 tiles of a head are contiguous
+  const unsigned tile = blockIdx.x, nt = (unsigned)S / 128u;     // 128-row tile over B*H*S: the S / 128 tiles of a head are contiguous
   const int r = threadIdx.x / NB, b = threadIdx.x % NB;
   const size_t row = (size_t)tile * 128 + r;
-  const int bh = (int)(row / S);
+  const int bh = (int)(tile / nt);
+  const int row_in_head = (int)(tile % nt) * 128 + r;
   const uint4* src = reinterpret_cast<const uint4*>(x + row * D + b * 16);
+  const bool valid = row_in_head < S_valid;                      // padding rows stay zero after the smoothing
   float v[16];
-  float am = 0.f;
+  __half2 am2 = __float2half2_rn(0.f);
 #pragma unroll
   for (int hv = 0; hv < 2; ++hv) {
-    uint4 u = __ldg(src + hv);
-    const __half* h = reinterpret_cast<const __half*>(&u);
+    uint4 u = make_uint4(0u, 0u, 0u, 0u), mu = u;
+    if (valid) {
+      u = __ldg(src + hv);
+      if (mean != nullptr) mu = __ldg(reinterpret_cast<const uint4*>(mean + (size_t)bh * D + b * 16) + hv);
+    }
+    const __half2 *h2 = reinterpret_cast<const __half2*>(&u), *mu2 = reinterpret_cast<const __half2*>(&mu);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const __half t = mean ? __hsub(h[e], mean[(size_t)bh * D + b * 16 + hv * 8 + e]) : h[e];
-      v[hv * 8 + e] = ((int)(row % S) < S_valid) ? __half2float(t) : 0.f;      // padding rows stay zero after the smoothing
-      am = fmaxf(am, fabsf(v[hv * 8 + e]));
+    for (int e = 0; e < 4; ++e) {
+      const __half2 t = __hsub2(h2[e], mu2[e]);                   // (x - (+0) = x without a mean)
+      am2 = __hmax2(am2, __habs2(t));                             // abs and max are exact in fp16
+      const float2 f = __half22float2(t);
+      v[hv * 8 + 2 * e] = f.x; v[hv * 8 + 2 * e + 1] = f.y;
     }
   }
+  const float am = fmaxf(__low2float(am2), __high2float(am2));
   const float sg = __fdiv_rn(fp4_head_amax_sync(am, amax, count, bh, (unsigned)(S / 128), red), 2688.0f);
-  if (sg_out != nullptr && row % S == 0 && b == 0) sg_out[bh] = sg;
+  if (sg_out != nullptr && row_in_head == 0 && b == 0) sg_out[bh] = sg;
   uint8_t sc = 0;
   float scale = 0.f;
   if (sg > 0.f) {
@@ -123,12 +154,7 @@ __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __ha
   }
   uint32_t w[2];
 #pragma unroll
-  for (int hv = 0; hv < 2; ++hv) {
-    float y[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = scale > 0.f ? __fdiv_rn(v[hv * 8 + e], scale) : 0.f;
-    w[hv] = pack_e2m1x8(y);
-  }
+  for (int hv = 0; hv < 2; ++hv) w[hv] = quant_e2m1x8(v + hv * 8, scale);
   *reinterpret_cast<uint2*>(codes + row * (D / 2) + b * 8) = make_uint2(w[0], w[1]);
   // scale-factor atoms of this tile: K step = b / 4, block s = b % 4
   sf[(size_t)tile * (NB / 4) * 512 + (b / 4) * 512 + 16 * (r % 32) + 4 * (r / 32) + (b % 4)] = sc;
@@ -169,12 +195,7 @@ __global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restr
     }
     uint32_t w[2];
 #pragma unroll
-    for (int hv = 0; hv < 2; ++hv) {
-      float y[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = scale > 0.f ? __fdiv_rn(x[hv * 8 + e], scale) : 0.f;
-      w[hv] = pack_e2m1x8(y);
-    }
+    for (int hv = 0; hv < 2; ++hv) w[hv] = quant_e2m1x8(x + hv * 8, scale);
     *reinterpret_cast<uint2*>(codes_t + ((size_t)bh * D + d) * (S / 2) + (size_t)j * 64 + b * 8) = make_uint2(w[0], w[1]);
     // rows of the B operand of P V are the D output columns; K step = b / 4 (64 keys), block s = b % 4
     sf[((size_t)bh * (S / 128) + j) * 1024 + (b / 4) * 512 + 16 * (d % 32) + 4 * (d / 32) + (b % 4)] = sc;
@@ -209,7 +230,7 @@ extern "C" int qa_fp4_quant_rows_ragged(const void* x_fp16, const void* mean_fp1
   const bool one_pass = false;
   if (!one_pass) {
     const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
-    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, D, S_valid);
+    fp4_head_amax_kernel<128><<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, S_valid);
   }
   fp4_quant_rows_kernel<128><<<(unsigned)((size_t)BH * S / 128), 1024, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16,
                                                                               (float*)amax_ws, one_pass ? (unsigned*)amax_ws + BH : nullptr,
@@ -235,7 +256,7 @@ extern "C" int qa_fp4_quant_vt(const void* v_fp16, void* amax_ws, void* codes_t,
   const bool one_pass = S / 128 <= fp4_sm_count();
   if (!one_pass) {
     const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
-    fp4_head_amax_kernel<<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, D, S);
+    fp4_head_amax_kernel<128><<<dim3(chunks, BH), 256, 0, st>>>((const __half*)v_fp16, nullptr, (float*)amax_ws, S, S);
   }
   fp4_quant_vt_kernel<128><<<(unsigned)((size_t)BH * (S / 128)), 256, 0, st>>>((const __half*)v_fp16, (float*)amax_ws,
                                                                              one_pass ? (unsigned*)amax_ws + BH : nullptr, (uint8_t*)codes_t,
