@@ -110,16 +110,18 @@ __device__ __forceinline__ float fp4_head_amax_sync(float m, float* amax, unsign
   return red[0];
 }
 
-// Q / K: one thread per 16-element block along D.  CTA = 128 rows x (D/16) blocks = one scale-factor tile.
-template <int D>
-__global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
-                                                                      float* __restrict__ amax, unsigned* __restrict__ count,
-                                                                      uint8_t* __restrict__ codes, uint8_t* __restrict__ sf,
-                                                                      float* __restrict__ sg_out, int S, int S_valid) {
+// Q / K: one thread per 16-element block along D.  CTA = ROWS rows x (D/16) blocks = ROWS / 128 of a scale-factor tile (small
+// CTAs: a 1024-thread CTA holds its slots from its first load to its last store and only two fit on an SM).
+template <int D, int ROWS>
+__global__ void __launch_bounds__(ROWS * D / 16) fp4_quant_rows_kernel(const __half* __restrict__ x, const __half* __restrict__ mean,
+                                                                       float* __restrict__ amax, unsigned* __restrict__ count,
+                                                                       uint8_t* __restrict__ codes, uint8_t* __restrict__ sf,
+                                                                       float* __restrict__ sg_out, int S, int S_valid) {
   constexpr int NB = D / 16;
+  constexpr unsigned PER_TILE = 128 / ROWS;
   __shared__ float red[32];
-  const unsigned tile = blockIdx.x, nt = (unsigned)S / 128u;     // 128-row tile over B*H*S: the S / 128 tiles of a head are contiguous
-  const int r = threadIdx.x / NB, b = threadIdx.x % NB;
+  const unsigned tile = blockIdx.x / PER_TILE, nt = (unsigned)S / 128u;    // 128-row tile over B*H*S: the S / 128 tiles of a head are contiguous
+  const int r = (int)(blockIdx.x % PER_TILE) * ROWS + threadIdx.x / NB, b = threadIdx.x % NB;
   const size_t row = (size_t)tile * 128 + r;
   const int bh = (int)(tile / nt);
   const int row_in_head = (int)(tile % nt) * 128 + r;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(128 * D / 16) fp4_quant_rows_kernel(const __ha
     }
   }
   const float am = fmaxf(__low2float(am2), __high2float(am2));
-  const float sg = __fdiv_rn(fp4_head_amax_sync(am, amax, count, bh, (unsigned)(S / 128), red), 2688.0f);
+  const float sg = __fdiv_rn(fp4_head_amax_sync(am, amax, count, bh, (unsigned)(S / ROWS), red), 2688.0f);
   if (sg_out != nullptr && row_in_head == 0 && b == 0) sg_out[bh] = sg;
   uint8_t sc = 0;
   float scale = 0.f;
@@ -224,17 +226,17 @@ extern "C" int qa_fp4_quant_rows_ragged(const void* x_fp16, const void* mean_fp1
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(amax_ws, 0, (size_t)BH * 8, st);
   if (e != cudaSuccess) return qa_fail(QA_ERR_CUDA, cudaGetErrorString(e));
-  // Two passes for Q / K: with 1024-thread CTAs only two fit on an SM, and CTAs that wait for the rest of their head leave too few
-  // loads in flight (measured: 0.18 ms in one pass vs 0.125 ms in two at B*H = 64, S = 8192); the V kernel (256 threads, tile in
+  // Two passes for Q / K: CTAs that wait for the rest of their head leave too few loads in flight (measured at B*H = 64, S = 8192:
+  // 0.129 ms in one pass vs 0.078 ms in two with 256-thread CTAs; 0.18 vs 0.125 ms with 1024-thread CTAs); the V kernel (tile in
   // shared memory) gains from the single pass (0.105 -> 0.099 ms)
   const bool one_pass = false;
   if (!one_pass) {
     const int chunks = (int)(((size_t)S * D / 8 + 256 * 16 - 1) / (256 * 16));
     fp4_head_amax_kernel<128><<<dim3(chunks, BH), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16, (float*)amax_ws, S, S_valid);
   }
-  fp4_quant_rows_kernel<128><<<(unsigned)((size_t)BH * S / 128), 1024, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16,
-                                                                              (float*)amax_ws, one_pass ? (unsigned*)amax_ws + BH : nullptr,
-                                                                              (uint8_t*)codes, (uint8_t*)sf, (float*)sg_f32, S, S_valid);
+  fp4_quant_rows_kernel<128, 32><<<(unsigned)((size_t)BH * S / 32), 256, 0, st>>>((const __half*)x_fp16, (const __half*)mean_fp16,
+                                                                                  (float*)amax_ws, one_pass ? (unsigned*)amax_ws + BH : nullptr,
+                                                                                  (uint8_t*)codes, (uint8_t*)sf, (float*)sg_f32, S, S_valid);
   return qa_check_launch("qa_fp4_quant_rows");
 }
 
