@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restr
                                                            uint8_t* __restrict__ sf, float* __restrict__ sg_out, int S) {
   __shared__ __half tile[128][D + 8];                            // +8 halves: 16-byte row skew against bank conflicts
   __shared__ float red[32];
+  __shared__ uint2 out_codes[D][9];                              // the tile's codes [d][64 bytes] (+8: bank skew) and its two scale-factor
+  __shared__ __align__(16) uint8_t out_sf[1024];                 // atoms, staged so that they leave in 16-byte pieces
   const int nt = S / 128;
   const int bh = blockIdx.x / nt, j = blockIdx.x % nt;           // 1-D grid, a head's tiles contiguous (see fp4_head_amax_sync)
   const uint4* src = reinterpret_cast<const uint4*>(v + ((size_t)bh * S + (size_t)j * 128) * D);
@@ -198,10 +200,18 @@ __global__ void __launch_bounds__(256) fp4_quant_vt_kernel(const __half* __restr
     uint32_t w[2];
 #pragma unroll
     for (int hv = 0; hv < 2; ++hv) w[hv] = quant_e2m1x8(x + hv * 8, scale);
-    *reinterpret_cast<uint2*>(codes_t + ((size_t)bh * D + d) * (S / 2) + (size_t)j * 64 + b * 8) = make_uint2(w[0], w[1]);
+    out_codes[d][b] = make_uint2(w[0], w[1]);
     // rows of the B operand of P V are the D output columns; K step = b / 4 (64 keys), block s = b % 4
-    sf[((size_t)bh * (S / 128) + j) * 1024 + (b / 4) * 512 + 16 * (d % 32) + 4 * (d / 32) + (b % 4)] = sc;
+    out_sf[(b / 4) * 512 + 16 * (d % 32) + 4 * (d / 32) + (b % 4)] = sc;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D * 4; i += 256) {                // 64 bytes per output column d, 16 per thread
+    const int d = i / 4, c = i % 4;
+    const uint2 lo = out_codes[d][2 * c], hi = out_codes[d][2 * c + 1];
+    *reinterpret_cast<uint4*>(codes_t + ((size_t)bh * D + d) * (S / 2) + (size_t)j * 64 + c * 16) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+  if (threadIdx.x < 64)
+    reinterpret_cast<uint4*>(sf + ((size_t)bh * (S / 128) + j) * 1024)[threadIdx.x] = reinterpret_cast<const uint4*>(out_sf)[threadIdx.x];
 }
 
 }  // namespace qa
