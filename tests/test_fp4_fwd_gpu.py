@@ -22,11 +22,22 @@ def _inputs(shape, seed, kind="randn"):
         q[:, :, :, 16:32] = 0
         v[:, 0] = 0
         k = k * 1e-3
+    if kind == "ties":                       # every quotient x / (sf * sg) exactly on an e2m1 rounding threshold, or one fp16 ulp beside it:
+        t = torch.tensor([6, .25, .75, 1.25, 1.75, 2.5, 3.5, 5, -.25, -.75, -1.25, -1.75, -2.5, -3.5, -5, .5])
+        q = (t / 64).repeat(shape[3] // 16).expand(shape).clone()          # head amax 42 -> sg = 2^-6; block amax 6 / 64 -> sf = 1
+        q[:, :, 0, :16] = t * 7                                            # the block that carries the head amax (sf = 448)
+        v = (t / 64).repeat(shape[2] // 16)[:, None].expand(shape).clone()  # V: blocks of 16 keys
+        v[:, :, :16, 0] = t * 7
+        q, v = q.to(torch.float16), v.to(torch.float16)
+        q.view(torch.int16)[:, :, 1::3] += 1; q.view(torch.int16)[:, :, 2::3] -= 1          # magnitude one ulp up / down
+        v.view(torch.int16)[..., 1::3] += 1; v.view(torch.int16)[..., 2::3] -= 1
+        return [q, q.clone(), v]
     return [t.to(torch.float16) for t in (q, k, v)]
 
 
 @pytest.mark.parametrize("shape,kind", [((1, 2, 256, 128), "randn"), ((2, 2, 512, 128), "offset"), ((1, 2, 384, 128), "zeros"),
                                         ((1, 2, 200, 128), "offset"), ((2, 1, 333, 128), "randn"),      # ragged: zero padding to 256 / 384
+                                        ((1, 2, 256, 128), "ties"),           # the division fallback of the code conversion
                                         ((1, 3, 8192, 128), "offset"),        # V in one pass: the 64 CTAs of a head wait for each other
                                         ((1, 1, 20480, 128), "randn")])       # 160 tiles per head > 148 SMs: V falls back to two passes
 def test_fp4_quantisation_is_bit_exact(shape, kind):
